@@ -1,0 +1,159 @@
+// ============================================================================
+// dge_oracle.hpp -- CPU ORACLE (TEST INFRASTRUCTURE ONLY -- NOT PRODUCT CODE)
+//
+// A dependency-free C++17 restatement of the hot path of
+// RobustFieldAutonomyLab/DRL_graph_exploration (the 2-D landmark-SLAM
+// simulator + exploration-graph builder).  Only `tests/`,
+// `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / --impl reference
+// leg may load the library built from this file.  The product path
+// (drl_graph_exploration_b200/) never links, imports or calls it.
+//
+// PARITY STATUS: **parity unpinned**.  The reference's arithmetic lives in
+// gtsam (fork `emex`, no commit pinned, not vendored under /root/reference)
+// and cannot be built here (gtsam/Eigen/boost absent).  This file restates the
+// published gtsam-4.0 semantics (Pose2 first-order chart, BetweenFactor,
+// BearingRangeFactor, PriorFactor, ISAM2 relinearisation schedule) and follows
+// the reference call sites line by line; the only known-answer data in the
+// reference (data/test_result/40_DQN_GCN.csv) is used as a loose tracking
+// check in tests/test_golden_tracking.py.
+//
+// Every function cites the reference file:line it follows (paths relative to
+// /root/reference).
+// ============================================================================
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <random>
+#include <unordered_map>
+#include <vector>
+
+namespace orc {
+
+// ---------------------------------------------------------------- config ---
+// scripts/envs/exploration_env.ini + pyss2d.py:10-55 (read_*_params) +
+// exploration_env.py:399-407 (reset overrides).  Angles already in radians and
+// already passed through Rot2(x).theta() where the reference setters do that
+// (include/em_exploration/Simulation2D.h:52-57,152).
+struct Config {
+  double env_min_x, env_max_x, env_min_y, env_max_y;   // +-S/2
+  double map_min_x, map_max_x, map_min_y, map_max_y;   // +-(S/2+20)  pyss2d.py:48-55
+  double resolution, sigma0;                           // [Virtual Map]
+  double bearing_noise, range_noise;                   // [Sensor Model]
+  double min_bearing, max_bearing, min_range, max_range;
+  double trans_noise, rot_noise;                       // [Control Model]
+  double sigma_x0, sigma_y0, sigma_theta0;             // [Simulator] prior sigmas
+  double angle_weight, dist_w0, dist_w1;               // [Planner]
+  double max_edge_length, occupancy_threshold;
+  double max_steps;                                    // Environment.max_steps (double, q21)
+  double relin_thresh;                                 // gtsam ISAM2Params default 0.1
+  int32_t relin_skip;                                  // gtsam ISAM2Params default 10
+  int32_t num_landmarks;                               // [Simulator] num
+};
+
+struct Pose { double x, y, th; };
+struct M2 { double a[4]; };   // row-major 2x2
+struct M3 { double a[9]; };   // row-major 3x3
+
+// RNG.h:47-126 : std::mt19937 + uniform_real_distribution<> + normal_distribution<>
+struct Rng {
+  std::mt19937 gen;
+  std::uniform_real_distribution<> uni{0.0, 1.0};
+  std::normal_distribution<> nrm{0.0, 1.0};
+  explicit Rng(uint32_t seed = 0) : gen(seed) {}
+  double uniformReal(double lo, double hi) { return (hi - lo) * uni(gen) + lo; }   // RNG.h:68-71
+  double normal(double m, double s) { return nrm(gen) * s + m; }                    // RNG.h:87-96
+};
+
+struct Meas { int32_t id; double bearing, range; };
+
+// per-step explicit noise record (what the GPU engine replays in parity mode):
+//   [0..3)                      move noise (x, y, theta)              Simulator2D.cpp:167-169
+//   [3 + c*2*Lt + 2*s + {0,1}]  measure() call c (0 = obstacle probe, 1 = real),
+//                               true-landmark scan slot s: (bearing, range) noise
+struct StepNoise { std::vector<double> v; };
+
+struct GraphOut {
+  int32_t n_nodes = 0, key_size = 0, land_size = 0, fro_size = 0, nearest_frontier_node = 0;
+  std::vector<double> features;          // [N,5] f64   exploration_env.py:274
+  std::vector<int64_t> edge_src, edge_dst;  // COO in policy.py:216-227 order
+  std::vector<double> edge_w;
+  std::vector<double> frontier_xy;       // [F,2]
+  std::vector<int32_t> all_frontier_cells; // row*cols+col of every frontier cell (row-major)
+};
+
+class Env {
+ public:
+  Config cfg;
+  // ---- ground truth (Simulator2D) ----
+  int Lt = 0;
+  std::vector<uint32_t> scan_id;           // unordered_map iteration order (q6)
+  std::vector<double> lm_x, lm_y;          // by id
+  Pose true_pose{0, 0, 0};
+  Rng rng_sensor, rng_control, rng_sim;    // q5: same seed, independent streams
+  // ---- SLAM2D ----
+  int T = 0;
+  std::vector<Pose> lin_pose, est_pose;    // ISAM2 linearisation point theta / estimate
+  std::vector<double> delta_pose;          // [T*3]
+  std::vector<double> odom;                // [(T-1)*3] factor k -> k+1
+  std::vector<int32_t> meas_ptr;           // CSR by pose, size T+1
+  std::vector<Meas> meas;
+  std::vector<uint8_t> observed;           // by id
+  std::vector<double> lin_l, est_l, delta_l;   // [Lt*2]
+  Pose prior_pose{0, 0, 0};
+  int update_count = 0;
+  bool use_dense_solver = false;
+  std::vector<M3> pose_cov, pose_info;     // marginals in tangent frame (q13)
+  std::vector<M2> land_cov, land_info;     // by id
+  // ---- VirtualMap ----
+  int rows = 0, cols = 0;
+  std::vector<double> prob;                // [V]
+  std::vector<M2> vinfo;                   // [V]
+  std::vector<int32_t> seen_count;         // integer visibility counts (q8), -1 = landmark cell
+  // ---- python-level state ----
+  int sim_step = 0;                        // pyss2d.py self.step
+  double dist = 0.0;                       // exploration_env.py self.dist
+
+  explicit Env(const Config &c);
+  // pyss2d.py:58-138 ; landmarks generated by Simulator2D::addLandmarks (Simulator2D.cpp:445-465)
+  void init(uint32_t seed, Pose start, StepNoise *rec = nullptr);
+  // same but with explicit landmarks (by id) -- for synthetic tests
+  void init_with_landmarks(uint32_t seed, Pose start, const std::vector<double> &xy, StepNoise *rec = nullptr);
+  // pyss2d.py:171-206 simulate(); returns false if the odom bounds check fired (q3)
+  bool simulate(const double odom_in[3], StepNoise *rec = nullptr);
+  // exploration_env.py:98-105
+  void step(const double odom_in[3], StepNoise *rec = nullptr);
+  bool done() const;                       // exploration_env.py:167-168
+  double explored() const;                 // VirtualMap.cpp:47-59
+  double utility(double distance) const;   // Planner2D.cpp:343-366
+  double landmark_error(double sigma0 = 1.0) const;   // exploration_env.py:170-176
+  double max_traj_uncertainty() const;     // exploration_env.py:190-194
+  int n_observed() const;
+  void graph(GraphOut &g) const;           // exploration_env.py:196-358 + policy.py:211-232
+  // Planner2D.cpp:937-1041 (closed form part)
+  std::vector<Pose> line_plan(double gx, double gy) const;
+  // Planner2D.cpp:1416-1468
+  double simulations_reward(const std::vector<Pose> &actions) const;
+
+  // building blocks exposed for kernel-level parity tests
+  void slam_optimize();                    // SLAM2D.cpp:374-430 (ISAM2 schedule emulation)
+  void update_virtual_map();               // VirtualMap.cpp:61-84,256-271
+  void cov_trace(std::vector<double> &out) const;   // VirtualMap.cpp:153-159
+
+ private:
+  void setup_grid();
+  void add_true_landmarks(const std::vector<double> &xy);
+  void move(const double odom_in[3], StepNoise *rec);
+  void measure(std::vector<Meas> &out, StepNoise *rec, int call);
+  void add_measurements(const std::vector<Meas> &ms);
+  void solve_structured(const std::vector<int> &lidx, int nl);
+  void solve_dense(const std::vector<int> &lidx, int nl);
+};
+
+// stand-alone virtual-map rebuild on explicit inputs (a6+a7), used for the
+// kernel-level parity tests and the C4 roofline sweep.
+void virtual_map_rebuild(const Config &cfg, int T, const double *pose /*[T,3]*/,
+                         const double *info /*[T,9]*/, int L, const double *lm /*[L,2]*/,
+                         int rows, int cols, double *prob /*[V]*/, double *vinfo /*[V,4]*/,
+                         int32_t *seen /*[V] nullable*/);
+
+}  // namespace orc
