@@ -1,0 +1,209 @@
+// C-ABI of libdge.so (see include/dge.h).  Owns the engine's HBM state; every launch goes to
+// the caller's stream so the Python side can order it with torch work or capture it in a
+// CUDA graph.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dge_internal.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const char *what) {
+  cudaError_t ce = cudaGetLastError();
+  g_err = std::string(what) + (ce != cudaSuccess ? std::string(": ") + cudaGetErrorString(ce) : std::string());
+  return code;
+}
+
+extern "C" const char *dge_last_error(void) { return g_err.c_str(); }
+
+namespace {
+struct Alloc {
+  std::vector<void *> ptrs;
+  bool ok = true;
+  template <typename T>
+  T *get(size_t n) {
+    void *p = nullptr;
+    if (!ok) return nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) { ok = false; return nullptr; }
+    cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T));
+    ptrs.push_back(p);
+    return static_cast<T *>(p);
+  }
+};
+struct EngineBox {
+  dge_engine e;
+  Alloc al;
+};
+}  // namespace
+
+extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int device, dge_handle *out) {
+  if (!cfg || !out || n_envs <= 0 || max_poses < 8) return fail(DGE_EINVAL, "dge_create: bad arguments");
+  if (cfg->num_landmarks < 1 || 2 * cfg->num_landmarks > 128) return fail(DGE_EINVAL, "dge_create: num_landmarks must be in [1,64]");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(DGE_ECUDA, "cudaSetDevice");
+  EngineBox *bx = new EngineBox();
+  dge_engine &e = bx->e;
+  memset(&e, 0, sizeof(e));
+  e.cfg = *cfg;
+  e.device = device;
+  DgeDims &d = e.d;
+  d.B = n_envs; d.Tmax = max_poses; d.Lt = cfg->num_landmarks;
+  d.cols = (int)floor((cfg->map_max_x - cfg->map_min_x) / cfg->resolution);   // VirtualMap.cpp:319-322
+  d.rows = (int)floor((cfg->map_max_y - cfg->map_min_y) / cfg->resolution);
+  d.V = d.rows * d.cols;
+  d.Mmax = d.Tmax * d.Lt;
+  d.Fmax = d.Lt + 1;
+  d.Ncap = d.Lt + d.Tmax + d.Fmax;
+  d.Ecap = 2 * (d.Mmax + d.Tmax + d.Fmax + d.Lt);
+  if (dge_slam_smem_bytes(d.Lt) > 227 * 1024) { delete bx; return fail(DGE_EINVAL, "dge_create: too many landmarks for the SLAM kernel's shared memory"); }
+  Alloc &al = bx->al;
+  const size_t B = d.B, T = d.Tmax, L = d.Lt, V = d.V, M = d.Mmax;
+  e.true_pose = al.get<double>(B * 3); e.lm_true = al.get<double>(B * L * 2); e.scan_id = al.get<int32_t>(B * L); e.seed = al.get<uint64_t>(B);
+  e.n_poses = al.get<int32_t>(B); e.sim_step = al.get<int32_t>(B); e.update_count = al.get<int32_t>(B); e.status = al.get<int32_t>(B);
+  e.prior_pose = al.get<double>(B * 3);
+  e.lin_pose = al.get<double>(B * T * 3); e.est_pose = al.get<double>(B * T * 3); e.delta_pose = al.get<double>(B * T * 3); e.odom = al.get<double>(B * T * 3);
+  e.pose_cov = al.get<double>(B * T * 6); e.pose_info = al.get<double>(B * T * 6);
+  e.meas_ptr = al.get<int32_t>(B * (T + 1)); e.meas_id = al.get<int32_t>(B * M); e.meas_pose = al.get<int32_t>(B * M); e.meas_b = al.get<double>(B * M); e.meas_r = al.get<double>(B * M);
+  e.observed = al.get<uint8_t>(B * L); e.lin_l = al.get<double>(B * L * 2); e.est_l = al.get<double>(B * L * 2); e.delta_l = al.get<double>(B * L * 2);
+  e.land_cov = al.get<double>(B * L * 3);
+  e.ws_pose = al.get<double>(B * T * 48); e.ws_meas = al.get<double>(B * M * 5);
+  e.ws_Bt = al.get<double>(B * T * 3 * 2 * L); e.ws_FB = al.get<double>(B * T * 3 * 2 * L); e.ws_midx = al.get<int32_t>(B * T * L);
+  e.vm_prep = al.get<double>(B * T * dge_vmap_prep_width()); e.vm_cbox = al.get<double>(B * (size_t)dge_vmap_nchunk(d.Tmax) * 4);
+  e.seen = al.get<int32_t>(B * V); e.active = al.get<uint8_t>(B);
+  e.prob = al.get<double>(B * V); e.vinfo = al.get<double>(B * V * 3); e.metrics = al.get<double>(B * 8); e.dist = al.get<double>(B);
+  e.done = al.get<uint8_t>(B);
+  e.plan = al.get<double>(B * 6); e.plan_cursor = al.get<int32_t>(B);
+  e.odom_dev_scratch = al.get<double>(B * 3); e.mask_dev_scratch = al.get<uint8_t>(B);
+  e.g_counts = al.get<int32_t>(B * 4); e.g_frontier = al.get<int32_t>(B * d.Fmax); e.g_fassoc = al.get<int32_t>(B * (L + 1)); e.g_sel = al.get<int32_t>(B);
+  if (!al.ok) {
+    for (void *p : al.ptrs) cudaFree(p);
+    delete bx;
+    return fail(DGE_ENOMEM, "dge_create: cudaMalloc failed");
+  }
+  *out = &bx->e;
+  return DGE_OK;
+}
+
+extern "C" int dge_destroy(dge_handle h) {
+  if (!h) return DGE_EINVAL;
+  EngineBox *bx = reinterpret_cast<EngineBox *>(h);   // e is the first member
+  cudaSetDevice(h->device);
+  for (void *p : bx->al.ptrs) cudaFree(p);
+  delete bx;
+  return DGE_OK;
+}
+
+extern "C" int dge_dims(dge_handle h, int32_t *out) {
+  if (!h || !out) return DGE_EINVAL;
+  const DgeDims &d = h->d;
+  out[0] = d.B; out[1] = d.Tmax; out[2] = d.Lt; out[3] = d.rows; out[4] = d.cols; out[5] = d.Mmax; out[6] = d.Ncap; out[7] = d.Ecap;
+  return DGE_OK;
+}
+
+extern "C" int dge_reset(dge_handle h, const uint8_t *mask, const uint64_t *seeds, const double *start, const double *lm,
+                         const int32_t *scan, const double *noise, void *stream) {
+  if (!h) return DGE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = dge_launch_reset(h, mask, seeds, start, lm, scan, noise, st);
+  if (rc) return fail(rc, "dge_reset: k_reset");
+  rc = dge_launch_slam(h, mask, st);   // pyss2d.py:135 self.optimize()
+  if (rc) return fail(rc, "dge_reset: k_slam");
+  return DGE_OK;
+}
+
+extern "C" int dge_move_measure(dge_handle h, const double *odom, const uint8_t *mask, const double *noise, void *stream) {
+  if (!h || !odom) return DGE_EINVAL;
+  const int rc = dge_launch_move_measure(h, odom, mask, noise, 0, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_move_measure") : DGE_OK;
+}
+extern "C" int dge_slam_optimize(dge_handle h, const uint8_t *mask, void *stream) {
+  if (!h) return DGE_EINVAL;
+  const int rc = dge_launch_slam(h, mask, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_slam_optimize") : DGE_OK;
+}
+extern "C" int dge_virtual_map(dge_handle h, const uint8_t *mask, void *stream) {
+  if (!h) return DGE_EINVAL;
+  const int rc = dge_launch_vmap(h, mask, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_virtual_map") : DGE_OK;
+}
+
+extern "C" int dge_step(dge_handle h, const double *odom, const uint8_t *mask, const double *noise, void *stream) {
+  if (!h || !odom) return DGE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = dge_launch_move_measure(h, odom, mask, noise, 0, st);
+  if (rc) return fail(rc, "dge_step: move_measure");
+  if ((rc = dge_launch_slam(h, h->active, st))) return fail(rc, "dge_step: slam");
+  if ((rc = dge_launch_vmap(h, h->active, st))) return fail(rc, "dge_step: vmap");
+  return DGE_OK;
+}
+
+extern "C" int dge_step_queued(dge_handle h, void *stream) {
+  if (!h) return DGE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = dge_launch_move_measure(h, nullptr, nullptr, nullptr, 1, st);
+  if (rc) return fail(rc, "dge_step_queued: move_measure");
+  if ((rc = dge_launch_slam(h, h->active, st))) return fail(rc, "dge_step_queued: slam");
+  if ((rc = dge_launch_vmap(h, h->active, st))) return fail(rc, "dge_step_queued: vmap");
+  return DGE_OK;
+}
+
+extern "C" int dge_step_host(dge_handle h, const double *odom_host, const uint8_t *mask_host, uint8_t *done_host, double *obs_host, void *stream) {
+  if (!h || !odom_host) return DGE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t B = h->d.B;
+  if (cudaMemcpyAsync(h->odom_dev_scratch, odom_host, B * 3 * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host: H2D odom");
+  const uint8_t *mask = nullptr;
+  if (mask_host) {
+    if (cudaMemcpyAsync(h->mask_dev_scratch, mask_host, B, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host: H2D mask");
+    mask = h->mask_dev_scratch;
+  }
+  const int rc = dge_step(h, h->odom_dev_scratch, mask, nullptr, stream);
+  if (rc) return rc;
+  if (done_host && cudaMemcpyAsync(done_host, h->done, B, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host: D2H done");
+  if (obs_host && cudaMemcpyAsync(obs_host, h->prob, B * h->d.V * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host: D2H obs");
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host: sync");
+  return DGE_OK;
+}
+
+extern "C" int dge_virtual_map_rebuild(const dge_config *cfg, int n, int T, const double *pose, const double *cov, int L, const double *lm,
+                                       double *prob, double *vinfo, int32_t *seen, double *ws /* [n*T*12 + n*nchunk*4] */, void *stream) {
+  if (!cfg || n <= 0 || T <= 0 || !pose || !cov || !prob || !vinfo || !ws) return DGE_EINVAL;
+  double *prep = ws, *cbox = ws + (size_t)n * T * dge_vmap_prep_width();
+  const int rc = dge_vmap_standalone(cfg, n, T, pose, cov, L, lm, prob, vinfo, seen, prep, cbox, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_virtual_map_rebuild") : DGE_OK;
+}
+extern "C" int64_t dge_virtual_map_rebuild_ws_doubles(int n, int T) {
+  return (int64_t)n * T * dge_vmap_prep_width() + (int64_t)n * dge_vmap_nchunk(T) * 4;
+}
+
+extern "C" int dge_get_state(dge_handle h, dge_state_view *o) {
+  if (!h || !o) return DGE_EINVAL;
+  o->n_poses = h->n_poses; o->sim_step = h->sim_step; o->update_count = h->update_count;
+  o->true_pose = h->true_pose; o->est_pose = h->est_pose; o->lin_pose = h->lin_pose; o->delta_pose = h->delta_pose;
+  o->pose_cov = h->pose_cov; o->pose_info = h->pose_info; o->odom = h->odom;
+  o->meas_ptr = h->meas_ptr; o->meas_id = h->meas_id; o->meas_bearing = h->meas_b; o->meas_range = h->meas_r;
+  o->lm_true = h->lm_true; o->scan_id = h->scan_id; o->observed = h->observed; o->est_l = h->est_l; o->lin_l = h->lin_l;
+  o->land_cov = h->land_cov; o->prob = h->prob; o->vinfo = h->vinfo; o->seen = h->seen; o->metrics = h->metrics; o->done = h->done; o->status = h->status;
+  o->plan = h->plan; o->plan_cursor = h->plan_cursor;
+  return DGE_OK;
+}
+
+extern "C" int dge_graph(dge_handle h, const uint8_t *mask, const dge_graph_out *out, void *stream) {
+  if (!h || !out || !out->x || !out->edge_index || !out->edge_attr || !out->batch || !out->node_ptr || !out->edge_ptr ||
+      !out->key_size || !out->fro_size || !out->frontier_xy || !out->totals)
+    return fail(DGE_EINVAL, "dge_graph: null output buffer");
+  const int rc = dge_launch_graph(h, mask, out, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_graph") : DGE_OK;
+}
+
+extern "C" int dge_line_plan(dge_handle h, const double *goal, const uint8_t *mask, double *plan, void *stream) {
+  if (!h || !goal || !plan) return DGE_EINVAL;
+  const int rc = dge_launch_line_plan(h, goal, mask, plan, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_line_plan") : DGE_OK;
+}
+
+extern "C" int dge_select_and_plan(dge_handle h, const dge_graph_out *g, const float *q, const uint8_t *mask, int32_t *choice, void *stream) {
+  if (!h || !g || !q) return DGE_EINVAL;
+  const int rc = dge_launch_select_plan(h, g, q, mask, choice, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_select_and_plan") : DGE_OK;
+}

@@ -1,0 +1,172 @@
+// Internal definitions of the batched exploration-graph engine (sm_100a only).
+// HBM layout: structure-of-arrays, env-major; every per-env array is contiguous so the
+// CTA that owns an env streams it with fully coalesced 8-byte loads.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dge.h"
+
+#define DGE_PI 3.14159265358979323846
+
+struct DgeDims {
+  int B, Tmax, Lt, rows, cols, V, Mmax;
+  int Ncap, Ecap, Fmax;   // per-env graph capacities
+};
+
+struct dge_engine {
+  dge_config cfg;
+  DgeDims d;
+  int device;
+  // ---- ground truth / simulator ----
+  double *true_pose;     // [B,3]
+  double *lm_true;       // [B,Lt,2] by id
+  int32_t *scan_id;      // [B,Lt]   scan slot -> id  (std::unordered_map order in the reference, q6)
+  uint64_t *seed;        // [B] Philox key
+  // ---- SLAM state ----
+  int32_t *n_poses, *sim_step, *update_count, *status;
+  double *prior_pose;    // [B,3]
+  double *lin_pose, *est_pose, *delta_pose, *odom;   // [B,Tmax,3]
+  double *pose_cov, *pose_info;                      // [B,Tmax,6]
+  int32_t *meas_ptr;     // [B,Tmax+1]
+  int32_t *meas_id;      // [B,Mmax]
+  int32_t *meas_pose;    // [B,Mmax]  pose index of each measurement factor
+  double *meas_b, *meas_r;
+  uint8_t *observed;     // [B,Lt]
+  double *lin_l, *est_l, *delta_l;   // [B,Lt,2]
+  double *land_cov;      // [B,Lt,3]
+  // ---- solver workspace (L2-resident, streamed once forward, once backward) ----
+  double *ws_pose;       // [B,Tmax,48]: D(6) g(3) U(9) .. | @21 Dinv(6) FU(9) f(3) | @39 P(6) u(3)
+  double *ws_meas;       // [B,Mmax,5]: landmark-landmark block (3) + landmark rhs (2) per measurement
+  double *ws_Bt;         // [B,Tmax,3,2Lt]  border rows (pose-landmark blocks, then eliminated rows)
+  double *ws_FB;         // [B,Tmax,3,2Lt]  Dinv*Bt (becomes W = Lambda_xx^-1 Lambda_xl in the backward pass)
+  int32_t *ws_midx;      // [B,Tmax,Lt]     measurement index+1 of (pose, landmark rank), 0 = none
+  double *vm_prep;       // [B,Tmax,12]     digested poses for the virtual-map kernel
+  double *vm_cbox;       // [B,nchunk,4]    per-32-pose bounding boxes
+  int32_t *seen;         // [B,V]           integer visibility counts (-1 = landmark cell)
+  uint8_t *active;       // [B]             envs that actually stepped in the current dge_step
+  // ---- virtual map ----
+  double *prob;          // [B,V]
+  double *vinfo;         // [B,V,3]
+  double *metrics;       // [B,8]
+  double *dist;          // [B]
+  uint8_t *done;         // [B]
+  // ---- action queues ----
+  double *plan;          // [B,6]
+  int32_t *plan_cursor;  // [B]
+  // ---- scratch for host-buffer calls ----
+  double *odom_dev_scratch;  // [B,3]
+  uint8_t *mask_dev_scratch; // [B]
+  // graph scratch
+  int32_t *g_counts;     // [B,4] N,E,K,F per env
+  int32_t *g_frontier;   // [B,Fmax] frontier cell index
+  int32_t *g_fassoc;     // [B,Lt+1] node -> frontier association (-1 none): slot 0 robot, 1+i landmark rank i
+  int32_t *g_sel;        // [B] position of the env among the selected graphs (-1 = not selected)
+};
+
+// ------------------------------------------------------------- device math ---
+__device__ __forceinline__ double dge_wrap_pi(double t) {
+  double s, c;
+  sincos(t, &s, &c);
+  return atan2(s, c);
+}
+
+struct Pose3 { double x, y, th; };
+
+__device__ __forceinline__ Pose3 dge_compose(const Pose3 &a, const Pose3 &b) {
+  double s, c;
+  sincos(a.th, &s, &c);
+  Pose3 r;
+  r.x = a.x + c * b.x - s * b.y;
+  r.y = a.y + s * b.x + c * b.y;
+  r.th = dge_wrap_pi(a.th + b.th);
+  return r;
+}
+
+// between(p1,p2) and (optionally) H1 = d between / d p1  (gtsam Pose2::between)
+__device__ __forceinline__ Pose3 dge_between(const Pose3 &p1, const Pose3 &p2, double *H1) {
+  double s1, c1, s2, c2;
+  sincos(p1.th, &s1, &c1);
+  sincos(p2.th, &s2, &c2);
+  const double c = c1 * c2 + s1 * s2, s = -s1 * c2 + c1 * s2;
+  const double x = p2.x - p1.x, y = p2.y - p1.y;
+  Pose3 r;
+  r.x = c1 * x + s1 * y;
+  r.y = -s1 * x + c1 * y;
+  r.th = atan2(s, c);
+  if (H1) {
+    H1[0] = -c; H1[1] = -s; H1[2] = -s2 * x + c2 * y;
+    H1[3] = s;  H1[4] = -c; H1[5] = -c2 * x - s2 * y;
+    H1[6] = 0;  H1[7] = 0;  H1[8] = -1;
+  }
+  return r;
+}
+
+// symmetric 3x3 stored as 6: [xx, xy, xt, yy, yt, tt]
+__device__ __forceinline__ void dge_sym3_inv(const double *a, double *o, double *det_out = nullptr) {
+  const double c00 = a[3] * a[5] - a[4] * a[4];
+  const double c01 = a[2] * a[4] - a[1] * a[5];
+  const double c02 = a[1] * a[4] - a[2] * a[3];
+  const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+  const double id = 1.0 / det;
+  o[0] = c00 * id; o[1] = c01 * id; o[2] = c02 * id;
+  o[3] = (a[0] * a[5] - a[2] * a[2]) * id;
+  o[4] = (a[1] * a[2] - a[0] * a[4]) * id;
+  o[5] = (a[0] * a[3] - a[1] * a[1]) * id;
+  if (det_out) *det_out = det;
+}
+
+// full 3x3 (row-major 9) inverse of an SPD matrix via its symmetric part
+__device__ __forceinline__ void dge_spd3_inv9(const double *A, double *O) {
+  const double a[6] = {A[0], 0.5 * (A[1] + A[3]), 0.5 * (A[2] + A[6]), A[4], 0.5 * (A[5] + A[7]), A[8]};
+  double o[6];
+  dge_sym3_inv(a, o);
+  O[0] = o[0]; O[1] = o[1]; O[2] = o[2];
+  O[3] = o[1]; O[4] = o[3]; O[5] = o[4];
+  O[6] = o[2]; O[7] = o[4]; O[8] = o[5];
+}
+
+// ------------------------------------------------------------------ Philox ---
+// Philox4x32-10 counter-based generator (perf-mode noise; the reference's libstdc++
+// mt19937 streams are reproduced on the host side only, see DESIGN.md "RNG").
+__device__ __forceinline__ uint4 dge_philox(uint64_t key, uint64_t ctr_lo, uint64_t ctr_hi) {
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ double dge_u01(uint32_t a, uint32_t b) {  // (0,1), 53 bits
+  const uint64_t v = (((uint64_t)a << 32) | b) >> 11;
+  return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+// two independent N(0,1) from one Philox block (Box-Muller)
+__device__ __forceinline__ void dge_normal2(uint64_t key, uint64_t ctr_lo, uint64_t ctr_hi, double &n0, double &n1) {
+  const uint4 r = dge_philox(key, ctr_lo, ctr_hi);
+  const double u0 = dge_u01(r.x, r.y), u1 = dge_u01(r.z, r.w);
+  const double rad = sqrt(-2.0 * log(u0));
+  double s, c;
+  sincospi(2.0 * u1, &s, &c);
+  n0 = rad * c; n1 = rad * s;
+}
+
+// launch entry points implemented in the .cu files
+int dge_launch_reset(dge_engine *e, const uint8_t *mask, const uint64_t *seeds, const double *start, const double *lm,
+                     const int32_t *scan, const double *noise, cudaStream_t st);
+int dge_launch_move_measure(dge_engine *e, const double *odom, const uint8_t *mask, const double *noise, int from_queue, cudaStream_t st);
+int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st);
+int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st);
+int dge_vmap_standalone(const dge_config *cfg, int n, int T, const double *pose, const double *cov, int L, const double *lm,
+                        double *prob, double *vinfo, int32_t *seen, double *prep_ws, double *cbox_ws, cudaStream_t st);
+int dge_launch_graph(dge_engine *e, const uint8_t *mask, const dge_graph_out *out, cudaStream_t st);
+int dge_launch_line_plan(dge_engine *e, const double *goal, const uint8_t *mask, double *plan_out, cudaStream_t st);
+int dge_launch_select_plan(dge_engine *e, const dge_graph_out *g, const float *q, const uint8_t *mask, int32_t *choice, cudaStream_t st);
+int dge_vmap_nchunk(int T);
+int dge_vmap_prep_width();
+size_t dge_slam_smem_bytes(int Lt);

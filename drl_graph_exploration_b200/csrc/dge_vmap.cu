@@ -1,0 +1,271 @@
+// Virtual-map rebuild ("covariance-propagation kernel"): occupancy probability from integer
+// visibility counts + per-cell 2x2 information by an ordered covariance-intersection fold
+// over the trajectory.  Rows a6+a7(+a8) of SURVEY section 8.
+//
+// Replaces VirtualMap::updateProbability (VirtualMap.cpp:61-84 -> OccupancyMap::update,
+// OccupancyMap.cpp:55-138) and VirtualMap::updateInformation (VirtualMap.cpp:256-316 ->
+// predictVirtualLandmark :213-229, covarianceIntersection2D :364-377), which the reference
+// runs as an O(T*V) scan with Eigen LLT solves per (pose, cell) pair.
+//
+// B200 mapping: the fold is sequential per CELL but independent across cells, so one thread
+// owns one cell (state in registers: 3 information entries, visibility count, flags) and walks
+// the trajectory in order.  A CTA owns a 16x16 tile of cells; warps are 8x4 patches so that the
+// 7x7-cell sensor footprint of a pose keeps most lanes of a warp busy.  Poses are pre-digested
+// once per env (k_vmap_prep: cos/sin, covariance, validity, per-32-pose bounding boxes) and
+// staged through shared memory only for the chunks whose bounding box touches the tile.
+// The arithmetic is the closed form of the reference's expression
+//   Hl^-1 (R + Hx Sigma Hx^T) Hl^-T = Rot (M^-1 R M^-T + A Sigma A^T) Rot^T
+// (Hl = M Rot^T, Hx = M A), evaluated in fp64.
+#include "dge_internal.cuh"
+
+namespace {
+
+constexpr int TILE = 16;           // cells per tile side
+constexpr int VCH = 32;            // poses per chunk
+constexpr int PREP_W = 12;         // doubles per digested pose: x y c s Sxx Sxy Sxt Syy Syt Stt valid pad
+
+struct VmapCfg {
+  double map_min_x, map_min_y, res;
+  double max_range, min_range, max_bearing, min_bearing;
+  double rb, rr;                   // sigma_b^2, sigma_r^2
+  double i0;                       // 1/sigma0^2
+  double ptab[6];                  // probability for n_seen = 0..4(+) and for a landmark cell (host-evaluated, q8)
+  double wedge_tan;                // tan of the half-width of the rear blind wedge (with guard)
+  int fov_wide;
+  int rows, cols;
+};
+
+// ------------------------------------------------------------------ prep ---
+__global__ void __launch_bounds__(128) k_vmap_prep(VmapCfg c, int Tstride, const int32_t *n_poses, int Tfixed,
+                                                   const double *pose /*[n,Tstride,3]*/, const double *cov /*[n,Tstride,6]*/,
+                                                   const double *info /*nullable [n,Tstride,6]*/, double *prep /*[n,Tstride,PREP_W]*/,
+                                                   double *cbox /*[n,nchunk_max,4]*/, int nchunk_max, const uint8_t *mask) {
+  const int b = blockIdx.x;
+  if (mask && !mask[b]) return;
+  const int T = n_poses ? n_poses[b] : Tfixed;
+  const double *ps = pose + (size_t)b * Tstride * 3, *cv = cov + (size_t)b * Tstride * 6;
+  double *pr = prep + (size_t)b * Tstride * PREP_W;
+  for (int k = threadIdx.x; k < T; k += blockDim.x) {
+    double s, co;
+    sincos(ps[3 * k + 2], &s, &co);
+    double *o = pr + (size_t)k * PREP_W;
+    o[0] = ps[3 * k]; o[1] = ps[3 * k + 1]; o[2] = co; o[3] = s;
+    double S[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { S[i] = cv[6 * k + i]; o[4 + i] = S[i]; }
+    double det_info;
+    if (info) {
+      const double *a = info + ((size_t)b * Tstride + k) * 6;
+      det_info = a[0] * (a[3] * a[5] - a[4] * a[4]) - a[1] * (a[1] * a[5] - a[4] * a[2]) + a[2] * (a[1] * a[4] - a[3] * a[2]);
+    } else {
+      const double dc = S[0] * (S[3] * S[5] - S[4] * S[4]) - S[1] * (S[1] * S[5] - S[4] * S[2]) + S[2] * (S[1] * S[4] - S[3] * S[2]);
+      det_info = 1.0 / dc;
+    }
+    o[10] = (det_info < 1e-10) ? 0.0 : 1.0;   // VirtualMap.cpp:293
+    o[11] = 0.0;
+  }
+  __syncthreads();
+  // per-chunk bounding boxes (pose positions inflated by the sensor range)
+  const int nch = (T + VCH - 1) / VCH;
+  for (int ch = threadIdx.x; ch < nch; ch += blockDim.x) {
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int k = ch * VCH; k < min(T, (ch + 1) * VCH); ++k) {
+      const double x = pr[(size_t)k * PREP_W], y = pr[(size_t)k * PREP_W + 1];
+      x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y);
+    }
+    double *o = cbox + ((size_t)b * nchunk_max + ch) * 4;
+    o[0] = x0 - c.max_range - 0.01; o[1] = x1 + c.max_range + 0.01; o[2] = y0 - c.max_range - 0.01; o[3] = y1 + c.max_range + 0.01;
+  }
+}
+
+// ----------------------------------------------------------------- cells ---
+__global__ void __launch_bounds__(TILE * TILE) k_vmap_cells(VmapCfg c, int Tstride, const int32_t *n_poses, int Tfixed,
+                                                            const double *prep, const double *cbox, int nchunk_max,
+                                                            const double *lm /*[n,Lstride,2]*/, const uint8_t *lm_obs /*nullable*/,
+                                                            int Lstride, int Lfixed, double *prob /*[n,V]*/, double *vinfo /*[n,V,3]*/,
+                                                            int32_t *seen_out /*nullable [n,V]*/, const uint8_t *mask) {
+  const int b = blockIdx.y;
+  if (mask && !mask[b]) return;
+  const int T = n_poses ? n_poses[b] : Tfixed;
+  const int tiles_x = (c.cols + TILE - 1) / TILE;
+  const int tile_r = (blockIdx.x / tiles_x) * TILE, tile_c = (blockIdx.x % tiles_x) * TILE;
+  // warp = 8x4 patch; 8 warps tile the 16x16 block as 2 (x) by 4 (y)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = tile_c + (warp & 1) * 8 + (lane & 7);
+  const int row = tile_r + (warp >> 1) * 4 + (lane >> 3);
+  const bool valid_cell = row < c.rows && col < c.cols;
+  const double cx = c.map_min_x + c.res * (col + 0.5), cy = c.map_min_y + c.res * (row + 0.5);
+  // tile bounds (cell centres)
+  const double tx0 = c.map_min_x + c.res * (tile_c + 0.5), tx1 = c.map_min_x + c.res * (min(tile_c + TILE, c.cols) - 0.5);
+  const double ty0 = c.map_min_y + c.res * (tile_r + 0.5), ty1 = c.map_min_y + c.res * (min(tile_r + TILE, c.rows) - 0.5);
+
+  __shared__ double sp[VCH * PREP_W];
+  __shared__ int s_lmcell;
+
+  // landmark cells (OccupancyMap.cpp:126-131): a cell holding a landmark estimate saturates "occupied"
+  bool is_lm = false;
+  {
+    const double *l = lm + (size_t)b * Lstride * 2;
+    for (int j = 0; j < Lfixed; ++j) {
+      if (lm_obs && !lm_obs[(size_t)b * Lstride + j]) continue;
+      const int lr = (int)floor((l[2 * j + 1] - c.map_min_y) / c.res), lc = (int)floor((l[2 * j] - c.map_min_x) / c.res);
+      if (lr == row && lc == col) is_lm = true;
+    }
+  }
+  (void)s_lmcell;
+
+  double ixx = c.i0, ixy = 0.0, iyy = c.i0;
+  bool updated = false;
+  int cnt = 0;
+  const int nch = (T + VCH - 1) / VCH;
+  const double rmax_c2 = (c.max_range + 0.01) * (c.max_range + 0.01);
+  for (int ch = 0; ch < nch; ++ch) {
+    const double *bx = cbox + ((size_t)b * nchunk_max + ch) * 4;
+    if (bx[0] > tx1 || bx[1] < tx0 || bx[2] > ty1 || bx[3] < ty0) continue;   // uniform across the CTA
+    const int k0 = ch * VCH, kc = min(VCH, T - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kc * PREP_W; i += TILE * TILE) sp[i] = prep[((size_t)b * Tstride + k0) * PREP_W + i];
+    __syncthreads();
+    if (!valid_cell) continue;
+    for (int kk = 0; kk < kc; ++kk) {
+      const double *p = sp + kk * PREP_W;
+      const double dx = cx - p[0], dy = cy - p[1];
+      const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      if (d2 >= rmax_c2) continue;
+      const double r = __dsqrt_rn(d2);
+      if (!(r < c.max_range)) continue;                       // Distance.cpp:86 / checkWithoutMinRange
+      const double co = p[2], si = p[3];
+      const double qx = co * dx + si * dy, qy = -si * dx + co * dy;
+      // field-of-view gate min_b < atan2(qy,qx) < max_b  (Simulator2D.cpp:100-111)
+      bool in_fov;
+      if (c.fov_wide && (qx > 0.0 || fabs(qy) > -qx * c.wedge_tan)) in_fov = true;
+      else { const double bb = atan2(qy, qx); in_fov = bb < c.max_bearing && bb > c.min_bearing; }
+      if (!in_fov) continue;
+      ++cnt;                                                  // occupancy visibility count (q8)
+      if (!(r > c.min_range) || p[10] == 0.0) continue;       // full check (q10) ; det(info) gate
+      // body-frame covariance of the predicted virtual landmark
+      const double r2 = r * r;
+      const double sr = c.rr / r2;
+      const double Sxx = p[4], Sxy = p[5], Sxt = p[6], Syy = p[7], Syt = p[8], Stt = p[9];
+      const double cb00 = qy * qy * c.rb + qx * qx * sr + Sxx - 2.0 * qy * Sxt + qy * qy * Stt;
+      const double cb01 = qx * qy * (sr - c.rb) + Sxy - qy * Syt + qx * Sxt - qx * qy * Stt;
+      const double cb11 = qx * qx * c.rb + qy * qy * sr + Syy + 2.0 * qx * Syt + qx * qx * Stt;
+      const double idet = 1.0 / (cb00 * cb11 - cb01 * cb01);
+      const double lb00 = cb11 * idet, lb01 = -cb01 * idet, lb11 = cb00 * idet;   // body-frame information
+      // rotate to the map frame
+      const double cc = co * co, ss = si * si, cs = co * si;
+      const double nxx = cc * lb00 - 2.0 * cs * lb01 + ss * lb11;
+      const double nxy = cs * (lb00 - lb11) + (cc - ss) * lb01;
+      const double nyy = ss * lb00 + 2.0 * cs * lb01 + cc * lb11;
+      if (!updated) { ixx = nxx; ixy = nxy; iyy = nyy; updated = true; }
+      else {  // covariance intersection on information matrices (VirtualMap.cpp:364-377, q11)
+        const double a = ixx * iyy - ixy * ixy, bdet = nxx * nyy - nxy * nxy;
+        const double cm = iyy * nxx - 2.0 * ixy * nxy + ixx * nyy;   // det(m1) * tr(m1^-1 m2)
+        const double d = a + bdet - cm;
+        double w = 0.5 * (2.0 * bdet - cm) / d;
+        if ((w < 0 && d < 0) || (w > 1 && d > 0)) w = 0.0;
+        else if ((w < 0 && d > 0) || (w > 1 && d < 0)) w = 1.0;
+        ixx = w * ixx + (1.0 - w) * nxx; ixy = w * ixy + (1.0 - w) * nxy; iyy = w * iyy + (1.0 - w) * nyy;
+      }
+    }
+  }
+  if (!valid_cell) return;
+  const size_t cell = (size_t)b * c.rows * c.cols + (size_t)row * c.cols + col;
+  prob[cell] = is_lm ? c.ptab[5] : c.ptab[min(cnt, 4)];
+  vinfo[cell * 3] = ixx; vinfo[cell * 3 + 1] = ixy; vinfo[cell * 3 + 2] = iyy;
+  if (seen_out) seen_out[cell] = is_lm ? -1 : cnt;
+}
+
+// --------------------------------------------------------------- metrics ---
+// explored fraction (VirtualMap.cpp:47-59), utility(0) = sum trace(cov) (Planner2D.cpp:343-366),
+// known-cell count, done flag (exploration_env.py:167-168).
+__global__ void __launch_bounds__(256) k_vmap_metrics(dge_config cfg, DgeDims d, const double *prob, const double *vinfo,
+                                                      const int32_t *sim_step, const int32_t *status, const double *dist,
+                                                      double *metrics, uint8_t *done, const uint8_t *mask) {
+  const int b = blockIdx.x;
+  if (mask && !mask[b]) return;
+  const double *p = prob + (size_t)b * d.V, *vi = vinfo + (size_t)b * d.V * 3;
+  const int extg = 20;
+  int n_exp = 0, n_known = 0;
+  double tr = 0.0;
+  for (int i = threadIdx.x; i < d.V; i += 256) {
+    const double x = (i % d.cols + 0.5) * cfg.resolution + cfg.map_min_x, y = (i / d.cols + 0.5) * cfg.resolution + cfg.map_min_y;
+    const double pv = p[i];
+    if ((pv < 0.49 || pv > 0.6) && cfg.map_min_x + extg <= x && x <= cfg.map_max_x - extg && cfg.map_min_y + extg <= y && y <= cfg.map_max_y - extg) ++n_exp;
+    if (pv < cfg.occupancy_threshold) ++n_known;
+    const double a = vi[3 * i], bb = vi[3 * i + 1], c = vi[3 * i + 2];
+    tr += (a + c) / (a * c - bb * bb);
+  }
+  __shared__ double s_tr[256];
+  __shared__ int s_e[256], s_k[256];
+  s_tr[threadIdx.x] = tr; s_e[threadIdx.x] = n_exp; s_k[threadIdx.x] = n_known;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {   // fixed-order tree => run-to-run deterministic
+    if (threadIdx.x < o) { s_tr[threadIdx.x] += s_tr[threadIdx.x + o]; s_e[threadIdx.x] += s_e[threadIdx.x + o]; s_k[threadIdx.x] += s_k[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int ce = (d.rows - extg * 2 / (int)cfg.resolution) * (d.cols - extg * 2 / (int)cfg.resolution);
+    const double explored = (double)s_e[0] / ce;
+    const double pk = (double)s_k[0] / d.V;
+    metrics[8 * b + 0] = explored;
+    metrics[8 * b + 1] = s_tr[0];                 // utility at distance 0
+    metrics[8 * b + 2] = cfg.dist_w0 - (cfg.dist_w0 - cfg.dist_w1) * pk;   // distance weight
+    metrics[8 * b + 3] = (double)s_k[0];
+    metrics[8 * b + 6] = dist[b];
+    done[b] = (sim_step[b] > cfg.max_steps || explored > 0.85 || status[b] == DGE_ECAP) ? 1 : 0;
+  }
+}
+
+VmapCfg make_cfg(const dge_config &g, int rows, int cols) {
+  VmapCfg c;
+  c.map_min_x = g.map_min_x; c.map_min_y = g.map_min_y; c.res = g.resolution;
+  c.max_range = g.max_range; c.min_range = g.min_range; c.max_bearing = g.max_bearing; c.min_bearing = g.min_bearing;
+  c.rb = g.bearing_noise * g.bearing_noise; c.rr = g.range_noise * g.range_noise;
+  c.i0 = 1.0 / (g.sigma0 * g.sigma0);
+  // OccupancyMap.h:10-19 evaluated on the host with libm, by repeated addition + clamping exactly
+  // like OccupancyMap.cpp:55-62 (incl. MAX_LOGODDS = LOGODDS2PROB(0.95), q7)
+  const double LF = log(0.3 / (1.0 - 0.3)), LO = log(0.7 / (1.0 - 0.7)), MINL = log(0.05 / (1.0 - 0.05));
+  const double MAXL = exp(0.95) / (1.0 + exp(0.95));
+  double l = log(0.5 / (1.0 - 0.5));
+  for (int n = 0; n <= 4; ++n) {
+    c.ptab[n] = exp(l) / (1.0 + exp(l));
+    l = fmin(MAXL, fmax(MINL, l + LF));
+  }
+  const double lo = fmin(MAXL, fmax(MINL, log(0.5 / (1.0 - 0.5)) + LO));
+  c.ptab[5] = exp(lo) / (1.0 + exp(lo));
+  c.fov_wide = (g.max_bearing >= DGE_PI / 2 && g.min_bearing <= -DGE_PI / 2) ? 1 : 0;
+  const double half = fmax(DGE_PI - g.max_bearing, DGE_PI + g.min_bearing);
+  c.wedge_tan = tan(half) * (1.0 + 1e-6) + 1e-12;
+  c.rows = rows; c.cols = cols;
+  return c;
+}
+
+}  // namespace
+
+int dge_vmap_nchunk(int T) { return (T + VCH - 1) / VCH; }
+int dge_vmap_prep_width() { return PREP_W; }
+
+int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
+  const VmapCfg c = make_cfg(e->cfg, e->d.rows, e->d.cols);
+  const int nchm = dge_vmap_nchunk(e->d.Tmax);
+  k_vmap_prep<<<e->d.B, 128, 0, st>>>(c, e->d.Tmax, e->n_poses, 0, e->est_pose, e->pose_cov, e->pose_info, e->vm_prep, e->vm_cbox, nchm, mask);
+  const int tiles = ((e->d.cols + TILE - 1) / TILE) * ((e->d.rows + TILE - 1) / TILE);
+  k_vmap_cells<<<dim3(tiles, e->d.B), TILE * TILE, 0, st>>>(c, e->d.Tmax, e->n_poses, 0, e->vm_prep, e->vm_cbox, nchm, e->est_l, e->observed,
+                                                             e->d.Lt, e->d.Lt, e->prob, e->vinfo, e->seen, mask);
+  k_vmap_metrics<<<e->d.B, 256, 0, st>>>(e->cfg, e->d, e->prob, e->vinfo, e->sim_step, e->status, e->dist, e->metrics, e->done, mask);
+  return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
+}
+
+// stand-alone rebuild on caller-provided belief states (C4 roofline sweep, kernel-level parity)
+int dge_vmap_standalone(const dge_config *cfg, int n, int T, const double *pose, const double *cov, int L, const double *lm,
+                        double *prob, double *vinfo, int32_t *seen, double *prep_ws, double *cbox_ws, cudaStream_t st) {
+  const int cols = (int)floor((cfg->map_max_x - cfg->map_min_x) / cfg->resolution);
+  const int rows = (int)floor((cfg->map_max_y - cfg->map_min_y) / cfg->resolution);
+  const VmapCfg c = make_cfg(*cfg, rows, cols);
+  const int nchm = dge_vmap_nchunk(T);
+  k_vmap_prep<<<n, 128, 0, st>>>(c, T, nullptr, T, pose, cov, nullptr, prep_ws, cbox_ws, nchm, nullptr);
+  const int tiles = ((cols + TILE - 1) / TILE) * ((rows + TILE - 1) / TILE);
+  k_vmap_cells<<<dim3(tiles, n), TILE * TILE, 0, st>>>(c, T, nullptr, T, prep_ws, cbox_ws, nchm, lm, nullptr, L, L, prob, vinfo, seen, nullptr);
+  return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
+}

@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's ``scripts/envs/exploration_env.py`` on the CUDA engine.
+
+* ``VecExplorationEnv`` -- B environments stepped together (the B200-native entry point):
+  device-resident graph batches for the GNN, device-side policy read-out / line planning, and a
+  host-buffer API (``step_host`` / ``graph_host``) that mirrors what ``policy.py`` / ``test.py`` do
+  per env (NumPy in, NumPy out).
+* ``ExplorationEnv(map_size, env_index, test)`` -- the reference's single-env class
+  (exploration_env.py:22-422) as a B = 1 view: ``reset / step / graph_matrix / frontier /
+  actions_all_goals / status / done / get_landmark_error / max_uncertainty_of_trajectory ...``
+  with the reference's return shapes (``step`` returns the 3-tuple ``(obs, done, {})``, q17).
+
+All simulation, SLAM, virtual-map and graph arithmetic happens in ``libdge.so``; this file only
+moves buffers and reshapes results.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ..config import EnvConfig, start_pose_for_seed
+from ..data import Data
+from ..engine import DgeError, Engine, GraphOut, _check, _ptr, _stream_ptr
+
+RESET_ODOM = (1.0, 1.0, math.pi / 2.0)   # exploration_env.py:411-414: 4 x simulate((1, 1, pi/2))
+
+
+class Pose2:
+    """Duck-type of ss2d.Pose2 for the actions handed to ``step`` (x, y, theta)."""
+    __slots__ = ("x", "y", "theta")
+
+    def __init__(self, x=0.0, y=0.0, theta=0.0):
+        self.x, self.y, self.theta = float(x), float(y), float(theta)
+
+    def __repr__(self):
+        return f"Pose2({self.x:.6g}, {self.y:.6g}, {self.theta:.6g})"
+
+
+def expand_plan(plan_row, max_edge_length: float):
+    """(n_rot_pi, sign, rot_rem, n_fwd, fwd_rem, n_actions) -> list[Pose2]  (Planner2D.cpp:982-1038)"""
+    nrot, sign, rrem, nfwd, frem, _ = [float(v) for v in plan_row]
+    acts = [Pose2(0, 0, sign * math.pi) for _ in range(int(nrot))]
+    acts.append(Pose2(0, 0, sign * rrem))
+    acts += [Pose2(max_edge_length, 0, 0) for _ in range(int(nfwd))]
+    acts.append(Pose2(frem, 0, 0))
+    return acts
+
+
+class GraphBatch:
+    """Device-resident batched exploration graph (PyG DataLoader layout) + per-graph bookkeeping."""
+
+    def __init__(self, eng: Engine, n_graph_cap: int):
+        dev = eng.device
+        self.node_cap = n_graph_cap * eng.node_cap_env
+        self.edge_cap = n_graph_cap * eng.edge_cap_env
+        self.x = torch.empty(self.node_cap, 5, dtype=torch.float32, device=dev)
+        self.edge_index = torch.empty(2, self.edge_cap, dtype=torch.int64, device=dev)
+        self.edge_attr = torch.empty(self.edge_cap, dtype=torch.float32, device=dev)
+        self.batch = torch.empty(self.node_cap, dtype=torch.int64, device=dev)
+        self.node_ptr = torch.zeros(eng.B + 1, dtype=torch.int32, device=dev)
+        self.edge_ptr = torch.zeros(eng.B + 1, dtype=torch.int32, device=dev)
+        self.key_size = torch.zeros(eng.B, dtype=torch.int32, device=dev)
+        self.fro_size = torch.zeros(eng.B, dtype=torch.int32, device=dev)
+        self.frontier_xy = torch.zeros(eng.B, eng.Lt + 1, 2, dtype=torch.float64, device=dev)
+        self.totals = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.totals_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.c = GraphOut(self.x.data_ptr(), self.edge_index.data_ptr(), self.edge_attr.data_ptr(), self.batch.data_ptr(),
+                          self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.key_size.data_ptr(), self.fro_size.data_ptr(),
+                          self.frontier_xy.data_ptr(), self.totals.data_ptr(), self.node_cap, self.edge_cap)
+        self.n_graphs = self.n_nodes = self.n_edges = 0
+
+    def sync_sizes(self):
+        """One small D2H (pinned) so the host can size the dense GEMMs of the GNN."""
+        self.totals_host.copy_(self.totals, non_blocking=True)
+        torch.cuda.current_stream(self.x.device).synchronize()
+        g, n, e, ovf = self.totals_host.tolist()
+        if ovf:
+            raise DgeError("graph batch capacity exceeded")
+        self.n_graphs, self.n_nodes, self.n_edges = g, n, e
+        return g, n, e
+
+    def data(self) -> Data:
+        """``Data(x, edge_index, edge_attr)`` views of the valid prefix (no copies)."""
+        d = Data(self.x[:self.n_nodes], self.edge_index[:, :self.n_edges], self.edge_attr[:self.n_edges], self.batch[:self.n_nodes])
+        d.num_graphs = self.n_graphs
+        return d
+
+
+class VecExplorationEnv:
+    """B exploration environments resident on one B200."""
+
+    def __init__(self, n_envs: int, map_size: int = 40, cfg: Optional[EnvConfig] = None, max_poses: int = 512, device=0,
+                 seed0: int = 0, test: bool = True):
+        self.cfg = cfg or EnvConfig(map_size=map_size)
+        self.map_size = self.cfg.map_size
+        self.eng = Engine(self.cfg, n_envs, max_poses=max_poses, device=device)
+        self.B, self.device = n_envs, self.eng.device
+        self.test = test
+        self.graph = GraphBatch(self.eng, n_envs)
+        self._seeds = torch.arange(seed0, seed0 + n_envs, dtype=torch.int64, device=self.device)
+        self._next_seed = seed0 + n_envs
+        self._reset_odom = torch.tensor([RESET_ODOM] * n_envs, dtype=torch.float64, device=self.device)
+        self._choice = torch.zeros(n_envs, dtype=torch.int32, device=self.device)
+        self._ones = torch.ones(n_envs, dtype=torch.uint8, device=self.device)
+        self.episodes_done = 0
+
+    # ---------------------------------------------------------------- reset ---
+    def reset(self, mask: Optional[torch.Tensor] = None, seeds: Optional[torch.Tensor] = None, reference_worlds: bool = False):
+        """exploration_env.py:389-422.  ``reference_worlds`` reproduces the reference's start poses
+        (legacy NumPy RNG, pyss2d.py:88-95) on the host; landmarks/noise stay Philox (device)."""
+        eng = self.eng
+        if seeds is not None:
+            self._seeds = seeds.to(self.device, torch.int64).contiguous()
+        start = None
+        if reference_worlds:
+            sp = np.array([start_pose_for_seed(int(s), self.map_size, self.cfg.ext) for s in self._seeds.tolist()], dtype=np.float64)
+            start = torch.as_tensor(sp, device=self.device)
+        eng.reset(self._seeds, mask=mask, start=start)
+        for _ in range(4):
+            eng.step(self._reset_odom, mask=mask)
+        return eng.state["prob"]
+
+    def reset_done(self):
+        """Re-seed and reset the envs whose episode ended (device-side mask, no host sync)."""
+        done = self.eng.state["done"].clone()
+        self._seeds = torch.where(done.bool(), self._seeds + self.B, self._seeds)
+        self.reset(mask=done)
+        return done
+
+    # ----------------------------------------------------------------- step ---
+    def step(self, odom: torch.Tensor, mask: Optional[torch.Tensor] = None):
+        self.eng.step(odom, mask=mask)
+        return self.eng.state["prob"], self.eng.state["done"]
+
+    def step_queued(self):
+        self.eng.step_queued()
+        return self.eng.state["done"]
+
+    def needs_decision(self) -> torch.Tensor:
+        """[B] u8: envs whose action queue is empty (and are not done)."""
+        st = self.eng.state
+        return ((st["plan_cursor"] >= st["plan"][:, 5].to(torch.int32)) & (st["done"] == 0)).to(torch.uint8)
+
+    # ---------------------------------------------------------------- graph ---
+    def build_graph(self, mask: Optional[torch.Tensor] = None) -> GraphBatch:
+        eng = self.eng
+        _check(eng._L.dge_graph(eng._h, _ptr(mask), ctypes.byref(self.graph.c), _stream_ptr(self.device)), "dge_graph")
+        return self.graph
+
+    def select_and_plan(self, q: torch.Tensor, mask: Optional[torch.Tensor] = None):
+        """arg-max over each graph's frontier nodes + line plan into the env queues (device-side)."""
+        eng = self.eng
+        q = q.contiguous().view(-1).float()
+        _check(eng._L.dge_select_and_plan(eng._h, ctypes.byref(self.graph.c), _ptr(q), _ptr(mask), _ptr(self._choice),
+                                          _stream_ptr(self.device)), "dge_select_and_plan")
+        return self._choice
+
+    def line_plan(self, goals: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        eng = self.eng
+        out = torch.zeros(self.B, 6, dtype=torch.float64, device=self.device)
+        _check(eng._L.dge_line_plan(eng._h, _ptr(goals.contiguous()), _ptr(mask), _ptr(out), _stream_ptr(self.device)), "dge_line_plan")
+        return out
+
+    # ------------------------------------------------------------- host API ---
+    def step_host(self, odom_host: np.ndarray, done_host: np.ndarray, obs_host: Optional[np.ndarray] = None):
+        self.eng.step_host(odom_host, done_host, obs_host)
+
+    def graph_host(self, mask: Optional[torch.Tensor] = None):
+        """Per-env NumPy graphs like ``graph_matrix`` + ``data_process`` produce them (D2H copies)."""
+        g = self.build_graph(mask)
+        ng, n, e = g.sync_sizes()
+        x = g.x[:n].cpu().numpy(); ei = g.edge_index[:, :e].cpu().numpy(); ea = g.edge_attr[:e].cpu().numpy()
+        nptr = g.node_ptr[:ng + 1].cpu().numpy(); eptr = g.edge_ptr[:ng + 1].cpu().numpy()
+        ks = g.key_size[:ng].cpu().numpy(); fs = g.fro_size[:ng].cpu().numpy()
+        out = []
+        for i in range(ng):
+            sl, se = slice(nptr[i], nptr[i + 1]), slice(eptr[i], eptr[i + 1])
+            out.append(dict(x=x[sl], edge_index=ei[:, se] - nptr[i], edge_attr=ea[se], key_size=int(ks[i]), fro_size=int(fs[i])))
+        return out
+
+    def metrics(self):
+        m = self.eng.state["metrics"]
+        return dict(explored=m[:, 0], utility0=m[:, 1], landmark_error=m[:, 4], max_traj_uncertainty=m[:, 5], dist=m[:, 6])
+
+    def close(self):
+        self.eng.close()
+
+
+class ExplorationEnv:
+    """The reference's gym-style single env (exploration_env.py:22) on the CUDA engine (B = 1)."""
+
+    def __init__(self, map_size, env_index, test, num_landmarks: Optional[int] = None, max_poses: Optional[int] = None, device=0):
+        self.map_size, self.env_index, self.test = map_size, env_index, test
+        self.dist = 0.0
+        self._cfg = EnvConfig(map_size=map_size, num_landmarks=num_landmarks)
+        if max_poses is None:
+            max_poses = {20: 256, 40: 512, 60: 1536, 80: 3072, 100: 5008}.get(map_size, 2048)
+        self._vec = VecExplorationEnv(1, cfg=self._cfg, max_poses=max_poses, device=device, test=test)
+        self._np_random = np.random.default_rng()   # q20: training envs are seeded from an unseeded RNG
+        self._max_steps = self._cfg.max_steps
+        self.max_step = self._max_steps
+        self.map_resolution = self._cfg.resolution
+        self.leng_i_map, self.leng_j_map = self._cfg.rows, self._cfg.cols
+        self.ext = self._cfg.ext
+        self.loop_clo = False
+        self.nearest_frontier_point = 0
+        self._frontier, self._frontier_index = [], []
+        self._done = False
+        self._obs = self.reset()
+
+    # -- helpers --
+    def _st(self, name):
+        return self._vec.eng.state[name][0]
+
+    def _get_obs(self):
+        self._obs = self._st("prob").cpu().numpy()
+        return self._obs
+
+    def reset(self):
+        self._done = False
+        while True:
+            if not self.test:
+                seed = int(self._np_random.integers(0, np.iinfo(np.int32).max))
+            else:
+                seed = int(self.env_index)
+            seeds = torch.tensor([seed], dtype=torch.int64, device=self._vec.device)
+            self._vec.reset(seeds=seeds, reference_worlds=True)
+            if int(self._st("observed").sum()) < 1:    # exploration_env.py:416-419
+                print("regenerate a environment")
+                self.env_index = self.env_index + 50
+                continue
+            self.dist = 0.0
+            return self._get_obs()
+
+    def step(self, action):
+        odom = torch.tensor([[action.x, action.y, action.theta]], dtype=torch.float64, device=self._vec.device)
+        self._vec.step(odom)
+        self.dist = self.dist + math.sqrt(action.x ** 2 + action.y ** 2)
+        return self._get_obs(), self.done(), {}
+
+    def status(self):
+        return float(self._st("metrics")[0])
+
+    def done(self):
+        return self._done or bool(self._st("done"))
+
+    def get_landmark_error(self, sigma0=1.0):
+        return float(self._st("metrics")[4])
+
+    def max_uncertainty_of_trajectory(self):
+        return float(self._st("metrics")[5])
+
+    def get_dist(self):
+        return self.dist
+
+    def get_landmark_size(self):
+        return int(self._st("observed").sum())
+
+    def get_key_size(self):
+        return self.get_landmark_size() + int(self._st("n_poses"))
+
+    def graph_matrix(self):
+        """(adjacency [N,N] f64, features [N,5] f64, global_features [1], fro_size) like exploration_env.py:196-281.
+        The dense adjacency is assembled on the host from the device COO only for API compatibility."""
+        g = self._vec.graph_host()[0]
+        n, k, f = g["x"].shape[0], g["key_size"], g["fro_size"]
+        adj = np.zeros((n, n))
+        adj[g["edge_index"][0], g["edge_index"][1]] = g["edge_attr"]
+        feats = g["x"].astype(np.float64)
+        fxy = self._vec.graph.frontier_xy[0, :f].cpu().numpy()
+        self._frontier = [list(p) for p in fxy]
+        self.nearest_frontier_point = k
+        self._last_graph = g
+        land = self.get_landmark_size()
+        glob = np.array([np.mean(feats[1:land + 1][:, 0])]) if land > 0 else np.array([np.nan])
+        return adj, feats, glob, f
+
+    get_graph = graph_matrix   # BASELINE.json's name for it
+
+    def frontier(self):
+        self.graph_matrix()
+        return self._frontier
+
+    def line_plan(self, goal_key, fro=(0, 0)):
+        goal = torch.tensor([[fro[0], fro[1]]], dtype=torch.float64, device=self._vec.device)
+        plan = self._vec.line_plan(goal)[0].cpu().numpy()
+        return expand_plan(plan, self._cfg.max_edge_length)
+
+    def actions_all_goals(self):
+        key_size, fro_size = self.get_key_size(), len(self._frontier)
+        all_actions = [[]] * (key_size + fro_size)
+        for i, vi in enumerate(self._frontier):
+            all_actions[i + key_size] = self.line_plan(key_size, vi)
+        return all_actions
+
+    def is_nf(self, id):
+        return self.nearest_frontier_point == id
+
+    def index2coor(self, matrix_i, matrix_j):
+        half = self.map_size / 2 + self.ext
+        return [(matrix_j + 0.5) * self.map_resolution - half, (matrix_i + 0.5) * self.map_resolution - half]
+
+    def coor2index(self, x, y):
+        half = self.map_size / 2 + self.ext
+        return [int(round((y + half) / self.map_resolution - 0.5)), int(round((x + half) / self.map_resolution - 0.5))]
+
+    def close(self):
+        self._vec.close()

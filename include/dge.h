@@ -1,0 +1,185 @@
+/* ============================================================================
+ * dge.h -- C ABI of the B200-native batched exploration-graph engine (libdge.so)
+ *
+ * Drop-in boundary for the hot path of RobustFieldAutonomyLab/DRL_graph_exploration.
+ * The reference crosses Python<->C++ through two pybind11 modules, one object and
+ * one env at a time (src/SS2D.cpp:18-258 `ss2d`, src/Planner2D.cpp:9-106
+ * `planner2d`).  A batched GPU engine cannot sit behind an object-per-call API, so
+ * every entry point below replaces a *group* of those bindings for B independent
+ * environments at once; the reference interface each one replaces is cited.
+ * The Python side (`drl_graph_exploration_b200.envs`) re-creates the reference's
+ * `ExplorationEnv` / `SS2D` method surface on top of these calls.
+ *
+ * Conventions: plain pointers + sizes, no torch types.  Pointers suffixed `_dev`
+ * are device pointers, `_host` are host pointers (pinned for best speed); `stream`
+ * is a `cudaStream_t` passed as void*.  Every call returns 0 on success or a
+ * negative DGE_E* code -- it never aborts (the reference `assert`s / throws).
+ * All launches are asynchronous on `stream`; host-buffer variants synchronise the
+ * stream before returning.  One handle = one device, one stream at a time.
+ * ==========================================================================*/
+#ifndef DGE_H_
+#define DGE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGE_OK 0
+#define DGE_EINVAL (-1)   /* bad argument / capacity exceeded at create time        */
+#define DGE_ECUDA (-2)    /* CUDA runtime error (see dge_last_error)                */
+#define DGE_ENOMEM (-3)
+#define DGE_ECAP (-4)     /* a per-env capacity (poses / measurements) overflowed   */
+
+/* Parameters: scripts/envs/exploration_env.ini as read by pyss2d.py:10-55 and
+ * overridden by ExplorationEnv.reset (exploration_env.py:399-407).  Angles in
+ * radians, already normalised like the reference setters (Simulation2D.h:52-57). */
+typedef struct dge_config {
+  double env_min_x, env_max_x, env_min_y, env_max_y;
+  double map_min_x, map_max_x, map_min_y, map_max_y;
+  double resolution, sigma0;
+  double bearing_noise, range_noise, min_bearing, max_bearing, min_range, max_range;
+  double trans_noise, rot_noise;
+  double sigma_x0, sigma_y0, sigma_theta0;
+  double angle_weight, dist_w0, dist_w1, max_edge_length, occupancy_threshold;
+  double max_steps;
+  double relin_thresh;     /* gtsam::ISAM2Params::relinearizeThreshold (SLAM2D.cpp:10) */
+  int32_t relin_skip;      /* gtsam::ISAM2Params::relinearizeSkip                      */
+  int32_t num_landmarks;   /* [Simulator] num                                         */
+} dge_config;
+
+typedef struct dge_engine *dge_handle;
+
+/* Capacities fixed at creation. max_poses bounds the trajectory length per env
+ * (an env whose trajectory is full reports done). */
+int dge_create(const dge_config *cfg, int n_envs, int max_poses, int device, dge_handle *out);
+int dge_destroy(dge_handle h);
+const char *dge_last_error(void);
+/* out[0..8) = n_envs, max_poses, n_true_landmarks, rows, cols, max_meas_per_env,
+ *             max_graph_nodes_per_env, max_graph_edges_per_env */
+int dge_dims(dge_handle h, int32_t *out);
+
+/* ---- reset: replaces SS2D.__init__ (pyss2d.py:58-138): Simulator2D(seed),
+ * initialize_vehicle, random_landmarks, SLAM2D.add_prior, first measure+optimize.
+ *   mask_dev   [B] u8, nullable (null = all envs)
+ *   seeds_dev  [B] u64 Philox keys (perf mode RNG)
+ *   start_dev  [B,3] f64 nullable: explicit start poses (parity mode; else drawn on device
+ *              like pyss2d.py:88-95: integer x/y, whole-degree heading)
+ *   lm_dev     [B,Lt,2] f64 nullable: explicit true landmarks by id (else drawn on device
+ *              like Simulator2D::addLandmarks, Simulator2D.cpp:445-465)
+ *   scan_dev   [B,Lt] i32 nullable: landmark scan order (slot -> id); null = identity
+ *   noise_dev  [B, 3+4*Lt] f64 nullable: explicit measurement noise (layout below)   */
+int dge_reset(dge_handle h, const uint8_t *mask_dev, const uint64_t *seeds_dev, const double *start_dev,
+              const double *lm_dev, const int32_t *scan_dev, const double *noise_dev, void *stream);
+
+/* ---- step: replaces ExplorationEnv.step -> SS2D.simulate (exploration_env.py:98-105,
+ * pyss2d.py:171-206): Simulator2D.move + SLAM2D.add_odometry, Simulator2D.measure (x2),
+ * SLAM2D.add_measurement, SLAM2D.optimize(update_covariance=True),
+ * VirtualMap.update_probability + update_information.
+ *   odom_dev   [B,3] f64 (x, y, theta) body-frame command
+ *   mask_dev   [B] u8 nullable: envs to step
+ *   noise_dev  [B, 3+4*Lt] f64 nullable.  Parity mode: [0..3) move noise (x,y,theta);
+ *              [3 + c*2*Lt + 2*s + {0,1}] (bearing, range) noise of measure() call c
+ *              (0 = obstacle probe, unused; 1 = real) for scan slot s.  Null: Philox.  */
+int dge_step(dge_handle h, const double *odom_dev, const uint8_t *mask_dev, const double *noise_dev, void *stream);
+/* same, but every env executes the next action of its own queued line plan (filled by
+ * dge_select_and_plan); envs whose queue is empty do not step.                       */
+int dge_step_queued(dge_handle h, void *stream);
+/* the three stages of dge_step, separately launchable (profiling / tests) */
+int dge_move_measure(dge_handle h, const double *odom_dev, const uint8_t *mask_dev, const double *noise_dev, void *stream);
+int dge_slam_optimize(dge_handle h, const uint8_t *mask_dev, void *stream);   /* SLAM2D::optimize  SLAM2D.cpp:374-430 */
+int dge_virtual_map(dge_handle h, const uint8_t *mask_dev, void *stream);     /* VirtualMap.cpp:61-84,256-316         */
+
+/* host-buffer variant of dge_step (the call a ctypes/pybind caller makes): copies odom
+ * H2D, steps, copies done flags (and the occupancy maps when obs_host != NULL) D2H.  */
+int dge_step_host(dge_handle h, const double *odom_host, const uint8_t *mask_host, uint8_t *done_host,
+                  double *obs_host /* [B,rows,cols] nullable */, void *stream);
+
+/* ---- stand-alone virtual-map rebuild on caller-provided belief states (a6+a7;
+ * VirtualMap::updateProbability + updateInformation).  n problems, T poses each.
+ *   pose_dev [n,T,3], cov_dev [n,T,6] (upper triangle xx,xy,xt,yy,yt,tt of the pose
+ *   covariance = inverse information), lm_dev [n,L,2];  outputs prob_dev [n,V],
+ *   vinfo_dev [n,V,3] (xx,xy,yy).                                                  */
+int dge_virtual_map_rebuild(const dge_config *cfg, int n, int T, const double *pose_dev, const double *cov_dev,
+                            int L, const double *lm_dev, double *prob_dev, double *vinfo_dev,
+                            int32_t *seen_dev /* [n,V] nullable: integer visibility counts, -1 = landmark cell */,
+                            double *ws_dev /* dge_virtual_map_rebuild_ws_doubles(n,T) doubles */, void *stream);
+int64_t dge_virtual_map_rebuild_ws_doubles(int n, int T);
+
+/* ---- state views (device pointers owned by the engine; valid until dge_destroy).
+ * Replaces the per-object getters of ss2d: SLAM2D.map.iter_trajectory / iter_landmarks,
+ * VirtualMap.to_array / to_cov_trace / explored, Simulator2D.vehicle (SS2D.cpp:141-257). */
+typedef struct dge_state_view {
+  const int32_t *n_poses;        /* [B]                      */
+  const int32_t *sim_step;       /* [B] pyss2d self.step      */
+  const int32_t *update_count;   /* [B]                      */
+  const double *true_pose;       /* [B,3]                    */
+  const double *est_pose;        /* [B,Tmax,3]               */
+  const double *lin_pose;        /* [B,Tmax,3]               */
+  const double *delta_pose;      /* [B,Tmax,3]               */
+  const double *pose_cov;        /* [B,Tmax,6] upper triangle */
+  const double *pose_info;       /* [B,Tmax,6]               */
+  const double *odom;            /* [B,Tmax,3]               */
+  const int32_t *meas_ptr;       /* [B,Tmax+1]               */
+  const int32_t *meas_id;        /* [B,Mmax]                 */
+  const double *meas_bearing;    /* [B,Mmax]                 */
+  const double *meas_range;      /* [B,Mmax]                 */
+  const double *lm_true;         /* [B,Lt,2] by id           */
+  const int32_t *scan_id;        /* [B,Lt]                   */
+  const uint8_t *observed;       /* [B,Lt]                   */
+  const double *est_l;           /* [B,Lt,2]                 */
+  const double *lin_l;           /* [B,Lt,2]                 */
+  const double *land_cov;        /* [B,Lt,3] xx,xy,yy        */
+  const double *prob;            /* [B,V]                    */
+  const double *vinfo;           /* [B,V,3] xx,xy,yy         */
+  const int32_t *seen;           /* [B,V] visibility counts, -1 = landmark cell */
+  const double *metrics;         /* [B,8]: explored, utility(0), sum cov-trace, #p<thresh,
+                                    landmark_error, max pose-cov trace, dist, reserved */
+  const uint8_t *done;           /* [B]                      */
+  const int32_t *status;         /* [B] 0 ok, DGE_ECAP, or 1 = solver breakdown       */
+  const double *plan;            /* [B,6] queued line plan (see dge_line_plan)        */
+  const int32_t *plan_cursor;    /* [B] next action of the plan                       */
+} dge_state_view;
+int dge_get_state(dge_handle h, dge_state_view *out);
+
+/* ---- exploration graph: replaces ExplorationEnv.graph_matrix + frontier
+ * (exploration_env.py:196-358), SLAM2D.adjacency_degree_get / key_size / get_key_points
+ * (SLAM2D.cpp:141-273) and DeepQ.data_process (policy.py:211-232).  Emits one batched
+ * graph (PyG DataLoader layout) for the envs selected by mask, directly on device.
+ * Caller-owned output buffers with the capacities reported by dge_dims.             */
+typedef struct dge_graph_out {
+  float *x;                /* [Ncap,5]  node features f32                              */
+  int64_t *edge_index;     /* [2,Ecap]  (row 0 = src, row 1 = dst), stride = edge_cap   */
+  float *edge_attr;        /* [Ecap]                                                    */
+  int64_t *batch;          /* [Ncap]    graph id (position among selected envs)         */
+  int32_t *node_ptr;       /* [B+1]     per selected env                                */
+  int32_t *edge_ptr;       /* [B+1]                                                     */
+  int32_t *key_size;       /* [B]       K = L + T                                       */
+  int32_t *fro_size;       /* [B]       F                                               */
+  double *frontier_xy;     /* [B,Fmax,2] goal coordinates of frontier f (indexed by ENV, not by
+                              graph position), Fmax = Lt+1                              */
+  int32_t *totals;         /* [4]: n_graphs, N_tot, E_tot, overflow flag                */
+  int64_t node_cap, edge_cap;
+} dge_graph_out;
+int dge_graph(dge_handle h, const uint8_t *mask_dev, const dge_graph_out *out, void *stream);
+
+/* ---- line planner: replaces EMPlanner2D.line_planner (Planner2D.cpp:937-1041) for one
+ * goal per env.  goal_dev [B,2]; plan_dev [B,6] = (n_rot_pi, rot_sign, rot_remainder,
+ * n_fwd_full, fwd_remainder, n_actions).  Action i of the plan is expanded by
+ * dge_plan_action.  mask nullable.                                                   */
+int dge_line_plan(dge_handle h, const double *goal_dev, const uint8_t *mask_dev, double *plan_dev, void *stream);
+
+/* ---- policy head on device: per selected graph, argmax of q over its last fro_size
+ * nodes (policy.py:109 / test.py:112), goal = that frontier, line plan into the env's
+ * action queue.  q_dev [N_tot] f32 in the node order of `g`.                         */
+int dge_select_and_plan(dge_handle h, const dge_graph_out *g, const float *q_dev, const uint8_t *mask_dev,
+                        int32_t *choice_dev /* [B] nullable: chosen frontier index */, void *stream);
+
+/* ---- GNN building blocks (scripts/Networks.py GCN: GCNConv(improved=True) aggregate,
+ * bias, ReLU; Linear head) -- hand-written edge/dst-parallel kernels, see dge_gnn.h  */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGE_H_ */

@@ -1,0 +1,41 @@
+/* ============================================================================
+ * dge_gnn.h -- C ABI of the GNN message-passing kernels in libdge.so.
+ *
+ * Replaces, for the graph Q-network of scripts/Networks.py (GCN: Networks.py:12-28;
+ * the conv layers of GGNN / GraphUNet reuse the same aggregation), the PyG /
+ * torch_scatter call sites listed in SURVEY section 2.3: add_remaining_self_loops +
+ * weighted-degree scatter_add + symmetric norm (GCNConv.norm) and the per-edge
+ * gather * scale + scatter_add of GCNConv.propagate / GatedGraphConv.propagate.
+ * Plain device pointers; int64 edge indices exactly as torch `edge_index` rows.
+ * Return 0 ok, -1 bad argument, -2 CUDA error.  All launches are async on `stream`.
+ * ==========================================================================*/
+#ifndef DGE_GNN_H_
+#define DGE_GNN_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Deterministic CSR of E edges grouped by key[e] in [0,N) (key = edge_index[1] for the
+ * forward gather, edge_index[0] for the transposed/backward gather); rows sorted by edge id.
+ * rowptr [N+1], perm [E], ws [2N] scratch. */
+int dge_gnn_csr_build(int N, int E, const int64_t *key, int32_t *rowptr, int32_t *perm, int32_t *ws, void *stream);
+
+/* GCNConv.norm(improved: fill = 2): dis [N] = deg^-1/2, selfw [N] self-loop weight,
+ * norm [E] per-edge coefficient (0 on explicit self loops), selfnorm [N]. */
+int dge_gcn_norm(int N, int E, const int64_t *src, const int64_t *dst, const float *w, const int32_t *rowptr_src,
+                 const int32_t *perm_src, float fill, float *dis, float *selfw, float *norm, float *selfnorm, void *stream);
+
+/* out[i,:] = act(bias + selfcoef[i] X[i,:] + sum_{p in rowptr[i]..rowptr[i+1]} coef[perm[p]] * mask(X[nbr[perm[p]],:]))
+ *   X [N,C] f32 row-major (C <= 1024), nbr [E] int64 = the *other* endpoint of each edge,
+ *   coef [E], selfcoef [N] nullable, bias [C] nullable, gate [N,C] nullable (rows are
+ *   multiplied by gate>0: ReLU backward fused into the gather), relu 0/1, out [N,C] nullable,
+ *   head_w [C] nullable: also emit q[i] = dot(out[i,:], head_w) + head_b (Linear(C,1) fused). */
+int dge_gnn_aggregate(int N, int C, const float *X, const int32_t *rowptr, const int32_t *perm, const int64_t *nbr,
+                      const float *coef, const float *selfcoef, const float *bias, const float *gate, int relu, float *out,
+                      const float *head_w, float head_b, float *q, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
