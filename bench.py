@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the exploration hot path on B200.
+
+Workload (BASELINE.json configs[1]): 256 parallel envs per GPU, 20x20 map, 30 landmarks,
+GNN (GCN) policy inference only.  One "step" = one tick of the batched engine: envs whose
+action queue is empty get a decision (exploration graph -> GCN forward -> arg-max over frontier
+nodes -> line plan), then every env executes one simulator step (motion + association scan +
+SLAM solve + marginals + virtual-map rebuild); finished episodes are reset.
+metric = policy-driven env-steps/sec (reset steps are not counted).
+
+  python bench.py --gpus N --steps K --warmup W        # N > 1: launched under torchrun, one rank per GPU
+  python bench.py --impl reference ...                 # the reference path on host cores (CPU oracle + torch-CPU GCN)
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAP_SIZE, N_LANDMARKS, ENVS_PER_GPU, MAX_POSES = 20, 30, 256, 192
+WORKLOAD = f"{ENVS_PER_GPU} envs/GPU, {MAP_SIZE}x{MAP_SIZE} map, {N_LANDMARKS} landmarks, GCN policy inference (BASELINE configs[1])"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------ CPU reference arm ---
+def cpu_reference(n_envs: int, n_ticks: int, threads: int, seed0: int = 0):
+    """The reference path on host cores: CPU oracle envs (single-threaded each, like the reference)
+    spread over `threads` host threads + the pure-PyTorch GCN restatement on CPU.  Same tick
+    structure as the GPU arm."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from drl_graph_exploration_b200.config import EnvConfig
+    from oracle import gnn_ref
+    from oracle.oracle import OracleEnv
+
+    cfg = EnvConfig(map_size=MAP_SIZE, num_landmarks=N_LANDMARKS)
+    torch.manual_seed(0)
+    model = gnn_ref.GCN().eval()
+    torch.set_num_threads(threads)
+    reset_odom = (1.0, 1.0, math.pi / 2)
+
+    def fresh(seed):
+        e = OracleEnv(cfg, seed, record_noise=False)
+        for _ in range(4):
+            e.step(reset_odom, record_noise=False)
+        return e
+
+    pool = ThreadPoolExecutor(max_workers=threads)
+    envs = list(pool.map(fresh, range(seed0, seed0 + n_envs)))
+    queues = [[] for _ in envs]
+    next_seed = seed0 + n_envs
+    steps = 0
+
+    def graph_of(i):
+        return envs[i].graph()
+
+    def step_env(i):
+        envs[i].step(queues[i].pop(0), record_noise=False)
+        return envs[i].metrics()["done"]
+
+    def run_tick():
+        nonlocal steps, next_seed
+        need = [i for i in range(n_envs) if not queues[i]]
+        if need:
+            graphs = list(pool.map(graph_of, need))
+            xs, eis, eas, off = [], [], [], 0
+            for g in graphs:
+                xs.append(torch.tensor(g["features"], dtype=torch.float32)); eis.append(torch.tensor(g["edge_index"]) + off)
+                eas.append(torch.tensor(g["edge_attr"], dtype=torch.float32)); off += g["n_nodes"]
+            with torch.no_grad():
+                q = model(gnn_ref.Graph(torch.cat(xs), torch.cat(eis, dim=1), torch.cat(eas)), 0.0).view(-1).numpy()
+            off = 0
+            for i, g in zip(need, graphs):
+                f = g["fro_size"]
+                if f > 0:
+                    a = int(np.argmax(q[off + g["key_size"]: off + g["n_nodes"]]))
+                    queues[i] = [tuple(r) for r in envs[i].line_plan(*g["frontier_xy"][a])]
+                else:
+                    queues[i] = [(0.0, 0.0, 0.5)]
+                off += g["n_nodes"]
+        dones = list(pool.map(step_env, range(n_envs)))
+        steps += n_envs
+        for i, d in enumerate(dones):
+            if d or envs[i].sizes()["T"] >= MAX_POSES - 1:
+                envs[i] = fresh(next_seed); next_seed += 1; queues[i] = []
+
+    return run_tick, lambda: steps
+
+
+def run_reference(args):
+    threads = os.cpu_count() or 1
+    n_envs = min(ENVS_PER_GPU, max(threads, 8))
+    run_tick, count = cpu_reference(n_envs, 0, threads)
+    for _ in range(args.warmup):
+        run_tick()
+    c0, t0 = count(), time.perf_counter()
+    for _ in range(args.steps):
+        run_tick()
+    dt = time.perf_counter() - t0
+    val = (count() - c0) / dt
+    sample = f"{n_envs} of {ENVS_PER_GPU} envs x {args.steps} ticks, oracle envs on {threads} host threads + torch-CPU GCN"
+    print(json.dumps({"impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "sample": sample},
+                      "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------- GPU arm ---
+class GpuLoop:
+    def __init__(self, device, seed0):
+        from drl_graph_exploration_b200 import Networks, gnn
+        from drl_graph_exploration_b200.config import EnvConfig
+        from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv
+
+        self.gnn = gnn
+        cfg = EnvConfig(map_size=MAP_SIZE, num_landmarks=N_LANDMARKS)
+        self.env = VecExplorationEnv(ENVS_PER_GPU, cfg=cfg, max_poses=MAX_POSES, device=device, seed0=seed0)
+        torch.manual_seed(0)
+        self.model = Networks.GCN().to(self.env.device).eval()
+        self.env.reset()
+        self.dev = self.env.device
+        self.flags = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        self.flags_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self.steps_dev = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self.sumT_dev = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self.sumM_dev = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self.launches = 0
+        self.ev = {k: [] for k in ("slam", "vmap")}
+        self.graphs = 0
+
+    @torch.no_grad()
+    def tick(self, timed=False):
+        env, eng = self.env, self.env.eng
+        st = eng.state
+        need = env.needs_decision()
+        g = env.build_graph(need); self.launches += 3
+        ng, n, e = g.sync_sizes()
+        if ng > 0:
+            l0 = self.gnn.launch_count
+            q = self.model(g.data(), 0.0)
+            env.select_and_plan(q, need)
+            self.launches += self.gnn.launch_count - l0 + 1
+            self.graphs += ng
+        # one simulator step for every env (staged calls == dge_step_queued, with events around the stages)
+        from drl_graph_exploration_b200.engine import _check, _ptr, _stream_ptr
+        sp = _stream_ptr(self.dev)
+        _check(eng._L.dge_move_measure_queued(eng._h, sp), "move_measure_queued")
+        if timed:
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+        _check(eng._L.dge_slam_optimize(eng._h, _ptr(st["active"]), sp), "slam")
+        if timed:
+            e1.record()
+        _check(eng._L.dge_virtual_map(eng._h, _ptr(st["active"]), sp), "vmap")
+        if timed:
+            e2.record()
+            self.ev["slam"].append((e0, e1)); self.ev["vmap"].append((e1, e2))
+        self.launches += 5
+        act = st["active"].to(torch.int64)
+        self.steps_dev += act.sum()
+        self.sumT_dev += (act * st["n_poses"]).sum()
+        self.sumM_dev += (act * st["meas_ptr"].gather(1, st["n_poses"].long().view(-1, 1)).view(-1)).sum()
+        # episode ends: reset (4 forced steps) only when some env is done
+        self.flags[0] = st["done"].sum()
+        self.flags_host.copy_(self.flags, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        if int(self.flags_host[0]) > 0:
+            env.reset_done(); self.launches += 2 + 4 * 5
+
+
+def e2e_loop(loop: GpuLoop):
+    """The same tick through the reference-facing host API: graphs D2H -> host -> H2D for the GNN,
+    Q D2H, arg-max + line plans on the host, actions H2D, done flags + occupancy maps D2H."""
+    from drl_graph_exploration_b200.data import Batch, Data
+    from drl_graph_exploration_b200.envs.exploration_env import expand_plan
+
+    env, eng = loop.env, loop.env.eng
+    B = env.B
+    queues = [[] for _ in range(B)]
+    odom_host = np.zeros((B, 3)); done_host = np.zeros(B, dtype=np.uint8); obs_host = np.zeros((B, eng.rows, eng.cols))
+    mask_host = torch.zeros(B, dtype=torch.uint8).pin_memory()
+    stats = {"h2d": 0, "d2h": 0, "steps": 0}
+
+    @torch.no_grad()
+    def tick():
+        need = [i for i in range(B) if not queues[i]]
+        if need:
+            mask_host.zero_(); mask_host[need] = 1
+            mask = mask_host.to(env.device, non_blocking=True); stats["h2d"] += B
+            graphs = env.graph_host(mask)
+            for gph in graphs:
+                stats["d2h"] += gph["x"].nbytes + gph["edge_index"].nbytes + gph["edge_attr"].nbytes
+            datas = [Data(torch.from_numpy(gph["x"]), torch.from_numpy(gph["edge_index"]), torch.from_numpy(gph["edge_attr"])) for gph in graphs]
+            batch = Batch.from_data_list(datas).to(env.device)
+            stats["h2d"] += sum(gph["x"].nbytes + gph["edge_index"].nbytes + gph["edge_attr"].nbytes for gph in graphs)
+            q = loop.model(batch, 0.0).view(-1).cpu().numpy(); stats["d2h"] += q.nbytes
+            fxy = env.graph.frontier_xy.cpu().numpy(); stats["d2h"] += fxy.nbytes
+            goals = np.zeros((B, 2)); off = 0
+            for i, gph in zip(need, graphs):
+                n, k, f = gph["x"].shape[0], gph["key_size"], gph["fro_size"]
+                a = int(np.argmax(q[off + k: off + n])) if f > 0 else 0
+                goals[i] = fxy[i, a]; off += n
+            plans = env.line_plan(torch.as_tensor(goals, device=env.device), mask).cpu().numpy()
+            stats["h2d"] += goals.nbytes; stats["d2h"] += plans.nbytes
+            for i in need:
+                queues[i] = expand_plan(plans[i], eng.cfg.max_edge_length)
+        for i in range(B):
+            a = queues[i].pop(0)
+            odom_host[i] = (a.x, a.y, a.theta)
+        env.step_host(odom_host, done_host, obs_host)
+        stats["h2d"] += odom_host.nbytes; stats["d2h"] += done_host.nbytes + obs_host.nbytes
+        stats["steps"] += B
+        if done_host.any() or int(eng.state["n_poses"].max()) >= MAX_POSES - 1:
+            d = torch.as_tensor(done_host, device=env.device) | (eng.state["n_poses"] >= MAX_POSES - 1).to(torch.uint8)
+            eng.state["done"].copy_(d)
+            dn = env.reset_done().cpu().numpy()
+            for i in np.nonzero(dn)[0]:
+                queues[i] = []
+
+    return tick, stats
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-flush-l2", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = local
+    torch.cuda.set_device(device)
+    loop = GpuLoop(device, seed0=rank * 100000)
+    flush = None if args.no_flush_l2 else torch.empty(256 << 20, dtype=torch.uint8, device=loop.dev)
+
+    for _ in range(args.warmup):
+        loop.tick()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(device) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    loop.launches = 0; loop.graphs = 0
+    loop.steps_dev.zero_(); loop.sumT_dev.zero_(); loop.sumM_dev.zero_()
+    tick_events = []
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)           # L2 flush (untimed): > 126 MB written between timed ticks
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); loop.tick(timed=True); b.record()
+        tick_events.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(a.elapsed_time(b) for a, b in tick_events)
+    steps_rank = int(loop.steps_dev.item())
+    t = torch.tensor([total_ms], dtype=torch.float64, device=loop.dev)
+    s = torch.tensor([steps_rank, loop.graphs], dtype=torch.float64, device=loop.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item()); steps_all, graphs_all = float(s[0].item()), float(s[1].item())
+
+    out = None
+    if rank == 0:
+        pk, pk_kind = peaks()
+        value = steps_all / (total_ms / 1e3)
+        # roofline of the dominant simulator kernels (algorithmic fp64 bytes per SURVEY 8(d) x 2 for fp64)
+        T_mean = float(loop.sumT_dev.item()) / max(steps_rank, 1); M_mean = float(loop.sumM_dev.item()) / max(steps_rank, 1)
+        eng = loop.env.eng
+        ms_slam = sum(a.elapsed_time(b) for a, b in loop.ev["slam"]) / max(len(loop.ev["slam"]), 1)
+        ms_vmap = sum(a.elapsed_time(b) for a, b in loop.ev["vmap"]) / max(len(loop.ev["vmap"]), 1)
+        envs_per_launch = steps_rank / max(args.steps, 1)
+        bytes_vmap = 2 * (48 * T_mean + 20 * eng.V + 8 * eng.Lt) * envs_per_launch
+        bytes_slam = 2 * (72 * T_mean + 16 * M_mean + 32 * eng.Lt) * envs_per_launch
+        dom = "slam" if ms_slam >= ms_vmap else "vmap"
+        ach = (bytes_slam / (ms_slam * 1e-3) if dom == "slam" else bytes_vmap / (ms_vmap * 1e-3)) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_slam" if dom == "slam" else "k_vmap_prep+k_vmap_cells+k_vmap_metrics", "achieved": ach,
+                "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                "ms_per_launch": {"slam": ms_slam, "vmap": ms_vmap}, "mean_poses": T_mean, "mean_measurements": M_mean,
+                "vmap": {"achieved": bytes_vmap / (ms_vmap * 1e-3) / 1e9, "frac": bytes_vmap / (ms_vmap * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                "slam": {"achieved": bytes_slam / (ms_slam * 1e-3) / 1e9, "frac": bytes_slam / (ms_slam * 1e-3) / 1e9 / pk["hbm_gbs"]}}
+        out = {"metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": {"workload": WORKLOAD, "envs_per_gpu": ENVS_PER_GPU, "map_size": MAP_SIZE, "landmarks": N_LANDMARKS,
+                                               "policy": "GCN fp32, random init", "parallelism": f"env-sharded x{world}, no data-path collective",
+                                               "l2": "flushed (256 MiB write) between timed ticks" if flush is not None else "not flushed"},
+               "gnn_graphs_per_s": graphs_all / (total_ms / 1e3), "gpu_launches": loop.launches, "clocks": clocks, "roofline": roof}
+    # e2e + cpu baseline on rank 0 at N = 1 only
+    if rank == 0 and world == 1 and not args.no_e2e:
+        tick, stats = e2e_loop(loop)
+        n_e2e = max(10, args.steps // 4)
+        for _ in range(3):
+            tick()
+        stats.update(h2d=0, d2h=0, steps=0)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            tick()
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        out["e2e"] = {"value": stats["steps"] / dt, "unit": "env-steps/s", "h2d_bytes_per_step": stats["h2d"] / n_e2e,
+                      "d2h_bytes_per_step": stats["d2h"] / n_e2e, "ticks": n_e2e}
+    elif rank == 0:
+        out["e2e"] = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_envs = min(ENVS_PER_GPU, max(threads, 8))
+        run_tick, count = cpu_reference(n_envs, 0, threads, seed0=777)
+        run_tick()
+        c0, t0 = count(), time.perf_counter()
+        nt = 0
+        while time.perf_counter() - t0 < 15.0 and nt < 400:
+            run_tick(); nt += 1
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": (count() - c0) / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                               "sample": f"{n_envs} of {ENVS_PER_GPU} envs x {nt} ticks ({dt:.1f} s): CPU oracle envs on {threads} host threads + torch-CPU GCN"}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,11 @@ extern "C" int dge_move_measure(dge_handle h, const double *odom, const uint8_t 
   const int rc = dge_launch_move_measure(h, odom, mask, noise, 0, static_cast<cudaStream_t>(stream));
   return rc ? fail(rc, "dge_move_measure") : DGE_OK;
 }
+extern "C" int dge_move_measure_queued(dge_handle h, void *stream) {
+  if (!h) return DGE_EINVAL;
+  const int rc = dge_launch_move_measure(h, nullptr, nullptr, nullptr, 1, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_move_measure_queued") : DGE_OK;
+}
 extern "C" int dge_slam_optimize(dge_handle h, const uint8_t *mask, void *stream) {
   if (!h) return DGE_EINVAL;
   const int rc = dge_launch_slam(h, mask, static_cast<cudaStream_t>(stream));
@@ -183,7 +188,7 @@ extern "C" int dge_get_state(dge_handle h, dge_state_view *o) {
   o->pose_cov = h->pose_cov; o->pose_info = h->pose_info; o->odom = h->odom;
   o->meas_ptr = h->meas_ptr; o->meas_id = h->meas_id; o->meas_bearing = h->meas_b; o->meas_range = h->meas_r;
   o->lm_true = h->lm_true; o->scan_id = h->scan_id; o->observed = h->observed; o->est_l = h->est_l; o->lin_l = h->lin_l;
-  o->land_cov = h->land_cov; o->prob = h->prob; o->vinfo = h->vinfo; o->seen = h->seen; o->metrics = h->metrics; o->done = h->done; o->status = h->status;
+  o->land_cov = h->land_cov; o->prob = h->prob; o->vinfo = h->vinfo; o->seen = h->seen; o->metrics = h->metrics; o->done = h->done; o->active = h->active; o->status = h->status;
   o->plan = h->plan; o->plan_cursor = h->plan_cursor;
   return DGE_OK;
 }

@@ -294,12 +294,12 @@ __global__ void k_line_plan(dge_config cfg, DgeDims d, const int32_t *n_poses, c
 // policy.py:109 / test.py:112), goal = that frontier, plan into the env's queue.
 __global__ void __launch_bounds__(32) k_select_plan(dge_config cfg, DgeDims d, const int32_t *n_poses, const double *est_pose,
                                                     const int32_t *g_sel, dge_graph_out o, const float *q, const uint8_t *mask,
-                                                    double *plan, int32_t *cursor, int32_t *choice) {
+                                                    double *plan, int32_t *cursor, int32_t *choice, uint8_t *done) {
   const int b = blockIdx.x, lane = threadIdx.x;
   const int g = g_sel[b];
   if (g < 0 || (mask && !mask[b])) return;
   const int F = o.fro_size[g], K = o.key_size[g], n0 = o.node_ptr[g];
-  if (F <= 0) { if (lane == 0) { for (int i = 0; i < 6; ++i) plan[6 * b + i] = 0; cursor[b] = 0; if (choice) choice[b] = -1; } return; }
+  if (F <= 0) { if (lane == 0) { for (int i = 0; i < 6; ++i) plan[6 * b + i] = 0; cursor[b] = 0; if (choice) choice[b] = -1; done[b] = 1; /* q15: no frontier left = episode over */ } return; }
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int f = lane; f < F; f += 32) {   // ascending f per lane: strict > keeps the first maximum
@@ -347,6 +347,6 @@ int dge_launch_line_plan(dge_engine *e, const double *goal, const uint8_t *mask,
 }
 
 int dge_launch_select_plan(dge_engine *e, const dge_graph_out *g, const float *q, const uint8_t *mask, int32_t *choice, cudaStream_t st) {
-  k_select_plan<<<e->d.B, 32, 0, st>>>(e->cfg, e->d, e->n_poses, e->est_pose, e->g_sel, *g, q, mask, e->plan, e->plan_cursor, choice);
+  k_select_plan<<<e->d.B, 32, 0, st>>>(e->cfg, e->d, e->n_poses, e->est_pose, e->g_sel, *g, q, mask, e->plan, e->plan_cursor, choice, e->done);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }

@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
   if (act && (!(a.cfg.map_min_x < ox && ox < a.cfg.map_max_x) || !(a.cfg.map_min_y < oy && oy < a.cfg.map_max_y))) act = false;
   const int T = a.n_poses[b];
   if (act && T >= a.d.Tmax) { act = false; if (lane == 0) { a.status[b] = DGE_ECAP; a.done[b] = 1; } }
-  if (act && a.done[b]) act = false;
+  // (like the reference, a finished episode can still be stepped explicitly; only the queued
+  //  mode parks `done` envs until the caller resets them)
+  if (act && from_queue && a.done[b]) act = false;
   if (lane == 0) a.active[b] = act ? 1 : 0;
   if (!act) return;
   const uint64_t key = a.seed[b];

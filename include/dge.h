@@ -86,7 +86,9 @@ int dge_step(dge_handle h, const double *odom_dev, const uint8_t *mask_dev, cons
 /* same, but every env executes the next action of its own queued line plan (filled by
  * dge_select_and_plan); envs whose queue is empty do not step.                       */
 int dge_step_queued(dge_handle h, void *stream);
-/* the three stages of dge_step, separately launchable (profiling / tests) */
+/* the three stages of dge_step, separately launchable (profiling / tests); after the first
+ * stage `active` (see dge_state_view) flags the envs that actually moved.             */
+int dge_move_measure_queued(dge_handle h, void *stream);
 int dge_move_measure(dge_handle h, const double *odom_dev, const uint8_t *mask_dev, const double *noise_dev, void *stream);
 int dge_slam_optimize(dge_handle h, const uint8_t *mask_dev, void *stream);   /* SLAM2D::optimize  SLAM2D.cpp:374-430 */
 int dge_virtual_map(dge_handle h, const uint8_t *mask_dev, void *stream);     /* VirtualMap.cpp:61-84,256-316         */
@@ -137,6 +139,7 @@ typedef struct dge_state_view {
   const double *metrics;         /* [B,8]: explored, utility(0), sum cov-trace, #p<thresh,
                                     landmark_error, max pose-cov trace, dist, reserved */
   const uint8_t *done;           /* [B]                      */
+  const uint8_t *active;         /* [B] envs that moved in the last (queued) step        */
   const int32_t *status;         /* [B] 0 ok, DGE_ECAP, or 1 = solver breakdown       */
   const double *plan;            /* [B,6] queued line plan (see dge_line_plan)        */
   const int32_t *plan_cursor;    /* [B] next action of the plan                       */

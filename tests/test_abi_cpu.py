@@ -1,0 +1,56 @@
+"""No-GPU checks of the drop-in boundary: libdge.so loads and exports every symbol that
+include/*.h declares; the config struct layouts agree; the product path refuses to run without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    syms = []
+    for h in ("dge.h", "dge_gnn.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        syms += re.findall(r"\b(dge_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(syms))
+
+
+def test_library_exports_every_declared_symbol():
+    from drl_graph_exploration_b200 import build_ext
+    lib = ctypes.CDLL(build_ext.build())
+    missing = [s for s in _declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+    assert len(_declared_symbols()) >= 20
+
+
+def test_config_struct_layout_matches_oracle():
+    from drl_graph_exploration_b200.config import DgeConfigStruct, EnvConfig
+    from oracle import oracle
+    assert oracle.lib().orc_sizeof_config() == ctypes.sizeof(DgeConfigStruct)
+    c = EnvConfig(map_size=60).to_struct()
+    assert (c.map_min_x, c.map_max_x, c.env_max_y, c.num_landmarks) == (-50.0, 50.0, 30.0, 18)
+    assert EnvConfig(map_size=100).rows == 70 and EnvConfig(map_size=20).rows == 30
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_path_fails_loudly_without_gpu():
+    from drl_graph_exploration_b200.config import EnvConfig
+    from drl_graph_exploration_b200.engine import DgeError, Engine
+    from drl_graph_exploration_b200 import gnn
+    with pytest.raises(DgeError):
+        Engine(EnvConfig(map_size=20), 2)
+    with pytest.raises(DgeError):
+        gnn.GraphStructure(torch.zeros(2, 4, dtype=torch.long), None, 3)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "drl_graph_exploration_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f

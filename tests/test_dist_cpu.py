@@ -1,0 +1,43 @@
+"""world_size-2 gloo test (CPU) of the N>1 path: env sharding and the single flat gradient all-reduce."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from drl_graph_exploration_b200.dist import FlatGradBucket, env_seeds, shard_envs
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 8), torch.nn.ReLU(), torch.nn.Linear(8, 1))
+    bucket = FlatGradBucket(model.parameters())
+    lo, hi = shard_envs(10, rank, world)
+    x = torch.arange(10 * 5, dtype=torch.float32).view(10, 5)[lo:hi] / 50.0
+    bucket.zero_()
+    model(x).sum().backward()
+    local = bucket.flat.clone()
+    bucket.all_reduce_mean()
+    bucket.clamp_(0.5)
+    q.put((rank, lo, hi, local, bucket.flat.clone()))
+    dist.destroy_process_group()
+
+
+def test_shard_and_flat_allreduce():
+    assert shard_envs(256 * 8, 3, 8) == (768, 1024) and shard_envs(10, 1, 4) == (3, 6) and shard_envs(10, 3, 4) == (9, 10)
+    assert env_seeds(4, 6, episode=2).tolist() == [4 + 2 * (1 << 20), 5 + 2 * (1 << 20)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    (r0, lo0, hi0, l0, f0), (r1, lo1, hi1, l1, f1) = res
+    assert (lo0, hi0, lo1, hi1) == (0, 5, 5, 10)
+    assert torch.equal(f0, f1)                                     # replicas stay identical
+    assert torch.allclose(f0, ((l0 + l1) / 2).clamp(-0.5, 0.5))   # mean, THEN clamp

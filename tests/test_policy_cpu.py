@@ -1,0 +1,60 @@
+"""Host logic of the DQN mirror (no GPU): data_process order, cost, target construction."""
+import numpy as np
+import torch
+
+from drl_graph_exploration_b200.data import Data
+from drl_graph_exploration_b200.policy import DeepQ
+
+
+def _reference_scan(s_a):
+    """policy.py:216-227 described literally: walk the dense matrix row-major, emit (i,j) then (j,i) at the
+    first encounter of an undirected pair with non-zero weight."""
+    ei, ea, seen = [], [], set()
+    n = s_a.shape[0]
+    for i in range(n):
+        for j in range(n):
+            if (i, j) in seen or (j, i) in seen or s_a[i][j] == 0:
+                continue
+            ei.append([i, j]); ea.append(s_a[i][j])
+            if i != j:
+                ei.append([j, i]); ea.append(s_a[j][i])
+            seen.add((i, j)); seen.add((j, i))
+    return np.array(ei).T, np.array(ea)
+
+
+def test_data_process_order():
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 40):
+        a = rng.uniform(0.1, 6, (n, n)) * (rng.uniform(size=(n, n)) < 0.3)
+        a = np.triu(a, 1); a = a + a.T
+        if n > 2:
+            a[2, 2] = 1.5   # a self loop
+        x = rng.normal(size=(n, 5))
+        d = DeepQ().data_process([a, x])
+        ei, ea = _reference_scan(a)
+        if ei.size == 0:
+            assert d.edge_index.numel() == 0
+            continue
+        assert np.array_equal(d.edge_index.numpy(), ei)
+        assert np.allclose(d.edge_attr.numpy(), ea.astype(np.float32))
+        assert d.x.dtype == torch.float32 and d.edge_index.dtype == torch.long
+
+
+def test_cost_and_targets():
+    dq = DeepQ()
+    pred = torch.tensor([[1.0], [2.0], [3.0]]); a = torch.tensor([0.0, 1.0, 0.0]); y = torch.tensor([0.0, 0.5, 0.0])
+    assert torch.isclose(dq.cost(pred, y, a), torch.tensor((2.0 - 0.5) ** 2 / 64))
+
+    class Net(torch.nn.Module):            # target net stand-in: Q = first feature
+        def forward(self, data, prob, batch=None):
+            return data.x[:, :1]
+
+    def graph(vals):
+        n = len(vals)
+        return Data(torch.tensor([[v, 0, 0, 0, 0] for v in vals], dtype=torch.float), torch.zeros(2, 0, dtype=torch.long), torch.zeros(0))
+
+    mb = [(graph([0, 0, 0]), np.array([0.0, 0, 1]), 0.25, graph([9, 1, 4, 2]), False, 2),     # max over last 2 nodes = 4
+          (graph([0, 0]), np.array([0.0, 1]), -1.0, graph([5, 7, 8]), True, 1)]                # terminal: y = r
+    _, a, y = dq.build_targets(mb, torch.device("cpu"), Net())
+    assert a.tolist() == [0, 0, 1, 0, 1]
+    assert np.allclose(y.numpy(), [0, 0, 0.25 + 0.99 * 4, 0, -1.0])
