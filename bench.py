@@ -75,74 +75,16 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------ CPU reference arm ---
-def cpu_reference(n_envs: int, n_ticks: int, threads: int, seed0: int = 0):
-    """The reference path on host cores: CPU oracle envs (single-threaded each, like the reference)
-    spread over `threads` host threads + the pure-PyTorch GCN restatement on CPU.  Same tick
-    structure as the GPU arm."""
-    from concurrent.futures import ThreadPoolExecutor
-
-    from drl_graph_exploration_b200.config import EnvConfig
-    from oracle import gnn_ref
-    from oracle.oracle import OracleEnv
-
-    cfg = EnvConfig(map_size=MAP_SIZE, num_landmarks=N_LANDMARKS)
-    torch.manual_seed(0)
-    model = gnn_ref.GCN().eval()
-    torch.set_num_threads(threads)
-    reset_odom = (1.0, 1.0, math.pi / 2)
-
-    def fresh(seed):
-        e = OracleEnv(cfg, seed, record_noise=False)
-        for _ in range(4):
-            e.step(reset_odom, record_noise=False)
-        return e
-
-    pool = ThreadPoolExecutor(max_workers=threads)
-    envs = list(pool.map(fresh, range(seed0, seed0 + n_envs)))
-    queues = [[] for _ in envs]
-    next_seed = seed0 + n_envs
-    steps = 0
-
-    def graph_of(i):
-        return envs[i].graph()
-
-    def step_env(i):
-        envs[i].step(queues[i].pop(0), record_noise=False)
-        return envs[i].metrics()["done"]
-
-    def run_tick():
-        nonlocal steps, next_seed
-        need = [i for i in range(n_envs) if not queues[i]]
-        if need:
-            graphs = list(pool.map(graph_of, need))
-            xs, eis, eas, off = [], [], [], 0
-            for g in graphs:
-                xs.append(torch.tensor(g["features"], dtype=torch.float32)); eis.append(torch.tensor(g["edge_index"]) + off)
-                eas.append(torch.tensor(g["edge_attr"], dtype=torch.float32)); off += g["n_nodes"]
-            with torch.no_grad():
-                q = model(gnn_ref.Graph(torch.cat(xs), torch.cat(eis, dim=1), torch.cat(eas)), 0.0).view(-1).numpy()
-            off = 0
-            for i, g in zip(need, graphs):
-                f = g["fro_size"]
-                if f > 0:
-                    a = int(np.argmax(q[off + g["key_size"]: off + g["n_nodes"]]))
-                    queues[i] = [tuple(r) for r in envs[i].line_plan(*g["frontier_xy"][a])]
-                else:
-                    queues[i] = [(0.0, 0.0, 0.5)]
-                off += g["n_nodes"]
-        dones = list(pool.map(step_env, range(n_envs)))
-        steps += n_envs
-        for i, d in enumerate(dones):
-            if d or envs[i].sizes()["T"] >= MAX_POSES - 1:
-                envs[i] = fresh(next_seed); next_seed += 1; queues[i] = []
-
-    return run_tick, lambda: steps
+def cpu_reference(*a, **k):
+    """The reference path on host cores (oracle/cpu_loop.py): CPU-oracle envs on a C++ worker pool + torch-CPU GCN."""
+    from oracle.cpu_loop import cpu_reference as impl
+    return impl(*a, **k)
 
 
 def run_reference(args):
     threads = os.cpu_count() or 1
     n_envs = min(ENVS_PER_GPU, max(threads, 8))
-    run_tick, count = cpu_reference(n_envs, 0, threads)
+    run_tick, count = cpu_reference(MAP_SIZE, N_LANDMARKS, n_envs, threads, MAX_POSES)
     for _ in range(args.warmup):
         run_tick()
     c0, t0 = count(), time.perf_counter()
@@ -150,7 +92,7 @@ def run_reference(args):
         run_tick()
     dt = time.perf_counter() - t0
     val = (count() - c0) / dt
-    sample = f"{n_envs} of {ENVS_PER_GPU} envs x {args.steps} ticks, oracle envs on {threads} host threads + torch-CPU GCN"
+    sample = f"{n_envs} of {ENVS_PER_GPU} envs x {args.steps} ticks, CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN"
     print(json.dumps({"impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -173,14 +115,13 @@ class GpuLoop:
         self.model = Networks.GCN().to(self.env.device).eval()
         self.env.reset()
         self.dev = self.env.device
-        self.flags = torch.zeros(2, dtype=torch.int64, device=self.dev)
-        self.flags_host = torch.zeros(2, dtype=torch.int64).pin_memory()
-        self.steps_dev = torch.zeros((), dtype=torch.int64, device=self.dev)
-        self.sumT_dev = torch.zeros((), dtype=torch.int64, device=self.dev)
-        self.sumM_dev = torch.zeros((), dtype=torch.int64, device=self.dev)
         self.launches = 0
         self.ev = {k: [] for k in ("slam", "vmap")}
         self.graphs = 0
+
+    def counters(self):
+        """(policy env-steps, sum of trajectory lengths, sum of measurement counts) accumulated by the engine."""
+        return [int(v) for v in self.env.eng.state["counters"].tolist()[:3]]
 
     @torch.no_grad()
     def tick(self, timed=False):
@@ -188,7 +129,9 @@ class GpuLoop:
         st = eng.state
         need = env.needs_decision()
         g = env.build_graph(need); self.launches += 3
-        ng, n, e = g.sync_sizes()
+        ng, n, e = g.sync_sizes()      # the tick's only host sync: graph sizes + number of finished episodes
+        if g.n_done > 0:               # episode ends: reset (4 forced steps) those envs, they decide next tick
+            env.reset_done(); self.launches += 2 + 4 * 5
         if ng > 0:
             l0 = self.gnn.launch_count
             q = self.model(g.data(), 0.0)
@@ -210,16 +153,6 @@ class GpuLoop:
             e2.record()
             self.ev["slam"].append((e0, e1)); self.ev["vmap"].append((e1, e2))
         self.launches += 5
-        act = st["active"].to(torch.int64)
-        self.steps_dev += act.sum()
-        self.sumT_dev += (act * st["n_poses"]).sum()
-        self.sumM_dev += (act * st["meas_ptr"].gather(1, st["n_poses"].long().view(-1, 1)).view(-1)).sum()
-        # episode ends: reset (4 forced steps) only when some env is done
-        self.flags[0] = st["done"].sum()
-        self.flags_host.copy_(self.flags, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
-        if int(self.flags_host[0]) > 0:
-            env.reset_done(); self.launches += 2 + 4 * 5
 
 
 def e2e_loop(loop: GpuLoop):
@@ -310,7 +243,7 @@ def main():
     if sampler:
         sampler.start()
     loop.launches = 0; loop.graphs = 0
-    loop.steps_dev.zero_(); loop.sumT_dev.zero_(); loop.sumM_dev.zero_()
+    c_start = loop.counters()
     tick_events = []
     for _ in range(args.steps):
         if flush is not None:
@@ -323,7 +256,8 @@ def main():
         dist.barrier()
     clocks = sampler.stop() if sampler else None
     total_ms = sum(a.elapsed_time(b) for a, b in tick_events)
-    steps_rank = int(loop.steps_dev.item())
+    c_end = loop.counters()
+    steps_rank, sumT, sumM = (c_end[i] - c_start[i] for i in range(3))
     t = torch.tensor([total_ms], dtype=torch.float64, device=loop.dev)
     s = torch.tensor([steps_rank, loop.graphs], dtype=torch.float64, device=loop.dev)
     if world > 1:
@@ -335,7 +269,7 @@ def main():
         pk, pk_kind = peaks()
         value = steps_all / (total_ms / 1e3)
         # roofline of the dominant simulator kernels (algorithmic fp64 bytes per SURVEY 8(d) x 2 for fp64)
-        T_mean = float(loop.sumT_dev.item()) / max(steps_rank, 1); M_mean = float(loop.sumM_dev.item()) / max(steps_rank, 1)
+        T_mean = sumT / max(steps_rank, 1); M_mean = sumM / max(steps_rank, 1)
         eng = loop.env.eng
         ms_slam = sum(a.elapsed_time(b) for a, b in loop.ev["slam"]) / max(len(loop.ev["slam"]), 1)
         ms_vmap = sum(a.elapsed_time(b) for a, b in loop.ev["vmap"]) / max(len(loop.ev["vmap"]), 1)
@@ -373,15 +307,16 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_envs = min(ENVS_PER_GPU, max(threads, 8))
-        run_tick, count = cpu_reference(n_envs, 0, threads, seed0=777)
-        run_tick()
+        run_tick, count = cpu_reference(MAP_SIZE, N_LANDMARKS, n_envs, threads, MAX_POSES, seed0=777)
+        for _ in range(3):
+            run_tick()
         c0, t0 = count(), time.perf_counter()
         nt = 0
-        while time.perf_counter() - t0 < 15.0 and nt < 400:
+        while time.perf_counter() - t0 < 15.0 and nt < 4000:
             run_tick(); nt += 1
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": (count() - c0) / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                               "sample": f"{n_envs} of {ENVS_PER_GPU} envs x {nt} ticks ({dt:.1f} s): CPU oracle envs on {threads} host threads + torch-CPU GCN"}
+                               "sample": f"{n_envs} of {ENVS_PER_GPU} envs x {nt} ticks ({dt:.1f} s): CPU CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN"}
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:

@@ -75,6 +75,7 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.plan = al.get<double>(B * 6); e.plan_cursor = al.get<int32_t>(B);
   e.odom_dev_scratch = al.get<double>(B * 3); e.mask_dev_scratch = al.get<uint8_t>(B);
   e.g_counts = al.get<int32_t>(B * 4); e.g_frontier = al.get<int32_t>(B * d.Fmax); e.g_fassoc = al.get<int32_t>(B * (L + 1)); e.g_sel = al.get<int32_t>(B);
+  e.counters = al.get<unsigned long long>(4); e.count_steps = 1;
   if (!al.ok) {
     for (void *p : al.ptrs) cudaFree(p);
     delete bx;
@@ -189,7 +190,7 @@ extern "C" int dge_get_state(dge_handle h, dge_state_view *o) {
   o->meas_ptr = h->meas_ptr; o->meas_id = h->meas_id; o->meas_bearing = h->meas_b; o->meas_range = h->meas_r;
   o->lm_true = h->lm_true; o->scan_id = h->scan_id; o->observed = h->observed; o->est_l = h->est_l; o->lin_l = h->lin_l;
   o->land_cov = h->land_cov; o->prob = h->prob; o->vinfo = h->vinfo; o->seen = h->seen; o->metrics = h->metrics; o->done = h->done; o->active = h->active; o->status = h->status;
-  o->plan = h->plan; o->plan_cursor = h->plan_cursor;
+  o->plan = h->plan; o->plan_cursor = h->plan_cursor; o->counters = reinterpret_cast<const int64_t *>(h->counters);
   return DGE_OK;
 }
 
@@ -211,4 +212,10 @@ extern "C" int dge_select_and_plan(dge_handle h, const dge_graph_out *g, const f
   if (!h || !g || !q) return DGE_EINVAL;
   const int rc = dge_launch_select_plan(h, g, q, mask, choice, static_cast<cudaStream_t>(stream));
   return rc ? fail(rc, "dge_select_and_plan") : DGE_OK;
+}
+
+extern "C" int dge_set_counting(dge_handle h, int on) {
+  if (!h) return DGE_EINVAL;
+  h->count_steps = on ? 1 : 0;
+  return DGE_OK;
 }

@@ -49,17 +49,16 @@ __global__ void k_fill(int E, const int64_t *key, const int32_t *rowptr, int32_t
   perm[rowptr[r] + atomicAdd(&cursor[r], 1)] = e;
 }
 
-// rows are short (degree ~2..T): per-row insertion sort by edge id => deterministic summation order
-__global__ void k_sort_rows(int N, const int32_t *rowptr, int32_t *perm) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= N) return;
+// deterministic summation order: every edge finds its rank inside its row (rows are short,
+// degree ~2..T), one thread per edge, and lands at rowptr[row] + rank  => rows sorted by edge id.
+__global__ void k_rank_rows(int E, const int64_t *key, const int32_t *rowptr, const int32_t *tmp, int32_t *perm) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int r = (int)key[e];
   const int lo = rowptr[r], hi = rowptr[r + 1];
-  for (int i = lo + 1; i < hi; ++i) {
-    const int v = perm[i];
-    int j = i - 1;
-    while (j >= lo && perm[j] > v) { perm[j + 1] = perm[j]; --j; }
-    perm[j + 1] = v;
-  }
+  int rank = 0;
+  for (int q = lo; q < hi; ++q) rank += (tmp[q] < e) ? 1 : 0;
+  perm[lo + rank] = e;
 }
 
 // ------------------------------------------------------------------ GCN norm ---
@@ -176,15 +175,16 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace
 
-extern "C" int dge_gnn_csr_build(int N, int E, const int64_t *key, int32_t *rowptr, int32_t *perm, int32_t *ws /*[2N]*/, void *stream) {
+extern "C" int dge_gnn_csr_build(int N, int E, const int64_t *key, int32_t *rowptr, int32_t *perm, int32_t *ws /*[2N+E]*/, void *stream) {
   if (N <= 0 || E < 0 || !key || !rowptr || !perm || !ws) return -1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(ws, 0, sizeof(int32_t) * 2 * (size_t)N, st) != cudaSuccess) return -2;
   if (E > 0) k_count<<<cdiv(E, 256), 256, 0, st>>>(E, key, ws);
   k_scan<<<1, 1024, 0, st>>>(N, ws, rowptr);
   if (E > 0) {
-    k_fill<<<cdiv(E, 256), 256, 0, st>>>(E, key, rowptr, ws + N, perm);
-    k_sort_rows<<<cdiv(N, 128), 128, 0, st>>>(N, rowptr, perm);
+    int32_t *tmp = ws + 2 * (size_t)N;
+    k_fill<<<cdiv(E, 256), 256, 0, st>>>(E, key, rowptr, ws + N, tmp);
+    k_rank_rows<<<cdiv(E, 256), 256, 0, st>>>(E, key, rowptr, tmp, perm);
   }
   return CK();
 }

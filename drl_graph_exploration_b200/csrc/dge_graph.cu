@@ -139,10 +139,30 @@ __global__ void __launch_bounds__(GT) k_graph_count(GraphArgs a, const uint8_t *
 }
 
 // -------------------------------------------------------------- pass 2: scan ---
-__global__ void k_graph_scan(int B, const uint8_t *mask, const int32_t *g_counts, int32_t *g_sel, dge_graph_out o) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int g = 0, n = 0, e = 0;
-  for (int b = 0; b < B; ++b) {
+// single CTA, 1024 threads: three exclusive scans (graph position, node offset, edge offset) over
+// the selected envs; each thread owns a contiguous chunk of envs, chunk totals by Hillis-Steele.
+__global__ void __launch_bounds__(1024) k_graph_scan(int B, const uint8_t *mask, const int32_t *g_counts, int32_t *g_sel, dge_graph_out o,
+                                                     const uint8_t *done) {
+  __shared__ int sg[1024], sn[1024], se[1024], sd[1024];
+  const int tid = threadIdx.x;
+  const int per = (B + 1023) / 1024;
+  const int lo = min(B, tid * per), hi = min(B, lo + per);
+  int g = 0, n = 0, e = 0, nd = 0;
+  for (int b = lo; b < hi; ++b) {
+    nd += done[b] ? 1 : 0;
+    if (!(mask && !mask[b])) { ++g; n += g_counts[4 * b]; e += g_counts[4 * b + 1]; }
+  }
+  sg[tid] = g; sn[tid] = n; se[tid] = e; sd[tid] = nd;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int vg = tid >= off ? sg[tid - off] : 0, vn = tid >= off ? sn[tid - off] : 0, ve = tid >= off ? se[tid - off] : 0,
+              vd = tid >= off ? sd[tid - off] : 0;
+    __syncthreads();
+    sg[tid] += vg; sn[tid] += vn; se[tid] += ve; sd[tid] += vd;
+    __syncthreads();
+  }
+  g = tid ? sg[tid - 1] : 0; n = tid ? sn[tid - 1] : 0; e = tid ? se[tid - 1] : 0;
+  for (int b = lo; b < hi; ++b) {
     if (mask && !mask[b]) { g_sel[b] = -1; continue; }
     g_sel[b] = g;
     o.node_ptr[g] = n; o.edge_ptr[g] = e;
@@ -150,9 +170,13 @@ __global__ void k_graph_scan(int B, const uint8_t *mask, const int32_t *g_counts
     n += g_counts[4 * b]; e += g_counts[4 * b + 1];
     ++g;
   }
-  o.node_ptr[g] = n; o.edge_ptr[g] = e;
-  o.totals[0] = g; o.totals[1] = n; o.totals[2] = e;
-  o.totals[3] = (n > o.node_cap || e > o.edge_cap) ? 1 : 0;
+  if (tid == 1023) {
+    const int G = sg[1023], N = sn[1023], E = se[1023];
+    o.node_ptr[G] = N; o.edge_ptr[G] = E;
+    o.totals[0] = G; o.totals[1] = N; o.totals[2] = E;
+    o.totals[3] = (N > o.node_cap || E > o.edge_cap) ? 1 : 0;
+    o.totals[4] = sd[1023];   // envs whose episode is over (lets the host fold the reset check into the same D2H)
+  }
 }
 
 // -------------------------------------------------------------- pass 3: fill ---
@@ -335,7 +359,7 @@ int dge_launch_graph(dge_engine *e, const uint8_t *mask, const dge_graph_out *ou
   const GraphArgs a = make_gargs(e);
   const size_t sm1 = ((e->d.V + 15) / 16) * 16 + (2 * e->d.Lt + 2) * sizeof(int);
   k_graph_count<<<e->d.B, GT, sm1, st>>>(a, mask);
-  k_graph_scan<<<1, 32, 0, st>>>(e->d.B, mask, e->g_counts, e->g_sel, *out);
+  k_graph_scan<<<1, 1024, 0, st>>>(e->d.B, mask, e->g_counts, e->g_sel, *out, e->done);
   const size_t sm3 = (4 * e->d.Lt + 4) * sizeof(int);
   k_graph_fill<<<e->d.B, GT, sm3, st>>>(a, *out);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;

@@ -62,6 +62,8 @@ struct dge_engine {
   int32_t *g_frontier;   // [B,Fmax] frontier cell index
   int32_t *g_fassoc;     // [B,Lt+1] node -> frontier association (-1 none): slot 0 robot, 1+i landmark rank i
   int32_t *g_sel;        // [B] position of the env among the selected graphs (-1 = not selected)
+  unsigned long long *counters;   // [4] work counters: policy env-steps, sum of T, sum of M, reserved
+  int count_steps;       // host flag: 1 while stepping on behalf of the policy (reset steps are not counted)
 };
 
 // ------------------------------------------------------------- device math ---

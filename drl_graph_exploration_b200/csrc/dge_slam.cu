@@ -315,23 +315,42 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
 
   // ---------------------------------------------------------------- phase C ---
   // Sigma_ll = S^-1 (in-place Gauss-Jordan on the SPD Schur complement), dl = Sigma_ll gl
+  // Thread (c, h): column c = tid % 64 (+64 for a second pass when n2 > 64), rows r = h mod 2.
+  // The inner loop is a chain of shared-memory round trips, so loads are batched 6 rows at a time.
   for (int p = 0; p < n2; ++p) {
     if (tid < n2) colp[tid] = S[tid * n2 + p];
     __syncthreads();
     const double pv = colp[p];
     if (tid == 0 && !(pv > 0.0)) s_bad = 1;
     const double piv = 1.0 / pv;
-    if (tid < n2) {
-      const int c = tid;
+    const int h = tid >> 6;
+    for (int c = tid & 63; c < n2; c += 64) {
+      double *__restrict__ Sc = S + c;
+      const double *__restrict__ cp = colp;
       if (c == p) {
-        for (int r = 0; r < n2; ++r) S[r * n2 + p] = (r == p) ? piv : -colp[r] * piv;
+        for (int r = h; r < n2; r += 2) Sc[r * n2] = (r == p) ? piv : -cp[r] * piv;
       } else {
-        const double rowpc = S[p * n2 + c] * piv;
-        for (int r = 0; r < n2; ++r)
-          if (r != p) S[r * n2 + c] -= colp[r] * rowpc;
-        S[p * n2 + c] = rowpc;
+        const double rowpc = Sc[p * n2] * piv;
+        int r = h;
+        for (; r + 10 < n2; r += 12) {
+          double s0 = Sc[r * n2], s1 = Sc[(r + 2) * n2], s2 = Sc[(r + 4) * n2], s3 = Sc[(r + 6) * n2], s4 = Sc[(r + 8) * n2], s5 = Sc[(r + 10) * n2];
+          const double c0 = cp[r], c1 = cp[r + 2], c2 = cp[r + 4], c3 = cp[r + 6], c4 = cp[r + 8], c5 = cp[r + 10];
+          s0 -= c0 * rowpc; s1 -= c1 * rowpc; s2 -= c2 * rowpc; s3 -= c3 * rowpc; s4 -= c4 * rowpc; s5 -= c5 * rowpc;
+          if (r != p) Sc[r * n2] = s0;
+          if (r + 2 != p) Sc[(r + 2) * n2] = s1;
+          if (r + 4 != p) Sc[(r + 4) * n2] = s2;
+          if (r + 6 != p) Sc[(r + 6) * n2] = s3;
+          if (r + 8 != p) Sc[(r + 8) * n2] = s4;
+          if (r + 10 != p) Sc[(r + 10) * n2] = s5;
+        }
+        for (; r < n2; r += 2)
+          if (r != p) Sc[r * n2] -= cp[r] * rowpc;
       }
     }
+    __syncthreads();
+    // row p of the non-pivot columns (written after every thread has finished reading it)
+    for (int c = tid; c < n2; c += NT)
+      if (c != p) S[p * n2 + c] *= piv;
     __syncthreads();
   }
   if (tid < n2) {

@@ -181,9 +181,16 @@ __global__ void __launch_bounds__(TILE * TILE) k_vmap_cells(VmapCfg c, int Tstri
 // known-cell count, done flag (exploration_env.py:167-168).
 __global__ void __launch_bounds__(256) k_vmap_metrics(dge_config cfg, DgeDims d, const double *prob, const double *vinfo,
                                                       const int32_t *sim_step, const int32_t *status, const double *dist,
-                                                      double *metrics, uint8_t *done, const uint8_t *mask) {
+                                                      double *metrics, uint8_t *done, const uint8_t *mask,
+                                                      const int32_t *n_poses, const int32_t *meas_ptr, unsigned long long *counters) {
   const int b = blockIdx.x;
   if (mask && !mask[b]) return;
+  if (threadIdx.x == 0 && counters) {   // integer work counters (order-independent): env-steps, sum T, sum M
+    const int T = n_poses[b];
+    atomicAdd(&counters[0], 1ull);
+    atomicAdd(&counters[1], (unsigned long long)T);
+    atomicAdd(&counters[2], (unsigned long long)meas_ptr[(size_t)b * (d.Tmax + 1) + T]);
+  }
   const double *p = prob + (size_t)b * d.V, *vi = vinfo + (size_t)b * d.V * 3;
   const int extg = 20;
   int n_exp = 0, n_known = 0;
@@ -253,7 +260,8 @@ int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
   const int tiles = ((e->d.cols + TILE - 1) / TILE) * ((e->d.rows + TILE - 1) / TILE);
   k_vmap_cells<<<dim3(tiles, e->d.B), TILE * TILE, 0, st>>>(c, e->d.Tmax, e->n_poses, 0, e->vm_prep, e->vm_cbox, nchm, e->est_l, e->observed,
                                                              e->d.Lt, e->d.Lt, e->prob, e->vinfo, e->seen, mask);
-  k_vmap_metrics<<<e->d.B, 256, 0, st>>>(e->cfg, e->d, e->prob, e->vinfo, e->sim_step, e->status, e->dist, e->metrics, e->done, mask);
+  k_vmap_metrics<<<e->d.B, 256, 0, st>>>(e->cfg, e->d, e->prob, e->vinfo, e->sim_step, e->status, e->dist, e->metrics, e->done, mask,
+                                         e->n_poses, e->meas_ptr, e->count_steps ? e->counters : nullptr);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }
 

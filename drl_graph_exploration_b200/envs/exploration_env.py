@@ -65,18 +65,18 @@ class GraphBatch:
         self.key_size = torch.zeros(eng.B, dtype=torch.int32, device=dev)
         self.fro_size = torch.zeros(eng.B, dtype=torch.int32, device=dev)
         self.frontier_xy = torch.zeros(eng.B, eng.Lt + 1, 2, dtype=torch.float64, device=dev)
-        self.totals = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.totals_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.totals = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.totals_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self.c = GraphOut(self.x.data_ptr(), self.edge_index.data_ptr(), self.edge_attr.data_ptr(), self.batch.data_ptr(),
                           self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.key_size.data_ptr(), self.fro_size.data_ptr(),
                           self.frontier_xy.data_ptr(), self.totals.data_ptr(), self.node_cap, self.edge_cap)
-        self.n_graphs = self.n_nodes = self.n_edges = 0
+        self.n_graphs = self.n_nodes = self.n_edges = self.n_done = 0
 
     def sync_sizes(self):
         """One small D2H (pinned) so the host can size the dense GEMMs of the GNN."""
         self.totals_host.copy_(self.totals, non_blocking=True)
         torch.cuda.current_stream(self.x.device).synchronize()
-        g, n, e, ovf = self.totals_host.tolist()
+        g, n, e, ovf, self.n_done = self.totals_host.tolist()[:5]
         if ovf:
             raise DgeError("graph batch capacity exceeded")
         self.n_graphs, self.n_nodes, self.n_edges = g, n, e
@@ -118,9 +118,11 @@ class VecExplorationEnv:
         if reference_worlds:
             sp = np.array([start_pose_for_seed(int(s), self.map_size, self.cfg.ext) for s in self._seeds.tolist()], dtype=np.float64)
             start = torch.as_tensor(sp, device=self.device)
+        eng._L.dge_set_counting(eng._h, 0)          # the 4 forced steps are not policy steps
         eng.reset(self._seeds, mask=mask, start=start)
         for _ in range(4):
             eng.step(self._reset_odom, mask=mask)
+        eng._L.dge_set_counting(eng._h, 1)
         return eng.state["prob"]
 
     def reset_done(self):

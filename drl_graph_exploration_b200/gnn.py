@@ -65,7 +65,7 @@ class GraphStructure:
         i32 = dict(dtype=torch.int32, device=dev)
         self.rowptr_dst, self.perm_dst = torch.empty(self.N + 1, **i32), torch.empty(max(self.E, 1), **i32)
         self.rowptr_src, self.perm_src = torch.empty(self.N + 1, **i32), torch.empty(max(self.E, 1), **i32)
-        ws = torch.empty(2 * self.N, **i32)
+        ws = torch.empty(2 * self.N + self.E, **i32)
         with torch.cuda.device(dev):
             for key, rp, pm in ((self.dst, self.rowptr_dst, self.perm_dst), (self.src, self.rowptr_src, self.perm_src)):
                 rc = L.dge_gnn_csr_build(self.N, self.E, _p(key), _p(rp), _p(pm), _p(ws), _st(dev))

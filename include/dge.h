@@ -143,8 +143,12 @@ typedef struct dge_state_view {
   const int32_t *status;         /* [B] 0 ok, DGE_ECAP, or 1 = solver breakdown       */
   const double *plan;            /* [B,6] queued line plan (see dge_line_plan)        */
   const int32_t *plan_cursor;    /* [B] next action of the plan                       */
+  const int64_t *counters;       /* [4] work counters: env-steps, sum of trajectory lengths, sum of
+                                    measurement counts over those steps, reserved            */
 } dge_state_view;
 int dge_get_state(dge_handle h, dge_state_view *out);
+/* steps launched while counting is off (e.g. the 4 forced steps of a reset) do not touch `counters` */
+int dge_set_counting(dge_handle h, int on);
 
 /* ---- exploration graph: replaces ExplorationEnv.graph_matrix + frontier
  * (exploration_env.py:196-358), SLAM2D.adjacency_degree_get / key_size / get_key_points
@@ -162,7 +166,7 @@ typedef struct dge_graph_out {
   int32_t *fro_size;       /* [B]       F                                               */
   double *frontier_xy;     /* [B,Fmax,2] goal coordinates of frontier f (indexed by ENV, not by
                               graph position), Fmax = Lt+1                              */
-  int32_t *totals;         /* [4]: n_graphs, N_tot, E_tot, overflow flag                */
+  int32_t *totals;         /* [8]: n_graphs, N_tot, E_tot, overflow flag, #envs done, 0, 0, 0   */
   int64_t node_cap, edge_cap;
 } dge_graph_out;
 int dge_graph(dge_handle h, const uint8_t *mask_dev, const dge_graph_out *out, void *stream);

@@ -18,7 +18,7 @@ extern "C" {
 
 /* Deterministic CSR of E edges grouped by key[e] in [0,N) (key = edge_index[1] for the
  * forward gather, edge_index[0] for the transposed/backward gather); rows sorted by edge id.
- * rowptr [N+1], perm [E], ws [2N] scratch. */
+ * rowptr [N+1], perm [E], ws [2N+E] scratch. */
 int dge_gnn_csr_build(int N, int E, const int64_t *key, int32_t *rowptr, int32_t *perm, int32_t *ws, void *stream);
 
 /* GCNConv.norm(improved: fill = 2): dis [N] = deg^-1/2, selfw [N] self-loop weight,

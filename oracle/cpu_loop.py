@@ -1,0 +1,75 @@
+"""The reference path on host cores, tick-structured like the GPU arm of bench.py:
+CPU-oracle envs (each single-threaded, like the reference) spread over a persistent C++ worker
+pool + the pure-PyTorch GCN restatement on CPU.  TEST INFRASTRUCTURE (bench.py cpu_baseline /
+--impl reference only)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from drl_graph_exploration_b200.config import EnvConfig, start_pose_for_seed
+from oracle import gnn_ref
+from oracle.oracle import lib as _lib
+
+MAX_ACTIONS = 64
+
+
+def cpu_reference(map_size: int, n_landmarks: int, n_envs: int, threads: int, max_poses: int, seed0: int = 0, gnn_threads: int | None = None):
+    cfg = EnvConfig(map_size=map_size, num_landmarks=n_landmarks)
+    L = _lib()
+    cs = cfg.to_struct()
+    torch.manual_seed(0)
+    model = gnn_ref.GCN().eval()
+    torch.set_num_threads(gnn_threads or min(threads, 32))
+    vp = ctypes.c_void_p
+    handles = (vp * n_envs)(*[L.orc_create(ctypes.byref(cs)) for _ in range(n_envs)])
+    p = lambda a: a.ctypes.data_as(vp)
+    state = {"next_seed": seed0, "steps": 0}
+
+    def fresh(idx):
+        idx = np.asarray(idx, dtype=np.int64)
+        seeds = np.arange(state["next_seed"], state["next_seed"] + len(idx), dtype=np.uint32)
+        state["next_seed"] += len(idx)
+        starts = np.array([start_pose_for_seed(int(s), map_size, cfg.ext) for s in seeds], dtype=np.float64)
+        hs = (vp * len(idx))(*[handles[i] for i in idx])
+        L.orc_batch_fresh(hs, p(seeds), p(starts), len(idx), threads)
+
+    fresh(range(n_envs))
+    queues = [[] for _ in range(n_envs)]
+    odoms = np.zeros((n_envs, 3)); done = np.zeros(n_envs, dtype=np.uint8); Ts = np.zeros(n_envs, dtype=np.int32)
+
+    def run_tick():
+        need = [i for i in range(n_envs) if not queues[i]]
+        if need:
+            hs = (vp * len(need))(*[handles[i] for i in need])
+            sizes = np.zeros((len(need), 4), dtype=np.int32)
+            L.orc_batch_graph_build(hs, len(need), threads, p(sizes))
+            ntot, etot = int(sizes[:, 0].sum()), int(sizes[:, 3].sum())
+            x = np.zeros((ntot, 5), dtype=np.float32); ei = np.zeros((2, etot), dtype=np.int64); ea = np.zeros(etot, dtype=np.float32)
+            L.orc_batch_graph_fetch(len(need), p(x), p(ei), p(ea), ctypes.c_int64(etot))
+            with torch.no_grad():
+                q = model(gnn_ref.Graph(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ea)), 0.0).view(-1).numpy()
+            choice = np.full(len(need), -1, dtype=np.int32)
+            off = 0
+            for k in range(len(need)):
+                n, K, F = sizes[k, 0], sizes[k, 1], sizes[k, 2]
+                if F > 0:
+                    choice[k] = int(np.argmax(q[off + K: off + n]))
+                off += n
+            plans = np.zeros((len(need), MAX_ACTIONS, 3)); counts = np.zeros(len(need), dtype=np.int32)
+            L.orc_batch_line_plan(hs, len(need), p(choice), MAX_ACTIONS, p(plans), p(counts))
+            for k, i in enumerate(need):
+                queues[i] = [plans[k, a] for a in range(counts[k])] if counts[k] > 0 else [np.array([0.0, 0.0, 0.5])]
+        for i in range(n_envs):
+            odoms[i] = queues[i].pop(0)
+        L.orc_batch_step(handles, p(odoms), n_envs, threads, p(done), p(Ts))
+        state["steps"] += n_envs
+        redo = [i for i in range(n_envs) if done[i] or Ts[i] >= max_poses - 1]
+        if redo:
+            fresh(redo)
+            for i in redo:
+                queues[i] = []
+
+    return run_tick, (lambda: state["steps"])

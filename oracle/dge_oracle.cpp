@@ -70,7 +70,11 @@ static inline void predict_br(const Pose &p, double lx, double ly, double &beari
 // --------------------------------------------------------- small matrices ---
 // Utils.h:29-33 : inverse<N> = m.llt().solve(Identity)
 static bool chol_inv(int n, const double *A, double *Ainv) {
-  std::vector<double> L(n * n, 0.0);
+  // fixed-size path (2x2 / 3x3, like Eigen's fixed-size LLT in the reference): no heap traffic
+  double Lsmall[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ysmall[3];
+  std::vector<double> Lbig, ybig;
+  double *L = Lsmall, *y = ysmall;
+  if (n > 3) { Lbig.assign(static_cast<size_t>(n) * n, 0.0); ybig.resize(n); L = Lbig.data(); y = ybig.data(); }
   for (int i = 0; i < n; ++i)
     for (int j = 0; j <= i; ++j) {
       double s = A[i * n + j];
@@ -82,7 +86,6 @@ static bool chol_inv(int n, const double *A, double *Ainv) {
         L[i * n + j] = s / L[j * n + j];
       }
     }
-  std::vector<double> y(n);
   for (int col = 0; col < n; ++col) {
     for (int i = 0; i < n; ++i) {
       double s = (i == col) ? 1.0 : 0.0;

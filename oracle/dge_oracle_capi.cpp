@@ -2,7 +2,12 @@
 // dge_oracle_capi.cpp -- flat C API over the CPU ORACLE for ctypes.
 // TEST INFRASTRUCTURE ONLY (see dge_oracle.hpp).  Loaded by oracle/oracle.py.
 // ============================================================================
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -158,5 +163,106 @@ void orc_virtual_map_rebuild_batch(const orc::Config *cfg, int n, int threads, i
 }
 
 int orc_sizeof_config() { return static_cast<int>(sizeof(orc::Config)); }
+
+}  // extern "C"
+
+
+namespace {
+// persistent worker pool (libgomp is not available in this image)
+class Pool {
+ public:
+  explicit Pool(int n) { for (int i = 0; i < n; ++i) th_.emplace_back([this] { work(); }); }
+  ~Pool() { { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; } cv_.notify_all(); for (auto &t : th_) t.join(); }
+  void run(int n, const std::function<void(int)> &f) {
+    std::unique_lock<std::mutex> l(m_);
+    fn_ = &f; n_ = n; next_.store(0); pending_ = static_cast<int>(th_.size()); ++gen_;
+    cv_.notify_all();
+    done_.wait(l, [this] { return pending_ == 0; });
+  }
+  int size() const { return static_cast<int>(th_.size()); }
+ private:
+  void work() {
+    int seen = 0;
+    for (;;) {
+      { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return gen_ != seen; }); seen = gen_; if (stop_) return; }
+      for (int i; (i = next_.fetch_add(1)) < n_;) (*fn_)(i);
+      { std::lock_guard<std::mutex> l(m_); if (--pending_ == 0) done_.notify_one(); }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)> *fn_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_ = 0, gen_ = 0, pending_ = 0;
+  bool stop_ = false;
+};
+Pool &pool(int threads) {
+  static Pool *p = nullptr;
+  if (!p || p->size() != threads) { delete p; p = new Pool(threads); }
+  return *p;
+}
+}  // namespace
+// ---------------------------------------------------------------------------------------
+// Batched drivers for the CPU baseline (bench.py cpu_baseline / --impl reference): each env is
+// stepped single-threaded exactly like the reference; independent envs are spread over host
+// threads with a persistent worker pool so that Python is off the per-env path.
+extern "C" {
+
+// odoms [n,3]; out_done [n] (1 = episode finished), out_T [n] trajectory length
+void orc_batch_step(void **hs, const double *odoms, int n, int threads, uint8_t *out_done, int32_t *out_T) {
+  pool(threads).run(n, [&](int i) {
+    Env *e = static_cast<Env *>(hs[i]);
+    try { e->step(odoms + 3 * i, nullptr); } catch (...) { out_done[i] = 1; out_T[i] = e->T; return; }
+    out_done[i] = e->done() ? 1 : 0;
+    out_T[i] = e->T;
+  });
+}
+
+static std::vector<orc::GraphOut> g_batch_graphs;
+// builds the graphs of n envs in parallel; sizes [n,4] = N, K, F, E per env
+void orc_batch_graph_build(void **hs, int n, int threads, int32_t *sizes) {
+  g_batch_graphs.resize(n);
+  pool(threads).run(n, [&](int i) {
+    static_cast<Env *>(hs[i])->graph(g_batch_graphs[i]);
+    sizes[4 * i] = g_batch_graphs[i].n_nodes; sizes[4 * i + 1] = g_batch_graphs[i].key_size;
+    sizes[4 * i + 2] = g_batch_graphs[i].fro_size; sizes[4 * i + 3] = static_cast<int32_t>(g_batch_graphs[i].edge_src.size());
+  });
+}
+// concatenated (PyG DataLoader layout): x [Ntot,5] f32, edge_index [2,Etot] i64 (offset), edge_attr [Etot] f32
+void orc_batch_graph_fetch(int n, float *x, int64_t *edge_index, float *edge_attr, int64_t Etot) {
+  int64_t noff = 0, eoff = 0;
+  for (int i = 0; i < n; ++i) {
+    const orc::GraphOut &g = g_batch_graphs[i];
+    for (size_t k = 0; k < g.features.size(); ++k) x[noff * 5 + k] = static_cast<float>(g.features[k]);
+    for (size_t k = 0; k < g.edge_src.size(); ++k) {
+      edge_index[eoff + k] = g.edge_src[k] + noff; edge_index[Etot + eoff + k] = g.edge_dst[k] + noff;
+      edge_attr[eoff + k] = static_cast<float>(g.edge_w[k]);
+    }
+    noff += g.n_nodes; eoff += static_cast<int64_t>(g.edge_src.size());
+  }
+}
+// line plans towards frontier `choice[i]` of the graphs built by orc_batch_graph_build:
+// out [n,max_actions,3], counts [n]
+void orc_batch_line_plan(void **hs, int n, const int32_t *choice, int max_actions, double *out, int32_t *counts) {
+  for (int i = 0; i < n; ++i) {
+    const orc::GraphOut &g = g_batch_graphs[i];
+    if (g.fro_size <= 0 || choice[i] < 0) { counts[i] = 0; continue; }
+    const std::vector<orc::Pose> a = static_cast<Env *>(hs[i])->line_plan(g.frontier_xy[2 * choice[i]], g.frontier_xy[2 * choice[i] + 1]);
+    counts[i] = static_cast<int32_t>(std::min<size_t>(a.size(), max_actions));
+    for (int k = 0; k < counts[i]; ++k) { out[(static_cast<size_t>(i) * max_actions + k) * 3] = a[k].x; out[(static_cast<size_t>(i) * max_actions + k) * 3 + 1] = a[k].y; out[(static_cast<size_t>(i) * max_actions + k) * 3 + 2] = a[k].th; }
+  }
+}
+// fresh envs (SS2D.__init__ + the 4 forced steps of ExplorationEnv.reset) in parallel; starts [n,3]
+void orc_batch_fresh(void **hs, const uint32_t *seeds, const double *starts, int n, int threads) {
+  const double o[3] = {1.0, 1.0, 1.57079632679489661923};
+  pool(threads).run(n, [&](int i) {
+    Env *e = static_cast<Env *>(hs[i]);
+    try {
+      e->init(seeds[i], orc::Pose{starts[3 * i], starts[3 * i + 1], starts[3 * i + 2]}, nullptr);
+      for (int k = 0; k < 4; ++k) e->step(o, nullptr);
+    } catch (...) {}
+  });
+}
 
 }  // extern "C"

@@ -55,10 +55,10 @@ def compare_state(cfg, eng, oracles, step_tag, check_map=True):
             ok = ~border
             assert np.array_equal(st["seen"][b][ok], vm["seen"][ok]), f"{step_tag} env {b}: visibility counts"
             assert np.array_equal(st["prob"][b][ok], vm["prob"][ok]), f"{step_tag} env {b}: occupancy (bit-exact)"
-            _close(sym3_to_full(st["vinfo"][b])[ok], vm["info"][ok], RTOL, 1e-10, f"{step_tag} env {b} cell information")
+            _close(sym3_to_full(st["vinfo"][b])[ok], vm["info"][ok], 1e-4, 1e-10, f"{step_tag} env {b} cell information (CI fold: contract tolerance 1e-4; the weight (2b-c)/(2d) cancels)")
             if not border.any():
                 _close(st["metrics"][b, 0], m["explored"], 1e-12, 0, "explored")
-                _close(st["metrics"][b, 1], m["utility0"], RTOL, 1e-9, "utility")
+                _close(st["metrics"][b, 1], m["utility0"], 1e-5, 1e-9, "utility")
                 assert bool(st["done"][b]) == m["done"]
     return n_border
 

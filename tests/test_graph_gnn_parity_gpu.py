@@ -68,8 +68,10 @@ def test_graph_matches_oracle(map_size, n_lm):
             assert np.allclose(g["edge_attr"], r["edge_attr"].astype(np.float32), rtol=2e-7, atol=0)
             assert np.array_equal(fxy_all[b, :r["fro_size"]], r["frontier_xy"]), "frontier cells"
             ref_x = r["features"].astype(np.float32)
+            K, F = r["key_size"], r["fro_size"]
             assert np.array_equal(g["x"][:, 4], ref_x[:, 4]) and np.array_equal(g["x"][:, 3], ref_x[:, 3])
-            assert np.allclose(g["x"][:, :3], ref_x[:, :3], rtol=3e-6, atol=1e-6)
+            assert np.allclose(g["x"][:, 1:3], ref_x[:, 1:3], rtol=3e-6, atol=1e-6)
+            assert np.allclose(g["x"][:K, 0], ref_x[:K, 0], rtol=3e-6, atol=1e-9) and np.allclose(g["x"][K:, 0], ref_x[K:, 0], rtol=1e-4)  # frontier trace comes from the CI fold
             # policy read-out + line plan
             K, F = r["key_size"], r["fro_size"]
             a = int(np.argmax(qh[nptr[b] + K: nptr[b] + K + F]))
