@@ -66,7 +66,7 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.meas_ptr = al.get<int32_t>(B * (T + 1)); e.meas_id = al.get<int32_t>(B * M); e.meas_pose = al.get<int32_t>(B * M); e.meas_b = al.get<double>(B * M); e.meas_r = al.get<double>(B * M);
   e.observed = al.get<uint8_t>(B * L); e.lin_l = al.get<double>(B * L * 2); e.est_l = al.get<double>(B * L * 2); e.delta_l = al.get<double>(B * L * 2);
   e.land_cov = al.get<double>(B * L * 3);
-  e.ws_pose = al.get<double>(B * T * 48); e.ws_meas = al.get<double>(B * M * 5);
+  e.ws_pose = al.get<double>(B * T * 48); e.ws_meas = al.get<double>(B * M * 14);
   e.ws_Bt = al.get<double>(B * T * 3 * 2 * L); e.ws_FB = al.get<double>(B * T * 3 * 2 * L); e.ws_midx = al.get<int32_t>(B * T * L);
   e.vm_prep = al.get<double>(B * T * dge_vmap_prep_width()); e.vm_cbox = al.get<double>(B * (size_t)dge_vmap_nchunk(d.Tmax) * 4);
   e.seen = al.get<int32_t>(B * V); e.active = al.get<uint8_t>(B);
@@ -75,7 +75,9 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.plan = al.get<double>(B * 6); e.plan_cursor = al.get<int32_t>(B);
   e.odom_dev_scratch = al.get<double>(B * 3); e.mask_dev_scratch = al.get<uint8_t>(B);
   e.g_counts = al.get<int32_t>(B * 4); e.g_frontier = al.get<int32_t>(B * d.Fmax); e.g_fassoc = al.get<int32_t>(B * (L + 1)); e.g_sel = al.get<int32_t>(B);
-  e.counters = al.get<unsigned long long>(4); e.count_steps = 1;
+  e.slam_clocks = al.get<long long>(B * 8);
+  e.counters = al.get<unsigned long long>(4); e.count_steps = 1; e.park_done = 1;
+  e.rdist = al.get<double>(B); e.r_cmap = al.get<int32_t>(B * 2); e.r_cbase = al.get<int32_t>(B); e.r_u0 = al.get<double>(B);
   if (!al.ok) {
     for (void *p : al.ptrs) cudaFree(p);
     delete bx;
@@ -143,6 +145,16 @@ extern "C" int dge_step(dge_handle h, const double *odom, const uint8_t *mask, c
   return DGE_OK;
 }
 
+extern "C" int dge_step_queued_noise(dge_handle h, const double *noise, void *stream) {
+  if (!h) return DGE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = dge_launch_move_measure(h, nullptr, nullptr, noise, h->park_done ? 1 : 2, st);
+  if (rc) return fail(rc, "dge_step_queued_noise: move_measure");
+  if ((rc = dge_launch_slam(h, h->active, st))) return fail(rc, "dge_step_queued_noise: slam");
+  if ((rc = dge_launch_vmap(h, h->active, st))) return fail(rc, "dge_step_queued_noise: vmap");
+  return DGE_OK;
+}
+
 extern "C" int dge_step_queued(dge_handle h, void *stream) {
   if (!h) return DGE_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -190,7 +202,7 @@ extern "C" int dge_get_state(dge_handle h, dge_state_view *o) {
   o->meas_ptr = h->meas_ptr; o->meas_id = h->meas_id; o->meas_bearing = h->meas_b; o->meas_range = h->meas_r;
   o->lm_true = h->lm_true; o->scan_id = h->scan_id; o->observed = h->observed; o->est_l = h->est_l; o->lin_l = h->lin_l;
   o->land_cov = h->land_cov; o->prob = h->prob; o->vinfo = h->vinfo; o->seen = h->seen; o->metrics = h->metrics; o->done = h->done; o->active = h->active; o->status = h->status;
-  o->plan = h->plan; o->plan_cursor = h->plan_cursor; o->counters = reinterpret_cast<const int64_t *>(h->counters);
+  o->plan = h->plan; o->plan_cursor = h->plan_cursor; o->counters = reinterpret_cast<const int64_t *>(h->counters); o->slam_clocks = reinterpret_cast<const int64_t *>(h->slam_clocks);
   return DGE_OK;
 }
 

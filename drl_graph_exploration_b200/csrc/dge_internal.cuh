@@ -62,8 +62,14 @@ struct dge_engine {
   int32_t *g_frontier;   // [B,Fmax] frontier cell index
   int32_t *g_fassoc;     // [B,Lt+1] node -> frontier association (-1 none): slot 0 robot, 1+i landmark rank i
   int32_t *g_sel;        // [B] position of the env among the selected graphs (-1 = not selected)
+  double *rdist;         // [B] roll-out distance: sum of sqrt(x^2 + y^2 + angle_weight*theta^2) over executed actions
+  int32_t *r_cmap;       // [B,2] (as roll-out engine) source env / frontier of each clone slot
+  int32_t *r_cbase;      // [B]   (as source engine) first clone slot of each env
+  double *r_u0;          // [B]   (as roll-out engine) utility before the roll-out
   unsigned long long *counters;   // [4] work counters: policy env-steps, sum of T, sum of M, reserved
+  long long *slam_clocks; // [B,8] phase-boundary clocks of the last k_slam launch (+ T in slot 7)
   int count_steps;       // host flag: 1 while stepping on behalf of the policy (reset steps are not counted)
+  int park_done;         // host flag: queued stepping skips `done` envs (1, default) or runs every plan to its end (0, roll-out engines)
 };
 
 // ------------------------------------------------------------- device math ---

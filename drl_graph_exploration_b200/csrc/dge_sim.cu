@@ -23,7 +23,7 @@ struct SimArgs {
   double *meas_b, *meas_r;
   uint8_t *observed;
   double *lin_l, *est_l, *delta_l;
-  double *prob, *vinfo, *metrics, *dist, *plan;
+  double *prob, *vinfo, *metrics, *dist, *rdist, *plan;
   int32_t *plan_cursor;
   uint8_t *done, *active;
 };
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(32) k_reset(SimArgs a, const uint8_t *mask, co
     a.delta_pose[p0] = 0; a.delta_pose[p0 + 1] = 0; a.delta_pose[p0 + 2] = 0;
     a.n_poses[b] = 1; a.sim_step[b] = 1; a.update_count[b] = 0; a.status[b] = 0;
     a.meas_ptr[(size_t)b * (a.d.Tmax + 1)] = 0;
-    a.dist[b] = 0; a.done[b] = 0; a.active[b] = 1;
+    a.dist[b] = 0; a.rdist[b] = 0; a.done[b] = 0; a.active[b] = 1;
     for (int i = 0; i < 6; ++i) a.plan[6 * b + i] = 0;
     a.plan_cursor[b] = 0;
   }
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
   if (act && T >= a.d.Tmax) { act = false; if (lane == 0) { a.status[b] = DGE_ECAP; a.done[b] = 1; } }
   // (like the reference, a finished episode can still be stepped explicitly; only the queued
   //  mode parks `done` envs until the caller resets them)
-  if (act && from_queue && a.done[b]) act = false;
+  if (act && from_queue == 1 && a.done[b]) act = false;   // from_queue == 2: roll-out clones run their whole plan
   if (lane == 0) a.active[b] = act ? 1 : 0;
   if (!act) return;
   const uint64_t key = a.seed[b];
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
     a.n_poses[b] = T + 1;
     a.sim_step[b] += 1;
     a.dist[b] += sqrt(ox * ox + oy * oy);  // exploration_env.py:103
+    a.rdist[b] += sqrt(ox * ox + oy * oy + a.cfg.angle_weight * oth * oth);   // Planner2D.cpp:1440 (roll-out distance)
     if (from_queue) a.plan_cursor[b] += 1;
   }
   __syncwarp();
@@ -219,7 +220,7 @@ SimArgs make_args(dge_engine *e, uint8_t *active) {
   a.lin_pose = e->lin_pose; a.est_pose = e->est_pose; a.delta_pose = e->delta_pose; a.odom = e->odom;
   a.meas_ptr = e->meas_ptr; a.meas_id = e->meas_id; a.meas_pose = e->meas_pose; a.meas_b = e->meas_b; a.meas_r = e->meas_r;
   a.observed = e->observed; a.lin_l = e->lin_l; a.est_l = e->est_l; a.delta_l = e->delta_l;
-  a.prob = e->prob; a.vinfo = e->vinfo; a.metrics = e->metrics; a.dist = e->dist; a.plan = e->plan; a.plan_cursor = e->plan_cursor;
+  a.prob = e->prob; a.vinfo = e->vinfo; a.metrics = e->metrics; a.dist = e->dist; a.rdist = e->rdist; a.plan = e->plan; a.plan_cursor = e->plan_cursor;
   a.done = e->done; a.active = active;
   return a;
 }

@@ -23,6 +23,7 @@ namespace {
 constexpr int NT = 128;        // threads per CTA; also the max number of border columns (2*Lt <= 128)
 constexpr int CH = 32;         // poses staged per shared-memory chunk
 constexpr int WS_POSE = 48;    // doubles per pose in ws_pose
+constexpr int WS_MEAS = 14;    // doubles per measurement in ws_meas: C(3) gl(2) | D contribution(6) g contribution(3)
 
 struct SlamArgs {
   dge_config cfg;
@@ -30,13 +31,14 @@ struct SlamArgs {
   int32_t *n_poses, *update_count, *status;
   const double *prior_pose, *odom, *lm_true;
   double *lin_pose, *est_pose, *delta_pose, *pose_cov, *pose_info;
-  const int32_t *meas_ptr, *meas_id;
+  const int32_t *meas_ptr, *meas_id, *meas_pose;
   const double *meas_b, *meas_r;
   const uint8_t *observed;
   double *lin_l, *est_l, *delta_l, *land_cov;
   double *ws_pose, *ws_meas, *ws_Bt, *ws_FB;
   int32_t *ws_midx;
   double *metrics;
+  long long *clocks;   // [B,8] optional: SM clock at the phase boundaries (thread 0), for in-situ phase timing
 };
 
 __device__ __forceinline__ void predict_br(const Pose3 &p, double lx, double ly, double &bearing, double &range, double *Hx, double *Hl) {
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
   const int32_t *mid = a.meas_id + (size_t)b * a.d.Mmax;
   const double *mb = a.meas_b + (size_t)b * a.d.Mmax, *mr = a.meas_r + (size_t)b * a.d.Mmax;
   double *wsp = a.ws_pose + (size_t)b * Tmax * WS_POSE;
-  double *wsm = a.ws_meas + (size_t)b * a.d.Mmax * 5;
+  double *wsm = a.ws_meas + (size_t)b * a.d.Mmax * WS_MEAS;
   double *wBt = a.ws_Bt + (size_t)b * Tmax * 3 * N2C;
   double *wFB = a.ws_FB + (size_t)b * Tmax * 3 * N2C;
   int32_t *wmi = a.ws_midx + (size_t)b * Tmax * Lt;
@@ -128,65 +130,89 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
   __syncthreads();
   const int nl = s_nl, n2 = 2 * nl;
 
+  if (a.clocks && tid == 0) a.clocks[8 * b + 0] = clock64();
   // ---------------------------------------------------------------- phase A ---
-  // whitened linearisation of every factor at theta, one thread per pose.
+  // whitened linearisation of every factor at theta.
+  // A1: one thread per bearing-range factor (BearingRangeFactor<Pose2,Point2>): pose-pose, pose-landmark
+  //     and landmark-landmark blocks + right-hand sides -> ws_meas / border rows.
+  const int M = mptr[T];
+  const int32_t *mpose = a.meas_pose + (size_t)b * a.d.Mmax;
+  for (int p = tid; p < M; p += NT) {
+    const int k = mpose[p];
+    const Pose3 pk{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]};
+    const int id = mid[p], jr = lidx[id], c0 = 2 * jr;
+    double bb, rg, Hx[6], Hl[4];
+    predict_br(pk, linl[2 * id], linl[2 * id + 1], bb, rg, Hx, Hl);
+    double r0 = bb - mb[p];                      // Rot2 local coordinates: wrap to (-pi, pi]
+    if (r0 > DGE_PI) r0 -= 2 * DGE_PI; else if (r0 <= -DGE_PI) r0 += 2 * DGE_PI;
+    const double r1 = rg - mr[p];
+    double *m = wsm + (size_t)p * WS_MEAS;
+    m[0] = Hl[0] * wm[0] * Hl[0] + Hl[2] * wm[1] * Hl[2];
+    m[1] = Hl[0] * wm[0] * Hl[1] + Hl[2] * wm[1] * Hl[3];
+    m[2] = Hl[1] * wm[0] * Hl[1] + Hl[3] * wm[1] * Hl[3];
+    m[3] = -(Hl[0] * wm[0] * r0 + Hl[2] * wm[1] * r1);
+    m[4] = -(Hl[1] * wm[0] * r0 + Hl[3] * wm[1] * r1);
+    int q = 5;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int jj = i; jj < 3; ++jj, ++q) m[q] = Hx[i] * wm[0] * Hx[jj] + Hx[3 + i] * wm[1] * Hx[3 + jj];
+      m[11 + i] = -(Hx[i] * wm[0] * r0 + Hx[3 + i] * wm[1] * r1);
+      wBt[((size_t)k * 3 + i) * N2C + c0] = Hx[i] * wm[0] * Hl[0] + Hx[3 + i] * wm[1] * Hl[2];
+      wBt[((size_t)k * 3 + i) * N2C + c0 + 1] = Hx[i] * wm[0] * Hl[1] + Hx[3 + i] * wm[1] * Hl[3];
+    }
+    wmi[(size_t)k * Lt + jr] = p + 1;
+  }
+  // A2: one thread per pose: prior (k = 0) and the odometry factor k -> k+1 (its contribution to
+  //     pose k+1 is parked in gnext and picked up by the chain); measurement terms summed in factor order.
+  __syncthreads();
   for (int k = tid; k < T; k += NT) {
     const Pose3 pk{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]};
-    double D[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, U[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double D[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, U[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gn[3] = {0, 0, 0};
     if (k == 0) {  // PriorFactor<Pose2>: error = -Local(x, prior), H = I
       const Pose3 e = dge_between(pk, Pose3{a.prior_pose[3 * b], a.prior_pose[3 * b + 1], a.prior_pose[3 * b + 2]}, nullptr);
       const double wp[3] = {1.0 / (a.cfg.sigma_x0 * a.cfg.sigma_x0), 1.0 / (a.cfg.sigma_y0 * a.cfg.sigma_y0),
                             1.0 / (a.cfg.sigma_theta0 * a.cfg.sigma_theta0)};
       D[0] += wp[0]; D[3] += wp[1]; D[5] += wp[2];
       g[0] += wp[0] * e.x; g[1] += wp[1] * e.y; g[2] += wp[2] * e.th;   // g -= w * (-e)
-    }
-    if (k >= 1) {  // odometry factor (k-1 -> k): Jacobian wrt x_k is I
-      const Pose3 pm{lin[3 * (k - 1)], lin[3 * (k - 1) + 1], lin[3 * (k - 1) + 2]};
-      const Pose3 h = dge_between(pm, pk, nullptr);
-      const Pose3 e = dge_between(Pose3{od[3 * (k - 1)], od[3 * (k - 1) + 1], od[3 * (k - 1) + 2]}, h, nullptr);
+    } else {       // odometry factor (k-1 -> k): Jacobian wrt x_k is I (its rhs arrives through gnext of pose k-1)
       D[0] += wo[0]; D[3] += wo[1]; D[5] += wo[2];
-      g[0] -= wo[0] * e.x; g[1] -= wo[1] * e.y; g[2] -= wo[2] * e.th;
     }
-    if (k + 1 < T) {  // odometry factor (k -> k+1): Jacobian wrt x_k is H1
+    if (k + 1 < T) {  // BetweenFactor<Pose2>(x_k, x_k+1, odom): error = Local(odom, between), J = [H1 | I]
       double H1[9];
       const Pose3 pn{lin[3 * (k + 1)], lin[3 * (k + 1) + 1], lin[3 * (k + 1) + 2]};
       const Pose3 h = dge_between(pk, pn, H1);
       const Pose3 e = dge_between(Pose3{od[3 * k], od[3 * k + 1], od[3 * k + 2]}, h, nullptr);
       const double r[3] = {e.x, e.y, e.th};
       int q = 0;
+#pragma unroll
       for (int i = 0; i < 3; ++i) {
-        for (int j = i; j < 3; ++j, ++q) D[q] += H1[i] * wo[0] * H1[j] + H1[3 + i] * wo[1] * H1[3 + j] + H1[6 + i] * wo[2] * H1[6 + j];
-        for (int j = 0; j < 3; ++j) U[i * 3 + j] = H1[j * 3 + i] * wo[j];
+#pragma unroll
+        for (int jj = i; jj < 3; ++jj, ++q) D[q] += H1[i] * wo[0] * H1[jj] + H1[3 + i] * wo[1] * H1[3 + jj] + H1[6 + i] * wo[2] * H1[6 + jj];
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) U[i * 3 + jj] = H1[jj * 3 + i] * wo[jj];
         g[i] -= H1[i] * wo[0] * r[0] + H1[3 + i] * wo[1] * r[1] + H1[6 + i] * wo[2] * r[2];
+        gn[i] = -wo[i] * r[i];
       }
     }
-    for (int p = mptr[k]; p < mptr[k + 1]; ++p) {  // BearingRangeFactor<Pose2,Point2>
-      const int id = mid[p], jr = lidx[id], c0 = 2 * jr;
-      double bb, rg, Hx[6], Hl[4];
-      predict_br(pk, linl[2 * id], linl[2 * id + 1], bb, rg, Hx, Hl);
-      const double r0 = dge_wrap_pi(bb - mb[p]), r1 = rg - mr[p];
-      int q = 0;
-      for (int i = 0; i < 3; ++i) {
-        for (int j = i; j < 3; ++j, ++q) D[q] += Hx[i] * wm[0] * Hx[j] + Hx[3 + i] * wm[1] * Hx[3 + j];
-        g[i] -= Hx[i] * wm[0] * r0 + Hx[3 + i] * wm[1] * r1;
-        wBt[((size_t)k * 3 + i) * N2C + c0] = Hx[i] * wm[0] * Hl[0] + Hx[3 + i] * wm[1] * Hl[2];
-        wBt[((size_t)k * 3 + i) * N2C + c0 + 1] = Hx[i] * wm[0] * Hl[1] + Hx[3 + i] * wm[1] * Hl[3];
-      }
-      wmi[(size_t)k * Lt + jr] = p + 1;
-      double *m = wsm + (size_t)p * 5;
-      m[0] = Hl[0] * wm[0] * Hl[0] + Hl[2] * wm[1] * Hl[2];
-      m[1] = Hl[0] * wm[0] * Hl[1] + Hl[2] * wm[1] * Hl[3];
-      m[2] = Hl[1] * wm[0] * Hl[1] + Hl[3] * wm[1] * Hl[3];
-      m[3] = -(Hl[0] * wm[0] * r0 + Hl[2] * wm[1] * r1);
-      m[4] = -(Hl[1] * wm[0] * r0 + Hl[3] * wm[1] * r1);
+    for (int p = mptr[k]; p < mptr[k + 1]; ++p) {
+      const double *m = wsm + (size_t)p * WS_MEAS;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) D[i] += m[5 + i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) g[i] += m[11 + i];
     }
     double *w = wsp + (size_t)k * WS_POSE;
+#pragma unroll
     for (int i = 0; i < 6; ++i) w[i] = D[i];
-    for (int i = 0; i < 3; ++i) w[6 + i] = g[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { w[6 + i] = g[i]; w[18 + i] = gn[i]; }
+#pragma unroll
     for (int i = 0; i < 9; ++i) w[9 + i] = U[i];
   }
   __syncthreads();
 
+  if (a.clocks && tid == 0) a.clocks[8 * b + 1] = clock64();
   // ---------------------------------------------------------------- phase B ---
   // forward elimination along the chain.  The 3x3 pose recurrence is evaluated redundantly
   // by every thread (no communication); thread c additionally carries border column c.
@@ -197,19 +223,20 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
     double cD[6] = {0, 0, 0, 0, 0, 0}, cg[3] = {0, 0, 0};  // carries -U^T F from the previous pose
     double cB[3] = {0, 0, 0};
     double sd0 = 0, sd1 = 0, glc = 0;                       // own diagonal-block column of S, own gl
+    double gprev[3] = {0, 0, 0};                            // rhs of the odometry factor (k-1 -> k) wrt pose k
     for (int k0 = 0; k0 < T; k0 += CH) {
       const int kc = min(CH, T - k0);
       __syncthreads();
-      for (int i = tid; i < kc * 18; i += NT) stage[i] = wsp[(size_t)(k0 + i / 18) * WS_POSE + (i % 18)];
+      for (int i = tid; i < kc * 21; i += NT) stage[i] = wsp[(size_t)(k0 + i / 21) * WS_POSE + (i % 21)];
       __syncthreads();
       for (int kk = 0; kk < kc; ++kk) {
         const int k = k0 + kk;
-        const double *w = stage + kk * 18;
+        const double *w = stage + kk * 21;
         double D[6], g[3], U[9], Di[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) D[i] = w[i] + cD[i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) g[i] = w[6 + i] + cg[i];
+        for (int i = 0; i < 3; ++i) { g[i] = w[6 + i] + cg[i] + gprev[i]; gprev[i] = w[18 + i]; }
 #pragma unroll
         for (int i = 0; i < 9; ++i) U[i] = w[9 + i];
         double det;
@@ -248,7 +275,7 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
           for (int i = 0; i < 3; ++i) Bt[i] = wBt[((size_t)k * 3 + i) * N2C + c] + cB[i];
           const int p1 = wmi[(size_t)k * Lt + jr];
           if (p1) {  // pose k observes this column's landmark: landmark-landmark block and rhs
-            const double *m = wsm + (size_t)(p1 - 1) * 5;
+            const double *m = wsm + (size_t)(p1 - 1) * WS_MEAS;
             sd0 += comp ? m[1] : m[0];
             sd1 += comp ? m[2] : m[1];
             glc += m[3 + comp];
@@ -277,6 +304,7 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
   }
   __syncthreads();
 
+  if (a.clocks && tid == 0) a.clocks[8 * b + 2] = clock64();
   // ---------------------------------------------------------------- phase S ---
   // Schur complement S -= sum_k Bt_k^T FB_k  (n2 x 3T x n2 GEMM, upper 4x4 tiles, mirrored)
   if (n2 > 0) {
@@ -313,6 +341,7 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
   }
   __syncthreads();
 
+  if (a.clocks && tid == 0) a.clocks[8 * b + 3] = clock64();
   // ---------------------------------------------------------------- phase C ---
   // Sigma_ll = S^-1 (in-place Gauss-Jordan on the SPD Schur complement), dl = Sigma_ll gl
   // Thread (c, h): column c = tid % 64 (+64 for a second pass when n2 > 64), rows r = h mod 2.
@@ -327,9 +356,7 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
     for (int c = tid & 63; c < n2; c += 64) {
       double *__restrict__ Sc = S + c;
       const double *__restrict__ cp = colp;
-      if (c == p) {
-        for (int r = h; r < n2; r += 2) Sc[r * n2] = (r == p) ? piv : -cp[r] * piv;
-      } else {
+      if (c != p) {
         const double rowpc = Sc[p * n2] * piv;
         int r = h;
         for (; r + 10 < n2; r += 12) {
@@ -348,9 +375,11 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
       }
     }
     __syncthreads();
-    // row p of the non-pivot columns (written after every thread has finished reading it)
-    for (int c = tid; c < n2; c += NT)
+    // row p of the non-pivot columns and the pivot column itself (after every thread has finished reading them)
+    for (int c = tid; c < n2; c += NT) {
       if (c != p) S[p * n2 + c] *= piv;
+      S[c * n2 + p] = (c == p) ? piv : -colp[c] * piv;
+    }
     __syncthreads();
   }
   if (tid < n2) {
@@ -360,6 +389,7 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
   }
   __syncthreads();
 
+  if (a.clocks && tid == 0) a.clocks[8 * b + 4] = clock64();
   // --------------------------------------------------------------- phase D1 ---
   // backward substitution: W_k = FB_k - FU_k W_{k+1} (own column), P_k = Dinv_k + FU_k P_{k+1} FU_k^T,
   // u_k = f_k - FU_k u_{k+1} (redundant 3x3 chain).
@@ -423,6 +453,7 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
   }
   __syncthreads();
 
+  if (a.clocks && tid == 0) a.clocks[8 * b + 5] = clock64();
   // ---------------------------------------------------------------- phase E ---
   // per pose (one warp each): Sigma_kk = P_k + W_k Sigma_ll W_k^T, delta_k = u_k - W_k dl,
   // estimate = theta (+) delta, information = Sigma_kk^-1 (SLAM2D.cpp:400).
@@ -483,6 +514,7 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
     a.metrics[8 * b + 4] = le / Lt;   // ExplorationEnv.get_landmark_error  exploration_env.py:170-176
     a.metrics[8 * b + 5] = m;         // max_uncertainty_of_trajectory        exploration_env.py:190-194
     a.update_count[b] = uc;
+    if (a.clocks) { a.clocks[8 * b + 6] = clock64(); a.clocks[8 * b + 7] = T; }
     if (s_bad) a.status[b] = 1;
   }
 }
@@ -500,10 +532,11 @@ int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
   a.n_poses = e->n_poses; a.update_count = e->update_count; a.status = e->status;
   a.prior_pose = e->prior_pose; a.odom = e->odom; a.lm_true = e->lm_true;
   a.lin_pose = e->lin_pose; a.est_pose = e->est_pose; a.delta_pose = e->delta_pose; a.pose_cov = e->pose_cov; a.pose_info = e->pose_info;
-  a.meas_ptr = e->meas_ptr; a.meas_id = e->meas_id; a.meas_b = e->meas_b; a.meas_r = e->meas_r;
+  a.meas_ptr = e->meas_ptr; a.meas_id = e->meas_id; a.meas_pose = e->meas_pose; a.meas_b = e->meas_b; a.meas_r = e->meas_r;
   a.observed = e->observed; a.lin_l = e->lin_l; a.est_l = e->est_l; a.delta_l = e->delta_l; a.land_cov = e->land_cov;
   a.ws_pose = e->ws_pose; a.ws_meas = e->ws_meas; a.ws_Bt = e->ws_Bt; a.ws_FB = e->ws_FB; a.ws_midx = e->ws_midx;
   a.metrics = e->metrics;
+  a.clocks = e->slam_clocks;
   const size_t smem = dge_slam_smem_bytes(e->d.Lt);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {

@@ -100,19 +100,22 @@ __global__ void __launch_bounds__(TILE * TILE) k_vmap_cells(VmapCfg c, int Tstri
   const double ty0 = c.map_min_y + c.res * (tile_r + 0.5), ty1 = c.map_min_y + c.res * (min(tile_r + TILE, c.rows) - 0.5);
 
   __shared__ double sp[VCH * PREP_W];
-  __shared__ int s_lmcell;
+  __shared__ unsigned char s_lmflag[TILE * TILE];
 
-  // landmark cells (OccupancyMap.cpp:126-131): a cell holding a landmark estimate saturates "occupied"
-  bool is_lm = false;
+  // landmark cells (OccupancyMap.cpp:126-131): a cell holding a landmark estimate saturates "occupied".
+  // One thread per landmark marks the tile-local flag; every cell thread then reads its own flag.
+  s_lmflag[threadIdx.x] = 0;
+  __syncthreads();
   {
     const double *l = lm + (size_t)b * Lstride * 2;
-    for (int j = 0; j < Lfixed; ++j) {
+    for (int j = threadIdx.x; j < Lfixed; j += TILE * TILE) {
       if (lm_obs && !lm_obs[(size_t)b * Lstride + j]) continue;
-      const int lr = (int)floor((l[2 * j + 1] - c.map_min_y) / c.res), lc = (int)floor((l[2 * j] - c.map_min_x) / c.res);
-      if (lr == row && lc == col) is_lm = true;
+      const int lr = (int)floor((l[2 * j + 1] - c.map_min_y) / c.res) - tile_r, lc = (int)floor((l[2 * j] - c.map_min_x) / c.res) - tile_c;
+      if (lr >= 0 && lr < TILE && lc >= 0 && lc < TILE) s_lmflag[lr * TILE + lc] = 1;
     }
   }
-  (void)s_lmcell;
+  __syncthreads();
+  const bool is_lm = s_lmflag[(row - tile_r) * TILE + (col - tile_c)] != 0;
 
   double ixx = c.i0, ixy = 0.0, iyy = c.i0;
   bool updated = false;

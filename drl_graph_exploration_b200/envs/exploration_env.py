@@ -166,6 +166,41 @@ class VecExplorationEnv:
         _check(eng._L.dge_line_plan(eng._h, _ptr(goals.contiguous()), _ptr(mask), _ptr(out), _stream_ptr(self.device)), "dge_line_plan")
         return out
 
+    # ------------------------------------------------------------- roll-outs ---
+    def rollout_rewards(self, mask: Optional[torch.Tensor] = None, clone_slots: Optional[int] = None, noise: Optional[torch.Tensor] = None):
+        """rewards_all_goals (exploration_env.py:145-162) for every env selected in the last
+        ``build_graph(mask)``: one clone per (env, frontier) in a second engine, all clones stepped
+        together through their line plans.  Returns (raw [B,Fmax], normalised [B,Fmax], loop_clo [B]).
+        ``noise`` [n_steps, clone_slots, 3+4*Lt] makes the roll-out noise explicit (parity tests)."""
+        eng = self.eng
+        if getattr(self, "_roll", None) is None:
+            slots = clone_slots or min(self.B * (eng.Lt + 1), max(4 * self.B, 512))
+            self._roll = Engine(self.cfg, slots, max_poses=eng.Tmax, device=self.device)
+            self._roll_totals = torch.zeros(2, dtype=torch.int32, device=self.device)
+            self._roll_totals_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+            fm = eng.Lt + 1
+            self._roll_raw = torch.zeros(self.B, fm, dtype=torch.float64, device=self.device)
+            self._roll_norm = torch.zeros(self.B, fm, dtype=torch.float64, device=self.device)
+            self._roll_clo = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
+            L = eng._L
+            vp = ctypes.c_void_p
+            L.dge_rollout_prepare.argtypes = [vp, vp, vp, vp, vp, vp]
+            L.dge_rollout_rewards.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+            L.dge_step_queued_noise.argtypes = [vp, vp, vp]
+        roll, sp = self._roll, _stream_ptr(self.device)
+        roll._L.dge_set_counting(roll._h, 0)
+        _check(eng._L.dge_rollout_prepare(roll._h, eng._h, ctypes.byref(self.graph.c), _ptr(mask), _ptr(self._roll_totals), sp), "dge_rollout_prepare")
+        # upper bound of a line plan: <= 2 rotations + floor(diagonal / max_edge) forward steps + remainder
+        diag = math.hypot(self.cfg.map_size, self.cfg.map_size)
+        n_steps = 3 + int(diag / self.cfg.max_edge_length)
+        if noise is not None:
+            n_steps = noise.shape[0]
+        for i in range(n_steps):
+            _check(roll._L.dge_step_queued_noise(roll._h, _ptr(None if noise is None else noise[i].contiguous()), sp), "dge_step_queued_noise")
+        _check(eng._L.dge_rollout_rewards(roll._h, eng._h, ctypes.byref(self.graph.c), _ptr(mask), _ptr(self._roll_raw), _ptr(self._roll_norm),
+                                          _ptr(self._roll_clo), sp), "dge_rollout_rewards")
+        return self._roll_raw, self._roll_norm, self._roll_clo
+
     # ------------------------------------------------------------- host API ---
     def step_host(self, odom_host: np.ndarray, done_host: np.ndarray, obs_host: Optional[np.ndarray] = None):
         self.eng.step_host(odom_host, done_host, obs_host)

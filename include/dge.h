@@ -86,6 +86,7 @@ int dge_step(dge_handle h, const double *odom_dev, const uint8_t *mask_dev, cons
 /* same, but every env executes the next action of its own queued line plan (filled by
  * dge_select_and_plan); envs whose queue is empty do not step.                       */
 int dge_step_queued(dge_handle h, void *stream);
+int dge_step_queued_noise(dge_handle h, const double *noise_dev /* [B,3+4*Lt] explicit noise (parity) */, void *stream);
 /* the three stages of dge_step, separately launchable (profiling / tests); after the first
  * stage `active` (see dge_state_view) flags the envs that actually moved.             */
 int dge_move_measure_queued(dge_handle h, void *stream);
@@ -143,6 +144,7 @@ typedef struct dge_state_view {
   const int32_t *status;         /* [B] 0 ok, DGE_ECAP, or 1 = solver breakdown       */
   const double *plan;            /* [B,6] queued line plan (see dge_line_plan)        */
   const int32_t *plan_cursor;    /* [B] next action of the plan                       */
+  const int64_t *slam_clocks;    /* [B,8] SM clock at the 7 phase boundaries of the last SLAM launch, [.,7] = T */
   const int64_t *counters;       /* [4] work counters: env-steps, sum of trajectory lengths, sum of
                                     measurement counts over those steps, reserved            */
 } dge_state_view;
@@ -182,6 +184,20 @@ int dge_line_plan(dge_handle h, const double *goal_dev, const uint8_t *mask_dev,
  * action queue.  q_dev [N_tot] f32 in the node order of `g`.                         */
 int dge_select_and_plan(dge_handle h, const dge_graph_out *g, const float *q_dev, const uint8_t *mask_dev,
                         int32_t *choice_dev /* [B] nullable: chosen frontier index */, void *stream);
+
+/* ---- look-ahead roll-out rewards: replaces EMPlanner2D.simulations_reward
+ * (Planner2D.cpp:1416-1468, `planner2d` binding Planner2D.cpp:90) and
+ * ExplorationEnv.rewards_all_goals (exploration_env.py:145-162).  `dst` is a second engine of the
+ * same capacities whose slots receive one clone per (env, frontier) of the envs selected by
+ * mask in the graph `g` of `src` (SLAM2D/VirtualMap/Simulator2D copies + set_copy_isam + queued
+ * line plan).  The caller then advances `dst` with dge_step_queued until every queue is empty
+ * (at most 2 + floor(diagonal / max_edge_length) + 1 calls) and collects the rewards.
+ *   totals_dev [2]: number of clones, overflow flag (more clones than dst has slots)
+ *   raw_dev / norm_dev [B,Fmax]: U(before) - U(after) per frontier / min-max normalised to
+ *   [-1,0] or [-1,1];  loop_clo_dev [B]: the reference's loop-closure flag.            */
+int dge_rollout_prepare(dge_handle dst, dge_handle src, const dge_graph_out *g, const uint8_t *mask_dev, int32_t *totals_dev, void *stream);
+int dge_rollout_rewards(dge_handle dst, dge_handle src, const dge_graph_out *g, const uint8_t *mask_dev, double *raw_dev, double *norm_dev,
+                        uint8_t *loop_clo_dev, void *stream);
 
 /* ---- GNN building blocks (scripts/Networks.py GCN: GCNConv(improved=True) aggregate,
  * bias, ReLU; Linear head) -- hand-written edge/dst-parallel kernels, see dge_gnn.h  */

@@ -303,9 +303,10 @@ void Env::init_with_landmarks(uint32_t seed, Pose start, const std::vector<doubl
 // Simulator2D::move  Simulator2D.cpp:491-503 -> SimpleControlModel::evolve :161-182 ;
 // SLAM2D::addOdometry  SLAM2D.cpp:70-89
 void Env::move(const double o[3], StepNoise *rec) {
-  const double nx = rng_control.normal(0.0, cfg.trans_noise);
-  const double ny = rng_control.normal(0.0, cfg.trans_noise);
-  const double nt = rng_control.normal(0.0, cfg.rot_noise);
+  // forced_noise (tests only): explicit noise in the StepNoise layout instead of the mt19937 streams
+  const double nx = forced_noise ? forced_noise[0] : rng_control.normal(0.0, cfg.trans_noise);
+  const double ny = forced_noise ? forced_noise[1] : rng_control.normal(0.0, cfg.trans_noise);
+  const double nt = forced_noise ? forced_noise[2] : rng_control.normal(0.0, cfg.rot_noise);
   if (rec) { rec->v[0] = nx; rec->v[1] = ny; rec->v[2] = nt; }
   const Pose od{o[0], o[1], o[2]};
   true_pose = compose(compose(true_pose, od), Pose{nx, ny, nt});
@@ -323,8 +324,8 @@ void Env::measure(std::vector<Meas> &out, StepNoise *rec, int call) {
     const uint32_t id = scan_id[s];
     const double dx = true_pose.x - lm_x[id], dy = true_pose.y - lm_y[id];
     if (!(std::sqrt(dx * dx + dy * dy) < cfg.max_range)) continue;   // Distance.cpp:86-88
-    const double nb = rng_sensor.normal(0.0, cfg.bearing_noise);     // Simulator2D.cpp:116-117
-    const double nr = rng_sensor.normal(0.0, cfg.range_noise);
+    const double nb = forced_noise ? forced_noise[3 + call * 2 * Lt + 2 * s] : rng_sensor.normal(0.0, cfg.bearing_noise);     // Simulator2D.cpp:116-117
+    const double nr = forced_noise ? forced_noise[3 + call * 2 * Lt + 2 * s + 1] : rng_sensor.normal(0.0, cfg.range_noise);
     if (rec) { rec->v[3 + call * 2 * Lt + 2 * s] = nb; rec->v[3 + call * 2 * Lt + 2 * s + 1] = nr; }
     double b, r;
     predict_br(true_pose, lm_x[id], lm_y[id], b, r, nullptr, nullptr);
@@ -836,7 +837,7 @@ std::vector<Pose> Env::line_plan(double gx, double gy) const {  // Planner2D.cpp
 }
 
 // ------------------------------------------------------- roll-out reward ---
-double Env::simulations_reward(const std::vector<Pose> &actions) const {  // Planner2D.cpp:1416-1468
+double Env::simulations_reward(const std::vector<Pose> &actions, const double *noise) const {  // Planner2D.cpp:1416-1468
   Env tmp(*this);  // SLAM2D / VirtualMap / Simulator2D copies, RNG state included (:1417-1420)
   // SLAM2D::set_copy_isam (SLAM2D.cpp:490-497): fresh ISAM2 linearised at calculateBestEstimate()
   tmp.lin_pose = tmp.est_pose;
@@ -849,6 +850,7 @@ double Env::simulations_reward(const std::vector<Pose> &actions) const {  // Pla
   for (const Pose &a : actions) {
     dist_ += std::sqrt(a.x * a.x + a.y * a.y + cfg.angle_weight * a.th * a.th);
     const double o[3] = {a.x, a.y, a.th};
+    tmp.forced_noise = noise ? noise + static_cast<size_t>(&a - actions.data()) * (3 + 4 * Lt) : nullptr;
     tmp.move(o, nullptr);
     std::vector<Meas> ms;
     tmp.measure(ms, nullptr, 1);   // a single measure() here (no obstacle probe)

@@ -8,14 +8,17 @@
 // leg may load the library built from this file.  The product path
 // (drl_graph_exploration_b200/) never links, imports or calls it.
 //
-// PARITY STATUS: **parity unpinned**.  The reference's arithmetic lives in
-// gtsam (fork `emex`, no commit pinned, not vendored under /root/reference)
-// and cannot be built here (gtsam/Eigen/boost absent).  This file restates the
-// published gtsam-4.0 semantics (Pose2 first-order chart, BetweenFactor,
-// BearingRangeFactor, PriorFactor, ISAM2 relinearisation schedule) and follows
-// the reference call sites line by line; the only known-answer data in the
-// reference (data/test_result/40_DQN_GCN.csv) is used as a loose tracking
-// check in tests/test_golden_tracking.py.
+// PARITY STATUS: the reference's arithmetic lives in gtsam (fork `emex`, no
+// commit pinned, not vendored under /root/reference) and cannot be built here
+// (gtsam/Eigen/boost absent), so this file restates the published gtsam-4.0
+// semantics (Pose2 first-order chart, BetweenFactor, BearingRangeFactor,
+// PriorFactor, ISAM2 relinearisation schedule) and follows the reference call
+// sites line by line.  It is PINNED against the only known-answer data of the
+// reference, data/test_result/40_DQN_GCN.csv (test.py, seed 0, shipped DQN+GCN
+// weights): landmark error and max localisation uncertainty reproduced to
+// 1e-8..1e-9 relative over the first 54 steps, policy decisions identical
+// (tests/test_oracle_cpu.py::test_tracks_reference_golden_csv).  Beyond what
+// that run exercises (roll-out rewards, other map sizes): parity unpinned.
 //
 // Every function cites the reference file:line it follows (paths relative to
 // /root/reference).
@@ -101,6 +104,7 @@ class Env {
   std::vector<double> lin_l, est_l, delta_l;   // [Lt*2]
   Pose prior_pose{0, 0, 0};
   int update_count = 0;
+  const double *forced_noise = nullptr;    // tests only: explicit per-step noise (StepNoise layout)
   bool use_dense_solver = false;
   std::vector<M3> pose_cov, pose_info;     // marginals in tangent frame (q13)
   std::vector<M2> land_cov, land_info;     // by id
@@ -132,7 +136,7 @@ class Env {
   // Planner2D.cpp:937-1041 (closed form part)
   std::vector<Pose> line_plan(double gx, double gy) const;
   // Planner2D.cpp:1416-1468
-  double simulations_reward(const std::vector<Pose> &actions) const;
+  double simulations_reward(const std::vector<Pose> &actions, const double *noise = nullptr) const;   // noise [n,3+4Lt] nullable
 
   // building blocks exposed for kernel-level parity tests
   void slam_optimize();                    // SLAM2D.cpp:374-430 (ISAM2 schedule emulation)

@@ -140,6 +140,12 @@ double orc_sim_reward(void *h, const double *actions, int n) {
   for (int i = 0; i < n; ++i) a[i] = orc::Pose{actions[3 * i], actions[3 * i + 1], actions[3 * i + 2]};
   try { return static_cast<Env *>(h)->simulations_reward(a); } catch (...) { return std::nan(""); }
 }
+// same with explicit noise [n, 3+4*Lt] (kernel parity tests)
+double orc_sim_reward_noise(void *h, const double *actions, int n, const double *noise) {
+  std::vector<orc::Pose> a(n);
+  for (int i = 0; i < n; ++i) a[i] = orc::Pose{actions[3 * i], actions[3 * i + 1], actions[3 * i + 2]};
+  try { return static_cast<Env *>(h)->simulations_reward(a, noise); } catch (...) { return std::nan(""); }
+}
 
 void orc_virtual_map_rebuild(const orc::Config *cfg, int T, const double *pose, const double *info, int L, const double *lm,
                              int rows, int cols, double *prob, double *vinfo, int32_t *seen) {

@@ -150,9 +150,15 @@ class OracleEnv:
         n = self._L.orc_line_plan(self._h, ctypes.c_double(gx), ctypes.c_double(gy), _p(out), ctypes.c_int(256))
         return out[:n].copy()
 
-    def sim_reward(self, actions) -> float:
+    def sim_reward(self, actions, noise=None) -> float:
+        """EMPlanner2D::simulations_reward; `noise` [n_actions, 3+4*Lt] replaces the RNG streams (parity tests)."""
         a = np.ascontiguousarray(actions, dtype=np.float64)
-        return self._L.orc_sim_reward(self._h, _p(a), ctypes.c_int(len(a)))
+        if noise is None:
+            return self._L.orc_sim_reward(self._h, _p(a), ctypes.c_int(len(a)))
+        nz = np.ascontiguousarray(noise, dtype=np.float64)
+        assert nz.shape == (len(a), self.noise_len)
+        self._L.orc_sim_reward_noise.restype = ctypes.c_double
+        return self._L.orc_sim_reward_noise(self._h, _p(a), ctypes.c_int(len(a)), _p(nz))
 
     def rewards_all_goals(self, g=None):
         """exploration_env.py:145-162 (+ actions_all_goals :134-143); returns (rewards[N], loop_clo, actions)."""

@@ -1,0 +1,24 @@
+"""dev: in-situ phase timing of k_slam (SM clock at phase boundaries) after N ticks of the bench loop."""
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import numpy as np, torch
+import bench
+
+loop = bench.GpuLoop(0, 0)
+for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 60):
+    loop.tick()
+torch.cuda.synchronize()
+clk = loop.env.eng.state["slam_clocks"].cpu().numpy()
+act = loop.env.eng.state["active"].cpu().numpy().astype(bool)
+T = clk[:, 7]
+d = np.diff(clk[:, :7], axis=1).astype(np.float64)
+names = ["A(linearise)", "B(fwd chain)", "S(schur gemm)", "C(inverse)", "D(bwd chain)", "E(marginals)"]
+order = np.argsort(-T)
+print("active envs", act.sum(), "T mean", T[act].mean(), "T max", T[act].max())
+print("per-phase cycles: mean over active envs | slowest env | by T quantile")
+for i, n in enumerate(names):
+    print(f"{n:16s} mean {d[act, i].mean():10.0f}  max {d[act, i].max():10.0f}")
+tot = d.sum(axis=1)
+print(f"{'total':16s} mean {tot[act].mean():10.0f}  max {tot[act].max():10.0f}   (1965 MHz: max = {tot[act].max() / 1965:.1f} us)")
+for b in order[:4]:
+    print("env", b, "T", T[b], " ".join(f"{n.split('(')[0]}={d[b, i]:.0f}" for i, n in enumerate(names)), "total", tot[b])

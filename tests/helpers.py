@@ -57,6 +57,7 @@ def borderline_cells(cfg: EnvConfig, poses, tol=1e-6):
         d = np.sqrt(dx * dx + dy * dy)
         flag |= np.abs(d - cfg.max_range) < tol
         flag |= np.abs(d - cfg.min_range) < tol
+        flag |= d < tol     # an odd-integer start pose IS a cell centre: the bearing of a ~1e-12 vector is noise
         qx = math.cos(th) * dx + math.sin(th) * dy
         qy = -math.sin(th) * dx + math.cos(th) * dy
         b = np.arctan2(qy, qx)
