@@ -167,7 +167,10 @@ class GCN(torch.nn.Module):
     def _trunk(self, data, p):
         x = data.x
         gs = _structure(data, x.size(0))
-        x = self.conv1(x, gs, relu=True)
+        if not torch.is_grad_enabled() and x.size(1) <= 8:   # inference: aggregate the 5 input channels first, transform in the epilogue
+            x = gnn.gcn_conv_small_fused(x, self.conv1.weight, self.conv1.bias, gs, improved=True, relu=True)
+        else:
+            x = self.conv1(x, gs, relu=True)
         fused = (self._out == 1 and not torch.is_grad_enabled() and (p == 0 or p == 0.0))
         if fused:   # inference: conv2 aggregate + ReLU + Linear(1000,1) in one kernel
             # (the head bias is added as a tensor op: reading it on the host would force a sync)

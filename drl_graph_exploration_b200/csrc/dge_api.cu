@@ -75,6 +75,8 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.plan = al.get<double>(B * 6); e.plan_cursor = al.get<int32_t>(B);
   e.odom_dev_scratch = al.get<double>(B * 3); e.mask_dev_scratch = al.get<uint8_t>(B);
   e.g_counts = al.get<int32_t>(B * 4); e.g_frontier = al.get<int32_t>(B * d.Fmax); e.g_fassoc = al.get<int32_t>(B * (L + 1)); e.g_sel = al.get<int32_t>(B);
+  e.g_cnt = al.get<int32_t>(B * (size_t)d.Ncap); e.g_cur = al.get<int32_t>(B * (size_t)d.Ncap); e.g_dis = al.get<float>(B * (size_t)d.Ncap);
+  e.g_tmp = al.get<int32_t>(B * (size_t)d.Ecap);
   e.slam_clocks = al.get<long long>(B * 8);
   e.counters = al.get<unsigned long long>(4); e.count_steps = 1; e.park_done = 1;
   e.rdist = al.get<double>(B); e.r_cmap = al.get<int32_t>(B * 2); e.r_cbase = al.get<int32_t>(B); e.r_u0 = al.get<double>(B);

@@ -29,6 +29,8 @@ struct GraphArgs {
   const uint8_t *observed;
   const double *est_l, *land_cov, *prob, *vinfo;
   int32_t *g_counts, *g_frontier, *g_fassoc, *g_sel;
+  int32_t *g_cnt, *g_cur, *g_tmp;
+  float *g_dis;
 };
 
 __device__ __forceinline__ double dist_np(double ax, double ay, double bx, double by) {  // exploration_env.py:374-376
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(1024) k_graph_scan(int B, const uint8_t *mask,
     o.totals[0] = G; o.totals[1] = N; o.totals[2] = E;
     o.totals[3] = (N > o.node_cap || E > o.edge_cap) ? 1 : 0;
     o.totals[4] = sd[1023];   // envs whose episode is over (lets the host fold the reset check into the same D2H)
+    if (o.csr_rowptr && !o.totals[3]) o.csr_rowptr[N] = E;
   }
 }
 
@@ -281,6 +284,49 @@ __global__ void __launch_bounds__(GT) k_graph_fill(GraphArgs a, dge_graph_out o)
     xo[4] = (i < K - 1) ? -1.f : (i == K - 1 ? 0.f : 1.f);
     o.batch[n0 + i] = g;
   }
+  // ---- destination-sorted CSR + GCNConv(improved=True) normalisation of this graph, in place of the
+  // GNN's separate preprocessing launches (count / scan / fill / rank / degree / norm).  Rows sorted by
+  // edge id => deterministic aggregation order; the graph is symmetric, so in- and out-weights coincide.
+  if (!o.csr_rowptr) return;
+  const int E = a.g_counts[4 * b + 1];
+  int32_t *cnt = a.g_cnt + (size_t)b * a.d.Ncap, *cur = a.g_cur + (size_t)b * a.d.Ncap, *tmp = a.g_tmp + (size_t)b * a.d.Ecap;
+  float *dis = a.g_dis + (size_t)b * a.d.Ncap;
+  for (int i = tid; i < N; i += GT) { cnt[i] = 0; cur[i] = 0; }
+  __syncthreads();   // also orders the edge writes above before the reads below (same CTA)
+  for (int e = tid; e < E; e += GT) atomicAdd(&cnt[(int)(dst[e] - n0)], 1);
+  __syncthreads();
+  if (warp == 0) {   // exclusive scan of the in-degrees (N <= a few hundred): warp-serial chunks
+    int run = 0;
+    for (int i0 = 0; i0 < N; i0 += 32) {
+      const int i = i0 + lane;
+      const int v = i < N ? cnt[i] : 0;
+      int inc = v;
+      for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += t; }
+      if (i < N) { cnt[i] = run + inc - v; o.csr_rowptr[n0 + i] = e0 + run + inc - v; }
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += GT) { const int d = (int)(dst[e] - n0); tmp[cnt[d] + atomicAdd(&cur[d], 1)] = e; }
+  __syncthreads();
+  for (int e = tid; e < E; e += GT) {   // rank inside the row = position in ascending edge-id order
+    const int d = (int)(dst[e] - n0);
+    const int lo = cnt[d], hi = lo + cur[d];
+    int rank = 0;
+    for (int q = lo; q < hi; ++q) rank += (tmp[q] < e) ? 1 : 0;
+    o.csr_perm[e0 + lo + rank] = e0 + e;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += GT) {   // weighted degree in row order + the improved self loop (weight 2)
+    float deg = 0.f;
+    for (int q = cnt[i]; q < cnt[i] + cur[i]; ++q) deg += ew[o.csr_perm[e0 + q] - e0];
+    deg += 2.0f;
+    const float ds = 1.0f / sqrtf(deg);
+    dis[i] = ds;
+    o.gcn_selfnorm[n0 + i] = ds * 2.0f * ds;
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += GT) o.gcn_norm[e0 + e] = dis[(int)(src[e] - n0)] * ew[e] * dis[(int)(dst[e] - n0)];
 }
 
 // ------------------------------------------------------------- line planner ---
@@ -350,6 +396,7 @@ GraphArgs make_gargs(dge_engine *e) {
   a.meas_ptr = e->meas_ptr; a.meas_id = e->meas_id; a.meas_pose = e->meas_pose; a.meas_r = e->meas_r; a.observed = e->observed;
   a.est_l = e->est_l; a.land_cov = e->land_cov; a.prob = e->prob; a.vinfo = e->vinfo;
   a.g_counts = e->g_counts; a.g_frontier = e->g_frontier; a.g_fassoc = e->g_fassoc; a.g_sel = e->g_sel;
+  a.g_cnt = e->g_cnt; a.g_cur = e->g_cur; a.g_tmp = e->g_tmp; a.g_dis = e->g_dis;
   return a;
 }
 

@@ -62,6 +62,10 @@ struct dge_engine {
   int32_t *g_frontier;   // [B,Fmax] frontier cell index
   int32_t *g_fassoc;     // [B,Lt+1] node -> frontier association (-1 none): slot 0 robot, 1+i landmark rank i
   int32_t *g_sel;        // [B] position of the env among the selected graphs (-1 = not selected)
+  int32_t *g_cnt;        // [B,Ncap] in-degree / row start of each node (CSR build scratch)
+  int32_t *g_cur;        // [B,Ncap] fill cursor
+  float *g_dis;          // [B,Ncap] deg^-1/2
+  int32_t *g_tmp;        // [B,Ecap] unsorted row contents
   double *rdist;         // [B] roll-out distance: sum of sqrt(x^2 + y^2 + angle_weight*theta^2) over executed actions
   int32_t *r_cmap;       // [B,2] (as roll-out engine) source env / frontier of each clone slot
   int32_t *r_cbase;      // [B]   (as source engine) first clone slot of each env

@@ -20,8 +20,11 @@
 
 namespace {
 
-constexpr int NT = 128;        // threads per CTA; also the max number of border columns (2*Lt <= 128)
+constexpr int NT = 256;        // threads per CTA (>= the number of border columns, 2*Lt <= 128)
+constexpr int NH = NT / 64;    // row groups per column in the Gauss-Jordan sweep
 constexpr int CH = 32;         // poses staged per shared-memory chunk
+constexpr int SW = 39;         // doubles per staged pose: D(6) g(3) U(9) gnext(3) | Dinv(6) FU(9) f(3)
+constexpr int GK = 8;          // poses per staged chunk of border rows in the Schur-complement GEMM
 constexpr int WS_POSE = 48;    // doubles per pose in ws_pose
 constexpr int WS_MEAS = 14;    // doubles per measurement in ws_meas: C(3) gl(2) | D contribution(6) g contribution(3)
 
@@ -62,7 +65,7 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
+__global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask) {
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (mask && !mask[b]) return;
   const int T = a.n_poses[b];
@@ -70,12 +73,13 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
   extern __shared__ double smem[];
   // shared layout
   double *S = smem;                               // [N2C*N2C]  Schur complement -> Sigma_ll
-  double *stage = S + (size_t)N2C * N2C;          // [CH*21]
-  double *colp = stage + CH * 21;                 // [N2C]
+  double *stage = S + (size_t)N2C * N2C;          // [CH*SW]   per-pose 3x3 blocks of the current chunk
+  double *colp = stage + CH * SW;                 // [N2C]
   double *gl = colp + N2C;                        // [N2C]
   double *dl = gl + N2C;                          // [N2C]
   double *red = dl + N2C;                         // [NT/32 * 2]
-  int *lidx = (int *)(red + 2 * (NT / 32));       // [Lt]  id -> compact rank (-1 unobserved)
+  double *gbuf = red + 2 * (NT / 32);             // [2*GK*3*N2C] border-row staging (Schur GEMM) / per-warp W_k (phase E)
+  int *lidx = (int *)(gbuf + 2 * GK * 3 * N2C);   // [Lt]  id -> compact rank (-1 unobserved)
   int *lid = lidx + Lt;                           // [Lt]  rank -> id
   __shared__ int s_nl, s_bad;
 
@@ -214,81 +218,92 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
 
   if (a.clocks && tid == 0) a.clocks[8 * b + 1] = clock64();
   // ---------------------------------------------------------------- phase B ---
-  // forward elimination along the chain.  The 3x3 pose recurrence is evaluated redundantly
-  // by every thread (no communication); thread c additionally carries border column c.
+  // forward elimination along the chain, per 32-pose chunk:
+  //   B0  warp 0 runs the 3x3 pose recurrence  D~_k = D_k - U_{k-1}^T D~_{k-1}^-1 U_{k-1}  (fp64 issue is
+  //       2 cycles per warp instruction whatever the lane count, so the recurrence is done ONCE, not per thread);
+  //   B1  thread <-> border column: Bt = B_k + carry, FB = D~^-1 Bt, carry' = -U^T FB  (registers only,
+  //       next pose's border row prefetched), own diagonal block of S and own rhs accumulated on the way.
+  // column c lives on thread NT-1-c so that warp 0 carries columns only when n2 > NT - 32.
+  const int ccol = NT - 1 - tid;
+  const bool colv = ccol < n2;
   {
-    const int c = tid;
-    const bool colv = c < n2;
-    const int jr = c >> 1, comp = c & 1;
-    double cD[6] = {0, 0, 0, 0, 0, 0}, cg[3] = {0, 0, 0};  // carries -U^T F from the previous pose
-    double cB[3] = {0, 0, 0};
-    double sd0 = 0, sd1 = 0, glc = 0;                       // own diagonal-block column of S, own gl
-    double gprev[3] = {0, 0, 0};                            // rhs of the odometry factor (k-1 -> k) wrt pose k
+    const int c = ccol, jr = c >> 1, comp = c & 1;
+    // warp-0 lane roles for the 3x3 recurrence
+    const bool isD = lane < 9, isG = lane >= 9 && lane < 12;
+    const int li = isD ? lane / 3 : (isG ? lane - 9 : 0), lj = isD ? lane % 3 : 0;
+    const int lmin = min(li, lj), lmax = max(li, lj);
+    const int d6 = lmin == 0 ? lmax : (lmin == 1 ? 2 + lmax : 5);                  // index into the packed symmetric 3x3
+    const int i1 = (li + 1) % 3, i2 = (li + 2) % 3, j1 = (lj + 1) % 3, j2 = (lj + 2) % 3;
+    const int s11 = i1 * 3 + j1, s22 = i2 * 3 + j2, s12 = i1 * 3 + j2, s21 = i2 * 3 + j1;
+    double cDij = 0.0, cgi = 0.0, gprev = 0.0;                                       // warp-0 carried state
+    double cB[3] = {0, 0, 0}, sd0 = 0, sd1 = 0, glc = 0;                             // column state
     for (int k0 = 0; k0 < T; k0 += CH) {
       const int kc = min(CH, T - k0);
       __syncthreads();
-      for (int i = tid; i < kc * 21; i += NT) stage[i] = wsp[(size_t)(k0 + i / 21) * WS_POSE + (i % 21)];
+      for (int i = tid; i < kc * 21; i += NT) stage[(i / 21) * SW + (i % 21)] = wsp[(size_t)(k0 + i / 21) * WS_POSE + (i % 21)];
       __syncthreads();
-      for (int kk = 0; kk < kc; ++kk) {
-        const int k = k0 + kk;
-        const double *w = stage + kk * 21;
-        double D[6], g[3], U[9], Di[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) D[i] = w[i] + cD[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { g[i] = w[6 + i] + cg[i] + gprev[i]; gprev[i] = w[18 + i]; }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) U[i] = w[9 + i];
-        double det;
-        dge_sym3_inv(D, Di, &det);
-        if (!(det > 0.0) || !(D[0] > 0.0)) s_bad = 1;
-        // fu = Di U ; f = Di g
-        double fu[9], f[3];
-        const double Dm[9] = {Di[0], Di[1], Di[2], Di[1], Di[3], Di[4], Di[2], Di[4], Di[5]};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-#pragma unroll
-          for (int j = 0; j < 3; ++j) fu[i * 3 + j] = Dm[i * 3] * U[j] + Dm[i * 3 + 1] * U[3 + j] + Dm[i * 3 + 2] * U[6 + j];
-          f[i] = Dm[i * 3] * g[0] + Dm[i * 3 + 1] * g[1] + Dm[i * 3 + 2] * g[2];
+      if (warp == 0) {
+        // lane-parallel 3x3 recurrence: lanes 0..8 own entry (i,j) of the pose block, lanes 9..11 entry i of the
+        // rhs; operands of other lanes come by warp shuffle.  ~45 instructions on the loop-carried path instead
+        // of ~250 for a scalar 3x3 inverse + two products (fp64 issue is 2 cycles / warp instruction).
+        for (int kk = 0; kk < kc; ++kk) {
+          double *w = stage + kk * SW;
+          const double d = isD ? w[d6] + cDij : 1.0;                                  // D~[i][j]
+          double g = isG ? w[6 + li] + cgi + gprev : 0.0;                               // g~[i]
+          if (isG) gprev = w[18 + li];
+          // adjugate entry (cyclic indices give the sign): C[i][j] = d[i1][j1] d[i2][j2] - d[i1][j2] d[i2][j1]
+          const double ca = __shfl_sync(0xffffffffu, d, s11), cb = __shfl_sync(0xffffffffu, d, s22);
+          const double cc = __shfl_sync(0xffffffffu, d, s12), ce = __shfl_sync(0xffffffffu, d, s21);
+          const double cof = ca * cb - cc * ce;
+          const double pr = d * cof;
+          const double det = __shfl_sync(0xffffffffu, pr, 0) + __shfl_sync(0xffffffffu, pr, 1) + __shfl_sync(0xffffffffu, pr, 2);
+          const double d00 = __shfl_sync(0xffffffffu, d, 0);
+          if (!(det > 0.0) || !(d00 > 0.0)) s_bad = 1;
+          const double di = cof * (1.0 / det);                                           // Dinv[i][j] (symmetric)
+          const double r0 = __shfl_sync(0xffffffffu, di, li * 3), r1 = __shfl_sync(0xffffffffu, di, li * 3 + 1), r2 = __shfl_sync(0xffffffffu, di, li * 3 + 2);
+          const double g0 = __shfl_sync(0xffffffffu, g, 9), g1 = __shfl_sync(0xffffffffu, g, 10), g2 = __shfl_sync(0xffffffffu, g, 11);
+          // lanes 0..8: FU[i][j] = Dinv[i][:] U[:][j] ; lanes 9..11: f[i] = Dinv[i][:] g
+          const double val = isG ? (r0 * g0 + r1 * g1 + r2 * g2) : (r0 * w[9 + lj] + r1 * w[12 + lj] + r2 * w[15 + lj]);
+          const double f0 = __shfl_sync(0xffffffffu, val, lj), f1 = __shfl_sync(0xffffffffu, val, 3 + lj), f2 = __shfl_sync(0xffffffffu, val, 6 + lj);
+          const double h0 = __shfl_sync(0xffffffffu, val, 9), h1 = __shfl_sync(0xffffffffu, val, 10), h2 = __shfl_sync(0xffffffffu, val, 11);
+          // carries for the next pose: -U^T FU (lanes 0..8), -U^T f (lanes 9..11)
+          const double u0 = w[9 + li], u1 = w[12 + li], u2 = w[15 + li];
+          if (isD) cDij = -(u0 * f0 + u1 * f1 + u2 * f2);
+          if (isG) cgi = -(u0 * h0 + u1 * h1 + u2 * h2);
+          // Dinv | FU | f  -> shared (for B1) and workspace (for the backward pass)
+          double *wo_ = wsp + (size_t)(k0 + kk) * WS_POSE + 21;
+          if (isD) {
+            w[27 + lane] = val; wo_[6 + lane] = val;
+            if (lj >= li) { w[21 + d6] = di; wo_[d6] = di; }
+          } else if (isG) { w[36 + li] = val; wo_[15 + li] = val; }
         }
-        // carries for pose k+1: -U^T fu (symmetric), -U^T f
-        cD[0] = -(U[0] * fu[0] + U[3] * fu[3] + U[6] * fu[6]);
-        cD[1] = -(U[0] * fu[1] + U[3] * fu[4] + U[6] * fu[7]);
-        cD[2] = -(U[0] * fu[2] + U[3] * fu[5] + U[6] * fu[8]);
-        cD[3] = -(U[1] * fu[1] + U[4] * fu[4] + U[7] * fu[7]);
-        cD[4] = -(U[1] * fu[2] + U[4] * fu[5] + U[7] * fu[8]);
-        cD[5] = -(U[2] * fu[2] + U[5] * fu[5] + U[8] * fu[8]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) cg[i] = -(U[i] * f[0] + U[3 + i] * f[1] + U[6 + i] * f[2]);
-        if (tid == 0) {
-          double *wo_ = wsp + (size_t)k * WS_POSE + 21;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) wo_[i] = Di[i];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) wo_[6 + i] = fu[i];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) wo_[15 + i] = f[i];
-        }
-        if (colv) {
-          double Bt[3], fb[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) Bt[i] = wBt[((size_t)k * 3 + i) * N2C + c] + cB[i];
-          const int p1 = wmi[(size_t)k * Lt + jr];
+      }
+      __syncthreads();
+      if (colv) {
+        double nb0 = wBt[((size_t)k0 * 3 + 0) * N2C + c], nb1 = wBt[((size_t)k0 * 3 + 1) * N2C + c], nb2 = wBt[((size_t)k0 * 3 + 2) * N2C + c];
+        int np1 = wmi[(size_t)k0 * Lt + jr];
+        for (int kk = 0; kk < kc; ++kk) {
+          const int k = k0 + kk;
+          const double *w = stage + kk * SW;
+          double Bt[3] = {nb0 + cB[0], nb1 + cB[1], nb2 + cB[2]};
+          const int p1 = np1;
+          if (kk + 1 < kc) {   // prefetch the next border row while this one is eliminated
+            nb0 = wBt[((size_t)(k + 1) * 3 + 0) * N2C + c]; nb1 = wBt[((size_t)(k + 1) * 3 + 1) * N2C + c]; nb2 = wBt[((size_t)(k + 1) * 3 + 2) * N2C + c];
+            np1 = wmi[(size_t)(k + 1) * Lt + jr];
+          }
           if (p1) {  // pose k observes this column's landmark: landmark-landmark block and rhs
             const double *m = wsm + (size_t)(p1 - 1) * WS_MEAS;
             sd0 += comp ? m[1] : m[0];
             sd1 += comp ? m[2] : m[1];
             glc += m[3 + comp];
           }
+          const double d0 = w[21], d1 = w[22], d2 = w[23], d3 = w[24], d4 = w[25], d5 = w[26];
+          const double fb0 = d0 * Bt[0] + d1 * Bt[1] + d2 * Bt[2], fb1 = d1 * Bt[0] + d3 * Bt[1] + d4 * Bt[2], fb2 = d2 * Bt[0] + d4 * Bt[1] + d5 * Bt[2];
+          glc -= Bt[0] * w[36] + Bt[1] * w[37] + Bt[2] * w[38];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) fb[i] = Dm[i * 3] * Bt[0] + Dm[i * 3 + 1] * Bt[1] + Dm[i * 3 + 2] * Bt[2];
-          glc -= Bt[0] * f[0] + Bt[1] * f[1] + Bt[2] * f[2];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            cB[i] = -(U[i] * fb[0] + U[3 + i] * fb[1] + U[6 + i] * fb[2]);
-            wBt[((size_t)k * 3 + i) * N2C + c] = Bt[i];
-            wFB[((size_t)k * 3 + i) * N2C + c] = fb[i];
-          }
+          for (int i = 0; i < 3; ++i) cB[i] = -(w[9 + i] * fb0 + w[12 + i] * fb1 + w[15 + i] * fb2);
+          wBt[((size_t)k * 3 + 0) * N2C + c] = Bt[0]; wBt[((size_t)k * 3 + 1) * N2C + c] = Bt[1]; wBt[((size_t)k * 3 + 2) * N2C + c] = Bt[2];
+          wFB[((size_t)k * 3 + 0) * N2C + c] = fb0; wFB[((size_t)k * 3 + 1) * N2C + c] = fb1; wFB[((size_t)k * 3 + 2) * N2C + c] = fb2;
         }
       }
     }
@@ -306,37 +321,92 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
 
   if (a.clocks && tid == 0) a.clocks[8 * b + 2] = clock64();
   // ---------------------------------------------------------------- phase S ---
-  // Schur complement S -= sum_k Bt_k^T FB_k  (n2 x 3T x n2 GEMM, upper 4x4 tiles, mirrored)
+  // Schur complement S -= sum_k Bt_k^T FB_k : an n2 x 3T x n2 GEMM.  Border rows are staged through shared
+  // memory GK poses at a time (one linear, coalesced copy per operand); every thread keeps up to two 4x4
+  // tiles of the upper triangle in registers across all chunks; the result is mirrored.
   if (n2 > 0) {
     const int nt = (n2 + 3) / 4;
     const int ntile = nt * (nt + 1) / 2;
-    for (int t = tid; t < ntile; t += NT) {
-      int tr = 0, rem = t;
-      while (rem >= nt - tr) { rem -= nt - tr; ++tr; }
-      const int tc = tr + rem;
-      const int r0 = tr * 4, c0 = tc * 4;
-      double acc[16];
+    if (ntile <= 2 * NT) {
+      int tr[2], tc[2];
+      bool tv[2];
+      double acc[2][16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-      for (int ki = 0; ki < 3 * T; ++ki) {
-        const double *br = wBt + (size_t)ki * N2C + r0, *fc = wFB + (size_t)ki * N2C + c0;
-        double av[4], bv[4];
+      for (int s = 0; s < 2; ++s) {
+        const int t = tid + s * NT;
+        tv[s] = t < ntile;
+        int r_ = 0, rem = tv[s] ? t : 0;
+        while (rem >= nt - r_) { rem -= nt - r_; ++r_; }
+        tr[s] = r_; tc[s] = r_ + rem;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { av[i] = (r0 + i < n2) ? br[i] : 0.0; bv[i] = (c0 + i < n2) ? fc[i] : 0.0; }
+        for (int i = 0; i < 16; ++i) acc[s][i] = 0.0;
+      }
+      double *gA = gbuf, *gB = gbuf + GK * 3 * N2C;
+      for (int k0 = 0; k0 < T; k0 += GK) {
+        const int rows = min(GK, T - k0) * 3;
+        __syncthreads();
+        for (int i = tid; i < rows * N2C; i += NT) { gA[i] = wBt[(size_t)k0 * 3 * N2C + i]; gB[i] = wFB[(size_t)k0 * 3 * N2C + i]; }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (!tv[s]) continue;
+          const int r0 = tr[s] * 4, c0 = tc[s] * 4;   // columns beyond n2 read zeros/garbage of padded rows but are never stored
+          for (int ki = 0; ki < rows; ++ki) {
+            const double *ar = gA + ki * N2C + r0, *bc = gB + ki * N2C + c0;
+            const double a0 = ar[0], a1 = ar[1], a2 = ar[2], a3 = ar[3], b0 = bc[0], b1 = bc[1], b2 = bc[2], b3 = bc[3];
+            acc[s][0] += a0 * b0; acc[s][1] += a0 * b1; acc[s][2] += a0 * b2; acc[s][3] += a0 * b3;
+            acc[s][4] += a1 * b0; acc[s][5] += a1 * b1; acc[s][6] += a1 * b2; acc[s][7] += a1 * b3;
+            acc[s][8] += a2 * b0; acc[s][9] += a2 * b1; acc[s][10] += a2 * b2; acc[s][11] += a2 * b3;
+            acc[s][12] += a3 * b0; acc[s][13] += a3 * b1; acc[s][14] += a3 * b2; acc[s][15] += a3 * b3;
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (!tv[s]) continue;
+        const int r0 = tr[s] * 4, c0 = tc[s] * 4;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i * 4 + j] += av[i] * bv[j];
-      }
-      for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-          const int r = r0 + i, cc = c0 + j;
-          if (r < n2 && cc < n2 && (tr != tc || cc >= r)) {
-            const double v = S[r * n2 + cc] - acc[i * 4 + j];
-            S[r * n2 + cc] = v;
-            if (r != cc) S[cc * n2 + r] = v;
+          for (int j = 0; j < 4; ++j) {
+            const int r = r0 + i, cc = c0 + j;
+            if (r < n2 && cc < n2 && (tr[s] != tc[s] || cc >= r)) {
+              const double v = S[r * n2 + cc] - acc[s][i * 4 + j];
+              S[r * n2 + cc] = v;
+              if (r != cc) S[cc * n2 + r] = v;
+            }
           }
+      }
+    } else {   // very wide borders (more than 88 landmark columns): direct global-memory version
+      for (int t = tid; t < ntile; t += NT) {
+        int tr = 0, rem = t;
+        while (rem >= nt - tr) { rem -= nt - tr; ++tr; }
+        const int tc = tr + rem;
+        const int r0 = tr * 4, c0 = tc * 4;
+        double acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+        for (int ki = 0; ki < 3 * T; ++ki) {
+          const double *br = wBt + (size_t)ki * N2C + r0, *fc = wFB + (size_t)ki * N2C + c0;
+          double av[4], bv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { av[i] = (r0 + i < n2) ? br[i] : 0.0; bv[i] = (c0 + i < n2) ? fc[i] : 0.0; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i * 4 + j] += av[i] * bv[j];
         }
+        for (int i = 0; i < 4; ++i)
+          for (int j = 0; j < 4; ++j) {
+            const int r = r0 + i, cc = c0 + j;
+            if (r < n2 && cc < n2 && (tr != tc || cc >= r)) {
+              const double v = S[r * n2 + cc] - acc[i * 4 + j];
+              S[r * n2 + cc] = v;
+              if (r != cc) S[cc * n2 + r] = v;
+            }
+          }
+      }
     }
   }
   __syncthreads();
@@ -352,25 +422,25 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
     const double pv = colp[p];
     if (tid == 0 && !(pv > 0.0)) s_bad = 1;
     const double piv = 1.0 / pv;
-    const int h = tid >> 6;
+    const int h = tid >> 6;   // NH = NT/64 row groups per column
     for (int c = tid & 63; c < n2; c += 64) {
       double *__restrict__ Sc = S + c;
       const double *__restrict__ cp = colp;
       if (c != p) {
         const double rowpc = Sc[p * n2] * piv;
         int r = h;
-        for (; r + 10 < n2; r += 12) {
-          double s0 = Sc[r * n2], s1 = Sc[(r + 2) * n2], s2 = Sc[(r + 4) * n2], s3 = Sc[(r + 6) * n2], s4 = Sc[(r + 8) * n2], s5 = Sc[(r + 10) * n2];
-          const double c0 = cp[r], c1 = cp[r + 2], c2 = cp[r + 4], c3 = cp[r + 6], c4 = cp[r + 8], c5 = cp[r + 10];
+        for (; r + 5 * NH < n2; r += 6 * NH) {
+          double s0 = Sc[r * n2], s1 = Sc[(r + NH) * n2], s2 = Sc[(r + 2 * NH) * n2], s3 = Sc[(r + 3 * NH) * n2], s4 = Sc[(r + 4 * NH) * n2], s5 = Sc[(r + 5 * NH) * n2];
+          const double c0 = cp[r], c1 = cp[r + NH], c2 = cp[r + 2 * NH], c3 = cp[r + 3 * NH], c4 = cp[r + 4 * NH], c5 = cp[r + 5 * NH];
           s0 -= c0 * rowpc; s1 -= c1 * rowpc; s2 -= c2 * rowpc; s3 -= c3 * rowpc; s4 -= c4 * rowpc; s5 -= c5 * rowpc;
           if (r != p) Sc[r * n2] = s0;
-          if (r + 2 != p) Sc[(r + 2) * n2] = s1;
-          if (r + 4 != p) Sc[(r + 4) * n2] = s2;
-          if (r + 6 != p) Sc[(r + 6) * n2] = s3;
-          if (r + 8 != p) Sc[(r + 8) * n2] = s4;
-          if (r + 10 != p) Sc[(r + 10) * n2] = s5;
+          if (r + NH != p) Sc[(r + NH) * n2] = s1;
+          if (r + 2 * NH != p) Sc[(r + 2 * NH) * n2] = s2;
+          if (r + 3 * NH != p) Sc[(r + 3 * NH) * n2] = s3;
+          if (r + 4 * NH != p) Sc[(r + 4 * NH) * n2] = s4;
+          if (r + 5 * NH != p) Sc[(r + 5 * NH) * n2] = s5;
         }
-        for (; r < n2; r += 2)
+        for (; r < n2; r += NH)
           if (r != p) Sc[r * n2] -= cp[r] * rowpc;
       }
     }
@@ -390,63 +460,57 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
   __syncthreads();
 
   if (a.clocks && tid == 0) a.clocks[8 * b + 4] = clock64();
-  // --------------------------------------------------------------- phase D1 ---
-  // backward substitution: W_k = FB_k - FU_k W_{k+1} (own column), P_k = Dinv_k + FU_k P_{k+1} FU_k^T,
-  // u_k = f_k - FU_k u_{k+1} (redundant 3x3 chain).
+  // --------------------------------------------------------------- phase D ---
+  // backward substitution, per 32-pose chunk (descending):
+  //   D0  warp 0: P_k = Dinv_k + FU_k P_{k+1} FU_k^T (= [Lambda_xx^-1]_kk), u_k = f_k - FU_k u_{k+1};
+  //   D1  column threads: W_k = FB_k - FU_k W_{k+1}  (W = Lambda_xx^-1 Lambda_xl), next row prefetched.
+  // D1 does not depend on D0, so the two run concurrently on different warps.
   {
-    const int c = tid;
-    const bool colv = c < n2;
-    double Wn[3] = {0, 0, 0}, Pn[6] = {0, 0, 0, 0, 0, 0}, un[3] = {0, 0, 0};
+    const int c = ccol;
+    const bool isD = lane < 9, isG = lane >= 9 && lane < 12;
+    const int li = isD ? lane / 3 : (isG ? lane - 9 : 0), lj = isD ? lane % 3 : 0;
+    const int lmin = min(li, lj), lmax = max(li, lj);
+    const int d6 = lmin == 0 ? lmax : (lmin == 1 ? 2 + lmax : 5);
+    double Wn[3] = {0, 0, 0}, Pij = 0.0, ui = 0.0;
     for (int k1 = T; k1 > 0; k1 -= CH) {
       const int k0 = max(0, k1 - CH), kc = k1 - k0;
       __syncthreads();
-      for (int i = tid; i < kc * 18; i += NT) stage[i] = wsp[(size_t)(k0 + i / 18) * WS_POSE + 21 + (i % 18)];
+      for (int i = tid; i < kc * 18; i += NT) stage[(i / 18) * SW + (i % 18)] = wsp[(size_t)(k0 + i / 18) * WS_POSE + 21 + (i % 18)];
       __syncthreads();
-      for (int kk = kc - 1; kk >= 0; --kk) {
-        const int k = k0 + kk;
-        const double *w = stage + kk * 18;
-        double Di[6], fu[9], f[3];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Di[i] = w[i];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) fu[i] = w[6 + i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) f[i] = w[15 + i];
-        // M = fu * Pn (3x3 full), P = Di + M fu^T
-        const double Pm[9] = {Pn[0], Pn[1], Pn[2], Pn[1], Pn[3], Pn[4], Pn[2], Pn[4], Pn[5]};
-        double M[9];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) M[i * 3 + j] = fu[i * 3] * Pm[j] + fu[i * 3 + 1] * Pm[3 + j] + fu[i * 3 + 2] * Pm[6 + j];
-        double P[6];
-        P[0] = Di[0] + M[0] * fu[0] + M[1] * fu[1] + M[2] * fu[2];
-        P[1] = Di[1] + M[0] * fu[3] + M[1] * fu[4] + M[2] * fu[5];
-        P[2] = Di[2] + M[0] * fu[6] + M[1] * fu[7] + M[2] * fu[8];
-        P[3] = Di[3] + M[3] * fu[3] + M[4] * fu[4] + M[5] * fu[5];
-        P[4] = Di[4] + M[3] * fu[6] + M[4] * fu[7] + M[5] * fu[8];
-        P[5] = Di[5] + M[6] * fu[6] + M[7] * fu[7] + M[8] * fu[8];
-        double u[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) u[i] = f[i] - (fu[i * 3] * un[0] + fu[i * 3 + 1] * un[1] + fu[i * 3 + 2] * un[2]);
-        if (tid == 0) {
-          double *wo_ = wsp + (size_t)k * WS_POSE + 39;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) wo_[i] = P[i];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) wo_[6 + i] = u[i];
+      if (warp == 0) {
+        // lane-parallel: lanes 0..8 own P[i][j], lanes 9..11 own u[i]
+        for (int kk = kc - 1; kk >= 0; --kk) {
+          const double *w = stage + kk * SW;   // Dinv(6) FU(9) f(3)
+          // M[i][j] = FU[i][:] P[:][j]
+          const double p0 = __shfl_sync(0xffffffffu, Pij, lj), p1 = __shfl_sync(0xffffffffu, Pij, 3 + lj), p2 = __shfl_sync(0xffffffffu, Pij, 6 + lj);
+          const double fi0 = w[6 + li * 3], fi1 = w[6 + li * 3 + 1], fi2 = w[6 + li * 3 + 2];
+          const double Mij = fi0 * p0 + fi1 * p1 + fi2 * p2;
+          // P'[i][j] = Dinv[i][j] + M[i][:] FU[j][:]
+          const double m0 = __shfl_sync(0xffffffffu, Mij, li * 3), m1 = __shfl_sync(0xffffffffu, Mij, li * 3 + 1), m2 = __shfl_sync(0xffffffffu, Mij, li * 3 + 2);
+          const double un0 = __shfl_sync(0xffffffffu, ui, 9), un1 = __shfl_sync(0xffffffffu, ui, 10), un2 = __shfl_sync(0xffffffffu, ui, 11);
+          double *wo_ = wsp + (size_t)(k0 + kk) * WS_POSE + 39;
+          if (isD) {
+            Pij = w[d6] + m0 * w[6 + lj * 3] + m1 * w[6 + lj * 3 + 1] + m2 * w[6 + lj * 3 + 2];
+            if (lj >= li) wo_[d6] = Pij;
+          } else if (isG) {
+            ui = w[15 + li] - (fi0 * un0 + fi1 * un1 + fi2 * un2);
+            wo_[6 + li] = ui;
+          }
         }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Pn[i] = P[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) un[i] = u[i];
-        if (colv) {
-          double W[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-            W[i] = wFB[((size_t)k * 3 + i) * N2C + c] - (fu[i * 3] * Wn[0] + fu[i * 3 + 1] * Wn[1] + fu[i * 3 + 2] * Wn[2]);
-#pragma unroll
-          for (int i = 0; i < 3; ++i) { wFB[((size_t)k * 3 + i) * N2C + c] = W[i]; Wn[i] = W[i]; }
+      }
+      if (colv) {
+        const int kl = k0 + kc - 1;
+        double nf0 = wFB[((size_t)kl * 3 + 0) * N2C + c], nf1 = wFB[((size_t)kl * 3 + 1) * N2C + c], nf2 = wFB[((size_t)kl * 3 + 2) * N2C + c];
+        for (int kk = kc - 1; kk >= 0; --kk) {
+          const int k = k0 + kk;
+          const double *w = stage + kk * SW + 6;   // FU
+          const double f0 = nf0, f1 = nf1, f2 = nf2;
+          if (kk > 0) { nf0 = wFB[((size_t)(k - 1) * 3 + 0) * N2C + c]; nf1 = wFB[((size_t)(k - 1) * 3 + 1) * N2C + c]; nf2 = wFB[((size_t)(k - 1) * 3 + 2) * N2C + c]; }
+          const double W0 = f0 - (w[0] * Wn[0] + w[1] * Wn[1] + w[2] * Wn[2]);
+          const double W1 = f1 - (w[3] * Wn[0] + w[4] * Wn[1] + w[5] * Wn[2]);
+          const double W2 = f2 - (w[6] * Wn[0] + w[7] * Wn[1] + w[8] * Wn[2]);
+          wFB[((size_t)k * 3 + 0) * N2C + c] = W0; wFB[((size_t)k * 3 + 1) * N2C + c] = W1; wFB[((size_t)k * 3 + 2) * N2C + c] = W2;
+          Wn[0] = W0; Wn[1] = W1; Wn[2] = W2;
         }
       }
     }
@@ -455,42 +519,72 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
 
   if (a.clocks && tid == 0) a.clocks[8 * b + 5] = clock64();
   // ---------------------------------------------------------------- phase E ---
-  // per pose (one warp each): Sigma_kk = P_k + W_k Sigma_ll W_k^T, delta_k = u_k - W_k dl,
-  // estimate = theta (+) delta, information = Sigma_kk^-1 (SLAM2D.cpp:400).
-  double tmax = -1e300;
-  for (int k = warp; k < T; k += NT / 32) {
-    const double *Wk = wFB + (size_t)k * 3 * N2C;
-    double q[6] = {0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
-    for (int c = lane; c < n2; c += 32) {
-      double y0 = 0, y1 = 0, y2 = 0;
-      for (int r = 0; r < n2; ++r) {
-        const double s = S[r * n2 + c];
-        y0 += Wk[r] * s; y1 += Wk[N2C + r] * s; y2 += Wk[2 * N2C + r] * s;
+  // E1  one warp per pose: W_k (3 x n2) staged into shared memory, y = W_k Sigma_ll with two columns per lane,
+  //     q = y W_k^T and v = W_k dl reduced across the warp -> workspace.
+  // E2  one thread per pose: Sigma_kk = P_k + q, delta_k = u_k - v, estimate = theta (+) delta,
+  //     information = Sigma_kk^-1 (SLAM2D.cpp:400).
+  {
+    double *wb = gbuf + (size_t)warp * 3 * N2C;
+    for (int k = warp; k < T; k += NT / 32) {
+      const double *Wk = wFB + (size_t)k * 3 * N2C;
+      __syncwarp();
+      for (int i = lane; i < 3 * N2C; i += 32) wb[i] = Wk[i];
+      __syncwarp();
+      double q[6] = {0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
+      for (int cb = 0; cb < n2; cb += 64) {
+        const int c1 = cb + lane, c2 = cb + 32 + lane;
+        const bool v1 = c1 < n2, v2 = c2 < n2;
+        const int i1 = v1 ? c1 : 0, i2 = v2 ? c2 : 0;
+        double y0 = 0, y1 = 0, y2 = 0, z0 = 0, z1 = 0, z2 = 0;
+        for (int r = 0; r < n2; ++r) {
+          const double w0 = wb[r], w1 = wb[N2C + r], w2 = wb[2 * N2C + r];
+          const double s1 = S[r * n2 + i1], s2 = S[r * n2 + i2];
+          y0 += w0 * s1; y1 += w1 * s1; y2 += w2 * s1;
+          z0 += w0 * s2; z1 += w1 * s2; z2 += w2 * s2;
+        }
+        if (v1) {
+          const double w0 = wb[c1], w1 = wb[N2C + c1], w2 = wb[2 * N2C + c1], d = dl[c1];
+          q[0] += y0 * w0; q[1] += y0 * w1; q[2] += y0 * w2; q[3] += y1 * w1; q[4] += y1 * w2; q[5] += y2 * w2;
+          v[0] += w0 * d; v[1] += w1 * d; v[2] += w2 * d;
+        }
+        if (v2) {
+          const double w0 = wb[c2], w1 = wb[N2C + c2], w2 = wb[2 * N2C + c2], d = dl[c2];
+          q[0] += z0 * w0; q[1] += z0 * w1; q[2] += z0 * w2; q[3] += z1 * w1; q[4] += z1 * w2; q[5] += z2 * w2;
+          v[0] += w0 * d; v[1] += w1 * d; v[2] += w2 * d;
+        }
       }
-      const double w0 = Wk[c], w1 = Wk[N2C + c], w2 = Wk[2 * N2C + c], d = dl[c];
-      q[0] += y0 * w0; q[1] += y0 * w1; q[2] += y0 * w2; q[3] += y1 * w1; q[4] += y1 * w2; q[5] += y2 * w2;
-      v[0] += w0 * d; v[1] += w1 * d; v[2] += w2 * d;
-    }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) q[i] = warp_sum(q[i]);
+      for (int i = 0; i < 6; ++i) q[i] = warp_sum(q[i]);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) v[i] = warp_sum(v[i]);
-    if (lane == 0) {
-      const double *w = wsp + (size_t)k * WS_POSE + 39;
-      double C[6], I[6];
+      for (int i = 0; i < 3; ++i) v[i] = warp_sum(v[i]);
+      if (lane == 0) {
+        double *wo_ = wsp + (size_t)k * WS_POSE;   // slots 0..9 (D, g of phase A) are dead by now
 #pragma unroll
-      for (int i = 0; i < 6; ++i) C[i] = w[i] + q[i];
-      const double d0 = w[6] - v[0], d1 = w[7] - v[1], d2 = w[8] - v[2];
-      dge_sym3_inv(C, I);
-      double *pc = a.pose_cov + ((size_t)b * Tmax + k) * 6, *pi = a.pose_info + ((size_t)b * Tmax + k) * 6;
+        for (int i = 0; i < 6; ++i) wo_[i] = q[i];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { pc[i] = C[i]; pi[i] = I[i]; }
-      del[3 * k] = d0; del[3 * k + 1] = d1; del[3 * k + 2] = d2;
-      const Pose3 e = dge_compose(Pose3{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]}, Pose3{d0, d1, d2});
-      est[3 * k] = e.x; est[3 * k + 1] = e.y; est[3 * k + 2] = e.th;
-      tmax = fmax(tmax, C[0] + C[3] + C[5]);
+        for (int i = 0; i < 3; ++i) wo_[6 + i] = v[i];
+      }
     }
   }
+  __syncthreads();
+  double tmax = -1e300;
+  for (int k = tid; k < T; k += NT) {
+    const double *w = wsp + (size_t)k * WS_POSE;
+    double C[6], I[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) C[i] = w[39 + i] + w[i];
+    const double d0 = w[45] - w[6], d1 = w[46] - w[7], d2 = w[47] - w[8];
+    dge_sym3_inv(C, I);
+    double *pc = a.pose_cov + ((size_t)b * Tmax + k) * 6, *pi = a.pose_info + ((size_t)b * Tmax + k) * 6;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { pc[i] = C[i]; pi[i] = I[i]; }
+    del[3 * k] = d0; del[3 * k + 1] = d1; del[3 * k + 2] = d2;
+    const Pose3 e = dge_compose(Pose3{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]}, Pose3{d0, d1, d2});
+    est[3 * k] = e.x; est[3 * k + 1] = e.y; est[3 * k + 2] = e.th;
+    tmax = fmax(tmax, C[0] + C[3] + C[5]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
   if (lane == 0) red[warp] = tmax;
   // landmarks: delta, estimate, marginal covariance (SLAM2D.cpp:415-424)
   double lerr = 0.0;
@@ -523,7 +617,7 @@ __global__ void __launch_bounds__(NT) k_slam(SlamArgs a, const uint8_t *mask) {
 
 size_t dge_slam_smem_bytes(int Lt) {
   const size_t n2c = 2 * (size_t)Lt;
-  return (n2c * n2c + CH * 21 + 3 * n2c + 2 * (NT / 32)) * sizeof(double) + 2 * (size_t)Lt * sizeof(int) + 16;
+  return (n2c * n2c + CH * SW + 3 * n2c + 2 * (NT / 32) + 2 * GK * 3 * n2c) * sizeof(double) + 2 * (size_t)Lt * sizeof(int) + 16;
 }
 
 int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st) {

@@ -36,7 +36,8 @@ class GraphOut(ctypes.Structure):
     """``struct dge_graph_out`` (include/dge.h)."""
     _fields_ = [("x", ctypes.c_void_p), ("edge_index", ctypes.c_void_p), ("edge_attr", ctypes.c_void_p), ("batch", ctypes.c_void_p),
                 ("node_ptr", ctypes.c_void_p), ("edge_ptr", ctypes.c_void_p), ("key_size", ctypes.c_void_p), ("fro_size", ctypes.c_void_p),
-                ("frontier_xy", ctypes.c_void_p), ("totals", ctypes.c_void_p), ("node_cap", ctypes.c_int64), ("edge_cap", ctypes.c_int64)]
+                ("frontier_xy", ctypes.c_void_p), ("totals", ctypes.c_void_p), ("node_cap", ctypes.c_int64), ("edge_cap", ctypes.c_int64),
+                ("csr_rowptr", ctypes.c_void_p), ("csr_perm", ctypes.c_void_p), ("gcn_norm", ctypes.c_void_p), ("gcn_selfnorm", ctypes.c_void_p)]
 
 
 def load_library():

@@ -67,9 +67,14 @@ class GraphBatch:
         self.frontier_xy = torch.zeros(eng.B, eng.Lt + 1, 2, dtype=torch.float64, device=dev)
         self.totals = torch.zeros(8, dtype=torch.int32, device=dev)
         self.totals_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self.csr_rowptr = torch.zeros(self.node_cap + 1, dtype=torch.int32, device=dev)
+        self.csr_perm = torch.zeros(self.edge_cap, dtype=torch.int32, device=dev)
+        self.gcn_norm = torch.zeros(self.edge_cap, dtype=torch.float32, device=dev)
+        self.gcn_selfnorm = torch.zeros(self.node_cap, dtype=torch.float32, device=dev)
         self.c = GraphOut(self.x.data_ptr(), self.edge_index.data_ptr(), self.edge_attr.data_ptr(), self.batch.data_ptr(),
                           self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.key_size.data_ptr(), self.fro_size.data_ptr(),
-                          self.frontier_xy.data_ptr(), self.totals.data_ptr(), self.node_cap, self.edge_cap)
+                          self.frontier_xy.data_ptr(), self.totals.data_ptr(), self.node_cap, self.edge_cap,
+                          self.csr_rowptr.data_ptr(), self.csr_perm.data_ptr(), self.gcn_norm.data_ptr(), self.gcn_selfnorm.data_ptr())
         self.n_graphs = self.n_nodes = self.n_edges = self.n_done = 0
 
     def sync_sizes(self):
@@ -86,6 +91,12 @@ class GraphBatch:
         """``Data(x, edge_index, edge_attr)`` views of the valid prefix (no copies)."""
         d = Data(self.x[:self.n_nodes], self.edge_index[:, :self.n_edges], self.edge_attr[:self.n_edges], self.batch[:self.n_nodes])
         d.num_graphs = self.n_graphs
+        # the graph kernel already produced the destination-sorted CSR and the GCN normalisation:
+        # hand them to the GNN so that it launches no preprocessing kernels
+        from ..gnn import GraphStructure
+        d._dge_structure = GraphStructure.from_csr(d.edge_index, d.edge_attr, self.n_nodes, self.csr_rowptr[:self.n_nodes + 1],
+                                                   self.csr_perm[:max(self.n_edges, 1)], self.gcn_norm[:max(self.n_edges, 1)],
+                                                   self.gcn_selfnorm[:self.n_nodes])
         return d
 
 

@@ -62,17 +62,49 @@ class GraphStructure:
             ei = ei.long()
         self.src, self.dst = ei[0].contiguous(), ei[1].contiguous()
         self.weight = (torch.ones(self.E, device=dev) if edge_weight is None else edge_weight.contiguous().float())
+        self.rowptr_dst, self.perm_dst = self._build_csr(self.dst)
+        self._src_csr = None
+        self._gcn = {}
+
+    def _build_csr(self, key):
+        global launch_count
+        L, dev = _lib(), key.device
         i32 = dict(dtype=torch.int32, device=dev)
-        self.rowptr_dst, self.perm_dst = torch.empty(self.N + 1, **i32), torch.empty(max(self.E, 1), **i32)
-        self.rowptr_src, self.perm_src = torch.empty(self.N + 1, **i32), torch.empty(max(self.E, 1), **i32)
+        rp, pm = torch.empty(self.N + 1, **i32), torch.empty(max(self.E, 1), **i32)
         ws = torch.empty(2 * self.N + self.E, **i32)
         with torch.cuda.device(dev):
-            for key, rp, pm in ((self.dst, self.rowptr_dst, self.perm_dst), (self.src, self.rowptr_src, self.perm_src)):
-                rc = L.dge_gnn_csr_build(self.N, self.E, _p(key), _p(rp), _p(pm), _p(ws), _st(dev))
-                if rc:
-                    raise DgeError(f"dge_gnn_csr_build failed ({rc})")
-        launch_count += 8
-        self._gcn = {}
+            rc = L.dge_gnn_csr_build(self.N, self.E, _p(key), _p(rp), _p(pm), _p(ws), _st(dev))
+        if rc:
+            raise DgeError(f"dge_gnn_csr_build failed ({rc})")
+        launch_count += 5
+        return rp, pm
+
+    @classmethod
+    def from_csr(cls, edge_index, edge_weight, num_nodes, rowptr_dst, perm_dst, gcn_norm=None, gcn_selfnorm=None):
+        """Adopt a destination-sorted CSR (and, optionally, the improved-GCN normalisation) that was
+        already built on the device (the engine's graph kernel does) -- zero preprocessing launches."""
+        gs = cls.__new__(cls)
+        gs.N, gs.E = int(num_nodes), int(edge_index.shape[1])
+        gs.src, gs.dst = edge_index[0], edge_index[1]
+        gs.weight = edge_weight
+        gs.rowptr_dst, gs.perm_dst = rowptr_dst, perm_dst
+        gs._src_csr = None
+        gs._gcn = {} if gcn_norm is None else {True: (gcn_norm, gcn_selfnorm)}
+        return gs
+
+    @property
+    def rowptr_src(self):
+        return self._source_csr()[0]
+
+    @property
+    def perm_src(self):
+        return self._source_csr()[1]
+
+    def _source_csr(self):
+        """Source-sorted CSR (transposed gather: backward pass, weighted degree) -- built on first use."""
+        if self._src_csr is None:
+            self._src_csr = self._build_csr(self.src.contiguous())
+        return self._src_csr
 
     def gcn_norm(self, improved: bool = True):
         """(norm[E], selfnorm[N]) of GCNConv.norm -- cached per structure."""
@@ -148,6 +180,29 @@ def gcn_aggregate_head(xw: torch.Tensor, bias, gs: GraphStructure, head_w: torch
     norm, selfnorm = gs.gcn_norm(improved)
     _, q = _aggregate(gs, xw, False, norm, selfnorm, bias, None, True, want_out=False, head_w=head_w, head_b=head_b)
     return q
+
+
+def gcn_conv_small_fused(x: torch.Tensor, weight: torch.Tensor, bias, gs: GraphStructure, improved: bool = True, relu: bool = True):
+    """Inference-only first GCN layer: act(bias + (A_hat X) W) with the <= 8 input channels aggregated
+    before the transform (one kernel, no GEMM launch, no [N,C] intermediate)."""
+    global launch_count
+    _need_cuda(x, "gcn_conv_small_fused")
+    L = _lib()
+    if not hasattr(L, "_conv_small_ready"):
+        L.dge_gcn_conv_small.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp]
+        L._conv_small_ready = True
+    norm, selfnorm = gs.gcn_norm(improved)
+    x = x.contiguous().float()
+    N, cin = x.shape
+    C = weight.shape[1]
+    out = torch.empty(N, C, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.dge_gcn_conv_small(N, cin, C, _p(x), _p(gs.rowptr_dst), _p(gs.perm_dst), _p(gs.src), _p(norm), _p(selfnorm),
+                                  _p(weight.contiguous()), _p(None if bias is None else bias.contiguous()), int(relu), _p(out), _st(x.device))
+    if rc:
+        raise DgeError(f"dge_gcn_conv_small failed ({rc})")
+    launch_count += 1
+    return out
 
 
 def weighted_aggregate(x: torch.Tensor, gs: GraphStructure):

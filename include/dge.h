@@ -170,6 +170,12 @@ typedef struct dge_graph_out {
                               graph position), Fmax = Lt+1                              */
   int32_t *totals;         /* [8]: n_graphs, N_tot, E_tot, overflow flag, #envs done, 0, 0, 0   */
   int64_t node_cap, edge_cap;
+  /* optional (all four or none): destination-sorted CSR of the batch + GCNConv(improved) normalisation,
+   * built inside the graph kernel so that the GNN needs no preprocessing launches (dge_gnn.h). */
+  int32_t *csr_rowptr;     /* [Ncap+1]  incoming edges of node n: csr_perm[csr_rowptr[n] .. csr_rowptr[n+1]) */
+  int32_t *csr_perm;       /* [Ecap]    edge ids, ascending inside a row (deterministic summation order)   */
+  float *gcn_norm;         /* [Ecap]    deg^-1/2[src] * w * deg^-1/2[dst], deg includes the self loop of 2 */
+  float *gcn_selfnorm;     /* [Ncap]    2 / deg                                                            */
 } dge_graph_out;
 int dge_graph(dge_handle h, const uint8_t *mask_dev, const dge_graph_out *out, void *stream);
 

@@ -35,6 +35,11 @@ int dge_gnn_aggregate(int N, int C, const float *X, const int32_t *rowptr, const
                       const float *coef, const float *selfcoef, const float *bias, const float *gate, int relu, float *out,
                       const float *head_w, float head_b, float *q, void *stream);
 
+/* First GCN layer fused (GCNConv(5 -> C), Networks.py:15,22): out = act(bias + (A_hat X) W) with the
+ * Cin <= 8 input channels aggregated BEFORE the transform; W [Cin,C] row-major.  Inference only. */
+int dge_gcn_conv_small(int N, int Cin, int C, const float *X, const int32_t *rowptr, const int32_t *perm, const int64_t *nbr,
+                       const float *coef, const float *selfcoef, const float *W, const float *bias, int relu, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
