@@ -131,7 +131,7 @@ class GpuLoop:
         g = env.build_graph(need); self.launches += 3
         ng, n, e = g.sync_sizes()      # the tick's only host sync: graph sizes + number of finished episodes
         if g.n_done > 0:               # episode ends: reset (4 forced steps) those envs, they decide next tick
-            env.reset_done(); self.launches += 2 + 4 * 5
+            env.reset_done(in_pipeline=True); self.launches += 1
         if ng > 0:
             l0 = self.gnn.launch_count
             q = self.model(g.data(), 0.0)

@@ -26,6 +26,9 @@ struct SimArgs {
   double *prob, *vinfo, *metrics, *dist, *rdist, *plan;
   int32_t *plan_cursor;
   uint8_t *done, *active;
+  int32_t *forced;      // [B] forced steps left after an in-pipeline reset; DGE_FRESH_BIT = reset this tick
+  uint8_t *step_kind;   // [B] 1 = the last step was a policy step (counted), 0 = forced / fresh
+  double forced_odom[3];
 };
 
 // Association scan for the pose that was just appended (index k).  Lanes stride over the
@@ -87,7 +90,7 @@ __device__ void measure_append(const SimArgs &a, int b, int k, const double *noi
 }
 
 __global__ void __launch_bounds__(32) k_reset(SimArgs a, const uint8_t *mask, const uint64_t *seeds, const double *start,
-                                              const double *lm, const int32_t *scan, const double *noise) {
+                                              const double *lm, const int32_t *scan, const double *noise, int n_forced) {
   const int b = blockIdx.x, lane = threadIdx.x;
   if (mask && !mask[b]) return;
   const int Lt = a.d.Lt;
@@ -146,6 +149,10 @@ __global__ void __launch_bounds__(32) k_reset(SimArgs a, const uint8_t *mask, co
     a.dist[b] = 0; a.rdist[b] = 0; a.done[b] = 0; a.active[b] = 1;
     for (int i = 0; i < 6; ++i) a.plan[6 * b + i] = 0;
     a.plan_cursor[b] = 0;
+    // in-pipeline reset: the initial optimize() and the forced steps of ExplorationEnv.reset
+    // (exploration_env.py:411-414) ride along the next queued ticks instead of extra launches
+    a.forced[b] = n_forced > 0 ? (n_forced | DGE_FRESH_BIT) : 0;
+    a.step_kind[b] = 0;
   }
   __syncwarp();
   __threadfence_block();
@@ -158,8 +165,17 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
   const int Lt = a.d.Lt;
   bool act = !(mask && !mask[b]);
   double ox = 0, oy = 0, oth = 0;
+  int fl = 0;
+  if (act && from_queue == 1) {
+    fl = a.forced[b];
+    if (fl & DGE_FRESH_BIT) {   // reset earlier in this tick: no move, but SLAM (the initial optimize) runs
+      if (lane == 0) { a.forced[b] = fl & ~DGE_FRESH_BIT; a.active[b] = 1; a.step_kind[b] = 0; }
+      return;
+    }
+  }
   if (act) {
-    if (from_queue) {  // expand the compact line plan (Planner2D.cpp:982-1038)
+    if (fl > 0) { ox = a.forced_odom[0]; oy = a.forced_odom[1]; oth = a.forced_odom[2]; }
+    else if (from_queue) {  // expand the compact line plan (Planner2D.cpp:982-1038)
       const double *pl = a.plan + 6 * b;
       const int cur = a.plan_cursor[b], nrot = (int)pl[0], nfwd = (int)pl[3], nact = (int)pl[5];
       if (cur >= nact) act = false;
@@ -176,7 +192,7 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
   // (like the reference, a finished episode can still be stepped explicitly; only the queued
   //  mode parks `done` envs until the caller resets them)
   if (act && from_queue == 1 && a.done[b]) act = false;   // from_queue == 2: roll-out clones run their whole plan
-  if (lane == 0) a.active[b] = act ? 1 : 0;
+  if (lane == 0) { a.active[b] = act ? 1 : 0; a.step_kind[b] = (act && fl == 0) ? 1 : 0; }
   if (!act) return;
   const uint64_t key = a.seed[b];
   const uint64_t step_ctr = (uint64_t)a.sim_step[b] | ((uint64_t)a.update_count[b] << 32);
@@ -203,7 +219,8 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
     a.sim_step[b] += 1;
     a.dist[b] += sqrt(ox * ox + oy * oy);  // exploration_env.py:103
     a.rdist[b] += sqrt(ox * ox + oy * oy + a.cfg.angle_weight * oth * oth);   // Planner2D.cpp:1440 (roll-out distance)
-    if (from_queue) a.plan_cursor[b] += 1;
+    if (fl > 0) a.forced[b] = fl - 1;
+    else if (from_queue) a.plan_cursor[b] += 1;
   }
   __syncwarp();
   __threadfence_block();
@@ -222,14 +239,16 @@ SimArgs make_args(dge_engine *e, uint8_t *active) {
   a.observed = e->observed; a.lin_l = e->lin_l; a.est_l = e->est_l; a.delta_l = e->delta_l;
   a.prob = e->prob; a.vinfo = e->vinfo; a.metrics = e->metrics; a.dist = e->dist; a.rdist = e->rdist; a.plan = e->plan; a.plan_cursor = e->plan_cursor;
   a.done = e->done; a.active = active;
+  a.forced = e->forced; a.step_kind = e->step_kind;
+  for (int i = 0; i < 3; ++i) a.forced_odom[i] = e->forced_odom[i];
   return a;
 }
 
 }  // namespace
 
 int dge_launch_reset(dge_engine *e, const uint8_t *mask, const uint64_t *seeds, const double *start, const double *lm,
-                     const int32_t *scan, const double *noise, cudaStream_t st) {
-  k_reset<<<e->d.B, 32, 0, st>>>(make_args(e, e->active), mask, seeds, start, lm, scan, noise);
+                     const int32_t *scan, const double *noise, int n_forced, cudaStream_t st) {
+  k_reset<<<e->d.B, 32, 0, st>>>(make_args(e, e->active), mask, seeds, start, lm, scan, noise, n_forced);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }
 

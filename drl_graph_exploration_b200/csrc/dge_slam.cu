@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   __syncthreads();
   const int nl = s_nl, n2 = 2 * nl;
 
-  if (a.clocks && tid == 0) a.clocks[8 * b + 0] = clock64();
+  if (a.clocks && tid == 0) a.clocks[12 * b +0] = clock64();
   // ---------------------------------------------------------------- phase A ---
   // whitened linearisation of every factor at theta.
   // A1: one thread per bearing-range factor (BearingRangeFactor<Pose2,Point2>): pose-pose, pose-landmark
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   }
   __syncthreads();
 
-  if (a.clocks && tid == 0) a.clocks[8 * b + 1] = clock64();
+  if (a.clocks && tid == 0) a.clocks[12 * b +1] = clock64();
   // ---------------------------------------------------------------- phase B ---
   // forward elimination along the chain, per 32-pose chunk:
   //   B0  warp 0 runs the 3x3 pose recurrence  D~_k = D_k - U_{k-1}^T D~_{k-1}^-1 U_{k-1}  (fp64 issue is
@@ -237,11 +237,13 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     const int s11 = i1 * 3 + j1, s22 = i2 * 3 + j2, s12 = i1 * 3 + j2, s21 = i2 * 3 + j1;
     double cDij = 0.0, cgi = 0.0, gprev = 0.0;                                       // warp-0 carried state
     double cB[3] = {0, 0, 0}, sd0 = 0, sd1 = 0, glc = 0;                             // column state
+    long long tB0 = 0, tB1 = 0, tc0 = 0;
     for (int k0 = 0; k0 < T; k0 += CH) {
       const int kc = min(CH, T - k0);
       __syncthreads();
       for (int i = tid; i < kc * 21; i += NT) stage[(i / 21) * SW + (i % 21)] = wsp[(size_t)(k0 + i / 21) * WS_POSE + (i % 21)];
       __syncthreads();
+      if (a.clocks && tid == 0) tc0 = clock64();
       if (warp == 0) {
         // lane-parallel 3x3 recurrence: lanes 0..8 own entry (i,j) of the pose block, lanes 9..11 entry i of the
         // rhs; operands of other lanes come by warp shuffle.  ~45 instructions on the loop-carried path instead
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
         }
       }
       __syncthreads();
+      if (a.clocks && tid == 0) { const long long t1 = clock64(); tB0 += t1 - tc0; tc0 = t1; }
       if (colv) {
         double nb0 = wBt[((size_t)k0 * 3 + 0) * N2C + c], nb1 = wBt[((size_t)k0 * 3 + 1) * N2C + c], nb2 = wBt[((size_t)k0 * 3 + 2) * N2C + c];
         int np1 = wmi[(size_t)k0 * Lt + jr];
@@ -306,9 +309,11 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
           wFB[((size_t)k * 3 + 0) * N2C + c] = fb0; wFB[((size_t)k * 3 + 1) * N2C + c] = fb1; wFB[((size_t)k * 3 + 2) * N2C + c] = fb2;
         }
       }
+      if (a.clocks) { __syncthreads(); if (tid == 0) tB1 += clock64() - tc0; }
     }
     // seed S with the landmark-landmark blocks (block diagonal), gl with the reduced rhs
     __syncthreads();
+    if (a.clocks && tid == 0) { a.clocks[12 * b + 8] = tB0; a.clocks[12 * b + 9] = tB1; }
     for (int i = tid; i < n2 * n2; i += NT) S[i] = 0.0;
     __syncthreads();
     if (colv) {
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   }
   __syncthreads();
 
-  if (a.clocks && tid == 0) a.clocks[8 * b + 2] = clock64();
+  if (a.clocks && tid == 0) a.clocks[12 * b +2] = clock64();
   // ---------------------------------------------------------------- phase S ---
   // Schur complement S -= sum_k Bt_k^T FB_k : an n2 x 3T x n2 GEMM.  Border rows are staged through shared
   // memory GK poses at a time (one linear, coalesced copy per operand); every thread keeps up to two 4x4
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   }
   __syncthreads();
 
-  if (a.clocks && tid == 0) a.clocks[8 * b + 3] = clock64();
+  if (a.clocks && tid == 0) a.clocks[12 * b +3] = clock64();
   // ---------------------------------------------------------------- phase C ---
   // Sigma_ll = S^-1 (in-place Gauss-Jordan on the SPD Schur complement), dl = Sigma_ll gl
   // Thread (c, h): column c = tid % 64 (+64 for a second pass when n2 > 64), rows r = h mod 2.
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   }
   __syncthreads();
 
-  if (a.clocks && tid == 0) a.clocks[8 * b + 4] = clock64();
+  if (a.clocks && tid == 0) a.clocks[12 * b +4] = clock64();
   // --------------------------------------------------------------- phase D ---
   // backward substitution, per 32-pose chunk (descending):
   //   D0  warp 0: P_k = Dinv_k + FU_k P_{k+1} FU_k^T (= [Lambda_xx^-1]_kk), u_k = f_k - FU_k u_{k+1};
@@ -517,7 +522,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   }
   __syncthreads();
 
-  if (a.clocks && tid == 0) a.clocks[8 * b + 5] = clock64();
+  if (a.clocks && tid == 0) a.clocks[12 * b +5] = clock64();
   // ---------------------------------------------------------------- phase E ---
   // E1  one warp per pose: W_k (3 x n2) staged into shared memory, y = W_k Sigma_ll with two columns per lane,
   //     q = y W_k^T and v = W_k dl reduced across the warp -> workspace.
@@ -608,7 +613,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     a.metrics[8 * b + 4] = le / Lt;   // ExplorationEnv.get_landmark_error  exploration_env.py:170-176
     a.metrics[8 * b + 5] = m;         // max_uncertainty_of_trajectory        exploration_env.py:190-194
     a.update_count[b] = uc;
-    if (a.clocks) { a.clocks[8 * b + 6] = clock64(); a.clocks[8 * b + 7] = T; }
+    if (a.clocks) { a.clocks[12 * b +6] = clock64(); a.clocks[12 * b +7] = T; }
     if (s_bad) a.status[b] = 1;
   }
 }

@@ -185,10 +185,10 @@ __global__ void __launch_bounds__(TILE * TILE) k_vmap_cells(VmapCfg c, int Tstri
 __global__ void __launch_bounds__(256) k_vmap_metrics(dge_config cfg, DgeDims d, const double *prob, const double *vinfo,
                                                       const int32_t *sim_step, const int32_t *status, const double *dist,
                                                       double *metrics, uint8_t *done, const uint8_t *mask,
-                                                      const int32_t *n_poses, const int32_t *meas_ptr, unsigned long long *counters) {
+                                                      const int32_t *n_poses, const int32_t *meas_ptr, unsigned long long *counters, const uint8_t *step_kind) {
   const int b = blockIdx.x;
   if (mask && !mask[b]) return;
-  if (threadIdx.x == 0 && counters) {   // integer work counters (order-independent): env-steps, sum T, sum M
+  if (threadIdx.x == 0 && counters && step_kind[b]) {   // integer work counters (order-independent): env-steps, sum T, sum M
     const int T = n_poses[b];
     atomicAdd(&counters[0], 1ull);
     atomicAdd(&counters[1], (unsigned long long)T);
@@ -264,7 +264,7 @@ int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
   k_vmap_cells<<<dim3(tiles, e->d.B), TILE * TILE, 0, st>>>(c, e->d.Tmax, e->n_poses, 0, e->vm_prep, e->vm_cbox, nchm, e->est_l, e->observed,
                                                              e->d.Lt, e->d.Lt, e->prob, e->vinfo, e->seen, mask);
   k_vmap_metrics<<<e->d.B, 256, 0, st>>>(e->cfg, e->d, e->prob, e->vinfo, e->sim_step, e->status, e->dist, e->metrics, e->done, mask,
-                                         e->n_poses, e->meas_ptr, e->count_steps ? e->counters : nullptr);
+                                         e->n_poses, e->meas_ptr, e->count_steps ? e->counters : nullptr, e->step_kind);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }
 

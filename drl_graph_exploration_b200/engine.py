@@ -29,7 +29,7 @@ class _StateView(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "n_poses", "sim_step", "update_count", "true_pose", "est_pose", "lin_pose", "delta_pose", "pose_cov", "pose_info",
         "odom", "meas_ptr", "meas_id", "meas_bearing", "meas_range", "lm_true", "scan_id", "observed", "est_l", "lin_l",
-        "land_cov", "prob", "vinfo", "seen", "metrics", "done", "active", "status", "plan", "plan_cursor", "slam_clocks", "counters")]
+        "land_cov", "prob", "vinfo", "seen", "metrics", "done", "active", "status", "plan", "plan_cursor", "slam_clocks", "counters", "forced")]
 
 
 class GraphOut(ctypes.Structure):
@@ -55,6 +55,7 @@ def load_library():
         vp = ctypes.c_void_p
         L.dge_reset.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         L.dge_step.argtypes = [vp, vp, vp, vp, vp]
+        L.dge_reset_queued.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.dge_step_queued.argtypes = [vp, vp]
         L.dge_move_measure_queued.argtypes = [vp, vp]
         L.dge_set_counting.argtypes = [vp, ctypes.c_int]
@@ -130,7 +131,7 @@ class Engine:
             "lin_l": ((B, L, 2), torch.float64), "land_cov": ((B, L, 3), torch.float64), "prob": ((B, self.rows, self.cols), torch.float64),
             "vinfo": ((B, self.rows, self.cols, 3), torch.float64), "seen": ((B, self.rows, self.cols), torch.int32),
             "metrics": ((B, 8), torch.float64), "done": ((B,), torch.uint8), "active": ((B,), torch.uint8), "status": ((B,), torch.int32),
-            "plan": ((B, 6), torch.float64), "plan_cursor": ((B,), torch.int32), "counters": ((4,), torch.int64), "slam_clocks": ((B, 8), torch.int64),
+            "plan": ((B, 6), torch.float64), "plan_cursor": ((B,), torch.int32), "counters": ((4,), torch.int64), "slam_clocks": ((B, 12), torch.int64), "forced": ((B,), torch.int32),
         }
         self.state = {}
         for name, (shape, dt) in spec.items():
@@ -157,6 +158,13 @@ class Engine:
         self._chk(scan, (self.B, self.Lt), torch.int32); self._chk(noise, (self.B, self.noise_len), torch.float64)
         _check(self._L.dge_reset(self._h, _ptr(mask), _ptr(seeds), _ptr(start), _ptr(landmarks), _ptr(scan), _ptr(noise),
                                  _stream_ptr(self.device)), "dge_reset")
+
+    def reset_queued(self, seeds: torch.Tensor, mask: Optional[torch.Tensor], forced_odom, n_forced: int, start: Optional[torch.Tensor] = None):
+        """dge_reset_queued: in-pipeline reset (the initial optimize and the forced steps ride along the next queued ticks)."""
+        self._chk(seeds, (self.B,), torch.int64); self._chk(mask, (self.B,), torch.uint8); self._chk(start, (self.B, 3), torch.float64)
+        fo = (ctypes.c_double * 3)(*[float(v) for v in forced_odom])
+        _check(self._L.dge_reset_queued(self._h, _ptr(mask), _ptr(seeds), _ptr(start), None, None, fo, int(n_forced),
+                                        _stream_ptr(self.device)), "dge_reset_queued")
 
     def step(self, odom: torch.Tensor, mask: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None):
         self._chk(odom, (self.B, 3), torch.float64); self._chk(mask, (self.B,), torch.uint8)

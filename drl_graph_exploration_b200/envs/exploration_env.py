@@ -136,11 +136,17 @@ class VecExplorationEnv:
         eng._L.dge_set_counting(eng._h, 1)
         return eng.state["prob"]
 
-    def reset_done(self):
-        """Re-seed and reset the envs whose episode ended (device-side mask, no host sync)."""
+    def reset_done(self, in_pipeline: bool = False):
+        """Re-seed and reset the envs whose episode ended (device-side mask, no host sync).
+        ``in_pipeline``: only the world generation is launched now; the initial optimize() and the 4 forced
+        steps are executed by the next 5 ``step_queued`` ticks together with the other envs' steps (same
+        per-env operation sequence and Philox draws as the eager reset, one launch instead of 21)."""
         done = self.eng.state["done"].clone()
         self._seeds = torch.where(done.bool(), self._seeds + self.B, self._seeds)
-        self.reset(mask=done)
+        if in_pipeline:
+            self.eng.reset_queued(self._seeds, done, RESET_ODOM, 4)
+        else:
+            self.reset(mask=done)
         return done
 
     # ----------------------------------------------------------------- step ---
@@ -155,7 +161,7 @@ class VecExplorationEnv:
     def needs_decision(self) -> torch.Tensor:
         """[B] u8: envs whose action queue is empty (and are not done)."""
         st = self.eng.state
-        return ((st["plan_cursor"] >= st["plan"][:, 5].to(torch.int32)) & (st["done"] == 0)).to(torch.uint8)
+        return ((st["plan_cursor"] >= st["plan"][:, 5].to(torch.int32)) & (st["done"] == 0) & (st["forced"] == 0)).to(torch.uint8)
 
     # ---------------------------------------------------------------- graph ---
     def build_graph(self, mask: Optional[torch.Tensor] = None) -> GraphBatch:

@@ -73,6 +73,15 @@ int dge_dims(dge_handle h, int32_t *out);
 int dge_reset(dge_handle h, const uint8_t *mask_dev, const uint64_t *seeds_dev, const double *start_dev,
               const double *lm_dev, const int32_t *scan_dev, const double *noise_dev, void *stream);
 
+/* in-pipeline reset for the queued loop: same world generation as dge_reset, but the initial
+ * optimize() (pyss2d.py:135) and the n_forced forced actions of ExplorationEnv.reset
+ * (exploration_env.py:411-414, `forced_odom_host` = (1, 1, pi/2)) are executed by the next
+ * 1 + n_forced calls of dge_step_queued together with every other env's step -- a reset costs one small
+ * launch instead of 1 + 5*n_forced.  Forced steps are not counted in `counters` and the env asks for no decision
+ * (dge_state_view.forced != 0) until they are done.                                          */
+int dge_reset_queued(dge_handle h, const uint8_t *mask_dev, const uint64_t *seeds_dev, const double *start_dev,
+                     const double *lm_dev, const int32_t *scan_dev, const double *forced_odom_host, int n_forced, void *stream);
+
 /* ---- step: replaces ExplorationEnv.step -> SS2D.simulate (exploration_env.py:98-105,
  * pyss2d.py:171-206): Simulator2D.move + SLAM2D.add_odometry, Simulator2D.measure (x2),
  * SLAM2D.add_measurement, SLAM2D.optimize(update_covariance=True),
@@ -144,9 +153,10 @@ typedef struct dge_state_view {
   const int32_t *status;         /* [B] 0 ok, DGE_ECAP, or 1 = solver breakdown       */
   const double *plan;            /* [B,6] queued line plan (see dge_line_plan)        */
   const int32_t *plan_cursor;    /* [B] next action of the plan                       */
-  const int64_t *slam_clocks;    /* [B,8] SM clock at the 7 phase boundaries of the last SLAM launch, [.,7] = T */
+  const int64_t *slam_clocks;    /* [B,12] SM clock at the 7 phase boundaries of the last SLAM launch, [.,7] = T, [.,8..9] = cycles in the pose / border recurrences */
   const int64_t *counters;       /* [4] work counters: env-steps, sum of trajectory lengths, sum of
                                     measurement counts over those steps, reserved            */
+  const int32_t *forced;         /* [B] forced steps still queued by dge_reset_queued (bit 30 = initial optimize pending) */
 } dge_state_view;
 int dge_get_state(dge_handle h, dge_state_view *out);
 /* steps launched while counting is off (e.g. the 4 forced steps of a reset) do not touch `counters` */
