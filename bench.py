@@ -103,7 +103,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------- GPU arm ---
 class GpuLoop:
-    def __init__(self, device, seed0):
+    def __init__(self, device, seed0, overlap=True):
         from drl_graph_exploration_b200 import Networks, gnn
         from drl_graph_exploration_b200.config import EnvConfig
         from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv
@@ -115,6 +115,8 @@ class GpuLoop:
         self.model = Networks.GCN().to(self.env.device).eval()
         self.env.reset()
         self.dev = self.env.device
+        from drl_graph_exploration_b200.runner import PolicyLoop
+        self.runner = PolicyLoop(self.env, self.model, overlap=overlap)
         self.launches = 0
         self.ev = {k: [] for k in ("slam", "vmap")}
         self.graphs = 0
@@ -123,36 +125,11 @@ class GpuLoop:
         """(policy env-steps, sum of trajectory lengths, sum of measurement counts) accumulated by the engine."""
         return [int(v) for v in self.env.eng.state["counters"].tolist()[:3]]
 
-    @torch.no_grad()
     def tick(self, timed=False):
-        env, eng = self.env, self.env.eng
-        st = eng.state
-        need = env.needs_decision()
-        g = env.build_graph(need); self.launches += 3
-        ng, n, e = g.sync_sizes()      # the tick's only host sync: graph sizes + number of finished episodes
-        if g.n_done > 0:               # episode ends: reset (4 forced steps) those envs, they decide next tick
-            env.reset_done(in_pipeline=True); self.launches += 1
-        if ng > 0:
-            l0 = self.gnn.launch_count
-            q = self.model(g.data(), 0.0)
-            env.select_and_plan(q, need)
-            self.launches += self.gnn.launch_count - l0 + 1
-            self.graphs += ng
-        # one simulator step for every env (staged calls == dge_step_queued, with events around the stages)
-        from drl_graph_exploration_b200.engine import _check, _ptr, _stream_ptr
-        sp = _stream_ptr(self.dev)
-        _check(eng._L.dge_move_measure_queued(eng._h, sp), "move_measure_queued")
-        if timed:
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
-        _check(eng._L.dge_slam_optimize(eng._h, _ptr(st["active"]), sp), "slam")
-        if timed:
-            e1.record()
-        _check(eng._L.dge_virtual_map(eng._h, _ptr(st["active"]), sp), "vmap")
-        if timed:
-            e2.record()
-            self.ev["slam"].append((e0, e1)); self.ev["vmap"].append((e1, e2))
-        self.launches += 5
+        """One tick of drl_graph_exploration_b200.runner.PolicyLoop (step pipeline || policy pipeline)."""
+        self.runner.stage_events = self.ev if timed else None
+        self.runner.tick()
+        self.launches, self.graphs = self.runner.launches, self.runner.graphs
 
 
 def e2e_loop(loop: GpuLoop):
@@ -216,6 +193,7 @@ def main():
     ap.add_argument("--no-flush-l2", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the step and policy pipelines on one stream (A/B of the overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,7 +209,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = local
     torch.cuda.set_device(device)
-    loop = GpuLoop(device, seed0=rank * 100000)
+    loop = GpuLoop(device, seed0=rank * 100000, overlap=not args.no_overlap)
     flush = None if args.no_flush_l2 else torch.empty(256 << 20, dtype=torch.uint8, device=loop.dev)
 
     for _ in range(args.warmup):
@@ -242,7 +220,7 @@ def main():
     sampler = ClockSampler(device) if rank == 0 else None
     if sampler:
         sampler.start()
-    loop.launches = 0; loop.graphs = 0
+    loop.runner.launches = 0; loop.runner.graphs = 0
     c_start = loop.counters()
     tick_events = []
     for _ in range(args.steps):

@@ -110,7 +110,7 @@ extern "C" int dge_reset(dge_handle h, const uint8_t *mask, const uint64_t *seed
                          const int32_t *scan, const double *noise, void *stream) {
   if (!h) return DGE_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = dge_launch_reset(h, mask, seeds, start, lm, scan, noise, 0, st);
+  int rc = dge_launch_reset(h, mask, seeds, start, lm, scan, noise, 0, 0, st);
   if (rc) return fail(rc, "dge_reset: k_reset");
   rc = dge_launch_slam(h, mask, st);   // pyss2d.py:135 self.optimize()
   if (rc) return fail(rc, "dge_reset: k_slam");
@@ -121,8 +121,15 @@ extern "C" int dge_reset_queued(dge_handle h, const uint8_t *mask, const uint64_
                                 const int32_t *scan, const double *forced_odom_host, int n_forced, void *stream) {
   if (!h || !forced_odom_host || n_forced < 1 || n_forced >= DGE_FRESH_BIT) return fail(DGE_EINVAL, "dge_reset_queued: bad arguments");
   for (int i = 0; i < 3; ++i) h->forced_odom[i] = forced_odom_host[i];
-  const int rc = dge_launch_reset(h, mask, seeds, start, lm, scan, nullptr, n_forced, static_cast<cudaStream_t>(stream));
+  const int rc = dge_launch_reset(h, mask, seeds, start, lm, scan, nullptr, n_forced, 0, static_cast<cudaStream_t>(stream));
   return rc ? fail(rc, "dge_reset_queued: k_reset") : DGE_OK;
+}
+
+extern "C" int dge_reset_done_queued(dge_handle h, uint64_t seed_stride, const double *forced_odom_host, int n_forced, void *stream) {
+  if (!h || !forced_odom_host || seed_stride == 0 || n_forced < 1 || n_forced >= DGE_FRESH_BIT) return fail(DGE_EINVAL, "dge_reset_done_queued: bad arguments");
+  for (int i = 0; i < 3; ++i) h->forced_odom[i] = forced_odom_host[i];
+  const int rc = dge_launch_reset(h, h->done, nullptr, nullptr, nullptr, nullptr, nullptr, n_forced, seed_stride, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_reset_done_queued: k_reset") : DGE_OK;
 }
 
 extern "C" int dge_move_measure(dge_handle h, const double *odom, const uint8_t *mask, const double *noise, void *stream) {
@@ -213,7 +220,7 @@ extern "C" int dge_get_state(dge_handle h, dge_state_view *o) {
   o->meas_ptr = h->meas_ptr; o->meas_id = h->meas_id; o->meas_bearing = h->meas_b; o->meas_range = h->meas_r;
   o->lm_true = h->lm_true; o->scan_id = h->scan_id; o->observed = h->observed; o->est_l = h->est_l; o->lin_l = h->lin_l;
   o->land_cov = h->land_cov; o->prob = h->prob; o->vinfo = h->vinfo; o->seen = h->seen; o->metrics = h->metrics; o->done = h->done; o->active = h->active; o->status = h->status;
-  o->forced = h->forced; o->plan = h->plan; o->plan_cursor = h->plan_cursor; o->counters = reinterpret_cast<const int64_t *>(h->counters); o->slam_clocks = reinterpret_cast<const int64_t *>(h->slam_clocks);
+  o->forced = h->forced; o->seed = reinterpret_cast<const int64_t *>(h->seed); o->plan = h->plan; o->plan_cursor = h->plan_cursor; o->counters = reinterpret_cast<const int64_t *>(h->counters); o->slam_clocks = reinterpret_cast<const int64_t *>(h->slam_clocks);
   return DGE_OK;
 }
 

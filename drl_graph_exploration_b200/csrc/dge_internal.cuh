@@ -70,7 +70,7 @@ struct dge_engine {
   int32_t *r_cmap;       // [B,2] (as roll-out engine) source env / frontier of each clone slot
   int32_t *r_cbase;      // [B]   (as source engine) first clone slot of each env
   double *r_u0;          // [B]   (as roll-out engine) utility before the roll-out
-  unsigned long long *counters;   // [4] work counters: policy env-steps, sum of T, sum of M, reserved
+  unsigned long long *counters;   // [4] work counters: policy env-steps, sum of T, sum of M, episodes restarted by dge_reset_done_queued
   long long *slam_clocks; // [B,12] phase-boundary clocks of the last k_slam launch (+ T in slot 7, sub-phase cycles in 8..11)
   int32_t *forced;       // [B] forced steps left after an in-pipeline reset (| DGE_FRESH_BIT while the initial optimize is pending)
   uint8_t *step_kind;    // [B] 1 = the env's last step was a policy step
@@ -175,7 +175,7 @@ __device__ __forceinline__ void dge_normal2(uint64_t key, uint64_t ctr_lo, uint6
 
 // launch entry points implemented in the .cu files
 int dge_launch_reset(dge_engine *e, const uint8_t *mask, const uint64_t *seeds, const double *start, const double *lm,
-                     const int32_t *scan, const double *noise, int n_forced, cudaStream_t st);
+                     const int32_t *scan, const double *noise, int n_forced, uint64_t seed_stride, cudaStream_t st);
 int dge_launch_move_measure(dge_engine *e, const double *odom, const uint8_t *mask, const double *noise, int from_queue, cudaStream_t st);
 int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st);
 int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st);

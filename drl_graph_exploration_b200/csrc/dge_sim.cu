@@ -90,13 +90,15 @@ __device__ void measure_append(const SimArgs &a, int b, int k, const double *noi
 }
 
 __global__ void __launch_bounds__(32) k_reset(SimArgs a, const uint8_t *mask, const uint64_t *seeds, const double *start,
-                                              const double *lm, const int32_t *scan, const double *noise, int n_forced) {
+                                              const double *lm, const int32_t *scan, const double *noise, int n_forced, uint64_t seed_stride,
+                                              unsigned long long *episodes) {
   const int b = blockIdx.x, lane = threadIdx.x;
   if (mask && !mask[b]) return;
   const int Lt = a.d.Lt;
-  if (seeds && lane == 0) a.seed[b] = seeds[b];
+  // the mask may be the env's own `done` flag (dge_reset_done_queued): it is cleared below, after this read
+  const uint64_t key = seeds ? seeds[b] : a.seed[b] + seed_stride;
   __syncwarp();
-  const uint64_t key = seeds ? seeds[b] : a.seed[b];
+  if (lane == 0) { a.seed[b] = key; if (episodes) atomicAdd(episodes, 1ull); }
   // ---- start pose (pyss2d.py:88-95: integer x/y on the *map* half-width, whole-degree heading; q2)
   double sx, sy, sth;
   if (start) { sx = start[3 * b]; sy = start[3 * b + 1]; sth = start[3 * b + 2]; }
@@ -247,8 +249,9 @@ SimArgs make_args(dge_engine *e, uint8_t *active) {
 }  // namespace
 
 int dge_launch_reset(dge_engine *e, const uint8_t *mask, const uint64_t *seeds, const double *start, const double *lm,
-                     const int32_t *scan, const double *noise, int n_forced, cudaStream_t st) {
-  k_reset<<<e->d.B, 32, 0, st>>>(make_args(e, e->active), mask, seeds, start, lm, scan, noise, n_forced);
+                     const int32_t *scan, const double *noise, int n_forced, uint64_t seed_stride, cudaStream_t st) {
+  k_reset<<<e->d.B, 32, 0, st>>>(make_args(e, e->active), mask, seeds, start, lm, scan, noise, n_forced, seed_stride,
+                                 seed_stride ? e->counters + 3 : nullptr);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }
 

@@ -81,6 +81,9 @@ int dge_reset(dge_handle h, const uint8_t *mask_dev, const uint64_t *seeds_dev, 
  * (dge_state_view.forced != 0) until they are done.                                          */
 int dge_reset_queued(dge_handle h, const uint8_t *mask_dev, const uint64_t *seeds_dev, const double *start_dev,
                      const double *lm_dev, const int32_t *scan_dev, const double *forced_odom_host, int n_forced, void *stream);
+/* the same for every env whose `done` flag is set, entirely device-side (no mask to build, no host sync):
+ * the env's Philox key advances by seed_stride (> 0), `done` is cleared, counters[3] counts the restart. */
+int dge_reset_done_queued(dge_handle h, uint64_t seed_stride, const double *forced_odom_host, int n_forced, void *stream);
 
 /* ---- step: replaces ExplorationEnv.step -> SS2D.simulate (exploration_env.py:98-105,
  * pyss2d.py:171-206): Simulator2D.move + SLAM2D.add_odometry, Simulator2D.measure (x2),
@@ -155,8 +158,10 @@ typedef struct dge_state_view {
   const int32_t *plan_cursor;    /* [B] next action of the plan                       */
   const int64_t *slam_clocks;    /* [B,12] SM clock at the 7 phase boundaries of the last SLAM launch, [.,7] = T, [.,8..9] = cycles in the pose / border recurrences */
   const int64_t *counters;       /* [4] work counters: env-steps, sum of trajectory lengths, sum of
-                                    measurement counts over those steps, reserved            */
+                                    measurement counts over those steps, episodes restarted
+                                    by dge_reset_done_queued                                 */
   const int32_t *forced;         /* [B] forced steps still queued by dge_reset_queued (bit 30 = initial optimize pending) */
+  const int64_t *seed;           /* [B] Philox key of the env's current episode                                         */
 } dge_state_view;
 int dge_get_state(dge_handle h, dge_state_view *out);
 /* steps launched while counting is off (e.g. the 4 forced steps of a reset) do not touch `counters` */

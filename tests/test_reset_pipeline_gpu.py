@@ -84,3 +84,26 @@ def test_queued_reset_inside_running_loop():
         if checked >= 3:
             break
     assert checked >= 3
+
+
+def test_policy_loop_streams_are_race_free():
+    """runner.PolicyLoop: the two-stream schedule (step pipeline || policy pipeline) must produce exactly the
+    states of the same schedule run on one stream, through episode ends and in-pipeline restarts."""
+    from drl_graph_exploration_b200 import Networks
+    from drl_graph_exploration_b200.runner import PolicyLoop
+    states = []
+    for overlap in (False, True):
+        env = _mk(48)
+        env.reset()
+        torch.manual_seed(0)
+        model = Networks.GCN().to(env.device).eval()
+        loop = PolicyLoop(env, model, overlap=overlap)
+        for _ in range(150):
+            loop.tick()
+        torch.cuda.synchronize()
+        st = env.eng.state
+        states.append({k: st[k].clone() for k in ("n_poses", "sim_step", "true_pose", "prob", "seen", "counters", "seed", "plan", "plan_cursor", "forced")})
+        assert int(st["counters"][3]) >= 10          # episodes did restart in-pipeline
+        assert int(st["counters"][0]) > 48 * 100     # and most ticks were policy steps
+    for k in states[0]:
+        assert torch.equal(states[0][k], states[1][k]), k
