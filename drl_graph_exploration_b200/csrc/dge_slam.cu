@@ -41,7 +41,7 @@ struct SlamArgs {
   double *ws_pose, *ws_meas, *ws_Bt, *ws_FB;
   int32_t *ws_midx;
   double *metrics;
-  long long *clocks;   // [B,8] optional: SM clock at the phase boundaries (thread 0), for in-situ phase timing
+  long long *clocks;   // [B,12] optional: SM clock at the phase boundaries (thread 0), for in-situ phase timing
 };
 
 __device__ __forceinline__ void predict_br(const Pose3 &p, double lx, double ly, double &bearing, double &range, double *Hx, double *Hl) {
@@ -59,6 +59,19 @@ __device__ __forceinline__ void predict_br(const Pose3 &p, double lx, double ly,
   Hl[2] = rx * c - ry * s; Hl[3] = rx * s + ry * c;
 }
 
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {   // release: the producer's earlier shared stores are visible to waiters
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -70,7 +83,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   if (mask && !mask[b]) return;
   const int T = a.n_poses[b];
   const int Lt = a.d.Lt, Tmax = a.d.Tmax, N2C = 2 * Lt;  // N2C = border stride in the workspace
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   // shared layout
   double *S = smem;                               // [N2C*N2C]  Schur complement -> Sigma_ll
   double *stage = S + (size_t)N2C * N2C;          // [CH*SW]   per-pose 3x3 blocks of the current chunk
@@ -78,10 +91,12 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   double *gl = colp + N2C;                        // [N2C]
   double *dl = gl + N2C;                          // [N2C]
   double *red = dl + N2C;                         // [NT/32 * 2]
-  double *gbuf = red + 2 * (NT / 32);             // [2*GK*3*N2C] border-row staging (Schur GEMM) / per-warp W_k (phase E)
+  double *gjb = red + 2 * (NT / 32);              // [258] pivot row / column / reciprocal exchange of the Gauss-Jordan sweep
+  double *gbuf = gjb + 258;                       // [2*GK*3*N2C] border-row staging (Schur GEMM) / per-warp W_k (phase E)
   int *lidx = (int *)(gbuf + 2 * GK * 3 * N2C);   // [Lt]  id -> compact rank (-1 unobserved)
   int *lid = lidx + Lt;                           // [Lt]  rank -> id
   __shared__ int s_nl, s_bad;
+  __shared__ uint64_t s_bar[CH];   // one mbarrier per pose of the staged chunk: B0 (producer) -> B1 (consumers)
 
   const double wo[3] = {1.0 / (a.cfg.trans_noise * a.cfg.trans_noise), 1.0 / (a.cfg.trans_noise * a.cfg.trans_noise),
                         1.0 / (a.cfg.rot_noise * a.cfg.rot_noise)};
@@ -105,7 +120,10 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   // relinearizeSkip-th call, variables with max|delta| >= relinearizeThreshold move their
   // linearisation point: theta <- theta (+) delta, delta <- 0).
   const int uc = a.update_count[b] + 1;
-  if (tid == 0) { s_bad = 0; }
+  if (tid == 0) {
+    s_bad = 0;
+    for (int i = 0; i < CH; ++i) mbar_init(&s_bar[i], 1);
+  }
   if (a.cfg.relin_skip > 0 && uc % a.cfg.relin_skip == 0) {
     for (int k = tid; k < T; k += NT) {
       const double d0 = del[3 * k], d1 = del[3 * k + 1], d2 = del[3 * k + 2];
@@ -228,92 +246,105 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   const bool colv = ccol < n2;
   {
     const int c = ccol, jr = c >> 1, comp = c & 1;
-    // warp-0 lane roles for the 3x3 recurrence
-    const bool isD = lane < 9, isG = lane >= 9 && lane < 12;
-    const int li = isD ? lane / 3 : (isG ? lane - 9 : 0), lj = isD ? lane % 3 : 0;
-    const int lmin = min(li, lj), lmax = max(li, lj);
-    const int d6 = lmin == 0 ? lmax : (lmin == 1 ? 2 + lmax : 5);                  // index into the packed symmetric 3x3
-    const int i1 = (li + 1) % 3, i2 = (li + 2) % 3, j1 = (lj + 1) % 3, j2 = (lj + 2) % 3;
-    const int s11 = i1 * 3 + j1, s22 = i2 * 3 + j2, s12 = i1 * 3 + j2, s21 = i2 * 3 + j1;
-    double cDij = 0.0, cgi = 0.0, gprev = 0.0;                                       // warp-0 carried state
+    double cD[6] = {0, 0, 0, 0, 0, 0}, cg[3] = {0, 0, 0}, gp[3] = {0, 0, 0};        // warp-0 carried state
     double cB[3] = {0, 0, 0}, sd0 = 0, sd1 = 0, glc = 0;                             // column state
-    long long tB0 = 0, tB1 = 0, tc0 = 0;
     for (int k0 = 0; k0 < T; k0 += CH) {
       const int kc = min(CH, T - k0);
+      const uint32_t par = (k0 / CH) & 1;   // every pose barrier completes one phase per chunk
       __syncthreads();
       for (int i = tid; i < kc * 21; i += NT) stage[(i / 21) * SW + (i % 21)] = wsp[(size_t)(k0 + i / 21) * WS_POSE + (i % 21)];
       __syncthreads();
-      if (a.clocks && tid == 0) tc0 = clock64();
       if (warp == 0) {
-        // lane-parallel 3x3 recurrence: lanes 0..8 own entry (i,j) of the pose block, lanes 9..11 entry i of the
-        // rhs; operands of other lanes come by warp shuffle.  ~45 instructions on the loop-carried path instead
-        // of ~250 for a scalar 3x3 inverse + two products (fp64 issue is 2 cycles / warp instruction).
+        // B0: the 3x3 recurrence, scalar and identical on every lane (no shuffles: a shuffle round trip costs ~40
+        // cycles here, the whole inverse ~80); ~100 fp64 instructions = ~200 issue cycles per pose.
         for (int kk = 0; kk < kc; ++kk) {
           double *w = stage + kk * SW;
-          const double d = isD ? w[d6] + cDij : 1.0;                                  // D~[i][j]
-          double g = isG ? w[6 + li] + cgi + gprev : 0.0;                               // g~[i]
-          if (isG) gprev = w[18 + li];
-          // adjugate entry (cyclic indices give the sign): C[i][j] = d[i1][j1] d[i2][j2] - d[i1][j2] d[i2][j1]
-          const double ca = __shfl_sync(0xffffffffu, d, s11), cb = __shfl_sync(0xffffffffu, d, s22);
-          const double cc = __shfl_sync(0xffffffffu, d, s12), ce = __shfl_sync(0xffffffffu, d, s21);
-          const double cof = ca * cb - cc * ce;
-          const double pr = d * cof;
-          const double det = __shfl_sync(0xffffffffu, pr, 0) + __shfl_sync(0xffffffffu, pr, 1) + __shfl_sync(0xffffffffu, pr, 2);
-          const double d00 = __shfl_sync(0xffffffffu, d, 0);
-          if (!(det > 0.0) || !(d00 > 0.0)) s_bad = 1;
-          const double di = cof * (1.0 / det);                                           // Dinv[i][j] (symmetric)
-          const double r0 = __shfl_sync(0xffffffffu, di, li * 3), r1 = __shfl_sync(0xffffffffu, di, li * 3 + 1), r2 = __shfl_sync(0xffffffffu, di, li * 3 + 2);
-          const double g0 = __shfl_sync(0xffffffffu, g, 9), g1 = __shfl_sync(0xffffffffu, g, 10), g2 = __shfl_sync(0xffffffffu, g, 11);
-          // lanes 0..8: FU[i][j] = Dinv[i][:] U[:][j] ; lanes 9..11: f[i] = Dinv[i][:] g
-          const double val = isG ? (r0 * g0 + r1 * g1 + r2 * g2) : (r0 * w[9 + lj] + r1 * w[12 + lj] + r2 * w[15 + lj]);
-          const double f0 = __shfl_sync(0xffffffffu, val, lj), f1 = __shfl_sync(0xffffffffu, val, 3 + lj), f2 = __shfl_sync(0xffffffffu, val, 6 + lj);
-          const double h0 = __shfl_sync(0xffffffffu, val, 9), h1 = __shfl_sync(0xffffffffu, val, 10), h2 = __shfl_sync(0xffffffffu, val, 11);
-          // carries for the next pose: -U^T FU (lanes 0..8), -U^T f (lanes 9..11)
-          const double u0 = w[9 + li], u1 = w[12 + li], u2 = w[15 + li];
-          if (isD) cDij = -(u0 * f0 + u1 * f1 + u2 * f2);
-          if (isG) cgi = -(u0 * h0 + u1 * h1 + u2 * h2);
-          // Dinv | FU | f  -> shared (for B1) and workspace (for the backward pass)
-          double *wo_ = wsp + (size_t)(k0 + kk) * WS_POSE + 21;
-          if (isD) {
-            w[27 + lane] = val; wo_[6 + lane] = val;
-            if (lj >= li) { w[21 + d6] = di; wo_[d6] = di; }
-          } else if (isG) { w[36 + li] = val; wo_[15 + li] = val; }
+          const double d0 = w[0] + cD[0], d1 = w[1] + cD[1], d2 = w[2] + cD[2], d3 = w[3] + cD[3], d4 = w[4] + cD[4], d5 = w[5] + cD[5];
+          const double g0 = w[6] + cg[0] + gp[0], g1 = w[7] + cg[1] + gp[1], g2 = w[8] + cg[2] + gp[2];
+          gp[0] = w[18]; gp[1] = w[19]; gp[2] = w[20];
+          const double u00 = w[9], u01 = w[10], u02 = w[11], u10 = w[12], u11 = w[13], u12 = w[14], u20 = w[15], u21 = w[16], u22 = w[17];
+          // adjugate C of D~ (symmetric); D~^-1 = C / det.  Everything on the loop-carried path is expressed through C
+          // so that the reciprocal (~80 cycles) runs beside the two 3x3 products instead of in front of them.
+          const double c00 = d3 * d5 - d4 * d4, c01 = d2 * d4 - d1 * d5, c02 = d1 * d4 - d2 * d3;
+          const double c11 = d0 * d5 - d2 * d2, c12 = d1 * d2 - d0 * d4, c22 = d0 * d3 - d1 * d1;
+          const double det = d0 * c00 + d1 * c01 + d2 * c02;
+          if (!(det > 0.0) || !(d0 > 0.0)) s_bad = 1;
+          const double rd = 1.0 / det;
+          // CU = C U, Cg = C g
+          const double a00 = c00 * u00 + c01 * u10 + c02 * u20, a01 = c00 * u01 + c01 * u11 + c02 * u21, a02 = c00 * u02 + c01 * u12 + c02 * u22;
+          const double a10 = c01 * u00 + c11 * u10 + c12 * u20, a11 = c01 * u01 + c11 * u11 + c12 * u21, a12 = c01 * u02 + c11 * u12 + c12 * u22;
+          const double a20 = c02 * u00 + c12 * u10 + c22 * u20, a21 = c02 * u01 + c12 * u11 + c22 * u21, a22 = c02 * u02 + c12 * u12 + c22 * u22;
+          const double e0 = c00 * g0 + c01 * g1 + c02 * g2, e1 = c01 * g0 + c11 * g1 + c12 * g2, e2 = c02 * g0 + c12 * g1 + c22 * g2;
+          // carries for the next pose: -U^T D~^-1 U (symmetric), -U^T D~^-1 g
+          const double nrd = -rd;
+          cD[0] = (u00 * a00 + u10 * a10 + u20 * a20) * nrd; cD[1] = (u00 * a01 + u10 * a11 + u20 * a21) * nrd; cD[2] = (u00 * a02 + u10 * a12 + u20 * a22) * nrd;
+          cD[3] = (u01 * a01 + u11 * a11 + u21 * a21) * nrd; cD[4] = (u01 * a02 + u11 * a12 + u21 * a22) * nrd; cD[5] = (u02 * a02 + u12 * a12 + u22 * a22) * nrd;
+          cg[0] = (u00 * e0 + u10 * e1 + u20 * e2) * nrd; cg[1] = (u01 * e0 + u11 * e1 + u21 * e2) * nrd; cg[2] = (u02 * e0 + u12 * e1 + u22 * e2) * nrd;
+          if (lane == 0) {   // Dinv | FU | f -> shared (read by the column warps and copied to the workspace below)
+            w[21] = c00 * rd; w[22] = c01 * rd; w[23] = c02 * rd; w[24] = c11 * rd; w[25] = c12 * rd; w[26] = c22 * rd;
+            w[27] = a00 * rd; w[28] = a01 * rd; w[29] = a02 * rd; w[30] = a10 * rd; w[31] = a11 * rd; w[32] = a12 * rd; w[33] = a20 * rd; w[34] = a21 * rd; w[35] = a22 * rd;
+            w[36] = e0 * rd; w[37] = e1 * rd; w[38] = e2 * rd;
+            mbar_arrive(&s_bar[kk]);
+          }
         }
-      }
-      __syncthreads();
-      if (a.clocks && tid == 0) { const long long t1 = clock64(); tB0 += t1 - tc0; tc0 = t1; }
-      if (colv) {
-        double nb0 = wBt[((size_t)k0 * 3 + 0) * N2C + c], nb1 = wBt[((size_t)k0 * 3 + 1) * N2C + c], nb2 = wBt[((size_t)k0 * 3 + 2) * N2C + c];
-        int np1 = wmi[(size_t)k0 * Lt + jr];
-        for (int kk = 0; kk < kc; ++kk) {
-          const int k = k0 + kk;
-          const double *w = stage + kk * SW;
-          double Bt[3] = {nb0 + cB[0], nb1 + cB[1], nb2 + cB[2]};
-          const int p1 = np1;
-          if (kk + 1 < kc) {   // prefetch the next border row while this one is eliminated
-            nb0 = wBt[((size_t)(k + 1) * 3 + 0) * N2C + c]; nb1 = wBt[((size_t)(k + 1) * 3 + 1) * N2C + c]; nb2 = wBt[((size_t)(k + 1) * 3 + 2) * N2C + c];
-            np1 = wmi[(size_t)(k + 1) * Lt + jr];
-          }
-          if (p1) {  // pose k observes this column's landmark: landmark-landmark block and rhs
-            const double *m = wsm + (size_t)(p1 - 1) * WS_MEAS;
-            sd0 += comp ? m[1] : m[0];
-            sd1 += comp ? m[2] : m[1];
-            glc += m[3 + comp];
-          }
-          const double d0 = w[21], d1 = w[22], d2 = w[23], d3 = w[24], d4 = w[25], d5 = w[26];
-          const double fb0 = d0 * Bt[0] + d1 * Bt[1] + d2 * Bt[2], fb1 = d1 * Bt[0] + d3 * Bt[1] + d4 * Bt[2], fb2 = d2 * Bt[0] + d4 * Bt[1] + d5 * Bt[2];
-          glc -= Bt[0] * w[36] + Bt[1] * w[37] + Bt[2] * w[38];
+      } else {
+        if (colv) {
+          if (k0 == 0) {
+            // landmark-landmark diagonal block and rhs of this column: a gather over the column's factors, in pose
+            // order; independent loads (8 poses in flight), hidden behind the first poses of the chain
+            for (int k = 0; k < T; k += 8) {
+              int p1[8];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) cB[i] = -(w[9 + i] * fb0 + w[12 + i] * fb1 + w[15 + i] * fb2);
-          wBt[((size_t)k * 3 + 0) * N2C + c] = Bt[0]; wBt[((size_t)k * 3 + 1) * N2C + c] = Bt[1]; wBt[((size_t)k * 3 + 2) * N2C + c] = Bt[2];
-          wFB[((size_t)k * 3 + 0) * N2C + c] = fb0; wFB[((size_t)k * 3 + 1) * N2C + c] = fb1; wFB[((size_t)k * 3 + 2) * N2C + c] = fb2;
+              for (int u = 0; u < 8; ++u) p1[u] = (k + u < T) ? wmi[(size_t)(k + u) * Lt + jr] : 0;
+              double m0[8], m1[8], m2[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const double *m = wsm + (size_t)max(p1[u] - 1, 0) * WS_MEAS;
+                m0[u] = m[comp]; m1[u] = m[1 + comp]; m2[u] = m[3 + comp];
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (p1[u]) { sd0 += m0[u]; sd1 += m1[u]; glc += m2[u]; }
+            }
+          }
+          // B1: border column c.  Bt = B_k + carry, FB = D~^-1 Bt, carry' = -U^T FB, rhs; border rows prefetched
+          // 4 poses ahead (an L2 round trip is longer than one pose of the chain)
+          double nb[4][3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) nb[u][i] = (u < kc) ? wBt[((size_t)(k0 + u) * 3 + i) * N2C + c] : 0.0;
+          for (int kb = 0; kb < kc; kb += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int kk = kb + u;
+              if (kk < kc) {
+                const int k = k0 + kk;
+                const double b0 = nb[u][0] + cB[0], b1 = nb[u][1] + cB[1], b2 = nb[u][2] + cB[2];
+                if (kk + 4 < kc) {
+#pragma unroll
+                  for (int i = 0; i < 3; ++i) nb[u][i] = wBt[((size_t)(k + 4) * 3 + i) * N2C + c];
+                }
+                while (!mbar_try_wait(&s_bar[kk], par)) { }
+                const double *w = stage + kk * SW;
+                const double e0 = w[21], e1 = w[22], e2 = w[23], e3 = w[24], e4 = w[25], e5 = w[26];
+                const double fb0 = e0 * b0 + e1 * b1 + e2 * b2, fb1 = e1 * b0 + e3 * b1 + e4 * b2, fb2 = e2 * b0 + e4 * b1 + e5 * b2;
+                glc -= b0 * w[36] + b1 * w[37] + b2 * w[38];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) cB[i] = -(w[9 + i] * fb0 + w[12 + i] * fb1 + w[15 + i] * fb2);
+                wBt[((size_t)k * 3 + 0) * N2C + c] = b0; wBt[((size_t)k * 3 + 1) * N2C + c] = b1; wBt[((size_t)k * 3 + 2) * N2C + c] = b2;
+                wFB[((size_t)k * 3 + 0) * N2C + c] = fb0; wFB[((size_t)k * 3 + 1) * N2C + c] = fb1; wFB[((size_t)k * 3 + 2) * N2C + c] = fb2;
+              }
+            }
+          }
         }
+        // copy the chunk's Dinv | FU | f to the workspace (needed again by the backward pass)
+        while (!mbar_try_wait(&s_bar[kc - 1], par)) { }
+        for (int i = tid - 32; i < kc * 18; i += NT - 32) wsp[(size_t)(k0 + i / 18) * WS_POSE + 21 + (i % 18)] = stage[(i / 18) * SW + 21 + (i % 18)];
       }
-      if (a.clocks) { __syncthreads(); if (tid == 0) tB1 += clock64() - tc0; }
     }
     // seed S with the landmark-landmark blocks (block diagonal), gl with the reduced rhs
     __syncthreads();
-    if (a.clocks && tid == 0) { a.clocks[12 * b + 8] = tB0; a.clocks[12 * b + 9] = tB1; }
     for (int i = tid; i < n2 * n2; i += NT) S[i] = 0.0;
     __syncthreads();
     if (colv) {
@@ -418,9 +449,71 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
 
   if (a.clocks && tid == 0) a.clocks[12 * b +3] = clock64();
   // ---------------------------------------------------------------- phase C ---
-  // Sigma_ll = S^-1 (in-place Gauss-Jordan on the SPD Schur complement), dl = Sigma_ll gl
-  // Thread (c, h): column c = tid % 64 (+64 for a second pass when n2 > 64), rows r = h mod 2.
-  // The inner loop is a chain of shared-memory round trips, so loads are batched 6 rows at a time.
+  // Sigma_ll = S^-1 (Gauss-Jordan on the SPD Schur complement), dl = Sigma_ll gl.
+  if (n2 <= 64) {
+    // register-resident version: thread (h, c) = (tid / 64, tid % 64) keeps column c, rows h + 4q (q < 16) in
+    // registers for all n2 pivots.  Per pivot only the pivot row / column and the pivot's reciprocal travel through
+    // shared memory (double-buffered by parity => one barrier per pivot), the row loads are warp-uniform broadcasts,
+    // and the special cases (row p, column p, publishing row / column p+1) sit behind warp-uniform branches:
+    // the sweep is bound by instruction issue (2 CTAs x 8 warps share 4 schedulers), so instructions are what counts.
+    const int h = tid >> 6, c = tid & 63;
+    double *rowb = gjb, *colb = gjb + 128, *pivb = gjb + 256;   // [2][64], [2][64], [2]
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = (h + 4 * q < n2 && c < n2) ? S[(h + 4 * q) * n2 + c] : 0.0;
+    if (h == 0) rowb[c] = v[0];
+    if (c == 0) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) colb[h * 16 + q] = v[q];   // a thread's 16 rows are contiguous: 128-bit loads
+    }
+    if (tid == 0 && n2 > 0) { pivb[0] = 1.0 / v[0]; if (!(v[0] > 0.0)) s_bad = 1; }
+    __syncthreads();
+    for (int p = 0; p < n2; ++p) {
+      const int par = p & 1;
+      const double *rb = rowb + 64 * par, *cb = colb + 64 * par;
+      const double piv = pivb[par];
+      const double rpc = (c == p) ? piv : rb[c] * piv;
+      if ((p >> 5) == (warp & 1)) {      // this warp holds column p: clear it (its old content travels in cb)
+        if (c == p) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 16; q += 2) {
+        const double2 f2 = *reinterpret_cast<const double2 *>(cb + h * 16 + q);
+        v[q] = fma(-f2.x, rpc, v[q]); v[q + 1] = fma(-f2.y, rpc, v[q + 1]);
+      }
+      if (h == (p & 3)) {                // this warp holds row p
+        const int qp = p >> 2;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = (q == qp) ? rpc : v[q];
+      }
+      if (p + 1 < n2) {                  // publish pivot row / column p+1 and its reciprocal
+        const int pn = p + 1, qn = pn >> 2;
+        if (h == (pn & 3)) {
+          double vn = v[0];
+#pragma unroll
+          for (int q = 1; q < 16; ++q) vn = (q == qn) ? v[q] : vn;
+          rowb[64 * (par ^ 1) + c] = vn;
+          if (c == pn) { pivb[par ^ 1] = 1.0 / vn; if (!(vn > 0.0)) s_bad = 1; }
+        }
+        if ((pn >> 5) == (warp & 1)) {
+          if (c == pn) {
+#pragma unroll
+            for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(colb + 64 * (par ^ 1) + h * 16 + q) = make_double2(v[q], v[q + 1]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (h + 4 * q < n2 && c < n2) S[(h + 4 * q) * n2 + c] = v[q];
+    __syncthreads();
+  } else {
+  // shared-memory version for wider borders
+  // Thread (c, h): column c = tid % 64 (+64 for a second pass when n2 > 64), rows r = h mod NH.
   for (int p = 0; p < n2; ++p) {
     if (tid < n2) colp[tid] = S[tid * n2 + p];
     __syncthreads();
@@ -457,6 +550,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     }
     __syncthreads();
   }
+  }
   if (tid < n2) {
     double s = 0;
     for (int c = 0; c < n2; ++c) s += S[tid * n2 + c] * gl[c];
@@ -472,50 +566,60 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   // D1 does not depend on D0, so the two run concurrently on different warps.
   {
     const int c = ccol;
-    const bool isD = lane < 9, isG = lane >= 9 && lane < 12;
-    const int li = isD ? lane / 3 : (isG ? lane - 9 : 0), lj = isD ? lane % 3 : 0;
-    const int lmin = min(li, lj), lmax = max(li, lj);
-    const int d6 = lmin == 0 ? lmax : (lmin == 1 ? 2 + lmax : 5);
-    double Wn[3] = {0, 0, 0}, Pij = 0.0, ui = 0.0;
+    double Wn[3] = {0, 0, 0};
+    double P0 = 0, P1 = 0, P2 = 0, P3 = 0, P4 = 0, P5 = 0, un0 = 0, un1 = 0, un2 = 0;   // warp-0 carried state (P symmetric packed)
     for (int k1 = T; k1 > 0; k1 -= CH) {
       const int k0 = max(0, k1 - CH), kc = k1 - k0;
       __syncthreads();
       for (int i = tid; i < kc * 18; i += NT) stage[(i / 18) * SW + (i % 18)] = wsp[(size_t)(k0 + i / 18) * WS_POSE + 21 + (i % 18)];
       __syncthreads();
       if (warp == 0) {
-        // lane-parallel: lanes 0..8 own P[i][j], lanes 9..11 own u[i]
+        // D0: scalar, identical on every lane (see B0)
         for (int kk = kc - 1; kk >= 0; --kk) {
           const double *w = stage + kk * SW;   // Dinv(6) FU(9) f(3)
-          // M[i][j] = FU[i][:] P[:][j]
-          const double p0 = __shfl_sync(0xffffffffu, Pij, lj), p1 = __shfl_sync(0xffffffffu, Pij, 3 + lj), p2 = __shfl_sync(0xffffffffu, Pij, 6 + lj);
-          const double fi0 = w[6 + li * 3], fi1 = w[6 + li * 3 + 1], fi2 = w[6 + li * 3 + 2];
-          const double Mij = fi0 * p0 + fi1 * p1 + fi2 * p2;
-          // P'[i][j] = Dinv[i][j] + M[i][:] FU[j][:]
-          const double m0 = __shfl_sync(0xffffffffu, Mij, li * 3), m1 = __shfl_sync(0xffffffffu, Mij, li * 3 + 1), m2 = __shfl_sync(0xffffffffu, Mij, li * 3 + 2);
-          const double un0 = __shfl_sync(0xffffffffu, ui, 9), un1 = __shfl_sync(0xffffffffu, ui, 10), un2 = __shfl_sync(0xffffffffu, ui, 11);
-          double *wo_ = wsp + (size_t)(k0 + kk) * WS_POSE + 39;
-          if (isD) {
-            Pij = w[d6] + m0 * w[6 + lj * 3] + m1 * w[6 + lj * 3 + 1] + m2 * w[6 + lj * 3 + 2];
-            if (lj >= li) wo_[d6] = Pij;
-          } else if (isG) {
-            ui = w[15 + li] - (fi0 * un0 + fi1 * un1 + fi2 * un2);
-            wo_[6 + li] = ui;
+          const double f00 = w[6], f01 = w[7], f02 = w[8], f10 = w[9], f11 = w[10], f12 = w[11], f20 = w[12], f21 = w[13], f22 = w[14];
+          // M = FU P
+          const double m00 = f00 * P0 + f01 * P1 + f02 * P2, m01 = f00 * P1 + f01 * P3 + f02 * P4, m02 = f00 * P2 + f01 * P4 + f02 * P5;
+          const double m10 = f10 * P0 + f11 * P1 + f12 * P2, m11 = f10 * P1 + f11 * P3 + f12 * P4, m12 = f10 * P2 + f11 * P4 + f12 * P5;
+          const double m20 = f20 * P0 + f21 * P1 + f22 * P2, m21 = f20 * P1 + f21 * P3 + f22 * P4, m22 = f20 * P2 + f21 * P4 + f22 * P5;
+          // u' = f - FU u
+          const double v0 = w[15] - (f00 * un0 + f01 * un1 + f02 * un2), v1 = w[16] - (f10 * un0 + f11 * un1 + f12 * un2), v2 = w[17] - (f20 * un0 + f21 * un1 + f22 * un2);
+          // P' = Dinv + M FU^T
+          P0 = w[0] + m00 * f00 + m01 * f01 + m02 * f02; P1 = w[1] + m00 * f10 + m01 * f11 + m02 * f12; P2 = w[2] + m00 * f20 + m01 * f21 + m02 * f22;
+          P3 = w[3] + m10 * f10 + m11 * f11 + m12 * f12; P4 = w[4] + m10 * f20 + m11 * f21 + m12 * f22; P5 = w[5] + m20 * f20 + m21 * f21 + m22 * f22;
+          un0 = v0; un1 = v1; un2 = v2;
+          if (lane == 0) {
+            double *wo_ = wsp + (size_t)(k0 + kk) * WS_POSE + 39;
+            wo_[0] = P0; wo_[1] = P1; wo_[2] = P2; wo_[3] = P3; wo_[4] = P4; wo_[5] = P5; wo_[6] = v0; wo_[7] = v1; wo_[8] = v2;
           }
         }
       }
       if (colv) {
-        const int kl = k0 + kc - 1;
-        double nf0 = wFB[((size_t)kl * 3 + 0) * N2C + c], nf1 = wFB[((size_t)kl * 3 + 1) * N2C + c], nf2 = wFB[((size_t)kl * 3 + 2) * N2C + c];
-        for (int kk = kc - 1; kk >= 0; --kk) {
-          const int k = k0 + kk;
-          const double *w = stage + kk * SW + 6;   // FU
-          const double f0 = nf0, f1 = nf1, f2 = nf2;
-          if (kk > 0) { nf0 = wFB[((size_t)(k - 1) * 3 + 0) * N2C + c]; nf1 = wFB[((size_t)(k - 1) * 3 + 1) * N2C + c]; nf2 = wFB[((size_t)(k - 1) * 3 + 2) * N2C + c]; }
-          const double W0 = f0 - (w[0] * Wn[0] + w[1] * Wn[1] + w[2] * Wn[2]);
-          const double W1 = f1 - (w[3] * Wn[0] + w[4] * Wn[1] + w[5] * Wn[2]);
-          const double W2 = f2 - (w[6] * Wn[0] + w[7] * Wn[1] + w[8] * Wn[2]);
-          wFB[((size_t)k * 3 + 0) * N2C + c] = W0; wFB[((size_t)k * 3 + 1) * N2C + c] = W1; wFB[((size_t)k * 3 + 2) * N2C + c] = W2;
-          Wn[0] = W0; Wn[1] = W1; Wn[2] = W2;
+        // D1: W_k = FB_k - FU_k W_{k+1}, FB rows prefetched 4 poses ahead
+        double nf[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) nf[u][i] = (u < kc) ? wFB[((size_t)(k1 - 1 - u) * 3 + i) * N2C + c] : 0.0;
+        for (int kb = 0; kb < kc; kb += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int q = kb + u;           // q-th pose of the chunk counted from its end
+            if (q < kc) {
+              const int k = k1 - 1 - q;
+              const double f0 = nf[u][0], f1 = nf[u][1], f2 = nf[u][2];
+              if (q + 4 < kc) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) nf[u][i] = wFB[((size_t)(k - 4) * 3 + i) * N2C + c];
+              }
+              const double *w = stage + (k - k0) * SW + 6;   // FU
+              const double W0 = f0 - (w[0] * Wn[0] + w[1] * Wn[1] + w[2] * Wn[2]);
+              const double W1 = f1 - (w[3] * Wn[0] + w[4] * Wn[1] + w[5] * Wn[2]);
+              const double W2 = f2 - (w[6] * Wn[0] + w[7] * Wn[1] + w[8] * Wn[2]);
+              wFB[((size_t)k * 3 + 0) * N2C + c] = W0; wFB[((size_t)k * 3 + 1) * N2C + c] = W1; wFB[((size_t)k * 3 + 2) * N2C + c] = W2;
+              Wn[0] = W0; Wn[1] = W1; Wn[2] = W2;
+            }
+          }
         }
       }
     }
@@ -622,7 +726,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
 
 size_t dge_slam_smem_bytes(int Lt) {
   const size_t n2c = 2 * (size_t)Lt;
-  return (n2c * n2c + CH * SW + 3 * n2c + 2 * (NT / 32) + 2 * GK * 3 * n2c) * sizeof(double) + 2 * (size_t)Lt * sizeof(int) + 16;
+  return (n2c * n2c + CH * SW + 3 * n2c + 2 * (NT / 32) + 258 + 2 * GK * 3 * n2c) * sizeof(double) + 2 * (size_t)Lt * sizeof(int) + 16;
 }
 
 int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st) {

@@ -64,5 +64,12 @@ lines += ["## warp-stall samples by CUDA source line (top 25)", "", "| samples |
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
     code = text[k[1] - 1].strip()[:100].replace("|", "\\|") if k[0] == os.path.basename(cu) and 0 < k[1] <= len(text) else ""
     lines.append(f"| {v[0]} | {100 * v[0] / tot:.1f} | {v[1]} | {v[2]} | {v[3]} | {v[4]} | `{k[0]}:{k[1]}` {code} |")
+rng = os.environ.get("LINES")
+if rng:   # LINES=a-b : every sampled line of that source range, in source order
+    lo, hi_ = (int(v) for v in rng.split("-"))
+    lines += ["", f"## lines {lo}-{hi_} in source order", "", "| samples | barrier | long_sb | wait | short_sb | line |", "|---|---|---|---|---|---|"]
+    for k, v in sorted(agg.items(), key=lambda kv: kv[0][1]):
+        if k[0] == os.path.basename(cu) and lo <= k[1] <= hi_:
+            lines.append(f"| {v[0]} | {v[1]} | {v[2]} | {v[3]} | {v[4]} | `{k[1]}` {text[k[1] - 1].strip()[:110]} |")
 open(out, "w").write("\n".join(lines) + "\n")
 print("wrote", out)
