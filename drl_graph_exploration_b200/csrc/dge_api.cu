@@ -78,7 +78,7 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.g_cnt = al.get<int32_t>(B * (size_t)d.Ncap); e.g_cur = al.get<int32_t>(B * (size_t)d.Ncap); e.g_dis = al.get<float>(B * (size_t)d.Ncap);
   e.g_tmp = al.get<int32_t>(B * (size_t)d.Ecap);
   e.slam_clocks = al.get<long long>(B * 12);
-  e.forced = al.get<int32_t>(B); e.step_kind = al.get<uint8_t>(B);
+  e.forced = al.get<int32_t>(B); e.step_kind = al.get<uint8_t>(B); e.pending = al.get<uint8_t>(B);
   e.counters = al.get<unsigned long long>(4); e.count_steps = 1; e.park_done = 1;
   e.rdist = al.get<double>(B); e.r_cmap = al.get<int32_t>(B * 2); e.r_cbase = al.get<int32_t>(B); e.r_u0 = al.get<double>(B);
   if (!al.ok) {
@@ -220,7 +220,7 @@ extern "C" int dge_get_state(dge_handle h, dge_state_view *o) {
   o->meas_ptr = h->meas_ptr; o->meas_id = h->meas_id; o->meas_bearing = h->meas_b; o->meas_range = h->meas_r;
   o->lm_true = h->lm_true; o->scan_id = h->scan_id; o->observed = h->observed; o->est_l = h->est_l; o->lin_l = h->lin_l;
   o->land_cov = h->land_cov; o->prob = h->prob; o->vinfo = h->vinfo; o->seen = h->seen; o->metrics = h->metrics; o->done = h->done; o->active = h->active; o->status = h->status;
-  o->forced = h->forced; o->seed = reinterpret_cast<const int64_t *>(h->seed); o->plan = h->plan; o->plan_cursor = h->plan_cursor; o->counters = reinterpret_cast<const int64_t *>(h->counters); o->slam_clocks = reinterpret_cast<const int64_t *>(h->slam_clocks);
+  o->pending = h->pending; o->forced = h->forced; o->seed = reinterpret_cast<const int64_t *>(h->seed); o->plan = h->plan; o->plan_cursor = h->plan_cursor; o->counters = reinterpret_cast<const int64_t *>(h->counters); o->slam_clocks = reinterpret_cast<const int64_t *>(h->slam_clocks);
   return DGE_OK;
 }
 
@@ -230,6 +230,12 @@ extern "C" int dge_graph(dge_handle h, const uint8_t *mask, const dge_graph_out 
     return fail(DGE_EINVAL, "dge_graph: null output buffer");
   const int rc = dge_launch_graph(h, mask, out, static_cast<cudaStream_t>(stream));
   return rc ? fail(rc, "dge_graph") : DGE_OK;
+}
+
+extern "C" int dge_mark_pending(dge_handle h, void *stream) {
+  if (!h) return DGE_EINVAL;
+  const int rc = dge_launch_mark_pending(h, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "dge_mark_pending") : DGE_OK;
 }
 
 extern "C" int dge_line_plan(dge_handle h, const double *goal, const uint8_t *mask, double *plan, void *stream) {

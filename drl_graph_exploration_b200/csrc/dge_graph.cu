@@ -33,6 +33,12 @@ struct GraphArgs {
   float *g_dis;
 };
 
+// envs that need a decision: action queue empty, episode not finished, no forced reset steps outstanding
+__global__ void k_mark_pending(int B, const double *plan, const int32_t *cursor, const int32_t *forced, const uint8_t *done, uint8_t *pending) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) pending[b] = (cursor[b] >= (int)plan[6 * b + 5] && !done[b] && forced[b] == 0) ? 1 : 0;
+}
+
 __device__ __forceinline__ double dist_np(double ax, double ay, double bx, double by) {  // exploration_env.py:374-376
   const double dx = ax - bx, dy = ay - by;
   return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
@@ -401,6 +407,11 @@ GraphArgs make_gargs(dge_engine *e) {
 }
 
 }  // namespace
+
+int dge_launch_mark_pending(dge_engine *e, cudaStream_t st) {
+  k_mark_pending<<<(e->d.B + 255) / 256, 256, 0, st>>>(e->d.B, e->plan, e->plan_cursor, e->forced, e->done, e->pending);
+  return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
+}
 
 int dge_launch_graph(dge_engine *e, const uint8_t *mask, const dge_graph_out *out, cudaStream_t st) {
   const GraphArgs a = make_gargs(e);

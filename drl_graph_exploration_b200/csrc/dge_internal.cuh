@@ -74,6 +74,7 @@ struct dge_engine {
   long long *slam_clocks; // [B,12] phase-boundary clocks of the last k_slam launch (+ T in slot 7, sub-phase cycles in 8..11)
   int32_t *forced;       // [B] forced steps left after an in-pipeline reset (| DGE_FRESH_BIT while the initial optimize is pending)
   uint8_t *step_kind;    // [B] 1 = the env's last step was a policy step
+  uint8_t *pending;      // [B] envs that need a decision (dge_mark_pending)
   double forced_odom[3]; // host copy of the forced action (exploration_env.py:411-414)
   int count_steps;       // host flag: 1 while stepping on behalf of the policy (reset steps are not counted)
   int park_done;         // host flag: queued stepping skips `done` envs (1, default) or runs every plan to its end (0, roll-out engines)
@@ -182,6 +183,7 @@ int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st);
 int dge_vmap_standalone(const dge_config *cfg, int n, int T, const double *pose, const double *cov, int L, const double *lm,
                         double *prob, double *vinfo, int32_t *seen, double *prep_ws, double *cbox_ws, cudaStream_t st);
 int dge_launch_graph(dge_engine *e, const uint8_t *mask, const dge_graph_out *out, cudaStream_t st);
+int dge_launch_mark_pending(dge_engine *e, cudaStream_t st);
 int dge_launch_line_plan(dge_engine *e, const double *goal, const uint8_t *mask, double *plan_out, cudaStream_t st);
 int dge_launch_select_plan(dge_engine *e, const dge_graph_out *g, const float *q, const uint8_t *mask, int32_t *choice, cudaStream_t st);
 int dge_vmap_nchunk(int T);

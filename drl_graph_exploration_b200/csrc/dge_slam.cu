@@ -363,7 +363,77 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   if (n2 > 0) {
     const int nt = (n2 + 3) / 4;
     const int ntile = nt * (nt + 1) / 2;
-    if (ntile <= 2 * NT) {
+    if (ntile <= NT / 2 && N2C <= 64) {
+      // (the usual case, up to 60 border columns) two thread groups split the k dimension: group g takes poses
+      // [4g, 4g+4) of every staged round of GK = 8 poses, one 4x4 tile per thread, so all 8 warps carry DFMAs;
+      // the next round's rows are prefetched into registers while the current one is multiplied.
+      const int grp = tid >> 7, lt = tid & 127;
+      const bool tv = lt < ntile;
+      int tr = 0, rem = tv ? lt : 0;
+      while (rem >= nt - tr) { rem -= nt - tr; ++tr; }
+      const int tc = tr + rem, r0 = tr * 4, c0 = tc * 4;
+      double acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+      double *gA = gbuf, *gB = gbuf + GK * 3 * N2C;
+      constexpr int PF = 6;                                     // 2 operands x GK*3*N2C / NT <= 2 * PF  (N2C <= 64)
+      double pa[PF], pb[PF];
+      const int rows0 = min(GK, T) * 3;
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int i = tid + u * NT;
+        pa[u] = (i < rows0 * N2C) ? wBt[i] : 0.0; pb[u] = (i < rows0 * N2C) ? wFB[i] : 0.0;
+      }
+      for (int k0 = 0; k0 < T; k0 += GK) {
+        const int rows = min(GK, T - k0) * 3;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+          const int i = tid + u * NT;
+          if (i < rows * N2C) { gA[i] = pa[u]; gB[i] = pb[u]; }
+        }
+        __syncthreads();
+        if (k0 + GK < T) {
+          const int rown = min(GK, T - k0 - GK) * 3;
+          const size_t base = (size_t)(k0 + GK) * 3 * N2C;
+#pragma unroll
+          for (int u = 0; u < PF; ++u) {
+            const int i = tid + u * NT;
+            pa[u] = (i < rown * N2C) ? wBt[base + i] : 0.0; pb[u] = (i < rown * N2C) ? wFB[base + i] : 0.0;
+          }
+        }
+        if (tv) {
+          const int kb = grp * (GK / 2) * 3, ke = min(rows, kb + (GK / 2) * 3);
+          const double *ar = gA + kb * N2C + r0, *bc = gB + kb * N2C + c0;
+          for (int ki = kb; ki < ke; ++ki, ar += N2C, bc += N2C) {   // columns beyond n2 read zeros/garbage of padded rows but are never stored
+            const double2 a01 = *reinterpret_cast<const double2 *>(ar), a23 = *reinterpret_cast<const double2 *>(ar + 2);
+            const double2 b01 = *reinterpret_cast<const double2 *>(bc), b23 = *reinterpret_cast<const double2 *>(bc + 2);
+            acc[0] += a01.x * b01.x; acc[1] += a01.x * b01.y; acc[2] += a01.x * b23.x; acc[3] += a01.x * b23.y;
+            acc[4] += a01.y * b01.x; acc[5] += a01.y * b01.y; acc[6] += a01.y * b23.x; acc[7] += a01.y * b23.y;
+            acc[8] += a23.x * b01.x; acc[9] += a23.x * b01.y; acc[10] += a23.x * b23.x; acc[11] += a23.x * b23.y;
+            acc[12] += a23.y * b01.x; acc[13] += a23.y * b01.y; acc[14] += a23.y * b23.x; acc[15] += a23.y * b23.y;
+          }
+        }
+      }
+      // S -= acc: group 0 first, then group 1 (two fixed-order passes keep the result deterministic)
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        __syncthreads();
+        if (tv && grp == g) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = r0 + i, cc = c0 + j;
+              if (r < n2 && cc < n2 && (tr != tc || cc >= r)) {
+                const double v = S[r * n2 + cc] - acc[i * 4 + j];
+                S[r * n2 + cc] = v;
+                if (r != cc) S[cc * n2 + r] = v;
+              }
+            }
+        }
+      }
+    } else if (ntile <= 2 * NT) {
       int tr[2], tc[2];
       bool tv[2];
       double acc[2][16];
@@ -628,50 +698,69 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
 
   if (a.clocks && tid == 0) a.clocks[12 * b +5] = clock64();
   // ---------------------------------------------------------------- phase E ---
-  // E1  one warp per pose: W_k (3 x n2) staged into shared memory, y = W_k Sigma_ll with two columns per lane,
+  // E1  one warp per pair of poses: W_k (3 x n2) staged into shared memory, y = W_k Sigma_ll with two columns per lane,
   //     q = y W_k^T and v = W_k dl reduced across the warp -> workspace.
   // E2  one thread per pose: Sigma_kk = P_k + q, delta_k = u_k - v, estimate = theta (+) delta,
   //     information = Sigma_kk^-1 (SLAM2D.cpp:400).
   {
-    double *wb = gbuf + (size_t)warp * 3 * N2C;
-    for (int k = warp; k < T; k += NT / 32) {
-      const double *Wk = wFB + (size_t)k * 3 * N2C;
+    // two poses per warp pass: per row r of Sigma_ll 3 x 128-bit broadcast loads (the 6 interleaved W rows) and 2 loads
+    // of Sigma_ll feed 12 DFMAs, which makes the loop fp64-pipe-bound rather than issue-bound
+    double *wb = gbuf + (size_t)warp * 6 * N2C;   // [n2][6]: W_ka rows 0..2, W_kb rows 0..2
+    for (int kp = warp; 2 * kp < T; kp += NT / 32) {
+      const int ka = 2 * kp, kb = min(2 * kp + 1, T - 1);
+      const double *Wa = wFB + (size_t)ka * 3 * N2C, *Wb = wFB + (size_t)kb * 3 * N2C;
       __syncwarp();
-      for (int i = lane; i < 3 * N2C; i += 32) wb[i] = Wk[i];
+#pragma unroll
+      for (int row = 0; row < 3; ++row)
+        for (int r = lane; r < n2; r += 32) { wb[r * 6 + row] = Wa[row * N2C + r]; wb[r * 6 + 3 + row] = Wb[row * N2C + r]; }
       __syncwarp();
-      double q[6] = {0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
+      double qa[6] = {0, 0, 0, 0, 0, 0}, va[3] = {0, 0, 0}, qb[6] = {0, 0, 0, 0, 0, 0}, vb[3] = {0, 0, 0};
       for (int cb = 0; cb < n2; cb += 64) {
         const int c1 = cb + lane, c2 = cb + 32 + lane;
         const bool v1 = c1 < n2, v2 = c2 < n2;
-        const int i1 = v1 ? c1 : 0, i2 = v2 ? c2 : 0;
-        double y0 = 0, y1 = 0, y2 = 0, z0 = 0, z1 = 0, z2 = 0;
+        const double *sp1 = S + (v1 ? c1 : 0), *sp2 = S + (v2 ? c2 : 0);
+        const double *wr = wb;
+        double ya0 = 0, ya1 = 0, ya2 = 0, yb0 = 0, yb1 = 0, yb2 = 0, za0 = 0, za1 = 0, za2 = 0, zb0 = 0, zb1 = 0, zb2 = 0;
+#pragma unroll 4
         for (int r = 0; r < n2; ++r) {
-          const double w0 = wb[r], w1 = wb[N2C + r], w2 = wb[2 * N2C + r];
-          const double s1 = S[r * n2 + i1], s2 = S[r * n2 + i2];
-          y0 += w0 * s1; y1 += w1 * s1; y2 += w2 * s1;
-          z0 += w0 * s2; z1 += w1 * s2; z2 += w2 * s2;
+          const double2 w01 = *reinterpret_cast<const double2 *>(wr), w23 = *reinterpret_cast<const double2 *>(wr + 2), w45 = *reinterpret_cast<const double2 *>(wr + 4);
+          const double s1 = *sp1, s2 = *sp2;
+          ya0 += w01.x * s1; ya1 += w01.y * s1; ya2 += w23.x * s1; yb0 += w23.y * s1; yb1 += w45.x * s1; yb2 += w45.y * s1;
+          za0 += w01.x * s2; za1 += w01.y * s2; za2 += w23.x * s2; zb0 += w23.y * s2; zb1 += w45.x * s2; zb2 += w45.y * s2;
+          wr += 6; sp1 += n2; sp2 += n2;
         }
         if (v1) {
-          const double w0 = wb[c1], w1 = wb[N2C + c1], w2 = wb[2 * N2C + c1], d = dl[c1];
-          q[0] += y0 * w0; q[1] += y0 * w1; q[2] += y0 * w2; q[3] += y1 * w1; q[4] += y1 * w2; q[5] += y2 * w2;
-          v[0] += w0 * d; v[1] += w1 * d; v[2] += w2 * d;
+          const double *w = wb + c1 * 6;
+          const double d = dl[c1];
+          qa[0] += ya0 * w[0]; qa[1] += ya0 * w[1]; qa[2] += ya0 * w[2]; qa[3] += ya1 * w[1]; qa[4] += ya1 * w[2]; qa[5] += ya2 * w[2];
+          qb[0] += yb0 * w[3]; qb[1] += yb0 * w[4]; qb[2] += yb0 * w[5]; qb[3] += yb1 * w[4]; qb[4] += yb1 * w[5]; qb[5] += yb2 * w[5];
+          va[0] += w[0] * d; va[1] += w[1] * d; va[2] += w[2] * d; vb[0] += w[3] * d; vb[1] += w[4] * d; vb[2] += w[5] * d;
         }
         if (v2) {
-          const double w0 = wb[c2], w1 = wb[N2C + c2], w2 = wb[2 * N2C + c2], d = dl[c2];
-          q[0] += z0 * w0; q[1] += z0 * w1; q[2] += z0 * w2; q[3] += z1 * w1; q[4] += z1 * w2; q[5] += z2 * w2;
-          v[0] += w0 * d; v[1] += w1 * d; v[2] += w2 * d;
+          const double *w = wb + c2 * 6;
+          const double d = dl[c2];
+          qa[0] += za0 * w[0]; qa[1] += za0 * w[1]; qa[2] += za0 * w[2]; qa[3] += za1 * w[1]; qa[4] += za1 * w[2]; qa[5] += za2 * w[2];
+          qb[0] += zb0 * w[3]; qb[1] += zb0 * w[4]; qb[2] += zb0 * w[5]; qb[3] += zb1 * w[4]; qb[4] += zb1 * w[5]; qb[5] += zb2 * w[5];
+          va[0] += w[0] * d; va[1] += w[1] * d; va[2] += w[2] * d; vb[0] += w[3] * d; vb[1] += w[4] * d; vb[2] += w[5] * d;
         }
       }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) q[i] = warp_sum(q[i]);
+      for (int i = 0; i < 6; ++i) { qa[i] = warp_sum(qa[i]); qb[i] = warp_sum(qb[i]); }
 #pragma unroll
-      for (int i = 0; i < 3; ++i) v[i] = warp_sum(v[i]);
+      for (int i = 0; i < 3; ++i) { va[i] = warp_sum(va[i]); vb[i] = warp_sum(vb[i]); }
       if (lane == 0) {
-        double *wo_ = wsp + (size_t)k * WS_POSE;   // slots 0..9 (D, g of phase A) are dead by now
+        double *wo_ = wsp + (size_t)ka * WS_POSE;   // slots 0..9 (D, g of phase A) are dead by now
 #pragma unroll
-        for (int i = 0; i < 6; ++i) wo_[i] = q[i];
+        for (int i = 0; i < 6; ++i) wo_[i] = qa[i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) wo_[6 + i] = v[i];
+        for (int i = 0; i < 3; ++i) wo_[6 + i] = va[i];
+        if (2 * kp + 1 < T) {
+          double *wo2 = wsp + (size_t)kb * WS_POSE;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) wo2[i] = qb[i];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) wo2[6 + i] = vb[i];
+        }
       }
     }
   }

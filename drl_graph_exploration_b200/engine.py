@@ -29,7 +29,7 @@ class _StateView(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "n_poses", "sim_step", "update_count", "true_pose", "est_pose", "lin_pose", "delta_pose", "pose_cov", "pose_info",
         "odom", "meas_ptr", "meas_id", "meas_bearing", "meas_range", "lm_true", "scan_id", "observed", "est_l", "lin_l",
-        "land_cov", "prob", "vinfo", "seen", "metrics", "done", "active", "status", "plan", "plan_cursor", "slam_clocks", "counters", "forced", "seed")]
+        "land_cov", "prob", "vinfo", "seen", "metrics", "done", "active", "status", "plan", "plan_cursor", "slam_clocks", "counters", "forced", "seed", "pending")]
 
 
 class GraphOut(ctypes.Structure):
@@ -57,6 +57,7 @@ def load_library():
         L.dge_step.argtypes = [vp, vp, vp, vp, vp]
         L.dge_reset_queued.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.dge_reset_done_queued.argtypes = [vp, ctypes.c_uint64, vp, ctypes.c_int, vp]
+        L.dge_mark_pending.argtypes = [vp, vp]
         L.dge_step_queued.argtypes = [vp, vp]
         L.dge_move_measure_queued.argtypes = [vp, vp]
         L.dge_set_counting.argtypes = [vp, ctypes.c_int]
@@ -132,7 +133,7 @@ class Engine:
             "lin_l": ((B, L, 2), torch.float64), "land_cov": ((B, L, 3), torch.float64), "prob": ((B, self.rows, self.cols), torch.float64),
             "vinfo": ((B, self.rows, self.cols, 3), torch.float64), "seen": ((B, self.rows, self.cols), torch.int32),
             "metrics": ((B, 8), torch.float64), "done": ((B,), torch.uint8), "active": ((B,), torch.uint8), "status": ((B,), torch.int32),
-            "plan": ((B, 6), torch.float64), "plan_cursor": ((B,), torch.int32), "counters": ((4,), torch.int64), "slam_clocks": ((B, 12), torch.int64), "forced": ((B,), torch.int32), "seed": ((B,), torch.int64),
+            "plan": ((B, 6), torch.float64), "plan_cursor": ((B,), torch.int32), "counters": ((4,), torch.int64), "slam_clocks": ((B, 12), torch.int64), "forced": ((B,), torch.int32), "seed": ((B,), torch.int64), "pending": ((B,), torch.uint8),
         }
         self.state = {}
         for name, (shape, dt) in spec.items():

@@ -169,6 +169,12 @@ class VecExplorationEnv:
         _check(eng._L.dge_graph(eng._h, _ptr(mask), ctypes.byref(self.graph.c), _stream_ptr(self.device)), "dge_graph")
         return self.graph
 
+    def mark_pending(self) -> torch.Tensor:
+        """``needs_decision`` evaluated by one small kernel into the engine-owned ``pending`` mask."""
+        eng = self.eng
+        _check(eng._L.dge_mark_pending(eng._h, _stream_ptr(self.device)), "dge_mark_pending")
+        return eng.state["pending"]
+
     def select_and_plan(self, q: torch.Tensor, mask: Optional[torch.Tensor] = None):
         """arg-max over each graph's frontier nodes + line plan into the env queues (device-side)."""
         eng = self.eng

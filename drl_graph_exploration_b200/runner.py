@@ -45,7 +45,7 @@ class PolicyLoop:
         env, eng = self.env, self.env.eng
         L, h, st = eng._L, eng._h, eng.state
         main = torch.cuda.current_stream(self.dev)
-        need = env.needs_decision()
+        need = env.mark_pending()                    # before the step pipeline starts moving the queues
         if self.overlap:
             self.ev_need.record(main)
             self.s_step.wait_event(self.ev_need)     # orders the step pipeline after the previous tick's select_and_plan too
@@ -73,14 +73,14 @@ class PolicyLoop:
             self.ev_step.record(s1)
         self.launches += 6
         # ---- policy pipeline -----------------------------------------------------------------------------
-        g = env.build_graph(need); self.launches += 3
+        g = env.build_graph(need); self.launches += 4
         ng, _, _ = g.sync_sizes()                    # the tick's only host sync (main stream only)
         if ng > 0:
             l0 = gnn.launch_count
             q = self.model(g.data(), 0.0)
             if self.overlap:
                 main.wait_event(self.ev_move)        # plans are rewritten only after this tick's move kernel has read them
-            env.select_and_plan(q, need)
+            env.select_and_plan(q)                   # the envs of this graph batch
             self.launches += gnn.launch_count - l0 + 1
             self.graphs += ng
         if self.overlap:

@@ -162,6 +162,7 @@ typedef struct dge_state_view {
                                     by dge_reset_done_queued                                 */
   const int32_t *forced;         /* [B] forced steps still queued by dge_reset_queued (bit 30 = initial optimize pending) */
   const int64_t *seed;           /* [B] Philox key of the env's current episode                                         */
+  const uint8_t *pending;        /* [B] written by dge_mark_pending                                                     */
 } dge_state_view;
 int dge_get_state(dge_handle h, dge_state_view *out);
 /* steps launched while counting is off (e.g. the 4 forced steps of a reset) do not touch `counters` */
@@ -193,6 +194,10 @@ typedef struct dge_graph_out {
   float *gcn_selfnorm;     /* [Ncap]    2 / deg                                                            */
 } dge_graph_out;
 int dge_graph(dge_handle h, const uint8_t *mask_dev, const dge_graph_out *out, void *stream);
+/* writes dge_state_view.pending: 1 for the envs that need a decision right now (action queue empty, episode
+ * running, no forced reset steps outstanding) -- the selection the acting loop of policy.py:236-306 makes,
+ * evaluated on the device; pass it as mask_dev to dge_graph.                                            */
+int dge_mark_pending(dge_handle h, void *stream);
 
 /* ---- line planner: replaces EMPlanner2D.line_planner (Planner2D.cpp:937-1041) for one
  * goal per env.  goal_dev [B,2]; plan_dev [B,6] = (n_rot_pi, rot_sign, rot_remainder,
