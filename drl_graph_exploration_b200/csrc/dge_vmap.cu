@@ -22,6 +22,7 @@ namespace {
 
 constexpr int TILE = 16;           // cells per tile side
 constexpr int VCH = 32;            // poses per chunk
+constexpr int VU = 4;              // poses whose state-independent part is evaluated together (instruction-level parallelism)
 constexpr int PREP_W = 12;         // doubles per digested pose: x y c s Sxx Sxy Sxt Syy Syt Stt valid pad
 
 struct VmapCfg {
@@ -129,46 +130,68 @@ __global__ void __launch_bounds__(TILE * TILE) k_vmap_cells(VmapCfg c, int Tstri
     __syncthreads();
     for (int i = threadIdx.x; i < kc * PREP_W; i += TILE * TILE) sp[i] = prep[((size_t)b * Tstride + k0) * PREP_W + i];
     __syncthreads();
-    if (!valid_cell) continue;
-    for (int kk = 0; kk < kc; ++kk) {
-      const double *p = sp + kk * PREP_W;
-      const double dx = cx - p[0], dy = cy - p[1];
-      const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-      if (d2 >= rmax_c2) continue;
-      const double r = __dsqrt_rn(d2);
-      if (!(r < c.max_range)) continue;                       // Distance.cpp:86 / checkWithoutMinRange
-      const double co = p[2], si = p[3];
-      const double qx = co * dx + si * dy, qy = -si * dx + co * dy;
-      // field-of-view gate min_b < atan2(qy,qx) < max_b  (Simulator2D.cpp:100-111)
-      bool in_fov;
-      if (c.fov_wide && (qx > 0.0 || fabs(qy) > -qx * c.wedge_tan)) in_fov = true;
-      else { const double bb = atan2(qy, qx); in_fov = bb < c.max_bearing && bb > c.min_bearing; }
-      if (!in_fov) continue;
-      ++cnt;                                                  // occupancy visibility count (q8)
-      if (!(r > c.min_range) || p[10] == 0.0) continue;       // full check (q10) ; det(info) gate
-      // body-frame covariance of the predicted virtual landmark
-      const double r2 = r * r;
-      const double sr = c.rr / r2;
-      const double Sxx = p[4], Sxy = p[5], Sxt = p[6], Syy = p[7], Syt = p[8], Stt = p[9];
-      const double cb00 = qy * qy * c.rb + qx * qx * sr + Sxx - 2.0 * qy * Sxt + qy * qy * Stt;
-      const double cb01 = qx * qy * (sr - c.rb) + Sxy - qy * Syt + qx * Sxt - qx * qy * Stt;
-      const double cb11 = qx * qx * c.rb + qy * qy * sr + Syy + 2.0 * qx * Syt + qx * qx * Stt;
-      const double idet = 1.0 / (cb00 * cb11 - cb01 * cb01);
-      const double lb00 = cb11 * idet, lb01 = -cb01 * idet, lb11 = cb00 * idet;   // body-frame information
-      // rotate to the map frame
-      const double cc = co * co, ss = si * si, cs = co * si;
-      const double nxx = cc * lb00 - 2.0 * cs * lb01 + ss * lb11;
-      const double nxy = cs * (lb00 - lb11) + (cc - ss) * lb01;
-      const double nyy = ss * lb00 + 2.0 * cs * lb01 + cc * lb11;
-      if (!updated) { ixx = nxx; ixy = nxy; iyy = nyy; updated = true; }
-      else {  // covariance intersection on information matrices (VirtualMap.cpp:364-377, q11)
-        const double a = ixx * iyy - ixy * ixy, bdet = nxx * nyy - nxy * nxy;
-        const double cm = iyy * nxx - 2.0 * ixy * nxy + ixx * nyy;   // det(m1) * tr(m1^-1 m2)
-        const double d = a + bdet - cm;
-        double w = 0.5 * (2.0 * bdet - cm) / d;
-        if ((w < 0 && d < 0) || (w > 1 && d > 0)) w = 0.0;
-        else if ((w < 0 && d > 0) || (w > 1 && d < 0)) w = 1.0;
-        ixx = w * ixx + (1.0 - w) * nxx; ixy = w * ixy + (1.0 - w) * nxy; iyy = w * iyy + (1.0 - w) * nyy;
+    // (cells outside the map stay in the loop -- the warp votes below need every lane -- but are never `near`)
+    // The fold over poses is sequential per cell (covariance intersection is order dependent), and a visit is a
+    // ~40-deep fp64 dependency chain.  Only the last ~10 operations (the intersection itself) depend on the running
+    // state, so the state-independent part (geometry, predicted covariance, its inverse, rotation) is evaluated for
+    // VU consecutive poses at once -- straight-line code, VU independent chains in flight -- and then folded in order.
+    for (int kb = 0; kb < kc; kb += VU) {
+      double dxs[VU], dys[VU], d2s[VU];
+      bool near_any = false;
+#pragma unroll
+      for (int u = 0; u < VU; ++u) {
+        const double *p = sp + min(kb + u, kc - 1) * PREP_W;
+        dxs[u] = cx - p[0]; dys[u] = cy - p[1];
+        d2s[u] = __dadd_rn(__dmul_rn(dxs[u], dxs[u]), __dmul_rn(dys[u], dys[u]));
+        near_any |= valid_cell && (kb + u < kc) && d2s[u] < rmax_c2;
+      }
+      if (!__any_sync(0xffffffffu, near_any)) continue;
+      double nxx[VU], nxy[VU], nyy[VU];
+      bool vis[VU], upd[VU];
+#pragma unroll
+      for (int u = 0; u < VU; ++u) {
+        const double *p = sp + min(kb + u, kc - 1) * PREP_W;
+        const double dx = dxs[u], dy = dys[u], d2 = d2s[u];
+        const double r = __dsqrt_rn(d2);
+        const bool inr = valid_cell && (kb + u < kc) && d2 < rmax_c2 && r < c.max_range;          // Distance.cpp:86 / checkWithoutMinRange
+        const double co = p[2], si = p[3];
+        const double qx = co * dx + si * dy, qy = -si * dx + co * dy;
+        // field-of-view gate min_b < atan2(qy,qx) < max_b  (Simulator2D.cpp:100-111)
+        bool in_fov;
+        if (c.fov_wide && (qx > 0.0 || fabs(qy) > -qx * c.wedge_tan)) in_fov = true;
+        else if (inr) { const double bb = atan2(qy, qx); in_fov = bb < c.max_bearing && bb > c.min_bearing; }
+        else in_fov = false;
+        vis[u] = inr && in_fov;                                                     // occupancy visibility count (q8)
+        upd[u] = vis[u] && r > c.min_range && p[10] != 0.0;                         // full check (q10) ; det(info) gate
+        // body-frame covariance of the predicted virtual landmark
+        const double r2 = r * r;
+        const double sr = c.rr / r2;
+        const double Sxx = p[4], Sxy = p[5], Sxt = p[6], Syy = p[7], Syt = p[8], Stt = p[9];
+        const double cb00 = qy * qy * c.rb + qx * qx * sr + Sxx - 2.0 * qy * Sxt + qy * qy * Stt;
+        const double cb01 = qx * qy * (sr - c.rb) + Sxy - qy * Syt + qx * Sxt - qx * qy * Stt;
+        const double cb11 = qx * qx * c.rb + qy * qy * sr + Syy + 2.0 * qx * Syt + qx * qx * Stt;
+        const double idet = 1.0 / (cb00 * cb11 - cb01 * cb01);
+        const double lb00 = cb11 * idet, lb01 = -cb01 * idet, lb11 = cb00 * idet;   // body-frame information
+        // rotate to the map frame
+        const double cc = co * co, ss = si * si, cs = co * si;
+        nxx[u] = cc * lb00 - 2.0 * cs * lb01 + ss * lb11;
+        nxy[u] = cs * (lb00 - lb11) + (cc - ss) * lb01;
+        nyy[u] = ss * lb00 + 2.0 * cs * lb01 + cc * lb11;
+      }
+#pragma unroll
+      for (int u = 0; u < VU; ++u) {
+        if (vis[u]) ++cnt;
+        if (!upd[u]) continue;
+        if (!updated) { ixx = nxx[u]; ixy = nxy[u]; iyy = nyy[u]; updated = true; }
+        else {  // covariance intersection on information matrices (VirtualMap.cpp:364-377, q11)
+          const double a = ixx * iyy - ixy * ixy, bdet = nxx[u] * nyy[u] - nxy[u] * nxy[u];
+          const double cm = iyy * nxx[u] - 2.0 * ixy * nxy[u] + ixx * nyy[u];   // det(m1) * tr(m1^-1 m2)
+          const double d = a + bdet - cm;
+          double w = 0.5 * (2.0 * bdet - cm) / d;
+          if ((w < 0 && d < 0) || (w > 1 && d > 0)) w = 0.0;
+          else if ((w < 0 && d > 0) || (w > 1 && d < 0)) w = 1.0;
+          ixx = w * ixx + (1.0 - w) * nxx[u]; ixy = w * ixy + (1.0 - w) * nxy[u]; iyy = w * iyy + (1.0 - w) * nyy[u];
+        }
       }
     }
   }
