@@ -132,56 +132,12 @@ class GpuLoop:
         self.launches, self.graphs = self.runner.launches, self.runner.graphs
 
 
-def e2e_loop(loop: GpuLoop):
-    """The same tick through the reference-facing host API: graphs D2H -> host -> H2D for the GNN,
-    Q D2H, arg-max + line plans on the host, actions H2D, done flags + occupancy maps D2H."""
-    from drl_graph_exploration_b200.data import Batch, Data
-    from drl_graph_exploration_b200.envs.exploration_env import expand_plan
-
-    env, eng = loop.env, loop.env.eng
-    B = env.B
-    queues = [[] for _ in range(B)]
-    odom_host = np.zeros((B, 3)); done_host = np.zeros(B, dtype=np.uint8); obs_host = np.zeros((B, eng.rows, eng.cols))
-    mask_host = torch.zeros(B, dtype=torch.uint8).pin_memory()
-    stats = {"h2d": 0, "d2h": 0, "steps": 0}
-
-    @torch.no_grad()
-    def tick():
-        need = [i for i in range(B) if not queues[i]]
-        if need:
-            mask_host.zero_(); mask_host[need] = 1
-            mask = mask_host.to(env.device, non_blocking=True); stats["h2d"] += B
-            graphs = env.graph_host(mask)
-            for gph in graphs:
-                stats["d2h"] += gph["x"].nbytes + gph["edge_index"].nbytes + gph["edge_attr"].nbytes
-            datas = [Data(torch.from_numpy(gph["x"]), torch.from_numpy(gph["edge_index"]), torch.from_numpy(gph["edge_attr"])) for gph in graphs]
-            batch = Batch.from_data_list(datas).to(env.device)
-            stats["h2d"] += sum(gph["x"].nbytes + gph["edge_index"].nbytes + gph["edge_attr"].nbytes for gph in graphs)
-            q = loop.model(batch, 0.0).view(-1).cpu().numpy(); stats["d2h"] += q.nbytes
-            fxy = env.graph.frontier_xy.cpu().numpy(); stats["d2h"] += fxy.nbytes
-            goals = np.zeros((B, 2)); off = 0
-            for i, gph in zip(need, graphs):
-                n, k, f = gph["x"].shape[0], gph["key_size"], gph["fro_size"]
-                a = int(np.argmax(q[off + k: off + n])) if f > 0 else 0
-                goals[i] = fxy[i, a]; off += n
-            plans = env.line_plan(torch.as_tensor(goals, device=env.device), mask).cpu().numpy()
-            stats["h2d"] += goals.nbytes; stats["d2h"] += plans.nbytes
-            for i in need:
-                queues[i] = expand_plan(plans[i], eng.cfg.max_edge_length)
-        for i in range(B):
-            a = queues[i].pop(0)
-            odom_host[i] = (a.x, a.y, a.theta)
-        env.step_host(odom_host, done_host, obs_host)
-        stats["h2d"] += odom_host.nbytes; stats["d2h"] += done_host.nbytes + obs_host.nbytes
-        stats["steps"] += B
-        if done_host.any() or int(eng.state["n_poses"].max()) >= MAX_POSES - 1:
-            d = torch.as_tensor(done_host, device=env.device) | (eng.state["n_poses"] >= MAX_POSES - 1).to(torch.uint8)
-            eng.state["done"].copy_(d)
-            dn = env.reset_done().cpu().numpy()
-            for i in np.nonzero(dn)[0]:
-                queues[i] = []
-
-    return tick, stats
+def e2e_loop(loop: GpuLoop, overlap=True):
+    """The same tick through the reference-facing host-buffer API (drl_graph_exploration_b200.runner.HostPolicyLoop):
+    actions H2D from pinned memory, done flags + status metrics + occupancy maps D2H every step; graphs D2H -> host ->
+    H2D for the GNN, Q D2H, arg-max on the host, goals H2D, line plans D2H."""
+    from drl_graph_exploration_b200.runner import HostPolicyLoop
+    return HostPolicyLoop(loop.env, loop.model, overlap=overlap)
 
 
 def main():
@@ -269,17 +225,19 @@ def main():
                "gnn_graphs_per_s": graphs_all / (total_ms / 1e3), "gpu_launches": loop.launches, "clocks": clocks, "roofline": roof}
     # e2e + cpu baseline on rank 0 at N = 1 only
     if rank == 0 and world == 1 and not args.no_e2e:
-        tick, stats = e2e_loop(loop)
-        n_e2e = max(10, args.steps // 4)
-        for _ in range(3):
-            tick()
-        stats.update(h2d=0, d2h=0, steps=0)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
+        loop.env.reset()                      # fresh episodes: the host loop owns the action lists from here on
+        hl = e2e_loop(loop, overlap=not args.no_overlap)
+        n_e2e = max(20, args.steps)
+        for _ in range(max(args.warmup, 12)):   # past the first decision and a few restarts
+            hl.tick()
+        torch.cuda.synchronize()
+        s0, h0, d0, t0 = hl.steps, hl.h2d, hl.d2h, time.perf_counter()
         for _ in range(n_e2e):
-            tick()
+            hl.tick()
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
-        out["e2e"] = {"value": stats["steps"] / dt, "unit": "env-steps/s", "h2d_bytes_per_step": stats["h2d"] / n_e2e,
-                      "d2h_bytes_per_step": stats["d2h"] / n_e2e, "ticks": n_e2e}
+        out["e2e"] = {"value": (hl.steps - s0) / dt, "unit": "env-steps/s", "h2d_bytes_per_step": (hl.h2d - h0) / n_e2e,
+                      "d2h_bytes_per_step": (hl.d2h - d0) / n_e2e, "ticks": n_e2e, "ms_per_tick": 1e3 * dt / n_e2e,
+                      "api": "HostPolicyLoop: dge_step_host_async + dge_graph_host + dge_line_plan_host (pinned host buffers)"}
     elif rank == 0:
         out["e2e"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -74,6 +74,7 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.done = al.get<uint8_t>(B);
   e.plan = al.get<double>(B * 6); e.plan_cursor = al.get<int32_t>(B);
   e.odom_dev_scratch = al.get<double>(B * 3); e.mask_dev_scratch = al.get<uint8_t>(B);
+  e.mask_dev_scratch2 = al.get<uint8_t>(B); e.goal_dev_scratch = al.get<double>(B * 2); e.plan_dev_scratch = al.get<double>(B * 6);
   e.g_counts = al.get<int32_t>(B * 4); e.g_frontier = al.get<int32_t>(B * d.Fmax); e.g_fassoc = al.get<int32_t>(B * (L + 1)); e.g_sel = al.get<int32_t>(B);
   e.g_cnt = al.get<int32_t>(B * (size_t)d.Ncap); e.g_cur = al.get<int32_t>(B * (size_t)d.Ncap); e.g_dis = al.get<float>(B * (size_t)d.Ncap);
   e.g_tmp = al.get<int32_t>(B * (size_t)d.Ecap);
@@ -198,6 +199,79 @@ extern "C" int dge_step_host(dge_handle h, const double *odom_host, const uint8_
   if (done_host && cudaMemcpyAsync(done_host, h->done, B, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host: D2H done");
   if (obs_host && cudaMemcpyAsync(obs_host, h->prob, B * h->d.V * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host: D2H obs");
   if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host: sync");
+  return DGE_OK;
+}
+
+extern "C" int dge_step_host_async(dge_handle h, const double *odom_host, const uint8_t *mask_host, uint8_t *done_host, double *obs_host,
+                                   double *metrics_host, int flags, void *stream) {
+  if (!h || !odom_host) return DGE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t B = h->d.B;
+  if (cudaMemcpyAsync(h->odom_dev_scratch, odom_host, B * 3 * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host_async: H2D odom");
+  const uint8_t *mask = nullptr;
+  if (mask_host) {
+    if (cudaMemcpyAsync(h->mask_dev_scratch, mask_host, B, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host_async: H2D mask");
+    mask = h->mask_dev_scratch;
+  }
+  int rc = dge_launch_move_measure(h, h->odom_dev_scratch, mask, nullptr, (flags & DGE_STEP_HONOR_FORCED) ? 3 : 0, st);
+  if (rc) return fail(rc, "dge_step_host_async: move_measure");
+  if ((rc = dge_launch_slam(h, h->active, st))) return fail(rc, "dge_step_host_async: slam");
+  if ((rc = dge_launch_vmap(h, h->active, st))) return fail(rc, "dge_step_host_async: vmap");
+  if (done_host && cudaMemcpyAsync(done_host, h->done, B, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host_async: D2H done");
+  if (metrics_host && cudaMemcpyAsync(metrics_host, h->metrics, B * 8 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host_async: D2H metrics");
+  if (obs_host && cudaMemcpyAsync(obs_host, h->prob, B * h->d.V * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host_async: D2H obs");
+  if (!(flags & DGE_STEP_NO_SYNC) && cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_step_host_async: sync");
+  return DGE_OK;
+}
+
+extern "C" int dge_graph_host(dge_handle h, const uint8_t *mask_host, const dge_graph_out *dev, const dge_graph_host_out *host, void *stream) {
+  if (!h || !dev || !host || !host->x || !host->edge_index || !host->edge_attr || !host->node_ptr || !host->edge_ptr || !host->key_size ||
+      !host->fro_size || !host->frontier_xy || !host->totals)
+    return fail(DGE_EINVAL, "dge_graph_host: null buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t B = h->d.B;
+  const uint8_t *mask = nullptr;
+  if (mask_host) {
+    if (cudaMemcpyAsync(h->mask_dev_scratch2, mask_host, B, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host: H2D mask");
+    mask = h->mask_dev_scratch2;
+  }
+  int rc = dge_graph(h, mask, dev, stream);
+  if (rc) return rc;
+  if (cudaMemcpyAsync(host->totals, dev->totals, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host: D2H totals");
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host: sync");
+  const size_t G = host->totals[0], N = host->totals[1], E = host->totals[2];
+  if (host->totals[3]) return fail(DGE_ECAP, "dge_graph_host: graph batch capacity exceeded");
+  if (G == 0) return DGE_OK;
+  bool ok = true;
+  auto d2h = [&](void *dst, const void *src, size_t bytes) { if (bytes) ok = ok && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) == cudaSuccess; };
+  d2h(host->x, dev->x, N * 5 * sizeof(float));
+  d2h(host->edge_index, dev->edge_index, E * sizeof(int64_t));                    // row 0 (sources)
+  d2h(host->edge_index + E, dev->edge_index + dev->edge_cap, E * sizeof(int64_t)); // row 1 (destinations): [2,E] contiguous on the host
+  d2h(host->edge_attr, dev->edge_attr, E * sizeof(float));
+  d2h(host->node_ptr, dev->node_ptr, (G + 1) * sizeof(int32_t));
+  d2h(host->edge_ptr, dev->edge_ptr, (G + 1) * sizeof(int32_t));
+  d2h(host->key_size, dev->key_size, G * sizeof(int32_t));
+  d2h(host->fro_size, dev->fro_size, G * sizeof(int32_t));
+  d2h(host->frontier_xy, dev->frontier_xy, B * (size_t)h->d.Fmax * 2 * sizeof(double));
+  if (!ok) return fail(DGE_ECUDA, "dge_graph_host: D2H graph");
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host: sync");
+  return DGE_OK;
+}
+
+extern "C" int dge_line_plan_host(dge_handle h, const double *goal_host, const uint8_t *mask_host, double *plan_host, void *stream) {
+  if (!h || !goal_host || !plan_host) return DGE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t B = h->d.B;
+  if (cudaMemcpyAsync(h->goal_dev_scratch, goal_host, B * 2 * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_line_plan_host: H2D goals");
+  const uint8_t *mask = nullptr;
+  if (mask_host) {
+    if (cudaMemcpyAsync(h->mask_dev_scratch2, mask_host, B, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_line_plan_host: H2D mask");
+    mask = h->mask_dev_scratch2;
+  }
+  const int rc = dge_launch_line_plan(h, h->goal_dev_scratch, mask, h->plan_dev_scratch, st);
+  if (rc) return fail(rc, "dge_line_plan_host");
+  if (cudaMemcpyAsync(plan_host, h->plan_dev_scratch, B * 6 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_line_plan_host: D2H plans");
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_line_plan_host: sync");
   return DGE_OK;
 }
 

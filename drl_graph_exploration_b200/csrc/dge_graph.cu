@@ -358,9 +358,14 @@ __device__ void line_plan(const dge_config &cfg, double rx, double ry, double rt
 }
 
 __global__ void k_line_plan(dge_config cfg, DgeDims d, const int32_t *n_poses, const double *est_pose, const double *goal,
-                            const uint8_t *mask, double *plan_out) {
+                            const uint8_t *mask, double *plan_out, uint8_t *done) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= d.B || (mask && !mask[b])) return;
+  if (mask && mask[b] == 2) {   // no frontier left (q15): the episode is over, like k_select_plan's F <= 0 branch
+    for (int i = 0; i < 6; ++i) plan_out[6 * b + i] = 0;
+    if (done) done[b] = 1;
+    return;
+  }
   const int T = n_poses[b];
   const double *p = est_pose + ((size_t)b * d.Tmax + T - 1) * 3;
   line_plan(cfg, p[0], p[1], p[2], goal[2 * b], goal[2 * b + 1], plan_out + 6 * b);
@@ -424,7 +429,7 @@ int dge_launch_graph(dge_engine *e, const uint8_t *mask, const dge_graph_out *ou
 }
 
 int dge_launch_line_plan(dge_engine *e, const double *goal, const uint8_t *mask, double *plan_out, cudaStream_t st) {
-  k_line_plan<<<(e->d.B + 127) / 128, 128, 0, st>>>(e->cfg, e->d, e->n_poses, e->est_pose, goal, mask, plan_out);
+  k_line_plan<<<(e->d.B + 127) / 128, 128, 0, st>>>(e->cfg, e->d, e->n_poses, e->est_pose, goal, mask, plan_out, e->done);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }
 

@@ -57,6 +57,9 @@ struct dge_engine {
   // ---- scratch for host-buffer calls ----
   double *odom_dev_scratch;  // [B,3]
   uint8_t *mask_dev_scratch; // [B]
+  uint8_t *mask_dev_scratch2; // [B]   policy-side host calls (dge_graph_host / dge_line_plan_host) -- may run beside dge_step_host
+  double *goal_dev_scratch;  // [B,2]
+  double *plan_dev_scratch;  // [B,6]
   // graph scratch
   int32_t *g_counts;     // [B,4] N,E,K,F per env
   int32_t *g_frontier;   // [B,Fmax] frontier cell index

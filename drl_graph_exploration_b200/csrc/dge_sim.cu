@@ -168,7 +168,10 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
   bool act = !(mask && !mask[b]);
   double ox = 0, oy = 0, oth = 0;
   int fl = 0;
-  if (act && from_queue == 1) {
+  // from_queue: 0 = explicit odom, 1 = queued line plans (parks done envs), 2 = queued, roll-out clones (run every plan
+  // to its end), 3 = explicit odom from the host loop, except for envs an in-pipeline reset left in their forced phase
+  const bool queued = from_queue == 1 || from_queue == 2;
+  if (act && (from_queue == 1 || from_queue == 3)) {
     fl = a.forced[b];
     if (fl & DGE_FRESH_BIT) {   // reset earlier in this tick: no move, but SLAM (the initial optimize) runs
       if (lane == 0) { a.forced[b] = fl & ~DGE_FRESH_BIT; a.active[b] = 1; a.step_kind[b] = 0; }
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
   }
   if (act) {
     if (fl > 0) { ox = a.forced_odom[0]; oy = a.forced_odom[1]; oth = a.forced_odom[2]; }
-    else if (from_queue) {  // expand the compact line plan (Planner2D.cpp:982-1038)
+    else if (queued) {  // expand the compact line plan (Planner2D.cpp:982-1038)
       const double *pl = a.plan + 6 * b;
       const int cur = a.plan_cursor[b], nrot = (int)pl[0], nfwd = (int)pl[3], nact = (int)pl[5];
       if (cur >= nact) act = false;
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
     a.dist[b] += sqrt(ox * ox + oy * oy);  // exploration_env.py:103
     a.rdist[b] += sqrt(ox * ox + oy * oy + a.cfg.angle_weight * oth * oth);   // Planner2D.cpp:1440 (roll-out distance)
     if (fl > 0) a.forced[b] = fl - 1;
-    else if (from_queue) a.plan_cursor[b] += 1;
+    else if (queued) a.plan_cursor[b] += 1;
   }
   __syncwarp();
   __threadfence_block();

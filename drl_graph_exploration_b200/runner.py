@@ -86,3 +86,153 @@ class PolicyLoop:
         if self.overlap:
             main.wait_event(self.ev_step)            # join: the tick ends when both pipelines are done
         return ng
+
+
+class HostPolicyLoop:
+    """The same acting loop driven from the HOST through the host-buffer C ABI -- the batched form of what
+    the reference's ``test.py:100-143`` does per env: every observation crosses to the host and every
+    action comes from it.
+
+    Per tick (B envs):
+      * stepping envs: ``dge_step_host_async`` -- actions H2D from pinned memory, one simulator step, done flags +
+        ``ExplorationEnv.status`` metrics + occupancy maps D2H (exploration_env.py:98-105);
+      * envs whose action list ran empty: ``dge_graph_host`` (graph_matrix + data_process, host arrays out) ->
+        ``Data(...).to(device)`` -> ``model`` -> Q-values D2H -> arg-max over each graph's frontier nodes on the host
+        (test.py:112) -> ``dge_line_plan_host`` (actions_all_goals for the chosen frontier) -> host action lists;
+      * finished episodes restart in-pipeline (``dge_reset_done_queued``); the host tracks the reset phase.
+    The two pipelines work on disjoint env sets, so the policy side runs on a second stream while the step is in
+    flight; NumPy work is vectorised over envs (no per-env Python).
+    """
+
+    def __init__(self, env: VecExplorationEnv, model: torch.nn.Module, overlap: bool = True, read_obs: bool = True):
+        import numpy as np
+        from .engine import load_library
+        self.np = np
+        self.env, self.model, self.overlap = env, model, overlap
+        eng, g, B = env.eng, env.graph, env.B
+        self.dev = env.device
+        L = self._L = load_library()
+        vp = ctypes.c_void_p
+        L.dge_step_host_async.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.dge_graph_host.argtypes = [vp, vp, vp, vp, vp]
+        L.dge_line_plan_host.argtypes = [vp, vp, vp, vp, vp]
+        pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+        f64, f32, i32, i64, u8 = torch.float64, torch.float32, torch.int32, torch.int64, torch.uint8
+        # step-side host buffers
+        self.t_odom, self.t_mask, self.t_done = pin((B, 3), f64), pin((B,), u8), pin((B,), u8)
+        self.t_metrics = pin((B, 8), f64)
+        self.t_obs = pin((B, eng.rows, eng.cols), f64) if read_obs else None
+        # policy-side host buffers (capacity of the device staging batch)
+        self.t_need = pin((B,), u8)
+        self.t_x, self.t_ei, self.t_ea = pin((g.node_cap, 5), f32), pin((2 * g.edge_cap,), i64), pin((g.edge_cap,), f32)
+        self.t_nptr, self.t_eptr, self.t_ks, self.t_fs = pin((B + 1,), i32), pin((B + 1,), i32), pin((B,), i32), pin((B,), i32)
+        self.t_fxy, self.t_tot = pin((B, eng.Lt + 1, 2), f64), pin((8,), i32)
+        self.t_goal, self.t_plan = pin((B, 2), f64), pin((B, 6), f64)
+        self.t_q = pin((g.node_cap,), f32)
+
+        class _HostOut(ctypes.Structure):
+            _fields_ = [(n, vp) for n in ("x", "edge_index", "edge_attr", "node_ptr", "edge_ptr", "key_size", "fro_size", "frontier_xy", "totals")]
+        self._ho = _HostOut(*(t.data_ptr() for t in (self.t_x, self.t_ei, self.t_ea, self.t_nptr, self.t_eptr, self.t_ks, self.t_fs, self.t_fxy, self.t_tot)))
+        for name in ("odom", "mask", "done", "metrics", "need", "nptr", "ks", "fs", "fxy", "goal", "plan", "q"):
+            setattr(self, name, getattr(self, "t_" + name).numpy())
+        # host-side action lists in the compact form of dge_line_plan: (n_rot_pi, sign, rot_rem, n_fwd, fwd_rem, n_actions)
+        self.plans = np.zeros((B, 6)); self.cursor = np.zeros(B, dtype=np.int64)
+        self.phase = np.zeros(B, dtype=np.int64)       # ticks of reset work (initial optimize + forced steps) still to run
+        self.s_step = torch.cuda.Stream(self.dev) if overlap else None
+        self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
+        self.seed_stride = B
+        self.steps = 0                                  # policy env-steps executed
+        self.h2d = self.d2h = 0                         # bytes moved
+        self.launches = 0
+        self.graphs = 0
+        self._frange = np.arange(eng.Lt + 1)
+
+    def _next_actions(self):
+        """Vectorised expansion of action `cursor` of every env's line plan (Planner2D.cpp:982-1038) into odom[B,3]."""
+        np = self.np
+        pl, cur = self.plans, self.cursor
+        nrot, nfwd = pl[:, 0].astype(np.int64), pl[:, 3].astype(np.int64)
+        od = self.odom
+        od[:] = 0.0
+        od[:, 2] = np.where(cur < nrot, pl[:, 1] * np.pi, np.where(cur == nrot, pl[:, 1] * pl[:, 2], 0.0))
+        fwd = cur > nrot
+        od[:, 0] = np.where(fwd, np.where(cur < nrot + 1 + nfwd, self.env.cfg.max_edge_length, pl[:, 4]), 0.0)
+
+    @torch.no_grad()
+    def tick(self):
+        np = self.np
+        env, eng, L = self.env, self.env.eng, self._L
+        B = env.B
+        main = torch.cuda.current_stream(self.dev)
+        s1 = self.s_step if self.overlap else main
+        nact = self.plans[:, 5].astype(np.int64)
+        in_reset = self.phase > 0
+        has_act = (self.cursor < nact) & ~in_reset
+        need = ~has_act & ~in_reset
+        # ---- step pipeline (async on s1): reset finished episodes, then one simulator step from host actions ------
+        if self.overlap:
+            s1.wait_stream(main)
+        sp = ctypes.c_void_p(s1.cuda_stream)
+        _check(L.dge_reset_done_queued(eng._h, self.seed_stride, self._fo, 4, sp), "dge_reset_done_queued")
+        self._next_actions()
+        self.mask[:] = has_act | in_reset
+        _check(L.dge_step_host_async(eng._h, self.t_odom.data_ptr(), self.t_mask.data_ptr(), self.t_done.data_ptr(),
+                                     None if self.t_obs is None else self.t_obs.data_ptr(), self.t_metrics.data_ptr(), 1 | 2, sp), "dge_step_host_async")
+        self.launches += 6
+        self.h2d += self.t_odom.nbytes + B
+        self.d2h += B + self.t_metrics.nbytes + (0 if self.t_obs is None else self.t_obs.nbytes)
+        n_stepped = int(has_act.sum())
+        self.cursor[has_act] += 1
+        self.phase[in_reset] -= 1
+        # ---- policy pipeline (main stream, host in the loop) ----------------------------------------------------
+        if need.any():
+            mp = ctypes.c_void_p(main.cuda_stream)
+            self.need[:] = need
+            _check(L.dge_graph_host(eng._h, self.t_need.data_ptr(), ctypes.byref(env.graph.c), ctypes.byref(self._ho), mp), "dge_graph_host")
+            ng, n, e = (int(v) for v in self.t_tot[:3])
+            self.launches += 4
+            self.h2d += B
+            self.d2h += 32 + n * 20 + e * 20 + (2 * ng + 2) * 4 + 2 * ng * 4 + self.t_fxy.nbytes
+            if ng > 0:
+                from . import gnn
+                from .data import Data
+                # the policy gets the HOST graph batch, like DeepQ.test: data.to(device) -> model -> Q back on the host
+                x = self.t_x[:n].to(self.dev, non_blocking=True)
+                ei = self.t_ei[:2 * e].view(2, e).to(self.dev, non_blocking=True)
+                ea = self.t_ea[:e].to(self.dev, non_blocking=True)
+                self.h2d += n * 20 + e * 20
+                l0 = gnn.launch_count
+                q = self.model(Data(x, ei, ea), 0.0).view(-1)
+                self.t_q[:n].copy_(q, non_blocking=True)
+                main.synchronize()
+                self.launches += gnn.launch_count - l0
+                self.d2h += n * 4
+                # arg-max over the last fro_size nodes of every graph (test.py:112), vectorised with a padded gather
+                ks, fs, nptr = self.ks[:ng].astype(np.int64), self.fs[:ng].astype(np.int64), self.nptr[:ng].astype(np.int64)
+                idx = (nptr + ks)[:, None] + self._frange[None, :]
+                valid = self._frange[None, :] < fs[:, None]
+                vals = np.where(valid, self.q[np.minimum(idx, n - 1)], -np.inf)
+                choice = vals.argmax(axis=1)
+                envs = np.nonzero(need)[0]
+                choice = np.where(fs > 0, choice, 0)
+                self.goal[envs] = self.fxy[envs, choice]
+                nofro = envs[fs <= 0]
+                if nofro.size:                    # no frontier left (q15): episode over -- mask value 2 sets the done flag
+                    self.need[nofro] = 2
+                    self.phase[nofro] = 5
+                _check(L.dge_line_plan_host(eng._h, self.t_goal.data_ptr(), self.t_need.data_ptr(), self.t_plan.data_ptr(), mp), "dge_line_plan_host")
+                self.launches += 1
+                self.h2d += self.t_goal.nbytes + B
+                self.d2h += self.t_plan.nbytes
+                self.plans[envs] = self.plan[envs]
+                self.cursor[envs] = 0
+                self.last_choice = (envs, choice)
+                self.graphs += ng
+        # ---- join: the step's host buffers are valid after this ---------------------------------------------------
+        s1.synchronize()
+        done = self.done.astype(bool)
+        if done.any():
+            self.phase[done] = 5          # initial optimize + 4 forced steps, executed by the next 5 ticks
+            self.plans[done, 5] = 0; self.cursor[done] = 0
+        self.steps += n_stepped
+        return n_stepped

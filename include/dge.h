@@ -111,6 +111,19 @@ int dge_virtual_map(dge_handle h, const uint8_t *mask_dev, void *stream);     /*
 int dge_step_host(dge_handle h, const double *odom_host, const uint8_t *mask_host, uint8_t *done_host,
                   double *obs_host /* [B,rows,cols] nullable */, void *stream);
 
+/* the same for a host-driven acting loop (test.py:100-143 with B envs): flags select
+ *   DGE_STEP_NO_SYNC       do not synchronise -- the caller synchronises `stream` before reading the host buffers (lets the
+ *                          policy-side host calls below run on another stream meanwhile);
+ *   DGE_STEP_HONOR_FORCED  envs that dge_reset_queued / dge_reset_done_queued left in their reset phase (initial optimize +
+ *                          forced steps, exploration_env.py:411-414) execute that instead of the supplied odom (they must be
+ *                          selected by mask_host);
+ * metrics_host [B,8] nullable: dge_state_view.metrics after the step (ExplorationEnv.status / get_landmark_error /
+ * max_uncertainty_of_trajectory, exploration_env.py:164-194).                          */
+#define DGE_STEP_NO_SYNC 1
+#define DGE_STEP_HONOR_FORCED 2
+int dge_step_host_async(dge_handle h, const double *odom_host, const uint8_t *mask_host, uint8_t *done_host, double *obs_host,
+                        double *metrics_host, int flags, void *stream);
+
 /* ---- stand-alone virtual-map rebuild on caller-provided belief states (a6+a7;
  * VirtualMap::updateProbability + updateInformation).  n problems, T poses each.
  *   pose_dev [n,T,3], cov_dev [n,T,6] (upper triangle xx,xy,xt,yy,yt,tt of the pose
@@ -194,6 +207,19 @@ typedef struct dge_graph_out {
   float *gcn_selfnorm;     /* [Ncap]    2 / deg                                                            */
 } dge_graph_out;
 int dge_graph(dge_handle h, const uint8_t *mask_dev, const dge_graph_out *out, void *stream);
+/* host-buffer variant of dge_graph: what ExplorationEnv.graph_matrix + DeepQ.data_process hand to the caller, for the
+ * envs selected by mask_host, as ONE batch in PyG DataLoader layout.  `dev` = device staging buffers as for dge_graph;
+ * the valid prefixes are copied into the (pinned) host buffers: x [N,5], edge_index [2,E] CONTIGUOUS (row 1 starts at
+ * element E), edge_attr [E], node_ptr / edge_ptr [G+1], key_size / fro_size [G], frontier_xy [B,Fmax,2] (by env),
+ * totals [8] (G, N, E, overflow, #done).  Synchronises `stream`.                                               */
+typedef struct dge_graph_host_out {
+  float *x; int64_t *edge_index; float *edge_attr;
+  int32_t *node_ptr, *edge_ptr, *key_size, *fro_size;
+  double *frontier_xy;
+  int32_t *totals;
+} dge_graph_host_out;
+int dge_graph_host(dge_handle h, const uint8_t *mask_host, const dge_graph_out *dev, const dge_graph_host_out *host, void *stream);
+
 /* writes dge_state_view.pending: 1 for the envs that need a decision right now (action queue empty, episode
  * running, no forced reset steps outstanding) -- the selection the acting loop of policy.py:236-306 makes,
  * evaluated on the device; pass it as mask_dev to dge_graph.                                            */
@@ -201,9 +227,14 @@ int dge_mark_pending(dge_handle h, void *stream);
 
 /* ---- line planner: replaces EMPlanner2D.line_planner (Planner2D.cpp:937-1041) for one
  * goal per env.  goal_dev [B,2]; plan_dev [B,6] = (n_rot_pi, rot_sign, rot_remainder,
- * n_fwd_full, fwd_remainder, n_actions).  Action i of the plan is expanded by
- * dge_plan_action.  mask nullable.                                                   */
+ * n_fwd_full, fwd_remainder, n_actions); action i < n_actions is: i < n_rot_pi: (0,0,sign*pi); i == n_rot_pi:
+ * (0,0,sign*rot_remainder); then n_fwd_full x (max_edge_length,0,0) and one (fwd_remainder,0,0).  mask nullable;
+ * mask value 2 = "this env has no frontier left" (ExplorationEnv.frontier would crash, quirk q15): the episode
+ * is declared over (done flag set, empty plan).                                       */
 int dge_line_plan(dge_handle h, const double *goal_dev, const uint8_t *mask_dev, double *plan_dev, void *stream);
+
+/* host-buffer variant (EMExplorer.line_plan, pyplanner2d.py:76-78): goal_host [B,2], mask_host [B] nullable, plan_host [B,6]. */
+int dge_line_plan_host(dge_handle h, const double *goal_host, const uint8_t *mask_host, double *plan_host, void *stream);
 
 /* ---- policy head on device: per selected graph, argmax of q over its last fro_size
  * nodes (policy.py:109 / test.py:112), goal = that frontier, line plan into the env's

@@ -1,0 +1,75 @@
+"""HostPolicyLoop (host-buffer C ABI: dge_step_host_async / dge_graph_host / dge_line_plan_host) against the
+device-resident PolicyLoop: same seeds, same policy => every env goes through the same sequence of operations
+(test.py:100-143 per env), so after K ticks the engine states must agree.  The host path re-uploads the graph and
+builds its own CSR, so Q-values may differ in the last bit; states are compared exactly for the integer fields and
+to 1e-9 for fp64 (a flipped arg-max would show up as a different trajectory length)."""
+import numpy as np
+import pytest
+import torch
+
+from drl_graph_exploration_b200.config import EnvConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(n, seed0=300):
+    from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv
+    env = VecExplorationEnv(n, cfg=EnvConfig(map_size=20, num_landmarks=30), max_poses=96, seed0=seed0)
+    env.reset()
+    return env
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_host_loop_matches_device_loop(overlap):
+    from drl_graph_exploration_b200 import Networks
+    from drl_graph_exploration_b200.runner import HostPolicyLoop, PolicyLoop
+    a, b = _mk(24), _mk(24)
+    torch.manual_seed(0)
+    model = Networks.GCN().to(a.device).eval()
+    dev_loop = PolicyLoop(a, model, overlap=overlap)
+    host_loop = HostPolicyLoop(b, model, overlap=overlap)
+    K = 120                                        # long enough for several episodes to end and restart in-pipeline
+    for _ in range(K):
+        dev_loop.tick()
+        host_loop.tick()
+    torch.cuda.synchronize()
+    sa, sb = a.eng.state, b.eng.state
+    assert int(sa["counters"][3]) > 0              # some episodes restarted
+    for f in ("n_poses", "sim_step", "update_count", "meas_ptr", "observed", "seed", "seen"):
+        assert torch.equal(sa[f], sb[f]), f
+    assert int(sa["counters"][0]) == int(sb["counters"][0]) == host_loop.steps
+    T = sa["n_poses"].cpu().numpy()
+    ea, eb = sa["est_pose"].cpu().numpy(), sb["est_pose"].cpu().numpy()
+    for i in range(a.B):
+        np.testing.assert_allclose(ea[i, :T[i]], eb[i, :T[i]], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(sa["prob"].cpu().numpy(), sb["prob"].cpu().numpy(), rtol=0, atol=0)
+    # the host buffers hold what the step returned: done flags, metrics, occupancy maps
+    np.testing.assert_array_equal(host_loop.done, sb["done"].cpu().numpy())
+    np.testing.assert_array_equal(host_loop.t_obs.numpy(), sb["prob"].cpu().numpy())
+    np.testing.assert_array_equal(host_loop.metrics[:, 0], sb["metrics"][:, 0].cpu().numpy())
+    assert host_loop.h2d > 0 and host_loop.d2h > 0 and host_loop.graphs == dev_loop.graphs
+    a.close(); b.close()
+
+
+def test_graph_host_equals_device_graph():
+    """dge_graph_host: the host batch is the valid prefix of the device batch, edge_index contiguous [2,E]."""
+    import ctypes
+    from drl_graph_exploration_b200 import Networks
+    from drl_graph_exploration_b200.runner import HostPolicyLoop
+    env = _mk(8, seed0=7)
+    loop = HostPolicyLoop(env, Networks.GCN().to(env.device).eval(), overlap=False)
+    loop.need[:] = 1
+    loop.need[3] = 0
+    mp = ctypes.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+    rc = loop._L.dge_graph_host(env.eng._h, loop.t_need.data_ptr(), ctypes.byref(env.graph.c), ctypes.byref(loop._ho), mp)
+    assert rc == 0
+    ng, n, e = (int(v) for v in loop.t_tot[:3])
+    assert ng == 7 and n > 0 and e > 0
+    g = env.graph
+    assert torch.equal(loop.t_x[:n], g.x[:n].cpu())
+    assert torch.equal(loop.t_ei[:2 * e].view(2, e), g.edge_index[:, :e].cpu())
+    assert torch.equal(loop.t_ea[:e], g.edge_attr[:e].cpu())
+    assert torch.equal(loop.t_nptr[:ng + 1], g.node_ptr[:ng + 1].cpu())
+    assert torch.equal(loop.t_ks[:ng], g.key_size[:ng].cpu()) and torch.equal(loop.t_fs[:ng], g.fro_size[:ng].cpu())
+    assert torch.equal(loop.t_fxy, g.frontier_xy.cpu())
+    env.close()
