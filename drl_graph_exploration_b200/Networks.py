@@ -20,21 +20,25 @@ import torch.nn.functional as F
 
 from . import gnn
 
-_PRECISION = "fp32"
+_PRECISION = "tc3"
 
 
 def set_matmul_precision(mode: str):
-    """'fp32' (parity mode: 1e-4 on Q-values), 'tf32' or 'bf16' (throughput modes) for the dense node-MLP GEMMs."""
+    """Dense node-MLP GEMMs: 'tc3' (default) = hand-written tcgen05 kernel, 3xTF32 split, fp32-quality (1e-4 on
+    Q-values holds with ~100x margin); 'fp32' = library SGEMM (A/B reference); 'tf32' / 'bf16' = library
+    single-pass tensor-core modes (do not meet the parity tolerance)."""
     global _PRECISION
-    assert mode in ("fp32", "tf32", "bf16")
+    assert mode in ("tc3", "fp32", "tf32", "bf16")
     _PRECISION = mode
 
 
 def _mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    if _PRECISION == "tc3" and a.is_cuda and a.dim() == 2 and b.dim() == 2 and gnn.tc_supported(a.shape[1], b.shape[1]):
+        return gnn.tc_matmul(a, b)
     if _PRECISION == "bf16":
         return (a.bfloat16() @ b.bfloat16()).float()
     prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = _PRECISION == "tf32"
+    torch.backends.cuda.matmul.allow_tf32 = _PRECISION == "tf32"   # 'tc3' on an unsupported shape (K = 5 input layer): fp32
     try:
         return a @ b
     finally:

@@ -1,0 +1,285 @@
+// Dense node-MLP GEMM of the graph Q-network on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the cuBLAS SGEMM behind PyG's GCNConv / GatedGraphConv / GRUCell transforms
+// (scripts/Networks.py:22-24,76-82: X @ W with X [nodes,1000] fp32 and W [1000,1000|3000]), rows a16/a17 of
+// SURVEY section 8.  The contract on Q-values is 1e-4 relative in fp32, which a single TF32 (10-bit mantissa)
+// or BF16 pass does not meet over K = 1000, so the product is evaluated as a 3xTF32 split:
+//     x = hi + lo,  hi = tf32(x), lo = tf32(x - hi)          (x - hi is exact in fp32)
+//     A B^T ~= Ah Bh^T + Al Bh^T + Ah Bl^T                   (dropped term Al Bl^T ~ 2^-22 relative)
+// with fp32 accumulation in tensor memory: error ~1e-6 relative, i.e. fp32-GEMM quality at tensor-core speed.
+//
+// Kernel shape (one 128x128 output tile per CTA, 192 threads, warp-specialised):
+//   warp 0   TMA producer: per 32-wide K block four 128x32 fp32 boxes (Ah, Al, Bh, Bl; 128-byte swizzle)
+//            into a 3-stage shared-memory ring, completion on an mbarrier (expect_tx);
+//   warp 1   allocates 128 TMEM columns, then one elected lane issues tcgen05.mma.kind::tf32 (M128 N128 K8):
+//            3 products x 4 K-steps per stage, tcgen05.commit releases the stage / signals the epilogue;
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp and pass) -> registers -> 128-byte row
+//            segments of C (row / column masked).
+// Operands are K-major ([rows, K] with K contiguous): A = activations, B^T = the weight stored [out, in].
+// The row count can be read from device memory (M_dev) so that a graph batch whose size is only known on the
+// device needs no host synchronisation: CTAs beyond the live rows exit immediately.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dge_gnn.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;       // BK fp32 = 128 bytes = one SWIZZLE_128B row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;          // 16 KB per operand tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // Ah, Al, Bh, Bl
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 128;                   // 128 lanes x 128 fp32 columns = the 128x128 accumulator
+constexpr int UMMA_K = 8;                        // tf32: 32 bytes of K per instruction
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+
+// instruction descriptor (cute::UMMA::InstrDescriptor layout): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must fault (launch error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major tile of 128-byte rows, SWIZZLE_128B,
+// 8-row core groups 1024 bytes apart (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` when every MMA issued so far has retired
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+              const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
+              float *__restrict__ C, int M, const int32_t *__restrict__ M_dev, int N, int K, int ldc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int rows = M_dev ? min(M, *M_dev) : M;
+  if (m0 >= rows) return;                                  // uniform per CTA, before any barrier / allocation
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B tiles want 1024-byte alignment
+  const uint32_t bars = tiles + STAGES * STAGE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, slot = tfull + 8;
+  uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (slot - smem_u32(smem_raw)));
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                         // one warp owns the TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {                                       // ---- TMA producer
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+        const uint32_t st = tiles + s * STAGE_BYTES, fb = full0 + 8 * s;
+        mbar_expect_tx(fb, STAGE_BYTES);
+        tma_load_2d(st, &mAh, fb, kb * BK, m0);
+        tma_load_2d(st + TILE_BYTES, &mAl, fb, kb * BK, m0);
+        tma_load_2d(st + 2 * TILE_BYTES, &mBh, fb, kb * BK, n0);
+        tma_load_2d(st + 3 * TILE_BYTES, &mBl, fb, kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                       // ---- MMA issuer (one thread drives the tensor core)
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t st = tiles + s * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint32_t off = k * UMMA_K * 4;             // 32 bytes along K inside the swizzled 128-byte row
+          const uint64_t ah = smem_desc(st + off), al = smem_desc(st + TILE_BYTES + off);
+          const uint64_t bh = smem_desc(st + 2 * TILE_BYTES + off), bl = smem_desc(st + 3 * TILE_BYTES + off);
+          umma_tf32(tmem, al, bh, (kb | k) ? 1u : 0u);     // small terms first
+          umma_tf32(tmem, ah, bl, 1u);
+          umma_tf32(tmem, ah, bh, 1u);
+        }
+        umma_commit(empty0 + 8 * s);                       // stage free once these MMAs have read it
+      }
+      umma_commit(tfull);                                  // accumulator complete
+    }
+  } else {                                                 // ---- epilogue: TMEM -> registers -> C
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int q = warp & 3;                                // a warp reaches TMEM lanes [32 (warp % 4), +32)
+    const int row = m0 + q * 32 + lane;
+    float *crow = C + (size_t)row * ldc + n0;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < rows) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int col = n0 + c * 32 + 4 * i;
+          if (col + 3 < N) {
+            *reinterpret_cast<float4 *>(crow + c * 32 + 4 * i) =
+                make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          } else {
+            for (int j = 0; j < 4; ++j)
+              if (col + j < N) crow[c * 32 + 4 * i + j] = __uint_as_float(r[4 * i + j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// x -> (tf32(x), tf32(x - tf32(x))), round-to-nearest; 4 elements per thread
+__global__ void k_split_tf32(int64_t n4, const float4 *__restrict__ x, float4 *__restrict__ hi, float4 *__restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = x[i];
+  float4 h, l;
+  auto split = [](float a, float &ho, float &lw) {
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
+    ho = __uint_as_float(hb);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - ho));
+    lw = __uint_as_float(lb);
+  };
+  split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
+  hi[i] = h; lo[i] = l;
+}
+
+// W [K, N] row-major -> (Wt_hi, Wt_lo) [N, K]: the K-major B operand of X @ W
+__global__ void __launch_bounds__(256) k_prep_weight_t(int K, int N, const float *__restrict__ W, float *__restrict__ thi, float *__restrict__ tlo) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + tx;
+    tile[r][tx] = (k < K && n < N) ? W[(size_t)k * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    if (n < N && k < K) {
+      const float a = tile[tx][r];
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
+      const float h = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - h));
+      thi[(size_t)n * K + k] = h; tlo[(size_t)n * K + k] = __uint_as_float(lb);
+    }
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// [rows, K] fp32 row-major, box = 128 rows x 32 columns (128 bytes), 128-byte swizzle, out-of-bounds reads give 0
+bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t K) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {K, rows};
+  const cuuint64_t strides[1] = {K * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" int dge_gemm_split_tf32(int64_t n, const float *x, float *hi, float *lo, void *stream) {
+  if (n < 0 || (n & 3) || !x || !hi || !lo) return -1;
+  if (n == 0) return 0;
+  const int64_t n4 = n / 4;
+  k_split_tf32<<<(unsigned)((n4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n4, reinterpret_cast<const float4 *>(x),
+                                                                                              reinterpret_cast<float4 *>(hi), reinterpret_cast<float4 *>(lo));
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int dge_gemm_prep_weight(int K, int N, const float *W, float *Wt_hi, float *Wt_lo, void *stream) {
+  if (K <= 0 || N <= 0 || !W || !Wt_hi || !Wt_lo) return -1;
+  k_prep_weight_t<<<dim3((N + 31) / 32, (K + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(K, N, W, Wt_hi, Wt_lo);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, const float *Bt_hi,
+                               const float *Bt_lo, float *C, int ldc, void *stream) {
+  if (M < 0 || N <= 0 || K <= 0 || (K & 3) || (ldc & 3) || ldc < N || !A_hi || !A_lo || !Bt_hi || !Bt_lo || !C) return -1;
+  if (((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)Bt_hi | (uintptr_t)Bt_lo | (uintptr_t)C) & 15) return -1;
+  if (M == 0) return 0;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if (!make_map(&mAh, A_hi, M, K) || !make_map(&mAl, A_lo, M, K) || !make_map(&mBh, Bt_hi, N, K) || !make_map(&mBl, Bt_lo, N, K)) return -2;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM) != cudaSuccess) return -2;
+    configured = true;
+  }
+  const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  k_gemm_tf32x3<<<grid, GEMM_THREADS, GEMM_SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

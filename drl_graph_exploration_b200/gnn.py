@@ -208,3 +208,113 @@ def gcn_conv_small_fused(x: torch.Tensor, weight: torch.Tensor, bias, gs: GraphS
 def weighted_aggregate(x: torch.Tensor, gs: GraphStructure):
     """GatedGraphConv.propagate: sum_j w_ji x_j (no self loops, no bias)."""
     return _AggregateFn.apply(x, None, gs, gs.weight, None, False)
+
+
+# ------------------------------------------------------------------ tensor-core GEMM (tcgen05, 3xTF32) ---
+_gemm_ready = False
+
+
+def _gemm_lib():
+    global _gemm_ready
+    L = _lib()
+    if not _gemm_ready:
+        L.dge_gemm_split_tf32.argtypes = [ctypes.c_int64, _vp, _vp, _vp, _vp]
+        L.dge_gemm_prep_weight.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]
+        L.dge_gemm_tf32x3.argtypes = [ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]
+        _gemm_ready = True
+    return L
+
+
+def tc_supported(K: int, N: int) -> bool:
+    return K % 4 == 0 and N % 4 == 0 and K >= 32
+
+
+def split_tf32(x: torch.Tensor):
+    """x -> (hi, lo) TF32 parts (dge_gemm_split_tf32)."""
+    global launch_count
+    L = _gemm_lib()
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = L.dge_gemm_split_tf32(x.numel(), _p(x), _p(hi), _p(lo), _st(x.device))
+    if rc:
+        raise DgeError(f"dge_gemm_split_tf32 failed ({rc})")
+    launch_count += 1
+    return hi, lo
+
+
+def _weight_operand(w: torch.Tensor, transposed: bool):
+    """(hi, lo) of the K-major B operand: ``transposed`` -> W^T [N,K] of W [K,N] (forward X @ W); else W itself as
+    [N', K'] (backward dY @ W^T).  Split once per weight update: the result is cached ON the parameter object (on
+    the base tensor for views such as ``weight[i]``), keyed by the autograd version counter."""
+    global launch_count
+    owner = w._base if w._base is not None else w
+    cache = getattr(owner, "_dge_tf32_split", None)
+    if cache is None:
+        cache = {}
+        try:
+            owner._dge_tf32_split = cache
+        except Exception:
+            pass
+    key = (w.storage_offset(), tuple(w.shape), tuple(w.stride()), transposed)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1], hit[2]
+    L = _gemm_lib()
+    wd = w.detach().contiguous()
+    if transposed:
+        K, N = wd.shape
+        hi, lo = torch.empty(N, K, dtype=torch.float32, device=w.device), torch.empty(N, K, dtype=torch.float32, device=w.device)
+        with torch.cuda.device(w.device):
+            rc = L.dge_gemm_prep_weight(K, N, _p(wd), _p(hi), _p(lo), _st(w.device))
+        if rc:
+            raise DgeError(f"dge_gemm_prep_weight failed ({rc})")
+        launch_count += 1
+    else:
+        hi, lo = split_tf32(wd)
+    cache[key] = (w._version, hi, lo)
+    return hi, lo
+
+
+def _tc_gemm(a: torch.Tensor, bt_hi: torch.Tensor, bt_lo: torch.Tensor, m_dev: Optional[torch.Tensor] = None):
+    """C [M,N] = a [M,K] @ Bt[N,K]^T on the tcgen05 kernel."""
+    global launch_count
+    _need_cuda(a, "tc_gemm")
+    L = _gemm_lib()
+    M, K = a.shape
+    N = bt_hi.shape[0]
+    ah, al = split_tf32(a)
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = L.dge_gemm_tf32x3(M, _p(m_dev), N, K, _p(ah), _p(al), _p(bt_hi), _p(bt_lo), _p(c), N, _st(a.device))
+    if rc:
+        raise DgeError(f"dge_gemm_tf32x3 failed ({rc})")
+    launch_count += 1
+    return c
+
+
+class _TcMatmulFn(torch.autograd.Function):
+    """x @ w with forward and grad-input on the tcgen05 3xTF32 kernel; grad-weight (x^T @ dy, both operands
+    MN-major) stays a library GEMM for now."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        hi, lo = _weight_operand(w, True)
+        return _tc_gemm(x.float(), hi, lo)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            hi, lo = _weight_operand(w, False)            # dY [M,N] @ W^T: Bt = W [K,N] as stored
+            gx = _tc_gemm(gy.contiguous().float(), hi, lo)
+        if ctx.needs_input_grad[1]:
+            gw = x.t() @ gy
+        return gx, gw
+
+
+def tc_matmul(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """x [M,K] @ w [K,N], fp32-quality on the 5th-gen tensor cores (csrc/dge_gemm.cu)."""
+    return _TcMatmulFn.apply(x, w)

@@ -146,6 +146,7 @@ class HostPolicyLoop:
         self.launches = 0
         self.graphs = 0
         self._frange = np.arange(eng.Lt + 1)
+        self.timing = None                              # optional dict: host seconds per section (dev profiling)
 
     def _next_actions(self):
         """Vectorised expansion of action `cursor` of every env's line plan (Planner2D.cpp:982-1038) into odom[B,3]."""
@@ -163,6 +164,16 @@ class HostPolicyLoop:
         np = self.np
         env, eng, L = self.env, self.env.eng, self._L
         B = env.B
+        tm = self.timing
+        if tm is not None:
+            import time
+            t_prev = [time.perf_counter()]
+
+            def lap(name):
+                t = time.perf_counter(); tm[name] = tm.get(name, 0.0) + t - t_prev[0]; t_prev[0] = t
+        else:
+            def lap(name):
+                pass
         main = torch.cuda.current_stream(self.dev)
         s1 = self.s_step if self.overlap else main
         nact = self.plans[:, 5].astype(np.int64)
@@ -184,12 +195,14 @@ class HostPolicyLoop:
         n_stepped = int(has_act.sum())
         self.cursor[has_act] += 1
         self.phase[in_reset] -= 1
+        lap("step: host prep + async launches")
         # ---- policy pipeline (main stream, host in the loop) ----------------------------------------------------
         if need.any():
             mp = ctypes.c_void_p(main.cuda_stream)
             self.need[:] = need
             _check(L.dge_graph_host(eng._h, self.t_need.data_ptr(), ctypes.byref(env.graph.c), ctypes.byref(self._ho), mp), "dge_graph_host")
             ng, n, e = (int(v) for v in self.t_tot[:3])
+            lap("policy: dge_graph_host (2 syncs)")
             self.launches += 4
             self.h2d += B
             self.d2h += 32 + n * 20 + e * 20 + (2 * ng + 2) * 4 + 2 * ng * 4 + self.t_fxy.nbytes
@@ -202,9 +215,12 @@ class HostPolicyLoop:
                 ea = self.t_ea[:e].to(self.dev, non_blocking=True)
                 self.h2d += n * 20 + e * 20
                 l0 = gnn.launch_count
+                lap("policy: H2D graph")
                 q = self.model(Data(x, ei, ea), 0.0).view(-1)
+                lap("policy: model launches")
                 self.t_q[:n].copy_(q, non_blocking=True)
                 main.synchronize()
+                lap("policy: Q D2H (sync)")
                 self.launches += gnn.launch_count - l0
                 self.d2h += n * 4
                 # arg-max over the last fro_size nodes of every graph (test.py:112), vectorised with a padded gather
@@ -220,7 +236,9 @@ class HostPolicyLoop:
                 if nofro.size:                    # no frontier left (q15): episode over -- mask value 2 sets the done flag
                     self.need[nofro] = 2
                     self.phase[nofro] = 5
+                lap("policy: host arg-max")
                 _check(L.dge_line_plan_host(eng._h, self.t_goal.data_ptr(), self.t_need.data_ptr(), self.t_plan.data_ptr(), mp), "dge_line_plan_host")
+                lap("policy: dge_line_plan_host (sync)")
                 self.launches += 1
                 self.h2d += self.t_goal.nbytes + B
                 self.d2h += self.t_plan.nbytes
@@ -230,6 +248,7 @@ class HostPolicyLoop:
                 self.graphs += ng
         # ---- join: the step's host buffers are valid after this ---------------------------------------------------
         s1.synchronize()
+        lap("join: wait for the step stream")
         done = self.done.astype(bool)
         if done.any():
             self.phase[done] = 5          # initial optimize + 4 forced steps, executed by the next 5 ticks

@@ -40,6 +40,19 @@ int dge_gnn_aggregate(int N, int C, const float *X, const int32_t *rowptr, const
 int dge_gcn_conv_small(int N, int Cin, int C, const float *X, const int32_t *rowptr, const int32_t *perm, const int64_t *nbr,
                        const float *coef, const float *selfcoef, const float *W, const float *bias, int relu, float *out, void *stream);
 
+/* ---- dense node-MLP GEMM on the tcgen05 tensor cores (csrc/dge_gemm.cu): replaces the cuBLAS SGEMM behind
+ * GCNConv's `torch.matmul(x, self.weight)` (Networks.py:22-24 via PyG), GatedGraphConv's `h @ W[i]` and the GRUCell
+ * transforms (Networks.py:76-82).  C[M,N] = A[M,K] * Bt[N,K]^T in 3xTF32 (fp32-quality: ~1e-6 relative), fp32
+ * accumulation in tensor memory.  Operands are pre-split into (hi, lo) TF32 parts:
+ *   dge_gemm_split_tf32   x[n] -> hi[n], lo[n]                    (n % 4 == 0; activations, or a weight used as Bt as is)
+ *   dge_gemm_prep_weight  W[K,N] row-major -> Wt_hi, Wt_lo [N,K]   (the Bt operand of X @ W)
+ *   dge_gemm_tf32x3       K % 4 == 0, ldc % 4 == 0, 16-byte aligned pointers; M_dev nullable: live row count read on
+ *                         the device (<= M), so a batch sized on the device needs no host sync; rows >= *M_dev untouched. */
+int dge_gemm_split_tf32(int64_t n, const float *x, float *hi, float *lo, void *stream);
+int dge_gemm_prep_weight(int K, int N, const float *W, float *Wt_hi, float *Wt_lo, void *stream);
+int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, const float *Bt_hi,
+                    const float *Bt_lo, float *C, int ldc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
