@@ -253,6 +253,12 @@ extern "C" int dge_graph_host(dge_handle h, const uint8_t *mask_host, const dge_
   d2h(host->key_size, dev->key_size, G * sizeof(int32_t));
   d2h(host->fro_size, dev->fro_size, G * sizeof(int32_t));
   d2h(host->frontier_xy, dev->frontier_xy, B * (size_t)h->d.Fmax * 2 * sizeof(double));
+  if (host->csr_rowptr && host->csr_perm && host->gcn_norm && host->gcn_selfnorm && dev->csr_rowptr) {
+    d2h(host->csr_rowptr, dev->csr_rowptr, (N + 1) * sizeof(int32_t));
+    d2h(host->csr_perm, dev->csr_perm, E * sizeof(int32_t));
+    d2h(host->gcn_norm, dev->gcn_norm, E * sizeof(float));
+    d2h(host->gcn_selfnorm, dev->gcn_selfnorm, N * sizeof(float));
+  }
   if (!ok) return fail(DGE_ECUDA, "dge_graph_host: D2H graph");
   if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host: sync");
   return DGE_OK;

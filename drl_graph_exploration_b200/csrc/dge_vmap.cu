@@ -29,6 +29,7 @@ struct VmapCfg {
   double map_min_x, map_min_y, res;
   double max_range, min_range, max_bearing, min_bearing;
   double rb, rr;                   // sigma_b^2, sigma_r^2
+  double max_r2_lo, max_r2_hi, min_r2_lo, min_r2_hi;   // guard bands around max_range^2 / min_range^2 (see k_vmap_cells)
   double i0;                       // 1/sigma0^2
   double ptab[6];                  // probability for n_seen = 0..4(+) and for a landmark cell (host-evaluated, q8)
   double wedge_tan;                // tan of the half-width of the rear blind wedge (with guard)
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(128) k_vmap_prep(VmapCfg c, int Tstride, const
 }
 
 // ----------------------------------------------------------------- cells ---
-__global__ void __launch_bounds__(TILE * TILE) k_vmap_cells(VmapCfg c, int Tstride, const int32_t *n_poses, int Tfixed,
+__global__ void __launch_bounds__(TILE * TILE, 3) k_vmap_cells(VmapCfg c, int Tstride, const int32_t *n_poses, int Tfixed,
                                                             const double *prep, const double *cbox, int nchunk_max,
                                                             const double *lm /*[n,Lstride,2]*/, const uint8_t *lm_obs /*nullable*/,
                                                             int Lstride, int Lfixed, double *prob /*[n,V]*/, double *vinfo /*[n,V,3]*/,
@@ -146,14 +147,19 @@ __global__ void __launch_bounds__(TILE * TILE) k_vmap_cells(VmapCfg c, int Tstri
         near_any |= valid_cell && (kb + u < kc) && d2s[u] < rmax_c2;
       }
       if (!__any_sync(0xffffffffu, near_any)) continue;
-      double nxx[VU], nxy[VU], nyy[VU];
+      double nxx[VU], nxy[VU], nyy[VU], ndet[VU];
       bool vis[VU], upd[VU];
 #pragma unroll
       for (int u = 0; u < VU; ++u) {
         const double *p = sp + min(kb + u, kc - 1) * PREP_W;
         const double dx = dxs[u], dy = dys[u], d2 = d2s[u];
-        const double r = __dsqrt_rn(d2);
-        const bool inr = valid_cell && (kb + u < kc) && d2 < rmax_c2 && r < c.max_range;          // Distance.cpp:86 / checkWithoutMinRange
+        // range gates  r < max_range (Distance.cpp:86 / checkWithoutMinRange)  and  r > min_range (full check, q10) with
+        // r = sqrt(d2): decided on d2 alone outside a relative 1e-9 band around the squared limits, by the reference's
+        // own sqrt comparison inside it -- same integer visibility counts, no sqrt on the common path
+        bool in_max, out_min;
+        if (d2 < c.max_r2_lo) in_max = true; else if (d2 > c.max_r2_hi) in_max = false; else in_max = __dsqrt_rn(d2) < c.max_range;
+        if (d2 > c.min_r2_hi) out_min = true; else if (d2 < c.min_r2_lo) out_min = false; else out_min = __dsqrt_rn(d2) > c.min_range;
+        const bool inr = valid_cell && (kb + u < kc) && in_max;
         const double co = p[2], si = p[3];
         const double qx = co * dx + si * dy, qy = -si * dx + co * dy;
         // field-of-view gate min_b < atan2(qy,qx) < max_b  (Simulator2D.cpp:100-111)
@@ -162,21 +168,24 @@ __global__ void __launch_bounds__(TILE * TILE) k_vmap_cells(VmapCfg c, int Tstri
         else if (inr) { const double bb = atan2(qy, qx); in_fov = bb < c.max_bearing && bb > c.min_bearing; }
         else in_fov = false;
         vis[u] = inr && in_fov;                                                     // occupancy visibility count (q8)
-        upd[u] = vis[u] && r > c.min_range && p[10] != 0.0;                         // full check (q10) ; det(info) gate
-        // body-frame covariance of the predicted virtual landmark
-        const double r2 = r * r;
-        const double sr = c.rr / r2;
+        upd[u] = vis[u] && out_min && p[10] != 0.0;                                 // full check (q10) ; det(info) gate
+        // body-frame covariance of the predicted virtual landmark: cb = P + (rr / r^2) [qx qx, qx qy; qx qy, qy qy], with
+        // P the bearing-noise + pose-covariance part.  Its inverse (the body-frame information) needs ONE division:
+        //   det(cb) r^2 = det(P) r^2 + rr Q,  Q = P00 qy^2 - 2 P01 qx qy + P11 qx^2,   adj(cb) r^2 = adj(P) r^2 + rr [qy qy, -qx qy; ., qx qx]
         const double Sxx = p[4], Sxy = p[5], Sxt = p[6], Syy = p[7], Syt = p[8], Stt = p[9];
-        const double cb00 = qy * qy * c.rb + qx * qx * sr + Sxx - 2.0 * qy * Sxt + qy * qy * Stt;
-        const double cb01 = qx * qy * (sr - c.rb) + Sxy - qy * Syt + qx * Sxt - qx * qy * Stt;
-        const double cb11 = qx * qx * c.rb + qy * qy * sr + Syy + 2.0 * qx * Syt + qx * qx * Stt;
-        const double idet = 1.0 / (cb00 * cb11 - cb01 * cb01);
-        const double lb00 = cb11 * idet, lb01 = -cb01 * idet, lb11 = cb00 * idet;   // body-frame information
+        const double qxx = qx * qx, qyy = qy * qy, qxy = qx * qy;
+        const double P00 = qyy * (c.rb + Stt) + Sxx - 2.0 * qy * Sxt;
+        const double P01 = Sxy - qy * Syt + qx * Sxt - qxy * (c.rb + Stt);
+        const double P11 = qxx * (c.rb + Stt) + Syy + 2.0 * qx * Syt;
+        const double Q = P00 * qyy - 2.0 * P01 * qxy + P11 * qxx;
+        const double inv = 1.0 / ((P00 * P11 - P01 * P01) * d2 + c.rr * Q);
+        const double lb00 = (P11 * d2 + c.rr * qyy) * inv, lb01 = -(P01 * d2 + c.rr * qxy) * inv, lb11 = (P00 * d2 + c.rr * qxx) * inv;
         // rotate to the map frame
         const double cc = co * co, ss = si * si, cs = co * si;
         nxx[u] = cc * lb00 - 2.0 * cs * lb01 + ss * lb11;
         nxy[u] = cs * (lb00 - lb11) + (cc - ss) * lb01;
         nyy[u] = ss * lb00 + 2.0 * cs * lb01 + cc * lb11;
+        ndet[u] = d2 * inv;                                                          // det of the new information = 1 / det(cb)
       }
 #pragma unroll
       for (int u = 0; u < VU; ++u) {
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(TILE * TILE) k_vmap_cells(VmapCfg c, int Tstri
         if (!upd[u]) continue;
         if (!updated) { ixx = nxx[u]; ixy = nxy[u]; iyy = nyy[u]; updated = true; }
         else {  // covariance intersection on information matrices (VirtualMap.cpp:364-377, q11)
-          const double a = ixx * iyy - ixy * ixy, bdet = nxx[u] * nyy[u] - nxy[u] * nxy[u];
+          const double a = ixx * iyy - ixy * ixy, bdet = ndet[u];
           const double cm = iyy * nxx[u] - 2.0 * ixy * nxy[u] + ixx * nyy[u];   // det(m1) * tr(m1^-1 m2)
           const double d = a + bdet - cm;
           double w = 0.5 * (2.0 * bdet - cm) / d;
@@ -255,6 +264,8 @@ VmapCfg make_cfg(const dge_config &g, int rows, int cols) {
   c.map_min_x = g.map_min_x; c.map_min_y = g.map_min_y; c.res = g.resolution;
   c.max_range = g.max_range; c.min_range = g.min_range; c.max_bearing = g.max_bearing; c.min_bearing = g.min_bearing;
   c.rb = g.bearing_noise * g.bearing_noise; c.rr = g.range_noise * g.range_noise;
+  c.max_r2_lo = g.max_range * g.max_range * (1.0 - 1e-9); c.max_r2_hi = g.max_range * g.max_range * (1.0 + 1e-9);
+  c.min_r2_lo = g.min_range * g.min_range * (1.0 - 1e-9); c.min_r2_hi = g.min_range * g.min_range * (1.0 + 1e-9);
   c.i0 = 1.0 / (g.sigma0 * g.sigma0);
   // OccupancyMap.h:10-19 evaluated on the host with libm, by repeated addition + clamping exactly
   // like OccupancyMap.cpp:55-62 (incl. MAX_LOGODDS = LOGODDS2PROB(0.95), q7)

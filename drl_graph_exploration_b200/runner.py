@@ -129,10 +129,14 @@ class HostPolicyLoop:
         self.t_fxy, self.t_tot = pin((B, eng.Lt + 1, 2), f64), pin((8,), i32)
         self.t_goal, self.t_plan = pin((B, 2), f64), pin((B, 6), f64)
         self.t_q = pin((g.node_cap,), f32)
+        self.t_rowptr, self.t_perm = pin((g.node_cap + 1,), i32), pin((g.edge_cap,), i32)
+        self.t_norm, self.t_selfnorm = pin((g.edge_cap,), f32), pin((g.node_cap,), f32)
 
         class _HostOut(ctypes.Structure):
-            _fields_ = [(n, vp) for n in ("x", "edge_index", "edge_attr", "node_ptr", "edge_ptr", "key_size", "fro_size", "frontier_xy", "totals")]
-        self._ho = _HostOut(*(t.data_ptr() for t in (self.t_x, self.t_ei, self.t_ea, self.t_nptr, self.t_eptr, self.t_ks, self.t_fs, self.t_fxy, self.t_tot)))
+            _fields_ = [(n, vp) for n in ("x", "edge_index", "edge_attr", "node_ptr", "edge_ptr", "key_size", "fro_size", "frontier_xy", "totals",
+                                          "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm")]
+        self._ho = _HostOut(*(t.data_ptr() for t in (self.t_x, self.t_ei, self.t_ea, self.t_nptr, self.t_eptr, self.t_ks, self.t_fs, self.t_fxy, self.t_tot,
+                                                     self.t_rowptr, self.t_perm, self.t_norm, self.t_selfnorm)))
         for name in ("odom", "mask", "done", "metrics", "need", "nptr", "ks", "fs", "fxy", "goal", "plan", "q"):
             setattr(self, name, getattr(self, "t_" + name).numpy())
         # host-side action lists in the compact form of dge_line_plan: (n_rot_pi, sign, rot_rem, n_fwd, fwd_rem, n_actions)
@@ -205,18 +209,21 @@ class HostPolicyLoop:
             lap("policy: dge_graph_host (2 syncs)")
             self.launches += 4
             self.h2d += B
-            self.d2h += 32 + n * 20 + e * 20 + (2 * ng + 2) * 4 + 2 * ng * 4 + self.t_fxy.nbytes
+            self.d2h += 32 + n * 20 + e * 20 + (2 * ng + 2) * 4 + 2 * ng * 4 + self.t_fxy.nbytes + (n + 1) * 4 + e * 8 + n * 4
             if ng > 0:
                 from . import gnn
                 from .data import Data
                 # the policy gets the HOST graph batch, like DeepQ.test: data.to(device) -> model -> Q back on the host
-                x = self.t_x[:n].to(self.dev, non_blocking=True)
-                ei = self.t_ei[:2 * e].view(2, e).to(self.dev, non_blocking=True)
-                ea = self.t_ea[:e].to(self.dev, non_blocking=True)
-                self.h2d += n * 20 + e * 20
+                up = lambda t: t.to(self.dev, non_blocking=True)
+                x, ei, ea = up(self.t_x[:n]), up(self.t_ei[:2 * e].view(2, e)), up(self.t_ea[:e])
+                data = Data(x, ei, ea)
+                # the batch's CSR + GCN normalisation travelled with it (dge_graph_host_out): adopt instead of rebuilding
+                data._dge_structure = gnn.GraphStructure.from_csr(ei, ea, n, up(self.t_rowptr[:n + 1]), up(self.t_perm[:max(e, 1)]),
+                                                                  up(self.t_norm[:max(e, 1)]), up(self.t_selfnorm[:n]))
+                self.h2d += n * 20 + e * 20 + (n + 1) * 4 + e * 8 + n * 4
                 l0 = gnn.launch_count
                 lap("policy: H2D graph")
-                q = self.model(Data(x, ei, ea), 0.0).view(-1)
+                q = self.model(data, 0.0).view(-1)
                 lap("policy: model launches")
                 self.t_q[:n].copy_(q, non_blocking=True)
                 main.synchronize()

@@ -217,6 +217,11 @@ typedef struct dge_graph_host_out {
   int32_t *node_ptr, *edge_ptr, *key_size, *fro_size;
   double *frontier_xy;
   int32_t *totals;
+  /* optional (all four or none, and only if `dev` carries them): the destination-sorted CSR and the GCNConv(improved)
+   * normalisation of the batch -- csr_rowptr [N+1], csr_perm [E], gcn_norm [E], gcn_selfnorm [N] -- so that a caller
+   * who sends the batch back to the device does not have to rebuild them (PyG recomputes them in every GCNConv.forward) */
+  int32_t *csr_rowptr, *csr_perm;
+  float *gcn_norm, *gcn_selfnorm;
 } dge_graph_host_out;
 int dge_graph_host(dge_handle h, const uint8_t *mask_host, const dge_graph_out *dev, const dge_graph_host_out *host, void *stream);
 

@@ -65,9 +65,10 @@ def test_matmul_autograd_and_gcn_forward_parity():
     y.backward(gy)
     xr, wr = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
     (xr @ wr).backward(gy.double())
-    assert torch.allclose(y.double(), (xr @ wr).detach(), rtol=1e-5, atol=1e-5)
-    assert torch.allclose(x.grad.double(), xr.grad, rtol=1e-5, atol=1e-5)
-    assert torch.allclose(w.grad.double(), wr.grad, rtol=1e-4, atol=1e-4)
+    # element-wise error of the 3xTF32 product is ~1e-6 of sum|a||w| (~21 here): 1e-4 absolute on O(1) values
+    assert torch.allclose(y.double(), (xr @ wr).detach(), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(x.grad.double(), xr.grad, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(w.grad.double(), wr.grad, rtol=1e-4, atol=1e-3)
     # GCN Q-values: tensor-core path vs library fp32 path, 1e-4 relative (the contract), observed ~1e-6
     n = 300
     ei = torch.randint(0, n, (2, 900), device="cuda")
