@@ -20,19 +20,30 @@ import torch.nn.functional as F
 
 from . import gnn
 
-_PRECISION = "tc3"
+_PRECISION = "tc3"        # inference (autograd off)
+_PRECISION_TRAIN = "fp32"  # under autograd
 
 
-def set_matmul_precision(mode: str):
-    """Dense node-MLP GEMMs: 'tc3' (default) = hand-written tcgen05 kernel, 3xTF32 split, fp32-quality (1e-4 on
-    Q-values holds with ~100x margin); 'fp32' = library SGEMM (A/B reference); 'tf32' / 'bf16' = library
-    single-pass tensor-core modes (do not meet the parity tolerance)."""
-    global _PRECISION
-    assert mode in ("tc3", "fp32", "tf32", "bf16")
+def set_matmul_precision(mode: str, train: str | None = None):
+    """Dense node-MLP GEMMs.  ``mode`` (inference, autograd off): 'tc3' (default) = hand-written tcgen05 kernel, 3xTF32
+    split, fp32 accumulation in tensor memory -- ~1e-6 of sum|a||w| per product, Q-values within ~1e-5 of fp64 (contract
+    1e-4); 'fp32' = library SGEMM (A/B reference); 'tf32' / 'bf16' = library single-pass tensor-core modes (do not meet
+    the contract).  ``train`` (under autograd; default 'fp32'): 'tc3' runs forward and grad-input on the tcgen05 kernel
+    too (3.5x faster); it is opt-in because the ~1e-6 product error shows up as ~1e-3 of the largest gradient entry
+    after the cancellation in the weight-gradient sums, above the 2e-4 gradient parity the tests hold for fp32."""
+    global _PRECISION, _PRECISION_TRAIN
+    assert mode in ("tc3", "fp32", "tf32", "bf16") and train in (None, "tc3", "fp32", "tf32", "bf16")
     _PRECISION = mode
+    if train is not None:
+        _PRECISION_TRAIN = train
 
 
 def _mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    mode = _PRECISION_TRAIN if torch.is_grad_enabled() and (a.requires_grad or b.requires_grad) else _PRECISION
+    return _mm_mode(a, b, mode)
+
+
+def _mm_mode(a: torch.Tensor, b: torch.Tensor, _PRECISION: str) -> torch.Tensor:
     if _PRECISION == "tc3" and a.is_cuda and a.dim() == 2 and b.dim() == 2 and gnn.tc_supported(a.shape[1], b.shape[1]):
         return gnn.tc_matmul(a, b)
     if _PRECISION == "bf16":

@@ -32,7 +32,7 @@ cub = "/tmp/_ncu_sum_cub"; os.makedirs(cub, exist_ok=True)
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "drl_graph_exploration_b200", "libdge.so")], cwd=cub, capture_output=True)
 base = os.path.basename(cu).replace(".cu", "")
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(cub, base + ".sm_100a.cubin")], capture_output=True, text=True).stdout
-kname = rows[2][h.index("Kernel Name")].split("(")[0].split("::")[-1]
+kname = rows[2][h.index("Kernel Name")].split("(")[0].split("::")[-1].split("<")[0]
 addr2line, cur, infn = {}, None, False
 for l in dis.split("\n"):
     if ".text." in l and l.strip().startswith(".section"):
