@@ -34,6 +34,12 @@ MAP_SIZE, N_LANDMARKS, ENVS_PER_GPU, MAX_POSES = 20, 30, 256, 192
 WORKLOAD = f"{ENVS_PER_GPU} envs/GPU, {MAP_SIZE}x{MAP_SIZE} map, {N_LANDMARKS} landmarks, GCN policy inference (BASELINE configs[1])"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel in this workload, from the committed
+# `ncu --set full` captures (a number measured under the profiler is evidence for traffic, never a timing)
+NCU_TRAFFIC = {"slam": {"bytes": 6.6368e6 + 0.2383e6, "source": "profiles/r01_k_slam_v3_ncu.md"},
+               "vmap": {"bytes": None, "source": "profiles/ (k_vmap_env capture at this workload pending)"}}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -42,23 +48,44 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / power / throttle reasons DURING the timed region: NVML every 10 ms (nvidia-smi every 200 ms if NVML
+    is unavailable).  Reported: median SM clock under load, max SM clock, active slowdown reasons."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.h
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") else n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flags = []
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            flags.append("Active" if r & bit else "Not Active")
+        return [str(sm), str(mx), "0", flags[0], flags[3], flags[2], flags[1]]
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.01 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
@@ -71,7 +98,7 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 class L2Flush:
@@ -230,7 +257,8 @@ def main():
         dom = "slam" if ms_slam >= ms_vmap else "vmap"
         ach = (bytes_slam / (ms_slam * 1e-3) if dom == "slam" else bytes_vmap / (ms_vmap * 1e-3)) / 1e9
         roof = {"bound": "hbm", "kernel": "k_slam" if dom == "slam" else "k_vmap_prep+k_vmap_cells+k_vmap_metrics", "achieved": ach,
-                "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC[dom]["bytes"],
+                "traffic_source": NCU_TRAFFIC[dom]["source"],
                 "ms_per_launch": {"slam": ms_slam, "vmap": ms_vmap}, "mean_poses": T_mean, "mean_measurements": M_mean,
                 "vmap": {"achieved": bytes_vmap / (ms_vmap * 1e-3) / 1e9, "frac": bytes_vmap / (ms_vmap * 1e-3) / 1e9 / pk["hbm_gbs"]},
                 "slam": {"achieved": bytes_slam / (ms_slam * 1e-3) / 1e9, "frac": bytes_slam / (ms_slam * 1e-3) / 1e9 / pk["hbm_gbs"]}}
@@ -240,21 +268,30 @@ def main():
                                                "policy": "GCN fp32, random init", "parallelism": f"env-sharded x{world}, no data-path collective",
                                                "l2": L2Flush.HOW if flush is not None else "not flushed"},
                "gnn_graphs_per_s": graphs_all / (total_ms / 1e3), "gpu_launches": loop.launches, "clocks": clocks, "roofline": roof}
-    # e2e + cpu baseline on rank 0 at N = 1 only
-    if rank == 0 and world == 1 and not args.no_e2e:
+    # e2e: every rank drives its own envs through the host-buffer API; whole-job steps / max wall time over ranks
+    if not args.no_e2e:
         loop.env.reset()                      # fresh episodes: the host loop owns the action lists from here on
         hl = e2e_loop(loop, overlap=not args.no_overlap)
         n_e2e = max(20, args.steps)
         for _ in range(max(args.warmup, 12)):   # past the first decision and a few restarts
             hl.tick()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         s0, h0, d0, t0 = hl.steps, hl.h2d, hl.d2h, time.perf_counter()
         for _ in range(n_e2e):
             hl.tick()
-        torch.cuda.synchronize(); dt = time.perf_counter() - t0
-        out["e2e"] = {"value": (hl.steps - s0) / dt, "unit": "env-steps/s", "h2d_bytes_per_step": (hl.h2d - h0) / n_e2e,
-                      "d2h_bytes_per_step": (hl.d2h - d0) / n_e2e, "ticks": n_e2e, "ms_per_tick": 1e3 * dt / n_e2e,
-                      "api": "HostPolicyLoop: dge_step_host_async + dge_graph_host + dge_line_plan_host (pinned host buffers)"}
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        es = torch.tensor([hl.steps - s0, hl.h2d - h0, hl.d2h - d0], dtype=torch.float64, device=loop.dev)
+        et = torch.tensor([dt], dtype=torch.float64, device=loop.dev)
+        if world > 1:
+            dist.all_reduce(es, op=dist.ReduceOp.SUM); dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            dt = float(et.item())
+            out["e2e"] = {"value": float(es[0].item()) / dt, "unit": "env-steps/s", "h2d_bytes_per_step": float(es[1].item()) / n_e2e,
+                          "d2h_bytes_per_step": float(es[2].item()) / n_e2e, "ticks": n_e2e, "ms_per_tick": 1e3 * dt / n_e2e,
+                          "api": "HostPolicyLoop: dge_step_host_async + dge_graph_host + dge_line_plan_host (pinned host buffers), wall clock, max over ranks"}
     elif rank == 0:
         out["e2e"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
