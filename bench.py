@@ -256,7 +256,7 @@ def main():
         bytes_slam = 2 * (72 * T_mean + 16 * M_mean + 32 * eng.Lt) * envs_per_launch
         dom = "slam" if ms_slam >= ms_vmap else "vmap"
         ach = (bytes_slam / (ms_slam * 1e-3) if dom == "slam" else bytes_vmap / (ms_vmap * 1e-3)) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_slam" if dom == "slam" else "k_vmap_prep+k_vmap_cells+k_vmap_metrics", "achieved": ach,
+        roof = {"bound": "hbm", "kernel": "k_slam" if dom == "slam" else "k_vmap_env", "achieved": ach,
                 "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC[dom]["bytes"],
                 "traffic_source": NCU_TRAFFIC[dom]["source"],
                 "ms_per_launch": {"slam": ms_slam, "vmap": ms_vmap}, "mean_poses": T_mean, "mean_measurements": M_mean,
