@@ -145,6 +145,186 @@ def run_reference(args):
                       "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+
+# ---------------------------------------------------------------- extra workloads ---
+def _dist_setup():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def run_train(args):
+    """BASELINE configs[2] (C3): 256 envs per GPU, 40x40 map, DQN training with batched roll-out rewards, device replay and
+    one NCCL all-reduce of the flat gradient bucket per gradient step.  A step = one tick of trainer.VecDQNTrainer."""
+    from drl_graph_exploration_b200 import Networks
+    from drl_graph_exploration_b200.config import EnvConfig
+    from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv
+    from drl_graph_exploration_b200.trainer import VecDQNTrainer
+    rank, world, local, dist = _dist_setup()
+    ms, B = 40, ENVS_PER_GPU
+    cfg = EnvConfig(map_size=ms)
+    if args.train_gemm != "fp32":
+        Networks.set_matmul_precision("tc3", train=args.train_gemm)
+    env = VecExplorationEnv(B, cfg=cfg, max_poses=384, device=local, seed0=rank * 100000)
+    env.reset()
+    torch.manual_seed(0)                      # identical replicas on every rank
+    pol, tgt = Networks.GCN().to(env.device), Networks.GCN().to(env.device)
+    tr = VecDQNTrainer(env, pol, tgt, observe=0, train_steps_per_tick=args.train_steps_per_tick, seed=rank)
+    for _ in range(40):                       # prefill the replay (untimed): every rank needs one minibatch of transitions
+        tr.tick(learn=False)
+    assert tr.replay.size >= tr.dqn.BATCH, "prefill too short"
+    for _ in range(args.warmup):
+        tr.tick(learn=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    c0 = [int(v) for v in env.eng.state["counters"].tolist()[:3]]
+    d0, t0, r0, k0 = tr.decisions, tr.train_steps, tr.rollout_steps, tr.rollout_clones
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        tr.tick(learn=True)
+    b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = a.elapsed_time(b)
+    c1 = [int(v) for v in env.eng.state["counters"].tolist()[:3]]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=env.device)
+    v = torch.tensor([c1[0] - c0[0], tr.decisions - d0, tr.train_steps - t0, tr.rollout_steps - r0, tr.rollout_clones - k0], dtype=torch.float64, device=env.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        sec = float(t.item()) / 1e3
+        steps, dec, tsteps, rsteps, clones = (float(x) for x in v.tolist())
+        bsz = tr.dqn.BATCH
+        out = {"metric": "env-steps/sec (DQN training)", "value": steps / sec, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 simulator / f32 GNN",
+               "data": "synthetic",
+               "config": {"workload": f"{B} envs/GPU, {ms}x{ms} map, {cfg.n_landmarks} landmarks, DQN+GCN training (BASELINE configs[2])", "batch_graphs_per_rank": bsz,
+                          "train_steps_per_tick": args.train_steps_per_tick, "train_gemm": args.train_gemm, "replay": f"device ring, {tr.replay.capacity} transitions, {tr.replay.nbytes() / 2**30:.2f} GiB",
+                          "collective": "one all-reduce of the 4.0 MB flat gradient bucket per gradient step" if world > 1 else "none (1 rank)"},
+               "decisions_per_s": dec / sec, "train_steps_per_s": tsteps / sec / world, "rollout_clone_steps_per_s": None,
+               "gnn_samples_per_s": {"forward_acting": dec / sec, "forward_target": tsteps * bsz / sec, "forward_backward": tsteps * bsz / sec},
+               "rollout": {"clones_per_s": clones / sec, "clone_engine_ticks_per_s": rsteps / sec}, "loss": tr.last_loss, "epsilon": tr.epsilon, "clocks": clocks}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def synth_graph_batch(n_graphs, sizes, rng, device, n_landmarks=8):
+    """C5 topology: per graph a pose chain, every pose observing Poisson(1.5) of the L landmarks, F <= L+1
+    frontier stubs; x ~ N(0,1), edge_attr ~ U(0.1, 6); both edge directions, PyG DataLoader layout."""
+    src, dst, wts, bat, off = [], [], [], [], 0
+    for g in range(n_graphs):
+        n = int(sizes[g])
+        L = min(n_landmarks, max(1, n // 4)); F = min(L + 1, max(1, n // 8)); T = max(1, n - L - F)
+        L = n - T - F
+        e = [(L + k, L + k + 1) for k in range(T - 1)]
+        for k in range(T):
+            if L > 0:
+                for l in rng.choice(L, size=min(L, int(rng.poisson(1.5))), replace=False):
+                    e.append((int(l), L + k))
+        for f in range(F):
+            e.append((int(rng.integers(0, L + T)), L + T + f))
+        e = np.array(sorted(set(e)), dtype=np.int64).reshape(-1, 2)
+        s_, d_ = np.concatenate([e[:, 0], e[:, 1]]), np.concatenate([e[:, 1], e[:, 0]])
+        wh = rng.uniform(0.1, 6.0, e.shape[0])
+        src.append(s_ + off); dst.append(d_ + off); wts.append(np.concatenate([wh, wh])); bat.append(np.full(n, g)); off += n
+    ei = torch.tensor(np.stack([np.concatenate(src), np.concatenate(dst)]), dtype=torch.long, device=device)
+    w = torch.tensor(np.concatenate(wts), dtype=torch.float32, device=device)
+    x = torch.tensor(rng.normal(size=(off, 5)), dtype=torch.float32, device=device)
+    return x, ei, w, torch.tensor(np.concatenate(bat), dtype=torch.long, device=device)
+
+
+def run_gnn(args):
+    """BASELINE configs[4] (C5): batches of 64 graphs with 8..512 nodes (mixed), GCN forward and forward+backward+Adam."""
+    from drl_graph_exploration_b200 import Networks, gnn
+    from drl_graph_exploration_b200.data import Data
+    rank, world, local, dist = _dist_setup()
+    dev = torch.device("cuda", local)
+    rng = np.random.default_rng(1234 + rank)
+    nb, G = 8, 64
+    batches = []
+    for _ in range(nb):
+        sizes = rng.choice(np.arange(8, 513, 8), size=G)
+        batches.append(synth_graph_batch(G, sizes, rng, dev))
+    torch.manual_seed(0)
+    model = Networks.GCN().to(dev)
+    if args.train_gemm != "fp32":
+        Networks.set_matmul_precision("tc3", train=args.train_gemm)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+    from drl_graph_exploration_b200.dist import FlatGradBucket
+    bucket = FlatGradBucket(model.parameters())
+    flush = None if args.no_flush_l2 else L2Flush(dev)
+    nodes = sum(b[0].size(0) for b in batches) / nb
+    edges = sum(b[1].size(1) for b in batches) / nb
+
+    def fwd(i):
+        x, ei, w, bt = batches[i % nb]
+        with torch.no_grad():
+            return model(Data(x, ei, w, bt), 0.0)
+
+    def fwd_bwd(i):
+        x, ei, w, bt = batches[i % nb]
+        bucket.zero_()
+        q = model(Data(x, ei, w, bt), 0.5, batch=bt)
+        loss = (q.view(-1) ** 2).sum() / G
+        loss.backward()
+        bucket.all_reduce_mean(); bucket.clamp_(0.5)
+        opt.step()
+
+    res = {}
+    for name, fn in (("forward", fwd), ("forward_backward", fwd_bwd)):
+        model.eval() if name == "forward" else model.train()
+        for i in range(max(args.warmup, 3)):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        evs, l0 = [], gnn.launch_count
+        for i in range(args.steps):
+            if flush is not None:
+                flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(i); b.record(); evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = (float(t.item()) / 1e3, gnn.launch_count - l0)
+    if rank == 0:
+        pk, pk_kind = peaks()
+        sec_f, sec_b = res["forward"][0], res["forward_backward"][0]
+        gemm_flops = 2.0 * nodes * 1000 * 1000                     # the one [N,1000]x[1000,1000] product of a forward pass
+        out = {"metric": "GNN samples/sec", "value": world * G * args.steps / sec_f, "unit": "graphs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1e3 * sec_f / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMM, fp32 accumulate)",
+               "data": "synthetic",
+               "config": {"workload": "64 graphs/batch, 8..512 nodes mixed, GCN (BASELINE configs[4])", "mean_nodes_per_batch": nodes, "mean_edges_per_batch": edges,
+                          "train_gemm": args.train_gemm, "l2": L2Flush.HOW if flush is not None else "not flushed"},
+               "forward": {"graphs_per_s": world * G * args.steps / sec_f, "nodes_per_s": world * nodes * args.steps / sec_f, "ms_per_batch": 1e3 * sec_f / args.steps,
+                           "fp32_equiv_tflops_whole_pass": (2.012e6 * nodes * args.steps / sec_f) / 1e12},
+               "forward_backward": {"graphs_per_s": world * G * args.steps / sec_b, "nodes_per_s": world * nodes * args.steps / sec_b, "ms_per_batch": 1e3 * sec_b / args.steps,
+                                    "fp32_equiv_tflops_whole_pass": (3 * 2.012e6 * nodes * args.steps / sec_b) / 1e12, "includes": "backward, gradient all-reduce, clamp, Adam"},
+               "gpu_launches": res["forward"][1] + res["forward_backward"][1],
+               "roofline": {"bound": "tensor", "kernel": "k_gemm_tf32x3 inside the forward pass", "achieved": gemm_flops * args.steps / sec_f / 1e12, "peak": pk.get("bf16_tflops"),
+                            "peak_kind": pk_kind, "unit": "TFLOP/s", "frac": gemm_flops * args.steps / sec_f / 1e12 / pk.get("bf16_tflops", 1.0),
+                            "note": "whole forward pass time in the denominator (GEMM + 2 aggregations + head), fp32-equivalent flops; the kernel alone: profiles/r01_k_gemm_tf32x3_ncu.md",
+                            "traffic": None}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------- GPU arm ---
 class GpuLoop:
     def __init__(self, device, seed0, overlap=True):
@@ -194,6 +374,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the step and policy pipelines on one stream (A/B of the overlap)")
+    ap.add_argument("--workload", default="policy", choices=["policy", "train", "gnn"],
+                    help="policy = BASELINE configs[1] (the headline line); train = configs[2] DQN training; gnn = configs[4] GNN fwd / fwd+bwd")
+    ap.add_argument("--train-steps-per-tick", type=int, default=1)
+    ap.add_argument("--train-gemm", default="fp32", choices=["fp32", "tc3"], help="node-MLP GEMM under autograd (Networks.set_matmul_precision)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -203,6 +387,10 @@ def main():
             run_reference(args)
         return
 
+    if args.workload == "train":
+        return run_train(args)
+    if args.workload == "gnn":
+        return run_gnn(args)
     import torch.distributed as dist
     if world > 1:
         torch.cuda.set_device(local)

@@ -190,11 +190,15 @@ class VecExplorationEnv:
         return out
 
     # ------------------------------------------------------------- roll-outs ---
-    def rollout_rewards(self, mask: Optional[torch.Tensor] = None, clone_slots: Optional[int] = None, noise: Optional[torch.Tensor] = None):
+    def rollout_rewards(self, mask: Optional[torch.Tensor] = None, clone_slots: Optional[int] = None, noise: Optional[torch.Tensor] = None,
+                        auto_steps: bool = False):
         """rewards_all_goals (exploration_env.py:145-162) for every env selected in the last
         ``build_graph(mask)``: one clone per (env, frontier) in a second engine, all clones stepped
         together through their line plans.  Returns (raw [B,Fmax], normalised [B,Fmax], loop_clo [B]).
-        ``noise`` [n_steps, clone_slots, 3+4*Lt] makes the roll-out noise explicit (parity tests)."""
+        ``noise`` [n_steps, clone_slots, 3+4*Lt] makes the roll-out noise explicit (parity tests).
+        ``auto_steps``: read the longest clone plan back (one host sync) and launch exactly that many clone steps instead of
+        the upper bound of a line plan (typically 4-10 instead of 3 + diagonal / max_edge_length).
+        The caller keeps sum(fro_size) of the selected envs <= clone_slots (``VecDQNTrainer`` chunks the decision round)."""
         eng = self.eng
         if getattr(self, "_roll", None) is None:
             slots = clone_slots or min(self.B * (eng.Lt + 1), max(4 * self.B, 512))
@@ -218,6 +222,9 @@ class VecExplorationEnv:
         n_steps = 3 + int(diag / self.cfg.max_edge_length)
         if noise is not None:
             n_steps = noise.shape[0]
+        elif auto_steps:
+            n_steps = min(n_steps, int(roll.state["plan"][:, 5].max().item()))
+        self.rollout_steps = n_steps
         for i in range(n_steps):
             _check(roll._L.dge_step_queued_noise(roll._h, _ptr(None if noise is None else noise[i].contiguous()), sp), "dge_step_queued_noise")
         _check(eng._L.dge_rollout_rewards(roll._h, eng._h, ctypes.byref(self.graph.c), _ptr(mask), _ptr(self._roll_raw), _ptr(self._roll_norm),
@@ -355,6 +362,17 @@ class ExplorationEnv:
         for i, vi in enumerate(self._frontier):
             all_actions[i + key_size] = self.line_plan(key_size, vi)
         return all_actions
+
+    def rewards_all_goals(self, all_actions=None):
+        """exploration_env.py:145-162: look-ahead reward of every frontier (roll-outs on cloned simulator / SLAM / virtual
+        map, batched on the clone engine), min-max normalised; 0 for the SLAM nodes; sets ``loop_clo``."""
+        key_size, fro_size = self.get_key_size(), len(self._frontier)
+        rewards = np.zeros(key_size + fro_size)
+        if fro_size > 0:
+            _, norm, clo = self._vec.rollout_rewards(clone_slots=self._vec.eng.Lt + 1, auto_steps=True)
+            rewards[key_size:] = norm[0, :fro_size].cpu().numpy()
+            self.loop_clo = bool(clo[0])
+        return rewards
 
     def is_nf(self, id):
         return self.nearest_frontier_point == id

@@ -8,8 +8,10 @@ Differences that are deliberate (B200-first), none of which change a result:
   that layout on the device and skip it.
 * targets are built with a segmented max on the device instead of a NumPy loop.
 * multi-GPU: one flat-bucket all-reduce of the gradients before the clamp (``dist.FlatGradBucket``).
-The environment-facing training loop (``running``) needs the roll-out rewards of SURVEY row a14, which
-are a round-2 item; ``running`` therefore takes the reward function as an argument.
+The environment-facing DQN loop for B envs per GPU (roll-out rewards, device replay) is ``trainer.VecDQNTrainer``;
+``DeepQ.running`` / ``A2C.running`` below are the reference's single-env loops on ``ExplorationEnv`` (B = 1 view).
+
+``A2C`` mirrors policy.py:262-497 (n-step advantage actor-critic on the Policy*/Value* heads of ``Networks``).
 """
 from __future__ import annotations
 
@@ -18,6 +20,7 @@ from collections import deque
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from .data import Batch, Data
 from .dist import FlatGradBucket
@@ -134,3 +137,140 @@ class DeepQ(object):
         self.buffer.append(transition)
         if len(self.buffer) > self.REPLAY_MEMORY:
             self.buffer.popleft()
+
+
+class A2C(object):
+    """policy.py:262-497: n-step advantage actor-critic.  Same hyper-parameters, ``data_process / policy_cost / value_cost /
+    entropy_loss / train / test`` and the same n-step batch construction (policy.py:361-393, ``nstep_batch``)."""
+
+    def __init__(self, case_path="A2C_GCN/"):
+        self.case_path = case_path
+        self.GAMMA = 0.99          # policy.py:279-285
+        self.EXPLORE = 1e6
+        self.epoch = 1e4
+        self.nstep = 40
+        self.ent_coef = 0.01
+        self.vf_coef = 0.25
+        self.max_grad_norm = 0.5
+        self.buffer = deque()
+        self.map_size = 40
+        self.step_t = 0
+        self.temp_loss = 0
+        self.entro = 0
+        self.total_reward = np.empty([0, 0])
+        self._bucket = None
+
+    # ------------------------------------------------------------------ data ---
+    def data_process(self, data, device):
+        """policy.py:428-450: the DQN conversion plus an all-zero ``batch`` vector on the device."""
+        state = DeepQ.data_process(self, data)
+        return state, torch.zeros(np.shape(data[0])[0], dtype=torch.long, device=device)
+
+    # ------------------------------------------------------------ objectives ---
+    def policy_cost(self, prob, advantages, action, mask):
+        """policy.py:452-460: -sum(log pi(a) * A) / nstep; ``prob`` holds the frontier nodes only (masked softmax)."""
+        adv = torch.masked_select(advantages.view(-1), mask)
+        act = torch.masked_select(action, mask)
+        return (-(prob.view(-1).log() * adv) * act).sum() / self.nstep
+
+    def value_cost(self, pred, target):
+        """policy.py:462-466"""
+        return F.mse_loss(pred.view(-1), target.view(-1))
+
+    def entropy_loss(self, prob):
+        """policy.py:468-472 (detached: it is reported and scaled into the loss value, it carries no gradient)."""
+        p = prob.view(-1).detach()
+        entro = -(p.log() * p).sum() / self.nstep
+        self.entro = entro.item()
+        return entro
+
+    def nstep_batch(self, last_value):
+        """policy.py:361-393 on ``self.buffer`` (items ``(s_t, a_t, r_t, s_t1, terminal, fro_size, value)``):
+        discounted returns bootstrapped from ``last_value``, one-hot actions, frontier masks and the advantage vector
+        (return - value at the chosen node, 0 elsewhere).  Returns (Batch, a, mask, returns, y_adv)."""
+        buf = list(self.buffer)
+        ret, returns = float(last_value), []
+        for d in reversed(buf):                                     # ret = r + gamma * ret * (1 - terminal)
+            ret = d[2] + self.GAMMA * ret * (1.0 - float(bool(d[4])))
+            returns.append(ret)
+        returns = returns[::-1]
+        a, mask, adv = [], [], []
+        for d, g in zip(buf, returns):
+            act = np.asarray(d[1], dtype=np.float64)
+            m = np.zeros(act.size); m[act.size - int(d[5]):] = 1
+            y = np.zeros(act.size); y[int(np.argmax(act))] = g - d[6]
+            a.append(act); mask.append(m); adv.append(y)
+        return Batch.from_data_list([d[0] for d in buf]), np.concatenate(a), np.concatenate(mask), np.asarray(returns), np.concatenate(adv)
+
+    def train(self, data, action, mask, dis_reward, y_adv, device, modelA, modelC, optimizer):
+        """policy.py:474-497; multi-GPU: one all-reduce of the joint actor+critic gradient bucket before the clamp."""
+        modelA.train(); modelC.train()
+        data = data.to(device)
+        mask = torch.as_tensor(np.asarray(mask), dtype=torch.bool, device=device) if not torch.is_tensor(mask) else mask.to(device).bool()
+        params = [p for p in list(modelA.parameters()) + list(modelC.parameters()) if p.requires_grad]
+        if self._bucket is None or self._bucket.params[0] is not params[0]:
+            self._bucket = FlatGradBucket(params)
+        self._bucket.zero_()
+        actor_out = modelA(data, mask, batch=data.batch) + 1e-35
+        critic_out = modelC(data, mask, batch=data.batch)
+        dt = actor_out.dtype
+        y_adv = torch.as_tensor(y_adv, device=device).to(dt)
+        dis_reward = torch.as_tensor(dis_reward, device=device).to(critic_out.dtype)
+        action = torch.as_tensor(action, device=device).to(dt)
+        loss = (self.policy_cost(actor_out, y_adv, action, mask) - self.entropy_loss(actor_out) * self.ent_coef
+                + self.value_cost(critic_out, dis_reward) * self.vf_coef)
+        self.temp_loss = loss.item()
+        loss.backward()
+        self._bucket.all_reduce_mean()
+        self._bucket.clamp_(self.max_grad_norm)
+        optimizer.step()
+        return self.temp_loss
+
+    @torch.no_grad()
+    def test(self, data, batch, mask, device, model):
+        """policy.py:499-504"""
+        model.eval()
+        mask = torch.as_tensor(np.asarray(mask), dtype=torch.bool, device=device) if not torch.is_tensor(mask) else mask.to(device).bool()
+        return model(data.to(device), mask, batch)
+
+    def running(self, actor, critic, env=None, test=False, epochs=None, device=None, log=None):
+        """policy.py:297-426 on ``ExplorationEnv`` (the B = 1 view of the CUDA engine): sample a frontier from the actor's
+        masked softmax, follow its line plan, and every ``nstep`` decisions take one actor-critic gradient step."""
+        from .envs.exploration_env import ExplorationEnv
+        env = env or ExplorationEnv(self.map_size, 0, test)
+        device = device or env._vec.device
+        optimizer = torch.optim.Adam(list(actor.parameters()) + list(critic.parameters()), lr=1e-5)
+        rng = np.random.default_rng()
+        for _ in range(int(self.epoch if epochs is None else epochs)):
+            self.step_t += 1
+            adjacency, features, _, fro_size = env.graph_matrix()
+            node_size = adjacency.shape[0]
+            key_size = node_size - fro_size
+            s_t, b_t = self.data_process([adjacency, features], device)
+            mask = np.zeros(node_size); mask[node_size - fro_size:] = 1
+            all_actions = env.actions_all_goals()
+            rewards = env.rewards_all_goals(all_actions)
+            pi = self.test(s_t, b_t, mask, device, actor).view(-1).double().cpu().numpy()
+            val = float(self.test(s_t, b_t, mask, device, critic).item())
+            action_index = key_size + int(rng.choice(fro_size, p=pi / pi.sum()))
+            a_t = np.zeros(node_size); a_t[action_index] = 1
+            r_t = float(rewards[action_index])
+            done = False
+            for act in all_actions[action_index]:
+                _, done, _ = env.step(act)
+            current_done = done or env.loop_clo
+            adjacency, features, _, fro_size1 = env.graph_matrix()
+            s_t1, b_t1 = self.data_process([adjacency, features], device)
+            m1 = np.zeros(adjacency.shape[0]); m1[adjacency.shape[0] - fro_size1:] = 1
+            last_value = float(self.test(s_t1, b_t1, m1, device, critic).item())
+            self.buffer.append((s_t, a_t, r_t, s_t1, current_done, fro_size, val))
+            if len(self.buffer) == self.nstep:
+                batch, a, mk, returns, adv = self.nstep_batch(last_value)
+                self.train(batch, a, mk, returns, adv, device, actor, critic, optimizer)
+                self.buffer.clear()
+            if log is not None:
+                log(self.step_t, self.temp_loss, self.entro, env.status(), r_t, current_done)
+            if done:
+                env.reset()
+            self.total_reward = np.append(self.total_reward, r_t)
+        return env

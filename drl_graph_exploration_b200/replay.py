@@ -1,0 +1,114 @@
+"""Device-resident replay memory for the DQN path.
+
+The reference keeps a ``deque`` of ``(s_t, a_t, r_t, s_t1, terminal, fro_size1)`` tuples whose graphs are
+``torch_geometric.data.Data`` objects on the host (policy.py:131-133) and re-collates 2 x 64 of them through a
+``DataLoader`` for every gradient step (policy.py:141-151).  Here the graphs never leave HBM:
+
+* **graph ring**: fixed-stride slots ``x [G, Ncap, 5] f32``, ``ei [G, 2, Ecap] i32`` (node ids local to the graph),
+  ``ea [G, Ecap] f32`` plus per-slot ``(n_nodes, n_edges, key_size, fro_size)``.  A decision round of the vectorised
+  trainer stores its whole graph batch with three indexed writes (no per-graph host work).  ``s_t1`` of one transition
+  is ``s_t`` of the env's next one, so every graph is stored once.
+* **transition ring**: ``(slot_s, action_node, reward, slot_s1, terminal)`` as flat device tensors; FIFO like the
+  reference's ``popleft`` (policy.py:132-133).
+* **minibatch**: ``gather(slots)`` packs k stored graphs into one PyG-layout batch (``x``, ``edge_index`` with node
+  offsets, ``edge_attr``, ``batch``) with index arithmetic on the device -- one host sync for the two totals.
+
+A slot is re-used after ``G`` allocations; ``G = capacity + slack`` with ``slack`` >= the number of graphs that can be
+allocated between a transition's ``s_t`` and its completion (checked through allocation serials in ``sample``).
+Everything is plain tensor plumbing, so the CPU tests exercise the same code.
+"""
+from __future__ import annotations
+
+import torch
+
+from .data import Batch
+
+
+class GraphReplay:
+    def __init__(self, capacity: int, node_cap: int, edge_cap: int, device, slack: int = 0):
+        self.capacity, self.node_cap, self.edge_cap = int(capacity), int(node_cap), int(edge_cap)
+        self.G = G = self.capacity + int(slack)
+        dev = self.device = torch.device(device)
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        self.x, self.ei, self.ea = z((G, node_cap, 5), torch.float32), z((G, 2, edge_cap), torch.int32), z((G, edge_cap), torch.float32)
+        self.gn, self.ge, self.gk, self.gf = (z((G,), torch.int64) for _ in range(4))
+        self.gserial = torch.full((G,), -1, dtype=torch.int64, device=dev)
+        C = self.capacity
+        self.t_s, self.t_s1, self.t_a = z((C,), torch.int64), z((C,), torch.int64), z((C,), torch.int64)
+        self.t_r, self.t_term = z((C,), torch.float32), z((C,), torch.bool)
+        self.t_serial = z((C, 2), torch.int64)      # allocation serials of (s, s1) at append time: detects slot re-use
+        self.size = 0          # live transitions (host)
+        self.head = 0          # next transition position (host)
+        self.allocated = 0     # graphs allocated so far (host); slot of allocation i is i % G
+
+    # ------------------------------------------------------------------ graphs ---
+    def store_graphs(self, x, edge_index, edge_attr, batch, node_ptr, edge_ptr, key_size, fro_size, n_graphs: int) -> torch.Tensor:
+        """Stores a packed batch of ``n_graphs`` graphs (PyG DataLoader layout; ``node_ptr`` / ``edge_ptr`` [>= n_graphs+1]
+        exclusive prefix sums; edges of a graph contiguous and in graph order) and returns their slots [n_graphs] i64."""
+        dev, G = self.device, self.G
+        ng = int(n_graphs)
+        serial = torch.arange(self.allocated, self.allocated + ng, device=dev)
+        slots = serial % G
+        self.allocated += ng
+        nptr, eptr = node_ptr[:ng + 1].long(), edge_ptr[:ng + 1].long()
+        n_nodes, n_edges = x.size(0), edge_attr.size(0)
+        gid_n = batch[:n_nodes].long()
+        loc_n = torch.arange(n_nodes, device=dev) - nptr[gid_n]
+        self.x[slots[gid_n], loc_n] = x
+        gid_e = gid_n[edge_index[0]]                       # graph of an edge = graph of its source node
+        loc_e = torch.arange(n_edges, device=dev) - eptr[gid_e]
+        se = slots[gid_e]
+        self.ei[se, 0, loc_e] = (edge_index[0] - nptr[gid_e]).int()
+        self.ei[se, 1, loc_e] = (edge_index[1] - nptr[gid_e]).int()
+        self.ea[se, loc_e] = edge_attr
+        self.gn[slots] = nptr[1:] - nptr[:-1]
+        self.ge[slots] = eptr[1:] - eptr[:-1]
+        self.gk[slots] = key_size[:ng].long()
+        self.gf[slots] = fro_size[:ng].long()
+        self.gserial[slots] = serial
+        return slots
+
+    def gather(self, slots: torch.Tensor):
+        """Packs the graphs in ``slots`` [k] into one batch.  Returns (Batch, n_nodes [k], node_offset [k])."""
+        dev, k = self.device, slots.numel()
+        n, e = self.gn[slots], self.ge[slots]
+        noff, eoff = torch.cumsum(n, 0) - n, torch.cumsum(e, 0) - e
+        N, E = (int(v) for v in torch.stack([n.sum(), e.sum()]).tolist())       # the one host sync
+        ar = torch.arange(k, device=dev)
+        gid_n = torch.repeat_interleave(ar, n, output_size=N)
+        loc_n = torch.arange(N, device=dev) - noff[gid_n]
+        x = self.x[slots[gid_n], loc_n]
+        gid_e = torch.repeat_interleave(ar, e, output_size=E)
+        loc_e = torch.arange(E, device=dev) - eoff[gid_e]
+        se = slots[gid_e]
+        ei = torch.stack([self.ei[se, 0, loc_e], self.ei[se, 1, loc_e]]).long() + noff[gid_e]
+        b = Batch(x, ei, self.ea[se, loc_e], gid_n)
+        b.num_graphs = k
+        return b, n, noff
+
+    # ------------------------------------------------------------- transitions ---
+    def append(self, slot_s, action_node, reward, slot_s1, terminal):
+        """Appends m transitions (device tensors [m]); the oldest are overwritten beyond ``capacity``."""
+        m = int(slot_s.numel())
+        if m == 0:
+            return
+        C, dev = self.capacity, self.device
+        pos = (self.head + torch.arange(m, device=dev)) % C
+        self.t_s[pos], self.t_s1[pos], self.t_a[pos] = slot_s.long(), slot_s1.long(), action_node.long()
+        self.t_r[pos], self.t_term[pos] = reward.float(), terminal.bool()
+        self.t_serial[pos, 0], self.t_serial[pos, 1] = self.gserial[slot_s.long()], self.gserial[slot_s1.long()]
+        self.head = (self.head + m) % C
+        self.size = min(C, self.size + m)
+
+    def sample(self, k: int, generator=None, check: bool = False):
+        """k distinct transitions (random.sample, policy.py:141) -> (slot_s, action_node, reward, slot_s1, terminal)."""
+        assert self.size >= k, "replay holds fewer transitions than the minibatch"
+        idx = torch.randperm(self.size, device=self.device, generator=generator)[:k]
+        s, s1 = self.t_s[idx], self.t_s1[idx]
+        if check:   # a stored graph was overwritten while a live transition still refers to it: slack too small
+            ok = (self.gserial[s] == self.t_serial[idx, 0]) & (self.gserial[s1] == self.t_serial[idx, 1])
+            assert bool(ok.all()), "graph ring wrapped over a live transition: increase `slack`"
+        return s, self.t_a[idx], self.t_r[idx], s1, self.t_term[idx]
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.x, self.ei, self.ea))

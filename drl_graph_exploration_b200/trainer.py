@@ -1,0 +1,190 @@
+"""Vectorised DQN training loop: ``DeepQ.running`` (policy.py:60-209) for B environments per GPU.
+
+The reference trains on ONE env: per decision it builds the exploration graph, evaluates the look-ahead reward of
+every frontier on cloned simulators (``rewards_all_goals``), picks the arg-max of the dropout-perturbed Q-values
+("bayesian" exploration, policy.py:104-110), drives the env along the line plan, stores
+``(s_t, a_t, r_t, s_t1, done or loop_clo, fro_size1)`` and does one gradient step on 64 sampled transitions.
+
+Here the same per-env sequence runs for B envs on the batched engine (BASELINE config C3):
+
+* a **tick** = every env with a queued action executes one simulator step; every env whose queue ran empty gets a
+  decision: graph batch (``dge_graph``) -> roll-out rewards of all its frontiers on the clone engine
+  (``dge_rollout_*``) -> Q with functional dropout p = epsilon -> arg-max frontier + line plan on the device
+  (``dge_select_and_plan``);
+* the graph batch of a decision round is stored once in the device replay (``replay.GraphReplay``): it is ``s_t`` of
+  the transitions that start now and ``s_t1`` of the ones that end now;
+* ``train_steps_per_tick`` gradient steps per tick (``DeepQ.train``: loss sum((Q a - y)^2)/64, clamp +-0.5, Adam 1e-5)
+  with ONE all-reduce of the flat gradient bucket per step when ``torch.distributed`` is initialised -- every rank
+  takes the same number of steps per tick, so the collective never waits on data-dependent control flow.
+
+Deliberate differences, none of which change a per-env result: an episode that reaches ``done`` in the middle of a
+line plan restarts at once (the reference finishes the plan on the finished env, policy.py:117-118); an env left
+without frontier ends its episode (the reference would raise, quirk q15); epsilon decays per decision like the
+reference, counted over all envs.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .engine import _check, _stream_ptr
+from .envs.exploration_env import RESET_ODOM, VecExplorationEnv
+from .policy import DeepQ
+from .replay import GraphReplay
+
+
+class VecDQNTrainer:
+    def __init__(self, env: VecExplorationEnv, policy_net: torch.nn.Module, target_net: torch.nn.Module, dqn: DeepQ | None = None,
+                 replay_capacity: int | None = None, train_steps_per_tick: int = 1, observe: int | None = None, lr: float = 1e-5,
+                 clone_slots: int | None = None, seed: int = 0):
+        self.env, self.policy_net, self.target_net = env, policy_net, target_net
+        self.dqn = dqn or DeepQ()
+        self.dev = env.device
+        B, eng = env.B, env.eng
+        cap = int(replay_capacity if replay_capacity is not None else self.dqn.REPLAY_MEMORY)
+        # graphs allocated between a transition's s_t and its completion: <= B per tick x (longest plan + reset phase) ticks
+        self.replay = GraphReplay(cap, eng.node_cap_env, eng.edge_cap_env, self.dev, slack=B * 40)
+        self.optimizer = torch.optim.Adam(policy_net.parameters(), lr=lr)
+        self.target_net.load_state_dict(policy_net.state_dict())
+        self.target_net.eval()
+        self.train_steps_per_tick = int(train_steps_per_tick)
+        self.observe = int(self.dqn.OBSERVE if observe is None else observe)   # decisions before learning starts
+        self.clone_slots = clone_slots
+        i64 = lambda v: torch.full((B,), v, dtype=torch.int64, device=self.dev)
+        self.pend_slot, self.pend_a = i64(-1), i64(0)                  # in-flight transition of every env
+        self.pend_r = torch.zeros(B, dtype=torch.float32, device=self.dev)
+        self.pend_clo = torch.zeros(B, dtype=torch.bool, device=self.dev)
+        self._ar = torch.arange(B, device=self.dev)
+        self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
+        self.gen = torch.Generator(device=self.dev); self.gen.manual_seed(seed)
+        self.decisions = self.train_steps = self.ticks = self.transitions = 0
+        self.rollout_steps = self.rollout_clones = 0    # clone-engine ticks launched / clones evaluated
+        self.last_loss = float("nan")
+        self.reward_sum = 0.0
+
+    # ---------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _act(self):
+        """Step pipeline + decision round of one tick.  Returns the number of decisions taken."""
+        env, eng, rp, dqn = self.env, self.env.eng, self.replay, self.dqn
+        st, dev = eng.state, self.dev
+        done_prev = st["done"].bool().clone()          # episodes that ended in the previous tick's step
+        need = env.mark_pending().bool().clone()       # empty queue, not done, not in the reset phase
+        # ---- step pipeline: restart finished episodes, one simulator step for every env with a queued action ----
+        _check(eng._L.dge_reset_done_queued(eng._h, env.B, self._fo, 4, _stream_ptr(dev)), "dge_reset_done_queued")
+        eng.step_queued()
+        # ---- transitions that ended with the episode: terminal, s_t1 is not used by the target (policy.py:166-167) ----
+        ended = done_prev & (self.pend_slot >= 0)
+        # ---- decision round ----
+        g = env.build_graph(need.to(torch.uint8))
+        ng, n, e = g.sync_sizes()                      # host sync (sizes the GNN's GEMMs)
+        slot_new = torch.full_like(self.pend_slot, -1)
+        if ng > 0:
+            ordinal = torch.cumsum(need.long(), 0) - 1                      # graph ordinal of env b (graphs are in env order)
+            # roll-outs: one clone per (env, frontier); the decision round is cut into chunks that fit the clone engine
+            slots_c = self.clone_slots or min(env.B * (eng.Lt + 1), max(4 * env.B, 512))
+            fro_host = g.fro_size[:ng].tolist()                             # host sync (tiny)
+            lo = acc = 0
+            for i, f in enumerate(fro_host + [slots_c + 1]):
+                if acc + f > slots_c:
+                    m = (need & (ordinal >= lo) & (ordinal < i)).to(torch.uint8)
+                    _, norm, clo = env.rollout_rewards(m, clone_slots=slots_c, auto_steps=True)
+                    self.rollout_steps += env.rollout_steps; self.rollout_clones += acc
+                    lo, acc = i, 0
+                acc += f
+            d = g.data()
+            q = self.policy_net(d, float(self.epsilon))                     # functional dropout: "bayesian" exploration
+            choice = env.select_and_plan(q, need.to(torch.uint8)).long()    # [B], valid where need
+            slots = rp.store_graphs(d.x, d.edge_index, d.edge_attr, d.batch, g.node_ptr, g.edge_ptr, g.key_size, g.fro_size, ng)
+            o = ordinal.clamp(0, ng - 1)
+            slot_new = torch.where(need, slots[o], slot_new)
+            fro = torch.where(need, g.fro_size[:ng].long()[o], torch.zeros_like(o))
+            key = g.key_size[:ng].long()[o]
+        else:
+            fro = torch.zeros_like(self.pend_slot); key = fro; choice = fro
+            norm = clo = None
+        # ---- close the transitions of the envs that decided now (s_t1 = the graph just stored) and of the ended episodes ----
+        closing = need & (self.pend_slot >= 0)
+        fin = closing | ended
+        idx = fin.nonzero().view(-1)                   # host sync (number of transitions)
+        if idx.numel():
+            s1 = torch.where(closing, slot_new, self.pend_slot)[idx]
+            term = (ended | self.pend_clo | (closing & (fro <= 0)))[idx]
+            rp.append(self.pend_slot[idx], self.pend_a[idx], self.pend_r[idx], s1, term)
+            self.transitions += int(idx.numel())
+            self.reward_sum += float(self.pend_r[idx].sum())
+        self.pend_slot = torch.where(ended, torch.full_like(self.pend_slot, -1), self.pend_slot)
+        # ---- open the transitions of the envs that decided now ----
+        if ng > 0:
+            start = need & (fro > 0)
+            r = norm.gather(1, choice.clamp(0, norm.size(1) - 1).view(-1, 1)).view(-1).float()
+            self.pend_slot = torch.where(start, slot_new, torch.where(need, torch.full_like(slot_new, -1), self.pend_slot))
+            self.pend_a = torch.where(start, key + choice, self.pend_a)
+            self.pend_r = torch.where(start, r, self.pend_r)
+            self.pend_clo = torch.where(start, clo.bool(), self.pend_clo)
+        self.decisions += ng
+        dqn.step_t += ng
+        if dqn.epsilon > dqn.FINAL_EPSILON and dqn.step_t > self.observe:   # policy.py:78-79, per decision
+            dqn.epsilon = max(dqn.FINAL_EPSILON, dqn.epsilon - ng * (dqn.INITIAL_EPSILON - dqn.FINAL_EPSILON) / dqn.EXPLORE)
+        return ng
+
+    @property
+    def epsilon(self):
+        return self.dqn.epsilon
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def minibatch(self, k: int | None = None, check: bool = False):
+        """(s_j batch, action one-hot [N], y [N]) of policy.py:141-178, built on the device."""
+        dqn, rp = self.dqn, self.replay
+        k = k or dqn.BATCH
+        s, a, r, s1, term = rp.sample(k, generator=self.gen, check=check)
+        b_s, n_s, off_s = rp.gather(s)
+        b_s1, n_s1, off_s1 = rp.gather(s1)
+        return b_s, b_s1, dqn_targets_inputs(a, r, term, off_s, n_s1, off_s1, rp.gf[s1])
+
+    def learn(self, check: bool = False):
+        """One gradient step (policy.py:136-182); collective inside ``DeepQ.train``."""
+        dqn = self.dqn
+        if dqn.TARGET_UPDATE and self.train_steps % int(dqn.TARGET_UPDATE) == 0:
+            self.target_net.load_state_dict(self.policy_net.state_dict())
+        b_s, b_s1, (a, r, term, off_s, n_s1, off_s1, fro1) = self.minibatch(check=check)
+        with torch.no_grad():
+            q1 = dqn.test(b_s1, 0.0, self.dev, self.target_net).view(-1)
+        act, y = dqn_targets(q1, b_s1.batch, a, r, term, off_s, n_s1, off_s1, fro1, b_s.x.size(0), dqn.GAMMA)
+        self.last_loss = dqn.train(b_s, act, y, self.dev, self.policy_net, self.optimizer)
+        self.train_steps += 1
+        return self.last_loss
+
+    def tick(self, learn: bool | None = None):
+        ng = self._act()
+        self.ticks += 1
+        if learn is None:
+            learn = self.dqn.step_t > self.observe and self.replay.size >= self.dqn.BATCH
+        if learn:
+            for _ in range(self.train_steps_per_tick):
+                self.learn()
+        return ng
+
+    def save(self, path: str):
+        """``torch.save(policy_net.state_dict(), .../MyModel.pt)`` like policy.py:192 -- loadable by the reference."""
+        torch.save({k: v.detach().cpu() for k, v in self.policy_net.state_dict().items()}, path)
+
+
+def dqn_targets_inputs(a, r, term, off_s, n_s1, off_s1, fro1):
+    return a, r, term, off_s, n_s1, off_s1, fro1
+
+
+def dqn_targets(q1, batch1, a, r, term, off_s, n_s1, off_s1, fro1, n_nodes_s: int, gamma: float):
+    """policy.py:153-178 without the Python loop: y = r (+ gamma * max of the next state's last ``fro1`` Q-values unless
+    terminal) at the chosen node, 0 elsewhere; the action vector is one-hot at the same node."""
+    k = a.numel()
+    node = torch.arange(q1.numel(), device=q1.device)
+    in_tail = node >= (off_s1 + n_s1 - fro1)[batch1]
+    neg = torch.full_like(q1, -float("inf"))
+    max_q = torch.full((k,), -float("inf"), device=q1.device, dtype=q1.dtype).scatter_reduce(0, batch1, torch.where(in_tail, q1, neg), "amax")
+    yv = torch.where(term, r.to(q1.dtype), r.to(q1.dtype) + gamma * max_q)
+    at = off_s + a
+    act = torch.zeros(n_nodes_s, dtype=q1.dtype, device=q1.device); act[at] = 1.0
+    y = torch.zeros_like(act); y[at] = yv
+    return act, y

@@ -58,3 +58,40 @@ def test_cost_and_targets():
     _, a, y = dq.build_targets(mb, torch.device("cpu"), Net())
     assert a.tolist() == [0, 0, 1, 0, 1]
     assert np.allclose(y.numpy(), [0, 0, 0.25 + 0.99 * 4, 0, -1.0])
+
+
+def test_a2c_objectives_and_nstep_batch():
+    """A2C host logic against the formulas of policy.py:361-393,452-472 written out literally."""
+    from drl_graph_exploration_b200.policy import A2C
+    ac = A2C()
+    rng = np.random.default_rng(3)
+
+    def graph(n):
+        return Data(torch.tensor(rng.normal(size=(n, 5)), dtype=torch.float), torch.zeros(2, 0, dtype=torch.long), torch.zeros(0))
+
+    sizes, fros = [4, 3, 5], [2, 1, 3]
+    acts, rs, terms, vals = [], [0.5, -1.0, 0.25], [False, True, False], [0.1, -0.2, 0.3]
+    for n, f in zip(sizes, fros):
+        a = np.zeros(n); a[n - f + int(rng.integers(0, f))] = 1
+        acts.append(a)
+    for i in range(3):
+        ac.buffer.append((graph(sizes[i]), acts[i], rs[i], graph(sizes[i]), terms[i], fros[i], vals[i]))
+    batch, a, mask, returns, adv = ac.nstep_batch(last_value=2.0)
+    g2 = 0.25 + 0.99 * 2.0; g1 = -1.0; g0 = 0.5 + 0.99 * g1           # terminal at i = 1 cuts the bootstrap
+    assert np.allclose(returns, [g0, g1, g2])
+    assert np.array_equal(a, np.concatenate(acts))
+    assert mask.tolist() == [0, 0, 1, 1, 0, 0, 1, 0, 0, 1, 1, 1]
+    exp_adv = np.concatenate([acts[i] * ([g0, g1, g2][i] - vals[i]) for i in range(3)])
+    assert np.allclose(adv, exp_adv)
+    assert batch.x.shape == (12, 5) and batch.batch.tolist() == [0] * 4 + [1] * 3 + [2] * 5
+    # costs
+    mk = torch.tensor(mask, dtype=torch.bool)
+    prob = torch.tensor([0.3, 0.7, 1.0, 0.2, 0.5, 0.3])               # masked softmax output: frontier nodes only
+    pc = ac.policy_cost(prob, torch.tensor(adv), torch.tensor(a), mk)
+    lit = 0.0
+    pa, pv = np.asarray(a)[mask.astype(bool)], np.asarray(adv)[mask.astype(bool)]
+    for j in range(6):
+        lit += -np.log(float(prob[j])) * pv[j] * pa[j]
+    assert np.isclose(float(pc), lit / 40)
+    assert np.isclose(float(ac.entropy_loss(prob)), -float((prob.log() * prob).sum()) / 40)
+    assert np.isclose(float(ac.value_cost(torch.tensor([1.0, 2.0]), torch.tensor([0.0, 4.0]))), (1 + 4) / 2)

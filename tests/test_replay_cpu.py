@@ -1,0 +1,99 @@
+"""Device replay (replay.GraphReplay) and the vectorised DQN targets (trainer.dqn_targets) on CPU tensors:
+packing equals the reference's DataLoader collation (Batch.from_data_list), FIFO eviction equals the deque's popleft,
+targets equal DeepQ.build_targets (the literal restatement of policy.py:153-178)."""
+import numpy as np
+import torch
+
+from drl_graph_exploration_b200.data import Batch, Data
+from drl_graph_exploration_b200.policy import DeepQ
+from drl_graph_exploration_b200.replay import GraphReplay
+from drl_graph_exploration_b200.trainer import dqn_targets
+
+
+def _graph(rng, n):
+    e = int(rng.integers(0, 3 * n))
+    ei = torch.tensor(rng.integers(0, n, (2, e)), dtype=torch.long)
+    return Data(torch.tensor(rng.normal(size=(n, 5)), dtype=torch.float32), ei, torch.tensor(rng.uniform(0.1, 6, e), dtype=torch.float32))
+
+
+def _round(rng, sizes):
+    """A decision round as the engine emits it: packed batch + prefix sums + per-graph key/frontier sizes."""
+    items = [_graph(rng, n) for n in sizes]
+    b = Batch.from_data_list(items)
+    # the engine's edges are grouped by graph; Batch.from_data_list keeps that order
+    nptr = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32)
+    eptr = torch.tensor(np.concatenate([[0], np.cumsum([d.edge_attr.numel() for d in items])]), dtype=torch.int32)
+    fro = torch.tensor([int(rng.integers(1, n + 1)) for n in sizes], dtype=torch.int32)
+    key = torch.tensor(sizes, dtype=torch.int32) - fro
+    return items, b, nptr, eptr, key, fro
+
+
+def test_store_gather_equals_collation_and_ring_wraps():
+    rng = np.random.default_rng(0)
+    rp = GraphReplay(capacity=6, node_cap=40, edge_cap=120, device="cpu", slack=4)     # G = 10 slots
+    stored = {}
+    for rnd in range(5):
+        sizes = [int(v) for v in rng.integers(1, 40, int(rng.integers(1, 5)))]
+        items, b, nptr, eptr, key, fro = _round(rng, sizes)
+        slots = rp.store_graphs(b.x, b.edge_index, b.edge_attr, b.batch, nptr, eptr, key, fro, len(sizes))
+        for s, d, k, f in zip(slots.tolist(), items, key.tolist(), fro.tolist()):
+            stored[s] = (d, k, f)                                  # later rounds overwrite re-used slots
+        assert slots.tolist() == [(rp.allocated - len(sizes) + i) % rp.G for i in range(len(sizes))]
+    pick = torch.tensor(list(stored.keys())[::-1][:7])
+    got, n, off = rp.gather(pick)
+    ref = Batch.from_data_list([stored[int(s)][0] for s in pick])
+    assert torch.equal(got.x, ref.x) and torch.equal(got.edge_index, ref.edge_index)
+    assert torch.equal(got.edge_attr, ref.edge_attr) and torch.equal(got.batch, ref.batch)
+    assert n.tolist() == [stored[int(s)][0].x.size(0) for s in pick]
+    assert rp.gk[pick].tolist() == [stored[int(s)][1] for s in pick] and rp.gf[pick].tolist() == [stored[int(s)][2] for s in pick]
+
+
+def test_transition_ring_is_fifo_like_the_deque():
+    rp = GraphReplay(capacity=5, node_cap=4, edge_cap=4, device="cpu", slack=3)
+    z = torch.zeros(8, dtype=torch.int64)
+    rp.gserial[:] = torch.arange(8)
+    for lo in (0, 3, 6):                                           # 3 + 3 + 2 transitions into a ring of 5
+        m = min(3, 8 - lo)
+        ids = torch.arange(lo, lo + m)
+        rp.append(z[:m], ids, ids.float(), z[:m], torch.zeros(m, dtype=torch.bool))
+    assert rp.size == 5
+    assert sorted(rp.t_a.tolist()) == [3, 4, 5, 6, 7]              # the three oldest were dropped
+    s, a, r, s1, term = rp.sample(5, check=True)
+    assert sorted(a.tolist()) == [3, 4, 5, 6, 7] and torch.equal(a.float(), r)
+    try:
+        rp.gserial[0] = 99                                         # the slot was re-allocated under a live transition
+        rp.sample(5, check=True)
+        raise RuntimeError("expected the serial check to fire")
+    except AssertionError:
+        pass
+
+
+def test_vectorised_targets_equal_build_targets():
+    rng = np.random.default_rng(1)
+    dq = DeepQ()
+
+    class Net(torch.nn.Module):            # target-net stand-in: Q = first feature
+        def forward(self, data, prob, batch=None):
+            return data.x[:, :1]
+
+    k = 9
+    mb, rp = [], GraphReplay(capacity=32, node_cap=24, edge_cap=80, device="cpu", slack=8)
+    sizes = [int(v) for v in rng.integers(2, 24, 2 * k)]
+    items, b, nptr, eptr, key, fro = _round(rng, sizes)
+    slots = rp.store_graphs(b.x, b.edge_index, b.edge_attr, b.batch, nptr, eptr, key, fro, 2 * k)
+    a_node, r, term = [], [], []
+    for i in range(k):
+        s, s1 = items[2 * i], items[2 * i + 1]
+        an = int(key[2 * i]) + int(rng.integers(0, int(fro[2 * i])))
+        onehot = np.zeros(s.x.size(0)); onehot[an] = 1
+        rew, t = float(rng.uniform(-1, 1)), bool(rng.integers(0, 2))
+        mb.append((s, onehot, rew, s1, t, int(fro[2 * i + 1])))
+        a_node.append(an); r.append(rew); term.append(t)
+    _, a_ref, y_ref = dq.build_targets(mb, torch.device("cpu"), Net())
+    rp.append(slots[0::2], torch.tensor(a_node), torch.tensor(r), slots[1::2], torch.tensor(term))
+    s, a, rr, s1, tt = rp.t_s[:k], rp.t_a[:k], rp.t_r[:k], rp.t_s1[:k], rp.t_term[:k]
+    b_s, n_s, off_s = rp.gather(s)
+    b_s1, n_s1, off_s1 = rp.gather(s1)
+    q1 = Net()(b_s1, 0.0).view(-1)
+    act, y = dqn_targets(q1, b_s1.batch, a, rr, tt, off_s, n_s1, off_s1, rp.gf[s1], b_s.x.size(0), dq.GAMMA)
+    assert torch.equal(act, a_ref.float()) and torch.allclose(y, y_ref.float(), rtol=1e-6, atol=1e-7)

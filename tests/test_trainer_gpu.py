@@ -1,0 +1,97 @@
+"""Vectorised DQN trainer on the GPU engine (BASELINE config C3 at test size): the acting loop fills the device replay
+with well-formed transitions, the minibatch targets equal the literal restatement of policy.py:153-178 on the same
+transitions, and gradient steps change the policy while the target net stays put."""
+import numpy as np
+import pytest
+import torch
+
+from drl_graph_exploration_b200.config import EnvConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(B=24, map_size=20, n_lm=12, seed=0, **kw):
+    from drl_graph_exploration_b200 import Networks
+    from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv
+    from drl_graph_exploration_b200.trainer import VecDQNTrainer
+
+    env = VecExplorationEnv(B, cfg=EnvConfig(map_size=map_size, num_landmarks=n_lm), max_poses=128, seed0=seed)
+    env.reset()
+    torch.manual_seed(0)
+    pol, tgt = Networks.GCN().to(env.device), Networks.GCN().to(env.device)
+    return env, VecDQNTrainer(env, pol, tgt, replay_capacity=512, observe=0, **kw)
+
+
+def test_acting_loop_fills_replay_with_well_formed_transitions():
+    env, tr = _make()
+    rp = tr.replay
+    for _ in range(40):
+        tr.tick(learn=False)
+    torch.cuda.synchronize()
+    assert tr.decisions > 24 and tr.transitions > 24 and rp.size == min(tr.transitions, rp.capacity)
+    n = rp.size
+    s, a, r, s1, term = rp.t_s[:n], rp.t_a[:n], rp.t_r[:n], rp.t_s1[:n], rp.t_term[:n]
+    # the chosen node is one of the frontier nodes of s_t (policy.py:109-110: a_t[key_size + action_index] = 1)
+    assert bool(((a >= rp.gk[s]) & (a < rp.gk[s] + rp.gf[s])).all())
+    assert bool((rp.gn[s] == rp.gk[s] + rp.gf[s]).all()) and bool((rp.gn[s1] > 0).all())
+    # rewards are the min-max normalised look-ahead rewards of exploration_env.py:154-161
+    assert bool(((r >= -1.0) & (r <= 1.0)).all()) and float(r.abs().max()) > 0
+    # no stored graph was overwritten under a live transition
+    assert bool((rp.gserial[s] == rp.t_serial[:n, 0]).all()) and bool((rp.gserial[s1] == rp.t_serial[:n, 1]).all())
+    assert int(term.sum()) > 0 and int((~term).sum()) > 0
+    # stored graphs are the engine's graphs: symmetric COO with local node ids inside the graph
+    b, nn, off = rp.gather(s[:16])
+    ei = b.edge_index
+    assert int(ei.min()) >= 0 and int(ei.max()) < b.x.size(0)
+    assert bool((b.batch[ei[0]] == b.batch[ei[1]]).all())
+    N = b.x.size(0)                                                # data_process emits both directions (policy.py:222-226)
+    assert torch.equal(torch.sort(ei[0] * N + ei[1]).values, torch.sort(ei[1] * N + ei[0]).values)
+    assert bool((b.x[:, 4].abs() <= 1).all())                     # node type column: -1 / 0 / +1
+    env.close()
+
+
+def test_minibatch_targets_equal_literal_restatement_and_learning_moves_the_policy():
+    from drl_graph_exploration_b200.data import Data
+    from drl_graph_exploration_b200.trainer import dqn_targets
+
+    env, tr = _make(seed=100)
+    for _ in range(30):
+        tr.tick(learn=False)
+    dq, rp = tr.dqn, tr.replay
+    k = min(dq.BATCH, rp.size)
+    assert k >= 16
+    s, a, r, s1, term = rp.sample(k, generator=tr.gen, check=True)
+    b_s, n_s, off_s = rp.gather(s)
+    b_s1, n_s1, off_s1 = rp.gather(s1)
+    with torch.no_grad():
+        q1 = dq.test(b_s1, 0.0, tr.dev, tr.target_net).view(-1)
+    act, y = dqn_targets(q1, b_s1.batch, a, r, term, off_s, n_s1, off_s1, rp.gf[s1], b_s.x.size(0), dq.GAMMA)
+    # policy.py:153-178 literally, on the host
+    q1h, a_ref, y_ref, start = q1.cpu().numpy(), [], [], 0
+    for i in range(k):
+        n0, n1 = int(n_s[i]), int(n_s1[i])
+        onehot = np.zeros(n0); onehot[int(a[i])] = 1
+        ty = np.zeros(n0)
+        if bool(term[i]):
+            ty[int(a[i])] = float(r[i])
+        else:
+            ty[int(a[i])] = float(r[i]) + dq.GAMMA * np.max(q1h[start:start + n1][-int(rp.gf[s1[i]]):])
+        start += n1
+        a_ref.append(onehot); y_ref.append(ty)
+    assert np.array_equal(act.cpu().numpy(), np.concatenate(a_ref))
+    assert np.allclose(y.cpu().numpy(), np.concatenate(y_ref), rtol=1e-5, atol=1e-6)
+    # gradient steps: loss finite, policy moves, target stays until TARGET_UPDATE
+    before = {k_: v.clone() for k_, v in tr.policy_net.state_dict().items()}
+    tgt_before = {k_: v.clone() for k_, v in tr.target_net.state_dict().items()}
+    dq.BATCH = k
+    losses = [tr.learn(check=True) for _ in range(3)]
+    assert all(np.isfinite(l) for l in losses)
+    assert any(not torch.equal(before[k_], v) for k_, v in tr.policy_net.state_dict().items())
+    assert all(torch.equal(tgt_before[k_], v) for k_, v in tr.target_net.state_dict().items())
+    # the clamp of policy.py:251-252 was applied to what Adam saw
+    assert float(tr.dqn._bucket.flat.abs().max()) <= dq.max_grad_norm + 1e-7
+    # keeps running with learning inside the tick
+    for _ in range(5):
+        tr.tick()
+    assert tr.train_steps >= 8
+    env.close()
