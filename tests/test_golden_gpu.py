@@ -1,0 +1,71 @@
+"""The CUDA path against the reference's own known-answer data: test.py's loop (exploration graph -> DQN+GCN with the
+shipped weights -> arg-max frontier -> line plan -> steps) runs entirely on the GPU engine + CUDA GNN kernels, and the
+per-step metrics are compared DIRECTLY with rows of data/test_result/{40,60,80}_DQN_GCN.csv (fixtures under
+tests/golden, extracted by make_golden.py).  The CPU oracle only supplies what the golden run's RNG supplied: the
+world and the per-step noise draws (libstdc++ mt19937 streams cannot be replayed by the device's Philox)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import RESET_ODOM
+from drl_graph_exploration_b200.config import EnvConfig
+from oracle.oracle import OracleEnv
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("map_size,seed,n_steps", [(40, 0, 50), (40, 1, 40), (40, 8, 25), (60, 2, 30), (80, 2, 40)])
+def test_cuda_path_tracks_reference_golden_csv(map_size, seed, n_steps):
+    from drl_graph_exploration_b200 import Networks
+    from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv, expand_plan
+
+    g0 = np.load(os.path.join(GOLD, "ref_40_DQN_GCN_seed0.npz"))
+    sd = {k[3:]: torch.tensor(g0[k]) for k in g0.files if k.startswith("sd_")}
+    if (map_size, seed) == (40, 0):
+        gold = np.stack([g0["landmark_error"], g0["entropy"], g0["max_unc"]], axis=1)
+    else:
+        gold = np.load(os.path.join(GOLD, "ref_DQN_GCN_multi.npz"))[f"g_{map_size}_{seed}"]
+    cfg = EnvConfig(map_size=map_size)
+    env = VecExplorationEnv(1, cfg=cfg, max_poses=160)
+    dev = env.device
+    t = lambda a: torch.as_tensor(a, device=dev)
+    model = Networks.GCN().to(dev)
+    model.load_state_dict(sd)
+    model.eval()
+    while True:   # exploration_env.py:416-419 'regenerate a environment'
+        o = OracleEnv(cfg, seed)
+        lm = o.landmarks()
+        env.eng.reset(seeds=t(np.array([seed], dtype=np.int64)), start=t(np.array([o.start])), landmarks=t(lm["true"][None]),
+                      scan=t(lm["scan_id"][None].astype(np.int32)), noise=t(o.init_noise[None]))
+        for _ in range(4):
+            env.eng.step(t(np.array([RESET_ODOM])), noise=t(o.step(RESET_ODOM)[None]))
+        if int(env.eng.state["observed"][0].sum()) >= 1:
+            break
+        seed += 50
+    diff = {40: 1200, 60: 1600, 80: 2000}[map_size]
+    st = env.eng.state
+    step, worst = 0, 0.0
+    with torch.no_grad():
+        while step < n_steps:
+            g = env.build_graph()
+            g.sync_sizes()
+            q = model(g.data(), 0.0)
+            env.select_and_plan(q)
+            for act in expand_plan(st["plan"][0].cpu().numpy(), cfg.max_edge_length):
+                od = np.array([act.x, act.y, act.theta])
+                env.eng.step(t(od[None]), noise=t(o.step(od)[None]))
+                m = st["metrics"][0].cpu().numpy()
+                p = st["prob"][0].cpu().numpy()
+                ent = -(p * np.log(p)).sum() + 0.5 * np.log(0.5) * diff            # test.py:61-76
+                gl, ge, gm = gold[step]
+                dl, dm = abs(m[4] - gl) / gl, abs(m[5] - gm) / gm
+                assert dl < 1e-5 and dm < 1e-5 and abs(ent - ge) < 0.3, (map_size, seed, step, dl, dm, ent - ge)
+                worst = max(worst, dl, dm)
+                step += 1
+                if step >= n_steps:
+                    break
+    print(f"map {map_size} seed {seed}: {step} steps of the reference's result file followed by the CUDA path, worst rel err {worst:.2e}")
+    env.close()
