@@ -82,6 +82,7 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.forced = al.get<int32_t>(B); e.step_kind = al.get<uint8_t>(B); e.pending = al.get<uint8_t>(B);
   e.counters = al.get<unsigned long long>(4); e.count_steps = 1; e.park_done = 1;
   e.rdist = al.get<double>(B); e.r_cmap = al.get<int32_t>(B * 2); e.r_cbase = al.get<int32_t>(B); e.r_u0 = al.get<double>(B);
+  if (al.ok && cudaMallocHost(reinterpret_cast<void **>(&e.pack_hdr_host), 16 * sizeof(int64_t)) != cudaSuccess) al.ok = false;
   if (!al.ok) {
     for (void *p : al.ptrs) cudaFree(p);
     delete bx;
@@ -96,6 +97,7 @@ extern "C" int dge_destroy(dge_handle h) {
   EngineBox *bx = reinterpret_cast<EngineBox *>(h);   // e is the first member
   cudaSetDevice(h->device);
   for (void *p : bx->al.ptrs) cudaFree(p);
+  if (h->pack_hdr_host) cudaFreeHost(h->pack_hdr_host);
   delete bx;
   return DGE_OK;
 }
@@ -261,6 +263,102 @@ extern "C" int dge_graph_host(dge_handle h, const uint8_t *mask_host, const dge_
   }
   if (!ok) return fail(DGE_ECUDA, "dge_graph_host: D2H graph");
   if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host: sync");
+  return DGE_OK;
+}
+
+// ---- packed host transfer of a graph batch ---------------------------------------------------------------------
+// One arena holds the valid prefix of every array of the batch behind a 128-byte header, so that the batch crosses the
+// bus in ONE copy per direction (13 small D2H copies + 7 H2D copies otherwise) and the host / device views are plain
+// offsets into the same bytes.  Section order and alignment (16 B) are ABI: see dge_graph_packed in dge.h.
+namespace {
+__host__ __device__ inline int64_t pk_align(int64_t v) { return (v + 15) & ~int64_t(15); }
+struct PackLayout { int64_t off[12]; int64_t total; };
+__host__ __device__ inline PackLayout pack_layout(int64_t G, int64_t N, int64_t E, int64_t Fmax) {
+  PackLayout L;
+  int64_t o = 128;
+  const int64_t sz[12] = {N * 20, E * 16, E * 4, (G + 1) * 4, (G + 1) * 4, G * 4, G * 4, G * Fmax * 16, (N + 1) * 4, E * 4, E * 4, N * 4};
+  for (int i = 0; i < 12; ++i) { L.off[i] = o; o = pk_align(o + sz[i]); }
+  L.total = o;
+  return L;
+}
+__global__ void __launch_bounds__(256) k_graph_pack(dge_graph_out g, const int32_t *g_sel, int B, int Fmax, unsigned char *arena, int64_t cap) {
+  const int64_t G = g.totals[0], N = g.totals[1], E = g.totals[2];
+  const PackLayout L = pack_layout(G, N, E, Fmax);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  int64_t *hdr = reinterpret_cast<int64_t *>(arena);
+  if (tid == 0) {
+    hdr[0] = G; hdr[1] = N; hdr[2] = E; hdr[3] = g.totals[3] | (L.total > cap ? 2 : 0); hdr[4] = g.totals[4]; hdr[5] = L.total;
+  }
+  if (L.total > cap || g.totals[3]) return;
+  auto cp32 = [&](int64_t off, const void *src, int64_t words) {
+    uint32_t *d = reinterpret_cast<uint32_t *>(arena + off);
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
+    for (int64_t i = tid; i < words; i += nth) d[i] = s[i];
+  };
+  cp32(L.off[0], g.x, N * 5);
+  cp32(L.off[1], g.edge_index, E * 2);
+  cp32(L.off[1] + E * 8, g.edge_index + g.edge_cap, E * 2);
+  cp32(L.off[2], g.edge_attr, E);
+  cp32(L.off[3], g.node_ptr, G + 1);
+  cp32(L.off[4], g.edge_ptr, G + 1);
+  cp32(L.off[5], g.key_size, G);
+  cp32(L.off[6], g.fro_size, G);
+  {   // frontier coordinates by graph ordinal (the device array is indexed by env)
+    uint32_t *d = reinterpret_cast<uint32_t *>(arena + L.off[7]);
+    const int64_t per = (int64_t)Fmax * 4;     // words per env
+    for (int64_t i = tid; i < (int64_t)B * per; i += nth) {
+      const int b = (int)(i / per), gi = g_sel[b];
+      if (gi >= 0) d[(int64_t)gi * per + (i - (int64_t)b * per)] = reinterpret_cast<const uint32_t *>(g.frontier_xy)[i];
+    }
+  }
+  if (g.csr_rowptr) {
+    cp32(L.off[8], g.csr_rowptr, N + 1);
+    cp32(L.off[9], g.csr_perm, E);
+    cp32(L.off[10], g.gcn_norm, E);
+    cp32(L.off[11], g.gcn_selfnorm, N);
+  }
+}
+}  // namespace
+
+extern "C" int64_t dge_graph_packed_capacity(dge_handle h, const dge_graph_out *dev) {
+  if (!h || !dev) return -1;
+  return pack_layout(h->d.B, dev->node_cap, dev->edge_cap, h->d.Fmax).total;
+}
+
+extern "C" int dge_graph_host_packed_begin(dge_handle h, const uint8_t *mask_host, const dge_graph_out *dev, void *arena_dev, int64_t arena_cap, void *stream) {
+  if (!h || !dev || !arena_dev || arena_cap < 128) return fail(DGE_EINVAL, "dge_graph_host_packed_begin: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t *mask = nullptr;
+  if (mask_host) {
+    if (cudaMemcpyAsync(h->mask_dev_scratch2, mask_host, h->d.B, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host_packed_begin: H2D mask");
+    mask = h->mask_dev_scratch2;
+  }
+  const int rc = dge_graph(h, mask, dev, stream);
+  if (rc) return rc;
+  k_graph_pack<<<148, 256, 0, st>>>(*dev, h->g_sel, h->d.B, h->d.Fmax, static_cast<unsigned char *>(arena_dev), arena_cap);
+  if (cudaGetLastError() != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host_packed_begin: k_graph_pack");
+  if (cudaMemcpyAsync(h->pack_hdr_host, arena_dev, 128, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host_packed_begin: D2H header");
+  return DGE_OK;
+}
+
+extern "C" int dge_graph_host_packed_end(dge_handle h, const void *arena_dev, void *arena_host, int64_t arena_cap, dge_graph_packed *out, void *stream) {
+  if (!h || !arena_dev || !arena_host || !out) return fail(DGE_EINVAL, "dge_graph_host_packed_end: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host_packed_end: sync");
+  const int64_t *hdr = h->pack_hdr_host;
+  const int64_t G = hdr[0], N = hdr[1], E = hdr[2];
+  if (hdr[3]) return fail(DGE_ECAP, "dge_graph_host_packed_end: graph batch or arena capacity exceeded");
+  const PackLayout L = pack_layout(G, N, E, h->d.Fmax);
+  out->n_graphs = (int32_t)G; out->n_nodes = (int32_t)N; out->n_edges = (int32_t)E; out->n_done = (int32_t)hdr[4];
+  out->total_bytes = G > 0 ? L.total : 128;
+  int64_t *o = &out->x;
+  for (int i = 0; i < 12; ++i) o[i] = L.off[i];
+  memcpy(arena_host, hdr, 128);
+  if (G == 0) return DGE_OK;
+  if (L.total > arena_cap) return fail(DGE_ECAP, "dge_graph_host_packed_end: arena too small");
+  if (cudaMemcpyAsync(static_cast<unsigned char *>(arena_host) + 128, static_cast<const unsigned char *>(arena_dev) + 128, L.total - 128, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    return fail(DGE_ECUDA, "dge_graph_host_packed_end: D2H arena");
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host_packed_end: sync");
   return DGE_OK;
 }
 

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_aggregate(int N, int C, const float *__
                                                    const float *__restrict__ coef, const float *__restrict__ selfcoef,
                                                    const float *__restrict__ bias, const float *__restrict__ gate, int relu,
                                                    float *__restrict__ out, const float *__restrict__ head_w, float head_b,
-                                                   float *__restrict__ q) {
+                                                   float *__restrict__ q, const float *__restrict__ head_b_dev = nullptr) {
   constexpr int VEC = 4;
   const int i = blockIdx.x;
   const int c0 = threadIdx.x * VEC;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) k_aggregate(int N, int C, const float *__
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int wv = 0; wv < 8; ++wv) s += red[wv];
-      q[i] = s + head_b;
+      q[i] = s + head_b + (head_b_dev ? head_b_dev[0] : 0.f);
     }
   }
 }
@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(256) k_gcn_conv_small(int N, int Cin, int C, c
                                                         const int32_t *__restrict__ perm, const int64_t *__restrict__ nbr,
                                                         const float *__restrict__ coef, const float *__restrict__ selfcoef,
                                                         const float *__restrict__ W, const float *__restrict__ bias, int relu,
-                                                        float *__restrict__ out) {
+                                                        float *__restrict__ out, float *__restrict__ out_hi = nullptr,
+                                                        float *__restrict__ out_lo = nullptr) {
   const int i = blockIdx.x;
   __shared__ float agg[CIN_MAX];
   if (threadIdx.x < 32) {   // one warp aggregates the input row: lanes over edges (fixed order per lane, shuffle tree => deterministic)
@@ -251,7 +252,15 @@ __global__ void __launch_bounds__(256) k_gcn_conv_small(int N, int Cin, int C, c
 #pragma unroll
     for (int k = 0; k < CIN_MAX; ++k) if (k < Cin) r += agg[k] * W[(size_t)k * C + c];
     if (relu) r = fmaxf(r, 0.f);
-    out[(size_t)i * C + c] = r;
+    if (out) out[(size_t)i * C + c] = r;
+    if (out_hi) {   // operand of the 3xTF32 tensor-core GEMM that follows: (tf32(r), tf32(r - tf32(r))), as dge_gemm_split_tf32
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(r));
+      const float ho = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(r - ho));
+      out_hi[(size_t)i * C + c] = ho;
+      out_lo[(size_t)i * C + c] = __uint_as_float(lb);
+    }
   }
 }
 }  // namespace
@@ -260,5 +269,26 @@ extern "C" int dge_gcn_conv_small(int N, int Cin, int C, const float *X, const i
                                   const float *coef, const float *selfcoef, const float *W, const float *bias, int relu, float *out, void *stream) {
   if (N <= 0 || Cin <= 0 || Cin > 8 || C <= 0 || !X || !rowptr || !perm || !W || !out) return -1;
   k_gcn_conv_small<8><<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(N, Cin, C, X, rowptr, perm, nbr, coef, selfcoef, W, bias, relu, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---------------------------------------------- whole Q-network forward (inference), one call ------------------
+// Networks.GCN.forward with prob = 0 (Networks.py:18-28): relu(GCNConv(5,C)) -> relu(GCNConv(C,C)) -> Linear(C,1), as
+// three launches: first layer fused (aggregate 5 channels, transform, ReLU, TF32 split in the epilogue) -> tcgen05
+// 3xTF32 GEMM -> aggregate + bias + ReLU + head dot product.  ws = 3 * N * C floats (h_hi | h_lo | h W2).
+extern "C" int dge_gcn_q_forward(int N, int Cin, int C, const float *x, const int32_t *rowptr, const int32_t *perm, const int64_t *src,
+                                 const float *norm, const float *selfnorm, const float *W1, const float *b1, const float *W2t_hi,
+                                 const float *W2t_lo, const float *b2, const float *head_w, const float *head_b_dev, float *ws, float *q,
+                                 void *stream) {
+  if (N <= 0 || Cin <= 0 || Cin > 8 || C <= 0 || C > 1024 || (C & 3) || !x || !rowptr || !perm || !src || !norm || !selfnorm || !W1 || !W2t_hi ||
+      !W2t_lo || !head_w || !ws || !q || ((uintptr_t)ws & 15))
+    return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float *h_hi = ws, *h_lo = ws + (size_t)N * C, *xw = ws + 2 * (size_t)N * C;
+  k_gcn_conv_small<8><<<N, 256, 0, st>>>(N, Cin, C, x, rowptr, perm, src, norm, selfnorm, W1, b1, 1, nullptr, h_hi, h_lo);
+  if (cudaGetLastError() != cudaSuccess) return -2;
+  const int rc = dge_gemm_tf32x3(N, nullptr, C, C, h_hi, h_lo, W2t_hi, W2t_lo, xw, C, stream);
+  if (rc) return rc;
+  k_aggregate<true><<<N, 256, 0, st>>>(N, C, xw, rowptr, perm, src, norm, selfnorm, b2, nullptr, 1, nullptr, head_w, 0.f, q, head_b_dev);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

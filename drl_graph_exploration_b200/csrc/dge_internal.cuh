@@ -78,6 +78,7 @@ struct dge_engine {
   int32_t *forced;       // [B] forced steps left after an in-pipeline reset (| DGE_FRESH_BIT while the initial optimize is pending)
   uint8_t *step_kind;    // [B] 1 = the env's last step was a policy step
   uint8_t *pending;      // [B] envs that need a decision (dge_mark_pending)
+  int64_t *pack_hdr_host; // [16] pinned: header of the last packed graph batch (dge_graph_host_packed_*)
   double forced_odom[3]; // host copy of the forced action (exploration_env.py:411-414)
   int count_steps;       // host flag: 1 while stepping on behalf of the policy (reset steps are not counted)
   int park_done;         // host flag: queued stepping skips `done` envs (1, default) or runs every plan to its end (0, roll-out engines)

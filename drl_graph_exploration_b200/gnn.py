@@ -318,3 +318,37 @@ class _TcMatmulFn(torch.autograd.Function):
 def tc_matmul(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """x [M,K] @ w [K,N], fp32-quality on the 5th-gen tensor cores (csrc/dge_gemm.cu)."""
     return _TcMatmulFn.apply(x, w)
+
+
+# ------------------------------------------------------------- whole Q-network forward, one native call ---
+_q_ws: dict = {}
+
+
+def gcn_q_forward(x: torch.Tensor, gs: GraphStructure, w1: torch.Tensor, b1, w2: torch.Tensor, b2, head_w: torch.Tensor, head_b: torch.Tensor):
+    """Networks.GCN.forward at inference (prob = 0) through ``dge_gcn_q_forward``: one ctypes call, three launches
+    (fused first layer with the TF32 split in its epilogue -> tcgen05 GEMM -> aggregate + ReLU + head).  Returns q [N]."""
+    global launch_count
+    _need_cuda(x, "gcn_q_forward")
+    L = _gemm_lib()
+    if not hasattr(L, "_q_forward_ready"):
+        L.dge_gcn_q_forward.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 16
+        L._q_forward_ready = True
+    norm, selfnorm = gs.gcn_norm(True)
+    hi, lo = _weight_operand(w2, True)
+    x = x.contiguous().float()
+    N, cin = x.shape
+    C = w1.shape[1]
+    dev = x.device
+    ws = _q_ws.get(dev)
+    if ws is None or ws.numel() < 3 * N * C:      # grow-only workspace: no allocator traffic in the acting loop
+        ws = _q_ws[dev] = torch.empty(max(3 * N * C, 1 << 22), dtype=torch.float32, device=dev)
+    q = torch.empty(N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.dge_gcn_q_forward(N, cin, C, _p(x), _p(gs.rowptr_dst), _p(gs.perm_dst), _p(gs.src), _p(norm), _p(selfnorm),
+                                 _p(w1.detach().contiguous()), _p(None if b1 is None else b1.detach().contiguous()), _p(hi), _p(lo),
+                                 _p(None if b2 is None else b2.detach().contiguous()), _p(head_w.detach().contiguous()),
+                                 _p(None if head_b is None else head_b.detach()), _p(ws), _p(q), _st(dev))
+    if rc:
+        raise DgeError(f"dge_gcn_q_forward failed ({rc})")
+    launch_count += 3
+    return q

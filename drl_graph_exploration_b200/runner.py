@@ -116,6 +116,10 @@ class HostPolicyLoop:
         L.dge_step_host_async.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.dge_graph_host.argtypes = [vp, vp, vp, vp, vp]
         L.dge_line_plan_host.argtypes = [vp, vp, vp, vp, vp]
+        L.dge_graph_packed_capacity.restype = ctypes.c_int64
+        L.dge_graph_packed_capacity.argtypes = [vp, vp]
+        L.dge_graph_host_packed_begin.argtypes = [vp, vp, vp, vp, ctypes.c_int64, vp]
+        L.dge_graph_host_packed_end.argtypes = [vp, vp, vp, ctypes.c_int64, vp, vp]
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
         f64, f32, i32, i64, u8 = torch.float64, torch.float32, torch.int32, torch.int64, torch.uint8
         # step-side host buffers
@@ -128,6 +132,18 @@ class HostPolicyLoop:
         self.t_nptr, self.t_eptr, self.t_ks, self.t_fs = pin((B + 1,), i32), pin((B + 1,), i32), pin((B,), i32), pin((B,), i32)
         self.t_fxy, self.t_tot = pin((B, eng.Lt + 1, 2), f64), pin((8,), i32)
         self.t_goal, self.t_plan = pin((B, 2), f64), pin((B, 6), f64)
+        # packed graph transfer: one pinned arena, one device arena the pack kernel fills, one device arena the policy reads
+        self.arena_cap = int(L.dge_graph_packed_capacity(eng._h, ctypes.byref(g.c)))
+        self.a_host = torch.zeros(self.arena_cap, dtype=u8).pin_memory()
+        self.a_pack = torch.zeros(self.arena_cap, dtype=u8, device=self.dev)
+        self.a_dev = torch.zeros(self.arena_cap, dtype=u8, device=self.dev)
+
+        class _Packed(ctypes.Structure):
+            _fields_ = [(n, ctypes.c_int64) for n in ("total_bytes", "x", "edge_index", "edge_attr", "node_ptr", "edge_ptr", "key_size", "fro_size",
+                                                      "frontier_xy", "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm")] + \
+                       [(n, ctypes.c_int32) for n in ("n_graphs", "n_nodes", "n_edges", "n_done")]
+        self._pk = _Packed()
+        self.packed = True
         self.t_q = pin((g.node_cap,), f32)
         self.t_rowptr, self.t_perm = pin((g.node_cap + 1,), i32), pin((g.edge_cap,), i32)
         self.t_norm, self.t_selfnorm = pin((g.edge_cap,), f32), pin((g.node_cap,), f32)
@@ -184,9 +200,19 @@ class HostPolicyLoop:
         in_reset = self.phase > 0
         has_act = (self.cursor < nact) & ~in_reset
         need = ~has_act & ~in_reset
-        # ---- step pipeline (async on s1): reset finished episodes, then one simulator step from host actions ------
         if self.overlap:
             s1.wait_stream(main)
+        mp = ctypes.c_void_p(main.cuda_stream)
+        do_policy = bool(need.any())
+        if do_policy and self.packed:
+            # ---- policy pipeline, part 1 (main stream, async): graph kernels + pack; they run while the host launches the step ----
+            self.need[:] = need
+            _check(L.dge_graph_host_packed_begin(eng._h, self.t_need.data_ptr(), ctypes.byref(env.graph.c), self.a_pack.data_ptr(), self.arena_cap, mp),
+                   "dge_graph_host_packed_begin")
+            self.launches += 5
+            self.h2d += B
+            lap("policy: graph launch")
+        # ---- step pipeline (async on s1): reset finished episodes, then one simulator step from host actions ------
         sp = ctypes.c_void_p(s1.cuda_stream)
         _check(L.dge_reset_done_queued(eng._h, self.seed_stride, self._fo, 4, sp), "dge_reset_done_queued")
         self._next_actions()
@@ -201,26 +227,49 @@ class HostPolicyLoop:
         self.phase[in_reset] -= 1
         lap("step: host prep + async launches")
         # ---- policy pipeline (main stream, host in the loop) ----------------------------------------------------
-        if need.any():
-            mp = ctypes.c_void_p(main.cuda_stream)
-            self.need[:] = need
-            _check(L.dge_graph_host(eng._h, self.t_need.data_ptr(), ctypes.byref(env.graph.c), ctypes.byref(self._ho), mp), "dge_graph_host")
-            ng, n, e = (int(v) for v in self.t_tot[:3])
-            lap("policy: dge_graph_host (2 syncs)")
-            self.launches += 4
-            self.h2d += B
-            self.d2h += 32 + n * 20 + e * 20 + (2 * ng + 2) * 4 + 2 * ng * 4 + self.t_fxy.nbytes + (n + 1) * 4 + e * 8 + n * 4
+        if do_policy:
+            from . import gnn
+            from .data import Data
+            if self.packed:
+                pk = self._pk
+                _check(L.dge_graph_host_packed_end(eng._h, self.a_pack.data_ptr(), self.a_host.data_ptr(), self.arena_cap, ctypes.byref(pk), mp),
+                       "dge_graph_host_packed_end")
+                ng, n, e, tot = pk.n_graphs, pk.n_nodes, pk.n_edges, pk.total_bytes
+                lap("policy: graph D2H (2 syncs)")
+                self.d2h += tot
+            else:
+                self.need[:] = need
+                _check(L.dge_graph_host(eng._h, self.t_need.data_ptr(), ctypes.byref(env.graph.c), ctypes.byref(self._ho), mp), "dge_graph_host")
+                ng, n, e = (int(v) for v in self.t_tot[:3])
+                lap("policy: dge_graph_host (2 syncs)")
+                self.launches += 4
+                self.h2d += B
+                self.d2h += 32 + n * 20 + e * 20 + (2 * ng + 2) * 4 + 2 * ng * 4 + self.t_fxy.nbytes + (n + 1) * 4 + e * 8 + n * 4
             if ng > 0:
-                from . import gnn
-                from .data import Data
                 # the policy gets the HOST graph batch, like DeepQ.test: data.to(device) -> model -> Q back on the host
-                up = lambda t: t.to(self.dev, non_blocking=True)
-                x, ei, ea = up(self.t_x[:n]), up(self.t_ei[:2 * e].view(2, e)), up(self.t_ea[:e])
-                data = Data(x, ei, ea)
-                # the batch's CSR + GCN normalisation travelled with it (dge_graph_host_out): adopt instead of rebuilding
-                data._dge_structure = gnn.GraphStructure.from_csr(ei, ea, n, up(self.t_rowptr[:n + 1]), up(self.t_perm[:max(e, 1)]),
-                                                                  up(self.t_norm[:max(e, 1)]), up(self.t_selfnorm[:n]))
-                self.h2d += n * 20 + e * 20 + (n + 1) * 4 + e * 8 + n * 4
+                if self.packed:
+                    self.a_dev[:tot].copy_(self.a_host[:tot], non_blocking=True)          # ONE H2D for the whole batch
+                    f32, i32, i64 = torch.float32, torch.int32, torch.int64
+                    dv = lambda off, cnt, dt, sz: self.a_dev[off:off + cnt * sz].view(dt)
+                    x, ei, ea = dv(pk.x, n * 5, f32, 4).view(n, 5), dv(pk.edge_index, 2 * e, i64, 8).view(2, e), dv(pk.edge_attr, e, f32, 4)
+                    data = Data(x, ei, ea)
+                    data._dge_structure = gnn.GraphStructure.from_csr(ei, ea, n, dv(pk.csr_rowptr, n + 1, i32, 4), dv(pk.csr_perm, max(e, 1), i32, 4),
+                                                                      dv(pk.gcn_norm, max(e, 1), f32, 4), dv(pk.gcn_selfnorm, n, f32, 4))
+                    self.h2d += tot
+                    hv = lambda off, cnt, dt, sz: self.a_host[off:off + cnt * sz].view(dt).numpy()
+                    ks, fs = hv(pk.key_size, ng, i32, 4).astype(np.int64), hv(pk.fro_size, ng, i32, 4).astype(np.int64)
+                    nptr = hv(pk.node_ptr, ng, i32, 4).astype(np.int64)
+                    fxy_g = hv(pk.frontier_xy, ng * (eng.Lt + 1) * 2, torch.float64, 8).reshape(ng, eng.Lt + 1, 2)
+                else:
+                    up = lambda t: t.to(self.dev, non_blocking=True)
+                    x, ei, ea = up(self.t_x[:n]), up(self.t_ei[:2 * e].view(2, e)), up(self.t_ea[:e])
+                    data = Data(x, ei, ea)
+                    # the batch's CSR + GCN normalisation travelled with it (dge_graph_host_out): adopt instead of rebuilding
+                    data._dge_structure = gnn.GraphStructure.from_csr(ei, ea, n, up(self.t_rowptr[:n + 1]), up(self.t_perm[:max(e, 1)]),
+                                                                      up(self.t_norm[:max(e, 1)]), up(self.t_selfnorm[:n]))
+                    self.h2d += n * 20 + e * 20 + (n + 1) * 4 + e * 8 + n * 4
+                    ks, fs, nptr = self.ks[:ng].astype(np.int64), self.fs[:ng].astype(np.int64), self.nptr[:ng].astype(np.int64)
+                    fxy_g = None
                 l0 = gnn.launch_count
                 lap("policy: H2D graph")
                 q = self.model(data, 0.0).view(-1)
@@ -231,14 +280,13 @@ class HostPolicyLoop:
                 self.launches += gnn.launch_count - l0
                 self.d2h += n * 4
                 # arg-max over the last fro_size nodes of every graph (test.py:112), vectorised with a padded gather
-                ks, fs, nptr = self.ks[:ng].astype(np.int64), self.fs[:ng].astype(np.int64), self.nptr[:ng].astype(np.int64)
                 idx = (nptr + ks)[:, None] + self._frange[None, :]
                 valid = self._frange[None, :] < fs[:, None]
                 vals = np.where(valid, self.q[np.minimum(idx, n - 1)], -np.inf)
                 choice = vals.argmax(axis=1)
                 envs = np.nonzero(need)[0]
                 choice = np.where(fs > 0, choice, 0)
-                self.goal[envs] = self.fxy[envs, choice]
+                self.goal[envs] = self.fxy[envs, choice] if fxy_g is None else fxy_g[np.arange(ng), choice]
                 nofro = envs[fs <= 0]
                 if nofro.size:                    # no frontier left (q15): episode over -- mask value 2 sets the done flag
                     self.need[nofro] = 2

@@ -225,6 +225,23 @@ typedef struct dge_graph_host_out {
 } dge_graph_host_out;
 int dge_graph_host(dge_handle h, const uint8_t *mask_host, const dge_graph_out *dev, const dge_graph_host_out *host, void *stream);
 
+/* packed variant: the same batch behind ONE transfer per direction.  `begin` launches the graph kernels and a pack kernel
+ * that gathers the valid prefix of every array into `arena_dev` (caller-owned device bytes, >= dge_graph_packed_capacity)
+ * and returns without synchronising, so the caller can launch other work (the step of the other envs) meanwhile; `end`
+ * synchronises, copies header + payload into `arena_host` (pinned) in one D2H and reports the layout: byte offsets of
+ * the sections (16-byte aligned) -- x [N,5] f32, edge_index [2,E] i64 contiguous, edge_attr [E] f32, node_ptr / edge_ptr
+ * [G+1] i32, key_size / fro_size [G] i32, frontier_xy [G,Fmax,2] f64 (by GRAPH ordinal, unlike dge_graph_out), csr_rowptr
+ * [N+1] i32, csr_perm [E] i32, gcn_norm [E] f32, gcn_selfnorm [N] f32.  Sending `arena_host[:total_bytes]` back to a device
+ * buffer gives the GNN its inputs with the same offsets (what DeepQ.test's data.to(device) does, policy.py:255-259).  */
+typedef struct dge_graph_packed {
+  int64_t total_bytes;
+  int64_t x, edge_index, edge_attr, node_ptr, edge_ptr, key_size, fro_size, frontier_xy, csr_rowptr, csr_perm, gcn_norm, gcn_selfnorm;
+  int32_t n_graphs, n_nodes, n_edges, n_done;
+} dge_graph_packed;
+int64_t dge_graph_packed_capacity(dge_handle h, const dge_graph_out *dev);
+int dge_graph_host_packed_begin(dge_handle h, const uint8_t *mask_host, const dge_graph_out *dev, void *arena_dev, int64_t arena_cap, void *stream);
+int dge_graph_host_packed_end(dge_handle h, const void *arena_dev, void *arena_host, int64_t arena_cap, dge_graph_packed *out, void *stream);
+
 /* writes dge_state_view.pending: 1 for the envs that need a decision right now (action queue empty, episode
  * running, no forced reset steps outstanding) -- the selection the acting loop of policy.py:236-306 makes,
  * evaluated on the device; pass it as mask_dev to dge_graph.                                            */

@@ -53,6 +53,17 @@ int dge_gemm_prep_weight(int K, int N, const float *W, float *Wt_hi, float *Wt_l
 int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, const float *Bt_hi,
                     const float *Bt_lo, float *C, int ldc, void *stream);
 
+
+/* ---- the whole DQN Q-network forward at inference (Networks.GCN.forward with prob = 0, Networks.py:18-28: two
+ * GCNConv(improved) + ReLU and the Linear(C,1) head) in ONE call / three launches: fused first layer with the TF32 split
+ * in its epilogue -> dge_gemm_tf32x3 -> aggregate + bias + ReLU + head.  rowptr/perm = destination-sorted CSR, src =
+ * edge_index[0], norm/selfnorm from dge_gcn_norm (or the graph kernel), W1 [Cin,C], W2t_hi/lo = dge_gemm_prep_weight of
+ * conv2.weight, head_w [C], head_b_dev [1] on the device (nullable), ws >= 3*N*C floats (16-byte aligned), q [N].   */
+int dge_gcn_q_forward(int N, int Cin, int C, const float *x, const int32_t *rowptr, const int32_t *perm, const int64_t *src,
+                      const float *norm, const float *selfnorm, const float *W1, const float *b1, const float *W2t_hi,
+                      const float *W2t_lo, const float *b2, const float *head_w, const float *head_b_dev, float *ws, float *q,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

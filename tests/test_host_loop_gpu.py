@@ -19,8 +19,8 @@ def _mk(n, seed0=300):
     return env
 
 
-@pytest.mark.parametrize("overlap", [False, True])
-def test_host_loop_matches_device_loop(overlap):
+@pytest.mark.parametrize("overlap,packed", [(False, True), (True, True), (True, False)])
+def test_host_loop_matches_device_loop(overlap, packed):
     from drl_graph_exploration_b200 import Networks
     from drl_graph_exploration_b200.runner import HostPolicyLoop, PolicyLoop
     a, b = _mk(24), _mk(24)
@@ -28,6 +28,7 @@ def test_host_loop_matches_device_loop(overlap):
     model = Networks.GCN().to(a.device).eval()
     dev_loop = PolicyLoop(a, model, overlap=overlap)
     host_loop = HostPolicyLoop(b, model, overlap=overlap)
+    host_loop.packed = packed                      # one packed transfer per direction (default) / one copy per array
     K = 120                                        # long enough for several episodes to end and restart in-pipeline
     for _ in range(K):
         dev_loop.tick()
@@ -72,4 +73,36 @@ def test_graph_host_equals_device_graph():
     assert torch.equal(loop.t_nptr[:ng + 1], g.node_ptr[:ng + 1].cpu())
     assert torch.equal(loop.t_ks[:ng], g.key_size[:ng].cpu()) and torch.equal(loop.t_fs[:ng], g.fro_size[:ng].cpu())
     assert torch.equal(loop.t_fxy, g.frontier_xy.cpu())
+    env.close()
+
+
+def test_packed_graph_transfer_equals_device_graph():
+    """dge_graph_host_packed_begin/end: every section of the arena is the valid prefix of the device batch (frontier
+    coordinates by graph ordinal), and the header reports the totals."""
+    import ctypes
+    from drl_graph_exploration_b200 import Networks
+    from drl_graph_exploration_b200.runner import HostPolicyLoop
+    env = _mk(8, seed0=11)
+    loop = HostPolicyLoop(env, Networks.GCN().to(env.device).eval(), overlap=False)
+    loop.need[:] = 1
+    loop.need[5] = 0
+    mp = ctypes.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+    L, pk, g = loop._L, loop._pk, env.graph
+    assert L.dge_graph_host_packed_begin(env.eng._h, loop.t_need.data_ptr(), ctypes.byref(g.c), loop.a_pack.data_ptr(), loop.arena_cap, mp) == 0
+    assert L.dge_graph_host_packed_end(env.eng._h, loop.a_pack.data_ptr(), loop.a_host.data_ptr(), loop.arena_cap, ctypes.byref(pk), mp) == 0
+    ng, n, e = pk.n_graphs, pk.n_nodes, pk.n_edges
+    assert ng == 7 and n > 0 and e > 0 and pk.total_bytes <= loop.arena_cap
+    hv = lambda off, cnt, dt, sz: loop.a_host[off:off + cnt * sz].view(dt)
+    f32, i32, i64, f64 = torch.float32, torch.int32, torch.int64, torch.float64
+    assert torch.equal(hv(pk.x, n * 5, f32, 4).view(n, 5), g.x[:n].cpu())
+    assert torch.equal(hv(pk.edge_index, 2 * e, i64, 8).view(2, e), g.edge_index[:, :e].cpu())
+    assert torch.equal(hv(pk.edge_attr, e, f32, 4), g.edge_attr[:e].cpu())
+    assert torch.equal(hv(pk.node_ptr, ng + 1, i32, 4), g.node_ptr[:ng + 1].cpu()) and torch.equal(hv(pk.edge_ptr, ng + 1, i32, 4), g.edge_ptr[:ng + 1].cpu())
+    assert torch.equal(hv(pk.key_size, ng, i32, 4), g.key_size[:ng].cpu()) and torch.equal(hv(pk.fro_size, ng, i32, 4), g.fro_size[:ng].cpu())
+    envs = [b for b in range(8) if b != 5]
+    assert torch.equal(hv(pk.frontier_xy, ng * (env.eng.Lt + 1) * 2, f64, 8).view(ng, env.eng.Lt + 1, 2), g.frontier_xy[envs].cpu())
+    assert torch.equal(hv(pk.csr_rowptr, n + 1, i32, 4), g.csr_rowptr[:n + 1].cpu()) and torch.equal(hv(pk.csr_perm, e, i32, 4), g.csr_perm[:e].cpu())
+    assert torch.equal(hv(pk.gcn_norm, e, f32, 4), g.gcn_norm[:e].cpu()) and torch.equal(hv(pk.gcn_selfnorm, n, f32, 4), g.gcn_selfnorm[:n].cpu())
+    hdr = loop.a_host[:48].view(i64)
+    assert hdr[:3].tolist() == [ng, n, e] and int(hdr[5]) == pk.total_bytes
     env.close()
