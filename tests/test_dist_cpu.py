@@ -41,3 +41,73 @@ def test_shard_and_flat_allreduce():
     assert (lo0, hi0, lo1, hi1) == (0, 5, 5, 10)
     assert torch.equal(f0, f1)                                     # replicas stay identical
     assert torch.allclose(f0, ((l0 + l1) / 2).clamp(-0.5, 0.5))   # mean, THEN clamp
+
+
+class _TinyQ(torch.nn.Module):
+    """Stand-in with the Networks.GCN call signature (the CUDA GNN kernels need a GPU; the collective does not)."""
+
+    def __init__(self):
+        super().__init__()
+        self.l1, self.l2 = torch.nn.Linear(5, 16), torch.nn.Linear(16, 1)
+
+    def forward(self, data, prob, batch=None):
+        return self.l2(torch.relu(self.l1(data.x)))
+
+
+def _graphs(seed, n_graphs):
+    from drl_graph_exploration_b200.data import Batch, Data
+    g = torch.Generator().manual_seed(seed)
+    items = [Data(torch.randn(int(n), 5, generator=g), torch.zeros(2, 0, dtype=torch.long), torch.zeros(0)) for n in torch.randint(3, 9, (n_graphs,), generator=g)]
+    return Batch.from_data_list(items)
+
+
+def _train_worker(rank, world, port, q):
+    from drl_graph_exploration_b200.policy import DeepQ
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = _TinyQ()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    dq = DeepQ()
+    for step in range(3):                       # DeepQ.train: forward, loss, backward, ONE all-reduce, clamp, Adam
+        b = _graphs(100 * step + rank, 4)       # every rank trains on its own minibatch
+        n = b.x.size(0)
+        a = torch.zeros(n); a[::3] = 1.0
+        y = torch.linspace(-1, 1, n) * a
+        dq.train(b, a, y, torch.device("cpu"), model, opt)
+    q.put((rank, torch.cat([p.detach().flatten() for p in model.parameters()])))
+    dist.destroy_process_group()
+
+
+def test_dqn_train_step_keeps_replicas_identical_and_equals_averaged_gradients():
+    from drl_graph_exploration_b200.policy import DeepQ
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert torch.equal(res[0][1], res[1][1])                       # replicas identical after 3 steps
+    # single-process restatement: average the two ranks' gradients, clamp, Adam
+    torch.manual_seed(0)
+    model = _TinyQ()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    dq = DeepQ()
+    for step in range(3):
+        grads = []
+        for rank in range(2):
+            b = _graphs(100 * step + rank, 4)
+            n = b.x.size(0)
+            a = torch.zeros(n); a[::3] = 1.0
+            y = torch.linspace(-1, 1, n) * a
+            model.zero_grad()
+            dq.cost(model(b, 0.5), y, a).backward()
+            grads.append([p.grad.clone() for p in model.parameters()])
+        for p, g0, g1 in zip(model.parameters(), *grads):
+            p.grad = ((g0 + g1) / 2).clamp(-0.5, 0.5)
+        opt.step()
+    ref = torch.cat([p.detach().flatten() for p in model.parameters()])
+    assert torch.allclose(res[0][1], ref, rtol=1e-5, atol=1e-7)
