@@ -103,9 +103,11 @@ class GatedGraphConv(torch.nn.Module):
 
     def forward(self, x, gs: gnn.GraphStructure):
         h = x if x.size(1) == self.out_channels else torch.cat([x, x.new_zeros(x.size(0), self.out_channels - x.size(1))], dim=1)
+        native = (not torch.is_grad_enabled() and _PRECISION == "tc3" and h.is_cuda and self.out_channels % 4 == 0 and self.rnn.bias)
         for i in range(self.num_layers):
             m = gnn.weighted_aggregate(_mm(h, self.weight[i]), gs)
-            h = self.rnn(m, h)
+            # inference: the GRU's two transforms on the tcgen05 GEMM + one gate kernel; under autograd: torch's GRUCell
+            h = gnn.gru_cell_inference(m, h, self.rnn) if native else self.rnn(m, h)
         return h
 
 

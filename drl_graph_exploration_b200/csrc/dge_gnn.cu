@@ -176,7 +176,7 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 }  // namespace
 
 extern "C" int dge_gnn_csr_build(int N, int E, const int64_t *key, int32_t *rowptr, int32_t *perm, int32_t *ws /*[2N+E]*/, void *stream) {
-  if (N <= 0 || E < 0 || !key || !rowptr || !perm || !ws) return -1;
+  if (N <= 0 || E < 0 || (E > 0 && !key) || !rowptr || !perm || !ws) return -1;   // an edgeless batch is legal: every row empty
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(ws, 0, sizeof(int32_t) * 2 * (size_t)N, st) != cudaSuccess) return -2;
   if (E > 0) k_count<<<cdiv(E, 256), 256, 0, st>>>(E, key, ws);
@@ -280,7 +280,7 @@ extern "C" int dge_gcn_q_forward(int N, int Cin, int C, const float *x, const in
                                  const float *norm, const float *selfnorm, const float *W1, const float *b1, const float *W2t_hi,
                                  const float *W2t_lo, const float *b2, const float *head_w, const float *head_b_dev, float *ws, float *q,
                                  void *stream) {
-  if (N <= 0 || Cin <= 0 || Cin > 8 || C <= 0 || C > 1024 || (C & 3) || !x || !rowptr || !perm || !src || !norm || !selfnorm || !W1 || !W2t_hi ||
+  if (N <= 0 || Cin <= 0 || Cin > 8 || C <= 0 || C > 1024 || (C & 3) || !x || !rowptr || !perm || !selfnorm || !W1 || !W2t_hi ||
       !W2t_lo || !head_w || !ws || !q || ((uintptr_t)ws & 15))
     return -1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -290,5 +290,54 @@ extern "C" int dge_gcn_q_forward(int N, int Cin, int C, const float *x, const in
   const int rc = dge_gemm_tf32x3(N, nullptr, C, C, h_hi, h_lo, W2t_hi, W2t_lo, xw, C, stream);
   if (rc) return rc;
   k_aggregate<true><<<N, 256, 0, st>>>(N, C, xw, rowptr, perm, src, norm, selfnorm, b2, nullptr, 1, nullptr, head_w, 0.f, q, head_b_dev);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ------------------------------------------------------------------ GRU cell gates (GG-NN) ---------------------
+// torch.nn.GRUCell after its two dense transforms (GatedGraphConv.forward -> self.rnn(m, h), Networks.py:73-86 via PyG):
+//   r = sigmoid(gi_r + b_ir + gh_r + b_hr),  z = sigmoid(gi_z + b_iz + gh_z + b_hz),
+//   n = tanh(gi_n + b_in + r * (gh_n + b_hn)),  h' = (1 - z) * n + z * h          (gate order r | z | n along 3C)
+// gi = m W_ih^T and gh = h W_hh^T come from the tensor-core GEMM; this kernel is the HBM-bound rest: 7C floats in, C out
+// per node, float4 lanes, optional fused ReLU on the output (the activation GGNN applies after the last layer).
+namespace {
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
+__global__ void __launch_bounds__(256) k_gru_gates(int64_t n4, int C4, const float4 *__restrict__ gi, const float4 *__restrict__ gh,
+                                                   const float4 *__restrict__ b_ih, const float4 *__restrict__ b_hh,
+                                                   const float4 *__restrict__ h, int relu, float4 *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int64_t row = i / C4;
+  const int c = (int)(i - row * C4);
+  const int64_t g0 = row * 3 * C4 + c;
+  auto ld = [](const float4 *p, int64_t k) { return p[k]; };
+  const float4 ir = ld(gi, g0), iz = ld(gi, g0 + C4), in_ = ld(gi, g0 + 2 * C4);
+  const float4 hr = ld(gh, g0), hz = ld(gh, g0 + C4), hn = ld(gh, g0 + 2 * C4);
+  const float4 bir = b_ih[c], biz = b_ih[C4 + c], bin = b_ih[2 * C4 + c];
+  const float4 bhr = b_hh[c], bhz = b_hh[C4 + c], bhn = b_hh[2 * C4 + c];
+  const float4 hv = h[i];
+  auto cell = [&](float ir_, float iz_, float in2, float hr_, float hz_, float hn_, float b0, float b1, float b2, float c0, float c1, float c2, float hp) {
+    const float r = sigmoidf_((ir_ + b0) + (hr_ + c0));
+    const float z = sigmoidf_((iz_ + b1) + (hz_ + c1));
+    const float n = tanhf((in2 + b2) + r * (hn_ + c2));
+    const float o = (1.0f - z) * n + z * hp;
+    return relu ? fmaxf(o, 0.f) : o;
+  };
+  float4 o;
+  o.x = cell(ir.x, iz.x, in_.x, hr.x, hz.x, hn.x, bir.x, biz.x, bin.x, bhr.x, bhz.x, bhn.x, hv.x);
+  o.y = cell(ir.y, iz.y, in_.y, hr.y, hz.y, hn.y, bir.y, biz.y, bin.y, bhr.y, bhz.y, bhn.y, hv.y);
+  o.z = cell(ir.z, iz.z, in_.z, hr.z, hz.z, hn.z, bir.z, biz.z, bin.z, bhr.z, bhz.z, bhn.z, hv.z);
+  o.w = cell(ir.w, iz.w, in_.w, hr.w, hz.w, hn.w, bir.w, biz.w, bin.w, bhr.w, bhz.w, bhn.w, hv.w);
+  out[i] = o;
+}
+}  // namespace
+
+extern "C" int dge_gru_gates(int N, int C, const float *gi, const float *gh, const float *b_ih, const float *b_hh, const float *h, int relu,
+                             float *out, void *stream) {
+  if (N <= 0 || C <= 0 || (C & 3) || !gi || !gh || !b_ih || !b_hh || !h || !out) return -1;
+  if (((uintptr_t)gi | (uintptr_t)gh | (uintptr_t)b_ih | (uintptr_t)b_hh | (uintptr_t)h | (uintptr_t)out) & 15) return -1;
+  const int64_t n4 = (int64_t)N * (C / 4);
+  k_gru_gates<<<(unsigned)((n4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n4, C / 4, reinterpret_cast<const float4 *>(gi), reinterpret_cast<const float4 *>(gh), reinterpret_cast<const float4 *>(b_ih),
+      reinterpret_cast<const float4 *>(b_hh), reinterpret_cast<const float4 *>(h), relu, reinterpret_cast<float4 *>(out));
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -352,3 +352,27 @@ def gcn_q_forward(x: torch.Tensor, gs: GraphStructure, w1: torch.Tensor, b1, w2:
         raise DgeError(f"dge_gcn_q_forward failed ({rc})")
     launch_count += 3
     return q
+
+
+def gru_cell_inference(m: torch.Tensor, h: torch.Tensor, rnn: torch.nn.GRUCell, relu: bool = False) -> torch.Tensor:
+    """``rnn(m, h)`` of GatedGraphConv at inference: both dense transforms on the tcgen05 3xTF32 GEMM (the GRUCell weights
+    [3C, C] already are the K-major B operand), gate arithmetic in ``dge_gru_gates``."""
+    global launch_count
+    _need_cuda(m, "gru_cell_inference")
+    L = _gemm_lib()
+    if not hasattr(L, "_gru_ready"):
+        L.dge_gru_gates.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp]
+        L._gru_ready = True
+    ih_hi, ih_lo = _weight_operand(rnn.weight_ih, False)
+    hh_hi, hh_lo = _weight_operand(rnn.weight_hh, False)
+    m, h = m.contiguous().float(), h.contiguous().float()
+    gi, gh = _tc_gemm(m, ih_hi, ih_lo), _tc_gemm(h, hh_hi, hh_lo)
+    N, C = h.shape
+    out = torch.empty_like(h)
+    with torch.cuda.device(h.device):
+        rc = L.dge_gru_gates(N, C, _p(gi), _p(gh), _p(rnn.bias_ih.detach().contiguous()), _p(rnn.bias_hh.detach().contiguous()), _p(h), int(relu),
+                             _p(out), _st(h.device))
+    if rc:
+        raise DgeError(f"dge_gru_gates failed ({rc})")
+    launch_count += 1
+    return out

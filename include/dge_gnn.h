@@ -54,6 +54,12 @@ int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi
                     const float *Bt_lo, float *C, int ldc, void *stream);
 
 
+/* ---- GRU cell of the GG-NN family (torch.nn.GRUCell inside PyG GatedGraphConv, Networks.py:73-86): the gate arithmetic
+ * after the two dense transforms gi = m W_ih^T, gh = h W_hh^T [N,3C] (gate order r | z | n), biases [3C], previous state
+ * h [N,C] -> h' [N,C] (optionally ReLU'd).  C % 4 == 0, 16-byte aligned pointers.                                    */
+int dge_gru_gates(int N, int C, const float *gi, const float *gh, const float *b_ih, const float *b_hh, const float *h, int relu,
+                  float *out, void *stream);
+
 /* ---- the whole DQN Q-network forward at inference (Networks.GCN.forward with prob = 0, Networks.py:18-28: two
  * GCNConv(improved) + ReLU and the Linear(C,1) head) in ONE call / three launches: fused first layer with the TF32 split
  * in its epilogue -> dge_gemm_tf32x3 -> aggregate + bias + ReLU + head.  rowptr/perm = destination-sorted CSR, src =

@@ -215,3 +215,31 @@ def test_policy_and_value_heads_run():
     for cls in (Networks.PolicyGCN, Networks.ValueGCN, Networks.PolicyGGNN, Networks.ValueGGNN):
         out = cls().to(dev)(Data(batch.x, batch.edge_index, batch.edge_attr), mask, batch=batch.batch)
         assert torch.isfinite(out).all()
+
+
+def test_ggnn_inference_on_native_gru_path_matches_reference():
+    """GG-NN at inference: h W_i, the two GRUCell transforms (tcgen05 3xTF32 GEMM) and dge_gru_gates against the fp64
+    restatement of PyG's GatedGraphConv + torch GRUCell, with random and with the A2C-style dropout-free trunk."""
+    from drl_graph_exploration_b200 import Networks, gnn
+    from drl_graph_exploration_b200.data import Data
+    from oracle import gnn_ref
+
+    dev = torch.device("cuda")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    batch = _random_graph_batch(np.random.default_rng(4), 10, dev)
+    torch.manual_seed(2)
+    model = Networks.GGNN().to(dev).eval()
+    ref = gnn_ref.GGNN().double().to(dev)
+    ref.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    d32 = Data(batch.x, batch.edge_index, batch.edge_attr)
+    d64 = gnn_ref.Graph(batch.x.double(), batch.edge_index, batch.edge_attr.double())
+    with torch.no_grad():
+        l0 = gnn.launch_count
+        q = model(d32, 0.0).view(-1)                           # native path
+        launches = gnn.launch_count - l0
+        r = ref(d64, 0.0).view(-1)
+    q_autograd = model(Data(batch.x, batch.edge_index, batch.edge_attr), 0.0).view(-1).detach()   # torch GRUCell path
+    scale = r.abs().max()
+    assert (q.double() - r).abs().max() <= 1e-4 * scale, float((q.double() - r).abs().max() / scale)
+    assert (q - q_autograd).abs().max() <= 1e-4 * scale
+    assert launches >= 3 * (1 + 2 * 2 + 1 + 1)               # per layer: (split + GEMM) x 3 transforms, aggregate, gates
