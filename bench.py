@@ -36,8 +36,8 @@ WORKLOAD = f"{ENVS_PER_GPU} envs/GPU, {MAP_SIZE}x{MAP_SIZE} map, {N_LANDMARKS} l
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel in this workload, from the committed
 # `ncu --set full` captures (a number measured under the profiler is evidence for traffic, never a timing)
-NCU_TRAFFIC = {"slam": {"bytes": 6.6368e6 + 0.2383e6, "source": "profiles/r01_k_slam_v3_ncu.md"},
-               "vmap": {"bytes": None, "source": "profiles/ (k_vmap_env capture at this workload pending)"}}
+NCU_TRAFFIC = {"slam": {"bytes": 6.6368e6 + 0.2383e6, "source": "profiles/r01_k_slam_v3_ncu.md (mean T ~ 20; r01_k_slam_v5_ncu.md: 3.90 MB at mean T ~ 13)"},
+               "vmap": {"bytes": 0.64128e6, "source": "profiles/r01_k_vmap_env_bench_v5_ncu.md (mean T ~ 13; outputs still in L2 when the launch ends)"}}
 
 
 def peaks():
