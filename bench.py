@@ -245,10 +245,19 @@ def synth_graph_batch(n_graphs, sizes, rng, device, n_landmarks=8):
 
 
 def run_gnn(args):
+    rank, world, local, dist = _dist_setup()
+    out = measure_gnn(args, rank, world, local, dist)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_gnn(args, rank, world, local, dist, steps=None):
     """BASELINE configs[4] (C5): batches of 64 graphs with 8..512 nodes (mixed), GCN forward and forward+backward+Adam."""
     from drl_graph_exploration_b200 import Networks, gnn
     from drl_graph_exploration_b200.data import Data
-    rank, world, local, dist = _dist_setup()
+    n_steps = steps or args.steps
     dev = torch.device("cuda", local)
     rng = np.random.default_rng(1234 + rank)
     nb, G = 8, 64
@@ -290,7 +299,7 @@ def run_gnn(args):
         if world > 1:
             dist.barrier()
         evs, l0 = [], gnn.launch_count
-        for i in range(args.steps):
+        for i in range(n_steps):
             if flush is not None:
                 flush()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -306,23 +315,22 @@ def run_gnn(args):
         pk, pk_kind = peaks()
         sec_f, sec_b = res["forward"][0], res["forward_backward"][0]
         gemm_flops = 2.0 * nodes * 1000 * 1000                     # the one [N,1000]x[1000,1000] product of a forward pass
-        out = {"metric": "GNN samples/sec", "value": world * G * args.steps / sec_f, "unit": "graphs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": 1e3 * sec_f / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMM, fp32 accumulate)",
+        out = {"metric": "GNN samples/sec", "value": world * G * n_steps / sec_f, "unit": "graphs/s", "n_gpus": world, "steps": n_steps, "warmup": args.warmup,
+               "ms_per_step": 1e3 * sec_f / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMM, fp32 accumulate)",
                "data": "synthetic",
                "config": {"workload": "64 graphs/batch, 8..512 nodes mixed, GCN (BASELINE configs[4])", "mean_nodes_per_batch": nodes, "mean_edges_per_batch": edges,
                           "train_gemm": args.train_gemm, "l2": L2Flush.HOW if flush is not None else "not flushed"},
-               "forward": {"graphs_per_s": world * G * args.steps / sec_f, "nodes_per_s": world * nodes * args.steps / sec_f, "ms_per_batch": 1e3 * sec_f / args.steps,
-                           "fp32_equiv_tflops_whole_pass": (2.012e6 * nodes * args.steps / sec_f) / 1e12},
-               "forward_backward": {"graphs_per_s": world * G * args.steps / sec_b, "nodes_per_s": world * nodes * args.steps / sec_b, "ms_per_batch": 1e3 * sec_b / args.steps,
-                                    "fp32_equiv_tflops_whole_pass": (3 * 2.012e6 * nodes * args.steps / sec_b) / 1e12, "includes": "backward, gradient all-reduce, clamp, Adam"},
+               "forward": {"graphs_per_s": world * G * n_steps / sec_f, "nodes_per_s": world * nodes * n_steps / sec_f, "ms_per_batch": 1e3 * sec_f / n_steps,
+                           "fp32_equiv_tflops_whole_pass": (2.012e6 * nodes * n_steps / sec_f) / 1e12},
+               "forward_backward": {"graphs_per_s": world * G * n_steps / sec_b, "nodes_per_s": world * nodes * n_steps / sec_b, "ms_per_batch": 1e3 * sec_b / n_steps,
+                                    "fp32_equiv_tflops_whole_pass": (3 * 2.012e6 * nodes * n_steps / sec_b) / 1e12, "includes": "backward, gradient all-reduce, clamp, Adam"},
                "gpu_launches": res["forward"][1] + res["forward_backward"][1],
-               "roofline": {"bound": "tensor", "kernel": "k_gemm_tf32x3 inside the forward pass", "achieved": gemm_flops * args.steps / sec_f / 1e12, "peak": pk.get("bf16_tflops"),
-                            "peak_kind": pk_kind, "unit": "TFLOP/s", "frac": gemm_flops * args.steps / sec_f / 1e12 / pk.get("bf16_tflops", 1.0),
+               "roofline": {"bound": "tensor", "kernel": "k_gemm_tf32x3 inside the forward pass", "achieved": gemm_flops * n_steps / sec_f / 1e12, "peak": pk.get("bf16_tflops"),
+                            "peak_kind": pk_kind, "unit": "TFLOP/s", "frac": gemm_flops * n_steps / sec_f / 1e12 / pk.get("bf16_tflops", 1.0),
                             "note": "whole forward pass time in the denominator (GEMM + 2 aggregations + head), fp32-equivalent flops; the kernel alone: profiles/r01_k_gemm_tf32x3_ncu.md",
                             "traffic": None}}
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+        return out
+    return None
 
 
 # ------------------------------------------------------------------------- GPU arm ---
@@ -373,6 +381,7 @@ def main():
     ap.add_argument("--no-flush-l2", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gnn", action="store_true", help="skip the C5 GNN samples/sec measurement appended to the default line")
     ap.add_argument("--no-overlap", action="store_true", help="run the step and policy pipelines on one stream (A/B of the overlap)")
     ap.add_argument("--workload", default="policy", choices=["policy", "train", "gnn"],
                     help="policy = BASELINE configs[1] (the headline line); train = configs[2] DQN training; gnn = configs[4] GNN fwd / fwd+bwd")
@@ -497,6 +506,16 @@ def main():
                                "sample": f"{n_envs} of {ENVS_PER_GPU} envs x {nt} ticks ({dt:.1f} s): CPU CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN"}
     elif rank == 0:
         out["cpu_baseline"] = None
+    if not args.no_gnn:
+        # the second half of BASELINE's metric ("+ GNN samples/sec"): C5 batches through the GCN, forward and forward+backward
+        loop.env.close()
+        g = measure_gnn(args, rank, world, local, dist, steps=20)
+        if rank == 0:
+            out["gnn_c5"] = {"workload": g["config"]["workload"], "mean_nodes_per_batch": g["config"]["mean_nodes_per_batch"],
+                             "forward_graphs_per_s": g["forward"]["graphs_per_s"], "forward_ms_per_batch": g["forward"]["ms_per_batch"],
+                             "forward_backward_graphs_per_s": g["forward_backward"]["graphs_per_s"],
+                             "forward_backward_ms_per_batch": g["forward_backward"]["ms_per_batch"], "train_gemm": args.train_gemm,
+                             "tensor_roofline": g["roofline"]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
