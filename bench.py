@@ -488,7 +488,7 @@ def main():
             dt = float(et.item())
             out["e2e"] = {"value": float(es[0].item()) / dt, "unit": "env-steps/s", "h2d_bytes_per_step": float(es[1].item()) / n_e2e,
                           "d2h_bytes_per_step": float(es[2].item()) / n_e2e, "ticks": n_e2e, "ms_per_tick": 1e3 * dt / n_e2e,
-                          "api": "HostPolicyLoop: dge_step_host_async + dge_graph_host_packed_begin/end + dge_line_plan_host (pinned host buffers), wall clock, max over ranks"}
+                          "api": "HostPolicyLoop: dge_step_host_plans_async + dge_graph_host_packed_begin/end + dge_select_plan_host (pinned host buffers), wall clock, max over ranks"}
     elif rank == 0:
         out["e2e"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

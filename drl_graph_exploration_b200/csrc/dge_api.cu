@@ -83,6 +83,9 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.counters = al.get<unsigned long long>(4); e.count_steps = 1; e.park_done = 1;
   e.rdist = al.get<double>(B); e.r_cmap = al.get<int32_t>(B * 2); e.r_cbase = al.get<int32_t>(B); e.r_u0 = al.get<double>(B);
   if (al.ok && cudaMallocHost(reinterpret_cast<void **>(&e.pack_hdr_host), 16 * sizeof(int64_t)) != cudaSuccess) al.ok = false;
+  if (al.ok && cudaMallocHost(reinterpret_cast<void **>(&e.hp_odom), B * 3 * sizeof(double)) != cudaSuccess) al.ok = false;
+  if (al.ok && cudaMallocHost(reinterpret_cast<void **>(&e.hp_goal), B * 2 * sizeof(double)) != cudaSuccess) al.ok = false;
+  if (al.ok && cudaMallocHost(reinterpret_cast<void **>(&e.hp_mask), B) != cudaSuccess) al.ok = false;
   if (!al.ok) {
     for (void *p : al.ptrs) cudaFree(p);
     delete bx;
@@ -98,6 +101,9 @@ extern "C" int dge_destroy(dge_handle h) {
   cudaSetDevice(h->device);
   for (void *p : bx->al.ptrs) cudaFree(p);
   if (h->pack_hdr_host) cudaFreeHost(h->pack_hdr_host);
+  if (h->hp_odom) cudaFreeHost(h->hp_odom);
+  if (h->hp_goal) cudaFreeHost(h->hp_goal);
+  if (h->hp_mask) cudaFreeHost(h->hp_mask);
   delete bx;
   return DGE_OK;
 }
@@ -264,6 +270,54 @@ extern "C" int dge_graph_host(dge_handle h, const uint8_t *mask_host, const dge_
   if (!ok) return fail(DGE_ECUDA, "dge_graph_host: D2H graph");
   if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host: sync");
   return DGE_OK;
+}
+
+// ---- host-held action lists: "for act in actions: env.step(act)" (test.py:119-120, policy.py:117-118) for B envs.  The caller keeps
+// every env's line plan in the compact form of dge_line_plan and a cursor; action `cursor` is expanded here (Planner2D.cpp:982-1038).
+extern "C" int dge_step_host_plans_async(dge_handle h, const double *plans_host, const int64_t *cursor_host, const uint8_t *mask_host,
+                                         uint8_t *done_host, double *obs_host, double *metrics_host, int flags, void *stream) {
+  if (!h || !plans_host || !cursor_host) return DGE_EINVAL;
+  const int B = h->d.B;
+  const double pi = DGE_PI, edge = h->cfg.max_edge_length;
+  for (int b = 0; b < B; ++b) {
+    const double *pl = plans_host + 6 * (size_t)b;
+    const int64_t cur = cursor_host[b], nrot = (int64_t)pl[0], nfwd = (int64_t)pl[3];
+    double *od = h->hp_odom + 3 * (size_t)b;
+    od[0] = od[1] = od[2] = 0.0;
+    if (cur < nrot) od[2] = pl[1] * pi;
+    else if (cur == nrot) od[2] = pl[1] * pl[2];
+    else od[0] = (cur < nrot + 1 + nfwd) ? edge : pl[4];
+  }
+  return dge_step_host_async(h, h->hp_odom, mask_host, done_host, obs_host, metrics_host, flags, stream);
+}
+
+// ---- host-side policy read-out on a packed batch: np.argmax(readout_t[-fro_size:]) (test.py:112, policy.py:109) per graph, the chosen
+// frontier's coordinates as goal, line plan from the env's current estimate (actions_all_goals()[key_size + action_index]).
+extern "C" int dge_select_plan_host(dge_handle h, const void *arena_host, const dge_graph_packed *lay, const float *q_host, const uint8_t *mask_host,
+                                    double *plan_host, int32_t *choice_host, void *stream) {
+  if (!h || !arena_host || !lay || !q_host || !mask_host || !plan_host) return DGE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = h->d.B, Fmax = h->d.Fmax;
+  const unsigned char *ar = static_cast<const unsigned char *>(arena_host);
+  const int32_t *nptr = reinterpret_cast<const int32_t *>(ar + lay->node_ptr), *ks = reinterpret_cast<const int32_t *>(ar + lay->key_size);
+  const int32_t *fs = reinterpret_cast<const int32_t *>(ar + lay->fro_size);
+  const double *fxy = reinterpret_cast<const double *>(ar + lay->frontier_xy);
+  int g = 0;
+  for (int b = 0; b < B; ++b) {
+    h->hp_mask[b] = 0;
+    if (choice_host) choice_host[b] = -1;
+    if (!mask_host[b]) continue;
+    if (g >= lay->n_graphs) return fail(DGE_EINVAL, "dge_select_plan_host: mask selects more envs than the batch holds");
+    const int F = fs[g], n0 = nptr[g] + ks[g];
+    if (F <= 0) { h->hp_mask[b] = 2; ++g; continue; }       // no frontier left (q15): the episode is over
+    int best = 0;
+    for (int f = 1; f < F; ++f) if (q_host[n0 + f] > q_host[n0 + best]) best = f;   // first maximum, like np.argmax
+    h->hp_goal[2 * b] = fxy[((size_t)g * Fmax + best) * 2]; h->hp_goal[2 * b + 1] = fxy[((size_t)g * Fmax + best) * 2 + 1];
+    h->hp_mask[b] = 1;
+    if (choice_host) choice_host[b] = best;
+    ++g;
+  }
+  return dge_line_plan_host(h, h->hp_goal, h->hp_mask, plan_host, stream);
 }
 
 // ---- packed host transfer of a graph batch ---------------------------------------------------------------------

@@ -79,6 +79,9 @@ struct dge_engine {
   uint8_t *step_kind;    // [B] 1 = the env's last step was a policy step
   uint8_t *pending;      // [B] envs that need a decision (dge_mark_pending)
   int64_t *pack_hdr_host; // [16] pinned: header of the last packed graph batch (dge_graph_host_packed_*)
+  double *hp_odom;        // [B,3] pinned staging: actions expanded from host plans (dge_step_host_plans_async)
+  double *hp_goal;        // [B,2] pinned staging: goals chosen on the host (dge_select_plan_host)
+  uint8_t *hp_mask;       // [B]   pinned staging: mask of dge_select_plan_host (value 2 = no frontier left)
   double forced_odom[3]; // host copy of the forced action (exploration_env.py:411-414)
   int count_steps;       // host flag: 1 while stepping on behalf of the policy (reset steps are not counted)
   int park_done;         // host flag: queued stepping skips `done` envs (1, default) or runs every plan to its end (0, roll-out engines)

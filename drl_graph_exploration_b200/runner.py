@@ -120,6 +120,8 @@ class HostPolicyLoop:
         L.dge_graph_packed_capacity.argtypes = [vp, vp]
         L.dge_graph_host_packed_begin.argtypes = [vp, vp, vp, vp, ctypes.c_int64, vp]
         L.dge_graph_host_packed_end.argtypes = [vp, vp, vp, ctypes.c_int64, vp, vp]
+        L.dge_step_host_plans_async.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.dge_select_plan_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
         f64, f32, i32, i64, u8 = torch.float64, torch.float32, torch.int32, torch.int64, torch.uint8
         # step-side host buffers
@@ -145,6 +147,7 @@ class HostPolicyLoop:
         self._pk = _Packed()
         self.packed = True
         self.t_q = pin((g.node_cap,), f32)
+        self.t_choice = pin((B,), i32)
         self.t_rowptr, self.t_perm = pin((g.node_cap + 1,), i32), pin((g.edge_cap,), i32)
         self.t_norm, self.t_selfnorm = pin((g.edge_cap,), f32), pin((g.node_cap,), f32)
 
@@ -153,7 +156,7 @@ class HostPolicyLoop:
                                           "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm")]
         self._ho = _HostOut(*(t.data_ptr() for t in (self.t_x, self.t_ei, self.t_ea, self.t_nptr, self.t_eptr, self.t_ks, self.t_fs, self.t_fxy, self.t_tot,
                                                      self.t_rowptr, self.t_perm, self.t_norm, self.t_selfnorm)))
-        for name in ("odom", "mask", "done", "metrics", "need", "nptr", "ks", "fs", "fxy", "goal", "plan", "q"):
+        for name in ("odom", "mask", "done", "metrics", "need", "nptr", "ks", "fs", "fxy", "goal", "plan", "q", "choice"):
             setattr(self, name, getattr(self, "t_" + name).numpy())
         # host-side action lists in the compact form of dge_line_plan: (n_rot_pi, sign, rot_rem, n_fwd, fwd_rem, n_actions)
         self.plans = np.zeros((B, 6)); self.cursor = np.zeros(B, dtype=np.int64)
@@ -215,10 +218,15 @@ class HostPolicyLoop:
         # ---- step pipeline (async on s1): reset finished episodes, then one simulator step from host actions ------
         sp = ctypes.c_void_p(s1.cuda_stream)
         _check(L.dge_reset_done_queued(eng._h, self.seed_stride, self._fo, 4, sp), "dge_reset_done_queued")
-        self._next_actions()
         self.mask[:] = has_act | in_reset
-        _check(L.dge_step_host_async(eng._h, self.t_odom.data_ptr(), self.t_mask.data_ptr(), self.t_done.data_ptr(),
-                                     None if self.t_obs is None else self.t_obs.data_ptr(), self.t_metrics.data_ptr(), 1 | 2, sp), "dge_step_host_async")
+        if self.packed:   # the action lists stay in their compact form; action `cursor` is expanded inside the call
+            _check(L.dge_step_host_plans_async(eng._h, self.plans.ctypes.data, self.cursor.ctypes.data, self.t_mask.data_ptr(), self.t_done.data_ptr(),
+                                               None if self.t_obs is None else self.t_obs.data_ptr(), self.t_metrics.data_ptr(), 1 | 2, sp),
+                   "dge_step_host_plans_async")
+        else:
+            self._next_actions()
+            _check(L.dge_step_host_async(eng._h, self.t_odom.data_ptr(), self.t_mask.data_ptr(), self.t_done.data_ptr(),
+                                         None if self.t_obs is None else self.t_obs.data_ptr(), self.t_metrics.data_ptr(), 1 | 2, sp), "dge_step_host_async")
         self.launches += 6
         self.h2d += self.t_odom.nbytes + B
         self.d2h += B + self.t_metrics.nbytes + (0 if self.t_obs is None else self.t_obs.nbytes)
@@ -256,10 +264,6 @@ class HostPolicyLoop:
                     data._dge_structure = gnn.GraphStructure.from_csr(ei, ea, n, dv(pk.csr_rowptr, n + 1, i32, 4), dv(pk.csr_perm, max(e, 1), i32, 4),
                                                                       dv(pk.gcn_norm, max(e, 1), f32, 4), dv(pk.gcn_selfnorm, n, f32, 4))
                     self.h2d += tot
-                    hv = lambda off, cnt, dt, sz: self.a_host[off:off + cnt * sz].view(dt).numpy()
-                    ks, fs = hv(pk.key_size, ng, i32, 4).astype(np.int64), hv(pk.fro_size, ng, i32, 4).astype(np.int64)
-                    nptr = hv(pk.node_ptr, ng, i32, 4).astype(np.int64)
-                    fxy_g = hv(pk.frontier_xy, ng * (eng.Lt + 1) * 2, torch.float64, 8).reshape(ng, eng.Lt + 1, 2)
                 else:
                     up = lambda t: t.to(self.dev, non_blocking=True)
                     x, ei, ea = up(self.t_x[:n]), up(self.t_ei[:2 * e].view(2, e)), up(self.t_ea[:e])
@@ -269,7 +273,6 @@ class HostPolicyLoop:
                                                                       up(self.t_norm[:max(e, 1)]), up(self.t_selfnorm[:n]))
                     self.h2d += n * 20 + e * 20 + (n + 1) * 4 + e * 8 + n * 4
                     ks, fs, nptr = self.ks[:ng].astype(np.int64), self.fs[:ng].astype(np.int64), self.nptr[:ng].astype(np.int64)
-                    fxy_g = None
                 l0 = gnn.launch_count
                 lap("policy: H2D graph")
                 q = self.model(data, 0.0).view(-1)
@@ -279,14 +282,30 @@ class HostPolicyLoop:
                 lap("policy: Q D2H (sync)")
                 self.launches += gnn.launch_count - l0
                 self.d2h += n * 4
+                envs = np.nonzero(need)[0]
+                if self.packed:
+                    # arg-max over the last fro_size nodes of every graph (test.py:112) + line plan of the chosen frontier, one native call
+                    _check(L.dge_select_plan_host(eng._h, self.a_host.data_ptr(), ctypes.byref(pk), self.t_q.data_ptr(), self.t_need.data_ptr(),
+                                                  self.t_plan.data_ptr(), self.t_choice.data_ptr(), mp), "dge_select_plan_host")
+                    lap("policy: dge_select_plan_host (sync)")
+                    choice = self.choice[envs].astype(np.int64)
+                    self.phase[envs[choice < 0]] = 5          # no frontier left (q15): episode over
+                    self.launches += 1
+                    self.h2d += self.t_goal.nbytes + B
+                    self.d2h += self.t_plan.nbytes
+                    self.plans[envs] = self.plan[envs]
+                    self.cursor[envs] = 0
+                    self.last_choice = (envs, choice)
+                    self.graphs += ng
+                    ng = 0                                    # (skips the per-array path below)
+            if ng > 0:
                 # arg-max over the last fro_size nodes of every graph (test.py:112), vectorised with a padded gather
                 idx = (nptr + ks)[:, None] + self._frange[None, :]
                 valid = self._frange[None, :] < fs[:, None]
                 vals = np.where(valid, self.q[np.minimum(idx, n - 1)], -np.inf)
                 choice = vals.argmax(axis=1)
-                envs = np.nonzero(need)[0]
                 choice = np.where(fs > 0, choice, 0)
-                self.goal[envs] = self.fxy[envs, choice] if fxy_g is None else fxy_g[np.arange(ng), choice]
+                self.goal[envs] = self.fxy[envs, choice]
                 nofro = envs[fs <= 0]
                 if nofro.size:                    # no frontier left (q15): episode over -- mask value 2 sets the done flag
                     self.need[nofro] = 2

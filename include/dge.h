@@ -124,6 +124,11 @@ int dge_step_host(dge_handle h, const double *odom_host, const uint8_t *mask_hos
 int dge_step_host_async(dge_handle h, const double *odom_host, const uint8_t *mask_host, uint8_t *done_host, double *obs_host,
                         double *metrics_host, int flags, void *stream);
 
+/* the same with the action lists held by the caller in the compact form of dge_line_plan: plans_host [B,6], cursor_host [B] =
+ * index of the action to execute ("for act in actions: env.step(act)", test.py:119-120 / policy.py:117-118, for B envs).  */
+int dge_step_host_plans_async(dge_handle h, const double *plans_host, const int64_t *cursor_host, const uint8_t *mask_host,
+                              uint8_t *done_host, double *obs_host, double *metrics_host, int flags, void *stream);
+
 /* ---- stand-alone virtual-map rebuild on caller-provided belief states (a6+a7;
  * VirtualMap::updateProbability + updateInformation).  n problems, T poses each.
  *   pose_dev [n,T,3], cov_dev [n,T,6] (upper triangle xx,xy,xt,yy,yt,tt of the pose
@@ -241,6 +246,12 @@ typedef struct dge_graph_packed {
 int64_t dge_graph_packed_capacity(dge_handle h, const dge_graph_out *dev);
 int dge_graph_host_packed_begin(dge_handle h, const uint8_t *mask_host, const dge_graph_out *dev, void *arena_dev, int64_t arena_cap, void *stream);
 int dge_graph_host_packed_end(dge_handle h, const void *arena_dev, void *arena_host, int64_t arena_cap, dge_graph_packed *out, void *stream);
+/* host-side policy read-out on such a batch: per selected env (mask_host as given to ..._begin) the first arg-max of q_host over
+ * the graph's last fro_size nodes (np.argmax(readout_t[-fro_size:]), test.py:112 / policy.py:109), the chosen frontier as goal and
+ * its line plan (actions_all_goals()[key_size + action_index]) into plan_host [B,6]; choice_host [B] nullable (-1: not selected
+ * or no frontier left -- that env's episode is declared over, quirk q15).  Synchronises `stream`.                         */
+int dge_select_plan_host(dge_handle h, const void *arena_host, const dge_graph_packed *layout, const float *q_host, const uint8_t *mask_host,
+                         double *plan_host, int32_t *choice_host, void *stream);
 
 /* writes dge_state_view.pending: 1 for the envs that need a decision right now (action queue empty, episode
  * running, no forced reset steps outstanding) -- the selection the acting loop of policy.py:236-306 makes,
