@@ -39,3 +39,13 @@ for ms, seeds in EPISODES.items():
         multi[f"g_{ms}_{s}"] = np.array(eps[s][:60])
 np.savez_compressed(os.path.join(OUT, "ref_DQN_GCN_multi.npz"), **multi)
 print("wrote", os.path.join(OUT, "ref_DQN_GCN_multi.npz"))
+
+# ref_state_dict_layouts.json : parameter names and shapes of the six shipped checkpoints (data/torch_weights/*/MyModel.pt):
+# the drop-in contract of Networks.py is that `model.load_state_dict(torch.load('MyModel.pt'))` works unchanged.
+import json
+layouts = {}
+for case in ("DQN_GCN", "DQN_GG-NN", "DQN_g-U-Net", "A2C_GCN", "A2C_GG-NN", "A2C_g-U-Net"):
+    sdc = torch.load(os.path.join(REF, "data/torch_weights", case, "MyModel.pt"), map_location="cpu", weights_only=False)
+    layouts[case] = {k: list(v.shape) for k, v in sdc.items()}
+json.dump(layouts, open(os.path.join(OUT, "ref_state_dict_layouts.json"), "w"), indent=1, sort_keys=True)
+print("wrote", os.path.join(OUT, "ref_state_dict_layouts.json"))

@@ -95,3 +95,21 @@ def test_a2c_objectives_and_nstep_batch():
     assert np.isclose(float(pc), lit / 40)
     assert np.isclose(float(ac.entropy_loss(prob)), -float((prob.log() * prob).sum()) / 40)
     assert np.isclose(float(ac.value_cost(torch.tensor([1.0, 2.0]), torch.tensor([0.0, 4.0]))), (1 + 4) / 2)
+
+
+def test_state_dict_layouts_match_the_shipped_checkpoints():
+    """Networks.py drop-in contract: the six shipped data/torch_weights/*/MyModel.pt load unchanged, i.e. parameter names and
+    shapes are the reference's (fixture tests/golden/ref_state_dict_layouts.json, written by make_golden.py)."""
+    import json
+    import os
+    from drl_graph_exploration_b200 import Networks
+    lay = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_state_dict_layouts.json")))
+    unet = dict(in_channels=5, hidden_channels=1000, out_channels=1000, depth=3)          # test.py:40,54
+    cases = {"DQN_GCN": Networks.GCN(), "DQN_GG-NN": Networks.GGNN(), "DQN_g-U-Net": Networks.GraphUNet(**unet),
+             "A2C_GCN": Networks.PolicyGCN(), "A2C_GG-NN": Networks.PolicyGGNN(), "A2C_g-U-Net": Networks.PolicyGraphUNet(**unet)}
+    for name, model in cases.items():
+        ours = {k: list(v.shape) for k, v in model.state_dict().items()}
+        assert ours == lay[name], (name, sorted(set(ours) ^ set(lay[name])))
+        # and what torch.save(policy_net.state_dict(), ...) writes (policy.py:192,205) has the same layout
+        sd = {k: torch.zeros(s) for k, s in lay[name].items()}
+        model.load_state_dict(sd)
