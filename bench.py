@@ -172,7 +172,7 @@ def run_train(args):
     env.reset()
     torch.manual_seed(0)                      # identical replicas on every rank
     pol, tgt = Networks.GCN().to(env.device), Networks.GCN().to(env.device)
-    tr = VecDQNTrainer(env, pol, tgt, observe=0, train_steps_per_tick=args.train_steps_per_tick, seed=rank)
+    tr = VecDQNTrainer(env, pol, tgt, observe=0, train_steps_per_tick=args.train_steps_per_tick, seed=rank, overlap=not args.no_overlap)
     for _ in range(40):                       # prefill the replay (untimed): every rank needs one minibatch of transitions
         tr.tick(learn=False)
     assert tr.replay.size >= tr.dqn.BATCH, "prefill too short"
@@ -209,7 +209,8 @@ def run_train(args):
                "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 simulator / f32 GNN",
                "data": "synthetic",
                "config": {"workload": f"{B} envs/GPU, {ms}x{ms} map, {cfg.n_landmarks} landmarks, DQN+GCN training (BASELINE configs[2])", "batch_graphs_per_rank": bsz,
-                          "train_steps_per_tick": args.train_steps_per_tick, "train_gemm": args.train_gemm, "replay": f"device ring, {tr.replay.capacity} transitions, {tr.replay.nbytes() / 2**30:.2f} GiB",
+                          "train_steps_per_tick": args.train_steps_per_tick, "train_gemm": args.train_gemm,
+                          "schedule": "gradient step on a second stream beside the roll-out kernels" if not args.no_overlap else "sequential", "replay": f"device ring, {tr.replay.capacity} transitions, {tr.replay.nbytes() / 2**30:.2f} GiB",
                           "collective": "one all-reduce of the 4.0 MB flat gradient bucket per gradient step" if world > 1 else "none (1 rank)"},
                "decisions_per_s": dec / sec, "train_steps_per_s": tsteps / sec / world, "rollout_clone_steps_per_s": None,
                "gnn_samples_per_s": {"forward_acting": dec / sec, "forward_target": tsteps * bsz / sec, "forward_backward": tsteps * bsz / sec},

@@ -37,7 +37,7 @@ from .replay import GraphReplay
 class VecDQNTrainer:
     def __init__(self, env: VecExplorationEnv, policy_net: torch.nn.Module, target_net: torch.nn.Module, dqn: DeepQ | None = None,
                  replay_capacity: int | None = None, train_steps_per_tick: int = 1, observe: int | None = None, lr: float = 1e-5,
-                 clone_slots: int | None = None, seed: int = 0):
+                 clone_slots: int | None = None, seed: int = 0, overlap: bool = False):
         self.env, self.policy_net, self.target_net = env, policy_net, target_net
         self.dqn = dqn or DeepQ()
         self.dev = env.device
@@ -51,6 +51,11 @@ class VecDQNTrainer:
         self.train_steps_per_tick = int(train_steps_per_tick)
         self.observe = int(self.dqn.OBSERVE if observe is None else observe)   # decisions before learning starts
         self.clone_slots = clone_slots
+        # overlap: the gradient step of a tick runs on a second stream beside the roll-out kernels of the same tick (it trains
+        # on the replay as of the previous tick and finishes before this tick's Q forward reads the weights)
+        self.overlap = bool(overlap)
+        self.s_learn = torch.cuda.Stream(self.dev) if self.overlap else None
+        self.ev_tick, self.ev_learn = torch.cuda.Event(), torch.cuda.Event()
         i64 = lambda v: torch.full((B,), v, dtype=torch.int64, device=self.dev)
         self.pend_slot, self.pend_a = i64(-1), i64(0)                  # in-flight transition of every env
         self.pend_r = torch.zeros(B, dtype=torch.float32, device=self.dev)
@@ -65,10 +70,14 @@ class VecDQNTrainer:
 
     # ---------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def _act(self):
-        """Step pipeline + decision round of one tick.  Returns the number of decisions taken."""
+    def _act(self, side_work=None):
+        """Step pipeline + decision round of one tick.  Returns the number of decisions taken.  ``side_work``: callable run
+        (on its own stream) once the step and roll-out kernels of this tick are queued, before the Q forward."""
         env, eng, rp, dqn = self.env, self.env.eng, self.replay, self.dqn
         st, dev = eng.state, self.dev
+        main = torch.cuda.current_stream(dev)
+        if side_work is not None:
+            self.ev_tick.record(main)                  # everything of the previous tick (replay writes, weight reads) is before this
         done_prev = st["done"].bool().clone()          # episodes that ended in the previous tick's step
         need = env.mark_pending().bool().clone()       # empty queue, not done, not in the reset phase
         # ---- step pipeline: restart finished episodes, one simulator step for every env with a queued action ----
@@ -93,6 +102,10 @@ class VecDQNTrainer:
                     self.rollout_steps += env.rollout_steps; self.rollout_clones += acc
                     lo, acc = i, 0
                 acc += f
+        if side_work is not None:
+            side_work()
+            main.wait_event(self.ev_learn)             # the weights and the replay are the gradient step's until it is done
+        if ng > 0:
             d = g.data()
             q = self.policy_net(d, float(self.epsilon))                     # functional dropout: "bayesian" exploration
             choice = env.select_and_plan(q, need.to(torch.uint8)).long()    # [B], valid where need
@@ -156,11 +169,25 @@ class VecDQNTrainer:
         self.train_steps += 1
         return self.last_loss
 
+    def _learn_beside(self):
+        with torch.enable_grad(), torch.cuda.stream(self.s_learn):
+            self.s_learn.wait_event(self.ev_tick)
+            for _ in range(self.train_steps_per_tick):
+                self.learn()
+            self.ev_learn.record(self.s_learn)
+
     def tick(self, learn: bool | None = None):
-        ng = self._act()
-        self.ticks += 1
+        """One tick.  Sequential mode: act, then ``train_steps_per_tick`` gradient steps.  Overlap mode: the gradient steps run
+        beside this tick's roll-outs on the replay as of the previous tick -- the same sequence of operations as the
+        sequential mode shifted by one tick (a sequential run of k learning ticks == one acting tick + k overlapped ticks)."""
         if learn is None:
             learn = self.dqn.step_t > self.observe and self.replay.size >= self.dqn.BATCH
+        if self.overlap:
+            ng = self._act(self._learn_beside if learn else None)
+            self.ticks += 1
+            return ng
+        ng = self._act()
+        self.ticks += 1
         if learn:
             for _ in range(self.train_steps_per_tick):
                 self.learn()

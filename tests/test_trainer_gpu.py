@@ -95,3 +95,29 @@ def test_minibatch_targets_equal_literal_restatement_and_learning_moves_the_poli
         tr.tick()
     assert tr.train_steps >= 8
     env.close()
+
+
+def test_overlapped_learning_equals_sequential_learning():
+    """overlap=True runs the gradient step of a tick on a second stream beside the roll-out kernels.  It is the sequential
+    schedule shifted by one tick, so k sequential learning ticks and (one acting tick + k overlapped ticks) must leave
+    bit-identical weights -- a missing event between the streams (weights, replay) would break the equality."""
+    def run(overlap):
+        torch.manual_seed(7); torch.cuda.manual_seed(7)
+        env, tr = _make(B=16, seed=500, overlap=overlap)
+        tr.dqn.BATCH = 16
+        for _ in range(25):
+            tr.tick(learn=False)
+        assert tr.replay.size >= 16
+        if overlap:
+            tr.tick(learn=False)
+        for _ in range(6):
+            tr.tick(learn=True)
+        torch.cuda.synchronize()
+        w = torch.cat([p.detach().flatten().clone() for p in tr.policy_net.parameters()])
+        out = (w, tr.train_steps, tr.last_loss)
+        env.close()
+        return out
+    w_seq, n_seq, l_seq = run(False)
+    w_ovl, n_ovl, l_ovl = run(True)
+    assert n_seq == n_ovl == 6
+    assert torch.equal(w_seq, w_ovl) and l_seq == l_ovl
