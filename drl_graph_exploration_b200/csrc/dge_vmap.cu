@@ -296,6 +296,7 @@ constexpr unsigned ST_UPD = 1u << 30, ST_LM = 1u << 31, ST_CNT = ST_UPD - 1;
 struct EnvArgs {
   VmapCfg c;
   int Tstride, Tfixed, Lstride, Lfixed, hw, W, hb;     // hw = ceil(max_range / res), W = 2 hw + 1, hb = rows per band
+  int bg;                                              // bands per CTA: gridDim.y CTAs share an env (0 / gridDim.y == 1: the whole map)
   const int32_t *n_poses;
   const double *pose, *cov, *info;                     // [n,Tstride,3], [n,Tstride,6], nullable [n,Tstride,6]
   double *prep;                                        // [n,Tstride,PREP_W] scratch (L1/L2 resident)
@@ -315,23 +316,36 @@ __global__ void __launch_bounds__(MAXT, MINB) k_vmap_env(EnvArgs a) {
   if (a.mask && !a.mask[b]) return;
   const VmapCfg &c = a.c;
   const int T = a.n_poses ? a.n_poses[b] : a.Tfixed;
-  const int V = c.rows * c.cols, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  // band group of this CTA: rows [row_lo, row_hi) of the map (the whole map when the env is not split).  The shared-memory
+  // arrays hold those rows only and are addressed with GLOBAL cell indices through pointers shifted by cbase.
+  const bool split = gridDim.y > 1;
+  const int band0 = split ? blockIdx.y * a.bg : 0;
+  const int row_lo = split ? min(c.rows, band0 * a.hb) : 0, row_hi = split ? min(c.rows, (band0 + a.bg) * a.hb) : c.rows;
+  const int cbase = row_lo * c.cols, V = (row_hi - row_lo) * c.cols;            // V = cells of this CTA
+  const int Vmax = split ? a.bg * a.hb * c.cols : c.rows * c.cols;              // array pitch (same for every group)
   extern __shared__ __align__(16) unsigned char vm_smem[];
-  double *sxx = reinterpret_cast<double *>(vm_smem), *sxy = sxx + V, *syy = sxy + V;
-  unsigned *sst = reinterpret_cast<unsigned *>(syy + V);          // count | ST_UPD | ST_LM
-  int *s_frow = reinterpret_cast<int *>(sst + ((V + 1) & ~1));     // [T] cell row of every pose
+  double *sxx0 = reinterpret_cast<double *>(vm_smem), *sxy0 = sxx0 + Vmax, *syy0 = sxy0 + Vmax;
+  unsigned *sst0 = reinterpret_cast<unsigned *>(syy0 + Vmax);       // count | ST_UPD | ST_LM
+  int *s_frow = reinterpret_cast<int *>(sst0 + ((Vmax + 1) & ~1));  // [T] cell row of every pose
+  double *sxx = sxx0 - cbase, *sxy = sxy0 - cbase, *syy = syy0 - cbase;
+  unsigned *sst = sst0 - cbase;
   double *s_red = reinterpret_cast<double *>(s_frow + ((a.Tstride + 1) & ~1));   // [256] + 2 x int[256]
 
-  if (a.clocks && tid == 0) a.clocks[4 * b] = clock64();
+  if (a.clocks && !split && tid == 0) a.clocks[4 * b] = clock64();
   // ---- init cell state, digest the trajectory -------------------------------------------------------------
-  for (int i = tid; i < V; i += nthr) { sxx[i] = c.i0; sxy[i] = 0.0; syy[i] = c.i0; sst[i] = 0u; }
+  for (int i = tid; i < V; i += nthr) { sxx0[i] = c.i0; sxy0[i] = 0.0; syy0[i] = c.i0; sst0[i] = 0u; }
   const double *ps = a.pose + (size_t)b * a.Tstride * 3, *cv = a.cov + (size_t)b * a.Tstride * 6;
   double *pr = a.prep + (size_t)b * a.Tstride * PREP_W;
   for (int k = tid; k < T; k += nthr) {
+    const double px = ps[3 * k], py = ps[3 * k + 1];
+    const int frow = (int)floor((py - c.map_min_y) / c.res);
+    s_frow[k] = frow;
+    // a split env: every CTA digests the poses that reach its rows (CTAs of an env write identical values to the scratch)
+    if (split && !(frow + a.hw >= row_lo && frow - a.hw < row_hi)) continue;
     double s, co;
     sincos(ps[3 * k + 2], &s, &co);
     double *o = pr + (size_t)k * PREP_W;
-    const double px = ps[3 * k], py = ps[3 * k + 1];
     double S[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) S[i] = cv[6 * k + i];
@@ -348,7 +362,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_vmap_env(EnvArgs a) {
     for (int i = 0; i < 6; ++i) o[4 + i] = S[i];
     o[10] = (det_info < 1e-10) ? 0.0 : 1.0;   // VirtualMap.cpp:293
     o[11] = floor((px - c.map_min_x) / c.res);  // cell column of the pose (defines the candidate block only)
-    s_frow[k] = (int)floor((py - c.map_min_y) / c.res);
   }
   __syncthreads();
   // landmark cells (OccupancyMap.cpp:126-131)
@@ -357,15 +370,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_vmap_env(EnvArgs a) {
     for (int j = tid; j < a.Lfixed; j += nthr) {
       if (a.lm_obs && !a.lm_obs[(size_t)b * a.Lstride + j]) continue;
       const int lr = (int)floor((l[2 * j + 1] - c.map_min_y) / c.res), lc = (int)floor((l[2 * j] - c.map_min_x) / c.res);
-      if (lr >= 0 && lr < c.rows && lc >= 0 && lc < c.cols) atomicOr(&sst[lr * c.cols + lc], ST_LM);
+      if (lr >= row_lo && lr < row_hi && lc >= 0 && lc < c.cols) atomicOr(&sst[lr * c.cols + lc], ST_LM);
     }
   }
   // (the clock reads hang on the barrier's result: BAR.SYNC defers blocking, a bare clock read would run ahead of it)
   const int nb1 = __syncthreads_count(1);
-  if (a.clocks && tid == 0 && nb1) a.clocks[4 * b + 1] = clock64();
+  if (a.clocks && !split && tid == 0 && nb1) a.clocks[4 * b + 1] = clock64();
   // ---- ordered fold: warp = band of hb rows, lane = (row in band, column offset in the pose's block) ---------
-  const int r0 = warp * a.hb, r1 = min(c.rows, r0 + a.hb);
-  if (r0 < c.rows) {
+  const int r0 = (band0 + warp) * a.hb, r1 = min(row_hi, r0 + a.hb);
+  if (r0 < row_hi) {
     const int dr = lane / a.W, dc = lane - dr * a.W;
     const int row = r0 + dr;
     const bool lane_on = dr < (r1 - r0);
@@ -457,21 +470,21 @@ __global__ void __launch_bounds__(MAXT, MINB) k_vmap_env(EnvArgs a) {
     }
   }
   const int nb2 = __syncthreads_count(1);
-  if (a.clocks && tid == 0 && nb2) a.clocks[4 * b + 2] = clock64();
+  if (a.clocks && !split && tid == 0 && nb2) a.clocks[4 * b + 2] = clock64();
   // ---- write the map: every output byte once, coalesced -------------------------------------------------------
-  const size_t cell0 = (size_t)b * V;
+  const size_t cell0 = (size_t)b * c.rows * c.cols + cbase;
   for (int i = tid; i < V; i += nthr) {
-    const unsigned st = sst[i];
+    const unsigned st = sst0[i];
     const int cnt = (int)(st & ST_CNT);
     a.prob[cell0 + i] = (st & ST_LM) ? c.ptab[5] : c.ptab[min(cnt, 4)];
     if (a.seen) a.seen[cell0 + i] = (st & ST_LM) ? -1 : cnt;
   }
   for (int i = tid; i < 3 * V; i += nthr) {
     const int cell = i / 3, j = i - 3 * cell;
-    a.vinfo[cell0 * 3 + i] = j == 0 ? sxx[cell] : (j == 1 ? sxy[cell] : syy[cell]);
+    a.vinfo[cell0 * 3 + i] = j == 0 ? sxx0[cell] : (j == 1 ? sxy0[cell] : syy0[cell]);
   }
-  if (a.clocks && tid == 0) a.clocks[4 * b + 3] = clock64();
-  if (!a.metrics) return;
+  if (a.clocks && !split && tid == 0) a.clocks[4 * b + 3] = clock64();
+  if (!a.metrics || split) return;
 
   // ---- metrics (k_vmap_metrics, same summation order: 256 strided partial sums, fixed tree) ---------------------
   if (tid == 0 && a.counters && a.step_kind[b]) {
@@ -559,10 +572,29 @@ bool env_plan(const dge_config &g, int rows, int cols, int Tstride, int *hw, int
   *smem = V * 3 * sizeof(double) + ((V + 1) & ~(size_t)1) * sizeof(unsigned) + (size_t)((Tstride + 1) & ~1) * sizeof(int) + 256 * (sizeof(double) + 2 * sizeof(int)) + 16;
   return *smem <= 220 * 1024;
 }
-int env_launch(EnvArgs &a, const dge_config &g, int n, int rows, int cols, cudaStream_t st) {
+constexpr int SPLIT_BG = 4;   // bands per CTA of a split env (4 warps)
+int env_launch(EnvArgs &a, const dge_config &g, int n, int rows, int cols, cudaStream_t st, bool allow_split = false) {
   int nw;
   size_t smem;
+  a.bg = 0;
   if (!env_plan(g, rows, cols, a.Tstride, &a.hw, &a.W, &a.hb, &nw, &smem)) return 1;   // caller falls back to the cell-centric kernels
+  // Throughput regime (many more envs than SMs, no per-env metrics wanted): split every env into groups of SPLIT_BG bands, one
+  // 4-warp CTA each.  A band is a serial chain and most bands of a map are idle at any time; with whole-env CTAs their warps hold
+  // registers of an SM without issuing (2 CTAs of 13 warps, ~40 % busy at BASELINE config C4), with band groups 6-7 small CTAs share
+  // an SM, untouched groups retire at once and the busy chains of several envs fill the fp64 pipe.
+  const int nb = (rows + a.hb - 1) / a.hb;
+  if (allow_split && !a.metrics && nb > SPLIT_BG && (long long)n * nb >= 8 * 148) {
+    a.bg = SPLIT_BG;
+    const size_t Vg = (size_t)SPLIT_BG * a.hb * cols;
+    const size_t sm = Vg * 3 * sizeof(double) + ((Vg + 1) & ~(size_t)1) * sizeof(unsigned) + (size_t)((a.Tstride + 1) & ~1) * sizeof(int) + 16;
+    static size_t cfg_split = 0;
+    if (sm > 48 * 1024 && sm > cfg_split) {
+      if (cudaFuncSetAttribute(k_vmap_env<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DGE_ECUDA;
+      cfg_split = sm;
+    }
+    k_vmap_env<128, 6><<<dim3(n, (nb + SPLIT_BG - 1) / SPLIT_BG), SPLIT_BG * 32, sm, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
+  }
   // one instantiation per band count of the reference's maps (20/40/60/80/100 -> 8/10/13/15/18 warps) so that two
   // CTAs fit the register file of an SM; larger maps fall to the generic ceilings
   const int vi = nw <= 8 ? 0 : nw <= 10 ? 1 : nw <= 13 ? 2 : nw <= 15 ? 3 : nw <= 18 ? 4 : nw <= 24 ? 5 : 6;
@@ -621,7 +653,7 @@ int dge_vmap_standalone(const dge_config *cfg, int n, int T, const double *pose,
     a.sim_step = nullptr; a.status = nullptr; a.meas_ptr = nullptr; a.dist = nullptr;
     a.cfg = *cfg; a.d = DgeDims{};
     a.clocks = reinterpret_cast<long long *>(cbox_ws);   // the chunk-box scratch is unused by the fused kernel: phase clocks for dev profiling
-    const int rc = env_launch(a, *cfg, n, rows, cols, st);
+    const int rc = env_launch(a, *cfg, n, rows, cols, st, /*allow_split=*/true);
     if (rc != 1) return rc;
   }
   const int nchm = dge_vmap_nchunk(T);

@@ -58,3 +58,26 @@ def test_rebuild_properties_full_size():
     untouched = seen == 0
     assert (prob[untouched] == 0.5).all()
     assert ((seen > 0) | (seen == -1) | untouched).all()
+
+
+@pytest.mark.parametrize("map_size,T,L,n", [(60, 48, 200, 96), (100, 40, 50, 70)])
+def test_band_group_split_equals_whole_env_kernel_and_oracle(map_size, T, L, n):
+    """Throughput regime (n x bands >= 8 x 148): every env is split into band groups of 4 warps.  Same arithmetic, same order
+    per cell => bit-identical to the whole-env kernel (which a small batch selects), and oracle parity on a sample."""
+    from drl_graph_exploration_b200.engine import virtual_map_rebuild
+
+    cfg = EnvConfig(map_size=map_size, num_landmarks=L)
+    pose, cov, cov6, info, lm = synth_states(cfg, n, T, L, seed=1000 + T)
+    dev = torch.device("cuda")
+    tp, tc, tl = (torch.as_tensor(a, device=dev) for a in (pose, cov6, lm))
+    prob, vinfo, seen = virtual_map_rebuild(cfg, tp, tc, tl, want_seen=True)                       # split
+    k = 5
+    prob_w, vinfo_w, seen_w = virtual_map_rebuild(cfg, tp[:k].contiguous(), tc[:k].contiguous(), tl[:k].contiguous(), want_seen=True)   # whole-env CTAs
+    assert torch.equal(prob[:k], prob_w) and torch.equal(vinfo[:k], vinfo_w) and torch.equal(seen[:k], seen_w)
+    prob, vinfo, seen = prob.cpu().numpy(), vinfo.cpu().numpy(), seen.cpu().numpy()
+    for i in (0, n // 2, n - 1):
+        p_ref, i_ref, s_ref = oracle_rebuild(cfg, pose[i], info[i].reshape(T, 9), lm[i])
+        ok = ~borderline_cells(cfg, pose[i], tol=1e-9)
+        assert np.array_equal(seen[i][ok], s_ref[ok]) and np.array_equal(prob[i][ok], p_ref[ok])
+        a, b = sym3_to_full(vinfo[i])[ok], i_ref[ok]
+        assert (np.abs(a - b) / (1e-9 + np.maximum(np.abs(a), np.abs(b)))).max() < 1e-6
