@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
       if (warp == 0) {
         // B0: the 3x3 recurrence, scalar and identical on every lane (no shuffles: a shuffle round trip costs ~40
         // cycles here, the whole inverse ~80); ~100 fp64 instructions = ~200 issue cycles per pose.
+        const long long tb0 = (a.clocks && tid == 0) ? clock64() : 0;
         for (int kk = 0; kk < kc; ++kk) {
           double *w = stage + kk * SW;
           const double d0 = w[0] + cD[0], d1 = w[1] + cD[1], d2 = w[2] + cD[2], d3 = w[3] + cD[3], d4 = w[4] + cD[4], d5 = w[5] + cD[5];
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
             mbar_arrive(&s_bar[kk]);
           }
         }
+        if (a.clocks && tid == 0) a.clocks[12 * b + 8] = (k0 ? a.clocks[12 * b + 8] : 0) + (clock64() - tb0);   // cycles inside the pose recurrence
       } else {
         if (colv) {
           if (k0 == 0) {
@@ -309,6 +311,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
           }
           // B1: border column c.  Bt = B_k + carry, FB = D~^-1 Bt, carry' = -U^T FB, rhs; border rows prefetched
           // 4 poses ahead (an L2 round trip is longer than one pose of the chain)
+          const long long tb1 = (a.clocks && tid == NT - 1) ? clock64() : 0;
           double nb[4][3];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
               }
             }
           }
+          if (a.clocks && tid == NT - 1) a.clocks[12 * b + 9] = (k0 ? a.clocks[12 * b + 9] : 0) + (clock64() - tb1);   // cycles of border column 0 in its recurrence
         }
         // copy the chunk's Dinv | FU | f to the workspace (needed again by the backward pass)
         while (!mbar_try_wait(&s_bar[kc - 1], par)) { }

@@ -21,5 +21,5 @@ for i, n in enumerate(names):
 tot = d.sum(axis=1)
 print(f"{'total':16s} mean {tot[act].mean():10.0f}  max {tot[act].max():10.0f}   (1965 MHz: max = {tot[act].max() / 1965:.1f} us)")
 for b in order[:4]:
-    print("   B0 sub-steps (cycles/pose): det", clk[b, 8] / T[b], "rcp", clk[b, 9] / T[b], "val", clk[b, 10] / T[b], "carry+store", clk[b, 11] / T[b]);
+    print(f"   inside phase B: pose recurrence (warp 0) {clk[b, 8] / T[b]:.0f} cycles/pose, border column 0 (incl. its waits on the recurrence) {clk[b, 9] / T[b]:.0f} cycles/pose")
     print("env", b, "T", T[b], " ".join(f"{n.split('(')[0]}={d[b, i]:.0f}" for i, n in enumerate(names)), "total", tot[b])
