@@ -339,9 +339,10 @@ def gcn_q_forward(x: torch.Tensor, gs: GraphStructure, w1: torch.Tensor, b1, w2:
     N, cin = x.shape
     C = w1.shape[1]
     dev = x.device
-    ws = _q_ws.get(dev)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)      # one workspace per stream: calls on different streams may overlap
+    ws = _q_ws.get(key)
     if ws is None or ws.numel() < 3 * N * C:      # grow-only workspace: no allocator traffic in the acting loop
-        ws = _q_ws[dev] = torch.empty(max(3 * N * C, 1 << 22), dtype=torch.float32, device=dev)
+        ws = _q_ws[key] = torch.empty(max(3 * N * C, 1 << 22), dtype=torch.float32, device=dev)
     q = torch.empty(N, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = L.dge_gcn_q_forward(N, cin, C, _p(x), _p(gs.rowptr_dst), _p(gs.perm_dst), _p(gs.src), _p(norm), _p(selfnorm),

@@ -60,7 +60,6 @@ class VecDQNTrainer:
         self.pend_slot, self.pend_a = i64(-1), i64(0)                  # in-flight transition of every env
         self.pend_r = torch.zeros(B, dtype=torch.float32, device=self.dev)
         self.pend_clo = torch.zeros(B, dtype=torch.bool, device=self.dev)
-        self._ar = torch.arange(B, device=self.dev)
         self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
         self.gen = torch.Generator(device=self.dev); self.gen.manual_seed(seed)
         self.decisions = self.train_steps = self.ticks = self.transitions = 0
@@ -154,7 +153,7 @@ class VecDQNTrainer:
         s, a, r, s1, term = rp.sample(k, generator=self.gen, check=check)
         b_s, n_s, off_s = rp.gather(s)
         b_s1, n_s1, off_s1 = rp.gather(s1)
-        return b_s, b_s1, dqn_targets_inputs(a, r, term, off_s, n_s1, off_s1, rp.gf[s1])
+        return b_s, b_s1, (a, r, term, off_s, n_s1, off_s1, rp.gf[s1])
 
     def learn(self, check: bool = False):
         """One gradient step (policy.py:136-182); collective inside ``DeepQ.train``."""
@@ -196,10 +195,6 @@ class VecDQNTrainer:
     def save(self, path: str):
         """``torch.save(policy_net.state_dict(), .../MyModel.pt)`` like policy.py:192 -- loadable by the reference."""
         torch.save({k: v.detach().cpu() for k, v in self.policy_net.state_dict().items()}, path)
-
-
-def dqn_targets_inputs(a, r, term, off_s, n_s1, off_s1, fro1):
-    return a, r, term, off_s, n_s1, off_s1, fro1
 
 
 def dqn_targets(q1, batch1, a, r, term, off_s, n_s1, off_s1, fro1, n_nodes_s: int, gamma: float):
