@@ -210,3 +210,165 @@ def dqn_targets(q1, batch1, a, r, term, off_s, n_s1, off_s1, fro1, n_nodes_s: in
     act = torch.zeros(n_nodes_s, dtype=q1.dtype, device=q1.device); act[at] = 1.0
     y = torch.zeros_like(act); y[at] = yv
     return act, y
+
+
+class VecA2CTrainer:
+    """``A2C.running`` (policy.py:297-426) for B environments per GPU.
+
+    Per env the sequence is the reference's: at a decision the actor's masked softmax over the frontier nodes is sampled
+    (``np.random.choice(fro_size, p=readout_t)``, policy.py:326 -- here a Gumbel-max draw fed to the device-side read-out), the
+    critic's value of the state is recorded, the look-ahead reward of the chosen frontier comes from the batched roll-outs, the
+    env follows the line plan, and ``(s_t, a_t, r_t, done or loop_clo, fro_size, V(s_t))`` joins the env's n-step segment.  When an
+    env has ``nstep`` transitions its segment is closed with ``last_value = V(s_t+1)`` (the value at the env's next decision, 0
+    after a terminal), the discounted returns and advantages are formed like policy.py:361-393 and the segment is trained on.
+    All segments that close in the same tick form ONE batch (losses averaged over segments), so a tick takes at most one
+    gradient step; with ``torch.distributed`` every rank joins the all-reduce of that tick (zero gradient if it has no segment),
+    weighted by the number of segments, so ranks never wait on each other's episodes.
+    """
+
+    def __init__(self, env: VecExplorationEnv, actor: torch.nn.Module, critic: torch.nn.Module, a2c=None, lr: float = 1e-5,
+                 clone_slots: int | None = None, seed: int = 0):
+        from .dist import FlatGradBucket
+        from .policy import A2C
+        self.env, self.actor, self.critic = env, actor, critic
+        self.a2c = a2c or A2C()
+        self.dev = env.device
+        B, eng, n = env.B, env.eng, int(self.a2c.nstep)
+        self.store = GraphReplay(B * (n + 2), eng.node_cap_env, eng.edge_cap_env, self.dev, slack=B * 4)   # graph store only
+        self.params = [p for p in list(actor.parameters()) + list(critic.parameters()) if p.requires_grad]
+        self.optimizer = torch.optim.Adam(self.params, lr=lr)
+        self.bucket = FlatGradBucket(self.params)
+        self.clone_slots = clone_slots
+        z = lambda dt, *shape: torch.zeros(*shape, dtype=dt, device=self.dev)
+        self.seg_slot, self.seg_a = z(torch.int64, B, n), z(torch.int64, B, n)
+        self.seg_r, self.seg_val, self.seg_term = z(torch.float32, B, n), z(torch.float32, B, n), z(torch.bool, B, n)
+        self.seg_len = z(torch.int64, B)
+        self.pend_slot, self.pend_a = torch.full((B,), -1, dtype=torch.int64, device=self.dev), z(torch.int64, B)
+        self.pend_r, self.pend_val, self.pend_clo = z(torch.float32, B), z(torch.float32, B), z(torch.bool, B)
+        self._ar = torch.arange(B, device=self.dev)
+        self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
+        self.gen = torch.Generator(device=self.dev); self.gen.manual_seed(seed)
+        self.decisions = self.train_steps = self.segments = self.ticks = 0
+        self.last_loss, self.last_entropy, self.reward_sum = float("nan"), float("nan"), 0.0
+
+    @torch.no_grad()
+    def tick(self):
+        env, eng, a2c, st, dev = self.env, self.env.eng, self.a2c, self.env.eng.state, self.dev
+        B, n = env.B, int(a2c.nstep)
+        done_prev = st["done"].bool().clone()
+        need = env.mark_pending().bool().clone()
+        need_u8 = need.to(torch.uint8)
+        _check(eng._L.dge_reset_done_queued(eng._h, B, self._fo, 4, _stream_ptr(dev)), "dge_reset_done_queued")
+        eng.step_queued()
+        ended = done_prev & (self.pend_slot >= 0)
+        g = env.build_graph(need_u8)
+        ng, nn, ne = g.sync_sizes()
+        v_now = torch.zeros(B, dtype=torch.float32, device=dev)
+        if ng > 0:
+            ordinal = (torch.cumsum(need.long(), 0) - 1).clamp(0, ng - 1)
+            slots_c = self.clone_slots or min(B * (eng.Lt + 1), max(4 * B, 512))
+            fro_host = g.fro_size[:ng].tolist()
+            lo = acc = 0
+            for i, f in enumerate(fro_host + [slots_c + 1]):      # roll-outs in chunks that fit the clone engine
+                if acc + f > slots_c:
+                    m = (need & (ordinal >= lo) & (ordinal < i)).to(torch.uint8)
+                    _, norm, clo = env.rollout_rewards(m, clone_slots=slots_c, auto_steps=True)
+                    lo, acc = i, 0
+                acc += f
+            d = g.data()
+            key_g, fro_g, nptr = g.key_size[:ng].long(), g.fro_size[:ng].long(), g.node_ptr[:ng + 1].long()
+            local = torch.arange(nn, device=dev) - nptr[d.batch]
+            mask = local >= key_g[d.batch]                                    # frontier nodes (policy.py:316-317)
+            pi = a2c.test(d, d.batch, mask, dev, self.actor).view(-1)         # masked softmax, functional dropout 0.5 (q19)
+            val = a2c.test(d, d.batch, mask, dev, self.critic).view(-1)       # V(s) per graph
+            u = torch.rand(pi.numel(), device=dev, generator=self.gen).clamp_(1e-12, 1 - 1e-12)
+            score = torch.zeros(nn, dtype=torch.float32, device=dev)
+            score[mask] = (pi + 1e-35).log() - (-u.log()).log()               # Gumbel-max == np.random.choice(fro_size, p=pi)
+            choice = env.select_and_plan(score, need_u8).long()
+            slots = self.store.store_graphs(d.x, d.edge_index, d.edge_attr, d.batch, g.node_ptr, g.edge_ptr, g.key_size, g.fro_size, ng)
+            slot_new = torch.where(need, slots[ordinal], torch.full_like(self.pend_slot, -1))
+            fro = torch.where(need, fro_g[ordinal], torch.zeros_like(ordinal))
+            key = key_g[ordinal]
+            v_now = torch.where(need, val[ordinal].float(), v_now)
+        else:
+            fro = torch.zeros_like(self.pend_slot); key = fro; choice = fro; slot_new = torch.full_like(self.pend_slot, -1)
+        # ---- the in-flight transition of every env that decides now, or whose episode ended, joins its segment ----
+        closing = need & (self.pend_slot >= 0)
+        fin = closing | ended
+        pos = self.seg_len.clamp(max=n - 1)
+        put = lambda buf, v: buf.__setitem__((self._ar, pos), torch.where(fin, v, buf[self._ar, pos]))
+        put(self.seg_slot, self.pend_slot); put(self.seg_a, self.pend_a); put(self.seg_r, self.pend_r); put(self.seg_val, self.pend_val)
+        put(self.seg_term, ended | self.pend_clo | (closing & (fro <= 0)))
+        self.seg_len = self.seg_len + fin.long()
+        self.reward_sum += float(torch.where(fin, self.pend_r, torch.zeros_like(self.pend_r)).sum())
+        self.pend_slot = torch.where(fin, torch.full_like(self.pend_slot, -1), self.pend_slot)
+        # ---- segments that reached nstep: last_value = V(s_t+1) at this decision (0 after the episode's end) ----
+        complete = self.seg_len >= n
+        n_seg = int(complete.sum())                                           # host sync
+        self._train(complete, n_seg, torch.where(ended, torch.zeros_like(v_now), v_now))
+        # ---- open the transitions of the envs that decided now ----
+        if ng > 0:
+            start = need & (fro > 0)
+            r = norm.gather(1, choice.clamp(0, norm.size(1) - 1).view(-1, 1)).view(-1).float()
+            self.pend_slot = torch.where(start, slot_new, self.pend_slot)
+            self.pend_a = torch.where(start, key + choice, self.pend_a)
+            self.pend_r = torch.where(start, r, self.pend_r)
+            self.pend_val = torch.where(start, v_now, self.pend_val)
+            self.pend_clo = torch.where(start, clo.bool(), self.pend_clo)
+        self.decisions += ng
+        self.a2c.step_t += ng
+        self.ticks += 1
+        return ng
+
+    def _train(self, complete, n_seg, last_value):
+        """policy.py:361-393 + 474-497 for the segments that closed in this tick (one batch, one gradient step)."""
+        import torch.distributed as dist
+        a2c, dev, n = self.a2c, self.dev, int(self.a2c.nstep)
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        total = n_seg
+        if world > 1:      # every rank joins the collective of a tick in which ANY rank has a segment
+            t = torch.tensor([float(n_seg)], device=dev)
+            dist.all_reduce(t)
+            total = int(t.item())
+        if total == 0:
+            return
+        self.bucket.zero_()
+        if n_seg > 0:
+            rows = complete.nonzero().view(-1)
+            r, term, vals = self.seg_r[rows], self.seg_term[rows].float(), self.seg_val[rows]
+            returns = nstep_returns(r, term, last_value[rows], a2c.GAMMA)
+            slots = self.seg_slot[rows].view(-1)                              # segment-major, time order inside a segment
+            batch, n_nodes, off = self.store.gather(slots)
+            N = batch.x.size(0)
+            node = torch.arange(N, device=dev)
+            mask = node - off[batch.batch] >= (n_nodes - self.store.gf[slots])[batch.batch]
+            at = off + self.seg_a[rows].view(-1)
+            action = torch.zeros(N, device=dev); action[at] = 1.0
+            y_adv = torch.zeros(N, device=dev); y_adv[at] = (returns - vals).view(-1)
+            with torch.enable_grad():
+                self.actor.train(); self.critic.train()
+                actor_out = self.actor(batch, mask, batch=batch.batch) + 1e-35
+                critic_out = self.critic(batch, mask, batch=batch.batch)
+                ent = a2c.entropy_loss(actor_out)
+                # per segment the reference's loss; averaged over the segments of all ranks
+                loss = ((a2c.policy_cost(actor_out, y_adv, action, mask) - ent * a2c.ent_coef) / n_seg
+                        + a2c.value_cost(critic_out, returns.view(-1)) * a2c.vf_coef) * (n_seg / total)
+                loss.backward()
+            self.last_loss, self.last_entropy = float(loss) * total / n_seg, float(ent) / n_seg
+            self.seg_len = torch.where(complete, torch.zeros_like(self.seg_len), self.seg_len)
+            self.segments += n_seg
+        if world > 1:
+            dist.all_reduce(self.bucket.flat)
+        self.bucket.clamp_(a2c.max_grad_norm)                                 # policy.py:493-495
+        self.optimizer.step()
+        self.train_steps += 1
+
+
+def nstep_returns(r: torch.Tensor, term: torch.Tensor, last_value: torch.Tensor, gamma: float) -> torch.Tensor:
+    """policy.py:366-372 for S segments at once: r, term [S, nstep], last_value [S] -> discounted returns [S, nstep]
+    (``ret = r_i + gamma * ret * (1 - terminal_i)`` walking the segment backwards from ``last_value``)."""
+    ret, out = last_value, torch.zeros_like(r)
+    for i in range(r.size(1) - 1, -1, -1):
+        ret = r[:, i] + gamma * ret * (1.0 - term[:, i])
+        out[:, i] = ret
+    return out

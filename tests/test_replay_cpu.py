@@ -97,3 +97,21 @@ def test_vectorised_targets_equal_build_targets():
     q1 = Net()(b_s1, 0.0).view(-1)
     act, y = dqn_targets(q1, b_s1.batch, a, rr, tt, off_s, n_s1, off_s1, rp.gf[s1], b_s.x.size(0), dq.GAMMA)
     assert torch.equal(act, a_ref.float()) and torch.allclose(y, y_ref.float(), rtol=1e-6, atol=1e-7)
+
+
+def test_vectorised_nstep_returns_equal_the_reference_loop():
+    """trainer.nstep_returns (S segments at once) against A2C.nstep_batch (policy.py:361-393, one segment)."""
+    from drl_graph_exploration_b200.policy import A2C
+    from drl_graph_exploration_b200.trainer import nstep_returns
+    rng = np.random.default_rng(5)
+    S, n = 6, 7
+    r = rng.uniform(-1, 1, (S, n)); term = rng.uniform(size=(S, n)) < 0.3; last = rng.normal(size=S); vals = rng.normal(size=(S, n))
+    out = nstep_returns(torch.tensor(r), torch.tensor(term, dtype=torch.float64), torch.tensor(last), 0.99).numpy()
+    g = Data(torch.zeros(2, 5), torch.zeros(2, 0, dtype=torch.long), torch.zeros(0))
+    for s in range(S):
+        ac = A2C(); ac.nstep = n
+        for i in range(n):
+            ac.buffer.append((g, np.array([0.0, 1.0]), r[s, i], g, bool(term[s, i]), 1, vals[s, i]))
+        _, a, mask, returns, adv = ac.nstep_batch(last[s])
+        assert np.allclose(out[s], returns, rtol=1e-12, atol=1e-12)
+        assert np.allclose(adv.reshape(n, 2)[:, 1], returns - vals[s])

@@ -121,3 +121,37 @@ def test_overlapped_learning_equals_sequential_learning():
     w_ovl, n_ovl, l_ovl = run(True)
     assert n_seq == n_ovl == 6
     assert torch.equal(w_seq, w_ovl) and l_seq == l_ovl
+
+
+def test_vectorised_a2c_trainer_runs_segments_and_learns():
+    """VecA2CTrainer (A2C.running for B envs): segments of nstep decisions close, one gradient step per tick with closed
+    segments, actor and critic move, sampled actions are frontier nodes, values / rewards stored per transition are finite."""
+    from drl_graph_exploration_b200 import Networks
+    from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv
+    from drl_graph_exploration_b200.policy import A2C
+    from drl_graph_exploration_b200.trainer import VecA2CTrainer
+
+    env = VecExplorationEnv(16, cfg=EnvConfig(map_size=20, num_landmarks=12), max_poses=128, seed0=40)
+    env.reset()
+    torch.manual_seed(0)
+    actor, critic = Networks.PolicyGCN().to(env.device), Networks.ValueGCN().to(env.device)
+    before = torch.cat([p.detach().flatten().clone() for p in list(actor.parameters()) + list(critic.parameters())])
+    a2c = A2C(); a2c.nstep = 4
+    tr = VecA2CTrainer(env, actor, critic, a2c=a2c)
+    seen_partial = False
+    for _ in range(70):
+        tr.tick()
+        ln = tr.seg_len
+        assert int(ln.max()) < 4 and int(ln.min()) >= 0          # closed segments are consumed in the tick they close
+        seen_partial |= bool((ln > 0).any())
+        filled = torch.arange(4, device=env.device)[None, :] < ln[:, None]
+        s, a = tr.seg_slot[filled], tr.seg_a[filled]
+        if s.numel():
+            assert bool(((a >= tr.store.gk[s]) & (a < tr.store.gk[s] + tr.store.gf[s])).all())      # the sampled node is a frontier node
+            assert torch.isfinite(tr.seg_val[filled]).all() and bool((tr.seg_r[filled].abs() <= 1.0 + 1e-6).all())
+    torch.cuda.synchronize()
+    assert seen_partial and tr.segments >= 4 and tr.train_steps >= 2 and tr.decisions > 40
+    assert np.isfinite(tr.last_loss) and np.isfinite(tr.last_entropy) and tr.last_entropy > 0
+    after = torch.cat([p.detach().flatten() for p in list(actor.parameters()) + list(critic.parameters())])
+    assert not torch.equal(before, after) and torch.isfinite(after).all()
+    env.close()
