@@ -21,25 +21,38 @@ __global__ void k_count(int E, const int64_t *key, int32_t *cnt) {
   if (e < E) atomicAdd(&cnt[(int)key[e]], 1);
 }
 
-// single-CTA exclusive scan (N up to a few 100k nodes: 1024 threads, serial chunks)
+// single-CTA exclusive scan, tile by tile: coalesced loads of 1024 counts, shuffle scan inside the warps, one shared-memory
+// pass over the 32 warp totals, running carry in a register; the next tile's load is issued before the current tile's scan
+// (N is at most a few 100k nodes: a handful of tiles, latency-bound -- a multi-CTA decoupled look-back would not pay).
 __global__ void __launch_bounds__(1024) k_scan(int N, const int32_t *cnt, int32_t *rowptr) {
-  __shared__ int32_t part[1024];
-  const int tid = threadIdx.x;
-  const int per = (N + 1023) / 1024;
-  const int lo = min(N, tid * per), hi = min(N, lo + per);
-  int s = 0;
-  for (int i = lo; i < hi; ++i) s += cnt[i];
-  part[tid] = s;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int v = (tid >= o) ? part[tid - o] : 0;
+  __shared__ int32_t wsum[32];
+  __shared__ int32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int carry = 0;
+  int nxt = (tid < N) ? cnt[tid] : 0;
+  for (int base = 0; base < N; base += 1024) {
+    const int v = nxt;
+    const int nb = base + 1024 + tid;
+    nxt = (nb < N) ? cnt[nb] : 0;
+    int x = v;                                   // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[warp] = x;
     __syncthreads();
-    part[tid] += v;
+    if (warp == 0) {
+      int w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      wsum[lane] = w;                            // inclusive totals of the warps
+      if (lane == 31) s_carry = w;
+    }
+    __syncthreads();
+    const int before = carry + (warp ? wsum[warp - 1] : 0) + x - v;
+    if (base + tid < N) rowptr[base + tid] = before;
+    carry += s_carry;
     __syncthreads();
   }
-  int run = (tid == 0) ? 0 : part[tid - 1];
-  for (int i = lo; i < hi; ++i) { rowptr[i] = run; run += cnt[i]; }
-  if (tid == 1023) rowptr[N] = part[1023];
+  if (tid == 0) rowptr[N] = carry;
 }
 
 __global__ void k_fill(int E, const int64_t *key, const int32_t *rowptr, int32_t *cursor, int32_t *perm) {
@@ -64,21 +77,33 @@ __global__ void k_rank_rows(int E, const int64_t *key, const int32_t *rowptr, co
 // ------------------------------------------------------------------ GCN norm ---
 // GCNConv.norm (PyG 1.x, improved=True): add *remaining* self loops with weight `fill`,
 // deg_i = sum of the weights of the edges whose source is i, norm_e = deg^-1/2[src] w deg^-1/2[dst].
-__global__ void k_gcn_deg(int N, const int32_t *rowptr_src, const int32_t *perm_src, const int64_t *src, const int64_t *dst,
-                          const float *w, float fill, float *dis, float *selfw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_gcn_deg(int N, const int32_t *rowptr_src, const int32_t *perm_src, const int64_t *src, const int64_t *dst,
+                                                 const float *w, float fill, float *dis, float *selfw) {
+  // one warp per node: lanes stride the node's out-edges (coalesced reads of the row), partial sums combined by a fixed
+  // shuffle tree => deterministic whatever the edge count
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N) return;
   float deg = 0.f, loopw = 0.f;
-  bool has_loop = false;
-  for (int p = rowptr_src[i]; p < rowptr_src[i + 1]; ++p) {
+  int has_loop = 0;
+  for (int p = rowptr_src[i] + lane; p < rowptr_src[i + 1]; p += 32) {
     const int e = perm_src[p];
-    if ((int)dst[e] == i) { has_loop = true; loopw = w[e]; continue; }   // existing loops are re-appended after the plain edges
+    if ((int)dst[e] == i) { has_loop = 1; loopw = w[e]; continue; }   // existing loops are re-appended after the plain edges
     deg += w[e];
   }
-  const float lw = has_loop ? loopw : fill;
-  deg += lw;
-  dis[i] = (deg > 0.f) ? 1.0f / sqrtf(deg) : 0.f;   // deg^-0.5 with inf -> 0
-  selfw[i] = lw;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    deg += __shfl_xor_sync(0xffffffffu, deg, o);
+    const float lw2 = __shfl_xor_sync(0xffffffffu, loopw, o);
+    const int hl2 = __shfl_xor_sync(0xffffffffu, has_loop, o);
+    if (hl2 && !has_loop) loopw = lw2;            // (a node has at most one self loop in these graphs; the last one wins like before)
+    has_loop |= hl2;
+  }
+  if (lane == 0) {
+    const float lw = has_loop ? loopw : fill;
+    deg += lw;
+    dis[i] = (deg > 0.f) ? 1.0f / sqrtf(deg) : 0.f;   // deg^-0.5 with inf -> 0
+    selfw[i] = lw;
+  }
 }
 __global__ void k_gcn_norm(int E, const int64_t *src, const int64_t *dst, const float *w, const float *dis, float *norm) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,7 +218,7 @@ extern "C" int dge_gcn_norm(int N, int E, const int64_t *src, const int64_t *dst
                             const int32_t *perm_src, float fill, float *dis, float *selfw, float *norm, float *selfnorm, void *stream) {
   if (N <= 0) return -1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  k_gcn_deg<<<cdiv(N, 128), 128, 0, st>>>(N, rowptr_src, perm_src, src, dst, w, fill, dis, selfw);
+  k_gcn_deg<<<cdiv(N, 8), 256, 0, st>>>(N, rowptr_src, perm_src, src, dst, w, fill, dis, selfw);
   if (E > 0) k_gcn_norm<<<cdiv(E, 256), 256, 0, st>>>(E, src, dst, w, dis, norm);
   k_gcn_selfnorm<<<cdiv(N, 256), 256, 0, st>>>(N, dis, selfw, selfnorm);
   return CK();

@@ -243,3 +243,38 @@ def test_ggnn_inference_on_native_gru_path_matches_reference():
     assert (q.double() - r).abs().max() <= 1e-4 * scale, float((q.double() - r).abs().max() / scale)
     assert (q - q_autograd).abs().max() <= 1e-4 * scale
     assert launches >= 3 * (1 + 2 * 2 + 1 + 1)               # per layer: (split + GEMM) x 3 transforms, aggregate, gates
+
+
+def test_csr_build_and_gcn_norm_on_a_large_batch():
+    """gnn.GraphStructure on 5 000 nodes / 40 000 edges (several scan tiles, rows longer than a warp): CSR against a stable
+    torch sort, improved-GCN normalisation against its definition (PyG 1.x GCNConv.norm with add_remaining_self_loops)."""
+    from drl_graph_exploration_b200 import gnn
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    N, E = 5000, 40000
+    src = torch.randint(0, N, (E,), generator=g); dst = torch.randint(0, N, (E,), generator=g)
+    dst[:300] = 7                                                     # a hub: one row of 300+ incoming edges
+    src[300:420] = 11                                                 # and one node with 120+ outgoing edges
+    src[500:520] = dst[500:520]                                       # a few explicit self loops
+    w = torch.rand(E, generator=g) * 5 + 0.1
+    ei = torch.stack([src, dst]).to(dev); wd = w.to(dev)
+    gs = gnn.GraphStructure(ei, wd, N)
+    order = torch.sort(ei[1], stable=True)[1]
+    rowptr = torch.zeros(N + 1, dtype=torch.int64, device=dev); rowptr[1:] = torch.cumsum(torch.bincount(ei[1], minlength=N), 0)
+    assert torch.equal(gs.rowptr_dst.long(), rowptr) and torch.equal(gs.perm_dst.long(), order)
+    norm, selfnorm = gs.gcn_norm(True)
+    loop = ei[0] == ei[1]
+    deg = torch.zeros(N, dtype=torch.float64, device=dev).index_add_(0, ei[0][~loop], wd[~loop].double())
+    selfw = torch.full((N,), 2.0, dtype=torch.float64, device=dev)
+    has = torch.zeros(N, dtype=torch.bool, device=dev); has[ei[0][loop]] = True
+    # nodes with ONE explicit loop keep its weight (the random draw above may give a node two: skip those in the comparison)
+    cnt = torch.bincount(ei[0][loop], minlength=N)
+    lw = torch.zeros(N, dtype=torch.float64, device=dev).index_add_(0, ei[0][loop], wd[loop].double())
+    selfw = torch.where(cnt == 1, lw, selfw)
+    ok = cnt <= 1
+    deg = deg + selfw
+    dis = deg.pow(-0.5)
+    ref_norm = torch.where(loop, torch.zeros_like(deg[ei[0]]), dis[ei[0]] * wd.double() * dis[ei[1]])
+    eok = ok[ei[0]] & ok[ei[1]]
+    assert torch.allclose(norm.double()[eok], ref_norm[eok], rtol=2e-6, atol=1e-9)
+    assert torch.allclose(selfnorm.double()[ok], (dis * selfw * dis)[ok], rtol=2e-6, atol=1e-9)
