@@ -196,6 +196,47 @@ class VecDQNTrainer:
         """``torch.save(policy_net.state_dict(), .../MyModel.pt)`` like policy.py:192 -- loadable by the reference."""
         torch.save({k: v.detach().cpu() for k, v in self.policy_net.state_dict().items()}, path)
 
+    def run(self, n_ticks: int, out_dir: str | None = None, log_every: int = 100, save_every: int = 50000):
+        """The outer loop of ``DeepQ.running`` (policy.py:72-209) in ticks: trains for ``n_ticks`` and, if ``out_dir`` is given,
+        leaves the reference's artefacts there -- ``temp_reward.csv`` (decision count, mean reward of the closed transitions
+        since the last row), ``temp_loss.csv`` (decision count, loss), ``reward_data.csv`` (Step, Reward), ``MyModel.pt`` every
+        ``save_every`` decisions, ``Model_Policy.pt`` / ``Model_Target.pt`` at the end (policy.py:192-209)."""
+        import os
+        rewards, losses, rows = [], [], []
+        r0, n0, next_log, next_save = self.reward_sum, self.transitions, log_every, save_every
+        for _ in range(int(n_ticks)):
+            steps_before = self.train_steps
+            self.tick()
+            if self.train_steps > steps_before:
+                losses.append([self.dqn.step_t, self.last_loss])
+            if self.dqn.step_t >= next_log:
+                m = self.transitions - n0
+                if m > 0:
+                    rewards.append([self.dqn.step_t, (self.reward_sum - r0) / m])
+                    rows.append([self.dqn.step_t, (self.reward_sum - r0) / m])
+                r0, n0, next_log = self.reward_sum, self.transitions, next_log + log_every
+            if out_dir is not None and self.dqn.step_t >= next_save:
+                self.save(os.path.join(out_dir, "MyModel.pt"))
+                next_save += save_every
+        if out_dir is not None:
+            import numpy as np
+            os.makedirs(out_dir, exist_ok=True)
+            np.savetxt(os.path.join(out_dir, "temp_reward.csv"), np.asarray(rewards).reshape(-1, 2), delimiter=",")
+            np.savetxt(os.path.join(out_dir, "temp_loss.csv"), np.asarray(losses).reshape(-1, 2), delimiter=",")
+            with open(os.path.join(out_dir, "reward_data.csv"), "w") as f:
+                f.write("Step,Reward\n")
+                for step, rew in rows:
+                    f.write(f"{step},{rew}\n")
+            self.save(os.path.join(out_dir, "Model_Policy.pt"))
+            torch.save({k: v.detach().cpu() for k, v in self.target_net.state_dict().items()}, os.path.join(out_dir, "Model_Target.pt"))
+        return rewards, losses
+
+    def load(self, path: str):
+        """Resume from a ``MyModel.pt`` / ``Model_Policy.pt`` state dict (the reference's or ours)."""
+        sd = torch.load(path, map_location=self.dev)
+        self.policy_net.load_state_dict(sd)
+        self.target_net.load_state_dict(sd)
+
 
 def dqn_targets(q1, batch1, a, r, term, off_s, n_s1, off_s1, fro1, n_nodes_s: int, gamma: float):
     """policy.py:153-178 without the Python loop: y = r (+ gamma * max of the next state's last ``fro1`` Q-values unless

@@ -155,3 +155,24 @@ def test_vectorised_a2c_trainer_runs_segments_and_learns():
     after = torch.cat([p.detach().flatten() for p in list(actor.parameters()) + list(critic.parameters())])
     assert not torch.equal(before, after) and torch.isfinite(after).all()
     env.close()
+
+
+def test_training_run_leaves_the_reference_artefacts_and_resumes(tmp_path):
+    """VecDQNTrainer.run writes what DeepQ.running writes (policy.py:192-209): reward / loss CSVs and state dicts that load back
+    into the drop-in modules (and, by the layout test, into the reference's)."""
+    from drl_graph_exploration_b200 import Networks
+    env, tr = _make(B=16, seed=900)
+    tr.dqn.BATCH = 8
+    rewards, losses = tr.run(45, out_dir=str(tmp_path), log_every=20)
+    assert len(losses) > 0 and len(rewards) > 0 and all(-1.0 <= r <= 1.0 for _, r in rewards)
+    for name in ("temp_reward.csv", "temp_loss.csv", "reward_data.csv", "Model_Policy.pt", "Model_Target.pt"):
+        assert (tmp_path / name).exists(), name
+    assert (tmp_path / "reward_data.csv").read_text().splitlines()[0] == "Step,Reward"
+    assert np.loadtxt(tmp_path / "temp_loss.csv", delimiter=",").reshape(-1, 2).shape[0] == len(losses)
+    sd = torch.load(tmp_path / "Model_Policy.pt")
+    fresh = Networks.GCN()
+    fresh.load_state_dict(sd)
+    assert all(torch.equal(sd[k].cpu(), v.detach().cpu()) for k, v in tr.policy_net.state_dict().items())
+    tr.load(str(tmp_path / "Model_Policy.pt"))
+    assert all(torch.equal(a, b) for a, b in zip(tr.policy_net.state_dict().values(), tr.target_net.state_dict().values()))
+    env.close()
