@@ -143,8 +143,21 @@ class TopKPooling(torch.nn.Module):
         return x, torch.stack([row[keep], col[keep]]), edge_attr[keep], batch[perm], perm, score[perm]
 
 
-def _augment_adj(edge_index, edge_weight, num_nodes):
-    """Networks.py:216-225: add_self_loops -> sort -> spspmm(A, A) (coalesced) -> remove_self_loops."""
+def _augment_adj(edge_index, edge_weight, num_nodes, batch=None, n_graphs=None):
+    """Networks.py:216-225: add_self_loops -> sort -> spspmm(A, A) (coalesced) -> remove_self_loops.  On the GPU (inference and
+    training alike -- the edge weights carry no gradient) the block-diagonal batch goes through the native row-accumulator
+    kernels (gnn.augment_adj); the torch.sparse path below is the generic one (CPU tensors, graphs above 1024 nodes)."""
+    if edge_index.is_cuda and not edge_weight.requires_grad:
+        if batch is None:
+            gptr, mx, bt = torch.tensor([0, num_nodes], device=edge_index.device), num_nodes, None
+        else:
+            G = int(n_graphs) if n_graphs is not None else (int(batch.max()) + 1 if batch.numel() else 0)
+            counts = torch.bincount(batch, minlength=G)
+            gptr = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)])
+            mx, bt = (int(counts.max()) if G else 0), batch
+        out = gnn.augment_adj(edge_index, edge_weight.float(), num_nodes, bt, gptr, mx) if num_nodes > 0 else None
+        if out is not None:
+            return out
     loop = torch.arange(num_nodes, dtype=edge_index.dtype, device=edge_index.device)
     ei = torch.cat([edge_index, torch.stack([loop, loop])], dim=1)
     ew = torch.cat([edge_weight, edge_weight.new_ones(num_nodes)])
@@ -290,7 +303,7 @@ class GraphUNet(torch.nn.Module):
         x = self.act(self.down_convs[0](x, gs))
         xs, gss, perms = [x], [gs], []
         for i in range(1, self.depth + 1):
-            ei, ew = _augment_adj(ei, ew, x.size(0))
+            ei, ew = _augment_adj(ei, ew, x.size(0), batch)
             x, ei, ew, batch, perm, _ = self.pools[i - 1](x, ei, ew, batch)
             gs = gnn.GraphStructure(ei, ew, x.size(0))
             x = self.act(self.down_convs[i](x, gs))

@@ -366,3 +366,77 @@ extern "C" int dge_gru_gates(int N, int C, const float *gi, const float *gh, con
       reinterpret_cast<const float4 *>(b_hh), reinterpret_cast<const float4 *>(h), relu, reinterpret_cast<float4 *>(out));
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+// ------------------------------------------------------------------ g-U-Net: augmented adjacency ---------------
+// GraphUNet.augment_adj (Networks.py:216-225 via PyG): A <- remove_self_loops((A + I)(A + I)), coalesced (sorted by row, col).
+// The reference goes through torch_sparse.spspmm (cuSPARSE SpGEMM + sort + coalesce); the batched exploration graphs are
+// block diagonal with blocks of at most a few hundred nodes, so one warp per row accumulates its output row DENSELY over the
+// columns of its own graph in shared memory: for every k in N(i) + {i} (in edge order: deterministic sums), the lanes add
+// a_ik * a_kj for j in N(k) + {k}.  Two passes (count, fill) around the existing exclusive scan; columns come out ascending.
+namespace {
+constexpr int AUG_MAXG = 1024;   // largest graph (nodes) the shared-memory row accumulator holds
+constexpr int AUG_WARPS = 8;
+
+template <bool FILL>
+__global__ void __launch_bounds__(AUG_WARPS * 32) k_augment_adj(int N, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ perm,
+                                                                const int64_t *__restrict__ dst, const float *__restrict__ w,
+                                                                const int64_t *__restrict__ batch, const int64_t *__restrict__ gptr,
+                                                                int32_t *__restrict__ cnt, const int32_t *__restrict__ outptr,
+                                                                int64_t *__restrict__ orow, int64_t *__restrict__ ocol, float *__restrict__ oval) {
+  __shared__ float acc_all[AUG_WARPS][AUG_MAXG];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * AUG_WARPS + warp;
+  if (i >= N) return;
+  float *acc = acc_all[warp];
+  const int g = batch ? (int)batch[i] : 0;
+  const int n0 = (int)gptr[g], ng = (int)gptr[g + 1] - n0;
+  for (int j = lane; j < ng; j += 32) acc[j] = 0.f;
+  __syncwarp();
+  const int lo = rowptr[i], hi = rowptr[i + 1];
+  for (int p = lo - 1; p < hi; ++p) {              // p == lo - 1: the added self loop (k = i, weight 1)
+    const int k = (p < lo) ? i : (int)dst[perm[p]];
+    const float aik = (p < lo) ? 1.0f : w[perm[p]];
+    const int klo = rowptr[k], khi = rowptr[k + 1];
+    for (int q = klo + lane; q < khi; q += 32) {   // distinct columns inside one row of a coalesced input: no lane conflicts
+      const int e = perm[q];
+      acc[(int)dst[e] - n0] += aik * w[e];
+    }
+    __syncwarp();
+    if (lane == 0) acc[k - n0] += aik;             // a_kk = 1
+    __syncwarp();
+  }
+  // compact the non-zero columns (ascending), dropping the diagonal
+  int base = FILL ? outptr[i] : 0, total = 0;
+  for (int j0 = 0; j0 < ng; j0 += 32) {
+    const int j = j0 + lane;
+    const float v = (j < ng) ? acc[j] : 0.f;
+    const bool keep = j < ng && v != 0.f && (n0 + j) != i;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (FILL && keep) {
+      const int o = base + total + __popc(m & ((1u << lane) - 1));
+      orow[o] = i; ocol[o] = n0 + j; oval[o] = v;
+    }
+    total += __popc(m);
+  }
+  if (!FILL && lane == 0) cnt[i] = total;
+}
+}  // namespace
+
+// pass 1: cnt[N] = entries of every output row; the caller scans (dge_gnn_scan) and sizes the outputs; pass 2 fills them.
+extern "C" int dge_gnn_augment_adj_count(int N, const int32_t *rowptr_src, const int32_t *perm_src, const int64_t *dst, const float *w,
+                                         const int64_t *batch, const int64_t *graph_ptr, int max_graph_nodes, int32_t *cnt, int32_t *outptr, void *stream) {
+  if (N <= 0 || !rowptr_src || !perm_src || !graph_ptr || !cnt || !outptr) return -1;
+  if (max_graph_nodes > AUG_MAXG) return -3;      // larger graphs: the caller uses its generic path
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_augment_adj<false><<<cdiv(N, AUG_WARPS), AUG_WARPS * 32, 0, st>>>(N, rowptr_src, perm_src, dst, w, batch, graph_ptr, cnt, nullptr, nullptr, nullptr, nullptr);
+  k_scan<<<1, 1024, 0, st>>>(N, cnt, outptr);
+  return CK();
+}
+extern "C" int dge_gnn_augment_adj_fill(int N, const int32_t *rowptr_src, const int32_t *perm_src, const int64_t *dst, const float *w,
+                                        const int64_t *batch, const int64_t *graph_ptr, const int32_t *outptr, int64_t *out_row, int64_t *out_col,
+                                        float *out_val, void *stream) {
+  if (N <= 0 || !rowptr_src || !perm_src || !graph_ptr || !outptr || !out_row || !out_col || !out_val) return -1;
+  k_augment_adj<true><<<cdiv(N, AUG_WARPS), AUG_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(N, rowptr_src, perm_src, dst, w, batch, graph_ptr, nullptr,
+                                                                                                      outptr, out_row, out_col, out_val);
+  return CK();
+}

@@ -377,3 +377,39 @@ def gru_cell_inference(m: torch.Tensor, h: torch.Tensor, rnn: torch.nn.GRUCell, 
         raise DgeError(f"dge_gru_gates failed ({rc})")
     launch_count += 1
     return out
+
+
+def augment_adj(edge_index: torch.Tensor, edge_weight: torch.Tensor, num_nodes: int, batch: Optional[torch.Tensor], graph_ptr: torch.Tensor,
+                max_graph_nodes: int):
+    """GraphUNet.augment_adj on the native kernels: remove_self_loops((A + I)^2), entries sorted by (row, col) like
+    torch_sparse.spspmm's coalesced output.  The edge list must be coalesced (no duplicate pairs).  Returns None when a graph
+    is too large for the shared-memory row accumulator (the caller then takes its generic path)."""
+    global launch_count
+    _need_cuda(edge_index, "augment_adj")
+    L = _lib()
+    if not hasattr(L, "_augment_ready"):
+        L.dge_gnn_augment_adj_count.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp]
+        L.dge_gnn_augment_adj_fill.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L._augment_ready = True
+    if max_graph_nodes > 1024:
+        return None
+    dev, N = edge_index.device, int(num_nodes)
+    gs = GraphStructure(edge_index, edge_weight, N)
+    rp, pm = gs.rowptr_src, gs.perm_src
+    cnt = torch.empty(N, dtype=torch.int32, device=dev)
+    outptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    gp = graph_ptr.long().contiguous()
+    bt = None if batch is None else batch.long().contiguous()
+    with torch.cuda.device(dev):
+        rc = L.dge_gnn_augment_adj_count(N, _p(rp), _p(pm), _p(gs.dst), _p(gs.weight), _p(bt), _p(gp), int(max_graph_nodes), _p(cnt), _p(outptr), _st(dev))
+    if rc:
+        raise DgeError(f"dge_gnn_augment_adj_count failed ({rc})")
+    E2 = int(outptr[N].item())                       # host sync: sizes the output (spspmm synchronises for the same reason)
+    row, col = torch.empty(max(E2, 1), dtype=torch.int64, device=dev), torch.empty(max(E2, 1), dtype=torch.int64, device=dev)
+    val = torch.empty(max(E2, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.dge_gnn_augment_adj_fill(N, _p(rp), _p(pm), _p(gs.dst), _p(gs.weight), _p(bt), _p(gp), _p(outptr), _p(row), _p(col), _p(val), _st(dev))
+    if rc:
+        raise DgeError(f"dge_gnn_augment_adj_fill failed ({rc})")
+    launch_count += 3
+    return torch.stack([row[:E2], col[:E2]]), val[:E2]

@@ -60,6 +60,17 @@ int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi
 int dge_gru_gates(int N, int C, const float *gi, const float *gh, const float *b_ih, const float *b_hh, const float *h, int relu,
                   float *out, void *stream);
 
+/* ---- g-U-Net: GraphUNet.augment_adj (Networks.py:216-225: add_self_loops -> spspmm(A, A) -> remove_self_loops, coalesced)
+ * for a block-diagonal batch.  rowptr_src / perm_src = source-sorted CSR of the edge list (dge_gnn_csr_build on edge_index[0]),
+ * dst = edge_index[1], w = edge weights, batch [N] graph of every node (nullable: one graph), graph_ptr [G+1] node ranges.
+ * Pass 1 counts the entries of every output row and scans them into outptr [N+1] (outptr[N] = E', which the caller reads to
+ * size the outputs); pass 2 writes (row, col, value) sorted by (row, col).  Returns -3 when a graph has more than 1024 nodes. */
+int dge_gnn_augment_adj_count(int N, const int32_t *rowptr_src, const int32_t *perm_src, const int64_t *dst, const float *w,
+                              const int64_t *batch, const int64_t *graph_ptr, int max_graph_nodes, int32_t *cnt, int32_t *outptr, void *stream);
+int dge_gnn_augment_adj_fill(int N, const int32_t *rowptr_src, const int32_t *perm_src, const int64_t *dst, const float *w,
+                             const int64_t *batch, const int64_t *graph_ptr, const int32_t *outptr, int64_t *out_row, int64_t *out_col,
+                             float *out_val, void *stream);
+
 /* ---- the whole DQN Q-network forward at inference (Networks.GCN.forward with prob = 0, Networks.py:18-28: two
  * GCNConv(improved) + ReLU and the Linear(C,1) head) in ONE call / three launches: fused first layer with the TF32 split
  * in its epilogue -> dge_gemm_tf32x3 -> aggregate + bias + ReLU + head.  rowptr/perm = destination-sorted CSR, src =

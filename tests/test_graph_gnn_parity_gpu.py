@@ -278,3 +278,29 @@ def test_csr_build_and_gcn_norm_on_a_large_batch():
     eok = ok[ei[0]] & ok[ei[1]]
     assert torch.allclose(norm.double()[eok], ref_norm[eok], rtol=2e-6, atol=1e-9)
     assert torch.allclose(selfnorm.double()[ok], (dis * selfw * dis)[ok], rtol=2e-6, atol=1e-9)
+
+
+def test_native_augment_adj_equals_sparse_matmul_path():
+    """gnn.augment_adj (row-accumulator kernels) against the torch.sparse restatement of GraphUNet.augment_adj
+    (add_self_loops -> spspmm(A, A) coalesced -> remove_self_loops): same (row, col) list in the same order, same values."""
+    from drl_graph_exploration_b200 import Networks
+    dev = torch.device("cuda")
+    batch = _random_graph_batch(np.random.default_rng(8), 9, dev)
+    ei, ew, bt, n = batch.edge_index, batch.edge_attr, batch.batch, batch.x.size(0)
+    for level in range(2):                                       # the second round squares an already squared (denser) adjacency
+        nat_i, nat_w = Networks._augment_adj(ei, ew, n, bt)
+        loop = torch.arange(n, device=dev)
+        A = torch.sparse_coo_tensor(torch.cat([ei, torch.stack([loop, loop])], dim=1), torch.cat([ew, ew.new_ones(n)]), (n, n)).coalesce()
+        A2 = torch.sparse.mm(A, A).coalesce()
+        keep = A2.indices()[0] != A2.indices()[1]
+        ref_i, ref_w = A2.indices()[:, keep], A2.values()[keep]
+        assert torch.equal(nat_i, ref_i), level
+        assert torch.allclose(nat_w, ref_w, rtol=1e-5, atol=1e-6), level
+        assert bool((bt[nat_i[0]] == bt[nat_i[1]]).all())        # stays block diagonal
+        ei, ew = nat_i, nat_w
+    # a single graph without a batch vector
+    one = bt == 0
+    n1 = int(one.sum())
+    e1 = one[batch.edge_index[0]]
+    i1, w1 = Networks._augment_adj(batch.edge_index[:, e1], batch.edge_attr[e1], n1, None)
+    assert i1.size(1) > 0 and int(i1.max()) < n1 and bool((i1[0] != i1[1]).all())
