@@ -129,6 +129,13 @@ class TopKPooling(torch.nn.Module):
         n_graphs = int(batch.max()) + 1 if batch.numel() else 0
         counts = torch.bincount(batch, minlength=n_graphs)
         k = torch.ceil(self.ratio * counts.to(score.dtype)).long()
+        if x.is_cuda and n_graphs > 0 and not edge_attr.requires_grad:
+            max_n, n_kept = (int(v) for v in torch.stack([counts.max(), k.sum()]).tolist())
+            if max_n <= 1024:   # native: one CTA per graph sorts its scores; edges filtered + relabelled by a flag / scan / fill pass
+                zero = counts.new_zeros(1)
+                perm, newid = gnn.topk_pool(score.detach(), torch.cat([zero, torch.cumsum(counts, 0)]), torch.cat([zero, torch.cumsum(k, 0)]), max_n, n_kept)
+                ei2, ew2 = gnn.filter_adj(edge_index, edge_attr, newid)
+                return x[perm] * score[perm].view(-1, 1), ei2, ew2, batch[perm], perm, score[perm]
         # per-graph descending order: sort by (graph, -score) with a stable two-key sort
         order = torch.sort(score, descending=True, stable=True)[1]
         order = order[torch.sort(batch[order], stable=True)[1]]

@@ -440,3 +440,72 @@ extern "C" int dge_gnn_augment_adj_fill(int N, const int32_t *rowptr_src, const 
                                                                                                       outptr, out_row, out_col, out_val);
   return CK();
 }
+
+// ------------------------------------------------------------------ g-U-Net: top-k pooling ---------------------
+// TopKPooling (Networks.py:150-158 via PyG topk + filter_adj): per graph keep the k = ceil(ratio n) nodes with the highest
+// score, in descending score order (ties: lower node index first, like a stable descending sort), relabel, and keep the edges
+// whose two ends survive (in their original order).  One CTA per graph: bitonic sort of (score, index) in shared memory.
+namespace {
+constexpr int TOPK_MAXG = 1024;
+__global__ void __launch_bounds__(512) k_topk_pool(const float *__restrict__ score, const int64_t *__restrict__ gptr, const int64_t *__restrict__ kptr,
+                                                   int64_t *__restrict__ perm, int64_t *__restrict__ newid) {
+  __shared__ float ss[TOPK_MAXG];
+  __shared__ int si[TOPK_MAXG];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const int n0 = (int)gptr[g], n = (int)gptr[g + 1] - n0;
+  const int k0 = (int)kptr[g], k = (int)kptr[g + 1] - k0;
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int i = tid; i < P; i += blockDim.x) { ss[i] = (i < n) ? score[n0 + i] : -INFINITY; si[i] = (i < n) ? i : 0x7fffffff; }
+  __syncthreads();
+  // "a before b": higher score first, then lower index (NaN scores do not occur: tanh of finite values)
+  auto before = [](float sa, int ia, float sb, int ib) { return sa > sb || (sa == sb && ia < ib); };
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool up = ((lo & size) == 0);                  // ascending position = earlier in the final order
+        const float sa = ss[lo], sb = ss[hi];
+        const int ia = si[lo], ib = si[hi];
+        const bool swap = up ? before(sb, ib, sa, ia) : before(sa, ia, sb, ib);
+        if (swap) { ss[lo] = sb; ss[hi] = sa; si[lo] = ib; si[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += blockDim.x) newid[n0 + si[i]] = (i < k) ? (int64_t)(k0 + i) : (int64_t)-1;
+  for (int i = tid; i < k; i += blockDim.x) perm[k0 + i] = n0 + si[i];
+}
+__global__ void k_edge_keep(int E, const int64_t *__restrict__ src, const int64_t *__restrict__ dst, const int64_t *__restrict__ newid, int32_t *flag) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) flag[e] = (newid[src[e]] >= 0 && newid[dst[e]] >= 0) ? 1 : 0;
+}
+__global__ void k_edge_compact(int E, const int64_t *__restrict__ src, const int64_t *__restrict__ dst, const float *__restrict__ w,
+                               const int64_t *__restrict__ newid, const int32_t *__restrict__ flag, const int32_t *__restrict__ pos,
+                               int64_t *__restrict__ osrc, int64_t *__restrict__ odst, float *__restrict__ ow) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E && flag[e]) { const int o = pos[e]; osrc[o] = newid[src[e]]; odst[o] = newid[dst[e]]; ow[o] = w[e]; }
+}
+}  // namespace
+
+extern "C" int dge_gnn_topk_pool(int G, int max_graph_nodes, const float *score, const int64_t *graph_ptr, const int64_t *k_ptr, int64_t *perm,
+                                 int64_t *newid, void *stream) {
+  if (G <= 0 || !score || !graph_ptr || !k_ptr || !perm || !newid) return -1;
+  if (max_graph_nodes > TOPK_MAXG) return -3;
+  k_topk_pool<<<G, 512, 0, static_cast<cudaStream_t>(stream)>>>(score, graph_ptr, k_ptr, perm, newid);
+  return CK();
+}
+// filter_adj: flag + exclusive scan (pos [E+1], pos[E] = E') in the first call, compaction in the second
+extern "C" int dge_gnn_filter_adj_count(int E, const int64_t *src, const int64_t *dst, const int64_t *newid, int32_t *flag, int32_t *pos, void *stream) {
+  if (E <= 0 || !src || !dst || !newid || !flag || !pos) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_edge_keep<<<cdiv(E, 256), 256, 0, st>>>(E, src, dst, newid, flag);
+  k_scan<<<1, 1024, 0, st>>>(E, flag, pos);
+  return CK();
+}
+extern "C" int dge_gnn_filter_adj_fill(int E, const int64_t *src, const int64_t *dst, const float *w, const int64_t *newid, const int32_t *flag,
+                                       const int32_t *pos, int64_t *out_src, int64_t *out_dst, float *out_w, void *stream) {
+  if (E <= 0 || !src || !dst || !w || !newid || !flag || !pos || !out_src || !out_dst || !out_w) return -1;
+  k_edge_compact<<<cdiv(E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(E, src, dst, w, newid, flag, pos, out_src, out_dst, out_w);
+  return CK();
+}

@@ -413,3 +413,51 @@ def augment_adj(edge_index: torch.Tensor, edge_weight: torch.Tensor, num_nodes: 
         raise DgeError(f"dge_gnn_augment_adj_fill failed ({rc})")
     launch_count += 3
     return torch.stack([row[:E2], col[:E2]]), val[:E2]
+
+
+def topk_pool(score: torch.Tensor, graph_ptr: torch.Tensor, k_ptr: torch.Tensor, max_graph_nodes: int, n_kept: int):
+    """PyG ``topk``: per graph the k best-scored nodes in descending order -> (perm [n_kept], newid [N])."""
+    global launch_count
+    _need_cuda(score, "topk_pool")
+    L = _lib()
+    if not hasattr(L, "_topk_ready"):
+        L.dge_gnn_topk_pool.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.dge_gnn_filter_adj_count.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.dge_gnn_filter_adj_fill.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L._topk_ready = True
+    dev, N = score.device, score.numel()
+    perm = torch.empty(max(n_kept, 1), dtype=torch.int64, device=dev)
+    newid = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+    G = graph_ptr.numel() - 1
+    with torch.cuda.device(dev):
+        rc = L.dge_gnn_topk_pool(G, int(max_graph_nodes), _p(score.contiguous().float()), _p(graph_ptr.long().contiguous()),
+                                 _p(k_ptr.long().contiguous()), _p(perm), _p(newid), _st(dev))
+    if rc:
+        raise DgeError(f"dge_gnn_topk_pool failed ({rc})")
+    launch_count += 1
+    return perm[:n_kept], newid[:N]
+
+
+def filter_adj(edge_index: torch.Tensor, edge_weight: torch.Tensor, newid: torch.Tensor):
+    """PyG ``filter_adj``: edges whose ends both survive the pooling, relabelled, original order."""
+    global launch_count
+    L = _lib()
+    dev, E = edge_index.device, edge_index.size(1)
+    if E == 0:
+        return edge_index, edge_weight
+    ei = edge_index.contiguous()
+    src, dst, w = ei[0].contiguous(), ei[1].contiguous(), edge_weight.contiguous().float()
+    flag, pos = torch.empty(E, dtype=torch.int32, device=dev), torch.empty(E + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.dge_gnn_filter_adj_count(E, _p(src), _p(dst), _p(newid), _p(flag), _p(pos), _st(dev))
+    if rc:
+        raise DgeError(f"dge_gnn_filter_adj_count failed ({rc})")
+    E2 = int(pos[E].item())                                  # host sync: sizes the pooled edge list
+    out = torch.empty(2, max(E2, 1), dtype=torch.int64, device=dev)
+    ow = torch.empty(max(E2, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.dge_gnn_filter_adj_fill(E, _p(src), _p(dst), _p(w), _p(newid), _p(flag), _p(pos), _p(out[0]), _p(out[1]), _p(ow), _st(dev))
+    if rc:
+        raise DgeError(f"dge_gnn_filter_adj_fill failed ({rc})")
+    launch_count += 3
+    return out[:, :E2], ow[:E2]

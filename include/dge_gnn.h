@@ -71,6 +71,17 @@ int dge_gnn_augment_adj_fill(int N, const int32_t *rowptr_src, const int32_t *pe
                              const int64_t *batch, const int64_t *graph_ptr, const int32_t *outptr, int64_t *out_row, int64_t *out_col,
                              float *out_val, void *stream);
 
+/* ---- g-U-Net: TopKPooling (Networks.py:150-158 via PyG topk / filter_adj).  score [N] (tanh(x.w/|w|), computed by the caller),
+ * graph_ptr / k_ptr [G+1] = node ranges and prefix sums of k = ceil(ratio n) per graph.  perm [sum k]: kept nodes, per graph in
+ * descending score order (ties: lower index first); newid [N]: new index of a kept node, -1 otherwise.  Graphs of at most 1024
+ * nodes (else -3).  filter_adj keeps the edges whose ends both survive, relabelled, in their original order: ..._count writes
+ * flag [E] and pos [E+1] (pos[E] = number of kept edges, read by the caller to size the outputs), ..._fill compacts.          */
+int dge_gnn_topk_pool(int G, int max_graph_nodes, const float *score, const int64_t *graph_ptr, const int64_t *k_ptr, int64_t *perm,
+                      int64_t *newid, void *stream);
+int dge_gnn_filter_adj_count(int E, const int64_t *src, const int64_t *dst, const int64_t *newid, int32_t *flag, int32_t *pos, void *stream);
+int dge_gnn_filter_adj_fill(int E, const int64_t *src, const int64_t *dst, const float *w, const int64_t *newid, const int32_t *flag,
+                            const int32_t *pos, int64_t *out_src, int64_t *out_dst, float *out_w, void *stream);
+
 /* ---- the whole DQN Q-network forward at inference (Networks.GCN.forward with prob = 0, Networks.py:18-28: two
  * GCNConv(improved) + ReLU and the Linear(C,1) head) in ONE call / three launches: fused first layer with the TF32 split
  * in its epilogue -> dge_gemm_tf32x3 -> aggregate + bias + ReLU + head.  rowptr/perm = destination-sorted CSR, src =

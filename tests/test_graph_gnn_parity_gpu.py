@@ -304,3 +304,32 @@ def test_native_augment_adj_equals_sparse_matmul_path():
     e1 = one[batch.edge_index[0]]
     i1, w1 = Networks._augment_adj(batch.edge_index[:, e1], batch.edge_attr[e1], n1, None)
     assert i1.size(1) > 0 and int(i1.max()) < n1 and bool((i1[0] != i1[1]).all())
+
+
+def test_native_topk_pooling_equals_the_sort_based_path():
+    """gnn.topk_pool / gnn.filter_adj against the two-key stable sort + boolean-mask restatement of PyG topk / filter_adj:
+    same perm (order included, ties by lower index), same pooled edge list in the same order."""
+    from drl_graph_exploration_b200 import gnn
+    dev = torch.device("cuda")
+    b = _random_graph_batch(np.random.default_rng(12), 11, dev)
+    n = b.x.size(0)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    score = torch.tanh(torch.randn(n, generator=g)).to(dev)
+    score[5:9] = score[5]                                          # exact ties inside a graph
+    score[-3:] = score[-3]
+    counts = torch.bincount(b.batch)
+    k = torch.ceil(0.5 * counts.float()).long()
+    zero = counts.new_zeros(1)
+    perm, newid = gnn.topk_pool(score, torch.cat([zero, counts.cumsum(0)]), torch.cat([zero, k.cumsum(0)]), int(counts.max()), int(k.sum()))
+    order = torch.sort(score, descending=True, stable=True)[1]
+    order = order[torch.sort(b.batch[order], stable=True)[1]]
+    start = counts.cumsum(0) - counts
+    rank = torch.arange(n, device=dev) - start[b.batch[order]]
+    perm_ref = order[rank < k[b.batch[order]]]
+    assert torch.equal(perm, perm_ref)
+    mask = perm_ref.new_full((n,), -1); mask[perm_ref] = torch.arange(perm_ref.numel(), device=dev)
+    assert torch.equal(newid, mask)
+    ei2, ew2 = gnn.filter_adj(b.edge_index, b.edge_attr, newid)
+    row, col = mask[b.edge_index[0]], mask[b.edge_index[1]]
+    keep = (row >= 0) & (col >= 0)
+    assert torch.equal(ei2, torch.stack([row[keep], col[keep]])) and torch.equal(ew2, b.edge_attr[keep])
