@@ -6,6 +6,7 @@
 #include "dge_oracle.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cassert>
 #include <cstring>
 #include <limits>
@@ -237,6 +238,75 @@ void virtual_map_rebuild(const Config &cfg, int T, const double *pose, const dou
   }
 }
 
+
+// Iteration order of the reference's `std::unordered_map<unsigned, LandmarkBeliefState>` (Simulation2D.h:269) after the keys
+// 0 .. n-1 were emplaced in order into a fresh map (Simulator2D.cpp:448-463).  The order decides which landmark consumes which
+// noise draw in Simulator2D::measure (the kd-tree is filled by iterating the map, Simulator2D.cpp:335-340), so it is part of the
+// arithmetic.  It depends on the libstdc++ that built the reference: the host's std::unordered_map (GCC 13: 7,6,..,0 for n = 8)
+// does NOT reproduce the reference's result files; the hashtable of GCC 5 .. 7 (the compilers of the reference's era: Ubuntu
+// 16.04 / 18.04) does -- every ordered pair the golden CSVs can confirm agrees with it (tests/test_oracle_cpu.py), e.g.
+// 7,6,5,4,0,1,2,3 for n = 8.  That hashtable is restated here: singly linked node list + bucket table, insertion at the
+// bucket's begin (`_M_insert_bucket_begin`), rehash by re-linking in list order (`_M_rehash_aux`, unique keys), and the prime
+// rehash policy of those releases (`__n_elt + __n_ins >= _M_next_resize`, 12-entry fast table, growth factor 2).
+std::vector<uint32_t> reference_unordered_map_order(int n) {
+  static const unsigned long primes[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 103, 109, 113, 127,
+                                         137, 139, 149, 157, 167, 179, 193, 199, 211, 227, 241, 257, 277, 293, 313, 337, 359, 383, 409, 439, 467, 503, 541,
+                                         577, 619, 661, 709, 761, 823, 887, 953, 1031, 1109, 1193, 1289, 1381, 1493, 1613, 1741, 1879, 2029, 2179, 2357};
+  static const unsigned char fast_bkt[12] = {2, 2, 2, 3, 5, 5, 7, 7, 11, 11, 11, 11};
+  size_t next_resize = 0, n_bkt = 1;
+  auto next_bkt = [&](size_t want) -> size_t {
+    if (want <= 11) { next_resize = (size_t)std::ceil(fast_bkt[want] * 1.0L); return fast_bkt[want]; }
+    const unsigned long *p = std::lower_bound(primes, primes + sizeof(primes) / sizeof(primes[0]), (unsigned long)want);
+    next_resize = (size_t)std::ceil(*p * 1.0L);
+    return *p;
+  };
+  const int HEAD = -1;                       // the list's before-begin node
+  std::vector<int> nxt(n, -2);               // node = key
+  int head_next = -2;                        // -2 = null
+  std::vector<int> bucket(1, -3);            // bucket -> node BEFORE its first node (HEAD or a key), -3 = empty
+  auto next_of = [&](int node) -> int & { return node == HEAD ? head_next : nxt[node]; };
+  for (int key = 0; key < n; ++key) {
+    const size_t n_elt = (size_t)key;
+    if (n_elt + 1 >= next_resize) {          // _Prime_rehash_policy::_M_need_rehash
+      const long double min_bkts = (long double)(n_elt + 1);
+      if (min_bkts >= (long double)n_bkt) {
+        const size_t nb = next_bkt(std::max<size_t>((size_t)std::floor(min_bkts) + 1, n_bkt * 2));
+        std::vector<int> nbk(nb, -3);        // _M_rehash_aux(n, true_type)
+        int p = head_next;
+        head_next = -2;
+        size_t bbegin_bkt = 0;
+        while (p != -2) {
+          const int pn = nxt[p];
+          const size_t b = (size_t)p % nb;
+          if (nbk[b] == -3) {
+            nxt[p] = head_next; head_next = p; nbk[b] = HEAD;
+            if (nxt[p] != -2) nbk[bbegin_bkt] = p;
+            bbegin_bkt = b;
+          } else {
+            nxt[p] = next_of(nbk[b]); next_of(nbk[b]) = p;
+          }
+          p = pn;
+        }
+        bucket.swap(nbk);
+        n_bkt = nb;
+      } else {
+        next_resize = (size_t)std::floor(n_bkt * 1.0L);
+      }
+    }
+    const size_t b = (size_t)key % n_bkt;    // _M_insert_bucket_begin
+    if (bucket[b] != -3) {
+      nxt[key] = next_of(bucket[b]); next_of(bucket[b]) = key;
+    } else {
+      nxt[key] = head_next; head_next = key;
+      if (nxt[key] != -2) bucket[(size_t)nxt[key] % n_bkt] = key;
+      bucket[b] = HEAD;
+    }
+  }
+  std::vector<uint32_t> order;
+  for (int p = head_next; p != -2; p = nxt[p]) order.push_back((uint32_t)p);
+  return order;
+}
+
 // ==================================================================== Env ===
 Env::Env(const Config &c) : cfg(c) { setup_grid(); }
 
@@ -251,10 +321,8 @@ void Env::setup_grid() {  // VirtualMap.cpp:318-340
 void Env::add_true_landmarks(const std::vector<double> &xy) {
   Lt = static_cast<int>(xy.size() / 2);
   lm_x.resize(Lt); lm_y.resize(Lt);
-  std::unordered_map<unsigned int, int> umap;  // Simulation2D.h:269 ; q6
-  for (int i = 0; i < Lt; ++i) { lm_x[i] = xy[2 * i]; lm_y[i] = xy[2 * i + 1]; umap.emplace(static_cast<unsigned>(i), i); }
-  scan_id.clear();
-  for (const auto &it : umap) scan_id.push_back(it.first);  // Simulator2D.cpp:335-340
+  for (int i = 0; i < Lt; ++i) { lm_x[i] = xy[2 * i]; lm_y[i] = xy[2 * i + 1]; }
+  scan_id = reference_unordered_map_order(Lt);  // Simulation2D.h:269, Simulator2D.cpp:335-340 ; q6
   observed.assign(Lt, 0);
   lin_l.assign(2 * Lt, 0); est_l.assign(2 * Lt, 0); delta_l.assign(2 * Lt, 0);
   land_cov.assign(Lt, M2{{0, 0, 0, 0}}); land_info.assign(Lt, M2{{0, 0, 0, 0}});

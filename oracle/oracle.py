@@ -16,8 +16,12 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(_LIB_PATH):
+    # always through make: it rebuilds only when a source is newer than the library (a stale checker is worse than a slow one)
+    try:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    except (OSError, subprocess.CalledProcessError):
+        if not os.path.exists(_LIB_PATH):
+            raise
     return _LIB_PATH
 
 

@@ -23,9 +23,9 @@ arrs["max_unc"] = np.array([float(r["Max localization uncertainty"]) for r in ro
 np.savez_compressed(os.path.join(OUT, "ref_40_DQN_GCN_seed0.npz"), **arrs)
 print("wrote", os.path.join(OUT, "ref_40_DQN_GCN_seed0.npz"))
 
-# ref_DQN_GCN_multi.npz : first 60 rows (landmark error, map entropy, max localisation uncertainty) of further episodes of
+# ref_DQN_GCN_multi.npz : first 60 rows (landmark error, map entropy, max localisation uncertainty) of ALL 200 episodes of
 # data/test_result/{40,60,80,100}_DQN_GCN.csv (test.py runs seeds lo = 0..49 per map size, each padded to plot_max_step rows).
-EPISODES = {40: [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11], 60: [0, 1, 2, 3], 80: [0, 1, 2], 100: [0, 1]}
+EPISODES = {ms: list(range(50)) for ms in (40, 60, 80, 100)}      # every episode of the four result files
 multi = {}
 for ms, seeds in EPISODES.items():
     rows = [r for r in csv.DictReader(open(os.path.join(REF, f"data/test_result/{ms}_DQN_GCN.csv"))) if r["Step"]]

@@ -1,8 +1,10 @@
 """CPU tests of the oracle itself (no GPU): structured vs dense SLAM solve, golden CSV tracking,
 basic invariants.  These pin the checker before it is used to check the CUDA path."""
 import csv
+import json
 import math
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -108,57 +110,40 @@ def test_tracks_reference_golden_csv():
                     break
 
 
-def _track_episode(model, map_size, seed, gold, n_steps):
-    """test.py:78-150 on the oracle: reset (with the reference's 'regenerate a environment' rule,
-    exploration_env.py:416-419: no landmark seen after the 4 forced steps -> env_index += 50), then DQN+GCN decisions."""
-    cfg = EnvConfig(map_size=map_size)
-    while True:
-        e = OracleEnv(cfg, seed)
-        for _ in range(4):
-            e.step(RESET_ODOM)
-        if int(np.sum(e.landmarks()["observed"])) >= 1:
-            break
-        seed += 50
-    diff = {40: 1200, 60: 1600, 80: 2000, 100: 2400}[map_size]        # test.py:61-70
-    step, worst = 0, 0.0
-    with torch.no_grad():
-        while step < n_steps:
-            g = e.graph()
-            data = gnn_ref.Graph(torch.tensor(g["features"], dtype=torch.float32), torch.tensor(g["edge_index"]),
-                                 torch.tensor(g["edge_attr"], dtype=torch.float32))
-            q = model(data, 0.0).view(-1).numpy()
-            a = int(np.argmax(q[-g["fro_size"]:]))
-            for act in e.line_plan(*g["frontier_xy"][a]):
-                e.step(act)
-                m = e.metrics()
-                p = e.vmap()["prob"]
-                ent = -(p * np.log(p)).sum() + 0.5 * np.log(0.5) * diff
-                gl, ge, gm = gold[step]
-                dl, dm = abs(m["landmark_error"] - gl) / gl, abs(m["max_traj_uncertainty"] - gm) / gm
-                assert dl < 1e-5 and dm < 1e-5 and abs(ent - ge) < 0.3, (map_size, seed, step, dl, dm, ent - ge)
-                worst = max(worst, dl, dm)
-                step += 1
-                if step >= n_steps:
-                    break
-    return worst
+# (map size, seed, rows that must be followed): a spread over the four result files of the episodes the oracle follows for
+# >= 20 rows (tests/golden/oracle_golden_scan.json holds the full scan of all 200 episodes: 5377 rows followed, 123 episodes
+# for >= 18 rows; regenerate with tests/golden/scan_golden.py).  Several go through the 'regenerate a environment' rule.
+TRACKED = [(40, 1, 40), (40, 3, 30), (40, 8, 25), (40, 10, 35), (40, 12, 45), (40, 14, 40), (40, 24, 45), (40, 42, 45), (40, 46, 55),
+           (60, 2, 30), (60, 4, 55), (60, 7, 55), (60, 17, 55), (60, 21, 45), (60, 38, 55), (60, 40, 50),
+           (80, 1, 45), (80, 2, 45), (80, 6, 55), (80, 16, 55), (80, 24, 50), (80, 39, 45), (80, 49, 40),
+           (100, 0, 45), (100, 6, 55), (100, 16, 55), (100, 26, 50), (100, 28, 50), (100, 37, 55), (100, 48, 55)]
 
 
-# (map size, seed, steps tracked): every episode of the reference's DQN+GCN result files examined so far that the oracle
-# follows for >= 20 steps (17 of 20; 40/5, 40/10 and 60/0 leave the reference's noise stream within 4 steps -- DESIGN.md section 5).
-# Seeds 7, 8, 9, 11 (S = 40) and 0 (S = 80, 100) go through the 'regenerate' rule.
-TRACKED = [(40, 1, 40), (40, 2, 22), (40, 3, 30), (40, 4, 30), (40, 6, 20), (40, 8, 25), (40, 9, 18), (40, 11, 20), (60, 1, 20), (60, 2, 30), (60, 3, 20),
-           (80, 0, 18), (80, 1, 24), (80, 2, 40), (100, 0, 18), (100, 1, 20)]
+@pytest.fixture(scope="module")
+def golden_scan():
+    sys.path.insert(0, GOLD)
+    import scan_golden
+    return scan_golden, scan_golden.load_model(), np.load(os.path.join(GOLD, "ref_DQN_GCN_multi.npz"))
 
 
-@pytest.mark.parametrize("map_size,seed,n_steps", TRACKED)
-def test_tracks_more_reference_episodes(map_size, seed, n_steps):
+@pytest.mark.parametrize("map_size,seed,n_rows", TRACKED)
+def test_tracks_more_reference_episodes(golden_scan, map_size, seed, n_rows):
     """Further known-answer data of the reference: other seeds of 40_DQN_GCN.csv and the 60/80/100 m maps
     (tests/golden/ref_DQN_GCN_multi.npz, extracted by make_golden.py), followed end to end with the shipped weights."""
-    gold = np.load(os.path.join(GOLD, "ref_40_DQN_GCN_seed0.npz"))
-    sd = {k[3:]: torch.tensor(gold[k]) for k in gold.files if k.startswith("sd_")}
-    model = gnn_ref.GCN()
-    model.load_state_dict(sd)
-    model.eval()
-    multi = np.load(os.path.join(GOLD, "ref_DQN_GCN_multi.npz"))
-    worst = _track_episode(model, map_size, seed, multi[f"g_{map_size}_{seed}"], n_steps)
-    assert worst < 1e-5
+    scan, model, multi = golden_scan
+    rows, worst, why = scan.follow(model, map_size, seed, multi[f"g_{map_size}_{seed}"], max_rows=n_rows)
+    assert rows >= n_rows and worst < 1e-5, (rows, worst, why)
+
+
+def test_reference_scan_order_is_the_old_libstdcxx_hashtable_order():
+    """The order in which Simulator2D::measure visits the landmarks (= iteration order of the reference's unordered_map)
+    decides which landmark gets which noise draw.  The oracle restates the GCC 5-7 hashtable; the host's GCC 13
+    std::unordered_map gives 7,6,..,0 for 8 keys, which contradicts the golden files (oracle_golden_scan.json: with the
+    restated order 5377 rows of the 200 episodes are followed, with the host's order 4007)."""
+    e = OracleEnv(EnvConfig(map_size=40), 3)
+    assert e.landmarks()["scan_id"].tolist() == [7, 6, 5, 4, 0, 1, 2, 3]
+    e = OracleEnv(EnvConfig(map_size=60), 3)
+    assert e.landmarks()["scan_id"].tolist() == [17, 16, 15, 14, 13, 12, 11, 10, 3, 2, 1, 0, 4, 5, 6, 7, 8, 9]
+    scan = json.load(open(os.path.join(GOLD, "oracle_golden_scan.json")))
+    assert sum(v["rows"] for v in scan["summary"].values()) >= 5300
+    assert sum(v["episodes_ge_18_rows"] for v in scan["summary"].values()) >= 120
