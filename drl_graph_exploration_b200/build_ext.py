@@ -25,7 +25,7 @@ def needs_build() -> bool:
         return True
     t = os.path.getmtime(LIB)
     deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(HERE, "..", "include", "dge.h"))
+    deps += [os.path.join(HERE, "..", "include", h) for h in ("dge.h", "dge_gnn.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
