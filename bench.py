@@ -453,6 +453,15 @@ def main():
         envs_per_launch = steps_rank / max(args.steps, 1)
         bytes_vmap = 2 * (48 * T_mean + 20 * eng.V + 8 * eng.Lt) * envs_per_launch
         bytes_slam = 2 * (72 * T_mean + 16 * M_mean + 32 * eng.Lt) * envs_per_launch
+        # the honest bound of these two kernels is the fp64 pipe, not HBM: algorithmic fp64 flops of the SLAM
+        # solve per env-step = Schur complement 3 T n^2 + marginals 3 T n^2 + inverse n^3 FMAs (n = 2 x observed landmarks; the
+        # O(T n) chain phases are left out), against the DFMA rate measured on this GPU (profiles/r01_fp64_latency_b200.txt)
+        n2 = 2.0 * float(loop.env.eng.state["observed"].sum(dim=1).float().mean().item())
+        flops_slam = 2.0 * (6.0 * T_mean * n2 * n2 + n2 ** 3) * envs_per_launch
+        fp64_peak = 35.2e12
+        fp64 = {"kernel": "k_slam", "achieved_tflops": flops_slam / (ms_slam * 1e-3) / 1e12, "peak_tflops": fp64_peak / 1e12,
+                "frac": flops_slam / (ms_slam * 1e-3) / fp64_peak, "peak_source": "profiles/r01_fp64_latency_b200.txt (17.6 T DFMA/s measured)",
+                "mean_border_columns": n2}
         dom = "slam" if ms_slam >= ms_vmap else "vmap"
         ach = (bytes_slam / (ms_slam * 1e-3) if dom == "slam" else bytes_vmap / (ms_vmap * 1e-3)) / 1e9
         roof = {"bound": "hbm", "kernel": "k_slam" if dom == "slam" else "k_vmap_env", "achieved": ach,
@@ -460,7 +469,8 @@ def main():
                 "traffic_source": NCU_TRAFFIC[dom]["source"],
                 "ms_per_launch": {"slam": ms_slam, "vmap": ms_vmap}, "mean_poses": T_mean, "mean_measurements": M_mean,
                 "vmap": {"achieved": bytes_vmap / (ms_vmap * 1e-3) / 1e9, "frac": bytes_vmap / (ms_vmap * 1e-3) / 1e9 / pk["hbm_gbs"]},
-                "slam": {"achieved": bytes_slam / (ms_slam * 1e-3) / 1e9, "frac": bytes_slam / (ms_slam * 1e-3) / 1e9 / pk["hbm_gbs"]}}
+                "slam": {"achieved": bytes_slam / (ms_slam * 1e-3) / 1e9, "frac": bytes_slam / (ms_slam * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                "fp64": fp64}
         out = {"metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": {"workload": WORKLOAD, "envs_per_gpu": ENVS_PER_GPU, "map_size": MAP_SIZE, "landmarks": N_LANDMARKS,
