@@ -146,6 +146,22 @@ def run_reference(args):
 
 
 
+def finish(world, dist):
+    """End of a run.  One rank: normal interpreter exit.  Several ranks: everything is flushed, the ranks meet at a last barrier
+    and leave with os._exit(0) -- the NCCL / CUDA teardown (destroy_process_group + context destruction at interpreter
+    shutdown) is skipped on purpose: at N = 4 it did not return within 6 minutes AFTER the complete JSON line had been
+    written (r01), and nothing is left to release that the process exit does not release."""
+    sys.stdout.flush(); sys.stderr.flush()
+    if world > 1:
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
+
+
 # ---------------------------------------------------------------- extra workloads ---
 def _dist_setup():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -216,8 +232,7 @@ def run_train(args):
                "gnn_samples_per_s": {"forward_acting": dec / sec, "forward_target": tsteps * bsz / sec, "forward_backward": tsteps * bsz / sec},
                "rollout": {"clones_per_s": clones / sec, "clone_engine_ticks_per_s": rsteps / sec}, "loss": tr.last_loss, "epsilon": tr.epsilon, "clocks": clocks}
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world, dist)
 
 
 def synth_graph_batch(n_graphs, sizes, rng, device, n_landmarks=8):
@@ -250,8 +265,7 @@ def run_gnn(args):
     out = measure_gnn(args, rank, world, local, dist)
     if rank == 0:
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world, dist)
 
 
 def measure_gnn(args, rank, world, local, dist, steps=None):
@@ -530,8 +544,7 @@ def main():
                              "tensor_roofline": g["roofline"]}
     if rank == 0:
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world, dist)
 
 
 if __name__ == "__main__":
