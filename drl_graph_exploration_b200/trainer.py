@@ -275,7 +275,10 @@ class VecA2CTrainer:
         self.a2c = a2c or A2C()
         self.dev = env.device
         B, eng, n = env.B, env.eng, int(self.a2c.nstep)
-        self.store = GraphReplay(B * (n + 2), eng.node_cap_env, eng.edge_cap_env, self.dev, slack=B * 4)   # graph store only
+        # graph store only.  Slots are handed out round-robin over ALL envs, and a graph must survive until its env's segment
+        # trains (<= n more decisions of that env): 3 n slots per env leave room for an env that decides at half the average
+        # rate; the allocation serials kept with every transition turn an overwritten graph into an error (see _train)
+        self.store = GraphReplay(B * 3 * n, eng.node_cap_env, eng.edge_cap_env, self.dev, slack=B * 8)
         self.params = [p for p in list(actor.parameters()) + list(critic.parameters()) if p.requires_grad]
         self.optimizer = torch.optim.Adam(self.params, lr=lr)
         self.bucket = FlatGradBucket(self.params)
@@ -284,6 +287,7 @@ class VecA2CTrainer:
         self.seg_slot, self.seg_a = z(torch.int64, B, n), z(torch.int64, B, n)
         self.seg_r, self.seg_val, self.seg_term = z(torch.float32, B, n), z(torch.float32, B, n), z(torch.bool, B, n)
         self.seg_len = z(torch.int64, B)
+        self.seg_serial, self.pend_serial = z(torch.int64, B, n), z(torch.int64, B)
         self.pend_slot, self.pend_a = torch.full((B,), -1, dtype=torch.int64, device=self.dev), z(torch.int64, B)
         self.pend_r, self.pend_val, self.pend_clo = z(torch.float32, B), z(torch.float32, B), z(torch.bool, B)
         self._ar = torch.arange(B, device=self.dev)
@@ -339,6 +343,7 @@ class VecA2CTrainer:
         pos = self.seg_len.clamp(max=n - 1)
         put = lambda buf, v: buf.__setitem__((self._ar, pos), torch.where(fin, v, buf[self._ar, pos]))
         put(self.seg_slot, self.pend_slot); put(self.seg_a, self.pend_a); put(self.seg_r, self.pend_r); put(self.seg_val, self.pend_val)
+        put(self.seg_serial, self.pend_serial)
         put(self.seg_term, ended | self.pend_clo | (closing & (fro <= 0)))
         self.seg_len = self.seg_len + fin.long()
         self.reward_sum += float(torch.where(fin, self.pend_r, torch.zeros_like(self.pend_r)).sum())
@@ -352,6 +357,7 @@ class VecA2CTrainer:
             start = need & (fro > 0)
             r = norm.gather(1, choice.clamp(0, norm.size(1) - 1).view(-1, 1)).view(-1).float()
             self.pend_slot = torch.where(start, slot_new, self.pend_slot)
+            self.pend_serial = torch.where(start, self.store.gserial[slot_new.clamp(min=0)], self.pend_serial)
             self.pend_a = torch.where(start, key + choice, self.pend_a)
             self.pend_r = torch.where(start, r, self.pend_r)
             self.pend_val = torch.where(start, v_now, self.pend_val)
@@ -379,6 +385,8 @@ class VecA2CTrainer:
             r, term, vals = self.seg_r[rows], self.seg_term[rows].float(), self.seg_val[rows]
             returns = nstep_returns(r, term, last_value[rows], a2c.GAMMA)
             slots = self.seg_slot[rows].view(-1)                              # segment-major, time order inside a segment
+            if not bool((self.store.gserial[slots] == self.seg_serial[rows].view(-1)).all()):
+                raise RuntimeError("VecA2CTrainer: a stored graph was overwritten before its segment trained -- enlarge the graph store")
             batch, n_nodes, off = self.store.gather(slots)
             N = batch.x.size(0)
             node = torch.arange(N, device=dev)
