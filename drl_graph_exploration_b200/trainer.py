@@ -55,7 +55,7 @@ class VecDQNTrainer:
         # on the replay as of the previous tick and finishes before this tick's Q forward reads the weights)
         self.overlap = bool(overlap)
         self.s_learn = torch.cuda.Stream(self.dev) if self.overlap else None
-        self.ev_tick, self.ev_learn = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_tick, self.ev_learn = (torch.cuda.Event(), torch.cuda.Event()) if self.overlap else (None, None)
         i64 = lambda v: torch.full((B,), v, dtype=torch.int64, device=self.dev)
         self.pend_slot, self.pend_a = i64(-1), i64(0)                  # in-flight transition of every env
         self.pend_r = torch.zeros(B, dtype=torch.float32, device=self.dev)
@@ -74,7 +74,7 @@ class VecDQNTrainer:
         (on its own stream) once the step and roll-out kernels of this tick are queued, before the Q forward."""
         env, eng, rp, dqn = self.env, self.env.eng, self.replay, self.dqn
         st, dev = eng.state, self.dev
-        main = torch.cuda.current_stream(dev)
+        main = torch.cuda.current_stream(dev) if side_work is not None else None
         if side_work is not None:
             self.ev_tick.record(main)                  # everything of the previous tick (replay writes, weight reads) is before this
         done_prev = st["done"].bool().clone()          # episodes that ended in the previous tick's step
