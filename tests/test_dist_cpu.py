@@ -21,7 +21,7 @@ def _worker(rank, world, port, q):
     local = bucket.flat.clone()
     bucket.all_reduce_mean()
     bucket.clamp_(0.5)
-    q.put((rank, lo, hi, local, bucket.flat.clone()))
+    q.put((rank, lo, hi, local.numpy().copy(), bucket.flat.numpy().copy()))   # by value: a tensor would travel as an fd the exiting worker may close first
     dist.destroy_process_group()
 
 
@@ -37,7 +37,7 @@ def test_shard_and_flat_allreduce():
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
-    (r0, lo0, hi0, l0, f0), (r1, lo1, hi1, l1, f1) = res
+    (r0, lo0, hi0, l0, f0), (r1, lo1, hi1, l1, f1) = [(r, lo, hi, torch.from_numpy(l), torch.from_numpy(f)) for r, lo, hi, l, f in res]
     assert (lo0, hi0, lo1, hi1) == (0, 5, 5, 10)
     assert torch.equal(f0, f1)                                     # replicas stay identical
     assert torch.allclose(f0, ((l0 + l1) / 2).clamp(-0.5, 0.5))   # mean, THEN clamp
@@ -75,7 +75,7 @@ def _train_worker(rank, world, port, q):
         a = torch.zeros(n); a[::3] = 1.0
         y = torch.linspace(-1, 1, n) * a
         dq.train(b, a, y, torch.device("cpu"), model, opt)
-    q.put((rank, torch.cat([p.detach().flatten() for p in model.parameters()])))
+    q.put((rank, torch.cat([p.detach().flatten() for p in model.parameters()]).numpy().copy()))
     dist.destroy_process_group()
 
 
@@ -90,6 +90,7 @@ def test_dqn_train_step_keeps_replicas_identical_and_equals_averaged_gradients()
     res = sorted([q.get(timeout=180) for _ in procs], key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
+    res = [(r, torch.from_numpy(w)) for r, w in res]
     assert torch.equal(res[0][1], res[1][1])                       # replicas identical after 3 steps
     # single-process restatement: average the two ranks' gradients, clamp, Adam
     torch.manual_seed(0)
