@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cassert>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <stdexcept>
@@ -471,7 +472,33 @@ void Env::slam_optimize() {
   int nl = 0;
   for (int j = 0; j < Lt; ++j) if (observed[j]) lidx[j] = nl++;
   pose_cov.resize(T); pose_info.resize(T);
+  // EXPERIMENT (off unless DGE_ORACLE_WILDFIRE is set; not part of the pinned oracle, never used by the tests): ISAM2 does not
+  // hand every variable its exact delta -- cliques that were not re-eliminated keep their OLD delta unless it moved by at least
+  // wildfireThreshold (gtsam ISAM2-impl optimizeWildfireNode).  Without the Bayes tree the re-eliminated set is approximated by:
+  // the landmarks observed at this step, and every pose from the earliest previous observation of one of them to the newest.
+  static const char *wf_env = std::getenv("DGE_ORACLE_WILDFIRE");
+  const double wf = wf_env ? std::atof(wf_env) : 0.0;
+  std::vector<double> old_dp, old_dl;
+  if (wf > 0) { old_dp = delta_pose; old_dl = delta_l; }
   if (use_dense_solver) solve_dense(lidx, nl); else solve_structured(lidx, nl);
+  if (wf > 0 && T >= 2) {
+    int first_replaced = T - 2;
+    std::vector<uint8_t> lm_now(Lt, 0);
+    for (int p = meas_ptr[T - 1]; p < meas_ptr[T]; ++p) lm_now[meas[p].id] = 1;
+    for (int k = 0; k < T - 1; ++k)
+      for (int p = meas_ptr[k]; p < meas_ptr[k + 1]; ++p)
+        if (lm_now[meas[p].id]) first_replaced = std::min(first_replaced, k);   // (a landmark's LAST earlier observation would be the tree-faithful choice)
+    for (int k = 0; k < first_replaced && 3 * k + 2 < (int)old_dp.size(); ++k) {
+      double ch = 0;
+      for (int i = 0; i < 3; ++i) ch = std::max(ch, std::fabs(delta_pose[3 * k + i] - old_dp[3 * k + i]));
+      if (ch < wf) for (int i = 0; i < 3; ++i) delta_pose[3 * k + i] = old_dp[3 * k + i];
+    }
+    for (int j = 0; j < Lt; ++j) {
+      if (!observed[j] || lm_now[j]) continue;
+      const double ch = std::max(std::fabs(delta_l[2 * j] - old_dl[2 * j]), std::fabs(delta_l[2 * j + 1] - old_dl[2 * j + 1]));
+      if (ch < wf) { delta_l[2 * j] = old_dl[2 * j]; delta_l[2 * j + 1] = old_dl[2 * j + 1]; }
+    }
+  }
   for (int k = 0; k < T; ++k) {
     est_pose[k] = retract(lin_pose[k], &delta_pose[3 * k]);
     pose_info[k] = inv3(pose_cov[k]);   // SLAM2D.cpp:400  inverse(covariance)
