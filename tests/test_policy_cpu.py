@@ -113,3 +113,55 @@ def test_state_dict_layouts_match_the_shipped_checkpoints():
         # and what torch.save(policy_net.state_dict(), ...) writes (policy.py:192,205) has the same layout
         sd = {k: torch.zeros(s) for k, s in lay[name].items()}
         model.load_state_dict(sd)
+
+
+def test_env_config_defaults_are_the_reference_ini_values(tmp_path):
+    """EnvConfig() carries the values of scripts/envs/exploration_env.ini; from_ini reads a file in that format
+    (utils.py:42-45 load_config) and gives the same configuration; ExplorationEnv.reset's overrides (exploration_env.py:399-407)
+    are the map-size dependent bounds and the landmark count int(map_size^2 * 0.005)."""
+    from drl_graph_exploration_b200.config import EnvConfig
+    ini = tmp_path / "exploration_env.ini"
+    ini.write_text("""
+[Sensor Model]
+bearing_noise = 0.5 ; (degree)
+range_noise   = 0.02
+min_bearing   = -179.9
+max_bearing   =  179.9
+min_range     = 0.1
+max_range     = 6.0
+[Control Model]
+translation_noise = 0.1
+rotation_noise    = 0.2
+[Environment]
+min_x = -20
+max_x =  20
+min_y = -20
+max_y =  20
+max_steps = 5000
+safe_distance = 0.0
+[Virtual Map]
+resolution  = 2.0
+sigma0      = 1.0
+num_samples = 1
+[Simulator]
+seed   = 5
+lo = 0
+num    = 8
+sigma_x0     = 0.05
+sigma_y0     = 0.05
+sigma_theta0 = 0.01
+[Planner]
+angle_weight = 0.4
+distance_weight0 = 5.0
+distance_weight1 = 2.0
+max_edge_length = 2.0
+occupancy_threshold = 0.4
+""")
+    for ms, n_lm, rows in ((40, 8, 40), (60, 18, 50), (80, 32, 60), (100, 50, 70), (20, 2, 30)):
+        a, b = EnvConfig(map_size=ms), EnvConfig.from_ini(str(ini), ms)
+        assert a == b
+        assert a.n_landmarks == n_lm and a.rows == rows == a.cols
+        c = a.to_struct()
+        assert (c.env_min_x, c.env_max_x, c.map_min_x, c.map_max_x) == (-ms / 2, ms / 2, -ms / 2 - 20.0, ms / 2 + 20.0)
+        assert abs(c.max_bearing - np.radians(179.9)) < 1e-15 and abs(c.bearing_noise - np.radians(0.5)) < 1e-15
+        assert (c.relin_thresh, c.relin_skip) == (0.1, 10)                       # gtsam::ISAM2Params defaults (SLAM2D.cpp:10-12)
