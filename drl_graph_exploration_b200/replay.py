@@ -110,5 +110,22 @@ class GraphReplay:
             assert bool(ok.all()), "graph ring wrapped over a live transition: increase `slack`"
         return s, self.t_a[idx], self.t_r[idx], s1, self.t_term[idx]
 
+    _TENSORS = ("x", "ei", "ea", "gn", "ge", "gk", "gf", "gserial", "t_s", "t_s1", "t_a", "t_r", "t_term", "t_serial")
+
+    def state_dict(self) -> dict:
+        """Everything needed to resume: the two rings and their cursors (the reference pickles its deque of Data objects,
+        train.py:33-35 / run_training.py:63-64)."""
+        d = {k: getattr(self, k).detach().cpu() for k in self._TENSORS}
+        d.update(size=self.size, head=self.head, allocated=self.allocated, capacity=self.capacity, G=self.G,
+                 node_cap=self.node_cap, edge_cap=self.edge_cap)
+        return d
+
+    def load_state_dict(self, d: dict):
+        if (d["capacity"], d["G"], d["node_cap"], d["edge_cap"]) != (self.capacity, self.G, self.node_cap, self.edge_cap):
+            raise ValueError("replay checkpoint was written with other capacities")
+        for k in self._TENSORS:
+            getattr(self, k).copy_(d[k])
+        self.size, self.head, self.allocated = int(d["size"]), int(d["head"]), int(d["allocated"])
+
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.x, self.ei, self.ea))

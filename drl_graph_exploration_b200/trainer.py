@@ -231,6 +231,29 @@ class VecDQNTrainer:
             torch.save({k: v.detach().cpu() for k, v in self.target_net.state_dict().items()}, os.path.join(out_dir, "Model_Target.pt"))
         return rewards, losses
 
+    def checkpoint(self, path: str, include_replay: bool = True):
+        """The reference pickles the whole ``DeepQ`` object between its 10 000-step subprocess chunks (hyper-parameters, step_t,
+        epsilon, the replay deque: train.py:33-35, run_training.py:13-16,63-64) next to the two state dicts.  Same content
+        here, as one torch file: nets, optimizer, counters, epsilon, sampling generator and (optionally) the device replay.
+        Like in the reference the environments are NOT part of it: a resumed run starts fresh episodes."""
+        ck = {"policy": self.policy_net.state_dict(), "target": self.target_net.state_dict(), "optimizer": self.optimizer.state_dict(),
+              "dqn": {"step_t": self.dqn.step_t, "epsilon": self.dqn.epsilon},
+              "counters": {k: getattr(self, k) for k in ("decisions", "train_steps", "ticks", "transitions", "rollout_steps", "rollout_clones", "reward_sum")},
+              "gen": self.gen.get_state(), "replay": self.replay.state_dict() if include_replay else None}
+        torch.save(ck, path)
+
+    def restore(self, path: str):
+        ck = torch.load(path, map_location=self.dev, weights_only=False)
+        self.policy_net.load_state_dict(ck["policy"]); self.target_net.load_state_dict(ck["target"])
+        self.optimizer.load_state_dict(ck["optimizer"])
+        self.dqn.step_t, self.dqn.epsilon = ck["dqn"]["step_t"], ck["dqn"]["epsilon"]
+        for k, v in ck["counters"].items():
+            setattr(self, k, v)
+        self.gen.set_state(ck["gen"].cpu())
+        if ck["replay"] is not None:
+            self.replay.load_state_dict(ck["replay"])
+        self.pend_slot.fill_(-1)              # in-flight transitions belonged to the episodes of the old process
+
     def load(self, path: str):
         """Resume from a ``MyModel.pt`` / ``Model_Policy.pt`` state dict (the reference's or ours)."""
         sd = torch.load(path, map_location=self.dev)

@@ -191,3 +191,41 @@ def test_dqn_bookkeeping_transitions_targets_and_learning(monkeypatch):
     assert all(torch.equal(b, p.detach()) for b, p in zip(before, tgt.parameters()))      # target = the policy as of its last sync (step 0)
     # the pending table only holds envs that are between two decisions
     assert bool(((tr.pend_slot >= 0) | (tr.pend_slot == -1)).all())
+
+
+def test_dqn_checkpoint_and_resume(monkeypatch, tmp_path):
+    """checkpoint() / restore(): nets, optimizer, epsilon / step counters, sampling generator and the device replay survive a
+    process boundary (the reference pickles its DeepQ object between subprocess chunks); environments start fresh episodes."""
+    monkeypatch.setattr(trainer_mod, "_stream_ptr", lambda dev: None)
+
+    def make(seed):
+        torch.manual_seed(seed)
+        env = _Env(16, seed=seed)
+        tr = trainer_mod.VecDQNTrainer(env, _QNet(), _QNet(), replay_capacity=48, observe=0, lr=1e-2, seed=0)
+        tr.dqn.BATCH = 8
+        return env, tr
+    _, a = make(5)
+    for _ in range(60):
+        a.tick()
+    a.checkpoint(str(tmp_path / "ck.pt"))
+    _, b = make(99)                                   # different weights, empty replay, different env
+    b.restore(str(tmp_path / "ck.pt"))
+    for (k, v), (_, w) in zip(a.policy_net.state_dict().items(), b.policy_net.state_dict().items()):
+        assert torch.equal(v, w), k
+    for k in ("decisions", "train_steps", "transitions"):
+        assert getattr(a, k) == getattr(b, k)
+    assert (a.dqn.step_t, a.dqn.epsilon) == (b.dqn.step_t, b.dqn.epsilon)
+    ra, rb = a.replay, b.replay
+    assert (ra.size, ra.head, ra.allocated) == (rb.size, rb.head, rb.allocated)
+    for name in ra._TENSORS:
+        assert torch.equal(getattr(ra, name), getattr(rb, name)), name
+    assert bool((b.pend_slot == -1).all())
+    # the same minibatch is drawn and the same gradient step is taken after the restore (generator and Adam moments restored)
+    torch.manual_seed(123); la = a.learn()
+    torch.manual_seed(123); lb = b.learn()
+    assert la == lb
+    for v, w in zip(a.policy_net.parameters(), b.policy_net.parameters()):
+        assert torch.equal(v, w)
+    for _ in range(10):
+        b.tick()                                      # and it keeps running on its own envs
+    assert b.train_steps > a.train_steps - 1
