@@ -138,6 +138,63 @@ class DeepQ(object):
         if len(self.buffer) > self.REPLAY_MEMORY:
             self.buffer.popleft()
 
+    def running(self, model, modelTarget, test=False, env=None, epochs=None, device=None, method="bayesian", log=None):
+        """policy.py:60-209 on ``ExplorationEnv`` (the B = 1 view of the CUDA engine; ``trainer.VecDQNTrainer`` is the B-env form):
+        per decision the exploration graph, the look-ahead reward of every frontier, a frontier chosen from the dropout-perturbed
+        Q-values ("bayesian", dropout p = epsilon) or epsilon-greedily, the line plan executed step by step, the transition
+        ``(s_t, a_t, r_t, s_t1, done or loop_clo, fro_size1)`` stored, and -- after OBSERVE decisions -- one gradient step on BATCH
+        sampled transitions with the target network refreshed every TARGET_UPDATE decisions.  File outputs (reward CSVs,
+        ``MyModel.pt``) are the caller's business here: ``log(step_t, state, epsilon, q_max, explored, reward, terminal)`` is called
+        once per decision and the per-decision rewards are kept in ``self.total_reward``."""
+        from .envs.exploration_env import ExplorationEnv
+        env = env or ExplorationEnv(self.map_size, 0, test)
+        device = device or env._vec.device
+        policy_net, target_net = model, modelTarget
+        target_net.eval()
+        optimizer = torch.optim.Adam(policy_net.parameters(), lr=1e-5)
+        losses = []
+        for _ in range(int(self.epoch if epochs is None else epochs)):
+            self.step_t += 1
+            if self.epsilon > self.FINAL_EPSILON and self.step_t > self.OBSERVE:
+                self.epsilon -= (self.INITIAL_EPSILON - self.FINAL_EPSILON) / self.EXPLORE
+            adjacency, features, _, fro_size = env.graph_matrix()
+            node_size = adjacency.shape[0]
+            key_size = node_size - fro_size
+            s_t = self.data_process([adjacency, features])
+            all_actions = env.actions_all_goals()
+            rewards = env.rewards_all_goals(all_actions)
+            if method == "e-greedy":
+                q = self.test(s_t, 0.0, device, policy_net).view(-1).cpu().numpy()
+                explore = random.random() <= self.epsilon
+                action_index = random.randrange(fro_size) if explore else int(np.argmax(q[node_size - fro_size:]))
+                state = "explore" if explore else "exploit"
+            else:
+                q = self.test(s_t, self.epsilon, device, policy_net).view(-1).cpu().numpy()
+                action_index = int(np.argmax(q[node_size - fro_size:]))
+                state = "bayesian"
+            a_t = np.zeros(node_size)
+            a_t[key_size + action_index] = 1
+            r_t = float(rewards[key_size + action_index])
+            done = False
+            for act in all_actions[key_size + action_index]:
+                _, done, _ = env.step(act)
+            current_done = done or env.loop_clo
+            adjacency, features, _, fro_size1 = env.graph_matrix()
+            s_t1 = self.data_process([adjacency, features])
+            self.remember((s_t, a_t, r_t, s_t1, current_done, fro_size1))
+            if self.step_t > self.OBSERVE and len(self.buffer) >= self.BATCH:
+                if self.step_t % self.TARGET_UPDATE == 0:
+                    target_net.load_state_dict(policy_net.state_dict())
+                minibatch = random.sample(self.buffer, self.BATCH)
+                s_j, a, y = self.build_targets(minibatch, device, target_net)
+                losses.append([self.step_t, self.train(s_j, a, y, device, policy_net, optimizer)])
+            if log is not None:
+                log(self.step_t, state, self.epsilon, float(np.max(q)), env.status(), r_t, current_done)
+            if done:
+                env.reset()
+            self.total_reward = np.append(self.total_reward, r_t)
+        return env, losses
+
 
 class A2C(object):
     """policy.py:262-497: n-step advantage actor-critic.  Same hyper-parameters, ``data_process / policy_cost / value_cost /

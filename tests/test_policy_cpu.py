@@ -165,3 +165,73 @@ occupancy_threshold = 0.4
         assert (c.env_min_x, c.env_max_x, c.map_min_x, c.map_max_x) == (-ms / 2, ms / 2, -ms / 2 - 20.0, ms / 2 + 20.0)
         assert abs(c.max_bearing - np.radians(179.9)) < 1e-15 and abs(c.bearing_noise - np.radians(0.5)) < 1e-15
         assert (c.relin_thresh, c.relin_skip) == (0.1, 10)                       # gtsam::ISAM2Params defaults (SLAM2D.cpp:10-12)
+
+
+class _OneEnv:
+    """Duck-typed stand-in for ExplorationEnv (graph_matrix / actions_all_goals / rewards_all_goals / step / status / reset)."""
+
+    def __init__(self, seed=0):
+        self.rng = np.random.default_rng(seed)
+        self.loop_clo, self.steps, self.resets = False, 0, 0
+
+    def graph_matrix(self):
+        k, f = int(self.rng.integers(3, 6)), int(self.rng.integers(1, 4))
+        n = k + f
+        adj = np.zeros((n, n))
+        for i in range(n - 1):
+            adj[i, i + 1] = adj[i + 1, i] = self.rng.uniform(0.5, 2.0)
+        self._n, self._k, self._f = n, k, f
+        return adj, self.rng.normal(size=(n, 5)), np.array([0.0]), f
+
+    def actions_all_goals(self):
+        return [[]] * self._k + [["rot", "fwd", "fwd"][: int(self.rng.integers(2, 4))] for _ in range(self._f)]
+
+    def rewards_all_goals(self, all_actions):
+        r = np.zeros(self._n)
+        r[self._k:] = self.rng.uniform(-1, 1, self._f)
+        self.loop_clo = bool(self.rng.integers(0, 2))
+        return r
+
+    def step(self, act):
+        self.steps += 1
+        return None, self.steps % 17 == 0, {}
+
+    def status(self):
+        return 0.1
+
+    def reset(self):
+        self.resets += 1
+
+
+class _NodeQ(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.l = torch.nn.Linear(5, 1)
+
+    def forward(self, data, prob, batch=None):
+        return self.l(data.x)
+
+
+def test_deepq_running_follows_the_reference_loop():
+    """DeepQ.running on a stand-in env: one transition per decision with a one-hot action on a frontier node, learning starts
+    after OBSERVE decisions, epsilon decays per decision, the target net is refreshed every TARGET_UPDATE decisions, the env
+    is reset when an episode ends."""
+    import random
+    random.seed(0); torch.manual_seed(0)
+    dq = DeepQ()
+    dq.OBSERVE, dq.BATCH, dq.TARGET_UPDATE, dq.EXPLORE, dq.REPLAY_MEMORY = 10, 4, 7, 100, 25
+    pol, tgt = _NodeQ(), _NodeQ()
+    rows = []
+    env, losses = dq.running(pol, tgt, env=_OneEnv(), epochs=40, device=torch.device("cpu"), log=lambda *r: rows.append(r))
+    assert dq.step_t == 40 and len(rows) == 40 and dq.total_reward.shape == (40,)
+    assert len(dq.buffer) == 25                                        # popleft beyond REPLAY_MEMORY (policy.py:132-133)
+    assert len(losses) == 30 and losses[0][0] == 11 and all(np.isfinite(l) for _, l in losses)     # learning from decision OBSERVE + 1 on
+    assert abs(dq.epsilon - (0.9 - 30 * 0.9 / 100)) < 1e-12            # one decrement per decision after OBSERVE
+    for s_t, a_t, r_t, s_t1, term, fro1 in dq.buffer:
+        assert a_t.sum() == 1 and a_t.shape[0] == s_t.x.shape[0] and -1 <= r_t <= 1 and 1 <= fro1 <= 3
+        assert s_t.edge_index.shape[1] == 2 * (s_t.x.shape[0] - 1)
+    assert env.resets >= 1 and all(r[1] == "bayesian" for r in rows)
+    # e-greedy branch
+    dq2 = DeepQ(); dq2.OBSERVE, dq2.BATCH = 5, 4
+    _, l2 = dq2.running(_NodeQ(), _NodeQ(), env=_OneEnv(1), epochs=12, device=torch.device("cpu"), method="e-greedy")
+    assert len(l2) == 7
