@@ -235,3 +235,22 @@ def test_deepq_running_follows_the_reference_loop():
     dq2 = DeepQ(); dq2.OBSERVE, dq2.BATCH = 5, 4
     _, l2 = dq2.running(_NodeQ(), _NodeQ(), env=_OneEnv(1), epochs=12, device=torch.device("cpu"), method="e-greedy")
     assert len(l2) == 7
+
+
+def test_a2c_running_follows_the_reference_loop():
+    """A2C.running on the stand-in env: the actor's masked softmax is sampled, one gradient step every nstep decisions, the
+    buffer is cleared after it (policy.py:358-395)."""
+    from drl_graph_exploration_b200.policy import A2C
+    from test_trainer_logic_cpu import _Actor, _Critic
+    torch.manual_seed(0)
+    ac = A2C(); ac.nstep = 4
+    actor, critic = _Actor(), _Critic()
+    before = torch.cat([p.detach().flatten().clone() for p in list(actor.parameters()) + list(critic.parameters())])
+    rows = []
+    env = ac.running(actor, critic, env=_OneEnv(2), epochs=14, device=torch.device("cpu"), log=lambda *r: rows.append(r))
+    assert ac.step_t == 14 and len(rows) == 14 and len(ac.buffer) == 2            # three gradient steps, two transitions waiting
+    assert np.isfinite(ac.temp_loss) and ac.entro > 0 and ac.total_reward.shape == (14,)
+    after = torch.cat([p.detach().flatten() for p in list(actor.parameters()) + list(critic.parameters())])
+    assert not torch.equal(before, after)
+    for s_t, a_t, r_t, s_t1, term, fro, val in ac.buffer:
+        assert a_t.sum() == 1 and int(np.argmax(a_t)) >= a_t.shape[0] - fro and np.isfinite(val)
