@@ -529,7 +529,7 @@ def main():
             run_tick(); nt += 1
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": (count() - c0) / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                               "sample": f"{n_envs} of {ENVS_PER_GPU} envs x {nt} ticks ({dt:.1f} s): CPU CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN"}
+                               "sample": f"{n_envs} of {ENVS_PER_GPU} envs x {nt} ticks ({dt:.1f} s): CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN"}
     elif rank == 0:
         out["cpu_baseline"] = None
     if not args.no_gnn:

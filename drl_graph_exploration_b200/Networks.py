@@ -125,36 +125,45 @@ class TopKPooling(torch.nn.Module):
         torch.nn.init.uniform_(self.weight, -bound, bound)
 
     def forward(self, x, edge_index, edge_attr, batch):
+        gnn.require_cuda(x, "TopKPooling")
         score = torch.tanh((x * self.weight).sum(dim=-1) / self.weight.norm(p=2, dim=-1))
         n_graphs = int(batch.max()) + 1 if batch.numel() else 0
         counts = torch.bincount(batch, minlength=n_graphs)
         k = torch.ceil(self.ratio * counts.to(score.dtype)).long()
-        if x.is_cuda and n_graphs > 0 and not edge_attr.requires_grad:
+        if n_graphs > 0 and not edge_attr.requires_grad:
             max_n, n_kept = (int(v) for v in torch.stack([counts.max(), k.sum()]).tolist())
             if max_n <= 1024:   # native: one CTA per graph sorts its scores; edges filtered + relabelled by a flag / scan / fill pass
                 zero = counts.new_zeros(1)
                 perm, newid = gnn.topk_pool(score.detach(), torch.cat([zero, torch.cumsum(counts, 0)]), torch.cat([zero, torch.cumsum(k, 0)]), max_n, n_kept)
                 ei2, ew2 = gnn.filter_adj(edge_index, edge_attr, newid)
                 return x[perm] * score[perm].view(-1, 1), ei2, ew2, batch[perm], perm, score[perm]
-        # per-graph descending order: sort by (graph, -score) with a stable two-key sort
-        order = torch.sort(score, descending=True, stable=True)[1]
-        order = order[torch.sort(batch[order], stable=True)[1]]
-        start = torch.cumsum(counts, 0) - counts
-        rank = torch.arange(order.numel(), device=x.device) - start[batch[order]]
-        perm = order[rank < k[batch[order]]]
-        x = x[perm] * score[perm].view(-1, 1)
-        mask = perm.new_full((score.size(0),), -1)
-        mask[perm] = torch.arange(perm.numel(), device=perm.device)
-        row, col = mask[edge_index[0]], mask[edge_index[1]]
-        keep = (row >= 0) & (col >= 0)
-        return x, torch.stack([row[keep], col[keep]]), edge_attr[keep], batch[perm], perm, score[perm]
+        perm, ei2, ew2 = _topk_select_sorted(score, counts, k, edge_index, edge_attr, batch)
+        return x[perm] * score[perm].view(-1, 1), ei2, ew2, batch[perm], perm, score[perm]
+
+
+def _topk_select_sorted(score, counts, k, edge_index, edge_attr, batch):
+    """Device-side torch formulation of the selection for the two shapes the sort kernel does not take (a graph above 1024
+    nodes -- the reference's graphs stay below ~250 -- or edge weights that carry a gradient): per-graph descending order by a
+    stable two-key sort, ties to the lower index, then ``filter_adj``.  ``TopKPooling.forward`` only reaches it with CUDA
+    tensors; ``tests/test_networks_glue_cpu.py`` holds it against the restated PyG semantics."""
+    order = torch.sort(score, descending=True, stable=True)[1]
+    order = order[torch.sort(batch[order], stable=True)[1]]
+    start = torch.cumsum(counts, 0) - counts
+    rank = torch.arange(order.numel(), device=score.device) - start[batch[order]]
+    perm = order[rank < k[batch[order]]]
+    mask = perm.new_full((score.size(0),), -1)
+    mask[perm] = torch.arange(perm.numel(), device=perm.device)
+    row, col = mask[edge_index[0]], mask[edge_index[1]]
+    keep = (row >= 0) & (col >= 0)
+    return perm, torch.stack([row[keep], col[keep]]), edge_attr[keep]
 
 
 def _augment_adj(edge_index, edge_weight, num_nodes, batch=None, n_graphs=None):
-    """Networks.py:216-225: add_self_loops -> sort -> spspmm(A, A) (coalesced) -> remove_self_loops.  On the GPU (inference and
-    training alike -- the edge weights carry no gradient) the block-diagonal batch goes through the native row-accumulator
-    kernels (gnn.augment_adj); the torch.sparse path below is the generic one (CPU tensors, graphs above 1024 nodes)."""
-    if edge_index.is_cuda and not edge_weight.requires_grad:
+    """Networks.py:216-225: add_self_loops -> sort -> spspmm(A, A) (coalesced) -> remove_self_loops.  Inference and training
+    alike (the edge weights carry no gradient) the block-diagonal batch goes through the native row-accumulator kernels
+    (gnn.augment_adj).  CPU tensors raise; ``_augment_adj_sparse`` takes the shapes the kernel does not (see there)."""
+    gnn.require_cuda(edge_index, "augment_adj")
+    if not edge_weight.requires_grad:
         if batch is None:
             gptr, mx, bt = torch.tensor([0, num_nodes], device=edge_index.device), num_nodes, None
         else:
@@ -165,6 +174,13 @@ def _augment_adj(edge_index, edge_weight, num_nodes, batch=None, n_graphs=None):
         out = gnn.augment_adj(edge_index, edge_weight.float(), num_nodes, bt, gptr, mx) if num_nodes > 0 else None
         if out is not None:
             return out
+    return _augment_adj_sparse(edge_index, edge_weight, num_nodes)
+
+
+def _augment_adj_sparse(edge_index, edge_weight, num_nodes):
+    """(A + I)^2 without its diagonal through torch.sparse on the device, for a graph above 1024 nodes (the shared-memory row
+    accumulator of ``k_augment_adj`` is sized for that) or edge weights that carry a gradient.  Same structure and order as the
+    kernel's output; ``tests/test_networks_glue_cpu.py`` holds it against the restated PyG semantics."""
     loop = torch.arange(num_nodes, dtype=edge_index.dtype, device=edge_index.device)
     ei = torch.cat([edge_index, torch.stack([loop, loop])], dim=1)
     ew = torch.cat([edge_weight, edge_weight.new_ones(num_nodes)])

@@ -45,6 +45,9 @@ def _need_cuda(t: torch.Tensor, what: str):
         raise DgeError(f"{what}: the GNN kernels run on CUDA tensors only (no CPU fallback in the product path)")
 
 
+require_cuda = _need_cuda   # for the glue in Networks.py
+
+
 launch_count = 0   # kernels launched through this module (bench.py reports it as gpu_launches)
 
 

@@ -1,10 +1,12 @@
-"""The PyTorch glue of Networks.py that needs no kernel (generic paths of top-k pooling / augment_adj, segment softmax, mean
-pool) against the oracle's restatement of the PyG-1.x functions, on CPU tensors.  (The CUDA paths of the same functions are
-compared with these in the -m gpu tests.)"""
+"""The PyTorch glue of Networks.py that needs no kernel (the torch formulations of top-k selection / augment_adj for shapes
+the kernels do not take, segment softmax, mean pool) against the oracle's restatement of the PyG-1.x functions, on CPU tensors.
+(The CUDA paths of the same functions are compared with these in the -m gpu tests; the layer entry points refuse CPU tensors.)"""
 import numpy as np
+import pytest
 import torch
 
 from drl_graph_exploration_b200 import Networks
+from drl_graph_exploration_b200.engine import DgeError
 from oracle import gnn_ref
 
 
@@ -36,16 +38,27 @@ def test_segment_softmax_and_mean_pool():
 
 
 def test_topk_pooling_and_augment_adj_generic_paths():
+    """The torch formulations TopKPooling / _augment_adj use on the device for the shapes the kernels do not take (graphs above
+    1024 nodes, edge weights with a gradient), against the oracle's PyG restatement; the entry points themselves refuse CPU
+    tensors (no CPU fallback in the product path)."""
     rng = np.random.default_rng(1)
     x, ei, w, bt = _batch(rng, [9, 4, 16, 1, 7])
     pool = Networks.TopKPooling(6, ratio=0.5)
-    xo, eio, wo, bo, perm, score = pool(x, ei, w, bt)
+    with pytest.raises(DgeError):
+        pool(x, ei, w, bt)
+    with pytest.raises(DgeError):
+        Networks._augment_adj(ei, w, x.size(0))
+    with torch.no_grad():
+        score = torch.tanh((x * pool.weight).sum(dim=-1) / pool.weight.norm(p=2, dim=-1))
+    counts = torch.bincount(bt)
+    k = torch.ceil(0.5 * counts.float()).long()
+    perm, eio, wo = Networks._topk_select_sorted(score, counts, k, ei, w, bt)
+    xo, bo = x[perm] * score[perm].view(-1, 1), bt[perm]
     xr, eir, wr, br, permr = gnn_ref.topk_pool(x, ei, w, bt, pool.weight.detach(), 0.5)
     assert torch.equal(perm, permr) and torch.equal(bo, br)
     assert torch.allclose(xo, xr, rtol=1e-6, atol=1e-7) and torch.equal(eio, eir) and torch.equal(wo, wr)
-    counts = torch.bincount(bt)
-    assert torch.equal(torch.bincount(bo, minlength=5), torch.ceil(0.5 * counts.float()).long())         # k = ceil(ratio n) per graph
-    a_i, a_w = Networks._augment_adj(ei, w, x.size(0))
+    assert torch.equal(torch.bincount(bo, minlength=5), k)                                               # k = ceil(ratio n) per graph
+    a_i, a_w = Networks._augment_adj_sparse(ei, w, x.size(0))
     r_i, r_w = gnn_ref.augment_adj(ei, w, x.size(0))
     assert torch.equal(a_i, r_i) and torch.allclose(a_w, r_w, rtol=1e-6, atol=1e-7)
     assert bool((a_i[0] != a_i[1]).all()) and bool((bt[a_i[0]] == bt[a_i[1]]).all())
