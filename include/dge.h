@@ -15,7 +15,10 @@
  * is a `cudaStream_t` passed as void*.  Every call returns 0 on success or a
  * negative DGE_E* code -- it never aborts (the reference `assert`s / throws).
  * All launches are asynchronous on `stream`; host-buffer variants synchronise the
- * stream before returning.  One handle = one device, one stream at a time.
+ * stream before returning.  One handle = one device, one stream at a time; one
+ * device per PROCESS (the deployment model is one process per GPU: the opt-in
+ * shared-memory sizes of the kernels are set once per process, and the caller
+ * keeps the handle's device current around every call).
  * ==========================================================================*/
 #ifndef DGE_H_
 #define DGE_H_
