@@ -112,3 +112,54 @@ def test_dqn_train_step_keeps_replicas_identical_and_equals_averaged_gradients()
         opt.step()
     ref = torch.cat([p.detach().flatten() for p in model.parameters()])
     assert torch.allclose(res[0][1], ref, rtol=1e-5, atol=1e-7)
+
+
+def _a2c_run(seed_env, seed_sampling, ticks):
+    """VecA2CTrainer on the CPU stand-in engine of test_trainer_logic_cpu (same initial weights everywhere)."""
+    import test_trainer_logic_cpu as tl
+    from drl_graph_exploration_b200 import trainer as trainer_mod
+    from drl_graph_exploration_b200.policy import A2C
+    saved, trainer_mod._stream_ptr = trainer_mod._stream_ptr, lambda dev: None
+    try:
+        torch.manual_seed(0)
+        actor, critic = tl._Actor(), tl._Critic()
+        a2c = A2C(); a2c.nstep = 3
+        tr = trainer_mod.VecA2CTrainer(tl._Env(8, seed_env), actor, critic, a2c=a2c, lr=1e-2, seed=seed_sampling)
+        for _ in range(ticks):
+            tr.tick()
+    finally:
+        trainer_mod._stream_ptr = saved
+    return tr, torch.cat([p.detach().flatten() for p in tr.params]).numpy().copy()
+
+
+def _a2c_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tr, w_diff = _a2c_run(seed_env=10 + rank, seed_sampling=rank, ticks=60)     # every rank its own envs: segments close in different ticks
+    diff = (tr.train_steps, tr.segments, w_diff)
+    tr, w_same = _a2c_run(seed_env=5, seed_sampling=5, ticks=40)               # both ranks the same envs
+    q.put((rank, diff, (tr.train_steps, tr.segments, w_same)))
+    dist.destroy_process_group()
+
+
+def test_a2c_trainer_segment_weighted_allreduce_keeps_replicas_identical():
+    """trainer.VecA2CTrainer at world size 2: a rank joins the collective of every tick in which ANY rank closed a segment (so
+    the gradient-step counts agree although the segment counts do not), replicas stay bit-identical, and two ranks that hold
+    the same envs reproduce the single-process run (each contributes its loss weighted by its share of the segments)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_a2c_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, (steps0, seg0, w0), (ssteps0, sseg0, sw0)), (_, (steps1, seg1, w1), (ssteps1, sseg1, sw1)) = res
+    assert steps0 == steps1 and steps0 >= 5
+    assert seg0 != seg1                                                        # the shards really differed
+    assert torch.equal(torch.from_numpy(w0), torch.from_numpy(w1))
+    tr, w_single = _a2c_run(seed_env=5, seed_sampling=5, ticks=40)              # no process group in this process: world = 1
+    assert (ssteps0, sseg0) == (ssteps1, sseg1) == (tr.train_steps, tr.segments)
+    assert torch.equal(torch.from_numpy(sw0), torch.from_numpy(sw1))
+    assert torch.allclose(torch.from_numpy(sw0), torch.from_numpy(w_single), rtol=1e-5, atol=1e-7)
