@@ -66,6 +66,7 @@ class VecDQNTrainer:
         self.rollout_steps = self.rollout_clones = 0    # clone-engine ticks launched / clones evaluated
         self.last_loss = float("nan")
         self.reward_sum = 0.0
+        self._learning = False                          # see _learning_started
 
     # ---------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -180,7 +181,7 @@ class VecDQNTrainer:
         beside this tick's roll-outs on the replay as of the previous tick -- the same sequence of operations as the
         sequential mode shifted by one tick (a sequential run of k learning ticks == one acting tick + k overlapped ticks)."""
         if learn is None:
-            learn = self.dqn.step_t > self.observe and self.replay.size >= self.dqn.BATCH
+            learn = self._learning_started()
         if self.overlap:
             ng = self._act(self._learn_beside if learn else None)
             self.ticks += 1
@@ -191,6 +192,22 @@ class VecDQNTrainer:
             for _ in range(self.train_steps_per_tick):
                 self.learn()
         return ng
+
+    def _learning_started(self) -> bool:
+        """policy.py:136: learning starts once OBSERVE decisions have passed (and, here, one minibatch of transitions exists).
+        Both counts are rank-local, and a rank that started alone would sit in the gradient all-reduce of ``DeepQ.train``
+        without a partner: with several ranks the start is agreed on (one scalar MIN all-reduce per tick until every rank is
+        ready -- both conditions are monotone, so nothing is exchanged afterwards)."""
+        if self._learning:
+            return True
+        import torch.distributed as dist
+        ready = self.dqn.step_t > self.observe and self.replay.size >= self.dqn.BATCH
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            t = torch.tensor([1.0 if ready else 0.0], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ready = bool(t.item() >= 1.0)
+        self._learning = ready
+        return ready
 
     def save(self, path: str):
         """``torch.save(policy_net.state_dict(), .../MyModel.pt)`` like policy.py:192 -- loadable by the reference."""
@@ -253,6 +270,7 @@ class VecDQNTrainer:
         if ck["replay"] is not None:
             self.replay.load_state_dict(ck["replay"])
         self.pend_slot.fill_(-1)              # in-flight transitions belonged to the episodes of the old process
+        self._learning = False                # re-agreed on by the ranks of the new process group
 
     def load(self, path: str):
         """Resume from a ``MyModel.pt`` / ``Model_Policy.pt`` state dict (the reference's or ours)."""

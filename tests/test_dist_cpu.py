@@ -163,3 +163,43 @@ def test_a2c_trainer_segment_weighted_allreduce_keeps_replicas_identical():
     assert (ssteps0, sseg0) == (ssteps1, sseg1) == (tr.train_steps, tr.segments)
     assert torch.equal(torch.from_numpy(sw0), torch.from_numpy(sw1))
     assert torch.allclose(torch.from_numpy(sw0), torch.from_numpy(w_single), rtol=1e-5, atol=1e-7)
+
+
+def _dqn_worker(rank, world, port, q):
+    import test_trainer_logic_cpu as tl
+    from drl_graph_exploration_b200 import trainer as trainer_mod
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    trainer_mod._stream_ptr = lambda dev: None
+    torch.manual_seed(0)
+    pol, tgt = tl._QNet(), tl._QNet()
+    env = tl._Env(16 if rank == 0 else 3, seed=20 + rank)          # rank 1 collects its first minibatch much later than rank 0
+    tr = trainer_mod.VecDQNTrainer(env, pol, tgt, replay_capacity=64, observe=0, lr=1e-2, seed=rank)
+    tr.dqn.BATCH = 8
+    first = None
+    for i in range(90):
+        tr.tick()
+        if first is None and tr.train_steps > 0:
+            first = (i, tr.replay.size)
+    q.put((rank, tr.train_steps, first, torch.cat([p.detach().flatten() for p in pol.parameters()]).numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_dqn_trainer_ranks_agree_on_the_tick_learning_starts():
+    """trainer.VecDQNTrainer at world size 2 with unequal shards: the start of learning (OBSERVE decisions passed, one minibatch
+    of transitions in the rank's replay) is agreed on collectively, so no rank ever enters the gradient all-reduce alone: both
+    ranks take their first gradient step in the same tick, the same number of steps overall, and the replicas stay identical."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dqn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, steps0, first0, w0), (_, steps1, first1, w1) = res
+    assert steps0 == steps1 and steps0 > 10
+    assert first0[0] == first1[0]                     # same tick ...
+    assert first0[1] > first1[1] >= 8                 # ... although rank 0 had its minibatch long before
+    assert torch.equal(torch.from_numpy(w0), torch.from_numpy(w1))
