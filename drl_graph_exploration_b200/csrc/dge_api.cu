@@ -88,6 +88,10 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   if (al.ok && cudaMallocHost(reinterpret_cast<void **>(&e.hp_mask), B) != cudaSuccess) al.ok = false;
   if (!al.ok) {
     for (void *p : al.ptrs) cudaFree(p);
+    if (e.pack_hdr_host) cudaFreeHost(e.pack_hdr_host);
+    if (e.hp_odom) cudaFreeHost(e.hp_odom);
+    if (e.hp_goal) cudaFreeHost(e.hp_goal);
+    if (e.hp_mask) cudaFreeHost(e.hp_mask);
     delete bx;
     return fail(DGE_ENOMEM, "dge_create: cudaMalloc failed");
   }
