@@ -217,8 +217,11 @@ class VecDQNTrainer:
         """The outer loop of ``DeepQ.running`` (policy.py:72-209) in ticks: trains for ``n_ticks`` and, if ``out_dir`` is given,
         leaves the reference's artefacts there -- ``temp_reward.csv`` (decision count, mean reward of the closed transitions
         since the last row), ``temp_loss.csv`` (decision count, loss), ``reward_data.csv`` (Step, Reward), ``MyModel.pt`` every
-        ``save_every`` decisions, ``Model_Policy.pt`` / ``Model_Target.pt`` at the end (policy.py:192-209)."""
+        ``save_every`` decisions, ``Model_Policy.pt`` / ``Model_Target.pt`` at the end (policy.py:192-209).  With several ranks the
+        replicas are identical: pass ``out_dir`` on rank 0 only (the reward rows are those of the rank's own envs)."""
         import os
+        if out_dir is not None:
+            os.makedirs(out_dir, exist_ok=True)     # before the loop: MyModel.pt is written from inside it
         rewards, losses, rows = [], [], []
         r0, n0, next_log, next_save = self.reward_sum, self.transitions, log_every, save_every
         for _ in range(int(n_ticks)):
@@ -237,7 +240,6 @@ class VecDQNTrainer:
                 next_save += save_every
         if out_dir is not None:
             import numpy as np
-            os.makedirs(out_dir, exist_ok=True)
             np.savetxt(os.path.join(out_dir, "temp_reward.csv"), np.asarray(rewards).reshape(-1, 2), delimiter=",")
             np.savetxt(os.path.join(out_dir, "temp_loss.csv"), np.asarray(losses).reshape(-1, 2), delimiter=",")
             with open(os.path.join(out_dir, "reward_data.csv"), "w") as f:

@@ -229,3 +229,25 @@ def test_dqn_checkpoint_and_resume(monkeypatch, tmp_path):
     for _ in range(10):
         b.tick()                                      # and it keeps running on its own envs
     assert b.train_steps > a.train_steps - 1
+
+
+def test_dqn_run_leaves_the_reference_artefacts(monkeypatch, tmp_path):
+    """VecDQNTrainer.run on the stand-in engine: the reference's training artefacts (policy.py:192-209) appear in a directory
+    that does not exist yet -- MyModel.pt is written from inside the loop --, the CSV rows carry the decision count, and the
+    saved state dicts load back into a fresh network."""
+    monkeypatch.setattr(trainer_mod, "_stream_ptr", lambda dev: None)
+    torch.manual_seed(0)
+    tr = trainer_mod.VecDQNTrainer(_Env(16, seed=4), _QNet(), _QNet(), replay_capacity=64, observe=0, lr=1e-2, seed=0)
+    tr.dqn.BATCH = 8
+    out = tmp_path / "run" / "weights"
+    rewards, losses = tr.run(60, out_dir=str(out), log_every=25, save_every=40)
+    for name in ("temp_reward.csv", "temp_loss.csv", "reward_data.csv", "MyModel.pt", "Model_Policy.pt", "Model_Target.pt"):
+        assert (out / name).exists(), name
+    assert len(rewards) >= 2 and len(losses) == tr.train_steps > 10
+    rw = np.loadtxt(out / "temp_reward.csv", delimiter=",").reshape(-1, 2)
+    assert np.all(np.diff(rw[:, 0]) > 0) and rw[-1, 0] <= tr.dqn.step_t and np.all(np.abs(rw[:, 1]) <= 1)
+    assert (out / "reward_data.csv").read_text().splitlines()[0] == "Step,Reward"
+    net = _QNet()
+    net.load_state_dict(torch.load(out / "Model_Policy.pt"))
+    for a, b in zip(net.parameters(), tr.policy_net.parameters()):
+        assert torch.equal(a, b)
