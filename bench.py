@@ -242,7 +242,7 @@ def run_policy_bucketed(args):
     from drl_graph_exploration_b200.runner import BucketedPolicyLoop
     rank, world, local, dist = _dist_setup()
     loop = GpuLoop(local, seed0=rank * 100000)
-    bl = BucketedPolicyLoop(loop.env, loop.model, short_ticks=args.short_ticks, short_fraction=args.short_fraction)
+    bl = BucketedPolicyLoop(loop.env, loop.model, short_ticks=args.short_ticks, short_fraction=args.short_fraction, adaptive=args.adaptive_ticks)
     flush = None if args.no_flush_l2 else L2Flush(loop.dev)
     for _ in range(args.warmup):
         bl.round()
@@ -276,7 +276,7 @@ def run_policy_bucketed(args):
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": WORKLOAD, "schedule": f"two trajectory-length buckets, {args.short_ticks} short ticks per long tick, "
                                      f"{args.short_fraction:.2f} of the envs short", "l2": L2Flush.HOW if flush is not None else "not flushed"},
-                          "env_steps_per_round": steps / args.steps, "mean_poses": float(v[1].item()) / max(steps, 1.0),
+                          "env_steps_per_round": steps / args.steps, "adaptive": bool(args.adaptive_ticks), "short_ticks_last_round": bl.short_ticks, "mean_poses": float(v[1].item()) / max(steps, 1.0),
                           "gpu_launches": bl.launches, "clocks": clocks}))
     finish(world, dist)
 
@@ -446,6 +446,7 @@ def main():
     ap.add_argument("--no-gnn", action="store_true", help="skip the C5 GNN samples/sec measurement appended to the default line")
     ap.add_argument("--no-overlap", action="store_true", help="run the step and policy pipelines on one stream (A/B of the overlap)")
     ap.add_argument("--short-ticks", type=int, default=3, help="policy-bucketed: ticks of the short bucket per tick of the long one")
+    ap.add_argument("--adaptive-ticks", action="store_true", help="policy-bucketed: short ticks per round follow the measured long / short step times")
     ap.add_argument("--short-fraction", type=float, default=0.75, help="policy-bucketed: share of the envs (fewest poses) in the short bucket")
     ap.add_argument("--workload", default="policy", choices=["policy", "train", "gnn", "policy-bucketed"],
                     help="policy = BASELINE configs[1] (the headline line); train = configs[2] DQN training; gnn = configs[4] GNN fwd / fwd+bwd")

@@ -104,10 +104,14 @@ class BucketedPolicyLoop:
     env is in the state ``PolicyLoop`` leaves it in after n ticks (that is what the test compares, bit for bit)."""
 
     def __init__(self, env: VecExplorationEnv, model: torch.nn.Module, short_ticks: int = 3, short_fraction: float = 0.75,
-                 seed_stride: int | None = None):
+                 seed_stride: int | None = None, adaptive: bool = False, max_short_ticks: int = 8):
         self.env, self.model = env, model
         self.dev = env.device
         self.short_ticks, self.short_fraction = int(short_ticks), float(short_fraction)
+        # adaptive: the next round's number of short ticks = measured step time of the long bucket / mean step time of a short
+        # tick in the round before (CUDA events on the step streams; costs one host join per round)
+        self.adaptive, self.max_short_ticks = bool(adaptive), int(max_short_ticks)
+        self._timing = [[], []]                   # (begin, end) events of the step pipelines of the current round
         self.seed_stride = int(seed_stride or env.B)
         self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
         L, vp = env.eng._L, ctypes.c_void_p
@@ -144,6 +148,9 @@ class BucketedPolicyLoop:
         self.ev_need[k].record(main)
         s1.wait_event(self.ev_need[k])            # also orders the step after the bucket's previous select_and_plan
         sp = ctypes.c_void_p(s1.cuda_stream)
+        if self.adaptive:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(s1)
         # ---- step pipeline of bucket k ---------------------------------------------------------------------
         _check(L.dge_reset_done_queued_bucket(h, _ptr(member), _ptr(active), self.seed_stride, self._fo, 4, sp), "dge_reset_done_queued_bucket")
         _check(L.dge_move_measure_queued_bucket(h, _ptr(member), _ptr(active), sp), "dge_move_measure_queued_bucket")
@@ -151,6 +158,9 @@ class BucketedPolicyLoop:
         _check(L.dge_slam_optimize(h, _ptr(active), sp), "dge_slam_optimize")
         _check(L.dge_virtual_map(h, _ptr(active), sp), "dge_virtual_map")
         self.ev_step[k].record(s1)
+        if self.adaptive:
+            t1.record(s1)
+            self._timing[k].append((t0, t1))
         self.launches += 5
         # ---- policy pipeline (main stream, one bucket after the other) --------------------------------------
         g = env.build_graph(need); self.launches += 3
@@ -168,6 +178,12 @@ class BucketedPolicyLoop:
     def round(self) -> int:
         """One tick of the long bucket beside ``short_ticks`` ticks of the short one.  Returns the decisions taken."""
         main = torch.cuda.current_stream(self.dev)
+        if self.adaptive and self._timing[0] and self._timing[1]:
+            self._timing[0][-1][1].synchronize(); self._timing[1][-1][1].synchronize()
+            t_long = sum(a.elapsed_time(b) for a, b in self._timing[0]) / len(self._timing[0])
+            t_short = sum(a.elapsed_time(b) for a, b in self._timing[1]) / len(self._timing[1])
+            self.short_ticks = max(1, min(self.max_short_ticks, int(t_long / max(t_short, 1e-6) + 0.5)))
+        self._timing = [[], []]
         for ev in self.ev_step:
             main.wait_event(ev)                   # join (a never-recorded event does not block)
         self._assign()
