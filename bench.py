@@ -235,52 +235,6 @@ def run_train(args):
     finish(world, dist)
 
 
-def run_policy_bucketed(args):
-    """A/B line for runner.BucketedPolicyLoop (EXPERIMENTAL, not the headline): the workload of the default line, but the envs
-    tick in two trajectory-length buckets on their own streams instead of in lock step.  A step = one round (one tick of the
-    long bucket beside ``--short-ticks`` ticks of the short one); value = policy env-steps of all ranks / max-over-ranks time."""
-    from drl_graph_exploration_b200.runner import BucketedPolicyLoop
-    rank, world, local, dist = _dist_setup()
-    loop = GpuLoop(local, seed0=rank * 100000)
-    bl = BucketedPolicyLoop(loop.env, loop.model, short_ticks=args.short_ticks, short_fraction=args.short_fraction, adaptive=args.adaptive_ticks)
-    flush = None if args.no_flush_l2 else L2Flush(loop.dev)
-    for _ in range(args.warmup):
-        bl.round()
-    bl.join(); torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    c0, events = loop.counters(), []
-    for _ in range(args.steps):
-        bl.join()
-        if flush is not None:
-            flush()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); bl.round(); bl.join(); b.record()
-        events.append((a, b))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop() if sampler else None
-    c1 = loop.counters()
-    t = torch.tensor([sum(a.elapsed_time(b) for a, b in events)], dtype=torch.float64, device=loop.dev)
-    v = torch.tensor([c1[0] - c0[0], c1[1] - c0[1]], dtype=torch.float64, device=loop.dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(v, op=dist.ReduceOp.SUM)
-    if rank == 0:
-        ms, steps = float(t.item()), float(v[0].item())
-        print(json.dumps({"metric": "env-steps/sec (bucketed ticks, experimental)", "value": steps / (ms / 1e3), "unit": "env-steps/s", "n_gpus": world,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": WORKLOAD, "schedule": f"two trajectory-length buckets, {args.short_ticks} short ticks per long tick, "
-                                     f"{args.short_fraction:.2f} of the envs short", "l2": L2Flush.HOW if flush is not None else "not flushed"},
-                          "env_steps_per_round": steps / args.steps, "adaptive": bool(args.adaptive_ticks), "short_ticks_last_round": bl.short_ticks, "mean_poses": float(v[1].item()) / max(steps, 1.0),
-                          "gpu_launches": bl.launches, "clocks": clocks}))
-    finish(world, dist)
-
-
 def synth_graph_batch(n_graphs, sizes, rng, device, n_landmarks=8):
     """C5 topology: per graph a pose chain, every pose observing Poisson(1.5) of the L landmarks, F <= L+1
     frontier stubs; x ~ N(0,1), edge_attr ~ U(0.1, 6); both edge directions, PyG DataLoader layout."""
@@ -445,10 +399,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gnn", action="store_true", help="skip the C5 GNN samples/sec measurement appended to the default line")
     ap.add_argument("--no-overlap", action="store_true", help="run the step and policy pipelines on one stream (A/B of the overlap)")
-    ap.add_argument("--short-ticks", type=int, default=3, help="policy-bucketed: ticks of the short bucket per tick of the long one")
-    ap.add_argument("--adaptive-ticks", action="store_true", help="policy-bucketed: short ticks per round follow the measured long / short step times")
-    ap.add_argument("--short-fraction", type=float, default=0.75, help="policy-bucketed: share of the envs (fewest poses) in the short bucket")
-    ap.add_argument("--workload", default="policy", choices=["policy", "train", "gnn", "policy-bucketed"],
+    ap.add_argument("--workload", default="policy", choices=["policy", "train", "gnn"],
                     help="policy = BASELINE configs[1] (the headline line); train = configs[2] DQN training; gnn = configs[4] GNN fwd / fwd+bwd")
     ap.add_argument("--train-steps-per-tick", type=int, default=1)
     ap.add_argument("--train-gemm", default="fp32", choices=["fp32", "tc3"], help="node-MLP GEMM under autograd (Networks.set_matmul_precision)")
@@ -465,8 +416,6 @@ def main():
         return run_train(args)
     if args.workload == "gnn":
         return run_gnn(args)
-    if args.workload == "policy-bucketed":
-        return run_policy_bucketed(args)
     import torch.distributed as dist
     if world > 1:
         torch.cuda.set_device(local)

@@ -145,20 +145,6 @@ extern "C" int dge_reset_done_queued(dge_handle h, uint64_t seed_stride, const d
   return rc ? fail(rc, "dge_reset_done_queued: k_reset") : DGE_OK;
 }
 
-extern "C" int dge_reset_done_queued_bucket(dge_handle h, const uint8_t *bucket, uint8_t *active, uint64_t seed_stride, const double *forced_odom_host,
-                                            int n_forced, void *stream) {
-  if (!h || !bucket || !active || !forced_odom_host || seed_stride == 0 || n_forced < 1 || n_forced >= DGE_FRESH_BIT)
-    return fail(DGE_EINVAL, "dge_reset_done_queued_bucket: bad arguments");
-  for (int i = 0; i < 3; ++i) h->forced_odom[i] = forced_odom_host[i];
-  const int rc = dge_launch_reset_done_bucket(h, bucket, active, n_forced, seed_stride, static_cast<cudaStream_t>(stream));
-  return rc ? fail(rc, "dge_reset_done_queued_bucket: k_reset") : DGE_OK;
-}
-extern "C" int dge_move_measure_queued_bucket(dge_handle h, const uint8_t *bucket, uint8_t *active, void *stream) {
-  if (!h || !bucket || !active) return fail(DGE_EINVAL, "dge_move_measure_queued_bucket: bad arguments");
-  const int rc = dge_launch_move_measure_bucket(h, bucket, active, static_cast<cudaStream_t>(stream));
-  return rc ? fail(rc, "dge_move_measure_queued_bucket") : DGE_OK;
-}
-
 extern "C" int dge_move_measure(dge_handle h, const double *odom, const uint8_t *mask, const double *noise, void *stream) {
   if (!h || !odom) return DGE_EINVAL;
   const int rc = dge_launch_move_measure(h, odom, mask, noise, 0, static_cast<cudaStream_t>(stream));

@@ -185,8 +185,6 @@ __device__ __forceinline__ void dge_normal2(uint64_t key, uint64_t ctr_lo, uint6
 int dge_launch_reset(dge_engine *e, const uint8_t *mask, const uint64_t *seeds, const double *start, const double *lm,
                      const int32_t *scan, const double *noise, int n_forced, uint64_t seed_stride, cudaStream_t st);
 int dge_launch_move_measure(dge_engine *e, const double *odom, const uint8_t *mask, const double *noise, int from_queue, cudaStream_t st);
-int dge_launch_reset_done_bucket(dge_engine *e, const uint8_t *bucket, uint8_t *active, int n_forced, uint64_t seed_stride, cudaStream_t st);
-int dge_launch_move_measure_bucket(dge_engine *e, const uint8_t *bucket, uint8_t *active, cudaStream_t st);
 int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st);
 int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st);
 int dge_vmap_standalone(const dge_config *cfg, int n, int T, const double *pose, const double *cov, int L, const double *lm,

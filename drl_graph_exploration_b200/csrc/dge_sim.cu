@@ -91,10 +91,9 @@ __device__ void measure_append(const SimArgs &a, int b, int k, const double *noi
 
 __global__ void __launch_bounds__(32) k_reset(SimArgs a, const uint8_t *mask, const uint64_t *seeds, const double *start,
                                               const double *lm, const int32_t *scan, const double *noise, int n_forced, uint64_t seed_stride,
-                                              unsigned long long *episodes, const uint8_t *bucket) {
+                                              unsigned long long *episodes) {
   const int b = blockIdx.x, lane = threadIdx.x;
   if (mask && !mask[b]) return;
-  if (bucket && !bucket[b]) return;   // bucketed stepping: only the envs of the caller's bucket (dge_reset_done_queued_bucket)
   const int Lt = a.d.Lt;
   // the mask may be the env's own `done` flag (dge_reset_done_queued): it is cleared below, after this read
   const uint64_t key = seeds ? seeds[b] : a.seed[b] + seed_stride;
@@ -163,13 +162,9 @@ __global__ void __launch_bounds__(32) k_reset(SimArgs a, const uint8_t *mask, co
   measure_append(a, b, 0, noise ? noise + (size_t)b * (3 + 4 * Lt) + 3 + 2 * Lt : nullptr, key, 0);
 }
 
-__global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *odom_in, const uint8_t *mask, const double *noise, int from_queue_flags) {
+__global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *odom_in, const uint8_t *mask, const double *noise, int from_queue) {
   const int b = blockIdx.x, lane = threadIdx.x;
   const int Lt = a.d.Lt;
-  // bit 3 (bucketed stepping): envs outside the mask are not touched at all -- their activity flag and step kind belong to
-  // another bucket's launches, possibly in flight on another stream
-  if ((from_queue_flags & 8) && mask && !mask[b]) return;
-  const int from_queue = from_queue_flags & 7;
   bool act = !(mask && !mask[b]);
   double ox = 0, oy = 0, oth = 0;
   int fl = 0;
@@ -259,21 +254,7 @@ SimArgs make_args(dge_engine *e, uint8_t *active) {
 int dge_launch_reset(dge_engine *e, const uint8_t *mask, const uint64_t *seeds, const double *start, const double *lm,
                      const int32_t *scan, const double *noise, int n_forced, uint64_t seed_stride, cudaStream_t st) {
   k_reset<<<e->d.B, 32, 0, st>>>(make_args(e, e->active), mask, seeds, start, lm, scan, noise, n_forced, seed_stride,
-                                 seed_stride ? e->counters + 3 : nullptr, nullptr);
-  return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
-}
-
-// The queued step pipeline of ONE bucket of envs (runner.BucketedPolicyLoop): `bucket` [B] selects the envs, `active` [B] is the
-// bucket's own activity mask.  Nothing of an env outside the bucket is read or written, so several buckets can be in flight on
-// different streams.
-int dge_launch_reset_done_bucket(dge_engine *e, const uint8_t *bucket, uint8_t *active, int n_forced, uint64_t seed_stride, cudaStream_t st) {
-  k_reset<<<e->d.B, 32, 0, st>>>(make_args(e, active), e->done, nullptr, nullptr, nullptr, nullptr, nullptr, n_forced, seed_stride,
-                                 e->counters + 3, bucket);
-  return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
-}
-
-int dge_launch_move_measure_bucket(dge_engine *e, const uint8_t *bucket, uint8_t *active, cudaStream_t st) {
-  k_move_measure<<<e->d.B, 32, 0, st>>>(make_args(e, active), nullptr, bucket, nullptr, 1 | 8);
+                                 seed_stride ? e->counters + 3 : nullptr);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }
 

@@ -88,117 +88,6 @@ class PolicyLoop:
         return ng
 
 
-class BucketedPolicyLoop:
-    """``PolicyLoop`` without the lock step.  EXPERIMENTAL in round 1: written against the r01 phase clocks, compiled, covered by
-    ``tests/test_zz_bucketed_loop_gpu.py`` (opt-in), not yet run on a GPU -- ``PolicyLoop`` stays the measured default.
-
-    Why: one launch of the SLAM kernel for all B envs lasts as long as its longest trajectory (r01: 290 K cycles for T = 76 while
-    the mean env needs 91 K), and in ``PolicyLoop`` every env waits for it every tick.  The reference steps one env at a time, so
-    there is no such coupling to preserve: here the envs are split by trajectory length into a *long* and a *short* bucket, each
-    with its own step stream and its own activity mask, and one **round** is one tick of the long bucket beside ``short_ticks``
-    ticks of the short bucket.  Membership is re-drawn at every round boundary (the only point where all streams are joined):
-    the ``short_fraction`` of the envs with the fewest poses are short.  The policy pipelines (graph build, GNN, read-out) of
-    all ticks share the main stream -- they are cheap next to the SLAM kernel and use one graph batch buffer.
-
-    Per env the sequence of operations and of Philox draws is exactly the one of ``PolicyLoop``: after n ticks of its bucket an
-    env is in the state ``PolicyLoop`` leaves it in after n ticks (that is what the test compares, bit for bit)."""
-
-    def __init__(self, env: VecExplorationEnv, model: torch.nn.Module, short_ticks: int = 3, short_fraction: float = 0.75,
-                 seed_stride: int | None = None, adaptive: bool = False, max_short_ticks: int = 8):
-        self.env, self.model = env, model
-        self.dev = env.device
-        self.short_ticks, self.short_fraction = int(short_ticks), float(short_fraction)
-        # adaptive: the next round's number of short ticks = measured step time of the long bucket / mean step time of a short
-        # tick in the round before (CUDA events on the step streams; costs one host join per round)
-        self.adaptive, self.max_short_ticks = bool(adaptive), int(max_short_ticks)
-        self._timing = [[], []]                   # (begin, end) events of the step pipelines of the current round
-        self.seed_stride = int(seed_stride or env.B)
-        self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
-        L, vp = env.eng._L, ctypes.c_void_p
-        L.dge_reset_done_queued_bucket.argtypes = [vp, vp, vp, ctypes.c_uint64, vp, ctypes.c_int, vp]
-        L.dge_move_measure_queued_bucket.argtypes = [vp, vp, vp, vp]
-        u8 = lambda: torch.zeros(env.B, dtype=torch.uint8, device=self.dev)
-        self.member = [u8(), u8()]                # [0] long trajectories, [1] short ones
-        self.active = [u8(), u8()]                # activity mask of each bucket's step pipeline (zero outside the bucket)
-        self.s_step = [torch.cuda.Stream(self.dev) for _ in range(2)]
-        self.ev_need = [torch.cuda.Event() for _ in range(2)]
-        self.ev_move = [torch.cuda.Event() for _ in range(2)]
-        self.ev_step = [torch.cuda.Event() for _ in range(2)]
-        self.ticks_of = torch.zeros(env.B, dtype=torch.int64, device=self.dev)   # ticks every env has taken part in so far
-        self.launches = self.graphs = self.rounds = 0
-
-    def _assign(self):
-        """Bucket membership from the current trajectory lengths (device-side, no host sync)."""
-        T = self.env.eng.state["n_poses"].float()
-        k = max(1, min(self.env.B, int(round(self.short_fraction * self.env.B))))
-        short = T <= torch.kthvalue(T, k).values
-        self.member[1].copy_(short)
-        self.member[0].copy_(~short)
-        for a in self.active:
-            a.zero_()                             # an env that changes buckets must not stay active in its old one
-
-    def _tick(self, k: int, main) -> int:
-        from . import gnn
-        env, eng = self.env, self.env.eng
-        L, h = eng._L, eng._h
-        s1, member, active = self.s_step[k], self.member[k], self.active[k]
-        main.wait_event(self.ev_step[k])          # this bucket's previous step: its queues, done flags and estimates are final
-        need = env.mark_pending() & member
-        self.ticks_of += member
-        self.ev_need[k].record(main)
-        s1.wait_event(self.ev_need[k])            # also orders the step after the bucket's previous select_and_plan
-        sp = ctypes.c_void_p(s1.cuda_stream)
-        if self.adaptive:
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record(s1)
-        # ---- step pipeline of bucket k ---------------------------------------------------------------------
-        _check(L.dge_reset_done_queued_bucket(h, _ptr(member), _ptr(active), self.seed_stride, self._fo, 4, sp), "dge_reset_done_queued_bucket")
-        _check(L.dge_move_measure_queued_bucket(h, _ptr(member), _ptr(active), sp), "dge_move_measure_queued_bucket")
-        self.ev_move[k].record(s1)
-        _check(L.dge_slam_optimize(h, _ptr(active), sp), "dge_slam_optimize")
-        _check(L.dge_virtual_map(h, _ptr(active), sp), "dge_virtual_map")
-        self.ev_step[k].record(s1)
-        if self.adaptive:
-            t1.record(s1)
-            self._timing[k].append((t0, t1))
-        self.launches += 5
-        # ---- policy pipeline (main stream, one bucket after the other) --------------------------------------
-        g = env.build_graph(need); self.launches += 3
-        ng, _, _ = g.sync_sizes()
-        if ng > 0:
-            l0 = gnn.launch_count
-            q = self.model(g.data(), 0.0)
-            main.wait_event(self.ev_move[k])      # plans are rewritten only after this tick's move kernel has read them
-            env.select_and_plan(q)
-            self.launches += gnn.launch_count - l0 + 1
-            self.graphs += ng
-        return ng
-
-    @torch.no_grad()
-    def round(self) -> int:
-        """One tick of the long bucket beside ``short_ticks`` ticks of the short one.  Returns the decisions taken."""
-        main = torch.cuda.current_stream(self.dev)
-        if self.adaptive and self._timing[0] and self._timing[1]:
-            self._timing[0][-1][1].synchronize(); self._timing[1][-1][1].synchronize()
-            t_long = sum(a.elapsed_time(b) for a, b in self._timing[0]) / len(self._timing[0])
-            t_short = sum(a.elapsed_time(b) for a, b in self._timing[1]) / len(self._timing[1])
-            self.short_ticks = max(1, min(self.max_short_ticks, int(t_long / max(t_short, 1e-6) + 0.5)))
-        self._timing = [[], []]
-        for ev in self.ev_step:
-            main.wait_event(ev)                   # join (a never-recorded event does not block)
-        self._assign()
-        ng = self._tick(0, main)
-        for _ in range(self.short_ticks):
-            ng += self._tick(1, main)
-        self.rounds += 1
-        return ng
-
-    def join(self):
-        main = torch.cuda.current_stream(self.dev)
-        for ev in self.ev_step:
-            main.wait_event(ev)
-
-
 class HostPolicyLoop:
     """The same acting loop driven from the HOST through the host-buffer C ABI -- the batched form of what
     the reference's ``test.py:100-143`` does per env: every observation crosses to the host and every

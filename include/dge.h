@@ -109,17 +109,6 @@ int dge_move_measure(dge_handle h, const double *odom_dev, const uint8_t *mask_d
 int dge_slam_optimize(dge_handle h, const uint8_t *mask_dev, void *stream);   /* SLAM2D::optimize  SLAM2D.cpp:374-430 */
 int dge_virtual_map(dge_handle h, const uint8_t *mask_dev, void *stream);     /* VirtualMap.cpp:61-84,256-316         */
 
-/* ---- bucketed stepping (runner.BucketedPolicyLoop; EXPERIMENTAL in round 1: compiled, not yet run on a GPU).  The reference
- * steps one env at a time, so an env with a long trajectory never holds up another one; a lock-step batch does (the launch of
- * SLAM2D::optimize for B envs lasts as long as its longest trajectory).  These two entry points run the first two stages of
- * the queued step pipeline for the envs of ONE bucket only -- `bucket_dev` [B] u8 selects them, `active_dev` [B] u8 is the
- * bucket's own activity mask (written for the bucket's envs only; pass it as the mask of dge_slam_optimize / dge_virtual_map
- * afterwards) -- and touch nothing of any other env, so buckets of short and long trajectories can tick at their own rates
- * on their own streams.  Per env the sequence of operations and of Philox draws is the one of dge_step_queued.           */
-int dge_reset_done_queued_bucket(dge_handle h, const uint8_t *bucket_dev, uint8_t *active_dev, uint64_t seed_stride,
-                                 const double *forced_odom_host, int n_forced, void *stream);
-int dge_move_measure_queued_bucket(dge_handle h, const uint8_t *bucket_dev, uint8_t *active_dev, void *stream);
-
 /* host-buffer variant of dge_step (the call a ctypes/pybind caller makes): copies odom
  * H2D, steps, copies done flags (and the occupancy maps when obs_host != NULL) D2H.  */
 int dge_step_host(dge_handle h, const double *odom_host, const uint8_t *mask_host, uint8_t *done_host,
