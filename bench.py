@@ -24,6 +24,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv and int(os.environ.get("RANK", "0")) == 0:
+    # the reference arm runs on rank 0 alone with all the host threads it can use: torchrun's default OMP_NUM_THREADS=1
+    # (set for every worker when the variable is unset) must not throttle its torch-CPU GCN -- before torch / MKL load
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 import torch
 
