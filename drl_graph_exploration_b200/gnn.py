@@ -327,17 +327,31 @@ def tc_matmul(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
 _q_ws: dict = {}
 
 
+def _q_forward_lib():
+    L = _gemm_lib()
+    if not hasattr(L, "_q_forward_ready"):
+        L.dge_gcn_q_forward.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 16
+        L._q_forward_ready = True
+    return L
+
+
+def _q_forward_model_args(w1: torch.Tensor, b1, w2: torch.Tensor, b2, head_w: torch.Tensor, head_b):
+    """The seven pointer arguments of ``dge_gcn_q_forward`` that depend on the model only (w1, b1, W2^T hi / lo, b2, head weight,
+    head bias) and the tensors that keep them alive."""
+    hi, lo = _weight_operand(w2, True)
+    keep = [w1.detach().contiguous(), None if b1 is None else b1.detach().contiguous(), hi, lo, None if b2 is None else b2.detach().contiguous(),
+            head_w.detach().contiguous(), None if head_b is None else head_b.detach()]
+    return [_p(t) for t in keep], keep
+
+
 def gcn_q_forward(x: torch.Tensor, gs: GraphStructure, w1: torch.Tensor, b1, w2: torch.Tensor, b2, head_w: torch.Tensor, head_b: torch.Tensor):
     """Networks.GCN.forward at inference (prob = 0) through ``dge_gcn_q_forward``: one ctypes call, three launches
     (fused first layer with the TF32 split in its epilogue -> tcgen05 GEMM -> aggregate + ReLU + head).  Returns q [N]."""
     global launch_count
     _need_cuda(x, "gcn_q_forward")
-    L = _gemm_lib()
-    if not hasattr(L, "_q_forward_ready"):
-        L.dge_gcn_q_forward.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 16
-        L._q_forward_ready = True
+    L = _q_forward_lib()
     norm, selfnorm = gs.gcn_norm(True)
-    hi, lo = _weight_operand(w2, True)
+    margs, keep = _q_forward_model_args(w1, b1, w2, b2, head_w, head_b)
     x = x.contiguous().float()
     N, cin = x.shape
     C = w1.shape[1]
@@ -348,14 +362,78 @@ def gcn_q_forward(x: torch.Tensor, gs: GraphStructure, w1: torch.Tensor, b1, w2:
         ws = _q_ws[key] = torch.empty(max(3 * N * C, 1 << 22), dtype=torch.float32, device=dev)
     q = torch.empty(N, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        rc = L.dge_gcn_q_forward(N, cin, C, _p(x), _p(gs.rowptr_dst), _p(gs.perm_dst), _p(gs.src), _p(norm), _p(selfnorm),
-                                 _p(w1.detach().contiguous()), _p(None if b1 is None else b1.detach().contiguous()), _p(hi), _p(lo),
-                                 _p(None if b2 is None else b2.detach().contiguous()), _p(head_w.detach().contiguous()),
-                                 _p(None if head_b is None else head_b.detach()), _p(ws), _p(q), _st(dev))
+        rc = L.dge_gcn_q_forward(N, cin, C, _p(x), _p(gs.rowptr_dst), _p(gs.perm_dst), _p(gs.src), _p(norm), _p(selfnorm), *margs,
+                                 _p(ws), _p(q), _st(dev))
     if rc:
         raise DgeError(f"dge_gcn_q_forward failed ({rc})")
     launch_count += 3
     return q
+
+
+class QForwardPlan:
+    """``gcn_q_forward`` for the acting loop with its argument list prepared once.  Between two ticks of ``runner.PolicyLoop``
+    every pointer of the call is the same -- the weights (inference) and the engine-owned graph batch buffers (x, destination
+    CSR, GCN normalisation: ``envs.exploration_env.GraphBatch``) -- and only the node count changes, so the per-tick Python glue
+    of the generic route (``GraphBatch.data()`` views, ``GraphStructure.from_csr``, module dispatch, 16 pointer conversions; ~90 us
+    of the loop's critical host path per tick, profiles/r01_policyloop_host_profile.txt) shrinks to one ctypes call.  Same entry
+    point, same arguments, same three launches as ``Networks.GCN.forward(data, 0.0)`` on ``batch.data()``: identical Q-values
+    (tests/test_q_plan_cpu.py compares the argument lists, tests/test_zz_q_plan_gpu.py the values).  The model arguments are
+    re-derived when a parameter changes (version counter / storage)."""
+
+    def __init__(self, model, batch):
+        self.model, self.batch = model, batch
+        self.cin, self.C = (int(v) for v in model.conv1.weight.shape)
+        self.dev = batch.x.device
+        self.q = torch.empty(batch.node_cap, dtype=torch.float32, device=self.dev)
+        self._gargs = [_p(batch.x), _p(batch.csr_rowptr), _p(batch.csr_perm), _p(batch.edge_index), _p(batch.gcn_norm), _p(batch.gcn_selfnorm)]
+        self._qarg = _p(self.q)
+        self._sig = self._margs = self._keep = self._ws = self._wsarg = None
+
+    @staticmethod
+    def eligible(model) -> bool:
+        """The conditions under which ``Networks.GCN._trunk`` itself takes the ``dge_gcn_q_forward`` route (precision mode and
+        autograd state are the caller's to check per tick)."""
+        from . import Networks
+        if type(model) is not Networks.GCN:      # the DQN Q-network itself (a subclass may read the trunk differently)
+            return False
+        try:
+            cin, C = model.conv1.weight.shape
+            return (getattr(model, "_out", None) == 1 and model.conv1.weight.is_cuda and cin <= 8 and model.conv2.out_channels % 4 == 0
+                    and model.conv2.out_channels <= 1024 and tuple(model.conv2.weight.shape) == (C, C) and model.conv1.improved and model.conv2.improved)
+        except AttributeError:
+            return False
+
+    def _params(self):
+        m = self.model
+        return (m.conv1.weight, m.conv1.bias, m.conv2.weight, m.conv2.bias, m.fully_con1.weight, m.fully_con1.bias)
+
+    def __call__(self, n_nodes: int, graph_args=None) -> torch.Tensor:
+        """Q-values [n_nodes] of the batch currently in the engine's graph buffers (a view of the plan's output buffer).
+        ``graph_args``: the six graph pointers (x, rowptr, perm, src, norm, selfnorm) when the batch lives elsewhere -- the host
+        loop's packed arena (runner.packed_graph_args)."""
+        global launch_count
+        n = int(n_nodes)
+        gargs = self._gargs if graph_args is None else graph_args
+        if n > self.batch.node_cap:
+            raise DgeError("QForwardPlan: more nodes than the graph batch holds")
+        sig = tuple((t.data_ptr(), t._version) if t is not None else None for t in self._params())
+        if sig != self._sig:
+            w1, b1, w2, b2, hw, hb = self._params()
+            self._margs, self._keep = _q_forward_model_args(w1, b1, w2, b2, hw[0], hb)
+            self._sig = sig
+        if self._ws is None or self._ws.numel() < 3 * n * self.C:
+            self._ws = torch.empty(max(3 * n * self.C, 1 << 22), dtype=torch.float32, device=self.dev)
+            self._wsarg = _p(self._ws)
+        L = _q_forward_lib()
+        if torch.cuda.current_device() == self.dev.index:
+            rc = L.dge_gcn_q_forward(n, self.cin, self.C, *gargs, *self._margs, self._wsarg, self._qarg, _st(self.dev))
+        else:
+            with torch.cuda.device(self.dev):
+                rc = L.dge_gcn_q_forward(n, self.cin, self.C, *gargs, *self._margs, self._wsarg, self._qarg, _st(self.dev))
+        if rc:
+            raise DgeError(f"dge_gcn_q_forward failed ({rc})")
+        launch_count += 3
+        return self.q[:n]
 
 
 def gru_cell_inference(m: torch.Tensor, h: torch.Tensor, rnn: torch.nn.GRUCell, relu: bool = False) -> torch.Tensor:

@@ -38,10 +38,14 @@ class PolicyLoop:
         self.launches = 0          # kernels of this package launched so far (libdge.so + gnn kernels; cuBLAS GEMMs not counted)
         self.graphs = 0            # graphs scored so far
         self.stage_events = None   # optional {"slam": [], "vmap": []} of (start, end) CUDA events on the step stream
+        # Networks.GCN at inference: the Q forward's argument list is prepared once (gnn.QForwardPlan) -- every pointer of the call
+        # is constant between ticks; other models (and other precision modes) go through model(g.data(), 0.0)
+        from . import gnn
+        self._plan = gnn.QForwardPlan(model, env.graph) if gnn.QForwardPlan.eligible(model) else None
 
     @torch.no_grad()
     def tick(self):
-        from . import gnn
+        from . import Networks, gnn
         env, eng = self.env, self.env.eng
         L, h, st = eng._L, eng._h, eng.state
         main = torch.cuda.current_stream(self.dev)
@@ -74,10 +78,10 @@ class PolicyLoop:
         self.launches += 6
         # ---- policy pipeline -----------------------------------------------------------------------------
         g = env.build_graph(need); self.launches += 4
-        ng, _, _ = g.sync_sizes()                    # the tick's only host sync (main stream only)
+        ng, nn, _ = g.sync_sizes()                   # the tick's only host sync (main stream only)
         if ng > 0:
             l0 = gnn.launch_count
-            q = self.model(g.data(), 0.0)
+            q = self._plan(nn) if self._plan is not None and Networks._PRECISION == "tc3" else self.model(g.data(), 0.0)
             if self.overlap:
                 main.wait_event(self.ev_move)        # plans are rewritten only after this tick's move kernel has read them
             env.select_and_plan(q)                   # the envs of this graph batch
@@ -86,6 +90,27 @@ class PolicyLoop:
         if self.overlap:
             main.wait_event(self.ev_step)            # join: the tick ends when both pipelines are done
         return ng
+
+
+def packed_graph_data(arena: torch.Tensor, pk, n: int, e: int):
+    """``Data`` views of a packed graph batch (``dge_graph_packed`` layout, include/dge.h) in a device arena, with the batch's
+    destination CSR and GCN normalisation adopted (no preprocessing launches)."""
+    from . import gnn
+    from .data import Data
+    f32, i32, i64 = torch.float32, torch.int32, torch.int64
+    dv = lambda off, cnt, dt, sz: arena[off:off + cnt * sz].view(dt)
+    x, ei, ea = dv(pk.x, n * 5, f32, 4).view(n, 5), dv(pk.edge_index, 2 * e, i64, 8).view(2, e), dv(pk.edge_attr, e, f32, 4)
+    data = Data(x, ei, ea)
+    data._dge_structure = gnn.GraphStructure.from_csr(ei, ea, n, dv(pk.csr_rowptr, n + 1, i32, 4), dv(pk.csr_perm, max(e, 1), i32, 4),
+                                                      dv(pk.gcn_norm, max(e, 1), f32, 4), dv(pk.gcn_selfnorm, n, f32, 4))
+    return data
+
+
+def packed_graph_args(arena: torch.Tensor, pk):
+    """The graph pointers of ``dge_gcn_q_forward`` (x, destination CSR row pointers and permutation, edge sources, GCN norm and
+    self-norm) for the same arena: what ``packed_graph_data`` + ``Networks.GCN.forward`` would pass, as plain addresses."""
+    base = arena.data_ptr()
+    return [ctypes.c_void_p(base + int(off)) for off in (pk.x, pk.csr_rowptr, pk.csr_perm, pk.edge_index, pk.gcn_norm, pk.gcn_selfnorm)]
 
 
 class HostPolicyLoop:
@@ -170,6 +195,8 @@ class HostPolicyLoop:
         self.graphs = 0
         self._frange = np.arange(eng.Lt + 1)
         self.timing = None                              # optional dict: host seconds per section (dev profiling)
+        from . import gnn
+        self._plan = gnn.QForwardPlan(model, g) if gnn.QForwardPlan.eligible(model) else None
 
     def _next_actions(self):
         """Vectorised expansion of action `cursor` of every env's line plan (Planner2D.cpp:982-1038) into odom[B,3]."""
@@ -236,7 +263,7 @@ class HostPolicyLoop:
         lap("step: host prep + async launches")
         # ---- policy pipeline (main stream, host in the loop) ----------------------------------------------------
         if do_policy:
-            from . import gnn
+            from . import Networks, gnn
             from .data import Data
             if self.packed:
                 pk = self._pk
@@ -255,14 +282,11 @@ class HostPolicyLoop:
                 self.d2h += 32 + n * 20 + e * 20 + (2 * ng + 2) * 4 + 2 * ng * 4 + self.t_fxy.nbytes + (n + 1) * 4 + e * 8 + n * 4
             if ng > 0:
                 # the policy gets the HOST graph batch, like DeepQ.test: data.to(device) -> model -> Q back on the host
+                use_plan = self.packed and self._plan is not None and Networks._PRECISION == "tc3"
                 if self.packed:
                     self.a_dev[:tot].copy_(self.a_host[:tot], non_blocking=True)          # ONE H2D for the whole batch
-                    f32, i32, i64 = torch.float32, torch.int32, torch.int64
-                    dv = lambda off, cnt, dt, sz: self.a_dev[off:off + cnt * sz].view(dt)
-                    x, ei, ea = dv(pk.x, n * 5, f32, 4).view(n, 5), dv(pk.edge_index, 2 * e, i64, 8).view(2, e), dv(pk.edge_attr, e, f32, 4)
-                    data = Data(x, ei, ea)
-                    data._dge_structure = gnn.GraphStructure.from_csr(ei, ea, n, dv(pk.csr_rowptr, n + 1, i32, 4), dv(pk.csr_perm, max(e, 1), i32, 4),
-                                                                      dv(pk.gcn_norm, max(e, 1), f32, 4), dv(pk.gcn_selfnorm, n, f32, 4))
+                    if not use_plan:
+                        data = packed_graph_data(self.a_dev, pk, n, e)
                     self.h2d += tot
                 else:
                     up = lambda t: t.to(self.dev, non_blocking=True)
@@ -275,7 +299,8 @@ class HostPolicyLoop:
                     ks, fs, nptr = self.ks[:ng].astype(np.int64), self.fs[:ng].astype(np.int64), self.nptr[:ng].astype(np.int64)
                 l0 = gnn.launch_count
                 lap("policy: H2D graph")
-                q = self.model(data, 0.0).view(-1)
+                # Networks.GCN: the prepared call (gnn.QForwardPlan) on the arena's sections; any other model: Data views + module
+                q = self._plan(n, packed_graph_args(self.a_dev, pk)) if use_plan else self.model(data, 0.0).view(-1)
                 lap("policy: model launches")
                 self.t_q[:n].copy_(q, non_blocking=True)
                 main.synchronize()
