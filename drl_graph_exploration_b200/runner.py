@@ -40,8 +40,7 @@ class PolicyLoop:
         self.stage_events = None   # optional {"slam": [], "vmap": []} of (start, end) CUDA events on the step stream
         # Networks.GCN at inference: the Q forward's argument list is prepared once (gnn.QForwardPlan) -- every pointer of the call
         # is constant between ticks; other models (and other precision modes) go through model(g.data(), 0.0)
-        from . import gnn
-        self._plan = gnn.QForwardPlan(model, env.graph) if gnn.QForwardPlan.eligible(model) else None
+        self._plan = _make_plan(model, env.graph)
 
     @torch.no_grad()
     def tick(self):
@@ -81,7 +80,11 @@ class PolicyLoop:
         ng, nn, _ = g.sync_sizes()                   # the tick's only host sync (main stream only)
         if ng > 0:
             l0 = gnn.launch_count
-            q = self._plan(nn) if self._plan is not None and Networks._PRECISION == "tc3" else self.model(g.data(), 0.0)
+            q = None
+            if self._plan is not None and Networks._PRECISION == "tc3":
+                q = _planned_q(self, nn, None)
+            if q is None:
+                q = self.model(g.data(), 0.0)
             if self.overlap:
                 main.wait_event(self.ev_move)        # plans are rewritten only after this tick's move kernel has read them
             env.select_and_plan(q)                   # the envs of this graph batch
@@ -90,6 +93,33 @@ class PolicyLoop:
         if self.overlap:
             main.wait_event(self.ev_step)            # join: the tick ends when both pipelines are done
         return ng
+
+
+def _make_plan(model, batch):
+    """``gnn.QForwardPlan`` for a ``Networks.GCN`` Q-network on the GPU, ``None`` for every other model."""
+    from . import gnn
+    try:
+        return gnn.QForwardPlan(model, batch) if gnn.QForwardPlan.eligible(model) else None
+    except Exception as exc:      # noqa: BLE001
+        import warnings
+        warnings.warn(f"gnn.QForwardPlan not available ({type(exc).__name__}: {exc}); using model(data, 0.0)")
+        return None
+
+
+def _planned_q(loop, n_nodes: int, graph_args):
+    """Q-values through the loop's ``gnn.QForwardPlan``.  The plan is glue around the same native call the module route makes; if
+    the glue itself fails (anything but the native call's own error), the loop says so once and continues on the module route --
+    both routes run the same kernels with the same arguments."""
+    from .engine import DgeError
+    try:
+        return loop._plan(n_nodes, graph_args)
+    except DgeError:
+        raise
+    except Exception as exc:      # noqa: BLE001
+        import warnings
+        warnings.warn(f"gnn.QForwardPlan disabled for this loop ({type(exc).__name__}: {exc}); using model(data, 0.0)")
+        loop._plan = None
+        return None
 
 
 def packed_graph_data(arena: torch.Tensor, pk, n: int, e: int):
@@ -195,8 +225,7 @@ class HostPolicyLoop:
         self.graphs = 0
         self._frange = np.arange(eng.Lt + 1)
         self.timing = None                              # optional dict: host seconds per section (dev profiling)
-        from . import gnn
-        self._plan = gnn.QForwardPlan(model, g) if gnn.QForwardPlan.eligible(model) else None
+        self._plan = _make_plan(model, g)
 
     def _next_actions(self):
         """Vectorised expansion of action `cursor` of every env's line plan (Planner2D.cpp:982-1038) into odom[B,3]."""
@@ -300,7 +329,9 @@ class HostPolicyLoop:
                 l0 = gnn.launch_count
                 lap("policy: H2D graph")
                 # Networks.GCN: the prepared call (gnn.QForwardPlan) on the arena's sections; any other model: Data views + module
-                q = self._plan(n, packed_graph_args(self.a_dev, pk)) if use_plan else self.model(data, 0.0).view(-1)
+                q = _planned_q(self, n, packed_graph_args(self.a_dev, pk)) if use_plan else None
+                if q is None:
+                    q = self.model(data if not use_plan else packed_graph_data(self.a_dev, pk, n, e), 0.0).view(-1)
                 lap("policy: model launches")
                 self.t_q[:n].copy_(q, non_blocking=True)
                 main.synchronize()

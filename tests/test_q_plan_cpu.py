@@ -132,3 +132,24 @@ def test_packed_arena_pointers_equal_the_views_of_the_generic_route(fake_gpu):
     plan(n, runner.packed_graph_args(arena, pk))
     gen, pl = fake_gpu.calls
     assert gen[:16] == pl[:16] and pl[3] == arena.data_ptr() + pk.x and pl[6] == arena.data_ptr() + pk.edge_index
+
+
+def test_glue_errors_fall_back_to_the_module_route_loudly_native_errors_do_not():
+    from drl_graph_exploration_b200 import runner
+
+    def broken(n, gargs=None):
+        raise ValueError("glue")
+
+    loop = types.SimpleNamespace(_plan=broken)
+    with pytest.warns(UserWarning, match="QForwardPlan disabled"):
+        assert runner._planned_q(loop, 5, None) is None
+    assert loop._plan is None
+
+    def native_failure(n, gargs=None):
+        raise gnn.DgeError("dge_gcn_q_forward failed (-2)")
+
+    loop = types.SimpleNamespace(_plan=native_failure)
+    with pytest.raises(gnn.DgeError):
+        runner._planned_q(loop, 5, None)
+    assert loop._plan is native_failure
+    assert runner._make_plan(torch.nn.Linear(5, 1), None) is None        # not the DQN Q-network: no plan, no warning

@@ -30,6 +30,7 @@ def test_plan_returns_the_q_values_of_the_module_and_the_loop_is_unchanged():
         for _ in range(ticks):
             loop.tick()
         torch.cuda.synchronize()
+        assert (loop._plan is not None) == use_plan          # the prepared route really ran (it disables itself, loudly, on a glue error)
         st = env.eng.state
         out = {k: st[k].clone() for k in ("n_poses", "sim_step", "plan", "plan_cursor", "est_pose", "prob", "metrics")}
         # one more decision round by hand: plan vs module on the same batch
