@@ -254,3 +254,29 @@ def test_a2c_running_follows_the_reference_loop():
     assert not torch.equal(before, after)
     for s_t, a_t, r_t, s_t1, term, fro, val in ac.buffer:
         assert a_t.sum() == 1 and int(np.argmax(a_t)) >= a_t.shape[0] - fro and np.isfinite(val)
+
+
+def test_compact_line_plans_expand_the_same_way_on_both_host_routes():
+    """The compact line plan (n_rot_pi, sign, rot_rem, n_fwd, fwd_rem, n_actions) of dge_line_plan is expanded in three places:
+    envs.exploration_env.expand_plan (per-env API), HostPolicyLoop._next_actions (vectorised host loop) and the kernels.  The
+    two host routes must produce the same action sequence (Planner2D.cpp:982-1038: pi-rotations, the remainder rotation, full
+    forward edges, the remainder edge)."""
+    import types
+    from drl_graph_exploration_b200.envs.exploration_env import expand_plan
+    from drl_graph_exploration_b200.runner import HostPolicyLoop
+    rng = np.random.default_rng(5)
+    B, edge = 64, 2.0
+    nrot = rng.integers(0, 2, B).astype(float); sign = rng.choice([-1.0, 1.0], B); rrem = rng.uniform(0, np.pi, B)
+    nfwd = rng.integers(0, 9, B).astype(float); frem = rng.uniform(0, edge, B)
+    plans = np.stack([nrot, sign, rrem, nfwd, frem, nrot + 1 + nfwd + 1], axis=1)
+    loop = types.SimpleNamespace(np=np, plans=plans, cursor=np.zeros(B, dtype=np.int64), odom=np.zeros((B, 3)),
+                                 env=types.SimpleNamespace(cfg=types.SimpleNamespace(max_edge_length=edge)))
+    want = [expand_plan(plans[b], edge) for b in range(B)]
+    for step in range(int(plans[:, 5].max())):
+        loop.cursor[:] = step
+        HostPolicyLoop._next_actions(loop)
+        for b in range(B):
+            if step < int(plans[b, 5]):
+                a = want[b][step]
+                assert np.allclose(loop.odom[b], [a.x, a.y, a.theta], rtol=0, atol=0), (b, step)
+    assert all(len(w) == int(plans[b, 5]) for b, w in enumerate(want))
