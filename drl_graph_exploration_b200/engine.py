@@ -69,9 +69,9 @@ def load_library():
         L.dge_virtual_map_rebuild.argtypes = [ctypes.POINTER(DgeConfigStruct), ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
         L.dge_virtual_map_rebuild_ws_doubles.restype = ctypes.c_int64
         L.dge_virtual_map_rebuild_ws_doubles.argtypes = [ctypes.c_int, ctypes.c_int]
-        for name in ("dge_graph", "dge_line_plan", "dge_select_and_plan"):
-            if hasattr(L, name):
-                getattr(L, name).restype = ctypes.c_int
+        L.dge_graph.argtypes = [vp, vp, vp, vp]
+        L.dge_line_plan.argtypes = [vp, vp, vp, vp, vp]
+        L.dge_select_and_plan.argtypes = [vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -54,3 +54,44 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def _header_prototypes():
+    """name -> number of parameters, for every function include/*.h declares."""
+    protos = {}
+    for h in ("dge.h", "dge_gnn.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        for name, args in re.findall(r"\b(dge_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", src):
+            args = args.strip()
+            protos[name] = 0 if args in ("", "void") else len(args.split(","))
+    return protos
+
+
+def test_ctypes_argtypes_match_the_header_prototypes():
+    """Every ``L.dge_*.argtypes = [...]`` in the package lists as many arguments as the prototype in include/*.h (a ctypes
+    binding with one pointer too few or too many still 'works' until the kernel reads a garbage argument)."""
+    protos = _header_prototypes()
+    assert len(protos) >= 40 and protos["dge_create"] == 5 and protos["dge_last_error"] == 0
+    from drl_graph_exploration_b200.config import DgeConfigStruct
+    from drl_graph_exploration_b200.engine import _StateView
+    vp = ctypes.c_void_p
+    ns = {"ctypes": ctypes, "vp": vp, "_vp": vp, "DgeConfigStruct": DgeConfigStruct, "_StateView": _StateView}
+    pkg = os.path.join(ROOT, "drl_graph_exploration_b200")
+    seen, bad = set(), []
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if not f.endswith(".py"):
+                continue
+            src = open(os.path.join(dp, f)).read()
+            for name, expr in re.findall(r"\.(dge_[a-z0-9_]+)\.argtypes\s*=\s*(\[[^\]]*\](?:\s*[+*]\s*(?:\[[^\]]*\]|\d+))*)\s*$", src, flags=re.M):
+                n = len(eval(expr, dict(ns)))          # noqa: S307 -- our own source, plain list arithmetic
+                seen.add(name)
+                if name not in protos:
+                    bad.append((f, name, "not declared in include/*.h"))
+                elif protos[name] != n:
+                    bad.append((f, name, f"argtypes has {n} entries, the prototype {protos[name]}"))
+    assert not bad, bad
+    unbound = sorted(set(protos) - seen - {"dge_last_error"})
+    assert not unbound, f"no argtypes for {unbound}"
