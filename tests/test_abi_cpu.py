@@ -66,7 +66,29 @@ def _header_prototypes():
         for name, args in re.findall(r"\b(dge_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", src):
             args = args.strip()
             protos[name] = 0 if args in ("", "void") else len(args.split(","))
+            kinds[name] = [] if args in ("", "void") else [_c_kind(a) for a in args.split(",")]
     return protos
+
+
+kinds = {}
+
+
+def _c_kind(decl: str) -> str:
+    """'ptr' | 'i32' | 'i64' | 'f32' | 'f64' of one C parameter declaration."""
+    d = decl.strip()
+    if "*" in d or re.search(r"\bdge_handle\b", d):
+        return "ptr"
+    for pat, k in ((r"\b(u?int64_t|long long|size_t)\b", "i64"), (r"\b(u?int32_t|int|unsigned)\b", "i32"), (r"\bfloat\b", "f32"), (r"\bdouble\b", "f64")):
+        if re.search(pat, d):
+            return k
+    raise AssertionError(f"unclassified parameter: {decl!r}")
+
+
+def _ctypes_kind(t) -> str:
+    if t is ctypes.c_void_p or t is ctypes.c_char_p or hasattr(t, "contents") or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+        return "ptr"
+    return {ctypes.c_int: "i32", ctypes.c_int32: "i32", ctypes.c_uint32: "i32", ctypes.c_int64: "i64", ctypes.c_uint64: "i64",
+            ctypes.c_float: "f32", ctypes.c_double: "f64"}[t]
 
 
 def test_ctypes_argtypes_match_the_header_prototypes():
@@ -86,12 +108,15 @@ def test_ctypes_argtypes_match_the_header_prototypes():
                 continue
             src = open(os.path.join(dp, f)).read()
             for name, expr in re.findall(r"\.(dge_[a-z0-9_]+)\.argtypes\s*=\s*(\[[^\]]*\](?:\s*[+*]\s*(?:\[[^\]]*\]|\d+))*)\s*$", src, flags=re.M):
-                n = len(eval(expr, dict(ns)))          # noqa: S307 -- our own source, plain list arithmetic
+                types_ = eval(expr, dict(ns))          # noqa: S307 -- our own source, plain list arithmetic
+                n = len(types_)
                 seen.add(name)
                 if name not in protos:
                     bad.append((f, name, "not declared in include/*.h"))
                 elif protos[name] != n:
                     bad.append((f, name, f"argtypes has {n} entries, the prototype {protos[name]}"))
+                elif [_ctypes_kind(t) for t in types_] != kinds[name]:      # pointer / 32-bit / 64-bit / float / double, position by position
+                    bad.append((f, name, f"argtypes kinds {[_ctypes_kind(t) for t in types_]} != prototype {kinds[name]}"))
     assert not bad, bad
     unbound = sorted(set(protos) - seen - {"dge_last_error"})
     assert not unbound, f"no argtypes for {unbound}"
