@@ -95,6 +95,19 @@ class PolicyLoop:
         return ng
 
 
+class GraphPacked(ctypes.Structure):
+    """``struct dge_graph_packed`` (include/dge.h): byte offsets of the sections of a packed graph batch + its totals."""
+    _fields_ = [(n, ctypes.c_int64) for n in ("total_bytes", "x", "edge_index", "edge_attr", "node_ptr", "edge_ptr", "key_size", "fro_size",
+                                              "frontier_xy", "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm")] + \
+               [(n, ctypes.c_int32) for n in ("n_graphs", "n_nodes", "n_edges", "n_done")]
+
+
+class GraphHostOut(ctypes.Structure):
+    """``struct dge_graph_host_out`` (include/dge.h): the caller's host buffers of ``dge_graph_host``."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("x", "edge_index", "edge_attr", "node_ptr", "edge_ptr", "key_size", "fro_size", "frontier_xy", "totals",
+                                               "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm")]
+
+
 def _make_plan(model, batch):
     """``gnn.QForwardPlan`` for a ``Networks.GCN`` Q-network on the GPU, ``None`` for every other model."""
     from . import gnn
@@ -195,21 +208,14 @@ class HostPolicyLoop:
         self.a_pack = torch.zeros(self.arena_cap, dtype=u8, device=self.dev)
         self.a_dev = torch.zeros(self.arena_cap, dtype=u8, device=self.dev)
 
-        class _Packed(ctypes.Structure):
-            _fields_ = [(n, ctypes.c_int64) for n in ("total_bytes", "x", "edge_index", "edge_attr", "node_ptr", "edge_ptr", "key_size", "fro_size",
-                                                      "frontier_xy", "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm")] + \
-                       [(n, ctypes.c_int32) for n in ("n_graphs", "n_nodes", "n_edges", "n_done")]
-        self._pk = _Packed()
+        self._pk = GraphPacked()
         self.packed = True
         self.t_q = pin((g.node_cap,), f32)
         self.t_choice = pin((B,), i32)
         self.t_rowptr, self.t_perm = pin((g.node_cap + 1,), i32), pin((g.edge_cap,), i32)
         self.t_norm, self.t_selfnorm = pin((g.edge_cap,), f32), pin((g.node_cap,), f32)
 
-        class _HostOut(ctypes.Structure):
-            _fields_ = [(n, vp) for n in ("x", "edge_index", "edge_attr", "node_ptr", "edge_ptr", "key_size", "fro_size", "frontier_xy", "totals",
-                                          "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm")]
-        self._ho = _HostOut(*(t.data_ptr() for t in (self.t_x, self.t_ei, self.t_ea, self.t_nptr, self.t_eptr, self.t_ks, self.t_fs, self.t_fxy, self.t_tot,
+        self._ho = GraphHostOut(*(t.data_ptr() for t in (self.t_x, self.t_ei, self.t_ea, self.t_nptr, self.t_eptr, self.t_ks, self.t_fs, self.t_fxy, self.t_tot,
                                                      self.t_rowptr, self.t_perm, self.t_norm, self.t_selfnorm)))
         for name in ("odom", "mask", "done", "metrics", "need", "nptr", "ks", "fs", "fxy", "goal", "plan", "q", "choice"):
             setattr(self, name, getattr(self, "t_" + name).numpy())

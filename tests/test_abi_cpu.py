@@ -120,3 +120,41 @@ def test_ctypes_argtypes_match_the_header_prototypes():
     assert not bad, bad
     unbound = sorted(set(protos) - seen - {"dge_last_error"})
     assert not unbound, f"no argtypes for {unbound}"
+
+
+def _header_structs():
+    """struct name -> [(field, kind)] in declaration order, for every ``typedef struct name { ... } name;`` of include/*.h."""
+    out = {}
+    for h in ("dge.h", "dge_gnn.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        for name, body in re.findall(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*\w+\s*;", src, flags=re.S):
+            fields = []
+            for decl in body.split(";"):
+                decl = decl.strip()
+                if not decl:
+                    continue
+                first, *rest = [d.strip() for d in decl.split(",")]
+                base = re.sub(r"[\*\s]*\w+$", "", first).strip()             # the type shared by a `T a, *b, c;` declaration
+                for d in [first] + rest:
+                    fname = re.search(r"(\w+)$", d).group(1)
+                    is_ptr = "*" in (d if d is not first else first[len(base):])
+                    fields.append((fname, "ptr" if is_ptr else _c_kind(base + " x")))
+            out[name] = fields
+    return out
+
+
+def test_ctypes_structures_mirror_the_header_structs():
+    """Field names, order and kinds (pointer / 32-bit / 64-bit / double) of every ctypes.Structure the package hands to the
+    library, against the struct of the same role in include/dge.h."""
+    from drl_graph_exploration_b200.config import DgeConfigStruct
+    from drl_graph_exploration_b200.engine import GraphOut, _StateView
+    from drl_graph_exploration_b200.runner import GraphHostOut, GraphPacked
+    hs = _header_structs()
+    for cname, py in (("dge_config", DgeConfigStruct), ("dge_state_view", _StateView), ("dge_graph_out", GraphOut),
+                      ("dge_graph_host_out", GraphHostOut), ("dge_graph_packed", GraphPacked)):
+        want = hs[cname]
+        got = [(n, _ctypes_kind(t)) for n, t in py._fields_]
+        assert got == want, (cname, [(a, b) for a, b in zip(got, want) if a != b], len(got), len(want))
+    assert ctypes.sizeof(GraphPacked) == 13 * 8 + 4 * 4 and ctypes.sizeof(GraphHostOut) == 13 * 8
