@@ -158,3 +158,23 @@ def test_ctypes_structures_mirror_the_header_structs():
         got = [(n, _ctypes_kind(t)) for n, t in py._fields_]
         assert got == want, (cname, [(a, b) for a, b in zip(got, want) if a != b], len(got), len(want))
     assert ctypes.sizeof(GraphPacked) == 13 * 8 + 4 * 4 and ctypes.sizeof(GraphHostOut) == 13 * 8
+
+
+def test_call_sites_pass_as_many_arguments_as_the_prototypes_take():
+    """Every ``<lib>.dge_*(...)`` call in the package, bench.py and the GPU tests' helpers passes the prototype's number of
+    arguments (calls with *args are skipped: gnn.QForwardPlan's are covered by tests/test_q_plan_cpu.py)."""
+    import ast
+    protos = _header_prototypes()
+    files = [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(ROOT, "drl_graph_exploration_b200")) for f in fs if f.endswith(".py")]
+    files += [os.path.join(ROOT, "bench.py")]
+    bad, n_calls = [], 0
+    for path in files:
+        for node in ast.walk(ast.parse(open(path).read())):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in protos:
+                if any(isinstance(a, ast.Starred) for a in node.args) or node.keywords:
+                    continue
+                n_calls += 1
+                if len(node.args) != protos[node.func.attr]:
+                    bad.append((os.path.basename(path), node.lineno, node.func.attr, len(node.args), protos[node.func.attr]))
+    assert not bad, bad
+    assert n_calls >= 50
