@@ -178,3 +178,11 @@ def test_call_sites_pass_as_many_arguments_as_the_prototypes_take():
                     bad.append((os.path.basename(path), node.lineno, node.func.attr, len(node.args), protos[node.func.attr]))
     assert not bad, bad
     assert n_calls >= 50
+
+
+def test_integration_doc_stub_lists_the_config_fields_of_the_header():
+    """INTEGRATION.md shows the ctypes binding a reference maintainer would write; its dge_config field list is the header's."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("class dge_config(ctypes.Structure)"):doc.index("vp = ctypes.c_void_p")]
+    names = re.findall(r'"(\w+)"', block)
+    assert names == [n for n, _ in _header_structs()["dge_config"]]
