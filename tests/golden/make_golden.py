@@ -49,3 +49,26 @@ for case in ("DQN_GCN", "DQN_GG-NN", "DQN_g-U-Net", "A2C_GCN", "A2C_GG-NN", "A2C
     layouts[case] = {k: list(v.shape) for k, v in sdc.items()}
 json.dump(layouts, open(os.path.join(OUT, "ref_state_dict_layouts.json"), "w"), indent=1, sort_keys=True)
 print("wrote", os.path.join(OUT, "ref_state_dict_layouts.json"))
+
+# ref_other_policies.npz : first 60 rows of ALL 1000 episodes the reference ships for its OTHER policies on the same simulator --
+# A2C+GG-NN (data/test_result/{ms}_A2C_GG-NN.csv) and Supervised+GCN / Nearest Frontier / Random / EM ({ms}_Others.csv), 50 seeds x 4
+# map sizes each.  Their decisions cannot be recomputed here (stochastic policy, unshipped weights, hand-written rules), but each
+# decision of a frontier-driven policy is one of the env's frontier goals: tests/golden/scan_guided.py follows these episodes by
+# trying every frontier and keeping the one whose rows match -- a policy-independent pin of simulator + SLAM + map + frontier +
+# line-plan arithmetic on trajectories the DQN policy never takes.
+OTHERS = {"A2C_GG-NN": ("{ms}_A2C_GG-NN.csv", "A2C+GG-NN"), "Supervised_GCN": ("{ms}_Others.csv", "Supervised+GCN"),
+          "Nearest_Frontier": ("{ms}_Others.csv", "Nearest Frontier"), "Random": ("{ms}_Others.csv", "Random"), "EM": ("{ms}_Others.csv", "EM")}
+others = {}
+for key, (pattern, cat) in OTHERS.items():
+    for ms in (40, 60, 80, 100):
+        rows = [r for r in csv.DictReader(open(os.path.join(REF, "data/test_result", pattern.format(ms=ms)))) if r["Step"] and r["Category"] == cat]
+        eps = []
+        for r in rows:
+            if float(r["Step"]) == 1.0:
+                eps.append([])
+            eps[-1].append((float(r["Landmarks error"]), float(r["Map entropy"]), float(r["Max localization uncertainty"])))
+        assert len(eps) == 50, (key, ms, len(eps))
+        for s in range(50):
+            others[f"g_{key}_{ms}_{s}"] = np.array(eps[s][:60])
+np.savez_compressed(os.path.join(OUT, "ref_other_policies.npz"), **others)
+print("wrote", os.path.join(OUT, "ref_other_policies.npz"))

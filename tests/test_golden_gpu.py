@@ -25,13 +25,17 @@ def test_cuda_path_tracks_reference_golden_csv(map_size, seed, n_steps, n_min):
     follow_episode(map_size, seed, n_steps, n_min)
 
 
-def follow_episode(map_size, seed, n_steps, n_min):
+def follow_episode(map_size, seed, n_steps, n_min, gold=None, choices=None, ent_tol=0.3):
+    """``gold`` / ``choices``: rows of another result file and the frontier index to take at every decision (instead of the
+    DQN+GCN arg-max) -- the policy-independent replay of test_zz_golden_guided_gpu.py."""
     from drl_graph_exploration_b200 import Networks
     from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv, expand_plan
 
     g0 = np.load(os.path.join(GOLD, "ref_40_DQN_GCN_seed0.npz"))
     sd = {k[3:]: torch.tensor(g0[k]) for k in g0.files if k.startswith("sd_")}
-    if (map_size, seed) == (40, 0):
+    if gold is not None:
+        pass
+    elif (map_size, seed) == (40, 0):
         gold = np.stack([g0["landmark_error"], g0["entropy"], g0["max_unc"]], axis=1)
     else:
         gold = np.load(os.path.join(GOLD, "ref_DQN_GCN_multi.npz"))[f"g_{map_size}_{seed}"]
@@ -54,12 +58,19 @@ def follow_episode(map_size, seed, n_steps, n_min):
         seed += 50
     diff = {40: 1200, 60: 1600, 80: 2000, 100: 2400}[map_size]
     st = env.eng.state
-    step, worst, diverged = 0, 0.0, None
+    step, worst, diverged, decision = 0, 0.0, None, 0
     with torch.no_grad():
         while step < n_steps and diverged is None:
             g = env.build_graph()
-            g.sync_sizes()
-            q = model(g.data(), 0.0)
+            _, n_nodes, _ = g.sync_sizes()
+            if choices is None:
+                q = model(g.data(), 0.0)
+            elif decision >= len(choices):
+                break
+            else:                                   # a one-hot "Q" puts the device-side arg-max on the recorded frontier
+                q = torch.zeros(n_nodes, device=dev)
+                q[int(g.key_size[0]) + int(choices[decision])] = 1.0
+            decision += 1
             env.select_and_plan(q)
             for act in expand_plan(st["plan"][0].cpu().numpy(), cfg.max_edge_length):
                 od = np.array([act.x, act.y, act.theta])
@@ -69,7 +80,7 @@ def follow_episode(map_size, seed, n_steps, n_min):
                 ent = -(p * np.log(p)).sum() + 0.5 * np.log(0.5) * diff            # test.py:61-76
                 gl, ge, gm = gold[step]
                 dl, dm = abs(m[4] - gl) / gl, abs(m[5] - gm) / gm
-                if not (dl < 1e-5 and dm < 1e-5 and abs(ent - ge) < 0.3):
+                if not (dl < 1e-5 and dm < 1e-5 and abs(ent - ge) < ent_tol):
                     diverged = (step, dl, dm, ent - ge)
                     break
                 worst = max(worst, dl, dm)

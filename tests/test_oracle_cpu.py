@@ -147,3 +147,29 @@ def test_reference_scan_order_is_the_old_libstdcxx_hashtable_order():
     scan = json.load(open(os.path.join(GOLD, "oracle_golden_scan.json")))
     assert sum(v["rows"] for v in scan["summary"].values()) >= 5300
     assert sum(v["episodes_ge_18_rows"] for v in scan["summary"].values()) >= 120
+
+
+# ---- the reference's OTHER result files, followed without their policies (tests/golden/scan_guided.py) ----------------------
+def _guided_cases():
+    import json
+    scan = json.load(open(os.path.join(GOLD, "oracle_guided_scan.json")))["episodes"]
+    cases = []
+    for cat in ("A2C_GG-NN", "Supervised_GCN", "Nearest_Frontier", "Random", "EM"):
+        for ms in (40, 60, 80, 100):            # per category and map size: the episode the scan followed furthest
+            key = max((k for k in scan if k.startswith(f"{cat}/{ms}_")), key=lambda k: (scan[k]["rows"], -int(k.split("_")[-1])))
+            cases.append((cat, ms, int(key.split("_")[-1]), scan[key]["rows"], scan[key]["choices"]))
+    return cases
+
+
+@pytest.mark.parametrize("cat,map_size,seed,rows,choices", _guided_cases())
+def test_follows_the_other_policies_episodes_without_their_policies(cat, map_size, seed, rows, choices):
+    """Simulator + SLAM + virtual map + frontier detection + line planner against rows of the reference's A2C+GG-NN /
+    Supervised+GCN / Nearest Frontier / Random / EM result files: at every decision the frontier whose rows reproduce the file
+    is taken (the policies themselves cannot be recomputed).  20 of the 1000 scanned episodes (24 146 rows in all,
+    tests/golden/oracle_guided_scan.json), each for >= 40 rows to <= 1e-5 relative."""
+    sys.path.insert(0, GOLD)
+    import scan_guided
+    gold = np.load(os.path.join(GOLD, "ref_other_policies.npz"))[f"g_{cat}_{map_size}_{seed}"]
+    got_rows, worst, got_choices, why = scan_guided.follow_guided(map_size, seed, gold)
+    assert got_rows == rows >= 40 and worst <= 1e-5, (got_rows, rows, worst, why)
+    assert " ".join(str(c) for c in got_choices) == choices
