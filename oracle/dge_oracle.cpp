@@ -16,6 +16,14 @@
 namespace orc {
 
 static const double kPi = 3.14159265358979323846;
+// ANALYSIS KNOB (default 0 = the pinned restatement): a shift of the vehicle position inside the nearest-frontier query only
+// (exploration_env.py:327).  The reference starts every episode at integer coordinates and its four forced reset steps
+// (1, 1, pi/2) walk a closed square, so the first decision is taken AT the integer start pose, where several frontier cell centres
+// are at exactly the same distance (e.g. 5 = |(0,5)| = |(4,3)|); `dist < min_dist` then picks whichever the rounding noise of the
+// pose estimate (1e-13) favours -- the reference's own choice is noise there.  tests/golden/scan_guided.py --knife tries the four
+// sign combinations (+-1e-9, +-1e-9) to measure how many of the early stops these ties cause.  Process-global on purpose: it is
+// a property of a scan run, not of an env.
+double g_knife_dx = 0.0, g_knife_dy = 0.0;
 
 // ------------------------------------------------------------ SE(2) algebra
 // gtsam-4.0 Pose2 semantics restated: rotation normalised to
@@ -865,7 +873,7 @@ void Env::graph(GraphOut &g) const {
   std::vector<std::vector<int>> fro_index; // [0] = robot, ip+1 = landmark ip
   g.frontier_xy.clear();
   if (!fx.empty()) {  // q15: the reference crashes when no frontier exists; here F = 0
-    fro.push_back(nearest(rob.x, rob.y));
+    fro.push_back(nearest(rob.x + g_knife_dx, rob.y + g_knife_dy));   // (analysis knob, 0 in the pinned restatement)
     fro_index.push_back({0});
     for (int ip = 0; ip < L; ++ip) {
       double lx, ly; key_xy(ip, lx, ly);

@@ -36,6 +36,8 @@
 #include <vector>
 
 namespace orc {
+extern double g_knife_dx, g_knife_dy;   // analysis knob of the golden scans (dge_oracle.cpp), 0 in every test
+
 
 // ---------------------------------------------------------------- config ---
 // scripts/envs/exploration_env.ini + pyss2d.py:10-55 (read_*_params) +

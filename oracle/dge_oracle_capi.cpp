@@ -20,6 +20,7 @@ extern "C" {
 void *orc_create(const orc::Config *cfg) { return new Env(*cfg); }
 void orc_destroy(void *h) { delete static_cast<Env *>(h); }
 void *orc_clone(void *h) { return new Env(*static_cast<Env *>(h)); }
+void orc_set_knife(double dx, double dy) { orc::g_knife_dx = dx; orc::g_knife_dy = dy; }   // analysis knob, see dge_oracle.cpp
 void orc_set_dense(void *h, int dense) { static_cast<Env *>(h)->use_dense_solver = dense != 0; }
 
 int orc_init(void *h, uint32_t seed, double sx, double sy, double sth, double *noise_rec) {
