@@ -19,7 +19,7 @@
 // reproduced to <= 1e-5 relative (mostly 1e-9..1e-15) over 5377 rows of the 200
 // episodes, policy decisions identical on those rows (tests/test_oracle_cpu.py,
 // tests/golden/scan_golden.py -> oracle_golden_scan.json); and, independently of
-// any policy, over 24 146 rows of the 1000 episodes of the reference's other
+// any policy, over 28 132 rows of the 1000 episodes of the reference's other
 // result files (A2C+GG-NN, Supervised+GCN, Nearest Frontier, Random, EM: at every
 // decision the frontier whose rows reproduce the file is taken,
 // tests/golden/scan_guided.py -> oracle_guided_scan.json).  Beyond what those

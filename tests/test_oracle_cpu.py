@@ -165,7 +165,7 @@ def _guided_cases():
 def test_follows_the_other_policies_episodes_without_their_policies(cat, map_size, seed, rows, choices):
     """Simulator + SLAM + virtual map + frontier detection + line planner against rows of the reference's A2C+GG-NN /
     Supervised+GCN / Nearest Frontier / Random / EM result files: at every decision the frontier whose rows reproduce the file
-    is taken (the policies themselves cannot be recomputed).  20 of the 1000 scanned episodes (24 146 rows in all,
+    is taken (the policies themselves cannot be recomputed).  20 of the 1000 scanned episodes (28 132 rows in all,
     tests/golden/oracle_guided_scan.json), each for >= 40 rows to <= 1e-5 relative."""
     sys.path.insert(0, GOLD)
     import scan_guided

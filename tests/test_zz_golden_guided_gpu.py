@@ -19,7 +19,8 @@ def _cases():
     scan = json.load(open(os.path.join(GOLD, "oracle_guided_scan.json")))["episodes"]
     out = []
     for cat, ms in (("Random", 40), ("Random", 100), ("A2C_GG-NN", 60), ("Nearest_Frontier", 80), ("Supervised_GCN", 40), ("EM", 60)):
-        key = max((k for k in scan if k.startswith(f"{cat}/{ms}_")), key=lambda k: (scan[k]["rows"], -int(k.split("_")[-1])))
+        # (only episodes whose every choice is in the engine's own frontier list: a "-1" is a cell tied with the nearest frontier)
+        key = max((k for k in scan if k.startswith(f"{cat}/{ms}_") and "-1" not in scan[k]["choices"]), key=lambda k: (scan[k]["rows"], -int(k.split("_")[-1])))
         out.append((cat, ms, int(key.split("_")[-1]), scan[key]["rows"], scan[key]["choices"]))
     return out
 
