@@ -16,7 +16,7 @@
 // sites line by line.  It is PINNED against the known-answer data of the
 // reference, data/test_result/{40,60,80,100}_DQN_GCN.csv (test.py, seeds 0..49,
 // shipped DQN+GCN weights): landmark error and max localisation uncertainty
-// reproduced to <= 1e-5 relative (mostly 1e-9..1e-15) over 5377 rows of the 200
+// reproduced to <= 1e-5 relative (mostly 1e-9..1e-15) over 6218 rows of the 200
 // episodes, policy decisions identical on those rows (tests/test_oracle_cpu.py,
 // tests/golden/scan_golden.py -> oracle_golden_scan.json); and, independently of
 // any policy, over 28 132 rows of the 1000 episodes of the reference's other

@@ -6,7 +6,7 @@ TEST INFRASTRUCTURE ONLY (the oracle for the GNN rows a16/a17 of SURVEY section 
 PyTorch-Geometric / torch_scatter / torch_sparse are not installable here and are unpinned
 in the reference (no requirements file) => **parity unpinned**; the shipped state dicts
 (``data/torch_weights/*/MyModel.pt``) pin parameter names and shapes, and the golden CSVs
-(``data/test_result/*_DQN_GCN.csv``) pin the DQN+GCN policy's choices end to end over 5377 rows
+(``data/test_result/*_DQN_GCN.csv``) pin the DQN+GCN policy's choices end to end over 6218 rows
 (tests/test_oracle_cpu.py); GG-NN and g-U-Net stay unpinned (the A2C result files are stochastic: dropout is always on).  All ops run in whatever dtype ``x`` has (fp32 in the
 reference; tests also use fp64 to bound the fp32 error of the CUDA kernels).
 """

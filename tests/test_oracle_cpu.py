@@ -111,7 +111,7 @@ def test_tracks_reference_golden_csv():
 
 
 # (map size, seed, rows that must be followed): a spread over the four result files of the episodes the oracle follows for
-# >= 20 rows (tests/golden/oracle_golden_scan.json holds the full scan of all 200 episodes: 5377 rows followed, 123 episodes
+# >= 20 rows (tests/golden/oracle_golden_scan.json holds the full scan of all 200 episodes: 6218 rows followed, 144 episodes
 # for >= 18 rows; regenerate with tests/golden/scan_golden.py).  Several go through the 'regenerate a environment' rule.
 TRACKED = [(40, 1, 40), (40, 3, 30), (40, 8, 25), (40, 10, 35), (40, 12, 45), (40, 14, 40), (40, 24, 45), (40, 42, 45), (40, 46, 55),
            (60, 2, 30), (60, 4, 55), (60, 7, 55), (60, 17, 55), (60, 21, 45), (60, 38, 55), (60, 40, 50),
