@@ -351,6 +351,14 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
                             "frac": gemm_flops * n_steps / sec_f / 1e12 / pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1.0)),
                             "note": "whole forward pass time in the denominator (GEMM + 2 aggregations + head), fp32-equivalent flops; the kernel alone: profiles/r01_k_gemm_tf32x3_ncu.md",
                             "traffic": None}}
+        # the same two legs on the host cores (the PyG restatement of the oracle, bounded sample): the "vs CPU ref" half of the metric
+        out["cpu_baseline"] = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle.cpu_loop import cpu_gnn_baseline
+                out["cpu_baseline"] = cpu_gnn_baseline([tuple(t.cpu() for t in b) for b in batches[:2]], os.cpu_count() or 1, budget_s=5.0)
+            except Exception as exc:      # noqa: BLE001 -- a reported baseline must never take the measured line down
+                out["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"}
         return out
     return None
 
@@ -547,7 +555,7 @@ def main():
                              "forward_graphs_per_s": g["forward"]["graphs_per_s"], "forward_ms_per_batch": g["forward"]["ms_per_batch"],
                              "forward_backward_graphs_per_s": g["forward_backward"]["graphs_per_s"],
                              "forward_backward_ms_per_batch": g["forward_backward"]["ms_per_batch"], "train_gemm": args.train_gemm,
-                             "tensor_roofline": g["roofline"]}
+                             "tensor_roofline": g["roofline"], "cpu_baseline": g.get("cpu_baseline")}
     if rank == 0:
         print(json.dumps(out))
     finish(world, dist)

@@ -73,3 +73,40 @@ def cpu_reference(map_size: int, n_landmarks: int, n_envs: int, threads: int, ma
                 queues[i] = []
 
     return run_tick, (lambda: state["steps"])
+
+
+def cpu_gnn_baseline(batches, threads: int, budget_s: float = 8.0):
+    """GNN samples/sec of the reference's GCN on host cores: the pure-PyTorch restatement of the PyG layers (gnn_ref.GCN, fp32, MKL
+    on ``threads`` threads) on the bench's own C5 batches -- forward, and forward + backward + Adam like DeepQ.train (policy.py:241-253).
+    ``batches`` = [(x, edge_index, edge_attr, batch)] CPU tensors; each leg runs for about ``budget_s`` seconds (>= 1 pass)."""
+    import time
+    torch.set_num_threads(max(1, min(threads, 32)))
+    torch.manual_seed(0)
+    model = gnn_ref.GCN()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+    graphs = [gnn_ref.Graph(x, ei, w) for x, ei, w, _ in batches]
+    n_graphs = [int(bt.max()) + 1 for _, _, _, bt in batches]
+
+    def forward(i):
+        with torch.no_grad():
+            model(graphs[i % len(graphs)], 0.0)
+
+    def forward_backward(i):
+        opt.zero_grad()
+        q = model(graphs[i % len(graphs)], 0.5)
+        ((q.view(-1) ** 2).sum() / n_graphs[i % len(graphs)]).backward()
+        for p in model.parameters():
+            p.grad.clamp_(-0.5, 0.5)
+        opt.step()
+
+    out = {"cores": int(torch.get_num_threads()), "kind": "port", "sample": f"{len(batches)} of the C5 batches, ~{budget_s:.0f} s per leg, gnn_ref.GCN (PyG restatement) fp32"}
+    for name, fn in (("forward", forward), ("forward_backward", forward_backward)):
+        model.eval() if name == "forward" else model.train()
+        fn(0)
+        t0, n, done = time.perf_counter(), 0, 0
+        while True:
+            fn(n); done += n_graphs[n % len(graphs)]; n += 1
+            if time.perf_counter() - t0 >= budget_s:
+                break
+        out[name + "_graphs_per_s"] = done / (time.perf_counter() - t0)
+    return out
