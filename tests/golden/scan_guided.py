@@ -11,7 +11,6 @@ no frontier reproduces ends the episode; only whole decisions are counted (the r
 record and expected to stop early.
 
     python tests/golden/scan_guided.py [workers]      # writes oracle_guided_scan.json (~15 s on 8 cores)
-    python tests/golden/scan_guided.py --knife        # analysis: the same under both resolutions of the knife-edge occupancy cells
 """
 import json
 import os
@@ -113,36 +112,9 @@ def _one(job):
     return f"{cat}/{ms}_{s}", {"rows": rows, "worst_rel_err": worst, "choices": " ".join(str(c) for c in dec), "stopped": why}
 
 
-def _one_knife(job):
-    """Rows followed by the pinned restatement and under the four resolutions of the nearest-frontier ties at integer poses (the
-    first decision is taken at the integer start pose, where several frontier cells are exactly equidistant: rounding noise of
-    the pose estimate decides in the reference)."""
-    import ctypes
-    from oracle.oracle import lib
-    cat, ms, s = job
-    gold = np.load(os.path.join(HERE, "ref_other_policies.npz"))[f"g_{cat}_{ms}_{s}"]
-    L = lib()
-    L.orc_set_knife.argtypes = [ctypes.c_double, ctypes.c_double]
-    out = []
-    for dx, dy in ((0.0, 0.0), (1e-9, 1e-9), (1e-9, -1e-9), (-1e-9, 1e-9), (-1e-9, -1e-9)):
-        L.orc_set_knife(dx, dy)
-        out.append(follow_guided(ms, s, gold)[0])
-    L.orc_set_knife(0.0, 0.0)
-    return f"{cat}/{ms}_{s}", out
-
-
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if a != "--knife"]
-    workers = int(args[0]) if args else (os.cpu_count() or 1)
+    workers = int(sys.argv[1]) if len(sys.argv) > 1 else (os.cpu_count() or 1)
     jobs = [(c, ms, s) for c in CATEGORIES for ms in (40, 60, 80, 100) for s in range(50)]
-    if "--knife" in sys.argv:       # analysis only: prints, writes nothing
-        with ProcessPoolExecutor(workers) as ex:
-            res = dict(ex.map(_one_knife, jobs, chunksize=4))
-        tot = [sum(v[i] for v in res.values()) for i in range(5)]
-        print(json.dumps({"rows_pinned": tot[0], "rows_per_sign_combination": tot[1:], "rows_best_resolution_per_episode": sum(max(v) for v in res.values()),
-                          "episodes_lt_5_rows_pinned": sum(v[0] < 5 for v in res.values()), "episodes_lt_5_rows_best": sum(max(v) < 5 for v in res.values()),
-                          "episodes_ge_18_rows_pinned": sum(v[0] >= 18 for v in res.values()), "episodes_ge_18_rows_best": sum(max(v) >= 18 for v in res.values())}, indent=1))
-        sys.exit(0)
     with ProcessPoolExecutor(workers) as ex:
         out = dict(ex.map(_one, jobs, chunksize=4))
     summary = {}
