@@ -63,7 +63,8 @@ def _candidates(e, g):
 
 
 def follow_guided(map_size, seed, gold, max_rows=60, tol=1e-5):
-    """Returns (rows followed, worst relative error, the frontier index chosen at every decision, why it stopped)."""
+    """Returns (rows followed, worst relative error, the frontier index chosen at every decision, why it stopped).
+    ``follow_guided.tie_decisions`` = at how many of the accepted decisions a tied alternative existed at all."""
     cfg = EnvConfig(map_size=map_size)
     while True:
         e = OracleEnv(cfg, seed, record_noise=False)
@@ -73,13 +74,15 @@ def follow_guided(map_size, seed, gold, max_rows=60, tol=1e-5):
             break
         seed += 50                                          # exploration_env.py:416-419
     row, worst, decisions = 0, 0.0, []
+    follow_guided.tie_decisions = 0
     n_gold = min(max_rows, len(gold))
     while row < n_gold:
         g = e.graph()
         if g["fro_size"] == 0:
             return row, worst, decisions, "no frontier"
         best = None
-        for f, goal in _candidates(e, g):
+        cands = _candidates(e, g)
+        for f, goal in cands:
             c = e.clone()
             r, w, ok = row, 0.0, True
             for act in c.line_plan(*goal):
@@ -100,6 +103,7 @@ def follow_guided(map_size, seed, gold, max_rows=60, tol=1e-5):
             return row, worst, decisions, f"row {row}: none of the {g['fro_size']} frontiers (nor a tied one) reproduces it"
         e, row, worst = best[0], best[1], max(worst, best[2])
         decisions.append(best[3])
+        follow_guided.tie_decisions += any(f < 0 for f, _ in cands)
         if e.metrics()["done"]:
             return row, worst, decisions, "episode done"
     return row, worst, decisions, "followed to the end of the fixture"
@@ -109,7 +113,8 @@ def _one(job):
     cat, ms, s = job
     gold = np.load(os.path.join(HERE, "ref_other_policies.npz"))[f"g_{cat}_{ms}_{s}"]
     rows, worst, dec, why = follow_guided(ms, s, gold)
-    return f"{cat}/{ms}_{s}", {"rows": rows, "worst_rel_err": worst, "choices": " ".join(str(c) for c in dec), "stopped": why}
+    return f"{cat}/{ms}_{s}", {"rows": rows, "worst_rel_err": worst, "choices": " ".join(str(c) for c in dec), "tie_decisions": follow_guided.tie_decisions,
+                                "stopped": why}
 
 
 if __name__ == "__main__":

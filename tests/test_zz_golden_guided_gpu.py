@@ -19,8 +19,9 @@ def _cases():
     scan = json.load(open(os.path.join(GOLD, "oracle_guided_scan.json")))["episodes"]
     out = []
     for cat, ms in (("Random", 40), ("Random", 100), ("A2C_GG-NN", 60), ("Nearest_Frontier", 80), ("Supervised_GCN", 40), ("EM", 60)):
-        # (only episodes whose every choice is in the engine's own frontier list: a "-1" is a cell tied with the nearest frontier)
-        key = max((k for k in scan if k.startswith(f"{cat}/{ms}_") and "-1" not in scan[k]["choices"]), key=lambda k: (scan[k]["rows"], -int(k.split("_")[-1])))
+        # (only episodes without a nearest-frontier tie at any decision: at a tie the engine's and the oracle's 1e-13 rounding noise
+        #  may pick different cells, and the recorded indices refer to the oracle's list)
+        key = max((k for k in scan if k.startswith(f"{cat}/{ms}_") and scan[k]["tie_decisions"] == 0), key=lambda k: (scan[k]["rows"], -int(k.split("_")[-1])))
         out.append((cat, ms, int(key.split("_")[-1]), scan[key]["rows"], scan[key]["choices"]))
     return out
 
