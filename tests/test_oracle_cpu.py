@@ -116,7 +116,10 @@ def test_tracks_reference_golden_csv():
 TRACKED = [(40, 1, 40), (40, 3, 30), (40, 8, 25), (40, 10, 35), (40, 12, 45), (40, 14, 40), (40, 24, 45), (40, 42, 45), (40, 46, 55),
            (60, 2, 30), (60, 4, 55), (60, 7, 55), (60, 17, 55), (60, 21, 45), (60, 38, 55), (60, 40, 50),
            (80, 1, 45), (80, 2, 45), (80, 6, 55), (80, 16, 55), (80, 24, 50), (80, 39, 45), (80, 49, 40),
-           (100, 0, 45), (100, 6, 55), (100, 16, 55), (100, 26, 50), (100, 28, 50), (100, 37, 55), (100, 48, 55)]
+           (100, 0, 45), (100, 6, 55), (100, 16, 55), (100, 26, 50), (100, 28, 50), (100, 37, 55), (100, 48, 55),
+           # followed only because the nearest-frontier ties of the first decision are enumerated (scan_golden._policy_goals): without
+           # that these stop after 1 / 1 / 5 / 15 rows
+           (40, 5, 55), (60, 11, 30), (80, 45, 40), (100, 8, 55)]
 
 
 @pytest.fixture(scope="module")
