@@ -40,10 +40,15 @@ MAP_SIZE, N_LANDMARKS, ENVS_PER_GPU, MAX_POSES = 20, 30, 256, 192
 WORKLOAD = f"{ENVS_PER_GPU} envs/GPU, {MAP_SIZE}x{MAP_SIZE} map, {N_LANDMARKS} landmarks, GCN policy inference (BASELINE configs[1])"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel in this workload, from the committed
-# `ncu --set full` captures (a number measured under the profiler is evidence for traffic, never a timing)
-NCU_TRAFFIC = {"slam": {"bytes": 6.6368e6 + 0.2383e6, "source": "profiles/r01_k_slam_v3_ncu.md (mean T ~ 20; r01_k_slam_v5_ncu.md: 3.90 MB at mean T ~ 13)"},
-               "vmap": {"bytes": 0.64128e6, "source": "profiles/r01_k_vmap_env_bench_v5_ncu.md (mean T ~ 13; outputs still in L2 when the launch ends)"}}
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the simulator kernels in this workload, from the committed
+    `ncu --set full` capture of the CURRENT kernels (profiles/traffic.json, written next to the capture's summary; a number measured
+    under the profiler is evidence for traffic, never a timing).  No file, or a file for another kernel version: null."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def peaks():
@@ -365,7 +370,7 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
 
 # ------------------------------------------------------------------------- GPU arm ---
 class GpuLoop:
-    def __init__(self, device, seed0, overlap=True):
+    def __init__(self, device, seed0, overlap=True, device_tick=True):
         from drl_graph_exploration_b200 import Networks, gnn
         from drl_graph_exploration_b200.config import EnvConfig
         from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv
@@ -378,10 +383,8 @@ class GpuLoop:
         self.env.reset()
         self.dev = self.env.device
         from drl_graph_exploration_b200.runner import PolicyLoop
-        self.runner = PolicyLoop(self.env, self.model, overlap=overlap)
-        self.launches = 0
+        self.runner = PolicyLoop(self.env, self.model, overlap=overlap, device_tick=None if device_tick else False)
         self.ev = {k: [] for k in ("slam", "vmap")}
-        self.graphs = 0
 
     def counters(self):
         """(policy env-steps, sum of trajectory lengths, sum of measurement counts) accumulated by the engine."""
@@ -391,7 +394,6 @@ class GpuLoop:
         """One tick of drl_graph_exploration_b200.runner.PolicyLoop (step pipeline || policy pipeline)."""
         self.runner.stage_events = self.ev if timed else None
         self.runner.tick()
-        self.launches, self.graphs = self.runner.launches, self.runner.graphs
 
 
 def e2e_loop(loop: GpuLoop, overlap=True):
@@ -405,7 +407,7 @@ def e2e_loop(loop: GpuLoop, overlap=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-flush-l2", action="store_true")
@@ -413,6 +415,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gnn", action="store_true", help="skip the C5 GNN samples/sec measurement appended to the default line")
     ap.add_argument("--no-overlap", action="store_true", help="run the step and policy pipelines on one stream (A/B of the overlap)")
+    ap.add_argument("--per-launch", action="store_true", help="policy loop: the per-launch schedule with one size sync per tick instead of dge_policy_tick (A/B)")
+    ap.add_argument("--ticks-per-step", type=int, default=50, help="policy loop: ticks per bench step (every tick is timed separately)")
+    ap.add_argument("--preroll", type=int, default=600, help="untimed ticks before warm-up (de-synchronises the episodes; independent of --warmup)")
     ap.add_argument("--workload", default="policy", choices=["policy", "train", "gnn"],
                     help="policy = BASELINE configs[1] (the headline line); train = configs[2] DQN training; gnn = configs[4] GNN fwd / fwd+bwd")
     ap.add_argument("--train-steps-per-tick", type=int, default=1)
@@ -436,9 +441,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = local
     torch.cuda.set_device(device)
-    loop = GpuLoop(device, seed0=rank * 100000, overlap=not args.no_overlap)
+    loop = GpuLoop(device, seed0=rank * 100000, overlap=not args.no_overlap, device_tick=not args.per_launch)
     flush = None if args.no_flush_l2 else L2Flush(loop.dev)
 
+    # untimed pre-roll, independent of --warmup: all envs were reset together, so the first ticks see T = 5..30 only.  Run until
+    # the episodes have de-synchronised (several episode lengths) and the mean trajectory length is stationary.
+    n_poses = loop.env.eng.state["n_poses"]
+    hist = []
+    for i in range(args.preroll):
+        loop.tick()
+        if (i + 1) % 100 == 0:
+            hist.append(float(n_poses.float().mean().item()))
     for _ in range(args.warmup):
         loop.tick()
     torch.cuda.synchronize()
@@ -450,21 +463,35 @@ def main():
     loop.runner.launches = 0; loop.runner.graphs = 0
     c_start = loop.counters()
     tick_events = []
-    for _ in range(args.steps):
+    t_host = 0.0
+    n_ticks = args.steps * args.ticks_per_step            # a step = ticks_per_step ticks, every tick timed on its own
+    for _ in range(n_ticks):
         if flush is not None:
-            flush()                  # L2 flush (untimed) between timed ticks
+            flush()                  # L2 flush (untimed) before every timed tick
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); loop.tick(timed=True); b.record()
+        a.record(); th = time.perf_counter(); loop.tick(); t_host += time.perf_counter() - th; b.record()
         tick_events.append((a, b))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if sampler else None
-    total_ms = sum(a.elapsed_time(b) for a, b in tick_events)
+    tick_ms = np.array([a.elapsed_time(b) for a, b in tick_events])
+    total_ms = float(tick_ms.sum())
     c_end = loop.counters()
     steps_rank, sumT, sumM = (c_end[i] - c_start[i] for i in range(3))
+    graphs_rank, launches_rank = loop.runner.graphs, loop.runner.launches
+    # per-kernel times of the two simulator kernels: CUDA events on the step stream around each launch, on the ticks that follow the
+    # timed region (same steady state; a replayed CUDA graph has no place for events, so these ticks use the per-launch schedule)
+    cs0 = loop.counters()
+    n_stage = min(max(n_ticks, 20), 100)
+    for _ in range(n_stage):
+        if flush is not None:
+            flush()
+        loop.tick(timed=True)
+    torch.cuda.synchronize()
+    cs1 = loop.counters()
     t = torch.tensor([total_ms], dtype=torch.float64, device=loop.dev)
-    s = torch.tensor([steps_rank, loop.graphs], dtype=torch.float64, device=loop.dev)
+    s = torch.tensor([steps_rank, graphs_rank], dtype=torch.float64, device=loop.dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(s, op=dist.ReduceOp.SUM)
     total_ms = float(t.item()); steps_all, graphs_all = float(s[0].item()), float(s[1].item())
@@ -475,27 +502,31 @@ def main():
         value = steps_all / (total_ms / 1e3)
         # roofline of the dominant simulator kernels (algorithmic fp64 bytes per SURVEY 8(d) x 2 for fp64)
         T_mean = sumT / max(steps_rank, 1); M_mean = sumM / max(steps_rank, 1)
+        st_steps = max(cs1[0] - cs0[0], 1)
+        T_stage, M_stage = (cs1[1] - cs0[1]) / st_steps, (cs1[2] - cs0[2]) / st_steps
         eng = loop.env.eng
         ms_slam = sum(a.elapsed_time(b) for a, b in loop.ev["slam"]) / max(len(loop.ev["slam"]), 1)
         ms_vmap = sum(a.elapsed_time(b) for a, b in loop.ev["vmap"]) / max(len(loop.ev["vmap"]), 1)
-        envs_per_launch = steps_rank / max(args.steps, 1)
-        bytes_vmap = 2 * (48 * T_mean + 20 * eng.V + 8 * eng.Lt) * envs_per_launch
-        bytes_slam = 2 * (72 * T_mean + 16 * M_mean + 32 * eng.Lt) * envs_per_launch
+        envs_per_launch = st_steps / n_stage
+        bytes_vmap = 2 * (48 * T_stage + 20 * eng.V + 8 * eng.Lt) * envs_per_launch
+        bytes_slam = 2 * (72 * T_stage + 16 * M_stage + 32 * eng.Lt) * envs_per_launch
         # the honest bound of these two kernels is the fp64 pipe, not HBM: algorithmic fp64 flops of the SLAM
         # solve per env-step = Schur complement 3 T n^2 + marginals 3 T n^2 + inverse n^3 FMAs (n = 2 x observed landmarks; the
         # O(T n) chain phases are left out), against the DFMA rate measured on this GPU (profiles/r01_fp64_latency_b200.txt)
         n2 = 2.0 * float(loop.env.eng.state["observed"].sum(dim=1).float().mean().item())
-        flops_slam = 2.0 * (6.0 * T_mean * n2 * n2 + n2 ** 3) * envs_per_launch
+        flops_slam = 2.0 * (6.0 * T_stage * n2 * n2 + n2 ** 3) * envs_per_launch
         fp64_peak = 35.2e12
         fp64 = {"kernel": "k_slam", "achieved_tflops": flops_slam / (ms_slam * 1e-3) / 1e12, "peak_tflops": fp64_peak / 1e12,
                 "frac": flops_slam / (ms_slam * 1e-3) / fp64_peak, "peak_source": "profiles/r01_fp64_latency_b200.txt (17.6 T DFMA/s measured)",
                 "mean_border_columns": n2}
         dom = "slam" if ms_slam >= ms_vmap else "vmap"
         ach = (bytes_slam / (ms_slam * 1e-3) if dom == "slam" else bytes_vmap / (ms_vmap * 1e-3)) / 1e9
+        traffic = ncu_traffic().get(dom, {})
         roof = {"bound": "hbm", "kernel": "k_slam" if dom == "slam" else "k_vmap_env", "achieved": ach,
-                "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC[dom]["bytes"],
-                "traffic_source": NCU_TRAFFIC[dom]["source"],
-                "ms_per_launch": {"slam": ms_slam, "vmap": ms_vmap}, "mean_poses": T_mean, "mean_measurements": M_mean,
+                "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic.get("bytes"),
+                "traffic_source": traffic.get("source"),
+                "sample": f"{n_stage} ticks of the per-launch schedule right after the timed region, CUDA events on the step stream around each launch",
+                "ms_per_launch": {"slam": ms_slam, "vmap": ms_vmap}, "mean_poses": T_stage, "mean_measurements": M_stage,
                 "vmap": {"achieved": bytes_vmap / (ms_vmap * 1e-3) / 1e9, "frac": bytes_vmap / (ms_vmap * 1e-3) / 1e9 / pk["hbm_gbs"]},
                 "slam": {"achieved": bytes_slam / (ms_slam * 1e-3) / 1e9, "frac": bytes_slam / (ms_slam * 1e-3) / 1e9 / pk["hbm_gbs"]},
                 "fp64": fp64}
@@ -503,13 +534,20 @@ def main():
                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": {"workload": WORKLOAD, "envs_per_gpu": ENVS_PER_GPU, "map_size": MAP_SIZE, "landmarks": N_LANDMARKS,
                                                "policy": "GCN fp32, random init", "parallelism": f"env-sharded x{world}, no data-path collective",
+                                               "step": f"{args.ticks_per_step} ticks of the acting loop, each timed by its own pair of CUDA events (L2 flushed before every tick)",
+                                               "tick": ("dge_policy_tick: one native call, replayed as a CUDA graph, no host sync" if not args.per_launch
+                                                        else "per-launch schedule, one size sync per tick"),
                                                "l2": L2Flush.HOW if flush is not None else "not flushed"},
-               "gnn_graphs_per_s": graphs_all / (total_ms / 1e3), "gpu_launches": loop.launches, "clocks": clocks, "roofline": roof}
+               "gnn_graphs_per_s": graphs_all / (total_ms / 1e3), "gpu_launches": launches_rank, "clocks": clocks, "roofline": roof,
+               "tick_ms": {"median": float(np.median(tick_ms)), "p10": float(np.percentile(tick_ms, 10)), "p90": float(np.percentile(tick_ms, 90)),
+                           "host_issue_ms": 1e3 * t_host / n_ticks, "ticks": n_ticks},
+               "mean_poses": T_mean, "envs_stepping_per_tick": steps_rank / n_ticks,
+               "preroll": {"ticks": args.preroll, "mean_poses_every_100_ticks": hist}}
     # e2e: every rank drives its own envs through the host-buffer API; whole-job steps / max wall time over ranks
     if not args.no_e2e:
         loop.env.reset()                      # fresh episodes: the host loop owns the action lists from here on
         hl = e2e_loop(loop, overlap=not args.no_overlap)
-        n_e2e = max(20, args.steps)
+        n_e2e = max(20, n_ticks)
         for _ in range(max(args.warmup, 12)):   # past the first decision and a few restarts
             hl.tick()
         torch.cuda.synchronize()

@@ -15,6 +15,8 @@ static int fail(int code, const char *what) {
   return code;
 }
 
+int dge_fail(int code, const char *what) { return fail(code, what); }
+
 extern "C" const char *dge_last_error(void) { return g_err.c_str(); }
 
 namespace {
@@ -80,7 +82,7 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.g_tmp = al.get<int32_t>(B * (size_t)d.Ecap);
   e.slam_clocks = al.get<long long>(B * 12);
   e.forced = al.get<int32_t>(B); e.step_kind = al.get<uint8_t>(B); e.pending = al.get<uint8_t>(B);
-  e.counters = al.get<unsigned long long>(4); e.count_steps = 1; e.park_done = 1;
+  e.counters = al.get<unsigned long long>(8); e.count_steps = 1; e.park_done = 1;
   e.rdist = al.get<double>(B); e.r_cmap = al.get<int32_t>(B * 2); e.r_cbase = al.get<int32_t>(B); e.r_u0 = al.get<double>(B);
   if (al.ok && cudaMallocHost(reinterpret_cast<void **>(&e.pack_hdr_host), 16 * sizeof(int64_t)) != cudaSuccess) al.ok = false;
   if (al.ok && cudaMallocHost(reinterpret_cast<void **>(&e.hp_odom), B * 3 * sizeof(double)) != cudaSuccess) al.ok = false;
@@ -103,6 +105,7 @@ extern "C" int dge_destroy(dge_handle h) {
   if (!h) return DGE_EINVAL;
   EngineBox *bx = reinterpret_cast<EngineBox *>(h);   // e is the first member
   cudaSetDevice(h->device);
+  dge_tick_release(h);
   for (void *p : bx->al.ptrs) cudaFree(p);
   if (h->pack_hdr_host) cudaFreeHost(h->pack_hdr_host);
   if (h->hp_odom) cudaFreeHost(h->hp_odom);

@@ -8,16 +8,17 @@
 //     A B^T ~= Ah Bh^T + Al Bh^T + Ah Bl^T                   (dropped term Al Bl^T ~ 2^-22 relative)
 // with fp32 accumulation in tensor memory: error ~1e-6 relative, i.e. fp32-GEMM quality at tensor-core speed.
 //
-// Kernel shape (one 128x128 output tile per CTA, 192 threads, warp-specialised):
+// Kernel shape (persistent: one CTA per SM walks the 128x128 output tiles; 192 threads, warp-specialised; the accumulator is
+// double-buffered in tensor memory so the epilogue of a tile overlaps the MMAs of the next one):
 //   warp 0   TMA producer: per 32-wide K block four 128x32 fp32 boxes (Ah, Al, Bh, Bl; 128-byte swizzle)
 //            into a 3-stage shared-memory ring, completion on an mbarrier (expect_tx);
-//   warp 1   allocates 128 TMEM columns, then one elected lane issues tcgen05.mma.kind::tf32 (M128 N128 K8):
+//   warp 1   allocates 256 TMEM columns, then one elected lane issues tcgen05.mma.kind::tf32 (M128 N128 K8):
 //            3 products x 4 K-steps per stage, tcgen05.commit releases the stage / signals the epilogue;
 //   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp and pass) -> registers -> 128-byte row
 //            segments of C (row / column masked).
 // Operands are K-major ([rows, K] with K contiguous): A = activations, B^T = the weight stored [out, in].
 // The row count can be read from device memory (M_dev) so that a graph batch whose size is only known on the
-// device needs no host synchronisation: CTAs beyond the live rows exit immediately.
+// device needs no host synchronisation: the tile loop is bounded by the live rows, surplus CTAs exit immediately.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
@@ -32,7 +33,7 @@ constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;          // 16 KB per operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // Ah, Al, Bh, Bl
 constexpr int GEMM_THREADS = 192;
-constexpr int TMEM_COLS = 128;                   // 128 lanes x 128 fp32 columns = the 128x128 accumulator
+constexpr int TMEM_COLS = 256;                   // 128 lanes x 2 x 128 fp32 columns = two 128x128 accumulators (double buffer)
 constexpr int UMMA_K = 8;                        // tf32: 32 bytes of K per instruction
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
 
@@ -91,24 +92,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
                : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent kernel: gridDim.x CTAs (<= one per SM) walk the live 128x128 tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+// (column tile fastest, so neighbouring CTAs share an A row block through L2).  The accumulator is double-buffered in tensor
+// memory (2 x 128 columns): the epilogue of tile i drains buffer i & 1 while the MMAs of tile i + 1 fill the other one, and the
+// TMA ring runs ahead across tile boundaries.  The live row count is read from device memory when M_dev is given.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
               const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
               float *__restrict__ C, int M, const int32_t *__restrict__ M_dev, int N, int K, int ldc) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int rows = M_dev ? min(M, *M_dev) : M;
-  if (m0 >= rows) return;                                  // uniform per CTA, before any barrier / allocation
+  const int n_tiles = (N + BN - 1) / BN;
+  const int total = ((rows + BM - 1) / BM) * n_tiles;
+  if ((int)blockIdx.x >= total) return;                    // uniform per CTA, before any barrier / allocation
   extern __shared__ uint8_t smem_raw[];
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B tiles want 1024-byte alignment
   const uint32_t bars = tiles + STAGES * STAGE_BYTES;
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, slot = tfull + 8;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16, slot = tempty0 + 16;
   uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (slot - smem_u32(smem_raw)));
   const int num_kb = (K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(tfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {                                         // one warp owns the TMEM allocation
@@ -122,61 +132,80 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {                                       // ---- TMA producer
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
-        const uint32_t st = tiles + s * STAGE_BYTES, fb = full0 + 8 * s;
-        mbar_expect_tx(fb, STAGE_BYTES);
-        tma_load_2d(st, &mAh, fb, kb * BK, m0);
-        tma_load_2d(st + TILE_BYTES, &mAl, fb, kb * BK, m0);
-        tma_load_2d(st + 2 * TILE_BYTES, &mBh, fb, kb * BK, n0);
-        tma_load_2d(st + 3 * TILE_BYTES, &mBl, fb, kb * BK, n0);
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
+          const uint32_t st = tiles + s * STAGE_BYTES, fb = full0 + 8 * s;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          tma_load_2d(st, &mAh, fb, kb * BK, m0);
+          tma_load_2d(st + TILE_BYTES, &mAl, fb, kb * BK, m0);
+          tma_load_2d(st + 2 * TILE_BYTES, &mBh, fb, kb * BK, n0);
+          tma_load_2d(st + 3 * TILE_BYTES, &mBl, fb, kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {                                       // ---- MMA issuer (one thread drives the tensor core)
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(tempty0 + 8 * acc, ((lt >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator (free at first use)
         tc_fence_after();
-        const uint32_t st = tiles + s * STAGE_BYTES;
+        const uint32_t td = tmem + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = tiles + s * STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint32_t off = k * UMMA_K * 4;             // 32 bytes along K inside the swizzled 128-byte row
-          const uint64_t ah = smem_desc(st + off), al = smem_desc(st + TILE_BYTES + off);
-          const uint64_t bh = smem_desc(st + 2 * TILE_BYTES + off), bl = smem_desc(st + 3 * TILE_BYTES + off);
-          umma_tf32(tmem, al, bh, (kb | k) ? 1u : 0u);     // small terms first
-          umma_tf32(tmem, ah, bl, 1u);
-          umma_tf32(tmem, ah, bh, 1u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t off = k * UMMA_K * 4;           // 32 bytes along K inside the swizzled 128-byte row
+            const uint64_t ah = smem_desc(st + off), al = smem_desc(st + TILE_BYTES + off);
+            const uint64_t bh = smem_desc(st + 2 * TILE_BYTES + off), bl = smem_desc(st + 3 * TILE_BYTES + off);
+            umma_tf32(td, al, bh, (kb | k) ? 1u : 0u);     // small terms first
+            umma_tf32(td, ah, bl, 1u);
+            umma_tf32(td, ah, bh, 1u);
+          }
+          umma_commit(empty0 + 8 * s);                     // stage free once these MMAs have read it
         }
-        umma_commit(empty0 + 8 * s);                       // stage free once these MMAs have read it
+        umma_commit(tfull0 + 8 * acc);                     // accumulator complete
       }
-      umma_commit(tfull);                                  // accumulator complete
     }
   } else {                                                 // ---- epilogue: TMEM -> registers -> C
-    mbar_wait(tfull, 0);
-    tc_fence_after();
     const int q = warp & 3;                                // a warp reaches TMEM lanes [32 (warp % 4), +32)
-    const int row = m0 + q * 32 + lane;
-    float *crow = C + (size_t)row * ldc + n0;
+    int lt = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      const int acc = lt & 1;
+      mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      float *crow = C + (size_t)row * ldc + n0;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, r);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < rows) {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < rows) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int col = n0 + c * 32 + 4 * i;
-          if (col + 3 < N) {
-            *reinterpret_cast<float4 *>(crow + c * 32 + 4 * i) =
-                make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-          } else {
-            for (int j = 0; j < 4; ++j)
-              if (col + j < N) crow[c * 32 + 4 * i + j] = __uint_as_float(r[4 * i + j]);
+          for (int i = 0; i < 8; ++i) {
+            const int col = n0 + c * 32 + 4 * i;
+            if (col + 3 < N) {
+              *reinterpret_cast<float4 *>(crow + c * 32 + 4 * i) =
+                  make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            } else {
+              for (int j = 0; j < 4; ++j)
+                if (col + j < N) crow[c * 32 + 4 * i + j] = __uint_as_float(r[4 * i + j]);
+            }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);       // 4 epilogue warps -> the accumulator may be overwritten
     }
   }
   tc_fence_before();
@@ -279,7 +308,13 @@ extern "C" int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const 
     if (cudaFuncSetAttribute(k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM) != cudaSuccess) return -2;
     configured = true;
   }
-  const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  const long long tiles_cap = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const unsigned grid = (unsigned)(tiles_cap < n_sm ? tiles_cap : n_sm);
   k_gemm_tf32x3<<<grid, GEMM_THREADS, GEMM_SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

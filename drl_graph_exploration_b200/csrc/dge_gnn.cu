@@ -126,11 +126,13 @@ __global__ void __launch_bounds__(256) k_aggregate(int N, int C, const float *__
                                                    const float *__restrict__ coef, const float *__restrict__ selfcoef,
                                                    const float *__restrict__ bias, const float *__restrict__ gate, int relu,
                                                    float *__restrict__ out, const float *__restrict__ head_w, float head_b,
-                                                   float *__restrict__ q, const float *__restrict__ head_b_dev = nullptr) {
+                                                   float *__restrict__ q, const float *__restrict__ head_b_dev = nullptr,
+                                                   const int32_t *__restrict__ N_dev = nullptr) {
   constexpr int VEC = 4;
-  const int i = blockIdx.x;
   const int c0 = threadIdx.x * VEC;
   const bool act = c0 < C;
+  const int n_live = N_dev ? min(N, *N_dev) : N;     // a batch sized on the device: the grid is a capacity, the loop bound is live
+  for (int i = blockIdx.x; i < n_live; i += gridDim.x) {
   float acc[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
@@ -192,6 +194,8 @@ __global__ void __launch_bounds__(256) k_aggregate(int N, int C, const float *__
       for (int wv = 0; wv < 8; ++wv) s += red[wv];
       q[i] = s + head_b + (head_b_dev ? head_b_dev[0] : 0.f);
     }
+    __syncthreads();   // `red` is reused by the next node of this CTA
+  }
   }
 }
 
@@ -247,9 +251,10 @@ __global__ void __launch_bounds__(256) k_gcn_conv_small(int N, int Cin, int C, c
                                                         const float *__restrict__ coef, const float *__restrict__ selfcoef,
                                                         const float *__restrict__ W, const float *__restrict__ bias, int relu,
                                                         float *__restrict__ out, float *__restrict__ out_hi = nullptr,
-                                                        float *__restrict__ out_lo = nullptr) {
-  const int i = blockIdx.x;
+                                                        float *__restrict__ out_lo = nullptr, const int32_t *__restrict__ N_dev = nullptr) {
   __shared__ float agg[CIN_MAX];
+  const int n_live = N_dev ? min(N, *N_dev) : N;
+  for (int i = blockIdx.x; i < n_live; i += gridDim.x) {
   if (threadIdx.x < 32) {   // one warp aggregates the input row: lanes over edges (fixed order per lane, shuffle tree => deterministic)
     float a[CIN_MAX];
 #pragma unroll
@@ -287,6 +292,8 @@ __global__ void __launch_bounds__(256) k_gcn_conv_small(int N, int Cin, int C, c
       out_lo[(size_t)i * C + c] = __uint_as_float(lb);
     }
   }
+  __syncthreads();   // `agg` is reused by the next node of this CTA
+  }
 }
 }  // namespace
 
@@ -301,21 +308,33 @@ extern "C" int dge_gcn_conv_small(int N, int Cin, int C, const float *X, const i
 // Networks.GCN.forward with prob = 0 (Networks.py:18-28): relu(GCNConv(5,C)) -> relu(GCNConv(C,C)) -> Linear(C,1), as
 // three launches: first layer fused (aggregate 5 channels, transform, ReLU, TF32 split in the epilogue) -> tcgen05
 // 3xTF32 GEMM -> aggregate + bias + ReLU + head dot product.  ws = 3 * N * C floats (h_hi | h_lo | h W2).
+// grid of a node-parallel kernel: one CTA per node up to a few waves of the machine, then grid-stride
+static inline int node_grid(int N) { return N < 148 * 16 ? N : 148 * 16; }
+
+// N_dev (nullable): the live node count on the device (<= N, which then is the capacity the launch is sized for) -- the form the
+// sync-free acting loop uses (dge_policy_tick, csrc/dge_tick.cu)
+int dge_gcn_q_forward_dev(int N, const int32_t *N_dev, int Cin, int C, const float *x, const int32_t *rowptr, const int32_t *perm, const int64_t *src,
+                          const float *norm, const float *selfnorm, const float *W1, const float *b1, const float *W2t_hi,
+                          const float *W2t_lo, const float *b2, const float *head_w, const float *head_b_dev, float *ws, float *q,
+                          cudaStream_t st) {
+  if (N <= 0 || Cin <= 0 || Cin > 8 || C <= 0 || C > 1024 || (C & 3) || !x || !rowptr || !perm || !selfnorm || !W1 || !W2t_hi ||
+      !W2t_lo || !head_w || !ws || !q || ((uintptr_t)ws & 15))
+    return -1;
+  float *h_hi = ws, *h_lo = ws + (size_t)N * C, *xw = ws + 2 * (size_t)N * C;
+  k_gcn_conv_small<8><<<node_grid(N), 256, 0, st>>>(N, Cin, C, x, rowptr, perm, src, norm, selfnorm, W1, b1, 1, nullptr, h_hi, h_lo, N_dev);
+  if (cudaGetLastError() != cudaSuccess) return -2;
+  const int rc = dge_gemm_tf32x3(N, N_dev, C, C, h_hi, h_lo, W2t_hi, W2t_lo, xw, C, st);
+  if (rc) return rc;
+  k_aggregate<true><<<node_grid(N), 256, 0, st>>>(N, C, xw, rowptr, perm, src, norm, selfnorm, b2, nullptr, 1, nullptr, head_w, 0.f, q, head_b_dev, N_dev);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 extern "C" int dge_gcn_q_forward(int N, int Cin, int C, const float *x, const int32_t *rowptr, const int32_t *perm, const int64_t *src,
                                  const float *norm, const float *selfnorm, const float *W1, const float *b1, const float *W2t_hi,
                                  const float *W2t_lo, const float *b2, const float *head_w, const float *head_b_dev, float *ws, float *q,
                                  void *stream) {
-  if (N <= 0 || Cin <= 0 || Cin > 8 || C <= 0 || C > 1024 || (C & 3) || !x || !rowptr || !perm || !selfnorm || !W1 || !W2t_hi ||
-      !W2t_lo || !head_w || !ws || !q || ((uintptr_t)ws & 15))
-    return -1;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float *h_hi = ws, *h_lo = ws + (size_t)N * C, *xw = ws + 2 * (size_t)N * C;
-  k_gcn_conv_small<8><<<N, 256, 0, st>>>(N, Cin, C, x, rowptr, perm, src, norm, selfnorm, W1, b1, 1, nullptr, h_hi, h_lo);
-  if (cudaGetLastError() != cudaSuccess) return -2;
-  const int rc = dge_gemm_tf32x3(N, nullptr, C, C, h_hi, h_lo, W2t_hi, W2t_lo, xw, C, stream);
-  if (rc) return rc;
-  k_aggregate<true><<<N, 256, 0, st>>>(N, C, xw, rowptr, perm, src, norm, selfnorm, b2, nullptr, 1, nullptr, head_w, 0.f, q, head_b_dev);
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  return dge_gcn_q_forward_dev(N, nullptr, Cin, C, x, rowptr, perm, src, norm, selfnorm, W1, b1, W2t_hi, W2t_lo, b2, head_w, head_b_dev, ws, q,
+                               static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------ GRU cell gates (GG-NN) ---------------------

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(GT) k_graph_count(GraphArgs a, const uint8_t *
 // single CTA, 1024 threads: three exclusive scans (graph position, node offset, edge offset) over
 // the selected envs; each thread owns a contiguous chunk of envs, chunk totals by Hillis-Steele.
 __global__ void __launch_bounds__(1024) k_graph_scan(int B, const uint8_t *mask, const int32_t *g_counts, int32_t *g_sel, dge_graph_out o,
-                                                     const uint8_t *done) {
+                                                     const uint8_t *done, unsigned long long *counters) {
   __shared__ int sg[1024], sn[1024], se[1024], sd[1024];
   const int tid = threadIdx.x;
   const int per = (B + 1023) / 1024;
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(1024) k_graph_scan(int B, const uint8_t *mask,
     o.totals[3] = (N > o.node_cap || E > o.edge_cap) ? 1 : 0;
     o.totals[4] = sd[1023];   // envs whose episode is over (lets the host fold the reset check into the same D2H)
     if (o.csr_rowptr && !o.totals[3]) o.csr_rowptr[N] = E;
+    if (counters) { counters[4] += G; counters[5] += N; counters[6] += E; counters[7] += 1; }   // single writer: this thread
   }
 }
 
@@ -422,7 +423,7 @@ int dge_launch_graph(dge_engine *e, const uint8_t *mask, const dge_graph_out *ou
   const GraphArgs a = make_gargs(e);
   const size_t sm1 = ((e->d.V + 15) / 16) * 16 + (2 * e->d.Lt + 2) * sizeof(int);
   k_graph_count<<<e->d.B, GT, sm1, st>>>(a, mask);
-  k_graph_scan<<<1, 1024, 0, st>>>(e->d.B, mask, e->g_counts, e->g_sel, *out, e->done);
+  k_graph_scan<<<1, 1024, 0, st>>>(e->d.B, mask, e->g_counts, e->g_sel, *out, e->done, e->count_steps ? e->counters : nullptr);
   const size_t sm3 = (4 * e->d.Lt + 4) * sizeof(int);
   k_graph_fill<<<e->d.B, GT, sm3, st>>>(a, *out);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;

@@ -73,7 +73,8 @@ struct dge_engine {
   int32_t *r_cmap;       // [B,2] (as roll-out engine) source env / frontier of each clone slot
   int32_t *r_cbase;      // [B]   (as source engine) first clone slot of each env
   double *r_u0;          // [B]   (as roll-out engine) utility before the roll-out
-  unsigned long long *counters;   // [4] work counters: policy env-steps, sum of T, sum of M, episodes restarted by dge_reset_done_queued
+  unsigned long long *counters;   // [8] work counters: policy env-steps, sum of T, sum of M, episodes restarted by dge_reset_done_queued,
+                                  //     graphs built for a decision, their nodes, their edges, graph batches
   long long *slam_clocks; // [B,12] phase-boundary clocks of the last k_slam launch (+ T in slot 7, sub-phase cycles in 8..11)
   int32_t *forced;       // [B] forced steps left after an in-pipeline reset (| DGE_FRESH_BIT while the initial optimize is pending)
   uint8_t *step_kind;    // [B] 1 = the env's last step was a policy step
@@ -85,6 +86,11 @@ struct dge_engine {
   double forced_odom[3]; // host copy of the forced action (exploration_env.py:411-414)
   int count_steps;       // host flag: 1 while stepping on behalf of the policy (reset steps are not counted)
   int park_done;         // host flag: queued stepping skips `done` envs (1, default) or runs every plan to its end (0, roll-out engines)
+  // ---- dge_policy_tick (csrc/dge_tick.cu): second stream + fork/join events, capture stream, the captured tick and what it was captured for
+  cudaStream_t tick_stream, tick_cap_stream;
+  cudaEvent_t ev_fork, ev_move, ev_join;
+  cudaGraphExec_t tick_exec;
+  void *tick_key;
 };
 
 // ------------------------------------------------------------- device math ---
@@ -193,6 +199,8 @@ int dge_launch_graph(dge_engine *e, const uint8_t *mask, const dge_graph_out *ou
 int dge_launch_mark_pending(dge_engine *e, cudaStream_t st);
 int dge_launch_line_plan(dge_engine *e, const double *goal, const uint8_t *mask, double *plan_out, cudaStream_t st);
 int dge_launch_select_plan(dge_engine *e, const dge_graph_out *g, const float *q, const uint8_t *mask, int32_t *choice, cudaStream_t st);
+void dge_tick_release(dge_engine *e);
+int dge_fail(int code, const char *what);   // records the message dge_last_error returns
 int dge_vmap_nchunk(int T);
 int dge_vmap_prep_width();
 size_t dge_slam_smem_bytes(int Lt);

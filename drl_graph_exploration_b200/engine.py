@@ -133,7 +133,7 @@ class Engine:
             "lin_l": ((B, L, 2), torch.float64), "land_cov": ((B, L, 3), torch.float64), "prob": ((B, self.rows, self.cols), torch.float64),
             "vinfo": ((B, self.rows, self.cols, 3), torch.float64), "seen": ((B, self.rows, self.cols), torch.int32),
             "metrics": ((B, 8), torch.float64), "done": ((B,), torch.uint8), "active": ((B,), torch.uint8), "status": ((B,), torch.int32),
-            "plan": ((B, 6), torch.float64), "plan_cursor": ((B,), torch.int32), "counters": ((4,), torch.int64), "slam_clocks": ((B, 12), torch.int64), "forced": ((B,), torch.int32), "seed": ((B,), torch.int64), "pending": ((B,), torch.uint8),
+            "plan": ((B, 6), torch.float64), "plan_cursor": ((B,), torch.int32), "counters": ((8,), torch.int64), "slam_clocks": ((B, 12), torch.int64), "forced": ((B,), torch.int32), "seed": ((B,), torch.int64), "pending": ((B,), torch.uint8),
         }
         self.state = {}
         for name, (shape, dt) in spec.items():

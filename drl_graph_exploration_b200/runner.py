@@ -1,16 +1,19 @@
-"""Device-resident acting loop: B environments follow a GNN policy with one host sync per tick.
+"""Device-resident acting loop: B environments follow a GNN policy with NO host synchronisation per tick.
 
 This is the batched counterpart of the reference's ``test.py`` / ``DeepQ.test`` inner loop
-(policy.py:236-306: get graph -> Q-values -> arg-max frontier -> ``env.step`` along the planned line),
+(test.py:100-143, policy.py:236-306: get graph -> Q-values -> arg-max frontier -> ``env.step`` along the planned line),
 scheduled for a GPU instead of one env at a time:
 
 * every tick, each env with a queued action executes exactly one simulator step
   (move + association scan, SLAM update, virtual-map rebuild -- the *step pipeline*), and each env whose
   queue ran empty gets its exploration graph built, scored by the policy and a new line plan queued
   (the *policy pipeline*).  A freshly planned env starts moving at the next tick;
-* the two pipelines touch disjoint env sets, so they run on two CUDA streams: the host-side size sync of
-  the graph batch and the GNN's dense GEMMs hide under the latency-bound SLAM kernel;
-* finished episodes restart in-pipeline (``dge_reset_done_queued``): no extra launches, no host branch.
+* the two pipelines touch disjoint env sets, so they run on two CUDA streams;
+* finished episodes restart in-pipeline (``dge_reset_done_queued``): no extra launches, no host branch;
+* for the DQN Q-network (``Networks.GCN``) the whole tick is ONE native call, ``dge_policy_tick`` (include/dge.h): the size of
+  the decision batch never leaves the device (launches are sized by capacity, kernels read the live counts), so the launch
+  sequence is fixed and is replayed as a CUDA graph -- one ``cudaGraphLaunch`` per tick.  Other policies (GG-NN, g-U-Net) go
+  through ``model(data, 0.0)`` and pay one size sync per tick.
 
 Per env the sequence of operations (and of Philox draws) is the same as in a sequential run of the
 reference loop; only the interleaving between envs differs.
@@ -25,8 +28,59 @@ from .engine import _check, _ptr
 from .envs.exploration_env import RESET_ODOM, VecExplorationEnv
 
 
+class GcnPolicy(ctypes.Structure):
+    """``struct dge_gcn_policy`` (include/dge.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("W1", "b1", "W2t_hi", "W2t_lo", "b2", "head_w", "head_b_dev", "ws", "q", "choice")] + \
+               [("node_cap", ctypes.c_int64), ("Cin", ctypes.c_int32), ("C", ctypes.c_int32)]
+
+
+class DeviceTick:
+    """Arguments of ``dge_policy_tick`` for one (env, Networks.GCN) pair, prepared once; re-derived when a parameter changes."""
+
+    def __init__(self, env: VecExplorationEnv, model, seed_stride: int, graph: bool = True, overlap: bool = True, node_cap: int | None = None):
+        from . import gnn
+        self.env, self.model = env, model
+        self.dev = env.device
+        L = env.eng._L
+        L.dge_policy_tick.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        self._L = L
+        self.cin, self.C = (int(v) for v in model.conv1.weight.shape)
+        g = env.graph
+        self.node_cap = int(min(g.node_cap, node_cap or g.node_cap))
+        self.ws = torch.empty(3 * self.node_cap * self.C, dtype=torch.float32, device=self.dev)
+        self.q = torch.zeros(self.node_cap, dtype=torch.float32, device=self.dev)
+        self.choice = torch.zeros(env.B, dtype=torch.int32, device=self.dev)
+        self.flags = (1 if graph else 0) | (0 if overlap else 2)
+        self.seed_stride = int(seed_stride)
+        self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
+        self._sig = self._pol = self._keep = None
+        self._gnn = gnn
+
+    def _policy(self):
+        m = self.model
+        params = (m.conv1.weight, m.conv1.bias, m.conv2.weight, m.conv2.bias, m.fully_con1.weight, m.fully_con1.bias)
+        sig = tuple((t.data_ptr(), t._version) if t is not None else None for t in params)
+        if sig != self._sig:
+            w1, b1, w2, b2, hw, hb = params
+            margs, self._keep = self._gnn._q_forward_model_args(w1, b1, w2, b2, hw[0], hb)
+            ptr = lambda a: None if a is None else a.value
+            self._pol = GcnPolicy(*(ptr(a) for a in margs), self.ws.data_ptr(), self.q.data_ptr(), self.choice.data_ptr(), self.node_cap, self.cin, self.C)
+            self._sig = sig
+        return self._pol
+
+    def __call__(self):
+        env = self.env
+        pol = self._policy()
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        _check(self._L.dge_policy_tick(env.eng._h, ctypes.byref(env.graph.c), ctypes.byref(pol), self.seed_stride, self._fo, 4, self.flags, st), "dge_policy_tick")
+
+
 class PolicyLoop:
-    def __init__(self, env: VecExplorationEnv, model: torch.nn.Module, overlap: bool = True, seed_stride: int | None = None):
+    def __init__(self, env: VecExplorationEnv, model: torch.nn.Module, overlap: bool = True, seed_stride: int | None = None,
+                 device_tick: bool | None = None, cuda_graph: bool = True):
+        """``device_tick``: None = use ``dge_policy_tick`` whenever the model is the DQN Q-network (Networks.GCN on the tcgen05
+        GEMM), False = the per-launch route with one size sync per tick (A/B, and the only route for other model families)."""
+        from . import Networks, gnn
         self.env, self.model, self.overlap = env, model, overlap
         self.dev = env.device
         self.seed_stride = int(seed_stride or env.B)
@@ -35,15 +89,56 @@ class PolicyLoop:
         self.ev_need = torch.cuda.Event()
         self.ev_move = torch.cuda.Event()
         self.ev_step = torch.cuda.Event()
-        self.launches = 0          # kernels of this package launched so far (libdge.so + gnn kernels; cuBLAS GEMMs not counted)
-        self.graphs = 0            # graphs scored so far
-        self.stage_events = None   # optional {"slam": [], "vmap": []} of (start, end) CUDA events on the step stream
+        self._launches = 0         # kernels of this package launched by the per-launch route (libdge.so + gnn kernels)
+        self._graphs = 0
+        self.ticks = 0
+        self.stage_events = None   # optional {"slam": [], "vmap": []} of (start, end) CUDA events on the step stream (per-launch route only)
+        eligible = gnn.QForwardPlan.eligible(model) and Networks._PRECISION == "tc3"
+        if device_tick and not eligible:
+            raise ValueError("PolicyLoop(device_tick=True) needs a Networks.GCN Q-network on the GPU with matmul precision 'tc3'")
+        self.device = DeviceTick(env, model, self.seed_stride, graph=cuda_graph, overlap=overlap) if (eligible and device_tick is not False) else None
+        self._c0 = None
         # Networks.GCN at inference: the Q forward's argument list is prepared once (gnn.QForwardPlan) -- every pointer of the call
         # is constant between ticks; other models (and other precision modes) go through model(g.data(), 0.0)
         self._plan = _make_plan(model, env.graph)
 
+    # kernels per device tick: mark_pending, reset, move_measure, slam, vmap, graph count/scan/fill, conv_small, gemm, aggregate, select_plan
+    DEVICE_TICK_LAUNCHES = 12
+
+    @property
+    def launches(self):
+        return self._launches + (self.DEVICE_TICK_LAUNCHES * self.ticks if self.device is not None else 0)
+
+    @launches.setter
+    def launches(self, v):
+        self._launches = int(v)
+        if self.device is not None:
+            self.ticks = 0
+
+    @property
+    def graphs(self):
+        """graphs scored so far (device route: the engine's work counter, read back on demand -- a host sync)"""
+        if self.device is None:
+            return self._graphs
+        c = int(self.env.eng.state["counters"][4].item())
+        return c - (self._c0 or 0)
+
+    @graphs.setter
+    def graphs(self, v):
+        self._graphs = int(v)
+        if self.device is not None:
+            self._c0 = int(self.env.eng.state["counters"][4].item()) - int(v)
+
     @torch.no_grad()
     def tick(self):
+        if self.device is not None and self.stage_events is None:
+            self.device()
+            self.ticks += 1
+            return None
+        return self._tick_launches()
+
+    @torch.no_grad()
+    def _tick_launches(self):
         from . import Networks, gnn
         env, eng = self.env, self.env.eng
         L, h, st = eng._L, eng._h, eng.state
@@ -74,9 +169,9 @@ class PolicyLoop:
             self.stage_events["slam"].append((e0, e1)); self.stage_events["vmap"].append((e1, e2))
         if self.overlap:
             self.ev_step.record(s1)
-        self.launches += 6
+        self._launches += 6
         # ---- policy pipeline -----------------------------------------------------------------------------
-        g = env.build_graph(need); self.launches += 4
+        g = env.build_graph(need); self._launches += 4
         ng, nn, _ = g.sync_sizes()                   # the tick's only host sync (main stream only)
         if ng > 0:
             l0 = gnn.launch_count
@@ -88,8 +183,9 @@ class PolicyLoop:
             if self.overlap:
                 main.wait_event(self.ev_move)        # plans are rewritten only after this tick's move kernel has read them
             env.select_and_plan(q)                   # the envs of this graph batch
-            self.launches += gnn.launch_count - l0 + 1
-            self.graphs += ng
+            self._launches += gnn.launch_count - l0 + 1
+            if self.device is None:
+                self._graphs += ng
         if self.overlap:
             main.wait_event(self.ev_step)            # join: the tick ends when both pipelines are done
         return ng

@@ -178,9 +178,10 @@ typedef struct dge_state_view {
   const double *plan;            /* [B,6] queued line plan (see dge_line_plan)        */
   const int32_t *plan_cursor;    /* [B] next action of the plan                       */
   const int64_t *slam_clocks;    /* [B,12] SM clock at the 7 phase boundaries of the last SLAM launch, [.,7] = T, [.,8..9] = cycles in the pose / border recurrences */
-  const int64_t *counters;       /* [4] work counters: env-steps, sum of trajectory lengths, sum of
+  const int64_t *counters;       /* [8] work counters: env-steps, sum of trajectory lengths, sum of
                                     measurement counts over those steps, episodes restarted
-                                    by dge_reset_done_queued                                 */
+                                    by dge_reset_done_queued, graphs built by dge_graph, their
+                                    nodes, their edges, graph batches                          */
   const int32_t *forced;         /* [B] forced steps still queued by dge_reset_queued (bit 30 = initial optimize pending) */
   const int64_t *seed;           /* [B] Philox key of the env's current episode                                         */
   const uint8_t *pending;        /* [B] written by dge_mark_pending                                                     */
@@ -277,6 +278,33 @@ int dge_line_plan_host(dge_handle h, const double *goal_host, const uint8_t *mas
  * action queue.  q_dev [N_tot] f32 in the node order of `g`.                         */
 int dge_select_and_plan(dge_handle h, const dge_graph_out *g, const float *q_dev, const uint8_t *mask_dev,
                         int32_t *choice_dev /* [B] nullable: chosen frontier index */, void *stream);
+
+/* ---- one tick of the acting loop on the device: the body of the reference's test loop for B envs at once (test.py:100-143:
+ * graph_matrix -> data_process -> model(data, 0) -> np.argmax over the last fro_size nodes -> actions_all_goals -> env.step per
+ * action, exploration_env.py:98-105; an episode that ends is re-created like exploration_env.py:389-422).  Per call: every env
+ * whose action list ran empty gets its graph built, scored by the GCN Q-network (Networks.GCN, Networks.py:12-28, prob = 0) and
+ * a new line plan queued; every env with a queued action executes it (one simulator step); finished episodes restart
+ * (dge_reset_done_queued).  No host synchronisation: the size of the decision batch stays on the device (launches are sized by
+ * capacity).  `pol` = the network's parameters in the form dge_gcn_q_forward takes them (dge_gnn.h) + workspace:
+ *   ws >= 3 * node_cap * C floats (16-byte aligned), q [node_cap] Q-values of the batch's nodes, choice [B] nullable.
+ * flags: DGE_TICK_GRAPH       the launch sequence is captured into a CUDA graph at the first call (again whenever an argument
+ *                             changes) and replayed with one cudaGraphLaunch on `stream`;
+ *        DGE_TICK_ONE_STREAM  step and policy pipelines on `stream` one after the other (default: the step pipeline runs on an
+ *                             engine-owned second stream, forked and joined with events -- inside the captured graph too).   */
+typedef struct dge_gcn_policy {
+  const float *W1, *b1;             /* conv1: [Cin,C], [C] nullable                          */
+  const float *W2t_hi, *W2t_lo;     /* conv2 weight as dge_gemm_prep_weight leaves it [C,C]  */
+  const float *b2;                  /* [C] nullable                                          */
+  const float *head_w, *head_b_dev; /* Linear(C,1): [C], [1] nullable                        */
+  float *ws, *q;
+  int32_t *choice;
+  int64_t node_cap;
+  int32_t Cin, C;
+} dge_gcn_policy;
+#define DGE_TICK_GRAPH 1
+#define DGE_TICK_ONE_STREAM 2
+int dge_policy_tick(dge_handle h, const dge_graph_out *g, const dge_gcn_policy *pol, uint64_t seed_stride,
+                    const double *forced_odom_host, int n_forced, int flags, void *stream);
 
 /* ---- look-ahead roll-out rewards: replaces EMPlanner2D.simulations_reward
  * (Planner2D.cpp:1416-1468, `planner2d` binding Planner2D.cpp:90) and
