@@ -265,21 +265,18 @@ __global__ void __launch_bounds__(256) k_vmap_metrics(dge_config cfg, DgeDims d,
 //
 // The cell-centric kernel above tests every (pose, cell) pair of a tile for proximity (1 visit per ~100 tests at
 // BASELINE config C4).  Here the work is driven by the poses: a pose can only touch the W x W block of cells around
-// it (W = 2 ceil(max_range / res) + 1 = 7), so
-//   * the cell state (2x2 information, visibility count, flags) of the WHOLE map lives in shared memory
-//     (28 bytes per cell: 25 KB at 20x20 .. 137 KB at 100x100);
-//   * the map is cut into horizontal bands of HB = 32 / W rows, one warp per band.  A warp walks the trajectory in
-//     order (ballot over 32 poses -> the ones whose block reaches its band), and for each such pose its lanes ARE the
-//     W x HB cells of the block inside the band: lane = (row of the band, column offset), no search, ~50 % of the lanes
-//     inside the sensor disc instead of ~4 %;
-//   * bands own disjoint cells, so the order-dependent fold needs no synchronisation between warps; inside a warp
-//     consecutive poses are separated by __syncwarp (a cell changes lanes when the block slides);
-//   * the state-independent part of VU consecutive poses (geometry, predicted covariance, its inverse, rotation) is
-//     evaluated together before the ordered fold, as in the cell-centric kernel.
+// it (W = 2 ceil(max_range / res) + 1 = 7), and a visit is split in two:
+//   * PREDICT (order-independent, ~3/4 of the arithmetic): for every (pose, cell of its block) pair the gates and the
+//     predicted information Lambda_new = (Hl^-1 (R + Hx Sigma Hx^T) Hl^-T)^-1 (VirtualMap.cpp:213-229) -- one thread per
+//     pair, every warp of the CTA busy, KC poses (a chunk) at a time into a shared-memory record buffer;
+//   * FOLD (order-dependent, VirtualMap.cpp:307-313 / 364-377): one thread per cell of the chunk's bounding box walks the
+//     chunk's poses in trajectory order and folds the records that hit its cell into the cell state (2x2 information,
+//     visibility count, flags), which lives in shared memory for the whole map (28 bytes per cell).
+// The record buffer is double-buffered: the prediction of chunk i+1 is issued in front of the fold of chunk i (one barrier per
+// chunk), so the latency-bound fold chains of a few warps run beside the throughput-bound prediction of all of them.
 // HBM traffic is the algorithmic minimum: the trajectory is read once (digest written and re-read through L1/L2),
 // every output byte is written once.  Arithmetic, predicates and summation orders are those of the kernels above
-// (same parity tests).
-constexpr int ENV_MAX_WARPS = 32;
+// (bit-identical results, same parity tests).
 
 // reciprocal for the fused kernel: hardware seed (rcp.approx.ftz.f64, ~2^-23) + two Newton steps = full double accuracy
 // up to ~2 ulp, half the dependent latency of the IEEE division sequence (operands here are O(1e-3..1e15): no
@@ -292,11 +289,12 @@ __device__ __forceinline__ double vm_rcp(double x) {
   return r;
 }
 constexpr unsigned ST_UPD = 1u << 30, ST_LM = 1u << 31, ST_CNT = ST_UPD - 1;
+constexpr int ENV_THREADS = 256;
 
 struct EnvArgs {
   VmapCfg c;
-  int Tstride, Tfixed, Lstride, Lfixed, hw, W, hb;     // hw = ceil(max_range / res), W = 2 hw + 1, hb = rows per band
-  int bg;                                              // bands per CTA: gridDim.y CTAs share an env (0 / gridDim.y == 1: the whole map)
+  int Tstride, Tfixed, Lstride, Lfixed, hw, W;         // hw = ceil(max_range / res), W = 2 hw + 1
+  int kc;                                              // poses per chunk
   const int32_t *n_poses;
   const double *pose, *cov, *info;                     // [n,Tstride,3], [n,Tstride,6], nullable [n,Tstride,6]
   double *prep;                                        // [n,Tstride,PREP_W] scratch (L1/L2 resident)
@@ -310,39 +308,34 @@ struct EnvArgs {
   long long *clocks;                                   // nullable [n,4]: SM clock at start / after digest / after fold / end (thread 0)
 };
 
-template <int MAXT, int MINB>   // block-size ceiling and CTAs/SM (register budget)
-__global__ void __launch_bounds__(MAXT, MINB) k_vmap_env(EnvArgs a) {
+template <int WT>   // WT = block width W when known at compile time (7 for the reference's sensor / resolution), 0 = generic
+__global__ void __launch_bounds__(ENV_THREADS, 2) k_vmap_env(EnvArgs a) {
   const int b = blockIdx.x;
   if (a.mask && !a.mask[b]) return;
   const VmapCfg &c = a.c;
   const int T = a.n_poses ? a.n_poses[b] : a.Tfixed;
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  // band group of this CTA: rows [row_lo, row_hi) of the map (the whole map when the env is not split).  The shared-memory
-  // arrays hold those rows only and are addressed with GLOBAL cell indices through pointers shifted by cbase.
-  const bool split = gridDim.y > 1;
-  const int band0 = split ? blockIdx.y * a.bg : 0;
-  const int row_lo = split ? min(c.rows, band0 * a.hb) : 0, row_hi = split ? min(c.rows, (band0 + a.bg) * a.hb) : c.rows;
-  const int cbase = row_lo * c.cols, V = (row_hi - row_lo) * c.cols;            // V = cells of this CTA
-  const int Vmax = split ? a.bg * a.hb * c.cols : c.rows * c.cols;              // array pitch (same for every group)
+  const int tid = threadIdx.x, nthr = ENV_THREADS;
+  const int V = c.rows * c.cols, W = WT ? WT : a.W, WW = W * W, KC = a.kc, hw = a.hw;
   extern __shared__ __align__(16) unsigned char vm_smem[];
-  double *sxx0 = reinterpret_cast<double *>(vm_smem), *sxy0 = sxx0 + Vmax, *syy0 = sxy0 + Vmax;
-  unsigned *sst0 = reinterpret_cast<unsigned *>(syy0 + Vmax);       // count | ST_UPD | ST_LM
-  int *s_frow = reinterpret_cast<int *>(sst0 + ((Vmax + 1) & ~1));  // [T] cell row of every pose
-  double *sxx = sxx0 - cbase, *sxy = sxy0 - cbase, *syy = syy0 - cbase;
-  unsigned *sst = sst0 - cbase;
-  double *s_red = reinterpret_cast<double *>(s_frow + ((a.Tstride + 1) & ~1));   // [256] + 2 x int[256]
+  double *sxx = reinterpret_cast<double *>(vm_smem), *sxy = sxx + V, *syy = sxy + V;
+  unsigned *sst = reinterpret_cast<unsigned *>(syy + V);       // count | ST_UPD | ST_LM
+  unsigned *smk = sst + ((V + 1) & ~1);                        // per cell: which poses of the chunk update it (bit kk; low / high half = buffer 0 / 1)
+  int *s_fr = reinterpret_cast<int *>(smk + ((V + 1) & ~1));   // [Tstride] first row of every pose's block
+  int *s_fc = s_fr + ((a.Tstride + 1) & ~1);                   // [Tstride] first column
+  double *s_red = reinterpret_cast<double *>(s_fc + ((a.Tstride + 1) & ~1));   // [256] + 2 x int[256]
+  double *rec0 = s_red + 256 + 256;                            // 2 x { nxx, nxy, nyy, ndet [KC*WW] }
+  const int RS = KC * WW;                                      // records per buffer
+  int4 *s_box = reinterpret_cast<int4 *>((reinterpret_cast<uintptr_t>(rec0 + 8 * RS) + 15) & ~uintptr_t(15));   // [ceil(Tstride / KC)] cell box [r0, r1) x [c0, c1) of every chunk
 
-  if (a.clocks && !split && tid == 0) a.clocks[4 * b] = clock64();
+  if (a.clocks && tid == 0) a.clocks[4 * b] = clock64();
   // ---- init cell state, digest the trajectory -------------------------------------------------------------
-  for (int i = tid; i < V; i += nthr) { sxx0[i] = c.i0; sxy0[i] = 0.0; syy0[i] = c.i0; sst0[i] = 0u; }
+  for (int i = tid; i < V; i += nthr) { sxx[i] = c.i0; sxy[i] = 0.0; syy[i] = c.i0; sst[i] = 0u; smk[i] = 0u; }
   const double *ps = a.pose + (size_t)b * a.Tstride * 3, *cv = a.cov + (size_t)b * a.Tstride * 6;
   double *pr = a.prep + (size_t)b * a.Tstride * PREP_W;
   for (int k = tid; k < T; k += nthr) {
     const double px = ps[3 * k], py = ps[3 * k + 1];
-    const int frow = (int)floor((py - c.map_min_y) / c.res);
-    s_frow[k] = frow;
-    // a split env: every CTA digests the poses that reach its rows (CTAs of an env write identical values to the scratch)
-    if (split && !(frow + a.hw >= row_lo && frow - a.hw < row_hi)) continue;
+    s_fr[k] = (int)floor((py - c.map_min_y) / c.res) - hw;
+    s_fc[k] = (int)floor((px - c.map_min_x) / c.res) - hw;     // (defines the candidate block only)
     double s, co;
     sincos(ps[3 * k + 2], &s, &co);
     double *o = pr + (size_t)k * PREP_W;
@@ -361,56 +354,58 @@ __global__ void __launch_bounds__(MAXT, MINB) k_vmap_env(EnvArgs a) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) o[4 + i] = S[i];
     o[10] = (det_info < 1e-10) ? 0.0 : 1.0;   // VirtualMap.cpp:293
-    o[11] = floor((px - c.map_min_x) / c.res);  // cell column of the pose (defines the candidate block only)
+    o[11] = 0.0;
   }
   __syncthreads();
+  const int nch = (T + KC - 1) / KC;
+  for (int ch = tid; ch < nch; ch += nthr) {                 // bounding box of the cells a chunk's poses can touch
+    int r0 = 0x3fffffff, r1 = -0x3fffffff, c0 = 0x3fffffff, c1 = -0x3fffffff;
+    for (int k = ch * KC; k < min(T, (ch + 1) * KC); ++k) {
+      const int fr = s_fr[k], fc = s_fc[k];
+      r0 = min(r0, fr); r1 = max(r1, fr); c0 = min(c0, fc); c1 = max(c1, fc);
+    }
+    s_box[ch] = make_int4(max(r0, 0), min(r1 + W, c.rows), max(c0, 0), min(c1 + W, c.cols));
+  }
   // landmark cells (OccupancyMap.cpp:126-131)
   {
     const double *l = a.lm + (size_t)b * a.Lstride * 2;
     for (int j = tid; j < a.Lfixed; j += nthr) {
       if (a.lm_obs && !a.lm_obs[(size_t)b * a.Lstride + j]) continue;
       const int lr = (int)floor((l[2 * j + 1] - c.map_min_y) / c.res), lc = (int)floor((l[2 * j] - c.map_min_x) / c.res);
-      if (lr >= row_lo && lr < row_hi && lc >= 0 && lc < c.cols) atomicOr(&sst[lr * c.cols + lc], ST_LM);
+      if (lr >= 0 && lr < c.rows && lc >= 0 && lc < c.cols) atomicOr(&sst[lr * c.cols + lc], ST_LM);
     }
+  }
+  // this thread's (pose of the chunk, cell of its block) pairs are the same in every chunk: pair p = tid + r * nthr
+  constexpr int MAXR = 3;
+  int pk[MAXR], pdr[MAXR], pdc[MAXR];
+#pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    const int p = tid + r * nthr;
+    pk[r] = p / WW;
+    const int j = p - pk[r] * WW;
+    pdr[r] = j / W; pdc[r] = j - pdr[r] * W;
   }
   // (the clock reads hang on the barrier's result: BAR.SYNC defers blocking, a bare clock read would run ahead of it)
   const int nb1 = __syncthreads_count(1);
-  if (a.clocks && !split && tid == 0 && nb1) a.clocks[4 * b + 1] = clock64();
-  // ---- ordered fold: warp = band of hb rows, lane = (row in band, column offset in the pose's block) ---------
-  const int r0 = (band0 + warp) * a.hb, r1 = min(row_hi, r0 + a.hb);
-  if (r0 < row_hi) {
-    const int dr = lane / a.W, dc = lane - dr * a.W;
-    const int row = r0 + dr;
-    const bool lane_on = dr < (r1 - r0);
-    const double cy = c.map_min_y + c.res * (row + 0.5);
-    const int rowbase = row * c.cols;
-    // stream of the poses that reach this band, in trajectory order (warp-uniform): ballot over 32 poses at a time
-    int k0 = -32;
-    unsigned m = 0u;
-    auto next_pose = [&]() -> int {
-      while (m == 0u) {
-        k0 += 32;
-        if (k0 >= T) return -1;
-        const int kl = k0 + lane;
-        const int fr = (kl < T) ? s_frow[kl] : -0x3fffffff;
-        m = __ballot_sync(0xffffffffu, fr + a.hw >= r0 && fr - a.hw < r1);
-      }
-      const int k = k0 + __ffs(m) - 1;
-      m &= m - 1;
-      return k;
-    };
-    // state-independent part of one visit: geometry, gates, predicted information in the map frame
-    struct Visit { double nxx, nxy, nyy, ndet; int idx; bool vis, upd; };
-    auto predict = [&](int k) -> Visit {
-      Visit v;
-      const double *p = pr + (size_t)k * PREP_W;
-      const double2 p01 = *reinterpret_cast<const double2 *>(p), p23 = *reinterpret_cast<const double2 *>(p + 2);
-      const double2 p45 = *reinterpret_cast<const double2 *>(p + 4), p67 = *reinterpret_cast<const double2 *>(p + 6);
-      const double2 p89 = *reinterpret_cast<const double2 *>(p + 8), pab = *reinterpret_cast<const double2 *>(p + 10);
-      const int col = (int)pab.y - a.hw + dc;
-      const bool cell_on = lane_on && col >= 0 && col < c.cols;
-      v.idx = rowbase + min(max(col, 0), c.cols - 1);
-      const double cx = c.map_min_x + c.res * (col + 0.5);
+  if (a.clocks && tid == 0 && nb1) a.clocks[4 * b + 1] = clock64();
+
+  // ---- PREDICT: records of chunk ch (poses [ch KC, ch KC + kc)) into buffer ch & 1.  The visibility count is order-independent
+  // (integer, quirk q8): it goes straight into the cell state; which poses UPDATE a cell goes into the cell's chunk mask.
+  auto predict_chunk = [&](int ch) {
+    const int k0 = ch * KC, kc = min(KC, T - k0);
+    double *rxx = rec0 + (ch & 1) * 4 * RS, *rxy = rxx + RS, *ryy = rxy + RS, *rdt = ryy + RS;
+    const int mshift = (ch & 1) * 16;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+      const int p = tid + r * nthr, kk = pk[r];
+      if (kk >= kc) break;
+      const int k = k0 + kk;
+      const int row = s_fr[k] + pdr[r], col = s_fc[k] + pdc[r];
+      const bool cell_on = row >= 0 && row < c.rows && col >= 0 && col < c.cols;
+      const int idx = row * c.cols + col;
+      const double *q = pr + (size_t)k * PREP_W;
+      const double2 p01 = *reinterpret_cast<const double2 *>(q), p23 = *reinterpret_cast<const double2 *>(q + 2);
+      const double cx = c.map_min_x + c.res * (col + 0.5), cy = c.map_min_y + c.res * (row + 0.5);
       const double dx = cx - p01.x, dy = cy - p01.y;
       const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
       bool in_max, out_min;   // range gates on d2, the reference's sqrt comparison inside a 1e-9 band (see k_vmap_cells)
@@ -423,8 +418,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_vmap_env(EnvArgs a) {
       if (c.fov_wide && (qx > 0.0 || fabs(qy) > -qx * c.wedge_tan)) in_fov = true;
       else if (inr) { const double bb = atan2(qy, qx); in_fov = bb < c.max_bearing && bb > c.min_bearing; }
       else in_fov = false;
-      v.vis = inr && in_fov;
-      v.upd = v.vis && out_min && pab.x != 0.0;
+      const bool vis = inr && in_fov;
+      if (!vis) continue;
+      atomicAdd(&sst[idx], 1u);                          // visibility count (q8)
+      if (!(out_min && q[10] != 0.0)) continue;          // full check (q10) ; det(info) gate
+      atomicOr(&smk[idx], 1u << (mshift + kk));
+      const double2 p45 = *reinterpret_cast<const double2 *>(q + 4), p67 = *reinterpret_cast<const double2 *>(q + 6);
+      const double2 p89 = *reinterpret_cast<const double2 *>(q + 8);
       const double Sxx = p45.x, Sxy = p45.y, Sxt = p67.x, Syy = p67.y, Syt = p89.x, Stt = p89.y;
       const double qxx = qx * qx, qyy = qy * qy, qxy = qx * qy;
       const double P00 = qyy * (c.rb + Stt) + Sxx - 2.0 * qy * Sxt;
@@ -434,57 +434,71 @@ __global__ void __launch_bounds__(MAXT, MINB) k_vmap_env(EnvArgs a) {
       const double inv = vm_rcp((P00 * P11 - P01 * P01) * d2 + c.rr * Q);
       const double lb00 = (P11 * d2 + c.rr * qyy) * inv, lb01 = -(P01 * d2 + c.rr * qxy) * inv, lb11 = (P00 * d2 + c.rr * qxx) * inv;
       const double cc = co * co, ss = si * si, cs = co * si;
-      v.nxx = cc * lb00 - 2.0 * cs * lb01 + ss * lb11;
-      v.nxy = cs * (lb00 - lb11) + (cc - ss) * lb01;
-      v.nyy = ss * lb00 + 2.0 * cs * lb01 + cc * lb11;
-      v.ndet = d2 * inv;
-      return v;
-    };
-    // one-ahead software pipeline: the prediction of the next pose (independent of the map state) is issued in the
-    // same straight-line block as the order-dependent fold of the current one, so their fp64 latency chains overlap
-    int kn = next_pose();
-    Visit cur;
-    if (kn >= 0) cur = predict(kn);
-    while (kn >= 0) {
-      kn = next_pose();
-      Visit nxt = cur;
-      if (kn >= 0) nxt = predict(kn);
-      {   // branch-free fold (predicated stores only), so that it shares a basic block with the prediction above
-        const unsigned st = sst[cur.idx];
-        const double ixx = sxx[cur.idx], ixy = sxy[cur.idx], iyy = syy[cur.idx];
+      rxx[p] = cc * lb00 - 2.0 * cs * lb01 + ss * lb11;
+      rxy[p] = cs * (lb00 - lb11) + (cc - ss) * lb01;
+      ryy[p] = ss * lb00 + 2.0 * cs * lb01 + cc * lb11;
+      rdt[p] = d2 * inv;
+    }
+  };
+  // ---- FOLD: the cells of the chunk's bounding box, one thread per cell; a cell folds the poses of its chunk mask in
+  // trajectory order (lowest bit first) -----------------------------------------------------------------------------------
+  auto fold_chunk = [&](int ch) {
+    const int k0 = ch * KC;
+    const double *rxx = rec0 + (ch & 1) * 4 * RS, *rxy = rxx + RS, *ryy = rxy + RS, *rdt = ryy + RS;
+    const int mshift = (ch & 1) * 16;
+    const int4 bx = s_box[ch];
+    const int r0 = bx.x, r1 = bx.y, c0 = bx.z, c1 = bx.w;
+    const int bw = c1 - c0, nbc = (r1 > r0 && bw > 0) ? (r1 - r0) * bw : 0;
+    for (int ci = tid; ci < nbc; ci += nthr) {
+      const int rr_ = ci / bw, row = r0 + rr_, col = c0 + ci - rr_ * bw;
+      const int idx = row * c.cols + col;
+      unsigned m = (smk[idx] >> mshift) & 0xffffu;
+      if (!m) continue;
+      atomicAnd(&smk[idx], ~(0xffffu << mshift));        // (the other half may be set concurrently by the next chunk's prediction)
+      double ixx = sxx[idx], ixy = sxy[idx], iyy = syy[idx];
+      bool first = !(sst[idx] & ST_UPD);                 // the first hit overwrites the prior (VirtualMap.cpp:307-309)
+      while (m) {
+        const int kk = __ffs(m) - 1;
+        m &= m - 1;
+        const int j = kk * WW + (row - s_fr[k0 + kk]) * W + (col - s_fc[k0 + kk]);
+        const double nxx = rxx[j], nxy = rxy[j], nyy = ryy[j], bdet = rdt[j];
         // covariance intersection on information matrices (VirtualMap.cpp:364-377, q11)
-        const double aa = ixx * iyy - ixy * ixy, bdet = cur.ndet;
-        const double cm = iyy * cur.nxx - 2.0 * ixy * cur.nxy + ixx * cur.nyy;
+        const double aa = ixx * iyy - ixy * ixy;
+        const double cm = iyy * nxx - 2.0 * ixy * nxy + ixx * nyy;
         const double d = aa + bdet - cm;
         double w = 0.5 * (2.0 * bdet - cm) * vm_rcp(d);
         w = ((w < 0 && d < 0) || (w > 1 && d > 0)) ? 0.0 : (((w < 0 && d > 0) || (w > 1 && d < 0)) ? 1.0 : w);
-        const bool first = !(st & ST_UPD);            // the first hit overwrites the prior (VirtualMap.cpp:307-309)
-        const double oxx = first ? cur.nxx : w * ixx + (1.0 - w) * cur.nxx;
-        const double oxy = first ? cur.nxy : w * ixy + (1.0 - w) * cur.nxy;
-        const double oyy = first ? cur.nyy : w * iyy + (1.0 - w) * cur.nyy;
-        if (cur.upd) { sxx[cur.idx] = oxx; sxy[cur.idx] = oxy; syy[cur.idx] = oyy; }
-        if (cur.vis) sst[cur.idx] = (st + 1u) | (cur.upd ? ST_UPD : 0u);   // visibility count (q8)
+        ixx = first ? nxx : w * ixx + (1.0 - w) * nxx;
+        ixy = first ? nxy : w * ixy + (1.0 - w) * nxy;
+        iyy = first ? nyy : w * iyy + (1.0 - w) * nyy;
+        first = false;
       }
-      __syncwarp();                                 // the block slides: a cell changes lanes between consecutive poses
-      cur = nxt;
+      sxx[idx] = ixx; sxy[idx] = ixy; syy[idx] = iyy;
+      atomicOr(&sst[idx], ST_UPD);
     }
+  };
+  if (nch > 0) predict_chunk(0);
+  __syncthreads();
+  for (int ch = 0; ch < nch; ++ch) {
+    if (ch + 1 < nch) predict_chunk(ch + 1);    // issued in front of the fold: independent work for the warps that wait on fold chains
+    fold_chunk(ch);
+    __syncthreads();
   }
-  const int nb2 = __syncthreads_count(1);
-  if (a.clocks && !split && tid == 0 && nb2) a.clocks[4 * b + 2] = clock64();
+  if (a.clocks && tid == 0) a.clocks[4 * b + 2] = clock64();
   // ---- write the map: every output byte once, coalesced -------------------------------------------------------
-  const size_t cell0 = (size_t)b * c.rows * c.cols + cbase;
+  const size_t cell0 = (size_t)b * V;
   for (int i = tid; i < V; i += nthr) {
-    const unsigned st = sst0[i];
+    const unsigned st = sst[i];
     const int cnt = (int)(st & ST_CNT);
     a.prob[cell0 + i] = (st & ST_LM) ? c.ptab[5] : c.ptab[min(cnt, 4)];
     if (a.seen) a.seen[cell0 + i] = (st & ST_LM) ? -1 : cnt;
   }
   for (int i = tid; i < 3 * V; i += nthr) {
     const int cell = i / 3, j = i - 3 * cell;
-    a.vinfo[cell0 * 3 + i] = j == 0 ? sxx0[cell] : (j == 1 ? sxy0[cell] : syy0[cell]);
+    a.vinfo[cell0 * 3 + i] = j == 0 ? sxx[cell] : (j == 1 ? sxy[cell] : syy[cell]);
   }
-  if (a.clocks && !split && tid == 0) a.clocks[4 * b + 3] = clock64();
-  if (!a.metrics || split) return;
+  if (a.clocks && tid == 0) a.clocks[4 * b + 3] = clock64();
+  if (!a.metrics) return;
 
   // ---- metrics (k_vmap_metrics, same summation order: 256 strided partial sums, fixed tree) ---------------------
   if (tid == 0 && a.counters && a.step_kind[b]) {
@@ -493,7 +507,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_vmap_env(EnvArgs a) {
     atomicAdd(&a.counters[2], (unsigned long long)a.meas_ptr[(size_t)b * (a.d.Tmax + 1) + T]);
   }
   int *s_e = reinterpret_cast<int *>(s_red + 256), *s_k = s_e + 256;
-  if (tid < 256) {
+  {
     const int extg = 20;
     int n_exp = 0, n_known = 0;
     double tr = 0.0;
@@ -559,55 +573,40 @@ int dge_vmap_nchunk(int T) { return (T + VCH - 1) / VCH; }
 int dge_vmap_prep_width() { return PREP_W; }
 
 namespace {
-// geometry of the fused kernel for a map: false if it does not fit (too many bands / too much shared memory)
-bool env_plan(const dge_config &g, int rows, int cols, int Tstride, int *hw, int *W, int *hb, int *nwarps, size_t *smem) {
+// geometry of the fused kernel for a map: chunk length and shared memory; false if the map does not fit
+size_t env_smem(size_t V, int Tstride, int kc, int W) {
+  const size_t rs = (size_t)kc * W * W;
+  return V * 3 * sizeof(double) + 2 * ((V + 1) & ~(size_t)1) * sizeof(unsigned) + 2 * (size_t)((Tstride + 1) & ~1) * sizeof(int) +
+         256 * (sizeof(double) + 2 * sizeof(int)) + 8 * rs * sizeof(double) + (size_t)((Tstride + kc - 1) / kc) * 16 + 32;
+}
+bool env_plan(const dge_config &g, int rows, int cols, int Tstride, int *hw, int *W, int *kc, size_t *smem) {
   *hw = (int)ceil(g.max_range / g.resolution);
   *W = 2 * *hw + 1;
-  if (*W > 32) return false;
-  *hb = 32 / *W;
-  int nw = (rows + *hb - 1) / *hb;
-  if (nw > ENV_MAX_WARPS) return false;
-  *nwarps = nw < 8 ? 8 : nw;                            // the metrics phase wants 256 threads
+  if (*W > 15) return false;
   const size_t V = (size_t)rows * cols;
-  *smem = V * 3 * sizeof(double) + ((V + 1) & ~(size_t)1) * sizeof(unsigned) + (size_t)((Tstride + 1) & ~1) * sizeof(int) + 256 * (sizeof(double) + 2 * sizeof(int)) + 16;
-  return *smem <= 220 * 1024;
-}
-constexpr int SPLIT_BG = 4;   // bands per CTA of a split env (4 warps)
-int env_launch(EnvArgs &a, const dge_config &g, int n, int rows, int cols, cudaStream_t st, bool allow_split = false) {
-  int nw;
-  size_t smem;
-  a.bg = 0;
-  if (!env_plan(g, rows, cols, a.Tstride, &a.hw, &a.W, &a.hb, &nw, &smem)) return 1;   // caller falls back to the cell-centric kernels
-  // Throughput regime (many more envs than SMs, no per-env metrics wanted): split every env into groups of SPLIT_BG bands, one
-  // 4-warp CTA each.  A band is a serial chain and most bands of a map are idle at any time; with whole-env CTAs their warps hold
-  // registers of an SM without issuing (2 CTAs of 13 warps, ~40 % busy at BASELINE config C4), with band groups 6-7 small CTAs share
-  // an SM, untouched groups retire at once and the busy chains of several envs fill the fp64 pipe.
-  const int nb = (rows + a.hb - 1) / a.hb;
-  if (allow_split && !a.metrics && nb > SPLIT_BG && (long long)n * nb >= 8 * 148) {
-    a.bg = SPLIT_BG;
-    const size_t Vg = (size_t)SPLIT_BG * a.hb * cols;
-    const size_t sm = Vg * 3 * sizeof(double) + ((Vg + 1) & ~(size_t)1) * sizeof(unsigned) + (size_t)((a.Tstride + 1) & ~1) * sizeof(int) + 16;
-    static size_t cfg_split = 0;
-    if (sm > 48 * 1024 && sm > cfg_split) {
-      if (cudaFuncSetAttribute(k_vmap_env<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DGE_ECUDA;
-      cfg_split = sm;
-    }
-    k_vmap_env<128, 6><<<dim3(n, (nb + SPLIT_BG - 1) / SPLIT_BG), SPLIT_BG * 32, sm, st>>>(a);
-    return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
+  // chunk length: (pose, cell) pairs of a chunk fill whole rounds of the CTA's threads (kc W^2 just below a multiple of 256;
+  // 15 / 10 / 5 for W = 7), at most 16 poses (chunk mask), the longest that leaves room for two CTAs per SM
+  int cand[3], nc = 0;
+  for (int r = 3; r >= 1; --r) { const int k = (r * ENV_THREADS) / (*W * *W); if (k >= 1 && k <= 16 && (nc == 0 || cand[nc - 1] != k)) cand[nc++] = k; }
+  if (nc == 0) cand[nc++] = 1;
+  for (int i = 0; i < nc; ++i) {
+    *kc = cand[i]; *smem = env_smem(V, Tstride, cand[i], *W);
+    if (*smem <= 113 * 1024) return true;
   }
-  // one instantiation per band count of the reference's maps (20/40/60/80/100 -> 8/10/13/15/18 warps) so that two
-  // CTAs fit the register file of an SM; larger maps fall to the generic ceilings
-  const int vi = nw <= 8 ? 0 : nw <= 10 ? 1 : nw <= 13 ? 2 : nw <= 15 ? 3 : nw <= 18 ? 4 : nw <= 24 ? 5 : 6;
-  void (*const kerns[7])(EnvArgs) = {k_vmap_env<256, 2>, k_vmap_env<320, 2>, k_vmap_env<416, 2>, k_vmap_env<480, 2>,
-                                     k_vmap_env<576, 2>, k_vmap_env<768, 1>, k_vmap_env<1024, 1>};
-  void (*kern)(EnvArgs) = kerns[vi];
-  static size_t configured[7] = {0, 0, 0, 0, 0, 0, 0};
-  size_t &cf = configured[vi];
+  *kc = cand[nc - 1]; *smem = env_smem(V, Tstride, *kc, *W);
+  return *smem <= 226 * 1024;
+}
+int env_launch(EnvArgs &a, const dge_config &g, int n, int rows, int cols, cudaStream_t st) {
+  size_t smem;
+  if (!env_plan(g, rows, cols, a.Tstride, &a.hw, &a.W, &a.kc, &smem)) return 1;   // caller falls back to the cell-centric kernels
+  void (*kern)(EnvArgs) = a.W == 7 ? k_vmap_env<7> : k_vmap_env<0>;
+  static size_t configured[2] = {0, 0};
+  size_t &cf = configured[a.W == 7 ? 1 : 0];
   if (smem > 48 * 1024 && smem > cf) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DGE_ECUDA;
     cf = smem;
   }
-  kern<<<n, nw * 32, smem, st>>>(a);
+  kern<<<n, ENV_THREADS, smem, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }
 }  // namespace
@@ -653,7 +652,7 @@ int dge_vmap_standalone(const dge_config *cfg, int n, int T, const double *pose,
     a.sim_step = nullptr; a.status = nullptr; a.meas_ptr = nullptr; a.dist = nullptr;
     a.cfg = *cfg; a.d = DgeDims{};
     a.clocks = reinterpret_cast<long long *>(cbox_ws);   // the chunk-box scratch is unused by the fused kernel: phase clocks for dev profiling
-    const int rc = env_launch(a, *cfg, n, rows, cols, st, /*allow_split=*/true);
+    const int rc = env_launch(a, *cfg, n, rows, cols, st);
     if (rc != 1) return rc;
   }
   const int nchm = dge_vmap_nchunk(T);
