@@ -14,8 +14,18 @@
 //     registers) and the O(T n^2) parts (Schur complement, W Sigma W^T) are GEMM-shaped
 //     phases parallel over poses.
 //   * all arithmetic fp64 (prior information 1/sigma^2 ~ 3e7 next to O(1) blocks).
-//   * workspace (D,g,U | Dinv,FU,f | P,u per pose; border rows Bt / FB->W) lives in HBM but is
+//   * workspace (D,g,U | Dinv,FU,f | P,u | q,v per pose; border rows Bt / FB / W) lives in HBM but is
 //     written and re-read by the same CTA within microseconds => L2-resident.
+//   * INCREMENTAL between relinearisations (what ISAM2 is for): as long as no linearisation point moves, the
+//     forward elimination of the closed poses 0..T-2 cannot change when pose T arrives -- the new factors touch the
+//     last two poses only, and a new landmark adds a border column that is zero on every older pose.  The state of the
+//     elimination after the closed poses (chain carries, border carries, partial Schur complement, partial landmark
+//     rhs) is cached per env; a step then closes ONE pose, eliminates the newest one provisionally, inverts the Schur
+//     complement and runs the backward pass + marginals.  A step that relinearises (every relin_skip-th update, if a
+//     delta exceeds the threshold) rebuilds the cache from pose 0.  Border columns are indexed by the landmark's SLOT
+//     (order of first observation since the last rebuild), so that columns never move while the cache lives.
+#include <cstdlib>
+
 #include "dge_internal.cuh"
 
 namespace {
@@ -25,7 +35,7 @@ constexpr int NH = NT / 64;    // row groups per column in the Gauss-Jordan swee
 constexpr int CH = 32;         // poses staged per shared-memory chunk
 constexpr int SW = 39;         // doubles per staged pose: D(6) g(3) U(9) gnext(3) | Dinv(6) FU(9) f(3)
 constexpr int GK = 8;          // poses per staged chunk of border rows in the Schur-complement GEMM
-constexpr int WS_POSE = 48;    // doubles per pose in ws_pose
+constexpr int WS_POSE = DGE_WS_POSE;    // doubles per pose in ws_pose: A-data D(6) g(3) U(9) gnext(3) @0 | B-data Dinv(6) FU(9) f(3) @21 | D-data P(6) u(3) @39 | E-data q(6) v(3) @48
 constexpr int WS_MEAS = 14;    // doubles per measurement in ws_meas: C(3) gl(2) | D contribution(6) g contribution(3)
 
 struct SlamArgs {
@@ -38,8 +48,11 @@ struct SlamArgs {
   const double *meas_b, *meas_r;
   const uint8_t *observed;
   double *lin_l, *est_l, *delta_l, *land_cov;
-  double *ws_pose, *ws_meas, *ws_Bt, *ws_FB;
+  double *ws_pose, *ws_meas, *ws_Bt, *ws_FB, *ws_W;
   int32_t *ws_midx;
+  int32_t *lm_slot, *fc_valid;   // [B,Lt] landmark id -> border slot ; [B] number of poses the cached elimination state was saved at
+  double *fc_state;              // [B, DGE_FC_WIDTH(Lt)] cached state: cD(6) cg(3) pad | cB [N2C][3] | gl [N2C] | S_partial [N2C][N2C]
+  int incremental;               // 0: every step eliminates from pose 0 (A/B switch, DGE_SLAM_INCREMENTAL=0)
   double *metrics;
   long long *clocks;   // [B,12] optional: SM clock at the phase boundaries (thread 0), for in-situ phase timing
 };
@@ -93,9 +106,11 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   double *red = dl + N2C;                         // [NT/32 * 2]
   double *gjb = red + 2 * (NT / 32);              // [258] pivot row / column / reciprocal exchange of the Gauss-Jordan sweep
   double *gbuf = gjb + 258;                       // [2*GK*3*N2C] border-row staging (Schur GEMM) / per-warp W_k (phase E)
-  int *lidx = (int *)(gbuf + 2 * GK * 3 * N2C);   // [Lt]  id -> compact rank (-1 unobserved)
-  int *lid = lidx + Lt;                           // [Lt]  rank -> id
-  __shared__ int s_nl, s_bad;
+  double *openB = gbuf + 2 * GK * 3 * N2C;        // [3*N2C] border rows Bt / FB of the newest (open) pose
+  double *openFB = openB + 3 * N2C;               // [3*N2C]
+  int *lidx = (int *)(openFB + 3 * N2C);          // [Lt]  id -> border slot (-1 unobserved)
+  int *lid = lidx + Lt;                           // [Lt]  slot -> id
+  __shared__ int s_nl, s_nl_old, s_bad;
   __shared__ uint64_t s_bar[CH];   // one mbarrier per pose of the staged chunk: B0 (producer) -> B1 (consumers)
 
   const double wo[3] = {1.0 / (a.cfg.trans_noise * a.cfg.trans_noise), 1.0 / (a.cfg.trans_noise * a.cfg.trans_noise),
@@ -113,7 +128,11 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   double *wsm = a.ws_meas + (size_t)b * a.d.Mmax * WS_MEAS;
   double *wBt = a.ws_Bt + (size_t)b * Tmax * 3 * N2C;
   double *wFB = a.ws_FB + (size_t)b * Tmax * 3 * N2C;
+  double *wW = a.ws_W + (size_t)b * Tmax * 3 * N2C;
   int32_t *wmi = a.ws_midx + (size_t)b * Tmax * Lt;
+  int32_t *slot_g = a.lm_slot + (size_t)b * Lt;
+  double *fc = a.fc_state + (size_t)b * DGE_FC_WIDTH(Lt);     // cD(6) cg(3) | cB | gl | S_partial
+  double *fc_cB = fc + 16, *fc_gl = fc_cB + 3 * N2C, *fc_S = fc_gl + N2C;
 
   // ---------------------------------------------------------------- step 0 ---
   // ISAM2 relinearisation schedule (gtsam ISAM2::update: ++update_count; every
@@ -124,10 +143,12 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     s_bad = 0;
     for (int i = 0; i < CH; ++i) mbar_init(&s_bar[i], 1);
   }
+  int moved = 0;
   if (a.cfg.relin_skip > 0 && uc % a.cfg.relin_skip == 0) {
     for (int k = tid; k < T; k += NT) {
       const double d0 = del[3 * k], d1 = del[3 * k + 1], d2 = del[3 * k + 2];
       if (fmax(fabs(d0), fmax(fabs(d1), fabs(d2))) >= a.cfg.relin_thresh) {
+        moved = 1;
         const Pose3 p = dge_compose(Pose3{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]}, Pose3{d0, d1, d2});
         lin[3 * k] = p.x; lin[3 * k + 1] = p.y; lin[3 * k + 2] = p.th;
         del[3 * k] = 0; del[3 * k + 1] = 0; del[3 * k + 2] = 0;
@@ -136,21 +157,38 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     for (int j = tid; j < Lt; j += NT) {
       if (!obs[j]) continue;
       if (fmax(fabs(dell[2 * j]), fabs(dell[2 * j + 1])) >= a.cfg.relin_thresh) {
+        moved = 1;
         linl[2 * j] += dell[2 * j]; linl[2 * j + 1] += dell[2 * j + 1];
         dell[2 * j] = 0; dell[2 * j + 1] = 0;
       }
     }
   }
-  if (tid == 0) {  // compact landmark ranks in id order (== gtsam Symbol order of the 'l' keys)
+  // the cached elimination state is usable iff nothing was relinearised and it was saved one pose ago
+  const bool valid = !__syncthreads_or(moved) && a.incremental && T >= 2 && a.fc_valid[b] == T - 1;
+  const int k_lo = valid ? T - 2 : 0;          // poses [k_lo, T-1) are closed in this step; pose T-1 stays open
+  const int kz = valid ? T - 1 : 0;            // poses whose factors are linearised in this step
+  if (tid == 0) {  // border slots: a rebuild numbers the observed landmarks in id order, a light step appends the new ones
     int n = 0;
-    for (int j = 0; j < Lt; ++j) { if (obs[j]) { lidx[j] = n; lid[n] = j; ++n; } else lidx[j] = -1; }
+    if (!valid) {
+      for (int j = 0; j < Lt; ++j) { if (obs[j]) { lidx[j] = n; lid[n] = j; slot_g[j] = n; ++n; } else { lidx[j] = -1; slot_g[j] = -1; } }
+    } else {
+      for (int j = 0; j < Lt; ++j) { const int sl = obs[j] ? slot_g[j] : -1; lidx[j] = sl; if (sl >= 0) { lid[sl] = j; n = max(n, sl + 1); } }
+      s_nl_old = n;
+      for (int j = 0; j < Lt; ++j) if (obs[j] && lidx[j] < 0) { lidx[j] = n; lid[n] = j; slot_g[j] = n; ++n; }
+    }
+    if (!valid) s_nl_old = n;
     s_nl = n;
   }
-  // zero the sparse border inputs of this step
-  for (size_t i = tid; i < (size_t)T * 3 * N2C; i += NT) wBt[i] = 0.0;
-  for (size_t i = tid; i < (size_t)T * Lt; i += NT) wmi[i] = 0;
+  // zero the sparse border inputs of this step (and, on a rebuild, the cached state)
+  for (size_t i = (size_t)kz * 3 * N2C + tid; i < (size_t)T * 3 * N2C; i += NT) wBt[i] = 0.0;
+  for (size_t i = (size_t)kz * Lt + tid; i < (size_t)T * Lt; i += NT) wmi[i] = 0;
+  if (!valid) for (int i = tid; i < DGE_FC_WIDTH(Lt); i += NT) fc[i] = 0.0;
   __syncthreads();
   const int nl = s_nl, n2 = 2 * nl;
+  {   // a landmark first seen in a light step opens a border column that is zero on every closed pose (the workspace may hold an older episode's rows)
+    const int c_old = 2 * s_nl_old, nc = n2 - c_old;
+    for (int i = tid; i < nc * 3 * k_lo; i += NT) wFB[(size_t)(i / nc) * N2C + c_old + (i % nc)] = 0.0;
+  }
 
   if (a.clocks && tid == 0) a.clocks[12 * b +0] = clock64();
   // ---------------------------------------------------------------- phase A ---
@@ -159,7 +197,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   //     and landmark-landmark blocks + right-hand sides -> ws_meas / border rows.
   const int M = mptr[T];
   const int32_t *mpose = a.meas_pose + (size_t)b * a.d.Mmax;
-  for (int p = tid; p < M; p += NT) {
+  for (int p = mptr[kz] + tid; p < M; p += NT) {
     const int k = mpose[p];
     const Pose3 pk{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]};
     const int id = mid[p], jr = lidx[id], c0 = 2 * jr;
@@ -188,10 +226,17 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   // A2: one thread per pose: prior (k = 0) and the odometry factor k -> k+1 (its contribution to
   //     pose k+1 is parked in gnext and picked up by the chain); measurement terms summed in factor order.
   __syncthreads();
-  for (int k = tid; k < T; k += NT) {
+  for (int k = k_lo + tid; k < T; k += NT) {
     const Pose3 pk{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]};
     double D[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, U[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gn[3] = {0, 0, 0};
-    if (k == 0) {  // PriorFactor<Pose2>: error = -Local(x, prior), H = I
+    double *w = wsp + (size_t)k * WS_POSE;
+    const bool fresh = k >= kz;   // the pose's own factors (prior / incoming odometry / measurements) are linearised now; else they are in the workspace
+    if (!fresh) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) D[i] = w[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) g[i] = w[6 + i];
+    } else if (k == 0) {  // PriorFactor<Pose2>: error = -Local(x, prior), H = I
       const Pose3 e = dge_between(pk, Pose3{a.prior_pose[3 * b], a.prior_pose[3 * b + 1], a.prior_pose[3 * b + 2]}, nullptr);
       const double wp[3] = {1.0 / (a.cfg.sigma_x0 * a.cfg.sigma_x0), 1.0 / (a.cfg.sigma_y0 * a.cfg.sigma_y0),
                             1.0 / (a.cfg.sigma_theta0 * a.cfg.sigma_theta0)};
@@ -217,14 +262,14 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
         gn[i] = -wo[i] * r[i];
       }
     }
-    for (int p = mptr[k]; p < mptr[k + 1]; ++p) {
-      const double *m = wsm + (size_t)p * WS_MEAS;
+    if (fresh)
+      for (int p = mptr[k]; p < mptr[k + 1]; ++p) {
+        const double *m = wsm + (size_t)p * WS_MEAS;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) D[i] += m[5 + i];
+        for (int i = 0; i < 6; ++i) D[i] += m[5 + i];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) g[i] += m[11 + i];
-    }
-    double *w = wsp + (size_t)k * WS_POSE;
+        for (int i = 0; i < 3; ++i) g[i] += m[11 + i];
+      }
 #pragma unroll
     for (int i = 0; i < 6; ++i) w[i] = D[i];
 #pragma unroll
@@ -248,9 +293,22 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     const int c = ccol, jr = c >> 1, comp = c & 1;
     double cD[6] = {0, 0, 0, 0, 0, 0}, cg[3] = {0, 0, 0}, gp[3] = {0, 0, 0};        // warp-0 carried state
     double cB[3] = {0, 0, 0}, sd0 = 0, sd1 = 0, glc = 0;                             // column state
-    for (int k0 = 0; k0 < T; k0 += CH) {
+    if (valid) {   // resume behind the closed poses: chain carries, the rhs the last closed pose parked for its successor, border carries
+      if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cD[i] = fc[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { cg[i] = fc[6 + i]; gp[i] = k_lo > 0 ? wsp[(size_t)(k_lo - 1) * WS_POSE + 18 + i] : 0.0; }
+      }
+      if (colv) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cB[i] = fc_cB[3 * c + i];
+        glc = fc_gl[c];
+      }
+    }
+    for (int k0 = k_lo; k0 < T; k0 += CH) {
       const int kc = min(CH, T - k0);
-      const uint32_t par = (k0 / CH) & 1;   // every pose barrier completes one phase per chunk
+      const uint32_t par = ((k0 - k_lo) / CH) & 1;   // every pose barrier completes one phase per chunk
       __syncthreads();
       for (int i = tid; i < kc * 21; i += NT) stage[(i / 21) * SW + (i % 21)] = wsp[(size_t)(k0 + i / 21) * WS_POSE + (i % 21)];
       __syncthreads();
@@ -260,6 +318,12 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
         const long long tb0 = (a.clocks && tid == 0) ? clock64() : 0;
         for (int kk = 0; kk < kc; ++kk) {
           double *w = stage + kk * SW;
+          if (k0 + kk == T - 1 && lane == 0) {   // the closed poses end here: this is the state the next step resumes from
+#pragma unroll
+            for (int i = 0; i < 6; ++i) fc[i] = cD[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) fc[6 + i] = cg[i];
+          }
           const double d0 = w[0] + cD[0], d1 = w[1] + cD[1], d2 = w[2] + cD[2], d3 = w[3] + cD[3], d4 = w[4] + cD[4], d5 = w[5] + cD[5];
           const double g0 = w[6] + cg[0] + gp[0], g1 = w[7] + cg[1] + gp[1], g2 = w[8] + cg[2] + gp[2];
           gp[0] = w[18]; gp[1] = w[19]; gp[2] = w[20];
@@ -288,13 +352,13 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
             mbar_arrive(&s_bar[kk]);
           }
         }
-        if (a.clocks && tid == 0) a.clocks[12 * b + 8] = (k0 ? a.clocks[12 * b + 8] : 0) + (clock64() - tb0);   // cycles inside the pose recurrence
+        if (a.clocks && tid == 0) a.clocks[12 * b + 8] = (k0 > k_lo ? a.clocks[12 * b + 8] : 0) + (clock64() - tb0);   // cycles inside the pose recurrence
       } else {
         if (colv) {
-          if (k0 == 0) {
-            // landmark-landmark diagonal block and rhs of this column: a gather over the column's factors, in pose
-            // order; independent loads (8 poses in flight), hidden behind the first poses of the chain
-            for (int k = 0; k < T; k += 8) {
+          if (k0 == k_lo) {
+            // landmark-landmark diagonal block and rhs of this column: a gather over the column's factors linearised in this
+            // step, in pose order; independent loads (8 poses in flight), hidden behind the first poses of the chain
+            for (int k = kz; k < T; k += 8) {
               int p1[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) p1[u] = (k + u < T) ? wmi[(size_t)(k + u) * Lt + jr] : 0;
@@ -323,6 +387,11 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
               const int kk = kb + u;
               if (kk < kc) {
                 const int k = k0 + kk;
+                const bool open = k == T - 1;
+                if (open) {   // state behind the closed poses (see B0)
+                  fc_cB[3 * c] = cB[0]; fc_cB[3 * c + 1] = cB[1]; fc_cB[3 * c + 2] = cB[2];
+                  fc_gl[c] = glc;
+                }
                 const double b0 = nb[u][0] + cB[0], b1 = nb[u][1] + cB[1], b2 = nb[u][2] + cB[2];
                 if (kk + 4 < kc) {
 #pragma unroll
@@ -335,25 +404,30 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
                 glc -= b0 * w[36] + b1 * w[37] + b2 * w[38];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) cB[i] = -(w[9 + i] * fb0 + w[12 + i] * fb1 + w[15 + i] * fb2);
-                wBt[((size_t)k * 3 + 0) * N2C + c] = b0; wBt[((size_t)k * 3 + 1) * N2C + c] = b1; wBt[((size_t)k * 3 + 2) * N2C + c] = b2;
+                if (!open) {   // the open pose keeps its raw border row: it is eliminated again, with the same carry, when the next pose closes it
+                  wBt[((size_t)k * 3 + 0) * N2C + c] = b0; wBt[((size_t)k * 3 + 1) * N2C + c] = b1; wBt[((size_t)k * 3 + 2) * N2C + c] = b2;
+                } else {
+                  openB[c] = b0; openB[N2C + c] = b1; openB[2 * N2C + c] = b2;
+                  openFB[c] = fb0; openFB[N2C + c] = fb1; openFB[2 * N2C + c] = fb2;
+                }
                 wFB[((size_t)k * 3 + 0) * N2C + c] = fb0; wFB[((size_t)k * 3 + 1) * N2C + c] = fb1; wFB[((size_t)k * 3 + 2) * N2C + c] = fb2;
               }
             }
           }
-          if (a.clocks && tid == NT - 1) a.clocks[12 * b + 9] = (k0 ? a.clocks[12 * b + 9] : 0) + (clock64() - tb1);   // cycles of border column 0 in its recurrence
+          if (a.clocks && tid == NT - 1) a.clocks[12 * b + 9] = (k0 > k_lo ? a.clocks[12 * b + 9] : 0) + (clock64() - tb1);   // cycles of border column 0 in its recurrence
         }
         // copy the chunk's Dinv | FU | f to the workspace (needed again by the backward pass)
         while (!mbar_try_wait(&s_bar[kc - 1], par)) { }
         for (int i = tid - 32; i < kc * 18; i += NT - 32) wsp[(size_t)(k0 + i / 18) * WS_POSE + 21 + (i % 18)] = stage[(i / 18) * SW + 21 + (i % 18)];
       }
     }
-    // seed S with the landmark-landmark blocks (block diagonal), gl with the reduced rhs
+    // S = cached partial Schur complement (zero on a rebuild) + the landmark-landmark blocks gathered above; gl = reduced rhs
     __syncthreads();
-    for (int i = tid; i < n2 * n2; i += NT) S[i] = 0.0;
+    for (int i = tid; i < n2 * n2; i += NT) { const int r = i / n2; S[i] = fc_S[r * N2C + (i - r * n2)]; }
     __syncthreads();
     if (colv) {
-      S[(2 * jr) * n2 + c] = sd0;
-      S[(2 * jr + 1) * n2 + c] = sd1;
+      S[(2 * jr) * n2 + c] += sd0;
+      S[(2 * jr + 1) * n2 + c] += sd1;
       gl[c] = glc;
     }
   }
@@ -364,6 +438,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   // Schur complement S -= sum_k Bt_k^T FB_k : an n2 x 3T x n2 GEMM.  Border rows are staged through shared
   // memory GK poses at a time (one linear, coalesced copy per operand); every thread keeps up to two 4x4
   // tiles of the upper triangle in registers across all chunks; the result is mirrored.
+  const int Tc = T - 1;                         // closed poses [k_lo, Tc) enter the cached partial sum; the open pose is added after the save
   if (n2 > 0) {
     const int nt = (n2 + 3) / 4;
     const int ntile = nt * (nt + 1) / 2;
@@ -382,14 +457,17 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
       double *gA = gbuf, *gB = gbuf + GK * 3 * N2C;
       constexpr int PF = 6;                                     // 2 operands x GK*3*N2C / NT <= 2 * PF  (N2C <= 64)
       double pa[PF], pb[PF];
-      const int rows0 = min(GK, T) * 3;
+      const int rows0 = min(GK, Tc - k_lo) * 3;
+      {
+        const size_t base0 = (size_t)k_lo * 3 * N2C;
 #pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        const int i = tid + u * NT;
-        pa[u] = (i < rows0 * N2C) ? wBt[i] : 0.0; pb[u] = (i < rows0 * N2C) ? wFB[i] : 0.0;
+        for (int u = 0; u < PF; ++u) {
+          const int i = tid + u * NT;
+          pa[u] = (i < rows0 * N2C) ? wBt[base0 + i] : 0.0; pb[u] = (i < rows0 * N2C) ? wFB[base0 + i] : 0.0;
+        }
       }
-      for (int k0 = 0; k0 < T; k0 += GK) {
-        const int rows = min(GK, T - k0) * 3;
+      for (int k0 = k_lo; k0 < Tc; k0 += GK) {
+        const int rows = min(GK, Tc - k0) * 3;
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
@@ -397,8 +475,8 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
           if (i < rows * N2C) { gA[i] = pa[u]; gB[i] = pb[u]; }
         }
         __syncthreads();
-        if (k0 + GK < T) {
-          const int rown = min(GK, T - k0 - GK) * 3;
+        if (k0 + GK < Tc) {
+          const int rown = min(GK, Tc - k0 - GK) * 3;
           const size_t base = (size_t)(k0 + GK) * 3 * N2C;
 #pragma unroll
           for (int u = 0; u < PF; ++u) {
@@ -452,8 +530,8 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
         for (int i = 0; i < 16; ++i) acc[s][i] = 0.0;
       }
       double *gA = gbuf, *gB = gbuf + GK * 3 * N2C;
-      for (int k0 = 0; k0 < T; k0 += GK) {
-        const int rows = min(GK, T - k0) * 3;
+      for (int k0 = k_lo; k0 < Tc; k0 += GK) {
+        const int rows = min(GK, Tc - k0) * 3;
         __syncthreads();
         for (int i = tid; i < rows * N2C; i += NT) { gA[i] = wBt[(size_t)k0 * 3 * N2C + i]; gB[i] = wFB[(size_t)k0 * 3 * N2C + i]; }
         __syncthreads();
@@ -497,7 +575,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
         double acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-        for (int ki = 0; ki < 3 * T; ++ki) {
+        for (int ki = 3 * k_lo; ki < 3 * Tc; ++ki) {
           const double *br = wBt + (size_t)ki * N2C + r0, *fc = wFB + (size_t)ki * N2C + c0;
           double av[4], bv[4];
 #pragma unroll
@@ -517,6 +595,17 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
             }
           }
       }
+    }
+  }
+  __syncthreads();
+  // S now is the partial Schur complement behind the closed poses: cache it, then subtract the open pose's term Bt^T FB (rank 3)
+  for (int i = tid; i < n2 * n2; i += NT) { const int r = i / n2; fc_S[r * N2C + (i - r * n2)] = S[i]; }
+  for (int i = tid; i < n2 * n2; i += NT) {
+    const int r = i / n2, cc = i - r * n2;
+    if (r <= cc) {
+      const double v = S[i] - (openB[r] * openFB[cc] + openB[N2C + r] * openFB[N2C + cc] + openB[2 * N2C + r] * openFB[2 * N2C + cc]);
+      S[i] = v;
+      S[cc * n2 + r] = v;
     }
   }
   __syncthreads();
@@ -690,7 +779,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
               const double W0 = f0 - (w[0] * Wn[0] + w[1] * Wn[1] + w[2] * Wn[2]);
               const double W1 = f1 - (w[3] * Wn[0] + w[4] * Wn[1] + w[5] * Wn[2]);
               const double W2 = f2 - (w[6] * Wn[0] + w[7] * Wn[1] + w[8] * Wn[2]);
-              wFB[((size_t)k * 3 + 0) * N2C + c] = W0; wFB[((size_t)k * 3 + 1) * N2C + c] = W1; wFB[((size_t)k * 3 + 2) * N2C + c] = W2;
+              wW[((size_t)k * 3 + 0) * N2C + c] = W0; wW[((size_t)k * 3 + 1) * N2C + c] = W1; wW[((size_t)k * 3 + 2) * N2C + c] = W2;
               Wn[0] = W0; Wn[1] = W1; Wn[2] = W2;
             }
           }
@@ -712,7 +801,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     double *wb = gbuf + (size_t)warp * 6 * N2C;   // [n2][6]: W_ka rows 0..2, W_kb rows 0..2
     for (int kp = warp; 2 * kp < T; kp += NT / 32) {
       const int ka = 2 * kp, kb = min(2 * kp + 1, T - 1);
-      const double *Wa = wFB + (size_t)ka * 3 * N2C, *Wb = wFB + (size_t)kb * 3 * N2C;
+      const double *Wa = wW + (size_t)ka * 3 * N2C, *Wb = wW + (size_t)kb * 3 * N2C;
       __syncwarp();
 #pragma unroll
       for (int row = 0; row < 3; ++row)
@@ -753,13 +842,13 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
 #pragma unroll
       for (int i = 0; i < 3; ++i) { va[i] = warp_sum(va[i]); vb[i] = warp_sum(vb[i]); }
       if (lane == 0) {
-        double *wo_ = wsp + (size_t)ka * WS_POSE;   // slots 0..9 (D, g of phase A) are dead by now
+        double *wo_ = wsp + (size_t)ka * WS_POSE + 48;   // E-data (the A-data of the last two poses is needed again by the next step)
 #pragma unroll
         for (int i = 0; i < 6; ++i) wo_[i] = qa[i];
 #pragma unroll
         for (int i = 0; i < 3; ++i) wo_[6 + i] = va[i];
         if (2 * kp + 1 < T) {
-          double *wo2 = wsp + (size_t)kb * WS_POSE;
+          double *wo2 = wsp + (size_t)kb * WS_POSE + 48;
 #pragma unroll
           for (int i = 0; i < 6; ++i) wo2[i] = qb[i];
 #pragma unroll
@@ -774,8 +863,8 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     const double *w = wsp + (size_t)k * WS_POSE;
     double C[6], I[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) C[i] = w[39 + i] + w[i];
-    const double d0 = w[45] - w[6], d1 = w[46] - w[7], d2 = w[47] - w[8];
+    for (int i = 0; i < 6; ++i) C[i] = w[39 + i] + w[48 + i];
+    const double d0 = w[45] - w[54], d1 = w[46] - w[55], d2 = w[47] - w[56];
     dge_sym3_inv(C, I);
     double *pc = a.pose_cov + ((size_t)b * Tmax + k) * 6, *pi = a.pose_info + ((size_t)b * Tmax + k) * 6;
 #pragma unroll
@@ -810,6 +899,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     a.metrics[8 * b + 4] = le / Lt;   // ExplorationEnv.get_landmark_error  exploration_env.py:170-176
     a.metrics[8 * b + 5] = m;         // max_uncertainty_of_trajectory        exploration_env.py:190-194
     a.update_count[b] = uc;
+    a.fc_valid[b] = s_bad ? 0 : T;
     if (a.clocks) { a.clocks[12 * b +6] = clock64(); a.clocks[12 * b +7] = T; }
     if (s_bad) a.status[b] = 1;
   }
@@ -819,7 +909,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
 
 size_t dge_slam_smem_bytes(int Lt) {
   const size_t n2c = 2 * (size_t)Lt;
-  return (n2c * n2c + CH * SW + 3 * n2c + 2 * (NT / 32) + 258 + 2 * GK * 3 * n2c) * sizeof(double) + 2 * (size_t)Lt * sizeof(int) + 16;
+  return (n2c * n2c + CH * SW + 3 * n2c + 2 * (NT / 32) + 258 + 2 * GK * 3 * n2c + 6 * n2c) * sizeof(double) + 2 * (size_t)Lt * sizeof(int) + 16;
 }
 
 int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
@@ -830,7 +920,10 @@ int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
   a.lin_pose = e->lin_pose; a.est_pose = e->est_pose; a.delta_pose = e->delta_pose; a.pose_cov = e->pose_cov; a.pose_info = e->pose_info;
   a.meas_ptr = e->meas_ptr; a.meas_id = e->meas_id; a.meas_pose = e->meas_pose; a.meas_b = e->meas_b; a.meas_r = e->meas_r;
   a.observed = e->observed; a.lin_l = e->lin_l; a.est_l = e->est_l; a.delta_l = e->delta_l; a.land_cov = e->land_cov;
-  a.ws_pose = e->ws_pose; a.ws_meas = e->ws_meas; a.ws_Bt = e->ws_Bt; a.ws_FB = e->ws_FB; a.ws_midx = e->ws_midx;
+  a.ws_pose = e->ws_pose; a.ws_meas = e->ws_meas; a.ws_Bt = e->ws_Bt; a.ws_FB = e->ws_FB; a.ws_W = e->ws_W; a.ws_midx = e->ws_midx;
+  a.lm_slot = e->lm_slot; a.fc_valid = e->fc_valid; a.fc_state = e->fc_state;
+  static const int incremental = [] { const char *v = getenv("DGE_SLAM_INCREMENTAL"); return (v && v[0] == '0') ? 0 : 1; }();
+  a.incremental = incremental;
   a.metrics = e->metrics;
   a.clocks = e->slam_clocks;
   const size_t smem = dge_slam_smem_bytes(e->d.Lt);
