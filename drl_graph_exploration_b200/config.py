@@ -104,6 +104,13 @@ class EnvConfig:
         return int(self.map_size ** 2 * 0.005) if self.num_landmarks is None else int(self.num_landmarks)
 
     @property
+    def max_plan_actions(self) -> int:
+        """Upper bound of a line plan (Planner2D.cpp:982-1038): <= 2 rotation actions + floor(d / max_edge_length) forward steps + the
+        remainder step, with d <= the diagonal of the map."""
+        side = self.map_size + 2 * self.ext
+        return 3 + int(math.hypot(side, side) / self.max_edge_length)
+
+    @property
     def rows(self) -> int:   # VirtualMap.cpp:319-322
         return int(math.floor((self.map_size + 2 * self.ext) / self.resolution))
 

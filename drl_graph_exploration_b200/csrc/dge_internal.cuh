@@ -8,7 +8,7 @@
 #include "../../include/dge.h"
 
 #define DGE_PI 3.14159265358979323846
-#define DGE_WS_POSE 60
+#define DGE_WS_POSE 40
 #define DGE_FC_WIDTH(Lt) (16 + 4 * (2 * (Lt)) + (2 * (Lt)) * (2 * (Lt)))
 
 struct DgeDims {
@@ -38,14 +38,15 @@ struct dge_engine {
   double *lin_l, *est_l, *delta_l;   // [B,Lt,2]
   double *land_cov;      // [B,Lt,3]
   // ---- solver workspace (L2-resident, streamed once forward, once backward) ----
-  double *ws_pose;       // [B,Tmax,DGE_WS_POSE]: D(6) g(3) U(9) gnext(3) | @21 Dinv(6) FU(9) f(3) | @39 P(6) u(3) | @48 q(6) v(3)
+  double *ws_pose;       // [B,Tmax,DGE_WS_POSE]: D(6) g(3) U(9) gnext(3) | @21 Dinv(6) FU(9) f(3)
   double *ws_meas;       // [B,Mmax,5]: landmark-landmark block (3) + landmark rhs (2) per measurement
   double *ws_Bt;         // [B,Tmax,3,2Lt]  border rows (pose-landmark blocks, then eliminated rows)
   double *ws_FB;         // [B,Tmax,3,2Lt]  Dinv*Bt (becomes W = Lambda_xx^-1 Lambda_xl in the backward pass)
-  double *ws_W;          // [B,Tmax,3,2Lt]  W = Lambda_xx^-1 Lambda_xl (backward pass)
   int32_t *ws_midx;      // [B,Tmax,Lt]     measurement index+1 of (pose, landmark slot), 0 = none
   int32_t *lm_slot;      // [B,Lt]          landmark id -> border slot of the SLAM solve (-1 unobserved)
   int32_t *fc_valid;     // [B]             number of poses at which the cached forward-elimination state was saved (0 = none)
+  int32_t *step_order;   // [B] block -> env of the last SLAM launch (cost-ordered placement); step_order_live: valid for the virtual-map launch that follows
+  int step_order_live;
   double *fc_state;      // [B,DGE_FC_WIDTH(Lt)] cached forward-elimination state behind the closed poses (dge_slam.cu)
   double *vm_prep;       // [B,Tmax,12]     digested poses for the virtual-map kernel
   double *vm_cbox;       // [B,nchunk,4]    per-32-pose bounding boxes

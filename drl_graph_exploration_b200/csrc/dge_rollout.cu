@@ -108,20 +108,21 @@ __global__ void __launch_bounds__(256) k_rollout_clone(dge_config cfg, EngPtrs D
     return;
   }
   const size_t Tm = S.d.Tmax, Lt = S.d.Lt, V = S.d.V, Mm = S.d.Mmax;
+  const size_t Td = D.d.Tmax, Md = D.d.Mmax;      // the clone engine may hold longer trajectories than the source (room for the line plan)
   const int T = S.n_poses[b];
   const int M = S.meas_ptr[(size_t)b * (Tm + 1) + T];
   // SLAM2D(slam) copy + set_copy_isam: theta := calculateBestEstimate(), delta := 0, fresh ISAM2 (update count 1)
-  copy_n(D.lin_pose + c * Tm * 3, S.est_pose + b * Tm * 3, (size_t)T * 3);
-  copy_n(D.est_pose + c * Tm * 3, S.est_pose + b * Tm * 3, (size_t)T * 3);
-  for (size_t i = tid; i < (size_t)T * 3; i += blockDim.x) D.delta_pose[c * Tm * 3 + i] = 0.0;
-  copy_n(D.odom + c * Tm * 3, S.odom + b * Tm * 3, (size_t)T * 3);
-  copy_n(D.pose_cov + c * Tm * 6, S.pose_cov + b * Tm * 6, (size_t)T * 6);
-  copy_n(D.pose_info + c * Tm * 6, S.pose_info + b * Tm * 6, (size_t)T * 6);
-  copy_n(D.meas_ptr + c * (Tm + 1), S.meas_ptr + b * (Tm + 1), (size_t)T + 1);
-  copy_n(D.meas_id + c * Mm, S.meas_id + b * Mm, (size_t)M);
-  copy_n(D.meas_pose + c * Mm, S.meas_pose + b * Mm, (size_t)M);
-  copy_n(D.meas_b + c * Mm, S.meas_b + b * Mm, (size_t)M);
-  copy_n(D.meas_r + c * Mm, S.meas_r + b * Mm, (size_t)M);
+  copy_n(D.lin_pose + c * Td * 3, S.est_pose + b * Tm * 3, (size_t)T * 3);
+  copy_n(D.est_pose + c * Td * 3, S.est_pose + b * Tm * 3, (size_t)T * 3);
+  for (size_t i = tid; i < (size_t)T * 3; i += blockDim.x) D.delta_pose[c * Td * 3 + i] = 0.0;
+  copy_n(D.odom + c * Td * 3, S.odom + b * Tm * 3, (size_t)T * 3);
+  copy_n(D.pose_cov + c * Td * 6, S.pose_cov + b * Tm * 6, (size_t)T * 6);
+  copy_n(D.pose_info + c * Td * 6, S.pose_info + b * Tm * 6, (size_t)T * 6);
+  copy_n(D.meas_ptr + c * (Td + 1), S.meas_ptr + b * (Tm + 1), (size_t)T + 1);
+  copy_n(D.meas_id + c * Md, S.meas_id + b * Mm, (size_t)M);
+  copy_n(D.meas_pose + c * Md, S.meas_pose + b * Mm, (size_t)M);
+  copy_n(D.meas_b + c * Md, S.meas_b + b * Mm, (size_t)M);
+  copy_n(D.meas_r + c * Md, S.meas_r + b * Mm, (size_t)M);
   copy_n(D.lm_true + c * Lt * 2, S.lm_true + b * Lt * 2, Lt * 2);
   copy_n(D.scan_id + c * Lt, S.scan_id + b * Lt, Lt);
   copy_n(D.observed + c * Lt, S.observed + b * Lt, Lt);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(32) k_rollout_rewards(int Fmax, const uint8_t 
 
 extern "C" int dge_rollout_prepare(dge_handle dst, dge_handle src, const dge_graph_out *g, const uint8_t *mask, int32_t *totals_dev, void *stream) {
   if (!dst || !src || !g || !totals_dev) return DGE_EINVAL;
-  if (dst->d.Tmax != src->d.Tmax || dst->d.Lt != src->d.Lt || dst->d.V != src->d.V || dst->device != src->device) return DGE_EINVAL;
+  if (dst->d.Tmax < src->d.Tmax || dst->d.Lt != src->d.Lt || dst->d.V != src->d.V || dst->device != src->device) return DGE_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dst->park_done = 0;   // clones execute their whole plan even if the map crosses the 'explored' threshold on the way
   k_rollout_map<<<1, 1024, 0, st>>>(src->d.B, dst->d.B, mask, src->g_sel, *g, dst->r_cmap, src->r_cbase, totals_dev);

@@ -14,7 +14,7 @@
 //     registers) and the O(T n^2) parts (Schur complement, W Sigma W^T) are GEMM-shaped
 //     phases parallel over poses.
 //   * all arithmetic fp64 (prior information 1/sigma^2 ~ 3e7 next to O(1) blocks).
-//   * workspace (D,g,U | Dinv,FU,f | P,u | q,v per pose; border rows Bt / FB / W) lives in HBM but is
+//   * workspace (D,g,U | Dinv,FU,f per pose; border rows Bt / FB) lives in HBM but is
 //     written and re-read by the same CTA within microseconds => L2-resident.
 //   * INCREMENTAL between relinearisations (what ISAM2 is for): as long as no linearisation point moves, the
 //     forward elimination of the closed poses 0..T-2 cannot change when pose T arrives -- the new factors touch the
@@ -35,7 +35,8 @@ constexpr int NH = NT / 64;    // row groups per column in the Gauss-Jordan swee
 constexpr int CH = 32;         // poses staged per shared-memory chunk
 constexpr int SW = 39;         // doubles per staged pose: D(6) g(3) U(9) gnext(3) | Dinv(6) FU(9) f(3)
 constexpr int GK = 8;          // poses per staged chunk of border rows in the Schur-complement GEMM
-constexpr int WS_POSE = DGE_WS_POSE;    // doubles per pose in ws_pose: A-data D(6) g(3) U(9) gnext(3) @0 | B-data Dinv(6) FU(9) f(3) @21 | D-data P(6) u(3) @39 | E-data q(6) v(3) @48
+constexpr int WS_POSE = DGE_WS_POSE;    // doubles per pose in ws_pose: A-data D(6) g(3) U(9) gnext(3) @0 | B-data Dinv(6) FU(9) f(3) @21
+constexpr int WIDE_N2C = 96;   // more border columns than this: the backward pass works on half-size chunks (shared-memory budget)
 constexpr int WS_MEAS = 14;    // doubles per measurement in ws_meas: C(3) gl(2) | D contribution(6) g contribution(3)
 
 struct SlamArgs {
@@ -48,11 +49,12 @@ struct SlamArgs {
   const double *meas_b, *meas_r;
   const uint8_t *observed;
   double *lin_l, *est_l, *delta_l, *land_cov;
-  double *ws_pose, *ws_meas, *ws_Bt, *ws_FB, *ws_W;
+  double *ws_pose, *ws_meas, *ws_Bt, *ws_FB;
   int32_t *ws_midx;
   int32_t *lm_slot, *fc_valid;   // [B,Lt] landmark id -> border slot ; [B] number of poses the cached elimination state was saved at
   double *fc_state;              // [B, DGE_FC_WIDTH(Lt)] cached state: cD(6) cg(3) pad | cB [N2C][3] | gl [N2C] | S_partial [N2C][N2C]
   int incremental;               // 0: every step eliminates from pose 0 (A/B switch, DGE_SLAM_INCREMENTAL=0)
+  const int32_t *order;          // nullable [B]: block -> env (cost-ordered placement, k_step_order)
   double *metrics;
   long long *clocks;   // [B,12] optional: SM clock at the phase boundaries (thread 0), for in-situ phase timing
 };
@@ -85,6 +87,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// reciprocal of a pivot: hardware seed + two Newton steps (~2 ulp), half the dependent latency of the IEEE division
+__device__ __forceinline__ double gj_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -92,10 +112,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask) {
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = a.order ? a.order[blockIdx.x] : blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (mask && !mask[b]) return;
   const int T = a.n_poses[b];
   const int Lt = a.d.Lt, Tmax = a.d.Tmax, N2C = 2 * Lt;  // N2C = border stride in the workspace
+  const int ldS = N2C;                                   // row pitch of S / Sigma_ll in shared memory (= the cache's: copied straight)
   extern __shared__ __align__(16) double smem[];
   // shared layout
   double *S = smem;                               // [N2C*N2C]  Schur complement -> Sigma_ll
@@ -106,11 +127,16 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   double *red = dl + N2C;                         // [NT/32 * 2]
   double *gjb = red + 2 * (NT / 32);              // [258] pivot row / column / reciprocal exchange of the Gauss-Jordan sweep
   double *gbuf = gjb + 258;                       // [2*GK*3*N2C] border-row staging (Schur GEMM) / per-warp W_k (phase E)
-  double *openB = gbuf + 2 * GK * 3 * N2C;        // [3*N2C] border rows Bt / FB of the newest (open) pose
-  double *openFB = openB + 3 * N2C;               // [3*N2C]
-  int *lidx = (int *)(openFB + 3 * N2C);          // [Lt]  id -> border slot (-1 unobserved)
+  double *lastB = gbuf + 2 * GK * 3 * N2C;        // [2][3*N2C] border rows Bt of the pose closed last (k = T-2) and of the newest (open) pose
+  double *lastFB = lastB + 6 * N2C;               // [2][3*N2C] ... and their FB rows
+  double *openB = lastB + 3 * N2C, *openFB = lastFB + 3 * N2C;
+  // FB rows of the current chunk of the backward pass [ce*3*N2C]: own region, or (wide borders: half-size chunks) the upper half of gbuf
+  const bool wide = N2C > WIDE_N2C;
+  double *FBs = wide ? gbuf + GK * 3 * N2C : lastFB + 6 * N2C;
+  int *lidx = (int *)(lastFB + 6 * N2C + (wide ? 0 : 2 * GK * 3 * N2C));    // [Lt]  id -> border slot (-1 unobserved)
   int *lid = lidx + Lt;                           // [Lt]  slot -> id
   __shared__ int s_nl, s_nl_old, s_bad;
+  __shared__ unsigned char s_obs[64];
   __shared__ uint64_t s_bar[CH];   // one mbarrier per pose of the staged chunk: B0 (producer) -> B1 (consumers)
 
   const double wo[3] = {1.0 / (a.cfg.trans_noise * a.cfg.trans_noise), 1.0 / (a.cfg.trans_noise * a.cfg.trans_noise),
@@ -128,7 +154,6 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   double *wsm = a.ws_meas + (size_t)b * a.d.Mmax * WS_MEAS;
   double *wBt = a.ws_Bt + (size_t)b * Tmax * 3 * N2C;
   double *wFB = a.ws_FB + (size_t)b * Tmax * 3 * N2C;
-  double *wW = a.ws_W + (size_t)b * Tmax * 3 * N2C;
   int32_t *wmi = a.ws_midx + (size_t)b * Tmax * Lt;
   int32_t *slot_g = a.lm_slot + (size_t)b * Lt;
   double *fc = a.fc_state + (size_t)b * DGE_FC_WIDTH(Lt);     // cD(6) cg(3) | cB | gl | S_partial
@@ -143,6 +168,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     s_bad = 0;
     for (int i = 0; i < CH; ++i) mbar_init(&s_bar[i], 1);
   }
+  for (int j = tid; j < Lt; j += NT) { s_obs[j] = obs[j]; lidx[j] = slot_g[j]; }   // (thread 0 walks them below: no serial chain of global loads)
   int moved = 0;
   if (a.cfg.relin_skip > 0 && uc % a.cfg.relin_skip == 0) {
     for (int k = tid; k < T; k += NT) {
@@ -170,11 +196,11 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   if (tid == 0) {  // border slots: a rebuild numbers the observed landmarks in id order, a light step appends the new ones
     int n = 0;
     if (!valid) {
-      for (int j = 0; j < Lt; ++j) { if (obs[j]) { lidx[j] = n; lid[n] = j; slot_g[j] = n; ++n; } else { lidx[j] = -1; slot_g[j] = -1; } }
+      for (int j = 0; j < Lt; ++j) { if (s_obs[j]) { lidx[j] = n; lid[n] = j; slot_g[j] = n; ++n; } else { lidx[j] = -1; slot_g[j] = -1; } }
     } else {
-      for (int j = 0; j < Lt; ++j) { const int sl = obs[j] ? slot_g[j] : -1; lidx[j] = sl; if (sl >= 0) { lid[sl] = j; n = max(n, sl + 1); } }
+      for (int j = 0; j < Lt; ++j) { const int sl = s_obs[j] ? lidx[j] : -1; lidx[j] = sl; if (sl >= 0) { lid[sl] = j; n = max(n, sl + 1); } }
       s_nl_old = n;
-      for (int j = 0; j < Lt; ++j) if (obs[j] && lidx[j] < 0) { lidx[j] = n; lid[n] = j; slot_g[j] = n; ++n; }
+      for (int j = 0; j < Lt; ++j) if (s_obs[j] && lidx[j] < 0) { lidx[j] = n; lid[n] = j; slot_g[j] = n; ++n; }
     }
     if (!valid) s_nl_old = n;
     s_nl = n;
@@ -182,7 +208,12 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   // zero the sparse border inputs of this step (and, on a rebuild, the cached state)
   for (size_t i = (size_t)kz * 3 * N2C + tid; i < (size_t)T * 3 * N2C; i += NT) wBt[i] = 0.0;
   for (size_t i = (size_t)kz * Lt + tid; i < (size_t)T * Lt; i += NT) wmi[i] = 0;
-  if (!valid) for (int i = tid; i < DGE_FC_WIDTH(Lt); i += NT) fc[i] = 0.0;
+  // S starts from the cached partial Schur complement (copied asynchronously: it is first touched after phase B) or from zero
+  if (valid) { for (int i = tid; i < N2C * N2C / 2; i += NT) cp_async16(S + 2 * i, fc_S + 2 * i); cp_async_commit(); }
+  else {
+    for (int i = tid; i < N2C * N2C; i += NT) S[i] = 0.0;
+    for (int i = tid; i < 16 + 4 * N2C; i += NT) fc[i] = 0.0;
+  }
   __syncthreads();
   const int nl = s_nl, n2 = 2 * nl;
   {   // a landmark first seen in a light step opens a border column that is zero on every closed pose (the workspace may hold an older episode's rows)
@@ -406,9 +437,11 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
                 for (int i = 0; i < 3; ++i) cB[i] = -(w[9 + i] * fb0 + w[12 + i] * fb1 + w[15 + i] * fb2);
                 if (!open) {   // the open pose keeps its raw border row: it is eliminated again, with the same carry, when the next pose closes it
                   wBt[((size_t)k * 3 + 0) * N2C + c] = b0; wBt[((size_t)k * 3 + 1) * N2C + c] = b1; wBt[((size_t)k * 3 + 2) * N2C + c] = b2;
-                } else {
-                  openB[c] = b0; openB[N2C + c] = b1; openB[2 * N2C + c] = b2;
-                  openFB[c] = fb0; openFB[N2C + c] = fb1; openFB[2 * N2C + c] = fb2;
+                }
+                if (k >= T - 2) {   // the last two poses' rows stay on the SM for the rank-3 updates of S
+                  double *lb = lastB + (k - (T - 2)) * 3 * N2C, *lf = lastFB + (k - (T - 2)) * 3 * N2C;
+                  lb[c] = b0; lb[N2C + c] = b1; lb[2 * N2C + c] = b2;
+                  lf[c] = fb0; lf[N2C + c] = fb1; lf[2 * N2C + c] = fb2;
                 }
                 wFB[((size_t)k * 3 + 0) * N2C + c] = fb0; wFB[((size_t)k * 3 + 1) * N2C + c] = fb1; wFB[((size_t)k * 3 + 2) * N2C + c] = fb2;
               }
@@ -422,12 +455,11 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
       }
     }
     // S = cached partial Schur complement (zero on a rebuild) + the landmark-landmark blocks gathered above; gl = reduced rhs
-    __syncthreads();
-    for (int i = tid; i < n2 * n2; i += NT) { const int r = i / n2; S[i] = fc_S[r * N2C + (i - r * n2)]; }
+    cp_async_wait_all();
     __syncthreads();
     if (colv) {
-      S[(2 * jr) * n2 + c] += sd0;
-      S[(2 * jr + 1) * n2 + c] += sd1;
+      S[(2 * jr) * ldS + c] += sd0;
+      S[(2 * jr + 1) * ldS + c] += sd1;
       gl[c] = glc;
     }
   }
@@ -439,7 +471,16 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   // memory GK poses at a time (one linear, coalesced copy per operand); every thread keeps up to two 4x4
   // tiles of the upper triangle in registers across all chunks; the result is mirrored.
   const int Tc = T - 1;                         // closed poses [k_lo, Tc) enter the cached partial sum; the open pose is added after the save
-  if (n2 > 0) {
+  if (valid) {   // a light step closes one pose: its term Bt^T FB (rank 3) comes straight from shared memory
+    for (int i = tid; i < n2 * ldS; i += NT) {
+      const int r = i / ldS, cc = i - r * ldS;
+      if (r <= cc && cc < n2) {
+        const double v = S[i] - (lastB[r] * lastFB[cc] + lastB[N2C + r] * lastFB[N2C + cc] + lastB[2 * N2C + r] * lastFB[2 * N2C + cc]);
+        S[i] = v;
+        S[cc * ldS + r] = v;
+      }
+    }
+  } else if (n2 > 0) {
     const int nt = (n2 + 3) / 4;
     const int ntile = nt * (nt + 1) / 2;
     if (ntile <= NT / 2 && N2C <= 64) {
@@ -508,9 +549,9 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
             for (int j = 0; j < 4; ++j) {
               const int r = r0 + i, cc = c0 + j;
               if (r < n2 && cc < n2 && (tr != tc || cc >= r)) {
-                const double v = S[r * n2 + cc] - acc[i * 4 + j];
-                S[r * n2 + cc] = v;
-                if (r != cc) S[cc * n2 + r] = v;
+                const double v = S[r * ldS + cc] - acc[i * 4 + j];
+                S[r * ldS + cc] = v;
+                if (r != cc) S[cc * ldS + r] = v;
               }
             }
         }
@@ -560,9 +601,9 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
           for (int j = 0; j < 4; ++j) {
             const int r = r0 + i, cc = c0 + j;
             if (r < n2 && cc < n2 && (tr[s] != tc[s] || cc >= r)) {
-              const double v = S[r * n2 + cc] - acc[s][i * 4 + j];
-              S[r * n2 + cc] = v;
-              if (r != cc) S[cc * n2 + r] = v;
+              const double v = S[r * ldS + cc] - acc[s][i * 4 + j];
+              S[r * ldS + cc] = v;
+              if (r != cc) S[cc * ldS + r] = v;
             }
           }
       }
@@ -589,9 +630,9 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
           for (int j = 0; j < 4; ++j) {
             const int r = r0 + i, cc = c0 + j;
             if (r < n2 && cc < n2 && (tr != tc || cc >= r)) {
-              const double v = S[r * n2 + cc] - acc[i * 4 + j];
-              S[r * n2 + cc] = v;
-              if (r != cc) S[cc * n2 + r] = v;
+              const double v = S[r * ldS + cc] - acc[i * 4 + j];
+              S[r * ldS + cc] = v;
+              if (r != cc) S[cc * ldS + r] = v;
             }
           }
       }
@@ -599,16 +640,30 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   }
   __syncthreads();
   // S now is the partial Schur complement behind the closed poses: cache it, then subtract the open pose's term Bt^T FB (rank 3)
-  for (int i = tid; i < n2 * n2; i += NT) { const int r = i / n2; fc_S[r * N2C + (i - r * n2)] = S[i]; }
-  for (int i = tid; i < n2 * n2; i += NT) {
-    const int r = i / n2, cc = i - r * n2;
-    if (r <= cc) {
+  for (int i = tid; i < (valid ? n2 : N2C) * ldS; i += NT) fc_S[i] = S[i];    // (a rebuild writes every row: later slots must find zeros)
+  for (int i = tid; i < n2 * ldS; i += NT) {
+    const int r = i / ldS, cc = i - r * ldS;
+    if (r <= cc && cc < n2) {
       const double v = S[i] - (openB[r] * openFB[cc] + openB[N2C + r] * openFB[N2C + cc] + openB[2 * N2C + r] * openFB[2 * N2C + cc]);
       S[i] = v;
-      S[cc * n2 + r] = v;
+      S[cc * ldS + r] = v;
     }
   }
   __syncthreads();
+
+  // backward pass, chunk by chunk from the end: the FB rows and Dinv | FU | f of a chunk come in by cp.async while the previous
+  // chunk's marginals (or, for the first chunk, the inversion below) are computed
+  constexpr int SWD = 27;                          // staged doubles per pose: Dinv(6) FU(9) f(3) | P(6) u(3)
+  const int CE = wide ? NT / 32 : 2 * (NT / 32);   // poses per chunk (two per warp; wide borders: Wc and the FB rows share gbuf)
+  auto prefetch_chunk = [&](int k1, int buf) {
+    const int k0 = max(0, k1 - CE), kc = k1 - k0;
+    const double *src = wFB + (size_t)k0 * 3 * N2C;
+    for (int i = tid; i < kc * 3 * N2C / 2; i += NT) cp_async16(FBs + 2 * i, src + 2 * i);
+    double *sd = stage + buf * CE * SWD;
+    for (int i = tid; i < kc * 18; i += NT) cp_async8(sd + (i / 18) * SWD + (i % 18), wsp + (size_t)(k0 + i / 18) * WS_POSE + 21 + (i % 18));
+    cp_async_commit();
+  };
+  prefetch_chunk(T, 0);
 
   if (a.clocks && tid == 0) a.clocks[12 * b +3] = clock64();
   // ---------------------------------------------------------------- phase C ---
@@ -623,62 +678,65 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     double *rowb = gjb, *colb = gjb + 128, *pivb = gjb + 256;   // [2][64], [2][64], [2]
     double v[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = (h + 4 * q < n2 && c < n2) ? S[(h + 4 * q) * n2 + c] : 0.0;
+    for (int q = 0; q < 16; ++q) v[q] = (h + 4 * q < n2 && c < n2) ? S[(h + 4 * q) * ldS + c] : 0.0;
     if (h == 0) rowb[c] = v[0];
     if (c == 0) {
 #pragma unroll
       for (int q = 0; q < 16; ++q) colb[h * 16 + q] = v[q];   // a thread's 16 rows are contiguous: 128-bit loads
     }
-    if (tid == 0 && n2 > 0) { pivb[0] = 1.0 / v[0]; if (!(v[0] > 0.0)) s_bad = 1; }
+    if (tid == 0 && n2 > 0) { pivb[0] = gj_rcp(v[0]); if (!(v[0] > 0.0)) s_bad = 1; }
     __syncthreads();
-    for (int p = 0; p < n2; ++p) {
-      const int par = p & 1;
-      const double *rb = rowb + 64 * par, *cb = colb + 64 * par;
-      const double piv = pivb[par];
-      const double rpc = (c == p) ? piv : rb[c] * piv;
-      if ((p >> 5) == (warp & 1)) {      // this warp holds column p: clear it (its old content travels in cb)
-        if (c == p) {
+    // the pivot loop is unrolled completely (p = 4 qq + j): which register holds row p, and which warps hold row / column p and
+    // p + 1, are compile-time facts of every unrolled body -- no select chains over the 16 registers, no dynamic indexing
 #pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = 0.0;
-        }
-      }
+    for (int qq = 0; qq < 16; ++qq) {
 #pragma unroll
-      for (int q = 0; q < 16; q += 2) {
-        const double2 f2 = *reinterpret_cast<const double2 *>(cb + h * 16 + q);
-        v[q] = fma(-f2.x, rpc, v[q]); v[q + 1] = fma(-f2.y, rpc, v[q + 1]);
-      }
-      if (h == (p & 3)) {                // this warp holds row p
-        const int qp = p >> 2;
+      for (int j = 0; j < 4; ++j) {
+        const int p = 4 * qq + j;
+        if (p < n2) {
+          const int par = p & 1;
+          const double *rb = rowb + 64 * par, *cb = colb + 64 * par;
+          const double piv = pivb[par];
+          const double rpc = (c == p) ? piv : rb[c] * piv;
+          if ((p >> 5) == (warp & 1)) {      // this warp holds column p: clear it (its old content travels in cb)
+            if (c == p) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = (q == qp) ? rpc : v[q];
-      }
-      if (p + 1 < n2) {                  // publish pivot row / column p+1 and its reciprocal
-        const int pn = p + 1, qn = pn >> 2;
-        if (h == (pn & 3)) {
-          double vn = v[0];
-#pragma unroll
-          for (int q = 1; q < 16; ++q) vn = (q == qn) ? v[q] : vn;
-          rowb[64 * (par ^ 1) + c] = vn;
-          if (c == pn) { pivb[par ^ 1] = 1.0 / vn; if (!(vn > 0.0)) s_bad = 1; }
-        }
-        if ((pn >> 5) == (warp & 1)) {
-          if (c == pn) {
-#pragma unroll
-            for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(colb + 64 * (par ^ 1) + h * 16 + q) = make_double2(v[q], v[q + 1]);
+              for (int q = 0; q < 16; ++q) v[q] = 0.0;
+            }
           }
+#pragma unroll
+          for (int q = 0; q < 16; q += 2) {
+            const double2 f2 = *reinterpret_cast<const double2 *>(cb + h * 16 + q);
+            v[q] = fma(-f2.x, rpc, v[q]); v[q + 1] = fma(-f2.y, rpc, v[q + 1]);
+          }
+          if (h == j) v[qq] = rpc;           // this warp holds row p
+          if (p + 1 < n2) {                  // publish pivot row / column p+1 and its reciprocal
+            const int pn = p + 1, qn = pn >> 2;
+            if (h == (pn & 3)) {
+              const double vn = v[qn < 16 ? qn : 15];
+              rowb[64 * (par ^ 1) + c] = vn;
+              if (c == pn) { pivb[par ^ 1] = gj_rcp(vn); if (!(vn > 0.0)) s_bad = 1; }
+            }
+            if ((pn >> 5) == (warp & 1)) {
+              if (c == pn) {
+#pragma unroll
+                for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(colb + 64 * (par ^ 1) + h * 16 + q) = make_double2(v[q], v[q + 1]);
+              }
+            }
+          }
+          __syncthreads();
         }
       }
-      __syncthreads();
     }
 #pragma unroll
     for (int q = 0; q < 16; ++q)
-      if (h + 4 * q < n2 && c < n2) S[(h + 4 * q) * n2 + c] = v[q];
+      if (h + 4 * q < n2 && c < n2) S[(h + 4 * q) * ldS + c] = v[q];
     __syncthreads();
   } else {
   // shared-memory version for wider borders
   // Thread (c, h): column c = tid % 64 (+64 for a second pass when n2 > 64), rows r = h mod NH.
   for (int p = 0; p < n2; ++p) {
-    if (tid < n2) colp[tid] = S[tid * n2 + p];
+    if (tid < n2) colp[tid] = S[tid * ldS + p];
     __syncthreads();
     const double pv = colp[p];
     if (tid == 0 && !(pv > 0.0)) s_bad = 1;
@@ -688,58 +746,65 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
       double *__restrict__ Sc = S + c;
       const double *__restrict__ cp = colp;
       if (c != p) {
-        const double rowpc = Sc[p * n2] * piv;
+        const double rowpc = Sc[p * ldS] * piv;
         int r = h;
         for (; r + 5 * NH < n2; r += 6 * NH) {
-          double s0 = Sc[r * n2], s1 = Sc[(r + NH) * n2], s2 = Sc[(r + 2 * NH) * n2], s3 = Sc[(r + 3 * NH) * n2], s4 = Sc[(r + 4 * NH) * n2], s5 = Sc[(r + 5 * NH) * n2];
+          double s0 = Sc[r * ldS], s1 = Sc[(r + NH) * ldS], s2 = Sc[(r + 2 * NH) * ldS], s3 = Sc[(r + 3 * NH) * ldS], s4 = Sc[(r + 4 * NH) * ldS], s5 = Sc[(r + 5 * NH) * ldS];
           const double c0 = cp[r], c1 = cp[r + NH], c2 = cp[r + 2 * NH], c3 = cp[r + 3 * NH], c4 = cp[r + 4 * NH], c5 = cp[r + 5 * NH];
           s0 -= c0 * rowpc; s1 -= c1 * rowpc; s2 -= c2 * rowpc; s3 -= c3 * rowpc; s4 -= c4 * rowpc; s5 -= c5 * rowpc;
-          if (r != p) Sc[r * n2] = s0;
-          if (r + NH != p) Sc[(r + NH) * n2] = s1;
-          if (r + 2 * NH != p) Sc[(r + 2 * NH) * n2] = s2;
-          if (r + 3 * NH != p) Sc[(r + 3 * NH) * n2] = s3;
-          if (r + 4 * NH != p) Sc[(r + 4 * NH) * n2] = s4;
-          if (r + 5 * NH != p) Sc[(r + 5 * NH) * n2] = s5;
+          if (r != p) Sc[r * ldS] = s0;
+          if (r + NH != p) Sc[(r + NH) * ldS] = s1;
+          if (r + 2 * NH != p) Sc[(r + 2 * NH) * ldS] = s2;
+          if (r + 3 * NH != p) Sc[(r + 3 * NH) * ldS] = s3;
+          if (r + 4 * NH != p) Sc[(r + 4 * NH) * ldS] = s4;
+          if (r + 5 * NH != p) Sc[(r + 5 * NH) * ldS] = s5;
         }
         for (; r < n2; r += NH)
-          if (r != p) Sc[r * n2] -= cp[r] * rowpc;
+          if (r != p) Sc[r * ldS] -= cp[r] * rowpc;
       }
     }
     __syncthreads();
     // row p of the non-pivot columns and the pivot column itself (after every thread has finished reading them)
     for (int c = tid; c < n2; c += NT) {
-      if (c != p) S[p * n2 + c] *= piv;
-      S[c * n2 + p] = (c == p) ? piv : -colp[c] * piv;
+      if (c != p) S[p * ldS + c] *= piv;
+      S[c * ldS + p] = (c == p) ? piv : -colp[c] * piv;
     }
     __syncthreads();
   }
   }
   if (tid < n2) {
     double s = 0;
-    for (int c = 0; c < n2; ++c) s += S[tid * n2 + c] * gl[c];
+    for (int c = 0; c < n2; ++c) s += S[tid * ldS + c] * gl[c];
     dl[tid] = s;
   }
   __syncthreads();
 
   if (a.clocks && tid == 0) a.clocks[12 * b +4] = clock64();
-  // --------------------------------------------------------------- phase D ---
-  // backward substitution, per 32-pose chunk (descending):
-  //   D0  warp 0: P_k = Dinv_k + FU_k P_{k+1} FU_k^T (= [Lambda_xx^-1]_kk), u_k = f_k - FU_k u_{k+1};
-  //   D1  column threads: W_k = FB_k - FU_k W_{k+1}  (W = Lambda_xx^-1 Lambda_xl), next row prefetched.
-  // D1 does not depend on D0, so the two run concurrently on different warps.
+  // ------------------------------------------------------------ phases D + E ---
+  // backward substitution and marginal recovery, fused per chunk of CE poses (descending) -- W never leaves the SM:
+  //   D0  warp 0: P_k = Dinv_k + FU_k P_{k+1} FU_k^T (= [Lambda_xx^-1]_kk), u_k = f_k - FU_k u_{k+1}   -> shared memory;
+  //   D1  column threads: W_k = FB_k - FU_k W_{k+1}  (W = Lambda_xx^-1 Lambda_xl), FB rows prefetched    -> shared memory,
+  //       pose pairs interleaved [pair][column][6] as phase E reads them (D1 does not depend on D0: different warps);
+  //   E   one warp per pose pair of the chunk: y = W_k Sigma_ll with two columns per lane (per row r of Sigma_ll three
+  //       128-bit broadcast loads of the 6 interleaved W rows + 2 loads of Sigma_ll feed 12 DFMAs), q = y W_k^T and
+  //       v = W_k dl reduced across the warp; lanes 0 / 1 finish the two poses: Sigma_kk = P_k + q, delta_k = u_k - v,
+  //       estimate = theta (+) delta, information = Sigma_kk^-1 (SLAM2D.cpp:400).
+  double tmax = -1e300;
   {
     const int c = ccol;
     double Wn[3] = {0, 0, 0};
     double P0 = 0, P1 = 0, P2 = 0, P3 = 0, P4 = 0, P5 = 0, un0 = 0, un1 = 0, un2 = 0;   // warp-0 carried state (P symmetric packed)
-    for (int k1 = T; k1 > 0; k1 -= CH) {
-      const int k0 = max(0, k1 - CH), kc = k1 - k0;
-      __syncthreads();
-      for (int i = tid; i < kc * 18; i += NT) stage[(i / 18) * SW + (i % 18)] = wsp[(size_t)(k0 + i / 18) * WS_POSE + 21 + (i % 18)];
-      __syncthreads();
+    double *Wc = gbuf;                                  // [CE / 2][N2C][6]
+    int buf = 0;
+    for (int k1 = T; k1 > 0; k1 -= CE, buf ^= 1) {
+      const int k0 = max(0, k1 - CE), kc = k1 - k0;
+      double *sd = stage + buf * CE * SWD;
+      cp_async_wait_all();
+      __syncthreads();                                  // this chunk's inputs have landed; the previous chunk's E has finished reading Wc / its stage
       if (warp == 0) {
         // D0: scalar, identical on every lane (see B0)
         for (int kk = kc - 1; kk >= 0; --kk) {
-          const double *w = stage + kk * SW;   // Dinv(6) FU(9) f(3)
+          double *w = sd + kk * SWD;   // Dinv(6) FU(9) f(3) | P(6) u(3)
           const double f00 = w[6], f01 = w[7], f02 = w[8], f10 = w[9], f11 = w[10], f12 = w[11], f20 = w[12], f21 = w[13], f22 = w[14];
           // M = FU P
           const double m00 = f00 * P0 + f01 * P1 + f02 * P2, m01 = f00 * P1 + f01 * P3 + f02 * P4, m02 = f00 * P2 + f01 * P4 + f02 * P5;
@@ -751,129 +816,81 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
           P0 = w[0] + m00 * f00 + m01 * f01 + m02 * f02; P1 = w[1] + m00 * f10 + m01 * f11 + m02 * f12; P2 = w[2] + m00 * f20 + m01 * f21 + m02 * f22;
           P3 = w[3] + m10 * f10 + m11 * f11 + m12 * f12; P4 = w[4] + m10 * f20 + m11 * f21 + m12 * f22; P5 = w[5] + m20 * f20 + m21 * f21 + m22 * f22;
           un0 = v0; un1 = v1; un2 = v2;
-          if (lane == 0) {
-            double *wo_ = wsp + (size_t)(k0 + kk) * WS_POSE + 39;
-            wo_[0] = P0; wo_[1] = P1; wo_[2] = P2; wo_[3] = P3; wo_[4] = P4; wo_[5] = P5; wo_[6] = v0; wo_[7] = v1; wo_[8] = v2;
-          }
+          if (lane == 0) { w[18] = P0; w[19] = P1; w[20] = P2; w[21] = P3; w[22] = P4; w[23] = P5; w[24] = v0; w[25] = v1; w[26] = v2; }
         }
       }
       if (colv) {
-        // D1: W_k = FB_k - FU_k W_{k+1}, FB rows prefetched 4 poses ahead
-        double nf[4][3];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int i = 0; i < 3; ++i) nf[u][i] = (u < kc) ? wFB[((size_t)(k1 - 1 - u) * 3 + i) * N2C + c] : 0.0;
-        for (int kb = 0; kb < kc; kb += 4) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int q = kb + u;           // q-th pose of the chunk counted from its end
-            if (q < kc) {
-              const int k = k1 - 1 - q;
-              const double f0 = nf[u][0], f1 = nf[u][1], f2 = nf[u][2];
-              if (q + 4 < kc) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) nf[u][i] = wFB[((size_t)(k - 4) * 3 + i) * N2C + c];
-              }
-              const double *w = stage + (k - k0) * SW + 6;   // FU
-              const double W0 = f0 - (w[0] * Wn[0] + w[1] * Wn[1] + w[2] * Wn[2]);
-              const double W1 = f1 - (w[3] * Wn[0] + w[4] * Wn[1] + w[5] * Wn[2]);
-              const double W2 = f2 - (w[6] * Wn[0] + w[7] * Wn[1] + w[8] * Wn[2]);
-              wW[((size_t)k * 3 + 0) * N2C + c] = W0; wW[((size_t)k * 3 + 1) * N2C + c] = W1; wW[((size_t)k * 3 + 2) * N2C + c] = W2;
-              Wn[0] = W0; Wn[1] = W1; Wn[2] = W2;
-            }
+        // D1: W_k = FB_k - FU_k W_{k+1}; everything it reads is in shared memory
+        for (int kk = kc - 1; kk >= 0; --kk) {
+          const double *fb = FBs + (size_t)kk * 3 * N2C + c;
+          const double *w = sd + kk * SWD + 6;   // FU
+          const double W0 = fb[0] - (w[0] * Wn[0] + w[1] * Wn[1] + w[2] * Wn[2]);
+          const double W1 = fb[N2C] - (w[3] * Wn[0] + w[4] * Wn[1] + w[5] * Wn[2]);
+          const double W2 = fb[2 * N2C] - (w[6] * Wn[0] + w[7] * Wn[1] + w[8] * Wn[2]);
+          double *wo_ = Wc + ((size_t)(kk >> 1) * N2C + c) * 6 + 3 * (kk & 1);
+          wo_[0] = W0; wo_[1] = W1; wo_[2] = W2;
+          Wn[0] = W0; Wn[1] = W1; Wn[2] = W2;
+        }
+      }
+      __syncthreads();
+      if (k0 > 0) prefetch_chunk(k0, buf ^ 1);          // the next chunk streams in beside this chunk's marginals
+      if (2 * warp < kc) {
+        const double *wb = Wc + (size_t)warp * N2C * 6;   // [n2][6]: W_ka rows 0..2, W_kb rows 0..2 (kb may be beyond the chunk: its sums are not used)
+        double qa[6] = {0, 0, 0, 0, 0, 0}, va[3] = {0, 0, 0}, qb[6] = {0, 0, 0, 0, 0, 0}, vb[3] = {0, 0, 0};
+        for (int cb = 0; cb < n2; cb += 64) {
+          const int c1 = cb + lane, c2 = cb + 32 + lane;
+          const bool v1 = c1 < n2, v2 = c2 < n2;
+          const double *sp1 = S + (v1 ? c1 : 0), *sp2 = S + (v2 ? c2 : 0);
+          const double *wr = wb;
+          double ya0 = 0, ya1 = 0, ya2 = 0, yb0 = 0, yb1 = 0, yb2 = 0, za0 = 0, za1 = 0, za2 = 0, zb0 = 0, zb1 = 0, zb2 = 0;
+#pragma unroll 4
+          for (int r = 0; r < n2; ++r) {
+            const double2 w01 = *reinterpret_cast<const double2 *>(wr), w23 = *reinterpret_cast<const double2 *>(wr + 2), w45 = *reinterpret_cast<const double2 *>(wr + 4);
+            const double s1 = *sp1, s2 = *sp2;
+            ya0 += w01.x * s1; ya1 += w01.y * s1; ya2 += w23.x * s1; yb0 += w23.y * s1; yb1 += w45.x * s1; yb2 += w45.y * s1;
+            za0 += w01.x * s2; za1 += w01.y * s2; za2 += w23.x * s2; zb0 += w23.y * s2; zb1 += w45.x * s2; zb2 += w45.y * s2;
+            wr += 6; sp1 += ldS; sp2 += ldS;
+          }
+          if (v1) {
+            const double *w = wb + c1 * 6;
+            const double d = dl[c1];
+            qa[0] += ya0 * w[0]; qa[1] += ya0 * w[1]; qa[2] += ya0 * w[2]; qa[3] += ya1 * w[1]; qa[4] += ya1 * w[2]; qa[5] += ya2 * w[2];
+            qb[0] += yb0 * w[3]; qb[1] += yb0 * w[4]; qb[2] += yb0 * w[5]; qb[3] += yb1 * w[4]; qb[4] += yb1 * w[5]; qb[5] += yb2 * w[5];
+            va[0] += w[0] * d; va[1] += w[1] * d; va[2] += w[2] * d; vb[0] += w[3] * d; vb[1] += w[4] * d; vb[2] += w[5] * d;
+          }
+          if (v2) {
+            const double *w = wb + c2 * 6;
+            const double d = dl[c2];
+            qa[0] += za0 * w[0]; qa[1] += za0 * w[1]; qa[2] += za0 * w[2]; qa[3] += za1 * w[1]; qa[4] += za1 * w[2]; qa[5] += za2 * w[2];
+            qb[0] += zb0 * w[3]; qb[1] += zb0 * w[4]; qb[2] += zb0 * w[5]; qb[3] += zb1 * w[4]; qb[4] += zb1 * w[5]; qb[5] += zb2 * w[5];
+            va[0] += w[0] * d; va[1] += w[1] * d; va[2] += w[2] * d; vb[0] += w[3] * d; vb[1] += w[4] * d; vb[2] += w[5] * d;
           }
         }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { qa[i] = warp_sum(qa[i]); qb[i] = warp_sum(qb[i]); }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { va[i] = warp_sum(va[i]); vb[i] = warp_sum(vb[i]); }
+        const int kk = 2 * warp + lane;                 // lanes 0 / 1 finish the pair's two poses
+        if (lane < 2 && kk < kc) {
+          const int k = k0 + kk;
+          const double *w = sd + kk * SWD + 18;         // P(6) u(3)
+          double C[6], I[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) C[i] = w[i] + (lane ? qb[i] : qa[i]);
+          const double d0 = w[6] - (lane ? vb[0] : va[0]), d1 = w[7] - (lane ? vb[1] : va[1]), d2 = w[8] - (lane ? vb[2] : va[2]);
+          dge_sym3_inv(C, I);
+          double *pc = a.pose_cov + ((size_t)b * Tmax + k) * 6, *pi = a.pose_info + ((size_t)b * Tmax + k) * 6;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { pc[i] = C[i]; pi[i] = I[i]; }
+          del[3 * k] = d0; del[3 * k + 1] = d1; del[3 * k + 2] = d2;
+          const Pose3 e = dge_compose(Pose3{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]}, Pose3{d0, d1, d2});
+          est[3 * k] = e.x; est[3 * k + 1] = e.y; est[3 * k + 2] = e.th;
+          tmax = fmax(tmax, C[0] + C[3] + C[5]);
+        }
       }
     }
   }
-  __syncthreads();
-
   if (a.clocks && tid == 0) a.clocks[12 * b +5] = clock64();
-  // ---------------------------------------------------------------- phase E ---
-  // E1  one warp per pair of poses: W_k (3 x n2) staged into shared memory, y = W_k Sigma_ll with two columns per lane,
-  //     q = y W_k^T and v = W_k dl reduced across the warp -> workspace.
-  // E2  one thread per pose: Sigma_kk = P_k + q, delta_k = u_k - v, estimate = theta (+) delta,
-  //     information = Sigma_kk^-1 (SLAM2D.cpp:400).
-  {
-    // two poses per warp pass: per row r of Sigma_ll 3 x 128-bit broadcast loads (the 6 interleaved W rows) and 2 loads
-    // of Sigma_ll feed 12 DFMAs, which makes the loop fp64-pipe-bound rather than issue-bound
-    double *wb = gbuf + (size_t)warp * 6 * N2C;   // [n2][6]: W_ka rows 0..2, W_kb rows 0..2
-    for (int kp = warp; 2 * kp < T; kp += NT / 32) {
-      const int ka = 2 * kp, kb = min(2 * kp + 1, T - 1);
-      const double *Wa = wW + (size_t)ka * 3 * N2C, *Wb = wW + (size_t)kb * 3 * N2C;
-      __syncwarp();
-#pragma unroll
-      for (int row = 0; row < 3; ++row)
-        for (int r = lane; r < n2; r += 32) { wb[r * 6 + row] = Wa[row * N2C + r]; wb[r * 6 + 3 + row] = Wb[row * N2C + r]; }
-      __syncwarp();
-      double qa[6] = {0, 0, 0, 0, 0, 0}, va[3] = {0, 0, 0}, qb[6] = {0, 0, 0, 0, 0, 0}, vb[3] = {0, 0, 0};
-      for (int cb = 0; cb < n2; cb += 64) {
-        const int c1 = cb + lane, c2 = cb + 32 + lane;
-        const bool v1 = c1 < n2, v2 = c2 < n2;
-        const double *sp1 = S + (v1 ? c1 : 0), *sp2 = S + (v2 ? c2 : 0);
-        const double *wr = wb;
-        double ya0 = 0, ya1 = 0, ya2 = 0, yb0 = 0, yb1 = 0, yb2 = 0, za0 = 0, za1 = 0, za2 = 0, zb0 = 0, zb1 = 0, zb2 = 0;
-#pragma unroll 4
-        for (int r = 0; r < n2; ++r) {
-          const double2 w01 = *reinterpret_cast<const double2 *>(wr), w23 = *reinterpret_cast<const double2 *>(wr + 2), w45 = *reinterpret_cast<const double2 *>(wr + 4);
-          const double s1 = *sp1, s2 = *sp2;
-          ya0 += w01.x * s1; ya1 += w01.y * s1; ya2 += w23.x * s1; yb0 += w23.y * s1; yb1 += w45.x * s1; yb2 += w45.y * s1;
-          za0 += w01.x * s2; za1 += w01.y * s2; za2 += w23.x * s2; zb0 += w23.y * s2; zb1 += w45.x * s2; zb2 += w45.y * s2;
-          wr += 6; sp1 += n2; sp2 += n2;
-        }
-        if (v1) {
-          const double *w = wb + c1 * 6;
-          const double d = dl[c1];
-          qa[0] += ya0 * w[0]; qa[1] += ya0 * w[1]; qa[2] += ya0 * w[2]; qa[3] += ya1 * w[1]; qa[4] += ya1 * w[2]; qa[5] += ya2 * w[2];
-          qb[0] += yb0 * w[3]; qb[1] += yb0 * w[4]; qb[2] += yb0 * w[5]; qb[3] += yb1 * w[4]; qb[4] += yb1 * w[5]; qb[5] += yb2 * w[5];
-          va[0] += w[0] * d; va[1] += w[1] * d; va[2] += w[2] * d; vb[0] += w[3] * d; vb[1] += w[4] * d; vb[2] += w[5] * d;
-        }
-        if (v2) {
-          const double *w = wb + c2 * 6;
-          const double d = dl[c2];
-          qa[0] += za0 * w[0]; qa[1] += za0 * w[1]; qa[2] += za0 * w[2]; qa[3] += za1 * w[1]; qa[4] += za1 * w[2]; qa[5] += za2 * w[2];
-          qb[0] += zb0 * w[3]; qb[1] += zb0 * w[4]; qb[2] += zb0 * w[5]; qb[3] += zb1 * w[4]; qb[4] += zb1 * w[5]; qb[5] += zb2 * w[5];
-          va[0] += w[0] * d; va[1] += w[1] * d; va[2] += w[2] * d; vb[0] += w[3] * d; vb[1] += w[4] * d; vb[2] += w[5] * d;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { qa[i] = warp_sum(qa[i]); qb[i] = warp_sum(qb[i]); }
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { va[i] = warp_sum(va[i]); vb[i] = warp_sum(vb[i]); }
-      if (lane == 0) {
-        double *wo_ = wsp + (size_t)ka * WS_POSE + 48;   // E-data (the A-data of the last two poses is needed again by the next step)
-#pragma unroll
-        for (int i = 0; i < 6; ++i) wo_[i] = qa[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) wo_[6 + i] = va[i];
-        if (2 * kp + 1 < T) {
-          double *wo2 = wsp + (size_t)kb * WS_POSE + 48;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) wo2[i] = qb[i];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) wo2[6 + i] = vb[i];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  double tmax = -1e300;
-  for (int k = tid; k < T; k += NT) {
-    const double *w = wsp + (size_t)k * WS_POSE;
-    double C[6], I[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) C[i] = w[39 + i] + w[48 + i];
-    const double d0 = w[45] - w[54], d1 = w[46] - w[55], d2 = w[47] - w[56];
-    dge_sym3_inv(C, I);
-    double *pc = a.pose_cov + ((size_t)b * Tmax + k) * 6, *pi = a.pose_info + ((size_t)b * Tmax + k) * 6;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { pc[i] = C[i]; pi[i] = I[i]; }
-    del[3 * k] = d0; del[3 * k + 1] = d1; del[3 * k + 2] = d2;
-    const Pose3 e = dge_compose(Pose3{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]}, Pose3{d0, d1, d2});
-    est[3 * k] = e.x; est[3 * k + 1] = e.y; est[3 * k + 2] = e.th;
-    tmax = fmax(tmax, C[0] + C[3] + C[5]);
-  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
   if (lane == 0) red[warp] = tmax;
@@ -886,7 +903,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     const double ex = linl[2 * j] + dl[c0], ey = linl[2 * j + 1] + dl[c0 + 1];
     estl[2 * j] = ex; estl[2 * j + 1] = ey;
     double *lc = a.land_cov + ((size_t)b * Lt + j) * 3;
-    lc[0] = S[c0 * n2 + c0]; lc[1] = S[c0 * n2 + c0 + 1]; lc[2] = S[(c0 + 1) * n2 + c0 + 1];
+    lc[0] = S[c0 * ldS + c0]; lc[1] = S[c0 * ldS + c0 + 1]; lc[2] = S[(c0 + 1) * ldS + c0 + 1];
     const double dx = a.lm_true[((size_t)b * Lt + j) * 2] - ex, dy = a.lm_true[((size_t)b * Lt + j) * 2 + 1] - ey;
     lerr += sqrt(dx * dx + dy * dy);
   }
@@ -900,8 +917,40 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     a.metrics[8 * b + 5] = m;         // max_uncertainty_of_trajectory        exploration_env.py:190-194
     a.update_count[b] = uc;
     a.fc_valid[b] = s_bad ? 0 : T;
-    if (a.clocks) { a.clocks[12 * b +6] = clock64(); a.clocks[12 * b +7] = T; }
+    if (a.clocks) { a.clocks[12 * b +6] = clock64(); a.clocks[12 * b +7] = T; a.clocks[12 * b + 10] = valid ? 1 : 0; a.clocks[12 * b + 11] = n2; }
     if (s_bad) a.status[b] = 1;
+  }
+}
+
+// Cost-ordered placement of the envs on the SMs.  A launch lasts as long as its slowest CTA, and the step kernels run one CTA per
+// env with two CTAs per SM: blocks [0, n_sm) are dispatched one per SM, blocks [n_sm, B) fill the second slots of SMs 0 .. B-n_sm-1.
+// The 2 n_sm - B most expensive envs (long trajectory, rebuild due) go to the blocks that keep an SM to themselves, the rest is
+// paired expensive-with-cheap.  cost = trajectory length, doubled when the next update is on the relinearisation schedule.
+__global__ void __launch_bounds__(1024) k_step_order(int B, int n_sm, int relin_skip, const uint8_t *mask, const int32_t *n_poses,
+                                                     const int32_t *update_count, int32_t *order) {
+  extern __shared__ int s_cost[];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int cst = -1;
+    if (!mask || mask[b]) {
+      cst = n_poses[b];
+      if (relin_skip > 0 && (update_count[b] + 1) % relin_skip == 0) cst *= 2;
+    }
+    s_cost[b] = cst;
+  }
+  __syncthreads();
+  const int solo = (B > n_sm && B < 2 * n_sm) ? 2 * n_sm - B : 0;   // blocks [B - n_sm, n_sm) share their SM with nobody
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int cst = s_cost[b];
+    int rank = 0;
+    for (int o = 0; o < B; ++o) { const int co = s_cost[o]; rank += (co > cst || (co == cst && o < b)) ? 1 : 0; }
+    int blk;
+    if (solo == 0) blk = rank;
+    else if (rank < solo) blk = (B - n_sm) + rank;               // the most expensive: alone on an SM
+    else {
+      const int r = rank - solo, half = B - n_sm;                 // 2 * half envs left, two per SM: r-th most expensive with r-th cheapest
+      blk = r < half ? r : n_sm + (2 * half - 1 - r);
+    }
+    order[blk] = b;
   }
 }
 
@@ -909,7 +958,8 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
 
 size_t dge_slam_smem_bytes(int Lt) {
   const size_t n2c = 2 * (size_t)Lt;
-  return (n2c * n2c + CH * SW + 3 * n2c + 2 * (NT / 32) + 258 + 2 * GK * 3 * n2c + 6 * n2c) * sizeof(double) + 2 * (size_t)Lt * sizeof(int) + 16;
+  return (n2c * n2c + CH * SW + 3 * n2c + 2 * (NT / 32) + 258 + 2 * GK * 3 * n2c + 12 * n2c + (n2c > WIDE_N2C ? 0 : 2 * GK * 3 * n2c)) * sizeof(double) +
+         2 * (size_t)Lt * sizeof(int) + 16;
 }
 
 int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
@@ -920,10 +970,19 @@ int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
   a.lin_pose = e->lin_pose; a.est_pose = e->est_pose; a.delta_pose = e->delta_pose; a.pose_cov = e->pose_cov; a.pose_info = e->pose_info;
   a.meas_ptr = e->meas_ptr; a.meas_id = e->meas_id; a.meas_pose = e->meas_pose; a.meas_b = e->meas_b; a.meas_r = e->meas_r;
   a.observed = e->observed; a.lin_l = e->lin_l; a.est_l = e->est_l; a.delta_l = e->delta_l; a.land_cov = e->land_cov;
-  a.ws_pose = e->ws_pose; a.ws_meas = e->ws_meas; a.ws_Bt = e->ws_Bt; a.ws_FB = e->ws_FB; a.ws_W = e->ws_W; a.ws_midx = e->ws_midx;
+  a.ws_pose = e->ws_pose; a.ws_meas = e->ws_meas; a.ws_Bt = e->ws_Bt; a.ws_FB = e->ws_FB; a.ws_midx = e->ws_midx;
   a.lm_slot = e->lm_slot; a.fc_valid = e->fc_valid; a.fc_state = e->fc_state;
   static const int incremental = [] { const char *v = getenv("DGE_SLAM_INCREMENTAL"); return (v && v[0] == '0') ? 0 : 1; }();
   a.incremental = incremental;
+  static const int ordered = [] { const char *v = getenv("DGE_STEP_ORDER"); return (v && v[0] == '1') ? 1 : 0; }();   // off by default: measured no gain (r02)
+  static int n_sm = 0;
+  if (!n_sm && (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, e->device) != cudaSuccess || n_sm <= 0)) n_sm = 148;
+  a.order = nullptr;
+  if (ordered && e->d.B > n_sm && e->d.B < 2 * n_sm && e->d.B <= 4096) {
+    k_step_order<<<1, 1024, e->d.B * sizeof(int), st>>>(e->d.B, n_sm, e->cfg.relin_skip, mask, e->n_poses, e->update_count, e->step_order);
+    a.order = e->step_order;
+  }
+  e->step_order_live = a.order != nullptr;
   a.metrics = e->metrics;
   a.clocks = e->slam_clocks;
   const size_t smem = dge_slam_smem_bytes(e->d.Lt);

@@ -306,11 +306,12 @@ struct EnvArgs {
   const int32_t *sim_step, *status, *meas_ptr; const double *dist; double *metrics; uint8_t *done;
   unsigned long long *counters; const uint8_t *step_kind;
   long long *clocks;                                   // nullable [n,4]: SM clock at start / after digest / after fold / end (thread 0)
+  const int32_t *order;                                // nullable [n]: block -> env (cost-ordered placement of the step kernels, dge_slam.cu)
 };
 
 template <int WT>   // WT = block width W when known at compile time (7 for the reference's sensor / resolution), 0 = generic
 __global__ void __launch_bounds__(ENV_THREADS, 2) k_vmap_env(EnvArgs a) {
-  const int b = blockIdx.x;
+  const int b = a.order ? a.order[blockIdx.x] : blockIdx.x;
   if (a.mask && !a.mask[b]) return;
   const VmapCfg &c = a.c;
   const int T = a.n_poses ? a.n_poses[b] : a.Tfixed;
@@ -621,6 +622,7 @@ int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
     a.cfg = e->cfg; a.d = e->d; a.sim_step = e->sim_step; a.status = e->status; a.meas_ptr = e->meas_ptr; a.dist = e->dist;
     a.metrics = e->metrics; a.done = e->done; a.counters = e->count_steps ? e->counters : nullptr; a.step_kind = e->step_kind;
     a.clocks = nullptr;
+    a.order = (e->step_order_live && mask == e->active) ? e->step_order : nullptr;   // same envs, same costs as the SLAM launch just before
     const int rc = env_launch(a, e->cfg, e->d.B, e->d.rows, e->d.cols, st);
     if (rc != 1) return rc;
   }
@@ -652,6 +654,7 @@ int dge_vmap_standalone(const dge_config *cfg, int n, int T, const double *pose,
     a.sim_step = nullptr; a.status = nullptr; a.meas_ptr = nullptr; a.dist = nullptr;
     a.cfg = *cfg; a.d = DgeDims{};
     a.clocks = reinterpret_cast<long long *>(cbox_ws);   // the chunk-box scratch is unused by the fused kernel: phase clocks for dev profiling
+    a.order = nullptr;
     const int rc = env_launch(a, *cfg, n, rows, cols, st);
     if (rc != 1) return rc;
   }

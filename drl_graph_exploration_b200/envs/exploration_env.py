@@ -200,9 +200,15 @@ class VecExplorationEnv:
         the upper bound of a line plan (typically 4-10 instead of 3 + diagonal / max_edge_length).
         The caller keeps sum(fro_size) of the selected envs <= clone_slots (``VecDQNTrainer`` chunks the decision round)."""
         eng = self.eng
+        max_actions = self.cfg.max_plan_actions                    # <= 2 rotations + floor(d / max_edge) forward steps + remainder
+        if getattr(self, "_roll", None) is not None and clone_slots is not None and clone_slots != self._roll.B:
+            raise DgeError(f"rollout_rewards: the clone engine was created with {self._roll.B} slots, not {clone_slots}")
         if getattr(self, "_roll", None) is None:
             slots = clone_slots or min(self.B * (eng.Lt + 1), max(4 * self.B, 512))
-            self._roll = Engine(self.cfg, slots, max_poses=eng.Tmax, device=self.device)
+            if slots < eng.Lt + 1:
+                raise DgeError(f"rollout_rewards: clone_slots = {slots} cannot hold the frontiers of one env (up to {eng.Lt + 1})")
+            # a clone of an env near its pose capacity must still be able to run its whole line plan
+            self._roll = Engine(self.cfg, slots, max_poses=eng.Tmax + max_actions, device=self.device)
             self._roll_totals = torch.zeros(2, dtype=torch.int32, device=self.device)
             self._roll_totals_host = torch.zeros(2, dtype=torch.int32).pin_memory()
             fm = eng.Lt + 1
@@ -217,19 +223,30 @@ class VecExplorationEnv:
         roll, sp = self._roll, _stream_ptr(self.device)
         roll._L.dge_set_counting(roll._h, 0)
         _check(eng._L.dge_rollout_prepare(roll._h, eng._h, ctypes.byref(self.graph.c), _ptr(mask), _ptr(self._roll_totals), sp), "dge_rollout_prepare")
-        # upper bound of a line plan: <= 2 rotations + floor(diagonal / max_edge) forward steps + remainder
-        diag = math.hypot(self.cfg.map_size, self.cfg.map_size)
-        n_steps = 3 + int(diag / self.cfg.max_edge_length)
+        n_steps = max_actions
         if noise is not None:
             n_steps = noise.shape[0]
-        elif auto_steps:
+        elif auto_steps:     # one host sync: the longest clone plan and the overflow flag of the clone map
+            self._roll_totals_host.copy_(self._roll_totals, non_blocking=True)
             n_steps = min(n_steps, int(roll.state["plan"][:, 5].max().item()))
+            if int(self._roll_totals_host[1]):
+                raise DgeError("rollout_rewards: more (env, frontier) clones than the clone engine has slots; chunk the decision round or raise clone_slots")
         self.rollout_steps = n_steps
         for i in range(n_steps):
             _check(roll._L.dge_step_queued_noise(roll._h, _ptr(None if noise is None else noise[i].contiguous()), sp), "dge_step_queued_noise")
         _check(eng._L.dge_rollout_rewards(roll._h, eng._h, ctypes.byref(self.graph.c), _ptr(mask), _ptr(self._roll_raw), _ptr(self._roll_norm),
                                           _ptr(self._roll_clo), sp), "dge_rollout_rewards")
         return self._roll_raw, self._roll_norm, self._roll_clo
+
+    def rollout_overflowed(self) -> bool:
+        """True if the last ``rollout_rewards`` asked for more clones than the clone engine holds (host sync).  ``auto_steps``
+        checks this by itself; the explicit-noise / fixed-step modes leave the check to the caller."""
+        return bool(int(self._roll_totals[1].item()))
+
+    def capacity_overflows(self) -> torch.Tensor:
+        """[B] bool: envs whose episode was ended by a full trajectory buffer (status DGE_ECAP) rather than by the reference's
+        own rules (explored > 0.85 or step > max_steps, exploration_env.py:166-168)."""
+        return self.eng.state["status"] == -4
 
     # ------------------------------------------------------------- host API ---
     def step_host(self, odom_host: np.ndarray, done_host: np.ndarray, obs_host: Optional[np.ndarray] = None):
@@ -263,8 +280,8 @@ class ExplorationEnv:
         self.map_size, self.env_index, self.test = map_size, env_index, test
         self.dist = 0.0
         self._cfg = EnvConfig(map_size=map_size, num_landmarks=num_landmarks)
-        if max_poses is None:
-            max_poses = {20: 256, 40: 512, 60: 1536, 80: 3072, 100: 5008}.get(map_size, 2048)
+        if max_poses is None:     # the reference runs an episode until step > max_steps (exploration_env.py:168): no earlier cap here
+            max_poses = int(self._cfg.max_steps) + 8
         self._vec = VecExplorationEnv(1, cfg=self._cfg, max_poses=max_poses, device=device, test=test)
         self._np_random = np.random.default_rng()   # q20: training envs are seeded from an unseeded RNG
         self._max_steps = self._cfg.max_steps
@@ -305,6 +322,8 @@ class ExplorationEnv:
     def step(self, action):
         odom = torch.tensor([[action.x, action.y, action.theta]], dtype=torch.float64, device=self._vec.device)
         self._vec.step(odom)
+        if int(self._st("status")) == -4:      # DGE_ECAP: the trajectory buffer is full -- not an episode end the reference knows
+            raise DgeError(f"ExplorationEnv: pose capacity ({self._vec.eng.Tmax}) exhausted; create the env with a larger max_poses")
         self.dist = self.dist + math.sqrt(action.x ** 2 + action.y ** 2)
         return self._get_obs(), self.done(), {}
 

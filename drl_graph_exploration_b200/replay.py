@@ -14,7 +14,10 @@ The reference keeps a ``deque`` of ``(s_t, a_t, r_t, s_t1, terminal, fro_size1)`
   offsets, ``edge_attr``, ``batch``) with index arithmetic on the device -- one host sync for the two totals.
 
 A slot is re-used after ``G`` allocations; ``G = capacity + slack`` with ``slack`` >= the number of graphs that can be
-allocated between a transition's ``s_t`` and its completion (checked through allocation serials in ``sample``).
+allocated between a transition's ``s_t`` and its completion.  Every transition carries the allocation serials of its two
+graphs AS OF THE TIME THEY WERE STORED (the caller keeps the serial of ``s_t`` next to its slot while the transition is in
+flight); ``sample`` compares them with the ring on every call and accumulates the verdict in a device flag
+(``wrapped``, no host sync) that ``assert_intact`` reads.
 Everything is plain tensor plumbing, so the CPU tests exercise the same code.
 """
 from __future__ import annotations
@@ -37,6 +40,7 @@ class GraphReplay:
         self.t_s, self.t_s1, self.t_a = z((C,), torch.int64), z((C,), torch.int64), z((C,), torch.int64)
         self.t_r, self.t_term = z((C,), torch.float32), z((C,), torch.bool)
         self.t_serial = z((C, 2), torch.int64)      # allocation serials of (s, s1) at append time: detects slot re-use
+        self.wrapped = torch.zeros((), dtype=torch.bool, device=dev)   # a sampled transition referred to an overwritten graph
         self.size = 0          # live transitions (host)
         self.head = 0          # next transition position (host)
         self.allocated = 0     # graphs allocated so far (host); slot of allocation i is i % G
@@ -87,8 +91,11 @@ class GraphReplay:
         return b, n, noff
 
     # ------------------------------------------------------------- transitions ---
-    def append(self, slot_s, action_node, reward, slot_s1, terminal):
-        """Appends m transitions (device tensors [m]); the oldest are overwritten beyond ``capacity``."""
+    def append(self, slot_s, action_node, reward, slot_s1, terminal, serial_s=None, serial_s1=None):
+        """Appends m transitions (device tensors [m]); the oldest are overwritten beyond ``capacity``.  ``serial_s`` /
+        ``serial_s1``: allocation serials of the two graphs read when they were stored (``gserial[slot]`` right after
+        ``store_graphs``); without them the ring's current serials are recorded, which cannot see a slot that was recycled
+        while the transition was in flight."""
         m = int(slot_s.numel())
         if m == 0:
             return
@@ -96,7 +103,8 @@ class GraphReplay:
         pos = (self.head + torch.arange(m, device=dev)) % C
         self.t_s[pos], self.t_s1[pos], self.t_a[pos] = slot_s.long(), slot_s1.long(), action_node.long()
         self.t_r[pos], self.t_term[pos] = reward.float(), terminal.bool()
-        self.t_serial[pos, 0], self.t_serial[pos, 1] = self.gserial[slot_s.long()], self.gserial[slot_s1.long()]
+        self.t_serial[pos, 0] = self.gserial[slot_s.long()] if serial_s is None else serial_s.long()
+        self.t_serial[pos, 1] = self.gserial[slot_s1.long()] if serial_s1 is None else serial_s1.long()
         self.head = (self.head + m) % C
         self.size = min(C, self.size + m)
 
@@ -105,10 +113,17 @@ class GraphReplay:
         assert self.size >= k, "replay holds fewer transitions than the minibatch"
         idx = torch.randperm(self.size, device=self.device, generator=generator)[:k]
         s, s1 = self.t_s[idx], self.t_s1[idx]
-        if check:   # a stored graph was overwritten while a live transition still refers to it: slack too small
-            ok = (self.gserial[s] == self.t_serial[idx, 0]) & (self.gserial[s1] == self.t_serial[idx, 1])
-            assert bool(ok.all()), "graph ring wrapped over a live transition: increase `slack`"
+        # a stored graph was overwritten while a live transition still refers to it (slack too small): always tested, on the device
+        ok = (self.gserial[s] == self.t_serial[idx, 0]) & (self.gserial[s1] == self.t_serial[idx, 1])
+        self.wrapped |= ~ok.all()
+        if check:
+            self.assert_intact()
         return s, self.t_a[idx], self.t_r[idx], s1, self.t_term[idx]
+
+    def assert_intact(self):
+        """Raises if any minibatch sampled so far contained a transition whose graph slot had been recycled (one host sync)."""
+        if bool(self.wrapped):
+            raise RuntimeError("graph ring wrapped over a live transition: the replay trained on a wrong graph -- increase `slack`")
 
     _TENSORS = ("x", "ei", "ea", "gn", "ge", "gk", "gf", "gserial", "t_s", "t_s1", "t_a", "t_r", "t_term", "t_serial")
 

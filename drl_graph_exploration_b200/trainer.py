@@ -43,8 +43,9 @@ class VecDQNTrainer:
         self.dev = env.device
         B, eng = env.B, env.eng
         cap = int(replay_capacity if replay_capacity is not None else self.dqn.REPLAY_MEMORY)
-        # graphs allocated between a transition's s_t and its completion: <= B per tick x (longest plan + reset phase) ticks
-        self.replay = GraphReplay(cap, eng.node_cap_env, eng.edge_cap_env, self.dev, slack=B * 40)
+        # graphs allocated between a transition's s_t and its completion: <= B per tick x (longest line plan + reset phase) ticks
+        # (decisions without a frontier and transitions dropped by restore() allocate graphs too -- hence per tick, not per transition)
+        self.replay = GraphReplay(cap, eng.node_cap_env, eng.edge_cap_env, self.dev, slack=B * (env.cfg.max_plan_actions + 8) + 64)
         self.optimizer = torch.optim.Adam(policy_net.parameters(), lr=lr)
         self.target_net.load_state_dict(policy_net.state_dict())
         self.target_net.eval()
@@ -58,6 +59,8 @@ class VecDQNTrainer:
         self.ev_tick, self.ev_learn = (torch.cuda.Event(), torch.cuda.Event()) if self.overlap else (None, None)
         i64 = lambda v: torch.full((B,), v, dtype=torch.int64, device=self.dev)
         self.pend_slot, self.pend_a = i64(-1), i64(0)                  # in-flight transition of every env
+        self.pend_serial = i64(-1)                                     # allocation serial of its s_t, read when the graph was stored
+        self.ecap_episodes = torch.zeros((), dtype=torch.int64, device=self.dev)   # episodes cut short by the pose capacity (excluded from the replay)
         self.pend_r = torch.zeros(B, dtype=torch.float32, device=self.dev)
         self.pend_clo = torch.zeros(B, dtype=torch.bool, device=self.dev)
         self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
@@ -79,12 +82,15 @@ class VecDQNTrainer:
         if side_work is not None:
             self.ev_tick.record(main)                  # everything of the previous tick (replay writes, weight reads) is before this
         done_prev = st["done"].bool().clone()          # episodes that ended in the previous tick's step
+        ecap_prev = done_prev & (st["status"] == -4)   # ... because the trajectory buffer was full (DGE_ECAP): not a terminal state of the MDP
+        self.ecap_episodes = self.ecap_episodes + ecap_prev.sum()
         need = env.mark_pending().bool().clone()       # empty queue, not done, not in the reset phase
         # ---- step pipeline: restart finished episodes, one simulator step for every env with a queued action ----
         _check(eng._L.dge_reset_done_queued(eng._h, env.B, self._fo, 4, _stream_ptr(dev)), "dge_reset_done_queued")
         eng.step_queued()
         # ---- transitions that ended with the episode: terminal, s_t1 is not used by the target (policy.py:166-167) ----
-        ended = done_prev & (self.pend_slot >= 0)
+        ended = done_prev & (self.pend_slot >= 0) & ~ecap_prev      # a capacity stop drops its in-flight transition instead of storing y = r
+        self.pend_slot = torch.where(ecap_prev, torch.full_like(self.pend_slot, -1), self.pend_slot)
         # ---- decision round ----
         g = env.build_graph(need.to(torch.uint8))
         ng, n, e = g.sync_sizes()                      # host sync (sizes the GNN's GEMMs)
@@ -124,7 +130,8 @@ class VecDQNTrainer:
         if idx.numel():
             s1 = torch.where(closing, slot_new, self.pend_slot)[idx]
             term = (ended | self.pend_clo | (closing & (fro <= 0)))[idx]
-            rp.append(self.pend_slot[idx], self.pend_a[idx], self.pend_r[idx], s1, term)
+            ser1 = torch.where(closing, rp.gserial[slot_new.clamp(min=0)], self.pend_serial)[idx]     # s_t1 was stored in this tick (or is s_t itself)
+            rp.append(self.pend_slot[idx], self.pend_a[idx], self.pend_r[idx], s1, term, serial_s=self.pend_serial[idx], serial_s1=ser1)
             self.transitions += int(idx.numel())
             self.reward_sum += float(self.pend_r[idx].sum())
         self.pend_slot = torch.where(ended, torch.full_like(self.pend_slot, -1), self.pend_slot)
@@ -133,6 +140,7 @@ class VecDQNTrainer:
             start = need & (fro > 0)
             r = norm.gather(1, choice.clamp(0, norm.size(1) - 1).view(-1, 1)).view(-1).float()
             self.pend_slot = torch.where(start, slot_new, torch.where(need, torch.full_like(slot_new, -1), self.pend_slot))
+            self.pend_serial = torch.where(start, rp.gserial[slot_new.clamp(min=0)], self.pend_serial)
             self.pend_a = torch.where(start, key + choice, self.pend_a)
             self.pend_r = torch.where(start, r, self.pend_r)
             self.pend_clo = torch.where(start, clo.bool(), self.pend_clo)
@@ -230,6 +238,7 @@ class VecDQNTrainer:
             if self.train_steps > steps_before:
                 losses.append([self.dqn.step_t, self.last_loss])
             if self.dqn.step_t >= next_log:
+                self.replay.assert_intact()         # the per-minibatch serial test, read back once per log row
                 m = self.transitions - n0
                 if m > 0:
                     rewards.append([self.dqn.step_t, (self.reward_sum - r0) / m])

@@ -308,8 +308,9 @@ int dge_policy_tick(dge_handle h, const dge_graph_out *g, const dge_gcn_policy *
 
 /* ---- look-ahead roll-out rewards: replaces EMPlanner2D.simulations_reward
  * (Planner2D.cpp:1416-1468, `planner2d` binding Planner2D.cpp:90) and
- * ExplorationEnv.rewards_all_goals (exploration_env.py:145-162).  `dst` is a second engine of the
- * same capacities whose slots receive one clone per (env, frontier) of the envs selected by
+ * ExplorationEnv.rewards_all_goals (exploration_env.py:145-162).  `dst` is a second engine with the same
+ * map / landmark count and at least the pose capacity of `src` (give it max_poses + the longest line plan, so
+ * that a clone of an env near its capacity still runs its whole plan) whose slots receive one clone per (env, frontier) of the envs selected by
  * mask in the graph `g` of `src` (SLAM2D/VirtualMap/Simulator2D copies + set_copy_isam + queued
  * line plan).  The caller then advances `dst` with dge_step_queued until every queue is empty
  * (at most 2 + floor(diagonal / max_edge_length) + 1 calls) and collects the rewards.

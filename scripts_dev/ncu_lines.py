@@ -41,6 +41,6 @@ for r in srows[hi + 1:]:
     tot[0] += ie; tot[1] += s; tot[2] += f64
 lines = open(cu).read().split("\n")
 print(f"kernel {kname}: {tot[0]} warp instructions, {tot[2]} fp64 ({100.0 * tot[2] / max(tot[0], 1):.1f} %), {tot[1]} samples")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1 if os.environ.get("BY_SAMPLES") else 0])[:top]:
     txt = lines[k[1] - 1].strip()[:90] if k[0] == os.path.basename(cu) and 0 < k[1] <= len(lines) else ""
     print(f"{k[0]}:{k[1]:4d} inst {v[0]:10d} ({100.0 * v[0] / tot[0]:5.1f} %) fp64 {v[2]:9d} samples {v[1]:6d}  {txt}")

@@ -19,6 +19,14 @@ print("per-phase cycles: mean over active envs | slowest env | by T quantile")
 for i, n in enumerate(names):
     print(f"{n:16s} mean {d[act, i].mean():10.0f}  max {d[act, i].max():10.0f}")
 tot = d.sum(axis=1)
+light = clk[:, 10] == 1
+for name, sel in (("light (cached)", act & light), ("heavy (rebuild)", act & ~light)):
+    if sel.any():
+        print(f"-- {name}: {sel.sum()} envs, T mean {T[sel].mean():.1f} max {T[sel].max()}, n2 mean {clk[sel, 11].mean():.1f}; total mean {tot[sel].mean():.0f} max {tot[sel].max():.0f} cycles; "
+              + " ".join(f"{n.split('(')[0]}={d[sel, i].mean():.0f}/{d[sel, i].max():.0f}" for i, n in enumerate(names)))
+        top = np.argsort(-tot * sel)[:3]
+        for b in top:
+            print(f"     env {b} T {T[b]} n2 {clk[b, 11]} " + " ".join(f"{n.split('(')[0]}={d[b, i]:.0f}" for i, n in enumerate(names)), "total", tot[b])
 print(f"{'total':16s} mean {tot[act].mean():10.0f}  max {tot[act].max():10.0f}   (1965 MHz: max = {tot[act].max() / 1965:.1f} us)")
 for b in order[:4]:
     print(f"   inside phase B: pose recurrence (warp 0) {clk[b, 8] / T[b]:.0f} cycles/pose, border column 0 (incl. its waits on the recurrence) {clk[b, 9] / T[b]:.0f} cycles/pose")

@@ -2,6 +2,7 @@
 packing equals the reference's DataLoader collation (Batch.from_data_list), FIFO eviction equals the deque's popleft,
 targets equal DeepQ.build_targets (the literal restatement of policy.py:153-178)."""
 import numpy as np
+import pytest
 import torch
 
 from drl_graph_exploration_b200.data import Batch, Data
@@ -60,12 +61,32 @@ def test_transition_ring_is_fifo_like_the_deque():
     assert sorted(rp.t_a.tolist()) == [3, 4, 5, 6, 7]              # the three oldest were dropped
     s, a, r, s1, term = rp.sample(5, check=True)
     assert sorted(a.tolist()) == [3, 4, 5, 6, 7] and torch.equal(a.float(), r)
-    try:
-        rp.gserial[0] = 99                                         # the slot was re-allocated under a live transition
-        rp.sample(5, check=True)
-        raise RuntimeError("expected the serial check to fire")
-    except AssertionError:
-        pass
+    rp.gserial[0] = 99                                             # the slot was re-allocated under a live transition
+    rp.sample(5)                                                   # the test runs on every sample (device flag, no sync) ...
+    with pytest.raises(RuntimeError, match="wrapped"):
+        rp.assert_intact()                                         # ... and is read back on demand
+
+
+def test_serial_of_s_t_travels_with_the_in_flight_transition():
+    """a slot recycled BETWEEN storing s_t and closing its transition is only visible if the serial read at store time
+    is the one recorded -- reading the ring at append time records the new occupant's serial and the check passes silently."""
+    def ring():
+        rp = GraphReplay(capacity=4, node_cap=4, edge_cap=4, device="cpu", slack=0)      # G = 4 slots
+        x, ei, ea = torch.zeros(2, 5), torch.zeros(2, 0, dtype=torch.long), torch.zeros(0)
+        one = lambda: rp.store_graphs(x, ei, ea, torch.zeros(2, dtype=torch.long), torch.tensor([0, 2]), torch.tensor([0, 0]), torch.tensor([1]), torch.tensor([1]), 1)
+        return rp, one
+    for carry in (True, False):
+        rp, one = ring()
+        s = one(); ser = rp.gserial[s].clone()                     # s_t stored: slot 0, serial 0
+        for _ in range(4):
+            s1 = one()                                             # four more decisions elsewhere: slot 0 is recycled (serial 4)
+        rp.append(s, torch.tensor([1]), torch.tensor([0.5]), s1, torch.tensor([False]), serial_s=ser if carry else None)
+        rp.sample(1)
+        if carry:
+            with pytest.raises(RuntimeError, match="wrapped"):
+                rp.assert_intact()
+        else:
+            rp.assert_intact()                                     # (the old behaviour: blind to it)
 
 
 def test_vectorised_targets_equal_build_targets():

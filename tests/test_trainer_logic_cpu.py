@@ -55,7 +55,10 @@ class _Env:
         self.done = torch.zeros(B, dtype=torch.uint8)
         self.forced = np.zeros(B, dtype=np.int64)
         lib = types.SimpleNamespace(dge_reset_done_queued=self._reset_done)
-        self.eng = types.SimpleNamespace(Lt=3, node_cap_env=12, edge_cap_env=24, state={"done": self.done}, _L=lib, _h=None, step_queued=self._step)
+        self.status = torch.zeros(B, dtype=torch.int32)
+        self.eng = types.SimpleNamespace(Lt=3, node_cap_env=12, edge_cap_env=24, state={"done": self.done, "status": self.status}, _L=lib, _h=None, step_queued=self._step)
+        from drl_graph_exploration_b200.config import EnvConfig
+        self.cfg = EnvConfig(map_size=20)
         self.graph = _Graph(B, 3)
         self.rollout_steps = 0
 
