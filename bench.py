@@ -130,31 +130,41 @@ class L2Flush:
 
 
 # ------------------------------------------------------------------ CPU reference arm ---
-def cpu_reference(*a, **k):
-    """The reference path on host cores (oracle/cpu_loop.py): CPU-oracle envs on a C++ worker pool + torch-CPU GCN."""
-    from oracle.cpu_loop import cpu_reference as impl
-    return impl(*a, **k)
+REF_PREROLL = 200      # ticks before either CPU leg is timed: the episodes de-synchronise and the mean trajectory length becomes stationary
+
+
+def timed_reference(**k):
+    """The reference path on host cores (oracle/cpu_loop.py): all 256 CPU-oracle envs on a C++ worker pool + ONE torch-CPU GCN forward
+    per decision round, overlapped with the stepping of the other envs."""
+    from oracle.cpu_loop import timed_reference as impl
+    return impl(MAP_SIZE, N_LANDMARKS, ENVS_PER_GPU, os.cpu_count() or 1, MAX_POSES, **k)
 
 
 def run_reference(args):
+    """--impl reference: a step = `tps` ticks of all 256 envs, tps chosen from the warm-up so that the K timed steps last >= 2 s."""
     threads = os.cpu_count() or 1
-    n_envs = min(ENVS_PER_GPU, max(threads, 8))
-    run_tick, count = cpu_reference(MAP_SIZE, N_LANDMARKS, n_envs, threads, MAX_POSES)
+    from oracle.cpu_loop import cpu_reference
+    run_tick, count = cpu_reference(MAP_SIZE, N_LANDMARKS, ENVS_PER_GPU, threads, MAX_POSES)
+    for _ in range(REF_PREROLL):
+        run_tick()
+    t0 = time.perf_counter()
     for _ in range(args.warmup):
         run_tick()
-    c0, t0 = count(), time.perf_counter()
-    for _ in range(args.steps):
-        run_tick()
+    tick_s = (time.perf_counter() - t0) / args.warmup
+    tps = int(max(1, min(50, math.ceil(2.0 / (args.steps * tick_s)))))
+    c0, t0, sT = count(), time.perf_counter(), 0.0
+    for _ in range(args.steps * tps):
+        run_tick(); sT += run_tick.mean_poses()
     dt = time.perf_counter() - t0
     val = (count() - c0) / dt
-    sample = f"{n_envs} of {ENVS_PER_GPU} envs x {args.steps} ticks, CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN"
+    sample = (f"all {ENVS_PER_GPU} envs x {args.steps * tps} ticks ({dt:.1f} s, {tps} ticks per step) after {REF_PREROLL} pre-roll ticks, mean trajectory length "
+              f"{sT / (args.steps * tps):.1f}: CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN per decision round (overlapped with the stepping)")
     print(json.dumps({"impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "sample": sample},
+                      "config": {"workload": WORKLOAD, "sample": sample, "ticks_per_step": tps, "timed_seconds": dt},
                       "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
                       "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-
 
 
 def finish(world, dist):
@@ -184,13 +194,20 @@ def _dist_setup():
 
 
 def run_train(args):
+    rank, world, local, dist = _dist_setup()
+    out = measure_train(args, rank, world, local, dist, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps(out))
+    finish(world, dist)
+
+
+def measure_train(args, rank, world, local, dist, steps, warmup):
     """BASELINE configs[2] (C3): 256 envs per GPU, 40x40 map, DQN training with batched roll-out rewards, device replay and
     one NCCL all-reduce of the flat gradient bucket per gradient step.  A step = one tick of trainer.VecDQNTrainer."""
     from drl_graph_exploration_b200 import Networks
     from drl_graph_exploration_b200.config import EnvConfig
     from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv
     from drl_graph_exploration_b200.trainer import VecDQNTrainer
-    rank, world, local, dist = _dist_setup()
     ms, B = 40, ENVS_PER_GPU
     cfg = EnvConfig(map_size=ms)
     if args.train_gemm != "fp32":
@@ -203,7 +220,7 @@ def run_train(args):
     for _ in range(40):                       # prefill the replay (untimed): every rank needs one minibatch of transitions
         tr.tick(learn=False)
     assert tr.replay.size >= tr.dqn.BATCH, "prefill too short"
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         tr.tick(learn=True)
     torch.cuda.synchronize()
     if world > 1:
@@ -215,7 +232,7 @@ def run_train(args):
     d0, t0, r0, k0 = tr.decisions, tr.train_steps, tr.rollout_steps, tr.rollout_clones
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         tr.tick(learn=True)
     b.record()
     torch.cuda.synchronize()
@@ -228,12 +245,28 @@ def run_train(args):
     v = torch.tensor([c1[0] - c0[0], tr.decisions - d0, tr.train_steps - t0, tr.rollout_steps - r0, tr.rollout_clones - k0], dtype=torch.float64, device=env.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    # the one collective of the path, timed alone: the 4.0 MB flat gradient bucket, CUDA events, max over ranks
+    ar_us = None
+    if world > 1:
+        flat = tr.dqn._bucket.flat
+        for _ in range(5):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize(); dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            dist.all_reduce(flat)
+        b.record(); torch.cuda.synchronize()
+        tt = torch.tensor([a.elapsed_time(b) / 20 * 1e3], dtype=torch.float64, device=env.device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ar_us = float(tt.item())
+    out = None
     if rank == 0:
         sec = float(t.item()) / 1e3
-        steps, dec, tsteps, rsteps, clones = (float(x) for x in v.tolist())
+        env_steps, dec, tsteps, rsteps, clones = (float(x) for x in v.tolist())
         bsz = tr.dqn.BATCH
-        out = {"metric": "env-steps/sec (DQN training)", "value": steps / sec, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 simulator / f32 GNN",
+        out = {"metric": "env-steps/sec (DQN training)", "value": env_steps / sec, "unit": "env-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+               "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 simulator / f32 GNN",
                "data": "synthetic",
                "config": {"workload": f"{B} envs/GPU, {ms}x{ms} map, {cfg.n_landmarks} landmarks, DQN+GCN training (BASELINE configs[2])", "batch_graphs_per_rank": bsz,
                           "train_steps_per_tick": args.train_steps_per_tick, "train_gemm": args.train_gemm,
@@ -241,9 +274,10 @@ def run_train(args):
                           "collective": "one all-reduce of the 4.0 MB flat gradient bucket per gradient step" if world > 1 else "none (1 rank)"},
                "decisions_per_s": dec / sec, "train_steps_per_s": tsteps / sec / world, "rollout_clone_steps_per_s": None,
                "gnn_samples_per_s": {"forward_acting": dec / sec, "forward_target": tsteps * bsz / sec, "forward_backward": tsteps * bsz / sec},
-               "rollout": {"clones_per_s": clones / sec, "clone_engine_ticks_per_s": rsteps / sec}, "loss": tr.last_loss, "epsilon": tr.epsilon, "clocks": clocks}
-        print(json.dumps(out))
-    finish(world, dist)
+               "rollout": {"clones_per_s": clones / sec, "clone_engine_ticks_per_s": rsteps / sec}, "loss": tr.last_loss, "epsilon": tr.epsilon, "clocks": clocks,
+               "allreduce_us": ar_us}
+    env.close()
+    return out
 
 
 def synth_graph_batch(n_graphs, sizes, rng, device, n_landmarks=8):
@@ -368,6 +402,48 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
     return None
 
 
+def measure_c4_sweep(dev, n=1024, Ts=(32, 64, 128, 256, 512, 1024), reps=10):
+    """BASELINE configs[3] (C4): the covariance-propagation kernel (k_vmap_env: occupancy + ordered covariance-intersection fold) alone,
+    1024 envs, 60x60 map (V = 2500 cells), 200 landmarks, T synthetic poses per env (drl_graph_exploration_b200/synth.py), through
+    the C ABI (dge_virtual_map_rebuild) on pre-allocated buffers.  Algorithmic bytes per env-rebuild (SURVEY 8(d), fp64 state):
+    2 (48 T + 20 V + 8 L).  L2 flushed before every timed launch; median of `reps` launches, CUDA events on the launching stream."""
+    import ctypes
+    from drl_graph_exploration_b200.config import EnvConfig
+    from drl_graph_exploration_b200.engine import _ptr, _stream_ptr, load_library
+    from drl_graph_exploration_b200.synth import synth_states
+    pk, pk_kind = peaks()
+    cfg = EnvConfig(map_size=60, num_landmarks=200)
+    cs = cfg.to_struct()
+    L, V = 200, cfg.rows * cfg.cols
+    lib = load_library()
+    flush = L2Flush(dev)
+    rows = []
+    for T in Ts:
+        pose, _, cov6, _, lm = synth_states(cfg, n, T, L, seed=T)
+        tp, tc, tl = (torch.as_tensor(a, device=dev).contiguous() for a in (pose, cov6, lm))
+        prob = torch.empty(n, V, dtype=torch.float64, device=dev); vinfo = torch.empty(n, V, 3, dtype=torch.float64, device=dev)
+        seen = torch.empty(n, V, dtype=torch.int32, device=dev)
+        ws = torch.zeros(lib.dge_virtual_map_rebuild_ws_doubles(n, T), dtype=torch.float64, device=dev)
+        call = lambda s: lib.dge_virtual_map_rebuild(ctypes.byref(cs), n, T, _ptr(tp), _ptr(tc), L, _ptr(tl), _ptr(prob), _ptr(vinfo), _ptr(s), _ptr(ws), _stream_ptr(dev))
+        for _ in range(3):
+            assert call(seen) == 0
+        torch.cuda.synchronize()
+        visits = float(seen.clamp(min=0).sum())
+        ts = []
+        for _ in range(reps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); call(None); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        by = 2.0 * (48 * T + 20 * V + 8 * L) * n
+        gbs = by / (ms * 1e-3) / 1e9
+        rows.append({"T": T, "us": 1e3 * ms, "algorithmic_MB": by / 1e6, "GBps": gbs, "frac": gbs / pk["hbm_gbs"], "pair_visits": visits,
+                     "Gvisits_per_s": visits / ms / 1e6})
+    return {"workload": f"{n} envs, 60x60 map (V = {V}), {L} landmarks, k_vmap_env alone (BASELINE configs[3])", "peak_GBps": pk["hbm_gbs"], "peak_kind": pk_kind,
+            "bytes_per_env": "2 (48 T + 20 V + 8 L)", "l2": L2Flush.HOW, "rows": rows}
+
+
 # ------------------------------------------------------------------------- GPU arm ---
 class GpuLoop:
     def __init__(self, device, seed0, overlap=True, device_tick=True):
@@ -414,6 +490,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gnn", action="store_true", help="skip the C5 GNN samples/sec measurement appended to the default line")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 covariance-propagation roofline sweep appended to the default line (N = 1)")
+    ap.add_argument("--no-train", action="store_true", help="skip the C3 DQN-training measurement appended to the default line")
     ap.add_argument("--no-overlap", action="store_true", help="run the step and policy pipelines on one stream (A/B of the overlap)")
     ap.add_argument("--per-launch", action="store_true", help="policy loop: the per-launch schedule with one size sync per tick instead of dge_policy_tick (A/B)")
     ap.add_argument("--ticks-per-step", type=int, default=50, help="policy loop: ticks per bench step (every tick is timed separately)")
@@ -571,17 +649,10 @@ def main():
         out["e2e"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_envs = min(ENVS_PER_GPU, max(threads, 8))
-        run_tick, count = cpu_reference(MAP_SIZE, N_LANDMARKS, n_envs, threads, MAX_POSES, seed0=777)
-        for _ in range(3):
-            run_tick()
-        c0, t0 = count(), time.perf_counter()
-        nt = 0
-        while time.perf_counter() - t0 < 15.0 and nt < 4000:
-            run_tick(); nt += 1
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": (count() - c0) / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                               "sample": f"{n_envs} of {ENVS_PER_GPU} envs x {nt} ticks ({dt:.1f} s): CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN"}
+        r = timed_reference(preroll=REF_PREROLL, warmup=3, min_ticks=10, min_seconds=12.0, max_seconds=30.0, seed0=777)
+        out["cpu_baseline"] = {"value": r["value"], "unit": "env-steps/s", "cores": threads, "kind": "port",
+                               "sample": f"all {ENVS_PER_GPU} envs x {r['ticks']} ticks ({r['seconds']:.1f} s) after {REF_PREROLL} pre-roll ticks, mean trajectory length "
+                                         f"{r['mean_poses']:.1f}: CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN per decision round (overlapped with the stepping)"}
     elif rank == 0:
         out["cpu_baseline"] = None
     if not args.no_gnn:
@@ -594,6 +665,22 @@ def main():
                              "forward_backward_graphs_per_s": g["forward_backward"]["graphs_per_s"],
                              "forward_backward_ms_per_batch": g["forward_backward"]["ms_per_batch"], "train_gemm": args.train_gemm,
                              "tensor_roofline": g["roofline"], "cpu_baseline": g.get("cpu_baseline")}
+    if not args.no_c4 and world == 1:
+        try:
+            loop.env.close()
+        except Exception:
+            pass
+        out["c4_sweep"] = measure_c4_sweep(loop.dev)
+    if not args.no_train:
+        # BASELINE configs[2]: DQN training (the path's one collective, the gradient all-reduce, is in this leg when N > 1)
+        try:
+            loop.env.close()
+        except Exception:
+            pass
+        tr = measure_train(args, rank, world, local, dist, steps=100, warmup=10)
+        if rank == 0:
+            out["train_c3"] = {k: tr[k] for k in ("value", "unit", "ms_per_step", "decisions_per_s", "train_steps_per_s", "allreduce_us", "loss")}
+            out["train_c3"].update(workload=tr["config"]["workload"], schedule=tr["config"]["schedule"], collective=tr["config"]["collective"], ticks=100)
     if rank == 0:
         print(json.dumps(out))
     finish(world, dist)

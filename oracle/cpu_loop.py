@@ -16,41 +16,74 @@ from oracle.oracle import lib as _lib
 MAX_ACTIONS = 64
 
 
-def cpu_reference(map_size: int, n_landmarks: int, n_envs: int, threads: int, max_poses: int, seed0: int = 0, gnn_threads: int | None = None):
+def cpu_reference(map_size: int, n_landmarks: int, n_envs: int, threads: int, max_poses: int, seed0: int = 0, gnn_threads: int | None = None,
+                  overlap: bool = True):
+    """All ``n_envs`` envs live on the pool (n_envs / threads per worker).  One tick, like the GPU arm: the envs whose action list
+    ran empty get a decision -- graphs built on the pool, ONE GCN forward over the whole decision batch on the torch threads -- while
+    (``overlap``) the other envs are already stepping on the pool; the deciding envs step when their plans are there."""
+    import threading
     cfg = EnvConfig(map_size=map_size, num_landmarks=n_landmarks)
     L = _lib()
     cs = cfg.to_struct()
     torch.manual_seed(0)
     model = gnn_ref.GCN().eval()
-    torch.set_num_threads(gnn_threads or min(threads, 32))
+    torch.set_num_threads(gnn_threads or min(threads, 64))
     vp = ctypes.c_void_p
-    handles = (vp * n_envs)(*[L.orc_create(ctypes.byref(cs)) for _ in range(n_envs)])
+    handles = [L.orc_create(ctypes.byref(cs)) for _ in range(n_envs)]
     p = lambda a: a.ctypes.data_as(vp)
-    state = {"next_seed": seed0, "steps": 0}
+    state = {"next_seed": seed0, "steps": 0, "sumT": 0}
+    harr = lambda idx: (vp * len(idx))(*[handles[i] for i in idx])
 
     def fresh(idx):
         idx = np.asarray(idx, dtype=np.int64)
         seeds = np.arange(state["next_seed"], state["next_seed"] + len(idx), dtype=np.uint32)
         state["next_seed"] += len(idx)
         starts = np.array([start_pose_for_seed(int(s), map_size, cfg.ext) for s in seeds], dtype=np.float64)
-        hs = (vp * len(idx))(*[handles[i] for i in idx])
-        L.orc_batch_fresh(hs, p(seeds), p(starts), len(idx), threads)
+        L.orc_batch_fresh(harr(idx), p(seeds), p(starts), len(idx), threads)
 
     fresh(range(n_envs))
     queues = [[] for _ in range(n_envs)]
-    odoms = np.zeros((n_envs, 3)); done = np.zeros(n_envs, dtype=np.uint8); Ts = np.zeros(n_envs, dtype=np.int32)
+    Ts = np.zeros(n_envs, dtype=np.int32)
+
+    def step(idx):
+        """one simulator step of the envs ``idx`` on the pool; finished episodes restart"""
+        if not idx:
+            return
+        odoms = np.stack([queues[i].pop(0) for i in idx]).astype(np.float64)
+        done = np.zeros(len(idx), dtype=np.uint8); T = np.zeros(len(idx), dtype=np.int32)
+        L.orc_batch_step(harr(idx), p(odoms), len(idx), threads, p(done), p(T))
+        state["steps"] += len(idx)
+        Ts[idx] = T
+        redo = [i for k, i in enumerate(idx) if done[k] or T[k] >= max_poses - 1]
+        if redo:
+            fresh(redo)
+            for i in redo:
+                queues[i] = []
+                Ts[i] = 5
 
     def run_tick():
         need = [i for i in range(n_envs) if not queues[i]]
+        ready = [i for i in range(n_envs) if queues[i]]
         if need:
-            hs = (vp * len(need))(*[handles[i] for i in need])
+            hs = harr(need)
             sizes = np.zeros((len(need), 4), dtype=np.int32)
             L.orc_batch_graph_build(hs, len(need), threads, p(sizes))
             ntot, etot = int(sizes[:, 0].sum()), int(sizes[:, 3].sum())
             x = np.zeros((ntot, 5), dtype=np.float32); ei = np.zeros((2, etot), dtype=np.int64); ea = np.zeros(etot, dtype=np.float32)
             L.orc_batch_graph_fetch(len(need), p(x), p(ei), p(ea), ctypes.c_int64(etot))
-            with torch.no_grad():
-                q = model(gnn_ref.Graph(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ea)), 0.0).view(-1).numpy()
+            box = {}
+
+            def forward():
+                with torch.no_grad():
+                    box["q"] = model(gnn_ref.Graph(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ea)), 0.0).view(-1).numpy()
+
+            if overlap:       # the GCN forward (torch threads, GIL released inside the kernels) beside the pool stepping the other envs
+                th = threading.Thread(target=forward); th.start()
+                step(ready); ready = []
+                th.join()
+            else:
+                forward()
+            q = box["q"]
             choice = np.full(len(need), -1, dtype=np.int32)
             off = 0
             for k in range(len(need)):
@@ -62,17 +95,32 @@ def cpu_reference(map_size: int, n_landmarks: int, n_envs: int, threads: int, ma
             L.orc_batch_line_plan(hs, len(need), p(choice), MAX_ACTIONS, p(plans), p(counts))
             for k, i in enumerate(need):
                 queues[i] = [plans[k, a] for a in range(counts[k])] if counts[k] > 0 else [np.array([0.0, 0.0, 0.5])]
-        for i in range(n_envs):
-            odoms[i] = queues[i].pop(0)
-        L.orc_batch_step(handles, p(odoms), n_envs, threads, p(done), p(Ts))
-        state["steps"] += n_envs
-        redo = [i for i in range(n_envs) if done[i] or Ts[i] >= max_poses - 1]
-        if redo:
-            fresh(redo)
-            for i in redo:
-                queues[i] = []
+        step(ready + need)
+        state["sumT"] = int(Ts.sum())
 
+    run_tick.mean_poses = lambda: state["sumT"] / n_envs
     return run_tick, (lambda: state["steps"])
+
+
+def timed_reference(map_size, n_landmarks, n_envs, threads, max_poses, preroll, warmup, min_ticks, min_seconds, max_seconds, seed0=0):
+    """Pre-roll (episodes de-synchronise: the trajectory-length distribution must be the steady state the GPU arm is timed in), warm up,
+    then time ticks until BOTH ``min_ticks`` and ``min_seconds`` are reached (or ``max_seconds``).  -> dict"""
+    import time
+    run_tick, count = cpu_reference(map_size, n_landmarks, n_envs, threads, max_poses, seed0=seed0)
+    hist = []
+    for i in range(preroll):
+        run_tick()
+        if (i + 1) % 50 == 0:
+            hist.append(round(run_tick.mean_poses(), 1))
+    for _ in range(warmup):
+        run_tick()
+    c0, t0, nt, sT = count(), time.perf_counter(), 0, 0.0
+    while True:
+        run_tick(); nt += 1; sT += run_tick.mean_poses()
+        dt = time.perf_counter() - t0
+        if (nt >= min_ticks and dt >= min_seconds) or dt >= max_seconds:
+            break
+    return {"value": (count() - c0) / dt, "ticks": nt, "seconds": dt, "mean_poses": sT / nt, "preroll_mean_poses": hist, "n_envs": n_envs, "threads": threads}
 
 
 def cpu_gnn_baseline(batches, threads: int, budget_s: float = 8.0):
