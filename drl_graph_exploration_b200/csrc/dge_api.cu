@@ -443,14 +443,14 @@ extern "C" int dge_line_plan_host(dge_handle h, const double *goal_host, const u
 }
 
 extern "C" int dge_virtual_map_rebuild(const dge_config *cfg, int n, int T, const double *pose, const double *cov, int L, const double *lm,
-                                       double *prob, double *vinfo, int32_t *seen, double *ws /* [n*T*12 + n*nchunk*4] */, void *stream) {
+                                       double *prob, double *vinfo, int32_t *seen, double *ws /* dge_virtual_map_rebuild_ws_doubles(n, T) */, void *stream) {
   if (!cfg || n <= 0 || T <= 0 || !pose || !cov || !prob || !vinfo || !ws) return DGE_EINVAL;
   double *prep = ws, *cbox = ws + (size_t)n * T * dge_vmap_prep_width();
   const int rc = dge_vmap_standalone(cfg, n, T, pose, cov, L, lm, prob, vinfo, seen, prep, cbox, static_cast<cudaStream_t>(stream));
   return rc ? fail(rc, "dge_virtual_map_rebuild") : DGE_OK;
 }
 extern "C" int64_t dge_virtual_map_rebuild_ws_doubles(int n, int T) {
-  return (int64_t)n * T * dge_vmap_prep_width() + (int64_t)n * dge_vmap_nchunk(T) * 4;
+  return (int64_t)n * T * dge_vmap_prep_width() + (int64_t)n * (dge_vmap_nchunk(T) * 4 + 12);
 }
 
 extern "C" int dge_get_state(dge_handle h, dge_state_view *o) {

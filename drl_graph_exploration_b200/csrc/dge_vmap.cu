@@ -16,6 +16,8 @@
 // The arithmetic is the closed form of the reference's expression
 //   Hl^-1 (R + Hx Sigma Hx^T) Hl^-T = Rot (M^-1 R M^-T + A Sigma A^T) Rot^T
 // (Hl = M Rot^T, Hx = M A), evaluated in fp64.
+#include <cstdlib>
+
 #include "dge_internal.cuh"
 
 namespace {
@@ -260,23 +262,26 @@ __global__ void __launch_bounds__(256) k_vmap_metrics(dge_config cfg, DgeDims d,
 }
 
 // =============================================================== fused, pose-centric rebuild ===
-// k_vmap_env: ONE CTA per environment does the whole rebuild -- pose digest (k_vmap_prep), occupancy + ordered
-// covariance-intersection fold (k_vmap_cells) and the map metrics (k_vmap_metrics) -- in one launch.
+// k_vmap_env: ONE CTA per environment does the whole rebuild -- pose digest, occupancy + ordered covariance-intersection
+// fold and the map metrics -- in one launch, the map state (2x2 information + visibility count + flags, 28 bytes per cell)
+// living in shared memory from the first pose to the write-out.
 //
-// The cell-centric kernel above tests every (pose, cell) pair of a tile for proximity (1 visit per ~100 tests at
-// BASELINE config C4).  Here the work is driven by the poses: a pose can only touch the W x W block of cells around
-// it (W = 2 ceil(max_range / res) + 1 = 7), and a visit is split in two:
-//   * PREDICT (order-independent, ~3/4 of the arithmetic): for every (pose, cell of its block) pair the gates and the
-//     predicted information Lambda_new = (Hl^-1 (R + Hx Sigma Hx^T) Hl^-T)^-1 (VirtualMap.cpp:213-229) -- one thread per
-//     pair, every warp of the CTA busy, KC poses (a chunk) at a time into a shared-memory record buffer;
-//   * FOLD (order-dependent, VirtualMap.cpp:307-313 / 364-377): one thread per cell of the chunk's bounding box walks the
-//     chunk's poses in trajectory order and folds the records that hit its cell into the cell state (2x2 information,
-//     visibility count, flags), which lives in shared memory for the whole map (28 bytes per cell).
-// The record buffer is double-buffered: the prediction of chunk i+1 is issued in front of the fold of chunk i (one barrier per
-// chunk), so the latency-bound fold chains of a few warps run beside the throughput-bound prediction of all of them.
-// HBM traffic is the algorithmic minimum: the trajectory is read once (digest written and re-read through L1/L2),
-// every output byte is written once.  Arithmetic, predicates and summation orders are those of the kernels above
-// (bit-identical results, same parity tests).
+// The work is driven by the poses: a pose can only touch the W x W block of cells around it (W = 2 ceil(max_range / res) + 1
+// = 7), and a visit is split in two.  Up front, one thread per pose digests the trajectory (cos / sin, covariance, det gate,
+// first row / column of the block) into scratch: the transcendental latency is paid once, in parallel.  Then, per chunk of
+// KC <= 16 consecutive poses (digest rows scratch -> registers -> shared memory, one chunk ahead):
+//   * PREDICT (order-independent, ~3/4 of the arithmetic): every warp takes a contiguous slice of the chunk's (pose, cell)
+//     pairs; a branch-free GATE pass (range / field-of-view predicates, GR pairs per lane side by side; the 1e-9 bands around
+//     the range limits and the rear wedge go to a rare exact path with the reference's own sqrt / atan2 comparisons; integer
+//     visibility count) ballot-compacts the pairs that update a cell into a warp-private list, and the SPD pass -- the predicted
+//     information Lambda_new = (Hl^-1 (R + Hx Sigma Hx^T) Hl^-T)^-1 (VirtualMap.cpp:213-229) -- runs on the dense list only
+//     (no lane of an fp64 instruction idles on a pair outside the sensor disc).  Records go to a shared-memory buffer; a pair
+//     without update leaves a negative sentinel.
+//   * FOLD (order-dependent, VirtualMap.cpp:307-313 / 364-377): one thread per cell of the chunk's box collects the chunk's
+//     poses that hit its cell (bit mask from the sentinels), then folds their records in trajectory order, the next record
+//     loaded in front of the current fold's dependent chain.
+// Two barriers per chunk.  HBM traffic is the algorithmic minimum: the trajectory is read once, every output byte is
+// written once -- the information matrices by bulk copies (cp.async.bulk shared -> global) of the cell-interleaved state.
 
 // reciprocal for the fused kernel: hardware seed (rcp.approx.ftz.f64, ~2^-23) + two Newton steps = full double accuracy
 // up to ~2 ulp, half the dependent latency of the IEEE division sequence (operands here are O(1e-3..1e15): no
@@ -289,15 +294,16 @@ __device__ __forceinline__ double vm_rcp(double x) {
   return r;
 }
 constexpr unsigned ST_UPD = 1u << 30, ST_LM = 1u << 31, ST_CNT = ST_UPD - 1;
-constexpr int ENV_THREADS = 256;
+constexpr int DIG_W = 12;          // doubles per digested pose in shared memory: x y c s Sxx Sxy Sxt Syy Syt Stt valid (fr|fc)
 
 struct EnvArgs {
   VmapCfg c;
   int Tstride, Tfixed, Lstride, Lfixed, hw, W;         // hw = ceil(max_range / res), W = 2 hw + 1
-  int kc;                                              // poses per chunk
+  int kc;                                              // poses per chunk (<= 16)
+  int ppw;                                             // (pose, cell) pairs per warp and chunk = ceil(kc W^2 / warps), rounded up to 8
   const int32_t *n_poses;
   const double *pose, *cov, *info;                     // [n,Tstride,3], [n,Tstride,6], nullable [n,Tstride,6]
-  double *prep;                                        // [n,Tstride,PREP_W] scratch (L1/L2 resident)
+  double *prep;                                        // [n,Tstride,PREP_W] digest scratch (written and re-read by the env's CTA: L2)
   const double *lm; const uint8_t *lm_obs;             // [n,Lstride,2], nullable [n,Lstride]
   double *prob, *vinfo; int32_t *seen;                 // outputs; seen nullable
   const uint8_t *mask;
@@ -306,69 +312,67 @@ struct EnvArgs {
   const int32_t *sim_step, *status, *meas_ptr; const double *dist; double *metrics; uint8_t *done;
   unsigned long long *counters; const uint8_t *step_kind;
   long long *clocks;                                   // nullable [n,4]: SM clock at start / after digest / after fold / end (thread 0)
+  long long *phase;                                    // nullable [n,8]: cycles summed over the chunks (thread 0): gate, SPD, wait, fold, wait
   const int32_t *order;                                // nullable [n]: block -> env (cost-ordered placement of the step kernels, dge_slam.cu)
 };
 
-template <int WT>   // WT = block width W when known at compile time (7 for the reference's sensor / resolution), 0 = generic
-__global__ void __launch_bounds__(ENV_THREADS, 2) k_vmap_env(EnvArgs a) {
+template <int WT, int NTHR>   // WT = block width W when known at compile time (7 for the reference's sensor / resolution), 0 = generic
+__global__ void __launch_bounds__(NTHR, 2) k_vmap_env(EnvArgs a) {
+  constexpr int NWARP = NTHR / 32;
+  constexpr int GR = NTHR >= 512 ? 2 : 4;                // pairs a lane gates side by side
   const int b = a.order ? a.order[blockIdx.x] : blockIdx.x;
   if (a.mask && !a.mask[b]) return;
   const VmapCfg &c = a.c;
   const int T = a.n_poses ? a.n_poses[b] : a.Tfixed;
-  const int tid = threadIdx.x, nthr = ENV_THREADS;
-  const int V = c.rows * c.cols, W = WT ? WT : a.W, WW = W * W, KC = a.kc, hw = a.hw;
+  const int tid = threadIdx.x, nthr = NTHR, lane = tid & 31, warp = tid >> 5;
+  const int V = c.rows * c.cols, W = WT ? WT : a.W, WW = W * W, KC = a.kc, hw = a.hw, PPW = a.ppw;
   extern __shared__ __align__(16) unsigned char vm_smem[];
-  double *sxx = reinterpret_cast<double *>(vm_smem), *sxy = sxx + V, *syy = sxy + V;
-  unsigned *sst = reinterpret_cast<unsigned *>(syy + V);       // count | ST_UPD | ST_LM
-  unsigned *smk = sst + ((V + 1) & ~1);                        // per cell: which poses of the chunk update it (bit kk; low / high half = buffer 0 / 1)
-  int *s_fr = reinterpret_cast<int *>(smk + ((V + 1) & ~1));   // [Tstride] first row of every pose's block
-  int *s_fc = s_fr + ((a.Tstride + 1) & ~1);                   // [Tstride] first column
-  double *s_red = reinterpret_cast<double *>(s_fc + ((a.Tstride + 1) & ~1));   // [256] + 2 x int[256]
-  double *rec0 = s_red + 256 + 256;                            // 2 x { nxx, nxy, nyy, ndet [KC*WW] }
-  const int RS = KC * WW;                                      // records per buffer
-  int4 *s_box = reinterpret_cast<int4 *>((reinterpret_cast<uintptr_t>(rec0 + 8 * RS) + 15) & ~uintptr_t(15));   // [ceil(Tstride / KC)] cell box [r0, r1) x [c0, c1) of every chunk
+  double *sinf = reinterpret_cast<double *>(vm_smem);          // [V][3] xx xy yy, cell-interleaved = the layout of the output
+  unsigned *sst = reinterpret_cast<unsigned *>(sinf + 3 * (size_t)V);   // count | ST_UPD | ST_LM
+  double *dig = reinterpret_cast<double *>(sst + ((V + 1) & ~1));        // [2][KC][DIG_W]
+  const int RS = KC * WW;                                       // records per chunk
+  double *rxx = dig + 2 * KC * DIG_W, *rxy = rxx + RS, *ryy = rxy + RS;  // records (one buffer: predict and fold are separated by barriers)
+  double *s_red = ryy + RS;                                     // [256] + 2 x int[256]
+  int *s_fr = reinterpret_cast<int *>(s_red + 256 + 256);       // [2][16] first row of every pose's block
+  int *s_fc = s_fr + 32;                                        // [2][16] first column
+  int4 *s_box = reinterpret_cast<int4 *>((reinterpret_cast<uintptr_t>(s_fc + 32) + 15) & ~uintptr_t(15));   // [2] cell box [r0, r1) x [c0, c1) of the chunk
+  unsigned short *s_list = reinterpret_cast<unsigned short *>(s_box + 2);   // [NWARP][PPW] compacted pair indices
 
   if (a.clocks && tid == 0) a.clocks[4 * b] = clock64();
-  // ---- init cell state, digest the trajectory -------------------------------------------------------------
-  for (int i = tid; i < V; i += nthr) { sxx[i] = c.i0; sxy[i] = 0.0; syy[i] = c.i0; sst[i] = 0u; smk[i] = 0u; }
   const double *ps = a.pose + (size_t)b * a.Tstride * 3, *cv = a.cov + (size_t)b * a.Tstride * 6;
+  const double *pinfo = a.info ? a.info + (size_t)b * a.Tstride * 6 : nullptr;
+  const int nch = (T + KC - 1) / KC;
   double *pr = a.prep + (size_t)b * a.Tstride * PREP_W;
-  for (int k = tid; k < T; k += nthr) {
+
+  // ---- init cell state, then (one barrier later: the landmark flags need it) the digest of the whole trajectory, one thread per pose,
+  // and the landmark cells -- their cold global loads are in flight together ----------------------------------------------------
+  for (int i = tid; i < V; i += nthr) { sinf[3 * i] = c.i0; sinf[3 * i + 1] = 0.0; sinf[3 * i + 2] = c.i0; sst[i] = 0u; }
+  __syncthreads();
+  for (int k = nthr - 1 - tid; k < T; k += nthr) {   // (highest threads first: the low ones carry the landmark loop)
     const double px = ps[3 * k], py = ps[3 * k + 1];
-    s_fr[k] = (int)floor((py - c.map_min_y) / c.res) - hw;
-    s_fc[k] = (int)floor((px - c.map_min_x) / c.res) - hw;     // (defines the candidate block only)
+    const int fr = (int)floor((py - c.map_min_y) / c.res) - hw, fc = (int)floor((px - c.map_min_x) / c.res) - hw;   // (defines the candidate block only)
     double s, co;
     sincos(ps[3 * k + 2], &s, &co);
-    double *o = pr + (size_t)k * PREP_W;
     double S[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) S[i] = cv[6 * k + i];
     double det_info;
-    if (a.info) {
-      const double *q = a.info + ((size_t)b * a.Tstride + k) * 6;
+    if (pinfo) {
+      const double *q = pinfo + 6 * k;
       det_info = q[0] * (q[3] * q[5] - q[4] * q[4]) - q[1] * (q[1] * q[5] - q[4] * q[2]) + q[2] * (q[1] * q[4] - q[3] * q[2]);
     } else {
       const double dc = S[0] * (S[3] * S[5] - S[4] * S[4]) - S[1] * (S[1] * S[5] - S[4] * S[2]) + S[2] * (S[1] * S[4] - S[3] * S[2]);
       det_info = 1.0 / dc;
     }
+    double *o = (k < KC) ? dig + (size_t)k * DIG_W : pr + (size_t)k * PREP_W;   // the first chunk's rows go straight to shared memory
     o[0] = px; o[1] = py; o[2] = co; o[3] = s;
 #pragma unroll
     for (int i = 0; i < 6; ++i) o[4 + i] = S[i];
     o[10] = (det_info < 1e-10) ? 0.0 : 1.0;   // VirtualMap.cpp:293
-    o[11] = 0.0;
+    o[11] = __hiloint2double(fr, fc);
+    if (k < KC) { s_fr[k] = fr; s_fc[k] = fc; }
   }
-  __syncthreads();
-  const int nch = (T + KC - 1) / KC;
-  for (int ch = tid; ch < nch; ch += nthr) {                 // bounding box of the cells a chunk's poses can touch
-    int r0 = 0x3fffffff, r1 = -0x3fffffff, c0 = 0x3fffffff, c1 = -0x3fffffff;
-    for (int k = ch * KC; k < min(T, (ch + 1) * KC); ++k) {
-      const int fr = s_fr[k], fc = s_fc[k];
-      r0 = min(r0, fr); r1 = max(r1, fr); c0 = min(c0, fc); c1 = max(c1, fc);
-    }
-    s_box[ch] = make_int4(max(r0, 0), min(r1 + W, c.rows), max(c0, 0), min(c1 + W, c.cols));
-  }
-  // landmark cells (OccupancyMap.cpp:126-131)
-  {
+  {  // landmark cells (OccupancyMap.cpp:126-131)
     const double *l = a.lm + (size_t)b * a.Lstride * 2;
     for (int j = tid; j < a.Lfixed; j += nthr) {
       if (a.lm_obs && !a.lm_obs[(size_t)b * a.Lstride + j]) continue;
@@ -376,170 +380,271 @@ __global__ void __launch_bounds__(ENV_THREADS, 2) k_vmap_env(EnvArgs a) {
       if (lr >= 0 && lr < c.rows && lc >= 0 && lc < c.cols) atomicOr(&sst[lr * c.cols + lc], ST_LM);
     }
   }
-  // this thread's (pose of the chunk, cell of its block) pairs are the same in every chunk: pair p = tid + r * nthr
-  constexpr int MAXR = 3;
-  int pk[MAXR], pdr[MAXR], pdc[MAXR];
+  // a chunk's digest rows travel scratch -> registers (in front of the previous chunk's prediction) -> shared memory (behind its fold)
+  double drow = 0.0;
+  auto load_rows = [&](int ch) {
+    const int kk = tid / DIG_W, k = ch * KC + kk;
+    if (tid < KC * DIG_W && k < T) drow = pr[(size_t)k * PREP_W + (tid - kk * DIG_W)];
+  };
+  auto store_rows = [&](int ch) {
+    const int kk = tid / DIG_W, i = tid - kk * DIG_W, k = ch * KC + kk, bf = ch & 1;
+    if (tid < KC * DIG_W && k < T) {
+      dig[((size_t)bf * KC + kk) * DIG_W + i] = drow;
+      if (i == 11) { s_fr[bf * 16 + kk] = __double2hiint(drow); s_fc[bf * 16 + kk] = __double2loint(drow); }
+    }
+  };
+  auto chunk_box = [&](int ch) {   // last warp: cell box of the chunk's blocks (read by the fold, behind the next barrier)
+    const int bf = ch & 1, kc = min(KC, T - ch * KC);
+    int fr = lane < kc ? s_fr[bf * 16 + lane] : 0x3fffffff, fc = lane < kc ? s_fc[bf * 16 + lane] : 0x3fffffff;
+    int frm = lane < kc ? fr : -0x3fffffff, fcm = lane < kc ? fc : -0x3fffffff;
 #pragma unroll
-  for (int r = 0; r < MAXR; ++r) {
-    const int p = tid + r * nthr;
-    pk[r] = p / WW;
-    const int j = p - pk[r] * WW;
-    pdr[r] = j / W; pdc[r] = j - pdr[r] * W;
-  }
+    for (int o = 8; o > 0; o >>= 1) {
+      fr = min(fr, __shfl_xor_sync(0xffffffffu, fr, o)); frm = max(frm, __shfl_xor_sync(0xffffffffu, frm, o));
+      fc = min(fc, __shfl_xor_sync(0xffffffffu, fc, o)); fcm = max(fcm, __shfl_xor_sync(0xffffffffu, fcm, o));
+    }
+    if (lane == 0) s_box[bf] = make_int4(max(fr, 0), min(frm + W, c.rows), max(fc, 0), min(fcm + W, c.cols));
+  };
   // (the clock reads hang on the barrier's result: BAR.SYNC defers blocking, a bare clock read would run ahead of it)
   const int nb1 = __syncthreads_count(1);
   if (a.clocks && tid == 0 && nb1) a.clocks[4 * b + 1] = clock64();
 
-  // ---- PREDICT: records of chunk ch (poses [ch KC, ch KC + kc)) into buffer ch & 1.  The visibility count is order-independent
-  // (integer, quirk q8): it goes straight into the cell state; which poses UPDATE a cell goes into the cell's chunk mask.
-  auto predict_chunk = [&](int ch) {
-    const int k0 = ch * KC, kc = min(KC, T - k0);
-    double *rxx = rec0 + (ch & 1) * 4 * RS, *rxy = rxx + RS, *ryy = rxy + RS, *rdt = ryy + RS;
-    const int mshift = (ch & 1) * 16;
-#pragma unroll
-    for (int r = 0; r < MAXR; ++r) {
-      const int p = tid + r * nthr, kk = pk[r];
-      if (kk >= kc) break;
-      const int k = k0 + kk;
-      const int row = s_fr[k] + pdr[r], col = s_fc[k] + pdc[r];
-      const bool cell_on = row >= 0 && row < c.rows && col >= 0 && col < c.cols;
-      const int idx = row * c.cols + col;
-      const double *q = pr + (size_t)k * PREP_W;
-      const double2 p01 = *reinterpret_cast<const double2 *>(q), p23 = *reinterpret_cast<const double2 *>(q + 2);
-      const double cx = c.map_min_x + c.res * (col + 0.5), cy = c.map_min_y + c.res * (row + 0.5);
-      const double dx = cx - p01.x, dy = cy - p01.y;
-      const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-      bool in_max, out_min;   // range gates on d2, the reference's sqrt comparison inside a 1e-9 band (see k_vmap_cells)
-      if (d2 < c.max_r2_lo) in_max = true; else if (d2 > c.max_r2_hi) in_max = false; else in_max = __dsqrt_rn(d2) < c.max_range;
-      if (d2 > c.min_r2_hi) out_min = true; else if (d2 < c.min_r2_lo) out_min = false; else out_min = __dsqrt_rn(d2) > c.min_range;
-      const bool inr = cell_on && in_max;
-      const double co = p23.x, si = p23.y;
-      const double qx = co * dx + si * dy, qy = -si * dx + co * dy;
-      bool in_fov;
-      if (c.fov_wide && (qx > 0.0 || fabs(qy) > -qx * c.wedge_tan)) in_fov = true;
-      else if (inr) { const double bb = atan2(qy, qx); in_fov = bb < c.max_bearing && bb > c.min_bearing; }
-      else in_fov = false;
-      const bool vis = inr && in_fov;
-      if (!vis) continue;
-      atomicAdd(&sst[idx], 1u);                          // visibility count (q8)
-      if (!(out_min && q[10] != 0.0)) continue;          // full check (q10) ; det(info) gate
-      atomicOr(&smk[idx], 1u << (mshift + kk));
-      const double2 p45 = *reinterpret_cast<const double2 *>(q + 4), p67 = *reinterpret_cast<const double2 *>(q + 6);
-      const double2 p89 = *reinterpret_cast<const double2 *>(q + 8);
-      const double Sxx = p45.x, Sxy = p45.y, Sxt = p67.x, Syy = p67.y, Syt = p89.x, Stt = p89.y;
-      const double qxx = qx * qx, qyy = qy * qy, qxy = qx * qy;
-      const double P00 = qyy * (c.rb + Stt) + Sxx - 2.0 * qy * Sxt;
-      const double P01 = Sxy - qy * Syt + qx * Sxt - qxy * (c.rb + Stt);
-      const double P11 = qxx * (c.rb + Stt) + Syy + 2.0 * qx * Syt;
-      const double Q = P00 * qyy - 2.0 * P01 * qxy + P11 * qxx;
-      const double inv = vm_rcp((P00 * P11 - P01 * P01) * d2 + c.rr * Q);
-      const double lb00 = (P11 * d2 + c.rr * qyy) * inv, lb01 = -(P01 * d2 + c.rr * qxy) * inv, lb11 = (P00 * d2 + c.rr * qxx) * inv;
-      const double cc = co * co, ss = si * si, cs = co * si;
-      rxx[p] = cc * lb00 - 2.0 * cs * lb01 + ss * lb11;
-      rxy[p] = cs * (lb00 - lb11) + (cc - ss) * lb01;
-      ryy[p] = ss * lb00 + 2.0 * cs * lb01 + cc * lb11;
-      rdt[p] = d2 * inv;
-    }
-  };
-  // ---- FOLD: the cells of the chunk's bounding box, one thread per cell; a cell folds the poses of its chunk mask in
-  // trajectory order (lowest bit first) -----------------------------------------------------------------------------------
-  auto fold_chunk = [&](int ch) {
-    const int k0 = ch * KC;
-    const double *rxx = rec0 + (ch & 1) * 4 * RS, *rxy = rxx + RS, *ryy = rxy + RS, *rdt = ryy + RS;
-    const int mshift = (ch & 1) * 16;
-    const int4 bx = s_box[ch];
-    const int r0 = bx.x, r1 = bx.y, c0 = bx.z, c1 = bx.w;
-    const int bw = c1 - c0, nbc = (r1 > r0 && bw > 0) ? (r1 - r0) * bw : 0;
-    for (int ci = tid; ci < nbc; ci += nthr) {
-      const int rr_ = ci / bw, row = r0 + rr_, col = c0 + ci - rr_ * bw;
-      const int idx = row * c.cols + col;
-      unsigned m = (smk[idx] >> mshift) & 0xffffu;
-      if (!m) continue;
-      atomicAnd(&smk[idx], ~(0xffffu << mshift));        // (the other half may be set concurrently by the next chunk's prediction)
-      double ixx = sxx[idx], ixy = sxy[idx], iyy = syy[idx];
-      bool first = !(sst[idx] & ST_UPD);                 // the first hit overwrites the prior (VirtualMap.cpp:307-309)
-      while (m) {
-        const int kk = __ffs(m) - 1;
-        m &= m - 1;
-        const int j = kk * WW + (row - s_fr[k0 + kk]) * W + (col - s_fc[k0 + kk]);
-        const double nxx = rxx[j], nxy = rxy[j], nyy = ryy[j], bdet = rdt[j];
-        // covariance intersection on information matrices (VirtualMap.cpp:364-377, q11)
-        const double aa = ixx * iyy - ixy * ixy;
-        const double cm = iyy * nxx - 2.0 * ixy * nxy + ixx * nyy;
-        const double d = aa + bdet - cm;
-        double w = 0.5 * (2.0 * bdet - cm) * vm_rcp(d);
-        w = ((w < 0 && d < 0) || (w > 1 && d > 0)) ? 0.0 : (((w < 0 && d > 0) || (w > 1 && d < 0)) ? 1.0 : w);
-        ixx = first ? nxx : w * ixx + (1.0 - w) * nxx;
-        ixy = first ? nxy : w * ixy + (1.0 - w) * nxy;
-        iyy = first ? nyy : w * iyy + (1.0 - w) * nyy;
-        first = false;
-      }
-      sxx[idx] = ixx; sxy[idx] = ixy; syy[idx] = iyy;
-      atomicOr(&sst[idx], ST_UPD);
-    }
-  };
-  if (nch > 0) predict_chunk(0);
-  __syncthreads();
+  unsigned short *mylist = s_list + warp * PPW;
+  long long ph[5] = {0, 0, 0, 0, 0};
   for (int ch = 0; ch < nch; ++ch) {
-    if (ch + 1 < nch) predict_chunk(ch + 1);    // issued in front of the fold: independent work for the warps that wait on fold chains
-    fold_chunk(ch);
-    __syncthreads();
+    long long t0 = a.phase ? clock64() : 0, t1;
+    const int k0 = ch * KC, kc = min(KC, T - k0), bf = ch & 1;
+    const double *dg = dig + (size_t)bf * KC * DIG_W;
+    const int *fr_ = s_fr + bf * 16, *fc_ = s_fc + bf * 16;
+    if (ch + 1 < nch) load_rows(ch + 1);
+    if (warp == NWARP - 1) chunk_box(ch);
+    // ---- PREDICT, gate pass: this warp's slice of the chunk's pairs, GR pairs per lane evaluated side by side
+    // (independent straight-line instances: instruction-level parallelism for the latency of the fp64 predicates) -----
+    const int np = kc * WW, p_lo = min(np, warp * PPW), p_hi = min(np, p_lo + PPW);
+    int n_act = 0;
+    for (int p0 = p_lo; p0 < p_hi; p0 += 32 * GR) {
+      bool upd[GR], vis[GR], amb[GR];
+      int cidx[GR];
+#pragma unroll
+      for (int r = 0; r < GR; ++r) {   // branch-free fast path: the predicates away from their knife edges
+        const int pr_ = p0 + 32 * r + lane, p = min(pr_, p_hi - 1);
+        const bool pv = pr_ < p_hi;
+        const int kk = p / WW, j = p - kk * WW, dr = j / W, dcl = j - dr * W;
+        const int row = fr_[kk] + dr, col = fc_[kk] + dcl;
+        const bool cell_on = pv && row >= 0 && row < c.rows && col >= 0 && col < c.cols;
+        const double *q = dg + kk * DIG_W;
+        const double cx = c.map_min_x + c.res * (col + 0.5), cy = c.map_min_y + c.res * (row + 0.5);
+        const double dx = cx - q[0], dy = cy - q[1];
+        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        const bool in_max = d2 < c.max_r2_lo, out_min = d2 > c.min_r2_hi;
+        const bool band = (d2 >= c.max_r2_lo && d2 <= c.max_r2_hi) || (d2 >= c.min_r2_lo && d2 <= c.min_r2_hi);
+        const double co = q[2], si = q[3];
+        const double qx = co * dx + si * dy, qy = -si * dx + co * dy;
+        const bool fov_fast = c.fov_wide && (qx > 0.0 || fabs(qy) > -qx * c.wedge_tan);
+        amb[r] = cell_on && (band || (in_max && !fov_fast));
+        vis[r] = cell_on && in_max && fov_fast;
+        upd[r] = vis[r] && out_min && q[10] != 0.0;            // full check (q10) ; det(info) gate
+        cidx[r] = row * c.cols + col;
+      }
+#pragma unroll
+      for (int r = 0; r < GR; ++r) {
+        const int p = p0 + 32 * r + lane;
+        if (amb[r]) {   // rare: inside a 1e-9 band around a range limit (the reference's own sqrt comparison decides) or in the rear wedge (atan2)
+          const int kk = p / WW, j = p - kk * WW, dr = j / W, dcl = j - dr * W;
+          const int row = fr_[kk] + dr, col = fc_[kk] + dcl;
+          const double *q = dg + kk * DIG_W;
+          const double cx = c.map_min_x + c.res * (col + 0.5), cy = c.map_min_y + c.res * (row + 0.5);
+          const double dx = cx - q[0], dy = cy - q[1];
+          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          bool in_max, out_min;
+          if (d2 < c.max_r2_lo) in_max = true; else if (d2 > c.max_r2_hi) in_max = false; else in_max = __dsqrt_rn(d2) < c.max_range;
+          if (d2 > c.min_r2_hi) out_min = true; else if (d2 < c.min_r2_lo) out_min = false; else out_min = __dsqrt_rn(d2) > c.min_range;
+          const double co = q[2], si = q[3];
+          const double qx = co * dx + si * dy, qy = -si * dx + co * dy;
+          bool in_fov;
+          if (c.fov_wide && (qx > 0.0 || fabs(qy) > -qx * c.wedge_tan)) in_fov = true;
+          else if (in_max) { const double bb = atan2(qy, qx); in_fov = bb < c.max_bearing && bb > c.min_bearing; }
+          else in_fov = false;
+          vis[r] = in_max && in_fov;
+          upd[r] = vis[r] && out_min && q[10] != 0.0;
+        }
+        if (vis[r]) atomicAdd(&sst[cidx[r]], 1u);              // visibility count (q8): order-independent
+        if (p < p_hi && !upd[r]) rxx[p] = -1.0;                // sentinel: this pose does not update this cell
+        const unsigned m = __ballot_sync(0xffffffffu, upd[r]);
+        if (upd[r]) mylist[n_act + __popc(m & ((1u << lane) - 1u))] = (unsigned short)p;
+        n_act += __popc(m);
+      }
+    }
+    __syncwarp();
+    if (a.phase) { t1 = clock64(); ph[0] += t1 - t0; t0 = t1; }
+    // ---- PREDICT, SPD pass on the compacted list, two entries per lane side by side ---------------------------------
+    for (int i0 = 0; i0 < n_act; i0 += 64) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = i0 + 32 * r + lane;
+        const bool on = i < n_act;
+        const int p = mylist[min(i, n_act - 1)];
+        const int kk = p / WW, j = p - kk * WW, dr = j / W, dcl = j - dr * W;
+        const int row = fr_[kk] + dr, col = fc_[kk] + dcl;
+        const double *q = dg + kk * DIG_W;
+        const double cx = c.map_min_x + c.res * (col + 0.5), cy = c.map_min_y + c.res * (row + 0.5);
+        const double dx = cx - q[0], dy = cy - q[1];
+        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        const double co = q[2], si = q[3];
+        const double qx = co * dx + si * dy, qy = -si * dx + co * dy;
+        // body-frame covariance of the predicted virtual landmark: cb = P + (rr / r^2) [qx qx, qx qy; qx qy, qy qy], with P the
+        // bearing-noise + pose-covariance part.  Its inverse (the body-frame information) needs ONE reciprocal:
+        //   det(cb) r^2 = det(P) r^2 + rr Q,  Q = P00 qy^2 - 2 P01 qx qy + P11 qx^2,   adj(cb) r^2 = adj(P) r^2 + rr [qy qy, -qx qy; ., qx qx]
+        const double Sxx = q[4], Sxy = q[5], Sxt = q[6], Syy = q[7], Syt = q[8], Stt = q[9];
+        const double qxx = qx * qx, qyy = qy * qy, qxy = qx * qy;
+        const double P00 = qyy * (c.rb + Stt) + Sxx - 2.0 * qy * Sxt;
+        const double P01 = Sxy - qy * Syt + qx * Sxt - qxy * (c.rb + Stt);
+        const double P11 = qxx * (c.rb + Stt) + Syy + 2.0 * qx * Syt;
+        const double Q = P00 * qyy - 2.0 * P01 * qxy + P11 * qxx;
+        const double inv = vm_rcp((P00 * P11 - P01 * P01) * d2 + c.rr * Q);
+        const double lb00 = (P11 * d2 + c.rr * qyy) * inv, lb01 = -(P01 * d2 + c.rr * qxy) * inv, lb11 = (P00 * d2 + c.rr * qxx) * inv;
+        const double cc = co * co, ss = si * si, cs = co * si;   // rotate to the map frame
+        if (on) {
+          rxx[p] = cc * lb00 - 2.0 * cs * lb01 + ss * lb11;     // (diagonal of an SPD matrix: > 0, never the sentinel)
+          rxy[p] = cs * (lb00 - lb11) + (cc - ss) * lb01;
+          ryy[p] = ss * lb00 + 2.0 * cs * lb01 + cc * lb11;
+        }
+      }
+    }
+    if (a.phase) { t1 = clock64(); ph[1] += t1 - t0; t0 = t1; }
+    {
+      const int nbw = __syncthreads_count(1);
+      if (a.phase && nbw) { t1 = clock64(); ph[2] += t1 - t0; t0 = t1; }
+    }
+    // ---- FOLD: the cells of the chunk's box, one thread per cell, the chunk's poses in trajectory order ---------
+    {
+      const int4 bx = s_box[bf];
+      const int r0 = bx.x, c0 = bx.z, bw = bx.w - bx.z, nbc = (bx.y > r0 && bw > 0) ? (bx.y - r0) * bw : 0;
+      for (int ci = tid; ci < nbc; ci += nthr) {
+        const int rr_ = ci / bw, row = r0 + rr_, col = c0 + ci - rr_ * bw;
+        const int idx = row * c.cols + col;
+        unsigned m = 0;
+#pragma unroll 4
+        for (int kk = 0; kk < kc; ++kk) {
+          const unsigned dr = (unsigned)(row - fr_[kk]), dcl = (unsigned)(col - fc_[kk]);
+          if (dr < (unsigned)W && dcl < (unsigned)W && rxx[kk * WW + dr * W + dcl] >= 0.0) m |= 1u << kk;
+        }
+        if (!m) continue;
+        double *st = sinf + 3 * (size_t)idx;
+        double ixx = st[0], ixy = st[1], iyy = st[2];
+        bool first = !(sst[idx] & ST_UPD);                 // the first hit overwrites the prior (VirtualMap.cpp:307-309)
+        int kk = __ffs(m) - 1;
+        m &= m - 1;
+        int j = kk * WW + (row - fr_[kk]) * W + (col - fc_[kk]);
+        double nxx = rxx[j], nxy = rxy[j], nyy = ryy[j];
+        for (;;) {
+          double fxx = 0, fxy = 0, fyy = 0;
+          const bool more = m != 0;
+          if (more) {                                      // next record in flight beside this fold's dependent chain
+            kk = __ffs(m) - 1;
+            m &= m - 1;
+            j = kk * WW + (row - fr_[kk]) * W + (col - fc_[kk]);
+            fxx = rxx[j]; fxy = rxy[j]; fyy = ryy[j];
+          }
+          // covariance intersection on information matrices (VirtualMap.cpp:364-377, q11): a = det m1, b = det m2, w = num / d
+          const double bdet = nxx * nyy - nxy * nxy;
+          const double aa = ixx * iyy - ixy * ixy;
+          const double cm = iyy * nxx - 2.0 * ixy * nxy + ixx * nyy;
+          const double d = aa + bdet - cm, num = bdet - 0.5 * cm;
+          // the clip of q11 -- (w<0 & d<0) | (w>1 & d>0) -> 0 ; (w<0 & d>0) | (w>1 & d<0) -> 1 -- decided from the signs of num, d
+          // and num - d beside the reciprocal (w<0 <=> num, d of opposite sign; w>1 <=> num - d has the sign of d), not behind it
+          const bool dneg = d < 0, dpos = d > 0;
+          const bool wneg = (num < 0 && dpos) || (num > 0 && dneg), wbig = (num > d && dpos) || (num < d && dneg);
+          const bool to0 = first || (wneg && dneg) || (wbig && dpos), to1 = (wneg && dpos) || (wbig && dneg);
+          double w = num * vm_rcp(d);
+          w = to0 ? 0.0 : (to1 ? 1.0 : w);
+          ixx = fma(w, ixx - nxx, nxx);
+          ixy = fma(w, ixy - nxy, nxy);
+          iyy = fma(w, iyy - nyy, nyy);
+          first = false;
+          if (!more) break;
+          nxx = fxx; nxy = fxy; nyy = fyy;
+        }
+        st[0] = ixx; st[1] = ixy; st[2] = iyy;
+        sst[idx] |= ST_UPD;                                 // (the cell's only writer between the two barriers)
+      }
+    }
+    if (a.phase) { t1 = clock64(); ph[3] += t1 - t0; t0 = t1; }
+    if (ch + 1 < nch) store_rows(ch + 1);
+    {
+      const int nbw = __syncthreads_count(1);
+      if (a.phase && nbw) { t1 = clock64(); ph[4] += t1 - t0; }
+    }
   }
-  if (a.clocks && tid == 0) a.clocks[4 * b + 2] = clock64();
-  // ---- write the map: every output byte once, coalesced -------------------------------------------------------
+  if (a.phase && tid == 0) for (int i = 0; i < 5; ++i) a.phase[8 * b + i] = ph[i];
+  // ---- write the map: every output byte once ---------------------------------------------------------------------
   const size_t cell0 = (size_t)b * V;
+  const bool bulk = (V & 1) == 0;                        // 24 V bytes and the env's offset are multiples of 16
+  // the information matrices leave as bulk copies shared -> global of the cell-interleaved state: every writer orders its
+  // generic-proxy stores before the async proxy, then one thread issues the copies
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const int nb2 = __syncthreads_count(1);
+  if (a.clocks && tid == 0 && nb2) a.clocks[4 * b + 2] = clock64();
+  if (bulk && tid == 0) {
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(sinf);
+    char *dst = reinterpret_cast<char *>(a.vinfo + cell0 * 3);
+    const uint32_t total = 24u * (uint32_t)V;
+    for (uint32_t off = 0; off < total; off += 32768u) {
+      const uint32_t n = min(32768u, total - off);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src + off), "r"(n) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
   for (int i = tid; i < V; i += nthr) {
     const unsigned st = sst[i];
     const int cnt = (int)(st & ST_CNT);
     a.prob[cell0 + i] = (st & ST_LM) ? c.ptab[5] : c.ptab[min(cnt, 4)];
     if (a.seen) a.seen[cell0 + i] = (st & ST_LM) ? -1 : cnt;
   }
-  for (int i = tid; i < 3 * V; i += nthr) {
-    const int cell = i / 3, j = i - 3 * cell;
-    a.vinfo[cell0 * 3 + i] = j == 0 ? sxx[cell] : (j == 1 ? sxy[cell] : syy[cell]);
-  }
+  if (!bulk) for (int i = tid; i < 3 * V; i += nthr) a.vinfo[cell0 * 3 + i] = sinf[i];
   if (a.clocks && tid == 0) a.clocks[4 * b + 3] = clock64();
-  if (!a.metrics) return;
-
-  // ---- metrics (k_vmap_metrics, same summation order: 256 strided partial sums, fixed tree) ---------------------
-  if (tid == 0 && a.counters && a.step_kind[b]) {
-    atomicAdd(&a.counters[0], 1ull);
-    atomicAdd(&a.counters[1], (unsigned long long)T);
-    atomicAdd(&a.counters[2], (unsigned long long)a.meas_ptr[(size_t)b * (a.d.Tmax + 1) + T]);
-  }
-  int *s_e = reinterpret_cast<int *>(s_red + 256), *s_k = s_e + 256;
-  {
-    const int extg = 20;
-    int n_exp = 0, n_known = 0;
-    double tr = 0.0;
-    for (int i = tid; i < V; i += 256) {
-      const double x = (i % c.cols + 0.5) * a.cfg.resolution + a.cfg.map_min_x, y = (i / c.cols + 0.5) * a.cfg.resolution + a.cfg.map_min_y;
-      const unsigned st = sst[i];
-      const double pv = (st & ST_LM) ? c.ptab[5] : c.ptab[min((int)(st & ST_CNT), 4)];
-      if ((pv < 0.49 || pv > 0.6) && a.cfg.map_min_x + extg <= x && x <= a.cfg.map_max_x - extg && a.cfg.map_min_y + extg <= y && y <= a.cfg.map_max_y - extg) ++n_exp;
-      if (pv < a.cfg.occupancy_threshold) ++n_known;
-      const double qa = sxx[i], qb = sxy[i], qc = syy[i];
-      tr += (qa + qc) / (qa * qc - qb * qb);
+  if (a.metrics) {
+    // ---- metrics (k_vmap_metrics, same summation order: 256 strided partial sums, fixed tree) ---------------------
+    if (tid == 0 && a.counters && a.step_kind[b]) {
+      atomicAdd(&a.counters[0], 1ull);
+      atomicAdd(&a.counters[1], (unsigned long long)T);
+      atomicAdd(&a.counters[2], (unsigned long long)a.meas_ptr[(size_t)b * (a.d.Tmax + 1) + T]);
     }
-    s_red[tid] = tr; s_e[tid] = n_exp; s_k[tid] = n_known;
-  }
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (tid < o) { s_red[tid] += s_red[tid + o]; s_e[tid] += s_e[tid + o]; s_k[tid] += s_k[tid + o]; }
+    int *s_e = reinterpret_cast<int *>(s_red + 256), *s_k = s_e + 256;
+    if (tid < 256) {
+      const int extg = 20;
+      int n_exp = 0, n_known = 0;
+      double tr = 0.0;
+      for (int i = tid; i < V; i += 256) {
+        const double x = (i % c.cols + 0.5) * a.cfg.resolution + a.cfg.map_min_x, y = (i / c.cols + 0.5) * a.cfg.resolution + a.cfg.map_min_y;
+        const unsigned st = sst[i];
+        const double pv = (st & ST_LM) ? c.ptab[5] : c.ptab[min((int)(st & ST_CNT), 4)];
+        if ((pv < 0.49 || pv > 0.6) && a.cfg.map_min_x + extg <= x && x <= a.cfg.map_max_x - extg && a.cfg.map_min_y + extg <= y && y <= a.cfg.map_max_y - extg) ++n_exp;
+        if (pv < a.cfg.occupancy_threshold) ++n_known;
+        const double qa = sinf[3 * i], qb = sinf[3 * i + 1], qc = sinf[3 * i + 2];
+        tr += (qa + qc) / (qa * qc - qb * qb);
+      }
+      s_red[tid] = tr; s_e[tid] = n_exp; s_k[tid] = n_known;
+    }
     __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) { s_red[tid] += s_red[tid + o]; s_e[tid] += s_e[tid + o]; s_k[tid] += s_k[tid + o]; }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const int extg = 20;
+      const int ce = (a.d.rows - extg * 2 / (int)a.cfg.resolution) * (a.d.cols - extg * 2 / (int)a.cfg.resolution);
+      const double explored = (double)s_e[0] / ce;
+      const double pk = (double)s_k[0] / a.d.V;
+      a.metrics[8 * b + 0] = explored;
+      a.metrics[8 * b + 1] = s_red[0];
+      a.metrics[8 * b + 2] = a.cfg.dist_w0 - (a.cfg.dist_w0 - a.cfg.dist_w1) * pk;
+      a.metrics[8 * b + 3] = (double)s_k[0];
+      a.metrics[8 * b + 6] = a.dist[b];
+      a.done[b] = (a.sim_step[b] > a.cfg.max_steps || explored > 0.85 || a.status[b] == DGE_ECAP) ? 1 : 0;
+    }
   }
-  if (tid == 0) {
-    const int extg = 20;
-    const int ce = (a.d.rows - extg * 2 / (int)a.cfg.resolution) * (a.d.cols - extg * 2 / (int)a.cfg.resolution);
-    const double explored = (double)s_e[0] / ce;
-    const double pk = (double)s_k[0] / a.d.V;
-    a.metrics[8 * b + 0] = explored;
-    a.metrics[8 * b + 1] = s_red[0];
-    a.metrics[8 * b + 2] = a.cfg.dist_w0 - (a.cfg.dist_w0 - a.cfg.dist_w1) * pk;
-    a.metrics[8 * b + 3] = (double)s_k[0];
-    a.metrics[8 * b + 6] = a.dist[b];
-    a.done[b] = (a.sim_step[b] > a.cfg.max_steps || explored > 0.85 || a.status[b] == DGE_ECAP) ? 1 : 0;
-  }
+  // the shared-memory source of the bulk copies must stay alive until they have been read
+  if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 VmapCfg make_cfg(const dge_config &g, int rows, int cols) {
@@ -575,39 +680,42 @@ int dge_vmap_prep_width() { return PREP_W; }
 
 namespace {
 // geometry of the fused kernel for a map: chunk length and shared memory; false if the map does not fit
-size_t env_smem(size_t V, int Tstride, int kc, int W) {
-  const size_t rs = (size_t)kc * W * W;
-  return V * 3 * sizeof(double) + 2 * ((V + 1) & ~(size_t)1) * sizeof(unsigned) + 2 * (size_t)((Tstride + 1) & ~1) * sizeof(int) +
-         256 * (sizeof(double) + 2 * sizeof(int)) + 8 * rs * sizeof(double) + (size_t)((Tstride + kc - 1) / kc) * 16 + 32;
+int env_threads() {   // CTA size of the fused kernel: DGE_VMAP_THREADS=256|512 (A/B switch; 256 measured faster at C4: profiles/r02_c4_vmap_sweep_v2.md)
+  static const int n = [] { const char *v = getenv("DGE_VMAP_THREADS"); return (v && atoi(v) == 512) ? 512 : 256; }();
+  return n;
 }
-bool env_plan(const dge_config &g, int rows, int cols, int Tstride, int *hw, int *W, int *kc, size_t *smem) {
+size_t env_smem(size_t V, int kc, int W, int nthr) {
+  const size_t rs = (size_t)kc * W * W, nw = nthr / 32, ppw = (rs + nw - 1) / nw;
+  return V * 3 * sizeof(double) + ((V + 1) & ~(size_t)1) * sizeof(unsigned) + 2 * (size_t)kc * DIG_W * sizeof(double) + 3 * rs * sizeof(double) +
+         256 * (sizeof(double) + 2 * sizeof(int)) + 64 * sizeof(int) + 16 + 2 * sizeof(int4) + nw * ((ppw + 7) & ~(size_t)7) * sizeof(unsigned short) + 32;
+}
+bool env_plan(const dge_config &g, int rows, int cols, int nthr, int *hw, int *W, int *kc, int *ppw, size_t *smem) {
   *hw = (int)ceil(g.max_range / g.resolution);
   *W = 2 * *hw + 1;
   if (*W > 15) return false;
-  const size_t V = (size_t)rows * cols;
-  // chunk length: (pose, cell) pairs of a chunk fill whole rounds of the CTA's threads (kc W^2 just below a multiple of 256;
-  // 15 / 10 / 5 for W = 7), at most 16 poses (chunk mask), the longest that leaves room for two CTAs per SM
-  int cand[3], nc = 0;
-  for (int r = 3; r >= 1; --r) { const int k = (r * ENV_THREADS) / (*W * *W); if (k >= 1 && k <= 16 && (nc == 0 || cand[nc - 1] != k)) cand[nc++] = k; }
-  if (nc == 0) cand[nc++] = 1;
-  for (int i = 0; i < nc; ++i) {
-    *kc = cand[i]; *smem = env_smem(V, Tstride, cand[i], *W);
-    if (*smem <= 113 * 1024) return true;
+  const size_t V = (size_t)rows * cols, nw = nthr / 32;
+  // chunk length: 16 poses (the fold's hit mask; its digest rows are moved by 16 x 12 threads), shorter only if the record buffer
+  // would not leave room for two CTAs per SM
+  for (int k = 16; k >= 1; k >>= 1) {
+    *kc = k; *smem = env_smem(V, k, *W, nthr);
+    *ppw = (int)((((size_t)k * *W * *W + nw - 1) / nw + 7) & ~(size_t)7);
+    if (*smem <= 113 * 1024 || (k == 1 && *smem <= 226 * 1024)) return true;
   }
-  *kc = cand[nc - 1]; *smem = env_smem(V, Tstride, *kc, *W);
-  return *smem <= 226 * 1024;
+  return false;
 }
 int env_launch(EnvArgs &a, const dge_config &g, int n, int rows, int cols, cudaStream_t st) {
   size_t smem;
-  if (!env_plan(g, rows, cols, a.Tstride, &a.hw, &a.W, &a.kc, &smem)) return 1;   // caller falls back to the cell-centric kernels
-  void (*kern)(EnvArgs) = a.W == 7 ? k_vmap_env<7> : k_vmap_env<0>;
-  static size_t configured[2] = {0, 0};
-  size_t &cf = configured[a.W == 7 ? 1 : 0];
+  const int nthr = env_threads();
+  if (!env_plan(g, rows, cols, nthr, &a.hw, &a.W, &a.kc, &a.ppw, &smem)) return 1;   // caller falls back to the cell-centric kernels
+  const int vi = (a.W == 7 ? 1 : 0) + (nthr == 512 ? 2 : 0);
+  void (*kern)(EnvArgs) = vi == 3 ? k_vmap_env<7, 512> : vi == 2 ? k_vmap_env<0, 512> : vi == 1 ? k_vmap_env<7, 256> : k_vmap_env<0, 256>;
+  static size_t configured[4] = {0, 0, 0, 0};
+  size_t &cf = configured[vi];
   if (smem > 48 * 1024 && smem > cf) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DGE_ECUDA;
     cf = smem;
   }
-  kern<<<n, ENV_THREADS, smem, st>>>(a);
+  kern<<<n, nthr, smem, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }
 }  // namespace
@@ -621,7 +729,7 @@ int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
     a.lm = e->est_l; a.lm_obs = e->observed; a.prob = e->prob; a.vinfo = e->vinfo; a.seen = e->seen; a.mask = mask;
     a.cfg = e->cfg; a.d = e->d; a.sim_step = e->sim_step; a.status = e->status; a.meas_ptr = e->meas_ptr; a.dist = e->dist;
     a.metrics = e->metrics; a.done = e->done; a.counters = e->count_steps ? e->counters : nullptr; a.step_kind = e->step_kind;
-    a.clocks = nullptr;
+    a.clocks = nullptr; a.phase = nullptr;
     a.order = (e->step_order_live && mask == e->active) ? e->step_order : nullptr;   // same envs, same costs as the SLAM launch just before
     const int rc = env_launch(a, e->cfg, e->d.B, e->d.rows, e->d.cols, st);
     if (rc != 1) return rc;
@@ -653,7 +761,9 @@ int dge_vmap_standalone(const dge_config *cfg, int n, int T, const double *pose,
     a.metrics = nullptr; a.done = nullptr; a.counters = nullptr; a.step_kind = nullptr;
     a.sim_step = nullptr; a.status = nullptr; a.meas_ptr = nullptr; a.dist = nullptr;
     a.cfg = *cfg; a.d = DgeDims{};
-    a.clocks = reinterpret_cast<long long *>(cbox_ws);   // the chunk-box scratch is unused by the fused kernel: phase clocks for dev profiling
+    // dev profiling: phase clocks in the chunk-box scratch, which the fused kernel does not use ([n,4] clocks, then [n,8] per-chunk phase sums)
+    a.clocks = reinterpret_cast<long long *>(cbox_ws);
+    a.phase = reinterpret_cast<long long *>(cbox_ws) + (size_t)n * 4;
     a.order = nullptr;
     const int rc = env_launch(a, *cfg, n, rows, cols, st);
     if (rc != 1) return rc;

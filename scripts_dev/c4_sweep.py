@@ -43,8 +43,11 @@ for T in (32, 64, 128, 256, 512, 1024):
         ts.append(a.elapsed_time(b))
     ms = float(np.median(ts))
     nch = (T + 31) // 32
+    nch16 = (T + 15) // 16
     clk = ws[n * T * 12:].view(torch.int64)[:4 * n].view(n, 4).cpu().numpy()
     d = np.diff(clk, axis=1).mean(axis=0)
     by = 2.0 * (48 * T + 20 * V + 8 * L) * n
     gbs = by / (ms * 1e-3) / 1e9
+    ph = ws[n * T * 12:].view(torch.int64)[4 * n:12 * n].view(n, 8)[:, :5].double().mean(dim=0).cpu().numpy() / nch16
+    print(f"    per chunk cycles (thread 0): gate {ph[0]:.0f} spd {ph[1]:.0f} wait {ph[2]:.0f} fold {ph[3]:.0f} rows+wait {ph[4]:.0f}", file=sys.stderr)
     print(f"| {T} | {ms * 1e3:.1f} | {visits:.3g} | {by / 1e6:.1f} | {gbs:.1f} | {gbs / peak:.4f} | {visits / ms / 1e6:.2f} | {d[0]:.0f} / {d[1]:.0f} / {d[2]:.0f} |")
