@@ -48,6 +48,9 @@ struct dge_engine {
   int32_t *step_order;   // [B] block -> env of the last SLAM launch (cost-ordered placement); step_order_live: valid for the virtual-map launch that follows
   int step_order_live;
   double *fc_state;      // [B,DGE_FC_WIDTH(Lt)] cached forward-elimination state behind the closed poses (dge_slam.cu)
+  double *ck_state;      // [B,DGE_FC_WIDTH(Lt)] checkpoint of that state a rebuild leaves three poses before its end (the next rebuild resumes there)
+  int32_t *ck_pos;       // [B]             closed poses behind the checkpoint (0 = none)
+  int32_t *lm_first;     // [B,Lt]          pose index of a landmark's first observation
   double *vm_prep;       // [B,Tmax,12]     digested poses for the virtual-map kernel
   double *vm_cbox;       // [B,nchunk,4]    per-32-pose bounding boxes
   int32_t *seen;         // [B,V]           integer visibility counts (-1 = landmark cell)

@@ -19,7 +19,7 @@ struct EngPtrs {
   double *true_pose, *lm_true, *prior_pose;
   int32_t *scan_id;
   uint64_t *seed;
-  int32_t *n_poses, *sim_step, *update_count, *status, *fc_valid;
+  int32_t *n_poses, *sim_step, *update_count, *status, *fc_valid, *ck_pos, *lm_first;
   double *lin_pose, *est_pose, *delta_pose, *odom, *pose_cov, *pose_info;
   int32_t *meas_ptr, *meas_id, *meas_pose;
   double *meas_b, *meas_r;
@@ -33,7 +33,7 @@ struct EngPtrs {
 EngPtrs ptrs(dge_engine *e) {
   EngPtrs p;
   p.d = e->d; p.true_pose = e->true_pose; p.lm_true = e->lm_true; p.prior_pose = e->prior_pose; p.scan_id = e->scan_id; p.seed = e->seed;
-  p.n_poses = e->n_poses; p.sim_step = e->sim_step; p.update_count = e->update_count; p.status = e->status; p.fc_valid = e->fc_valid;
+  p.n_poses = e->n_poses; p.sim_step = e->sim_step; p.update_count = e->update_count; p.status = e->status; p.fc_valid = e->fc_valid; p.ck_pos = e->ck_pos; p.lm_first = e->lm_first;
   p.lin_pose = e->lin_pose; p.est_pose = e->est_pose; p.delta_pose = e->delta_pose; p.odom = e->odom; p.pose_cov = e->pose_cov; p.pose_info = e->pose_info;
   p.meas_ptr = e->meas_ptr; p.meas_id = e->meas_id; p.meas_pose = e->meas_pose; p.meas_b = e->meas_b; p.meas_r = e->meas_r;
   p.observed = e->observed; p.lin_l = e->lin_l; p.est_l = e->est_l; p.delta_l = e->delta_l; p.land_cov = e->land_cov;
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) k_rollout_clone(dge_config cfg, EngPtrs D
   copy_n(D.lm_true + c * Lt * 2, S.lm_true + b * Lt * 2, Lt * 2);
   copy_n(D.scan_id + c * Lt, S.scan_id + b * Lt, Lt);
   copy_n(D.observed + c * Lt, S.observed + b * Lt, Lt);
+  copy_n(D.lm_first + c * Lt, S.lm_first + b * Lt, Lt);
   copy_n(D.lin_l + c * Lt * 2, S.est_l + b * Lt * 2, Lt * 2);
   copy_n(D.est_l + c * Lt * 2, S.est_l + b * Lt * 2, Lt * 2);
   for (size_t i = tid; i < Lt * 2; i += blockDim.x) D.delta_l[c * Lt * 2 + i] = 0.0;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) k_rollout_clone(dge_config cfg, EngPtrs D
   if (tid == 0) {
     D.seed[c] = S.seed[b];                // Simulator2D copy incl. RNG state (:1420): every roll-out of an env sees the same noise stream
     D.n_poses[c] = T; D.sim_step[c] = S.sim_step[b]; D.update_count[c] = 1; D.status[c] = 0;
-    D.fc_valid[c] = 0;                    // the clone's SLAM solve starts from a full elimination (no cached state travels with a clone)
+    D.fc_valid[c] = 0; D.ck_pos[c] = 0;   // the clone's SLAM solve starts from a full elimination (no cached state or checkpoint travels with a clone)
     D.dist[c] = 0; D.rdist[c] = 0; D.done[c] = 0; D.active[c] = 0;
     const double *p = S.est_pose + ((size_t)b * Tm + T - 1) * 3;
     const int gi = 0; (void)gi;

@@ -22,6 +22,7 @@ struct SimArgs {
   int32_t *meas_ptr, *meas_id, *meas_pose;
   double *meas_b, *meas_r;
   uint8_t *observed;
+  int32_t *lm_first, *ck_pos;
   double *lin_l, *est_l, *delta_l;
   double *prob, *vinfo, *metrics, *dist, *rdist, *plan;
   int32_t *plan_cursor;
@@ -78,6 +79,7 @@ __device__ void measure_append(const SimArgs &a, int b, int k, const double *noi
         const double qx = zr * cb, qy = zr * sb;
         const double gx = ex + ec * qx - es * qy, gy = ey + es * qx + ec * qy;
         a.observed[(size_t)b * Lt + id] = 1;
+        a.lm_first[(size_t)b * Lt + id] = k;
         const size_t li = ((size_t)b * Lt + id) * 2;
         a.lin_l[li] = gx; a.lin_l[li + 1] = gy;
         a.est_l[li] = gx; a.est_l[li + 1] = gy;
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(32) k_reset(SimArgs a, const uint8_t *mask, co
   // the mask may be the env's own `done` flag (dge_reset_done_queued): it is cleared below, after this read
   const uint64_t key = seeds ? seeds[b] : a.seed[b] + seed_stride;
   __syncwarp();
-  if (lane == 0) { a.seed[b] = key; if (episodes) atomicAdd(episodes, 1ull); }
+  if (lane == 0) { a.seed[b] = key; a.ck_pos[b] = 0; if (episodes) atomicAdd(episodes, 1ull); }
   // ---- start pose (pyss2d.py:88-95: integer x/y on the *map* half-width, whole-degree heading; q2)
   double sx, sy, sth;
   if (start) { sx = start[3 * b]; sy = start[3 * b + 1]; sth = start[3 * b + 2]; }
@@ -241,7 +243,7 @@ SimArgs make_args(dge_engine *e, uint8_t *active) {
   a.n_poses = e->n_poses; a.sim_step = e->sim_step; a.update_count = e->update_count; a.status = e->status;
   a.lin_pose = e->lin_pose; a.est_pose = e->est_pose; a.delta_pose = e->delta_pose; a.odom = e->odom;
   a.meas_ptr = e->meas_ptr; a.meas_id = e->meas_id; a.meas_pose = e->meas_pose; a.meas_b = e->meas_b; a.meas_r = e->meas_r;
-  a.observed = e->observed; a.lin_l = e->lin_l; a.est_l = e->est_l; a.delta_l = e->delta_l;
+  a.observed = e->observed; a.lm_first = e->lm_first; a.ck_pos = e->ck_pos; a.lin_l = e->lin_l; a.est_l = e->est_l; a.delta_l = e->delta_l;
   a.prob = e->prob; a.vinfo = e->vinfo; a.metrics = e->metrics; a.dist = e->dist; a.rdist = e->rdist; a.plan = e->plan; a.plan_cursor = e->plan_cursor;
   a.done = e->done; a.active = active;
   a.forced = e->forced; a.step_kind = e->step_kind;

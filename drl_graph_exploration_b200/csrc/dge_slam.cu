@@ -22,7 +22,11 @@
 //     elimination after the closed poses (chain carries, border carries, partial Schur complement, partial landmark
 //     rhs) is cached per env; a step then closes ONE pose, eliminates the newest one provisionally, inverts the Schur
 //     complement and runs the backward pass + marginals.  A step that relinearises (every relin_skip-th update, if a
-//     delta exceeds the threshold) rebuilds the cache from pose 0.  Border columns are indexed by the landmark's SLOT
+//     delta exceeds the threshold) re-eliminates from a CHECKPOINT: the variables that move are, as a rule, the poses added since
+//     the last relinearisation and the landmarks first seen from them (their linearisation points are dead-reckoned guesses),
+//     i.e. the last ~10 poses, so every rebuild also saves the elimination state three poses before its end; the next one resumes
+//     there if no moved pose (minus one: its odometry factor reaches back) and no moved landmark's first observation lies before
+//     it, else from pose 0.  Border columns are indexed by the landmark's SLOT
 //     (order of first observation since the last rebuild), so that columns never move while the cache lives.
 #include <cstdlib>
 
@@ -52,6 +56,9 @@ struct SlamArgs {
   double *ws_pose, *ws_meas, *ws_Bt, *ws_FB;
   int32_t *ws_midx;
   int32_t *lm_slot, *fc_valid;   // [B,Lt] landmark id -> border slot ; [B] number of poses the cached elimination state was saved at
+  const int32_t *lm_first;       // [B,Lt] pose at which a landmark was first observed (k_move_measure)
+  int32_t *ck_pos;               // [B] number of closed poses behind the CHECKPOINT of the elimination state (0 = none)
+  double *ck_state;              // [B, DGE_FC_WIDTH(Lt)] checkpoint, same layout as fc_state
   double *fc_state;              // [B, DGE_FC_WIDTH(Lt)] cached state: cD(6) cg(3) pad | cB [N2C][3] | gl [N2C] | S_partial [N2C][N2C]
   int incremental;               // 0: every step eliminates from pose 0 (A/B switch, DGE_SLAM_INCREMENTAL=0)
   const int32_t *order;          // nullable [B]: block -> env (cost-ordered placement, k_step_order)
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   double *FBs = wide ? gbuf + GK * 3 * N2C : lastFB + 6 * N2C;
   int *lidx = (int *)(lastFB + 6 * N2C + (wide ? 0 : 2 * GK * 3 * N2C));    // [Lt]  id -> border slot (-1 unobserved)
   int *lid = lidx + Lt;                           // [Lt]  slot -> id
-  __shared__ int s_nl, s_nl_old, s_bad;
+  __shared__ int s_nl, s_nl_old, s_bad, red_i[NT / 32];
   __shared__ unsigned char s_obs[64];
   __shared__ uint64_t s_bar[CH];   // one mbarrier per pose of the staged chunk: B0 (producer) -> B1 (consumers)
 
@@ -158,6 +165,8 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   int32_t *slot_g = a.lm_slot + (size_t)b * Lt;
   double *fc = a.fc_state + (size_t)b * DGE_FC_WIDTH(Lt);     // cD(6) cg(3) | cB | gl | S_partial
   double *fc_cB = fc + 16, *fc_gl = fc_cB + 3 * N2C, *fc_S = fc_gl + N2C;
+  double *ck = a.ck_state + (size_t)b * DGE_FC_WIDTH(Lt);     // checkpoint: same layout
+  double *ck_cB = ck + 16, *ck_gl = ck_cB + 3 * N2C, *ck_S = ck_gl + N2C;
 
   // ---------------------------------------------------------------- step 0 ---
   // ISAM2 relinearisation schedule (gtsam ISAM2::update: ++update_count; every
@@ -169,12 +178,12 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     for (int i = 0; i < CH; ++i) mbar_init(&s_bar[i], 1);
   }
   for (int j = tid; j < Lt; j += NT) { s_obs[j] = obs[j]; lidx[j] = slot_g[j]; }   // (thread 0 walks them below: no serial chain of global loads)
-  int moved = 0;
+  int moved = 0, rmin = 0x7fffffff;   // rmin: first pose whose blocks a moved variable touches
   if (a.cfg.relin_skip > 0 && uc % a.cfg.relin_skip == 0) {
     for (int k = tid; k < T; k += NT) {
       const double d0 = del[3 * k], d1 = del[3 * k + 1], d2 = del[3 * k + 2];
       if (fmax(fabs(d0), fmax(fabs(d1), fabs(d2))) >= a.cfg.relin_thresh) {
-        moved = 1;
+        moved = 1; rmin = min(rmin, k - 1);   // (the odometry factor k-1 -> k enters the blocks of pose k-1)
         const Pose3 p = dge_compose(Pose3{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]}, Pose3{d0, d1, d2});
         lin[3 * k] = p.x; lin[3 * k + 1] = p.y; lin[3 * k + 2] = p.th;
         del[3 * k] = 0; del[3 * k + 1] = 0; del[3 * k + 2] = 0;
@@ -183,33 +192,51 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     for (int j = tid; j < Lt; j += NT) {
       if (!obs[j]) continue;
       if (fmax(fabs(dell[2 * j]), fabs(dell[2 * j + 1])) >= a.cfg.relin_thresh) {
-        moved = 1;
+        moved = 1; rmin = min(rmin, a.lm_first[(size_t)b * Lt + j]);
         linl[2 * j] += dell[2 * j]; linl[2 * j + 1] += dell[2 * j + 1];
         dell[2 * j] = 0; dell[2 * j + 1] = 0;
       }
     }
   }
   // the cached elimination state is usable iff nothing was relinearised and it was saved one pose ago
-  const bool valid = !__syncthreads_or(moved) && a.incremental && T >= 2 && a.fc_valid[b] == T - 1;
-  const int k_lo = valid ? T - 2 : 0;          // poses [k_lo, T-1) are closed in this step; pose T-1 stays open
-  const int kz = valid ? T - 1 : 0;            // poses whose factors are linearised in this step
+  const int any_moved = __syncthreads_or(moved);
+  const bool valid = !any_moved && a.incremental && T >= 2 && a.fc_valid[b] == T - 1;
+  // a rebuild resumes from the checkpoint if nothing in front of it moved (block-wide minimum of rmin), else from pose 0;
+  // it leaves a new checkpoint three poses before its end
+  int c_use = 0;
+  if (!valid && a.incremental && a.ck_pos[b] > 0 && a.ck_pos[b] <= T - 2) {
+    c_use = a.ck_pos[b];
+    if (any_moved) {
+      rmin = __reduce_min_sync(0xffffffffu, rmin);
+      if (lane == 0) red_i[warp] = rmin;
+      __syncthreads();
+      int r = red_i[0];
+      for (int w = 1; w < NT / 32; ++w) r = min(r, red_i[w]);
+      if (r < c_use) c_use = 0;
+      __syncthreads();
+    }
+  }
+  const int c_new = (!valid && a.incremental && T - 3 > c_use) ? T - 3 : -1;   // position of the checkpoint this step leaves (-1: none)
+  const int k_lo = valid ? T - 2 : c_use;      // poses [k_lo, T-1) are closed in this step; pose T-1 stays open
+  const int kz = valid ? T - 1 : c_use;        // poses whose factors are linearised in this step
+  const bool append = valid || c_use > 0;      // border slots are kept and new landmarks appended (a rebuild from pose 0 renumbers them)
   if (tid == 0) {  // border slots: a rebuild numbers the observed landmarks in id order, a light step appends the new ones
     int n = 0;
-    if (!valid) {
+    if (!append) {
       for (int j = 0; j < Lt; ++j) { if (s_obs[j]) { lidx[j] = n; lid[n] = j; slot_g[j] = n; ++n; } else { lidx[j] = -1; slot_g[j] = -1; } }
     } else {
       for (int j = 0; j < Lt; ++j) { const int sl = s_obs[j] ? lidx[j] : -1; lidx[j] = sl; if (sl >= 0) { lid[sl] = j; n = max(n, sl + 1); } }
       s_nl_old = n;
       for (int j = 0; j < Lt; ++j) if (s_obs[j] && lidx[j] < 0) { lidx[j] = n; lid[n] = j; slot_g[j] = n; ++n; }
     }
-    if (!valid) s_nl_old = n;
+    if (!append) s_nl_old = n;
     s_nl = n;
   }
   // zero the sparse border inputs of this step (and, on a rebuild, the cached state)
   for (size_t i = (size_t)kz * 3 * N2C + tid; i < (size_t)T * 3 * N2C; i += NT) wBt[i] = 0.0;
   for (size_t i = (size_t)kz * Lt + tid; i < (size_t)T * Lt; i += NT) wmi[i] = 0;
   // S starts from the cached partial Schur complement (copied asynchronously: it is first touched after phase B) or from zero
-  if (valid) { for (int i = tid; i < N2C * N2C / 2; i += NT) cp_async16(S + 2 * i, fc_S + 2 * i); cp_async_commit(); }
+  if (append) { const double *src = valid ? fc_S : ck_S; for (int i = tid; i < N2C * N2C / 2; i += NT) cp_async16(S + 2 * i, src + 2 * i); cp_async_commit(); }
   else {
     for (int i = tid; i < N2C * N2C; i += NT) S[i] = 0.0;
     for (int i = tid; i < 16 + 4 * N2C; i += NT) fc[i] = 0.0;
@@ -320,22 +347,28 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   // column c lives on thread NT-1-c so that warp 0 carries columns only when n2 > NT - 32.
   const int ccol = NT - 1 - tid;
   const bool colv = ccol < n2;
+  double sdB0 = 0, sdB1 = 0;   // landmark-landmark blocks of the factors at c_new and behind (added to S after the checkpoint)
   {
     const int c = ccol, jr = c >> 1, comp = c & 1;
     double cD[6] = {0, 0, 0, 0, 0, 0}, cg[3] = {0, 0, 0}, gp[3] = {0, 0, 0};        // warp-0 carried state
     double cB[3] = {0, 0, 0}, sd0 = 0, sd1 = 0, glc = 0;                             // column state
-    if (valid) {   // resume behind the closed poses: chain carries, the rhs the last closed pose parked for its successor, border carries
+    double sdA0 = 0, sdA1 = 0, glB = 0;   // checkpoint split of the landmark terms: diagonal blocks of the factors in front of c_new, rhs of those behind
+    if (append) {   // resume behind the closed poses (light step) / behind the checkpoint (rebuild): chain carries, the rhs the last closed pose parked for its successor, border carries
+      const double *rs = valid ? fc : ck;
       if (warp == 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) cD[i] = fc[i];
+        for (int i = 0; i < 6; ++i) cD[i] = rs[i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { cg[i] = fc[6 + i]; gp[i] = k_lo > 0 ? wsp[(size_t)(k_lo - 1) * WS_POSE + 18 + i] : 0.0; }
+        for (int i = 0; i < 3; ++i) { cg[i] = rs[6 + i]; gp[i] = k_lo > 0 ? wsp[(size_t)(k_lo - 1) * WS_POSE + 18 + i] : 0.0; }
       }
       if (colv) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) cB[i] = fc_cB[3 * c + i];
-        glc = fc_gl[c];
+        for (int i = 0; i < 3; ++i) cB[i] = rs[16 + 3 * c + i];
+        glc = rs[16 + 3 * N2C + c];
       }
+    }
+    if (c_new >= 0 && ccol < N2C && !colv) {   // columns without a landmark yet: zero in the checkpoint (a later slot resumes from zeros)
+      ck_cB[3 * ccol] = 0.0; ck_cB[3 * ccol + 1] = 0.0; ck_cB[3 * ccol + 2] = 0.0; ck_gl[ccol] = 0.0;
     }
     for (int k0 = k_lo; k0 < T; k0 += CH) {
       const int kc = min(CH, T - k0);
@@ -349,11 +382,12 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
         const long long tb0 = (a.clocks && tid == 0) ? clock64() : 0;
         for (int kk = 0; kk < kc; ++kk) {
           double *w = stage + kk * SW;
-          if (k0 + kk == T - 1 && lane == 0) {   // the closed poses end here: this is the state the next step resumes from
+          if ((k0 + kk == T - 1 || k0 + kk == c_new) && lane == 0) {   // the closed poses end here: the state the next step resumes from (/ the checkpoint)
+            double *sv = (k0 + kk == c_new) ? ck : fc;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) fc[i] = cD[i];
+            for (int i = 0; i < 6; ++i) sv[i] = cD[i];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) fc[6 + i] = cg[i];
+            for (int i = 0; i < 3; ++i) sv[6 + i] = cg[i];
           }
           const double d0 = w[0] + cD[0], d1 = w[1] + cD[1], d2 = w[2] + cD[2], d3 = w[3] + cD[3], d4 = w[4] + cD[4], d5 = w[5] + cD[5];
           const double g0 = w[6] + cg[0] + gp[0], g1 = w[7] + cg[1] + gp[1], g2 = w[8] + cg[2] + gp[2];
@@ -401,8 +435,12 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
               }
 #pragma unroll
               for (int u = 0; u < 8; ++u)
-                if (p1[u]) { sd0 += m0[u]; sd1 += m1[u]; glc += m2[u]; }
+                if (p1[u]) {
+                  if (k + u < c_new) { sdA0 += m0[u]; sdA1 += m1[u]; glc += m2[u]; }
+                  else { sd0 += m0[u]; sd1 += m1[u]; glB += m2[u]; }
+                }
             }
+            glc += glB;
           }
           // B1: border column c.  Bt = B_k + carry, FB = D~^-1 Bt, carry' = -U^T FB, rhs; border rows prefetched
           // 4 poses ahead (an L2 round trip is longer than one pose of the chain)
@@ -422,6 +460,10 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
                 if (open) {   // state behind the closed poses (see B0)
                   fc_cB[3 * c] = cB[0]; fc_cB[3 * c + 1] = cB[1]; fc_cB[3 * c + 2] = cB[2];
                   fc_gl[c] = glc;
+                }
+                if (k == c_new) {   // checkpoint: carries into pose c_new; rhs without the factors at c_new and behind
+                  ck_cB[3 * c] = cB[0]; ck_cB[3 * c + 1] = cB[1]; ck_cB[3 * c + 2] = cB[2];
+                  ck_gl[c] = glc - glB;
                 }
                 const double b0 = nb[u][0] + cB[0], b1 = nb[u][1] + cB[1], b2 = nb[u][2] + cB[2];
                 if (kk + 4 < kc) {
@@ -457,11 +499,13 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     // S = cached partial Schur complement (zero on a rebuild) + the landmark-landmark blocks gathered above; gl = reduced rhs
     cp_async_wait_all();
     __syncthreads();
-    if (colv) {
-      S[(2 * jr) * ldS + c] += sd0;
-      S[(2 * jr + 1) * ldS + c] += sd1;
+    if (colv) {   // (the blocks of the factors at c_new and behind follow after the checkpoint of S is saved)
+      S[(2 * jr) * ldS + c] += (c_new >= 0) ? sdA0 : sd0;
+      S[(2 * jr + 1) * ldS + c] += (c_new >= 0) ? sdA1 : sd1;
       gl[c] = glc;
     }
+    if (c_new < 0) { sd0 = 0; sd1 = 0; }
+    sdB0 = sd0; sdB1 = sd1;
   }
   __syncthreads();
 
@@ -471,16 +515,9 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   // memory GK poses at a time (one linear, coalesced copy per operand); every thread keeps up to two 4x4
   // tiles of the upper triangle in registers across all chunks; the result is mirrored.
   const int Tc = T - 1;                         // closed poses [k_lo, Tc) enter the cached partial sum; the open pose is added after the save
-  if (valid) {   // a light step closes one pose: its term Bt^T FB (rank 3) comes straight from shared memory
-    for (int i = tid; i < n2 * ldS; i += NT) {
-      const int r = i / ldS, cc = i - r * ldS;
-      if (r <= cc && cc < n2) {
-        const double v = S[i] - (lastB[r] * lastFB[cc] + lastB[N2C + r] * lastFB[N2C + cc] + lastB[2 * N2C + r] * lastFB[2 * N2C + cc]);
-        S[i] = v;
-        S[cc * ldS + r] = v;
-      }
-    }
-  } else if (n2 > 0) {
+  // Schur-complement update over the closed poses [ka, kb): S -= sum_k Bt_k^T FB_k
+  auto schur = [&](const int ka, const int kb) {
+    if (n2 <= 0 || kb <= ka) return;
     const int nt = (n2 + 3) / 4;
     const int ntile = nt * (nt + 1) / 2;
     if (ntile <= NT / 2 && N2C <= 64) {
@@ -498,17 +535,17 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
       double *gA = gbuf, *gB = gbuf + GK * 3 * N2C;
       constexpr int PF = 6;                                     // 2 operands x GK*3*N2C / NT <= 2 * PF  (N2C <= 64)
       double pa[PF], pb[PF];
-      const int rows0 = min(GK, Tc - k_lo) * 3;
+      const int rows0 = min(GK, kb - ka) * 3;
       {
-        const size_t base0 = (size_t)k_lo * 3 * N2C;
+        const size_t base0 = (size_t)ka * 3 * N2C;
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
           const int i = tid + u * NT;
           pa[u] = (i < rows0 * N2C) ? wBt[base0 + i] : 0.0; pb[u] = (i < rows0 * N2C) ? wFB[base0 + i] : 0.0;
         }
       }
-      for (int k0 = k_lo; k0 < Tc; k0 += GK) {
-        const int rows = min(GK, Tc - k0) * 3;
+      for (int k0 = ka; k0 < kb; k0 += GK) {
+        const int rows = min(GK, kb - k0) * 3;
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
@@ -516,8 +553,8 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
           if (i < rows * N2C) { gA[i] = pa[u]; gB[i] = pb[u]; }
         }
         __syncthreads();
-        if (k0 + GK < Tc) {
-          const int rown = min(GK, Tc - k0 - GK) * 3;
+        if (k0 + GK < kb) {
+          const int rown = min(GK, kb - k0 - GK) * 3;
           const size_t base = (size_t)(k0 + GK) * 3 * N2C;
 #pragma unroll
           for (int u = 0; u < PF; ++u) {
@@ -571,8 +608,8 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
         for (int i = 0; i < 16; ++i) acc[s][i] = 0.0;
       }
       double *gA = gbuf, *gB = gbuf + GK * 3 * N2C;
-      for (int k0 = k_lo; k0 < Tc; k0 += GK) {
-        const int rows = min(GK, Tc - k0) * 3;
+      for (int k0 = ka; k0 < kb; k0 += GK) {
+        const int rows = min(GK, kb - k0) * 3;
         __syncthreads();
         for (int i = tid; i < rows * N2C; i += NT) { gA[i] = wBt[(size_t)k0 * 3 * N2C + i]; gB[i] = wFB[(size_t)k0 * 3 * N2C + i]; }
         __syncthreads();
@@ -616,7 +653,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
         double acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-        for (int ki = 3 * k_lo; ki < 3 * Tc; ++ki) {
+        for (int ki = 3 * ka; ki < 3 * kb; ++ki) {
           const double *br = wBt + (size_t)ki * N2C + r0, *fc = wFB + (size_t)ki * N2C + c0;
           double av[4], bv[4];
 #pragma unroll
@@ -637,6 +674,26 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
           }
       }
     }
+    };
+  if (valid) {   // a light step closes one pose: its term Bt^T FB (rank 3) comes straight from shared memory
+    for (int i = tid; i < n2 * ldS; i += NT) {
+      const int r = i / ldS, cc = i - r * ldS;
+      if (r <= cc && cc < n2) {
+        const double v = S[i] - (lastB[r] * lastFB[cc] + lastB[N2C + r] * lastFB[N2C + cc] + lastB[2 * N2C + r] * lastFB[2 * N2C + cc]);
+        S[i] = v;
+        S[cc * ldS + r] = v;
+      }
+    }
+  } else if (c_new >= 0) {   // rebuild that leaves a checkpoint: the sum in front of c_new first, snapshot, then the rest
+    schur(k_lo, c_new);
+    __syncthreads();
+    for (int i = tid; i < N2C * ldS; i += NT) ck_S[i] = S[i];     // (every row: later slots must find zeros)
+    __syncthreads();
+    if (colv) { S[(2 * (ccol >> 1)) * ldS + ccol] += sdB0; S[(2 * (ccol >> 1) + 1) * ldS + ccol] += sdB1; }
+    __syncthreads();
+    schur(c_new, Tc);
+  } else {
+    schur(k_lo, Tc);
   }
   __syncthreads();
   // S now is the partial Schur complement behind the closed poses: cache it, then subtract the open pose's term Bt^T FB (rank 3)
@@ -802,21 +859,24 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
       cp_async_wait_all();
       __syncthreads();                                  // this chunk's inputs have landed; the previous chunk's E has finished reading Wc / its stage
       if (warp == 0) {
-        // D0: scalar, identical on every lane (see B0)
+        // D0 across lanes: lane l < 9 owns entry (i, j) = (l / 3, l % 3) of P_k and (j == 0) component i of u_k.  Per pose a lane forms
+        // row i of M = FU P (9 FMAs), its entry of P' = Dinv + M FU^T and its component of u' = f - FU u; the new P / u go round the warp
+        // by shuffles (the same ~13 dependent FMAs instead of ~60 scalar ones issued redundantly on every lane).  P stays full 3x3 in
+        // every lane; symmetric by construction up to rounding: the packed upper triangle is what is published, like the scalar version.
+        const int li = lane < 9 ? lane / 3 : 0, lj = lane < 9 ? lane % 3 : 0;
+        const int ta = min(li, lj), tb = max(li, lj), p6 = ta * 3 + tb - ta * (ta + 1) / 2;   // packed upper-triangle index of (i, j)
         for (int kk = kc - 1; kk >= 0; --kk) {
           double *w = sd + kk * SWD;   // Dinv(6) FU(9) f(3) | P(6) u(3)
-          const double f00 = w[6], f01 = w[7], f02 = w[8], f10 = w[9], f11 = w[10], f12 = w[11], f20 = w[12], f21 = w[13], f22 = w[14];
-          // M = FU P
-          const double m00 = f00 * P0 + f01 * P1 + f02 * P2, m01 = f00 * P1 + f01 * P3 + f02 * P4, m02 = f00 * P2 + f01 * P4 + f02 * P5;
-          const double m10 = f10 * P0 + f11 * P1 + f12 * P2, m11 = f10 * P1 + f11 * P3 + f12 * P4, m12 = f10 * P2 + f11 * P4 + f12 * P5;
-          const double m20 = f20 * P0 + f21 * P1 + f22 * P2, m21 = f20 * P1 + f21 * P3 + f22 * P4, m22 = f20 * P2 + f21 * P4 + f22 * P5;
-          // u' = f - FU u
-          const double v0 = w[15] - (f00 * un0 + f01 * un1 + f02 * un2), v1 = w[16] - (f10 * un0 + f11 * un1 + f12 * un2), v2 = w[17] - (f20 * un0 + f21 * un1 + f22 * un2);
-          // P' = Dinv + M FU^T
-          P0 = w[0] + m00 * f00 + m01 * f01 + m02 * f02; P1 = w[1] + m00 * f10 + m01 * f11 + m02 * f12; P2 = w[2] + m00 * f20 + m01 * f21 + m02 * f22;
-          P3 = w[3] + m10 * f10 + m11 * f11 + m12 * f12; P4 = w[4] + m10 * f20 + m11 * f21 + m12 * f22; P5 = w[5] + m20 * f20 + m21 * f21 + m22 * f22;
-          un0 = v0; un1 = v1; un2 = v2;
-          if (lane == 0) { w[18] = P0; w[19] = P1; w[20] = P2; w[21] = P3; w[22] = P4; w[23] = P5; w[24] = v0; w[25] = v1; w[26] = v2; }
+          const double fi0 = w[6 + 3 * li], fi1 = w[7 + 3 * li], fi2 = w[8 + 3 * li];      // row i of FU
+          const double fj0 = w[6 + 3 * lj], fj1 = w[7 + 3 * lj], fj2 = w[8 + 3 * lj];      // row j of FU
+          // row i of M = FU P
+          const double m0 = fi0 * P0 + fi1 * P1 + fi2 * P2, m1 = fi0 * P1 + fi1 * P3 + fi2 * P4, m2 = fi0 * P2 + fi1 * P4 + fi2 * P5;
+          const double pn = w[p6] + m0 * fj0 + m1 * fj1 + m2 * fj2;                          // P'(i, j)
+          const double vn = w[15 + li] - (fi0 * un0 + fi1 * un1 + fi2 * un2);                // u'(i)
+          P0 = __shfl_sync(0xffffffffu, pn, 0); P1 = __shfl_sync(0xffffffffu, pn, 1); P2 = __shfl_sync(0xffffffffu, pn, 2);
+          P3 = __shfl_sync(0xffffffffu, pn, 4); P4 = __shfl_sync(0xffffffffu, pn, 5); P5 = __shfl_sync(0xffffffffu, pn, 8);
+          un0 = __shfl_sync(0xffffffffu, vn, 0); un1 = __shfl_sync(0xffffffffu, vn, 3); un2 = __shfl_sync(0xffffffffu, vn, 6);
+          if (lane == 0) { w[18] = P0; w[19] = P1; w[20] = P2; w[21] = P3; w[22] = P4; w[23] = P5; w[24] = un0; w[25] = un1; w[26] = un2; }
         }
       }
       if (colv) {
@@ -866,29 +926,54 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
             va[0] += w[0] * d; va[1] += w[1] * d; va[2] += w[2] * d; vb[0] += w[3] * d; vb[1] += w[4] * d; vb[2] += w[5] * d;
           }
         }
+        // reduction over the columns: the two halves of the warp first trade poses (lower half keeps pose a, upper half pose b:
+        // 9 exchanges), then 4 butterfly steps inside each half -- 45 shuffled values instead of 90
+        double r9[9];
+        {
+          const bool up = lane >= 16;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { qa[i] = warp_sum(qa[i]); qb[i] = warp_sum(qb[i]); }
+          for (int i = 0; i < 6; ++i) {
+            const double mine = up ? qb[i] : qa[i], send = up ? qa[i] : qb[i];
+            r9[i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { va[i] = warp_sum(va[i]); vb[i] = warp_sum(vb[i]); }
-        const int kk = 2 * warp + lane;                 // lanes 0 / 1 finish the pair's two poses
-        if (lane < 2 && kk < kc) {
+          for (int i = 0; i < 3; ++i) {
+            const double mine = up ? vb[i] : va[i], send = up ? va[i] : vb[i];
+            r9[6 + i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) r9[i] += __shfl_xor_sync(0xffffffffu, r9[i], o);
+        }
+        const int kk = 2 * warp + (lane >> 4);          // lanes 0 / 16 hold the sums of the pair's two poses
+        if ((lane & 15) == 0 && kk < kc) {
           const int k = k0 + kk;
           const double *w = sd + kk * SWD + 18;         // P(6) u(3)
-          double C[6], I[6];
+          // Sigma_kk = P_k + q, delta_k = u_k - v; the inverse (information) and the estimate follow in one pass over all poses below
+          double *pc = a.pose_cov + ((size_t)b * Tmax + k) * 6;
+          double tr = 0;
 #pragma unroll
-          for (int i = 0; i < 6; ++i) C[i] = w[i] + (lane ? qb[i] : qa[i]);
-          const double d0 = w[6] - (lane ? vb[0] : va[0]), d1 = w[7] - (lane ? vb[1] : va[1]), d2 = w[8] - (lane ? vb[2] : va[2]);
-          dge_sym3_inv(C, I);
-          double *pc = a.pose_cov + ((size_t)b * Tmax + k) * 6, *pi = a.pose_info + ((size_t)b * Tmax + k) * 6;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) { pc[i] = C[i]; pi[i] = I[i]; }
-          del[3 * k] = d0; del[3 * k + 1] = d1; del[3 * k + 2] = d2;
-          const Pose3 e = dge_compose(Pose3{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]}, Pose3{d0, d1, d2});
-          est[3 * k] = e.x; est[3 * k + 1] = e.y; est[3 * k + 2] = e.th;
-          tmax = fmax(tmax, C[0] + C[3] + C[5]);
+          for (int i = 0; i < 6; ++i) { const double cv = w[i] + r9[i]; pc[i] = cv; if (i == 0 || i == 3 || i == 5) tr += cv; }
+          del[3 * k] = w[6] - r9[6]; del[3 * k + 1] = w[7] - r9[7]; del[3 * k + 2] = w[8] - r9[8];
+          tmax = fmax(tmax, tr);
         }
       }
     }
+  }
+  __syncthreads();
+  // estimate = theta (+) delta, information = Sigma_kk^-1 (SLAM2D.cpp:400): one thread per pose, all poses side by side
+  for (int k = tid; k < T; k += NT) {
+    const double *pc = a.pose_cov + ((size_t)b * Tmax + k) * 6;
+    double C[6], I[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) C[i] = pc[i];
+    dge_sym3_inv(C, I);
+    double *pi = a.pose_info + ((size_t)b * Tmax + k) * 6;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) pi[i] = I[i];
+    const Pose3 e = dge_compose(Pose3{lin[3 * k], lin[3 * k + 1], lin[3 * k + 2]}, Pose3{del[3 * k], del[3 * k + 1], del[3 * k + 2]});
+    est[3 * k] = e.x; est[3 * k + 1] = e.y; est[3 * k + 2] = e.th;
   }
   if (a.clocks && tid == 0) a.clocks[12 * b +5] = clock64();
 #pragma unroll
@@ -917,7 +1002,9 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     a.metrics[8 * b + 5] = m;         // max_uncertainty_of_trajectory        exploration_env.py:190-194
     a.update_count[b] = uc;
     a.fc_valid[b] = s_bad ? 0 : T;
-    if (a.clocks) { a.clocks[12 * b +6] = clock64(); a.clocks[12 * b +7] = T; a.clocks[12 * b + 10] = valid ? 1 : 0; a.clocks[12 * b + 11] = n2; }
+    if (!valid) a.ck_pos[b] = s_bad ? 0 : (c_new >= 0 ? c_new : c_use);
+    else if (s_bad) a.ck_pos[b] = 0;
+    if (a.clocks) { a.clocks[12 * b +6] = clock64(); a.clocks[12 * b +7] = T; a.clocks[12 * b + 10] = valid ? 1 : (c_use > 0 ? 2 : 0); a.clocks[12 * b + 11] = n2; }
     if (s_bad) a.status[b] = 1;
   }
 }
@@ -972,6 +1059,7 @@ int dge_launch_slam(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
   a.observed = e->observed; a.lin_l = e->lin_l; a.est_l = e->est_l; a.delta_l = e->delta_l; a.land_cov = e->land_cov;
   a.ws_pose = e->ws_pose; a.ws_meas = e->ws_meas; a.ws_Bt = e->ws_Bt; a.ws_FB = e->ws_FB; a.ws_midx = e->ws_midx;
   a.lm_slot = e->lm_slot; a.fc_valid = e->fc_valid; a.fc_state = e->fc_state;
+  a.lm_first = e->lm_first; a.ck_pos = e->ck_pos; a.ck_state = e->ck_state;
   static const int incremental = [] { const char *v = getenv("DGE_SLAM_INCREMENTAL"); return (v && v[0] == '0') ? 0 : 1; }();
   a.incremental = incremental;
   static const int ordered = [] { const char *v = getenv("DGE_STEP_ORDER"); return (v && v[0] == '1') ? 1 : 0; }();   // off by default: measured no gain (r02)
