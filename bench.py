@@ -210,13 +210,15 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
     from drl_graph_exploration_b200.trainer import VecDQNTrainer
     ms, B = 40, ENVS_PER_GPU
     cfg = EnvConfig(map_size=ms)
-    if args.train_gemm != "fp32":
+    if args.train_gemm in ("fp32", "tc3"):
         Networks.set_matmul_precision("tc3", train=args.train_gemm)
     env = VecExplorationEnv(B, cfg=cfg, max_poses=384, device=local, seed0=rank * 100000)
     env.reset()
     torch.manual_seed(0)                      # identical replicas on every rank
     pol, tgt = Networks.GCN().to(env.device), Networks.GCN().to(env.device)
     tr = VecDQNTrainer(env, pol, tgt, observe=0, train_steps_per_tick=args.train_steps_per_tick, seed=rank, overlap=not args.no_overlap)
+    if args.train_gemm != "native":            # A/B: the autograd path with torch's Adam
+        tr.optimizer = torch.optim.Adam(pol.parameters(), lr=1e-5)
     for _ in range(40):                       # prefill the replay (untimed): every rank needs one minibatch of transitions
         tr.tick(learn=False)
     assert tr.replay.size >= tr.dqn.BATCH, "prefill too short"
@@ -248,7 +250,7 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
     # the one collective of the path, timed alone: the 4.0 MB flat gradient bucket, CUDA events, max over ranks
     ar_us = None
     if world > 1:
-        flat = tr.dqn._bucket.flat
+        flat = (tr.dqn._bucket or tr.optimizer.bucket).flat
         for _ in range(5):
             dist.all_reduce(flat)
         torch.cuda.synchronize(); dist.barrier()
@@ -327,11 +329,15 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
         batches.append(synth_graph_batch(G, sizes, rng, dev))
     torch.manual_seed(0)
     model = Networks.GCN().to(dev)
-    if args.train_gemm != "fp32":
+    from drl_graph_exploration_b200.dist import FlatGradBucket, NativeAdam
+    native = args.train_gemm == "native"
+    if native:
+        opt = NativeAdam(model.parameters(), lr=1e-5)
+        bucket = opt.bucket
+    else:
         Networks.set_matmul_precision("tc3", train=args.train_gemm)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
-    from drl_graph_exploration_b200.dist import FlatGradBucket
-    bucket = FlatGradBucket(model.parameters())
+        opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+        bucket = FlatGradBucket(model.parameters())
     flush = None if args.no_flush_l2 else L2Flush(dev)
     nodes = sum(b[0].size(0) for b in batches) / nb
     edges = sum(b[1].size(1) for b in batches) / nb
@@ -343,6 +349,13 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
 
     def fwd_bwd(i):
         x, ei, w, bt = batches[i % nb]
+        if native:   # DeepQ.train on the native path: forward (dropout 0.5) + cost + backward in one call, all-reduce, clamp + Adam in one kernel
+            d = Data(x, ei, w, bt)
+            gnn.gcn_train_step(model, x, Networks._structure(d, x.size(0)), None, None, 1.0 / G, 0.5)
+            if world > 1:
+                dist.all_reduce(bucket.flat)
+            opt.step(clamp=0.5, gscale=1.0 / world)
+            return
         bucket.zero_()
         q = model(Data(x, ei, w, bt), 0.5, batch=bt)
         loss = (q.view(-1) ** 2).sum() / G
@@ -376,7 +389,7 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
         sec_f, sec_b = res["forward"][0], res["forward_backward"][0]
         gemm_flops = 2.0 * nodes * 1000 * 1000                     # the one [N,1000]x[1000,1000] product of a forward pass
         out = {"metric": "GNN samples/sec", "value": world * G * n_steps / sec_f, "unit": "graphs/s", "n_gpus": world, "steps": n_steps, "warmup": args.warmup,
-               "ms_per_step": 1e3 * sec_f / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMM, fp32 accumulate)",
+               "ms_per_step": 1e3 * sec_f / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMM, fp32 accumulate)", "train_path": "native (gnn.gcn_train_step + dist.NativeAdam)" if native else "autograd",
                "data": "synthetic",
                "config": {"workload": "64 graphs/batch, 8..512 nodes mixed, GCN (BASELINE configs[4])", "mean_nodes_per_batch": nodes, "mean_edges_per_batch": edges,
                           "train_gemm": args.train_gemm, "l2": L2Flush.HOW if flush is not None else "not flushed"},
@@ -499,7 +512,9 @@ def main():
     ap.add_argument("--workload", default="policy", choices=["policy", "train", "gnn"],
                     help="policy = BASELINE configs[1] (the headline line); train = configs[2] DQN training; gnn = configs[4] GNN fwd / fwd+bwd")
     ap.add_argument("--train-steps-per-tick", type=int, default=1)
-    ap.add_argument("--train-gemm", default="fp32", choices=["fp32", "tc3"], help="node-MLP GEMM under autograd (Networks.set_matmul_precision)")
+    ap.add_argument("--train-gemm", default="native", choices=["native", "fp32", "tc3"],
+                    help="training step of the GCN: native = gnn.gcn_train_step + dist.NativeAdam (hand-written kernels, tcgen05 3xTF32 GEMMs; the product path); "
+                         "fp32 / tc3 = autograd with the library fp32 GEMM / the tcgen05 GEMM for forward and grad-input (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -103,11 +103,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
               const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
-              float *__restrict__ C, int M, const int32_t *__restrict__ M_dev, int N, int K, int ldc) {
+              float *__restrict__ C, int M, const int32_t *__restrict__ M_dev, int N, int K, int ldc, int splits) {
+  // splits > 1 (weight-gradient shape: few output tiles, a long K): work item = (tile, K slice); the slices of a tile add their
+  // partial products into C with vector atomics (C zeroed by the caller; with two slices the sum is order-independent)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = M_dev ? min(M, *M_dev) : M;
   const int n_tiles = (N + BN - 1) / BN;
-  const int total = ((rows + BM - 1) / BM) * n_tiles;
+  const int total = ((rows + BM - 1) / BM) * n_tiles * splits;
   if ((int)blockIdx.x >= total) return;                    // uniform per CTA, before any barrier / allocation
   extern __shared__ uint8_t smem_raw[];
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B tiles want 1024-byte alignment
@@ -115,6 +117,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16, slot = tempty0 + 16;
   uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (slot - smem_u32(smem_raw)));
   const int num_kb = (K + BK - 1) / BK;
+  auto kb_lo = [&](int w) { return (int)((long long)(w % splits) * num_kb / splits); };
+  auto kb_hi = [&](int w) { return (int)((long long)(w % splits + 1) * num_kb / splits); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -133,9 +137,10 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
   if (warp == 0) {
     if (lane == 0) {                                       // ---- TMA producer
       int it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int t = w / splits;
         const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_lo(w), ke = kb_hi(w); kb < ke; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
           const uint32_t st = tiles + s * STAGE_BYTES, fb = full0 + 8 * s;
@@ -150,12 +155,13 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
   } else if (warp == 1) {
     if (lane == 0) {                                       // ---- MMA issuer (one thread drives the tensor core)
       int it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++lt) {
         const int acc = lt & 1;
         mbar_wait(tempty0 + 8 * acc, ((lt >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator (free at first use)
         tc_fence_after();
         const uint32_t td = tmem + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int kb0 = kb_lo(w);
+        for (int kb = kb0, ke = kb_hi(w); kb < ke; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
           tc_fence_after();
@@ -165,7 +171,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
             const uint32_t off = k * UMMA_K * 4;           // 32 bytes along K inside the swizzled 128-byte row
             const uint64_t ah = smem_desc(st + off), al = smem_desc(st + TILE_BYTES + off);
             const uint64_t bh = smem_desc(st + 2 * TILE_BYTES + off), bl = smem_desc(st + 3 * TILE_BYTES + off);
-            umma_tf32(td, al, bh, (kb | k) ? 1u : 0u);     // small terms first
+            umma_tf32(td, al, bh, (kb != kb0 || k) ? 1u : 0u);     // small terms first
             umma_tf32(td, ah, bl, 1u);
             umma_tf32(td, ah, bh, 1u);
           }
@@ -177,7 +183,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
   } else {                                                 // ---- epilogue: TMEM -> registers -> C
     const int q = warp & 3;                                // a warp reaches TMEM lanes [32 (warp % 4), +32)
     int lt = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++lt) {
+      const int t = w / splits;
       const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
       const int acc = lt & 1;
       mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
@@ -193,12 +200,13 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int col = n0 + c * 32 + 4 * i;
+            const float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
             if (col + 3 < N) {
-              *reinterpret_cast<float4 *>(crow + c * 32 + 4 * i) =
-                  make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+              if (splits > 1) atomicAdd(reinterpret_cast<float4 *>(crow + c * 32 + 4 * i), v);
+              else *reinterpret_cast<float4 *>(crow + c * 32 + 4 * i) = v;
             } else {
               for (int j = 0; j < 4; ++j)
-                if (col + j < N) crow[c * 32 + 4 * i + j] = __uint_as_float(r[4 * i + j]);
+                if (col + j < N) { if (splits > 1) atomicAdd(crow + c * 32 + 4 * i + j, __uint_as_float(r[4 * i + j])); else crow[c * 32 + 4 * i + j] = __uint_as_float(r[4 * i + j]); }
             }
           }
         }
@@ -268,11 +276,11 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 // [rows, K] fp32 row-major, box = 128 rows x 32 columns (128 bytes), 128-byte swizzle, out-of-bounds reads give 0
-bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t K) {
+bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t K, uint64_t pitch = 0) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
   if (!enc) return false;
   const cuuint64_t dims[2] = {K, rows};
-  const cuuint64_t strides[1] = {K * sizeof(float)};
+  const cuuint64_t strides[1] = {(pitch ? pitch : K) * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
   const cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -296,13 +304,19 @@ extern "C" int dge_gemm_prep_weight(int K, int N, const float *W, float *Wt_hi, 
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-extern "C" int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, const float *Bt_hi,
-                               const float *Bt_lo, float *C, int ldc, void *stream) {
-  if (M < 0 || N <= 0 || K <= 0 || (K & 3) || (ldc & 3) || ldc < N || !A_hi || !A_lo || !Bt_hi || !Bt_lo || !C) return -1;
+// general form: operand row pitches lda / ldb (floats, multiples of 4, >= K; 0 = K) and `splits` K slices per output tile
+// (splits > 1: C must be zeroed by the caller, partial products are added with atomics).  splits = 0: chosen here -- as many
+// slices as fill the SMs when the output has fewer tiles than the machine has SMs and K is long (the weight-gradient shape).
+extern "C" int dge_gemm_tf32x3_ex(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, int lda, const float *Bt_hi,
+                                  const float *Bt_lo, int ldb, float *C, int ldc, int splits, void *stream) {
+  if (M < 0 || N <= 0 || K <= 0 || (ldc & 3) || ldc < N || !A_hi || !A_lo || !Bt_hi || !Bt_lo || !C) return -1;
+  if (!lda) lda = K;
+  if (!ldb) ldb = K;
+  if ((lda & 3) || (ldb & 3) || lda < K || ldb < K) return -1;
   if (((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)Bt_hi | (uintptr_t)Bt_lo | (uintptr_t)C) & 15) return -1;
   if (M == 0) return 0;
   CUtensorMap mAh, mAl, mBh, mBl;
-  if (!make_map(&mAh, A_hi, M, K) || !make_map(&mAl, A_lo, M, K) || !make_map(&mBh, Bt_hi, N, K) || !make_map(&mBl, Bt_lo, N, K)) return -2;
+  if (!make_map(&mAh, A_hi, M, K, lda) || !make_map(&mAl, A_lo, M, K, lda) || !make_map(&mBh, Bt_hi, N, K, ldb) || !make_map(&mBl, Bt_lo, N, K, ldb)) return -2;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM) != cudaSuccess) return -2;
@@ -314,7 +328,20 @@ extern "C" int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const 
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
   }
   const long long tiles_cap = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
-  const unsigned grid = (unsigned)(tiles_cap < n_sm ? tiles_cap : n_sm);
-  k_gemm_tf32x3<<<grid, GEMM_THREADS, GEMM_SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc);
+  const int num_kb = (K + BK - 1) / BK;
+  if (splits <= 0) {
+    splits = 1;
+    if (!M_dev && tiles_cap < n_sm && num_kb >= 64) { splits = (int)(n_sm / tiles_cap); if (splits > num_kb / 16) splits = num_kb / 16; if (splits < 1) splits = 1; }
+  }
+  if (splits > num_kb) splits = num_kb;
+  const long long work = tiles_cap * splits;
+  const unsigned grid = (unsigned)(work < n_sm ? work : n_sm);
+  k_gemm_tf32x3<<<grid, GEMM_THREADS, GEMM_SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc, splits);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, const float *Bt_hi,
+                               const float *Bt_lo, float *C, int ldc, void *stream) {
+  if (K & 3) return -1;
+  return dge_gemm_tf32x3_ex(M, M_dev, N, K, A_hi, A_lo, 0, Bt_hi, Bt_lo, 0, C, ldc, 1, stream);
 }

@@ -323,6 +323,76 @@ def tc_matmul(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     return _TcMatmulFn.apply(x, w)
 
 
+# ------------------------------------------------------------- DQN training step of the GCN, one native call ---
+_train_ws: dict = {}
+_train_seed = [0x5DEECE66D]
+
+
+def _train_lib():
+    L = _gemm_lib()
+    if not hasattr(L, "_train_ready"):
+        L.dge_gcn_train_ws_floats.restype = ctypes.c_int64
+        L.dge_gcn_train_ws_floats.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.dge_gcn_train_step.argtypes = [ctypes.c_int] * 3 + [_vp] * 20 + [ctypes.c_float, ctypes.c_float, ctypes.c_uint64] + [_vp] * 10
+        L.dge_gemm_tf32x3_ex.argtypes = [ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp]
+        L.dge_clamp_adam_step.argtypes = [ctypes.c_int64, _vp, _vp, _vp, _vp, _vp] + [ctypes.c_float] * 6 + [_vp]
+        L._train_ready = True
+    return L
+
+
+def gcn_train_eligible(model) -> bool:
+    """Networks.GCN itself (the DQN Q-network) on CUDA with the shapes the native step takes."""
+    return QForwardPlan.eligible(model) and all(p.grad is not None and p.grad.is_contiguous() for p in model.parameters())
+
+
+def gcn_train_step(model, x: torch.Tensor, gs: GraphStructure, action, y, inv_batch: float, drop_p: float, seed: Optional[int] = None,
+                   return_debug: bool = False):
+    """Forward (functional dropout p), DeepQ.cost and the whole backward pass of ``Networks.GCN`` in ONE native call
+    (``dge_gcn_train_step``, csrc/dge_train.cu: 13 launches, the three [nodes,1000]x[1000,1000]-shaped products on the tcgen05
+    3xTF32 kernel, no autograd graph).  The gradients are WRITTEN into the parameters' ``.grad`` buffers (which must exist and be
+    contiguous: ``dist.FlatGradBucket``); returns (loss, q) as device tensors -- nothing is read back.  ``action`` / ``y``: [N] float
+    tensors (None: a = 1 / y = 0, i.e. loss = sum(q^2) * inv_batch)."""
+    global launch_count
+    _need_cuda(x, "gcn_train_step")
+    L = _train_lib()
+    dev = x.device
+    x = x.contiguous().float()
+    N, cin = x.shape
+    C = model.conv1.weight.shape[1]
+    norm, selfnorm = gs.gcn_norm(True)
+    w2 = model.conv2.weight
+    t_hi, t_lo = _weight_operand(w2, True)
+    s_hi, s_lo = _weight_operand(w2, False)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    need = int(L.dge_gcn_train_ws_floats(N, C))
+    ws = _train_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _train_ws[key] = torch.empty(max(need, 1 << 22), dtype=torch.float32, device=dev)
+    q = torch.empty(N, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    if seed is None:
+        _train_seed[0] = (_train_seed[0] * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        seed = _train_seed[0]
+    a = None if action is None else action.contiguous().float()
+    yy = None if y is None else y.contiguous().float()
+    m = model
+    hw, hb = m.fully_con1.weight, m.fully_con1.bias
+    with torch.cuda.device(dev):
+        rc = L.dge_gcn_train_step(N, cin, C, _p(x), _p(gs.rowptr_dst), _p(gs.perm_dst), _p(gs.rowptr_src), _p(gs.perm_src), _p(gs.src), _p(gs.dst),
+                                  _p(norm), _p(selfnorm), _p(m.conv1.weight.detach()), _p(m.conv1.bias.detach()), _p(t_hi), _p(t_lo), _p(s_hi), _p(s_lo),
+                                  _p(m.conv2.bias.detach()), _p(hw.detach()), _p(hb.detach()), _p(a), _p(yy),
+                                  ctypes.c_float(inv_batch), ctypes.c_float(drop_p), ctypes.c_uint64(seed),
+                                  _p(m.conv1.weight.grad), _p(m.conv1.bias.grad), _p(w2.grad), _p(m.conv2.bias.grad), _p(hw.grad), _p(hb.grad),
+                                  _p(loss), _p(q), _p(ws), _st(dev))
+    if rc:
+        raise DgeError(f"dge_gcn_train_step failed ({rc})")
+    launch_count += 13
+    if return_debug:   # tests: the activations the backward pass used (h1, dropout(h2)) -- views of the workspace, valid until the next call
+        NC = N * C
+        return loss[0], q, dict(h1=ws[8 * N:8 * N + NC].view(N, C), d2=ws[8 * N + 4 * NC:8 * N + 5 * NC].view(N, C))
+    return loss[0], q
+
+
 # ------------------------------------------------------------- whole Q-network forward, one native call ---
 _q_ws: dict = {}
 

@@ -23,6 +23,7 @@ import torch
 import torch.nn.functional as F
 
 from .data import Batch, Data
+from . import gnn
 from .dist import FlatGradBucket
 
 
@@ -47,6 +48,7 @@ class DeepQ(object):
         self.temp_loss = 0
         self.total_reward = np.empty([0, 0])
         self._bucket = None
+        self.native_steps = 0      # gradient steps taken on the native path (keys the dropout stream together with torch.initial_seed())
 
     # ------------------------------------------------------------------ data ---
     def data_process(self, data):
@@ -75,9 +77,29 @@ class DeepQ(object):
         return torch.pow(readout_action - target.view(-1), 2).sum() / self.BATCH
 
     def train(self, data, action, y, device, model, optimizer):
-        """policy.py:241-253 (model.train(), dropout p=0.5, clamp +-0.5, Adam step)."""
+        """policy.py:241-253 (model.train(), dropout p=0.5, clamp +-0.5, Adam step).  With ``dist.NativeAdam`` as the optimizer and
+        the DQN Q-network itself (``Networks.GCN`` on CUDA) the whole step runs on the hand-written kernels: forward + cost +
+        backward in one native call (``gnn.gcn_train_step``), the gradient all-reduce, then clamp + Adam in one kernel; the loss
+        stays on the device (``temp_loss`` is a 0-d tensor then: ``float()`` it to read it)."""
         model.train()
         data = data.to(device)
+        from .dist import NativeAdam
+        if isinstance(optimizer, NativeAdam) and data.x.is_cuda and gnn.QForwardPlan.eligible(model):
+            from . import Networks
+            import torch.distributed as tdist
+            gs = Networks._structure(data, data.x.size(0))
+            y = torch.as_tensor(y, device=device, dtype=torch.float32)
+            action = torch.as_tensor(action, device=device, dtype=torch.float32)
+            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self.native_steps) & 0xFFFFFFFFFFFFFFFF
+            self.native_steps += 1
+            self._bucket = optimizer.bucket
+            loss, _ = gnn.gcn_train_step(model, data.x, gs, action, y, 1.0 / self.BATCH, 0.5, seed=seed)
+            world = tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
+            if world > 1:
+                tdist.all_reduce(optimizer.bucket.flat, op=tdist.ReduceOp.SUM)     # the one collective of the path
+            optimizer.step(clamp=self.max_grad_norm, gscale=1.0 / world)          # mean over ranks, clamp, Adam: one kernel
+            self.temp_loss = loss
+            return loss
         if self._bucket is None or self._bucket.params[0] is not next(p for p in model.parameters() if p.requires_grad):
             self._bucket = FlatGradBucket(model.parameters())
         self._bucket.zero_()

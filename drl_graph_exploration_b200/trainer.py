@@ -46,7 +46,11 @@ class VecDQNTrainer:
         # graphs allocated between a transition's s_t and its completion: <= B per tick x (longest line plan + reset phase) ticks
         # (decisions without a frontier and transitions dropped by restore() allocate graphs too -- hence per tick, not per transition)
         self.replay = GraphReplay(cap, eng.node_cap_env, eng.edge_cap_env, self.dev, slack=B * (env.cfg.max_plan_actions + 8) + 64)
-        self.optimizer = torch.optim.Adam(policy_net.parameters(), lr=lr)
+        # the DQN Q-network on CUDA trains on the native step (gnn.gcn_train_step + dist.NativeAdam); any other net on autograd + torch Adam
+        from . import gnn
+        from .dist import NativeAdam
+        native = gnn.QForwardPlan.eligible(policy_net)
+        self.optimizer = NativeAdam(policy_net.parameters(), lr=lr) if native else torch.optim.Adam(policy_net.parameters(), lr=lr)
         self.target_net.load_state_dict(policy_net.state_dict())
         self.target_net.eval()
         self.train_steps_per_tick = int(train_steps_per_tick)
@@ -67,7 +71,7 @@ class VecDQNTrainer:
         self.gen = torch.Generator(device=self.dev); self.gen.manual_seed(seed)
         self.decisions = self.train_steps = self.ticks = self.transitions = 0
         self.rollout_steps = self.rollout_clones = 0    # clone-engine ticks launched / clones evaluated
-        self.last_loss = float("nan")
+        self._loss = float("nan")
         self.reward_sum = 0.0
         self._learning = False                          # see _learning_started
 
@@ -173,9 +177,14 @@ class VecDQNTrainer:
         with torch.no_grad():
             q1 = dqn.test(b_s1, 0.0, self.dev, self.target_net).view(-1)
         act, y = dqn_targets(q1, b_s1.batch, a, r, term, off_s, n_s1, off_s1, fro1, b_s.x.size(0), dqn.GAMMA)
-        self.last_loss = dqn.train(b_s, act, y, self.dev, self.policy_net, self.optimizer)
+        self._loss = dqn.train(b_s, act, y, self.dev, self.policy_net, self.optimizer)    # (a device scalar on the native path: no sync here)
         self.train_steps += 1
-        return self.last_loss
+        return self.last_loss if check else self._loss
+
+    @property
+    def last_loss(self) -> float:
+        """Loss of the last gradient step (reading it synchronises with the step's stream on the native path)."""
+        return float(self._loss)
 
     def _learn_beside(self):
         with torch.enable_grad(), torch.cuda.stream(self.s_learn):
@@ -265,7 +274,7 @@ class VecDQNTrainer:
         here, as one torch file: nets, optimizer, counters, epsilon, sampling generator and (optionally) the device replay.
         Like in the reference the environments are NOT part of it: a resumed run starts fresh episodes."""
         ck = {"policy": self.policy_net.state_dict(), "target": self.target_net.state_dict(), "optimizer": self.optimizer.state_dict(),
-              "dqn": {"step_t": self.dqn.step_t, "epsilon": self.dqn.epsilon},
+              "dqn": {"step_t": self.dqn.step_t, "epsilon": self.dqn.epsilon, "native_steps": self.dqn.native_steps},
               "counters": {k: getattr(self, k) for k in ("decisions", "train_steps", "ticks", "transitions", "rollout_steps", "rollout_clones", "reward_sum")},
               "gen": self.gen.get_state(), "replay": self.replay.state_dict() if include_replay else None}
         torch.save(ck, path)
@@ -275,6 +284,7 @@ class VecDQNTrainer:
         self.policy_net.load_state_dict(ck["policy"]); self.target_net.load_state_dict(ck["target"])
         self.optimizer.load_state_dict(ck["optimizer"])
         self.dqn.step_t, self.dqn.epsilon = ck["dqn"]["step_t"], ck["dqn"]["epsilon"]
+        self.dqn.native_steps = ck["dqn"].get("native_steps", 0)
         for k, v in ck["counters"].items():
             setattr(self, k, v)
         self.gen.set_state(ck["gen"].cpu())

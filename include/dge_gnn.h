@@ -52,6 +52,33 @@ int dge_gemm_split_tf32(int64_t n, const float *x, float *hi, float *lo, void *s
 int dge_gemm_prep_weight(int K, int N, const float *W, float *Wt_hi, float *Wt_lo, void *stream);
 int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, const float *Bt_hi,
                     const float *Bt_lo, float *C, int ldc, void *stream);
+/* general form: operand row pitches lda / ldb in floats (multiples of 4, >= K; 0 = K, which then may be any length) and `splits`
+ * K slices per output tile (> 1: C must be zeroed by the caller, the slices add their partial products with atomics; 0: chosen
+ * by the library -- the weight-gradient shape x^T dy of autograd's mm backward, few output tiles and K = nodes, is split
+ * across the SMs).                                                                                                     */
+int dge_gemm_tf32x3_ex(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, int lda, const float *Bt_hi,
+                       const float *Bt_lo, int ldb, float *C, int ldc, int splits, void *stream);
+
+/* ---- one DQN training step of the GCN Q-network without autograd (csrc/dge_train.cu).  Replaces DeepQ.train + DeepQ.cost
+ * (scripts/policy.py:234-253: model(data, 0.5) -> sum((Q a - y)^2) / BATCH -> backward) for scripts/Networks.py:12-28:
+ * forward with functional dropout drop_p (Philox stream keyed by drop_seed), cost, and the gradients of all six parameters.
+ * (rowptr_d, perm_d): destination-sorted CSR (dge_gnn_csr_build on edge_index[1]); (rowptr_s, perm_s): source-sorted;
+ * src / dst = edge_index rows; norm / selfnorm from dge_gcn_norm(fill = 2).  W2t_(hi,lo) = dge_gemm_prep_weight(W2),
+ * W2_(hi,lo) = dge_gemm_split_tf32(W2).  act / y [N] nullable (a = 1 / y = 0).  Gradients are written to gW1 [Cin,C], gb1 [C],
+ * gW2 [C,C], gb2 [C], gWh [C], gbh [1]; loss [1] and q [N] stay on the device.  ws: dge_gcn_train_ws_floats(N, C) floats,
+ * 16-byte aligned.  Cin <= 8, C % 4 == 0, C <= 1024.                                                                     */
+int64_t dge_gcn_train_ws_floats(int N, int C);
+int dge_gcn_train_step(int N, int Cin, int C, const float *x, const int32_t *rowptr_d, const int32_t *perm_d, const int32_t *rowptr_s,
+                       const int32_t *perm_s, const int64_t *src, const int64_t *dst, const float *norm, const float *selfnorm,
+                       const float *W1, const float *b1, const float *W2t_hi, const float *W2t_lo, const float *W2_hi, const float *W2_lo,
+                       const float *b2, const float *Wh, const float *bh, const float *act, const float *y, float inv_batch, float drop_p,
+                       uint64_t drop_seed, float *gW1, float *gb1, float *gW2, float *gb2, float *gWh, float *gbh, float *loss, float *q,
+                       float *ws, void *stream);
+/* The optimizer half of the step (policy.py:251-253: clamp(+-clamp) on every gradient element, then torch.optim.Adam.step) as one
+ * kernel over flat buffers of n floats: g <- clamp(g * gscale), m, v, p updated with torch's Adam arithmetic (amsgrad off, no
+ * weight decay); step [1] int64 on the device is incremented first.                                                      */
+int dge_clamp_adam_step(int64_t n, float *p, float *g, float *m, float *v, int64_t *step, float lr, float beta1, float beta2, float eps,
+                        float clamp, float gscale, void *stream);
 
 
 /* ---- GRU cell of the GG-NN family (torch.nn.GRUCell inside PyG GatedGraphConv, Networks.py:73-86): the gate arithmetic
