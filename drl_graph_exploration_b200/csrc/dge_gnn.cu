@@ -8,6 +8,7 @@
 // rows streamed with 16-byte coalesced loads, self-loop / bias / ReLU (and, for the output
 // layer, the Linear(1000,1) head) fused in the epilogue -- no atomics, no [E,1000] temporary.
 // The dense X@W / grad GEMMs are tensor-core GEMMs outside this file.
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -158,6 +159,19 @@ __global__ void __launch_bounds__(256) k_aggregate(int N, int C, const float *__
   };
   const int lo = rowptr[i], hi = rowptr[i + 1];
   int p = lo;
+  if (V4 && !gate) {
+    for (; p + 7 < hi; p += 8) {   // eight neighbour rows in flight: indices and coefficients first, then the row loads back to back
+      int nn[8]; float ff[8]; float4 xx[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int e = perm[p + u]; nn[u] = (int)nbr[e]; ff[u] = coef[e]; }
+      if (act) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xx[u] = *reinterpret_cast<const float4 *>(X + (size_t)nn[u] * C + c0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc[0] += ff[u] * xx[u].x; acc[1] += ff[u] * xx[u].y; acc[2] += ff[u] * xx[u].z; acc[3] += ff[u] * xx[u].w; }
+      }
+    }
+  }
   for (; p + 1 < hi; p += 2) {   // two neighbour rows in flight
     const int e0 = perm[p], e1 = perm[p + 1];
     const int n0 = (int)nbr[e0], n1 = (int)nbr[e1];
@@ -199,6 +213,158 @@ __global__ void __launch_bounds__(256) k_aggregate(int N, int C, const float *__
   }
 }
 
+// ------------------------------------------------------------ aggregate, bulk-async staged ---
+// The same gather (GCNConv.propagate, Networks.py:22-24 via PyG) with the neighbour rows STAGED: a producer warp streams every
+// neighbour's feature row (C floats = 4 KB for C = 1000) into a shared-memory ring with one bulk asynchronous copy per row
+// (cp.async.bulk global -> shared, completion counted in bytes on the slot's mbarrier); the eight consumer warps wait on the
+// slot, accumulate coef * row in registers (float4 per thread) and hand the slot back.  The producer runs ahead across node
+// boundaries -- RING rows (32 KB) are in flight per CTA whatever the consumers do, instead of the two loads per thread of the
+// direct-load kernel (ncu r01: 28 % of DRAM peak, 17.9 long-scoreboard stalls per issue).  Several destination rows per CTA
+// (grid-stride); epilogue as above (self loop = one more staged row, bias, ReLU, optional dropout, optional head).
+constexpr int AGG_GROUP = 4;          // rows per ring slot: one mbarrier round trip per AGG_GROUP rows
+constexpr int AGG_RING = 4, AGG_CONSUMERS = 256, AGG_THREADS = AGG_CONSUMERS + 32;   // AGG_RING slots x AGG_GROUP rows in flight per CTA
+__device__ __forceinline__ uint32_t agg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ uint4 agg_philox(uint64_t key, uint64_t ctr) {   // Philox4x32-10 (as csrc/dge_train.cu)
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__global__ void __launch_bounds__(AGG_THREADS) k_aggregate_bulk(int N, int C, const float *__restrict__ X, const int32_t *__restrict__ rowptr,
+                                                                const int32_t *__restrict__ perm, const int64_t *__restrict__ nbr,
+                                                                const float *__restrict__ coef, const float *__restrict__ selfcoef,
+                                                                const float *__restrict__ bias, int relu, float drop_p, uint64_t drop_seed,
+                                                                float *__restrict__ out, const float *__restrict__ head_w, float head_b,
+                                                                float *__restrict__ q, const float *__restrict__ head_b_dev,
+                                                                const int32_t *__restrict__ N_dev) {
+  extern __shared__ __align__(16) unsigned char agg_smem[];
+  float *ring = reinterpret_cast<float *>(agg_smem);                                   // [AGG_RING][AGG_GROUP][C]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(agg_smem + (size_t)AGG_RING * AGG_GROUP * C * sizeof(float));   // full[RING], empty[RING]
+  __shared__ float red[8];
+  const int n_live = N_dev ? min(N, *N_dev) : N;
+  const uint32_t full0 = agg_smem_u32(bars), empty0 = full0 + 8 * AGG_RING;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AGG_RING; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s), "r"(AGG_CONSUMERS / 32) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t row_bytes = (uint32_t)C * sizeof(float);
+  if (threadIdx.x >= AGG_CONSUMERS) {
+    // ---- producer: one lane issues the bulk copies, in exactly the order the consumers fold the rows
+    if (threadIdx.x == AGG_CONSUMERS) {
+      uint32_t it = 0;
+      for (int i = blockIdx.x; i < n_live; i += gridDim.x) {
+        const int lo = rowptr[i], hi = rowptr[i + 1];
+        const int nrows = hi - lo + (selfcoef ? 1 : 0);                                // the last one: the node's own row (self loop)
+        for (int r0 = 0; r0 < nrows; r0 += AGG_GROUP, ++it) {                          // a slot takes up to AGG_GROUP rows of ONE node
+          const int g = min(AGG_GROUP, nrows - r0);
+          const uint32_t s = it % AGG_RING, ph = (it / AGG_RING) & 1;
+          agg_mbar_wait(empty0 + 8 * s, ph ^ 1);                                       // (free at first use)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8 * s), "r"(row_bytes * (uint32_t)g) : "memory");
+          for (int u = 0; u < g; ++u) {
+            const int p = lo + r0 + u;
+            const int n = p < hi ? (int)nbr[perm[p]] : i;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(agg_smem_u32(ring + ((size_t)s * AGG_GROUP + u) * C)), "l"(X + (size_t)n * C), "r"(row_bytes), "r"(full0 + 8 * s) : "memory");
+          }
+        }
+      }
+    }
+    return;
+  }
+  // ---- consumers
+  const int c0 = threadIdx.x * 4, lane = threadIdx.x & 31;
+  const bool act = c0 < C;
+  const float dscale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  uint32_t it = 0;
+  for (int i = blockIdx.x; i < n_live; i += gridDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int lo = rowptr[i], hi = rowptr[i + 1];
+    const int nrows = hi - lo + (selfcoef ? 1 : 0);
+    for (int r0 = 0; r0 < nrows; r0 += AGG_GROUP, ++it) {
+      const int g = min(AGG_GROUP, nrows - r0);
+      float cf[AGG_GROUP];
+#pragma unroll
+      for (int u = 0; u < AGG_GROUP; ++u) { const int p = lo + r0 + u; cf[u] = u < g ? (p < hi ? coef[perm[p]] : selfcoef[i]) : 0.f; }
+      const uint32_t s = it % AGG_RING, ph = (it / AGG_RING) & 1;
+      agg_mbar_wait(full0 + 8 * s, ph);
+      if (act) {
+#pragma unroll
+        for (int u = 0; u < AGG_GROUP; ++u) {
+          if (u < g) {
+            const float4 x = *reinterpret_cast<const float4 *>(ring + ((size_t)s * AGG_GROUP + u) * C + c0);
+            acc.x += cf[u] * x.x; acc.y += cf[u] * x.y; acc.z += cf[u] * x.z; acc.w += cf[u] * x.w;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * s) : "memory");
+    }
+    float hq = 0.f;
+    if (act) {
+      float r[4] = {acc.x, acc.y, acc.z, acc.w};
+      if (bias) { const float4 b = *reinterpret_cast<const float4 *>(bias + c0); r[0] += b.x; r[1] += b.y; r[2] += b.z; r[3] += b.w; }
+      if (relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
+      if (drop_p > 0.f) {   // functional dropout (Networks.py:26): keep with probability 1 - p, scale by 1 / (1 - p)
+        const uint4 u = agg_philox(drop_seed, (uint64_t)i * 256 + threadIdx.x);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) r[v] = ((uu[v] >> 8) * (1.0f / 16777216.0f) >= drop_p) ? r[v] * dscale : 0.f;
+      }
+      if (out) *reinterpret_cast<float4 *>(out + (size_t)i * C + c0) = make_float4(r[0], r[1], r[2], r[3]);
+      if (head_w) { const float4 w = *reinterpret_cast<const float4 *>(head_w + c0); hq = r[0] * w.x + r[1] * w.y + r[2] * w.z + r[3] * w.w; }
+    }
+    if (head_w) {   // reduction of the head dot product over the consumer warps (fixed order => deterministic); named barrier: the producer is not part of it
+      for (int o = 16; o > 0; o >>= 1) hq += __shfl_xor_sync(0xffffffffu, hq, o);
+      if (lane == 0) red[threadIdx.x >> 5] = hq;
+      asm volatile("bar.sync 1, %0;" ::"r"(AGG_CONSUMERS) : "memory");
+      if (threadIdx.x == 0) {
+        float sacc = 0.f;
+        for (int wv = 0; wv < 8; ++wv) sacc += red[wv];
+        q[i] = sacc + head_b + (head_b_dev ? head_b_dev[0] : 0.f);
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(AGG_CONSUMERS) : "memory");
+    }
+  }
+}
+inline size_t agg_bulk_smem(int C) { return (size_t)AGG_RING * AGG_GROUP * C * sizeof(float) + 2 * AGG_RING * sizeof(uint64_t); }
+// the bulk kernel takes rows of a multiple of 16 bytes at 16-byte aligned addresses (C % 4 == 0), up to 1024 channels
+inline bool agg_bulk_ok(int C, const float *X, const float *out, const float *bias, const float *head_w) {
+  // opt-in (DGE_AGG_BULK=1): measured SLOWER than the direct-load kernel with eight rows in flight at the 4 KB rows of this network
+  // (profiles/r02_aggregate_ab.md) -- a row is one float4 per thread, so the per-slot mbarrier round trip is not amortised
+  static const bool on = [] { const char *v = getenv("DGE_AGG_BULK"); return v && v[0] == '1'; }();
+  if (!on) return false;
+  return C % 4 == 0 && C <= 1024 && ((uintptr_t)X % 16 == 0) && (!out || (uintptr_t)out % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0) &&
+         (!head_w || (uintptr_t)head_w % 16 == 0);
+}
+inline int agg_bulk_launch(int grid, int N, int C, const float *X, const int32_t *rowptr, const int32_t *perm, const int64_t *nbr, const float *coef,
+                           const float *selfcoef, const float *bias, int relu, float drop_p, uint64_t drop_seed, float *out, const float *head_w,
+                           float head_b, float *q, const float *head_b_dev, const int32_t *N_dev, cudaStream_t st) {
+  const size_t smem = agg_bulk_smem(C);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(k_aggregate_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    configured = smem;
+  }
+  k_aggregate_bulk<<<grid, AGG_THREADS, smem, st>>>(N, C, X, rowptr, perm, nbr, coef, selfcoef, bias, relu, drop_p, drop_seed, out, head_w, head_b, q, head_b_dev, N_dev);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 #define CK() (cudaGetLastError() == cudaSuccess ? 0 : -2)
 
@@ -233,6 +399,8 @@ extern "C" int dge_gnn_aggregate(int N, int C, const float *X, const int32_t *ro
                                  const float *head_w, float head_b, float *q, void *stream) {
   if (N <= 0 || C <= 0 || C > 1024 || !X || !rowptr || !perm) return -1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!gate && agg_bulk_ok(C, X, out, bias, head_w))   // neighbour rows staged by bulk asynchronous copies
+    return agg_bulk_launch(N < 148 * 4 ? N : 148 * 4, N, C, X, rowptr, perm, nbr, coef, selfcoef, bias, relu, 0.f, 0, out, head_w, head_b, q, nullptr, nullptr, st);
   if (C % 4 == 0 && ((uintptr_t)X % 16 == 0) && (!out || (uintptr_t)out % 16 == 0) && (!gate || (uintptr_t)gate % 16 == 0))
     k_aggregate<true><<<N, 256, 0, st>>>(N, C, X, rowptr, perm, nbr, coef, selfcoef, bias, gate, relu, out, head_w, head_b, q);
   else
@@ -325,6 +493,8 @@ int dge_gcn_q_forward_dev(int N, const int32_t *N_dev, int Cin, int C, const flo
   if (cudaGetLastError() != cudaSuccess) return -2;
   const int rc = dge_gemm_tf32x3(N, N_dev, C, C, h_hi, h_lo, W2t_hi, W2t_lo, xw, C, st);
   if (rc) return rc;
+  if (agg_bulk_ok(C, xw, nullptr, b2, head_w))
+    return agg_bulk_launch(N < 148 * 4 ? N : 148 * 4, N, C, xw, rowptr, perm, src, norm, selfnorm, b2, 1, 0.f, 0, nullptr, head_w, 0.f, q, head_b_dev, N_dev, st);
   k_aggregate<true><<<node_grid(N), 256, 0, st>>>(N, C, xw, rowptr, perm, src, norm, selfnorm, b2, nullptr, 1, nullptr, head_w, 0.f, q, head_b_dev, N_dev);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -527,4 +697,12 @@ extern "C" int dge_gnn_filter_adj_fill(int E, const int64_t *src, const int64_t 
   if (E <= 0 || !src || !dst || !w || !newid || !flag || !pos || !out_src || !out_dst || !out_w) return -1;
   k_edge_compact<<<cdiv(E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(E, src, dst, w, newid, flag, pos, out_src, out_dst, out_w);
   return CK();
+}
+
+// second-layer aggregation of the training forward (csrc/dge_train.cu): d2 = dropout(relu(A t2 + b2)), q = d2 Wh + bh
+int dge_agg_fwd_train_bulk(int N, int C, const float *X, const int32_t *rowptr, const int32_t *perm, const int64_t *nbr, const float *coef,
+                           const float *selfcoef, const float *bias, float drop_p, uint64_t drop_seed, const float *head_w, const float *head_b_dev,
+                           float *d2, float *q, cudaStream_t st) {
+  if (!agg_bulk_ok(C, X, d2, bias, head_w)) return -1;
+  return agg_bulk_launch(N < 148 * 4 ? N : 148 * 4, N, C, X, rowptr, perm, nbr, coef, selfcoef, bias, 1, drop_p, drop_seed, d2, head_w, 0.f, q, head_b_dev, nullptr, st);
 }

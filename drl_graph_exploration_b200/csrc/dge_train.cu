@@ -18,7 +18,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "../../include/dge_gnn.h"
+
+int dge_agg_fwd_train_bulk(int N, int C, const float *X, const int32_t *rowptr, const int32_t *perm, const int64_t *nbr, const float *coef,
+                           const float *selfcoef, const float *bias, float drop_p, uint64_t drop_seed, const float *head_w, const float *head_b_dev,
+                           float *d2, float *q, cudaStream_t st);
 
 namespace {
 
@@ -125,6 +131,17 @@ __global__ void __launch_bounds__(256) k_agg_fwd_train(int N, int C, const float
     };
     const int lo = rowptr[i], hi = rowptr[i + 1];
     int p = lo;
+    for (; p + 7 < hi; p += 8) {   // eight neighbour rows in flight: indices and coefficients first, then the row loads back to back
+      int nn[8]; float ff[8]; float4 xx[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int e = perm[p + u]; nn[u] = (int)nbr[e]; ff[u] = coef[e]; }
+      if (act) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xx[u] = *reinterpret_cast<const float4 *>(X + (size_t)nn[u] * C + c0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc.x += ff[u] * xx[u].x; acc.y += ff[u] * xx[u].y; acc.z += ff[u] * xx[u].z; acc.w += ff[u] * xx[u].w; }
+      }
+    }
     for (; p + 3 < hi; p += 4) {   // four neighbour rows in flight
       const int e0 = perm[p], e1 = perm[p + 1], e2 = perm[p + 2], e3 = perm[p + 3];
       const int n0 = (int)nbr[e0], n1 = (int)nbr[e1], n2 = (int)nbr[e2], n3 = (int)nbr[e3];
@@ -339,7 +356,9 @@ extern "C" int dge_gcn_train_step(int N, int Cin, int C, const float *x, const i
   k_split_transpose<<<tg, 256, 0, st>>>(N, C, (int)Np, h1, h1_hi, h1_lo, h1t_hi, h1t_lo); CKL();
   int rc = dge_gemm_tf32x3_ex(N, nullptr, C, C, h1_hi, h1_lo, 0, W2t_hi, W2t_lo, 0, t2, C, 1, st);
   if (rc) return rc;
-  k_agg_fwd_train<<<node_grid(N), 256, 0, st>>>(N, C, t2, rowptr_d, perm_d, src, norm, selfnorm, b2, drop_p, drop_seed, Wh, bh, d2, q); CKL();
+  rc = dge_agg_fwd_train_bulk(N, C, t2, rowptr_d, perm_d, src, norm, selfnorm, b2, drop_p, drop_seed, Wh, bh, d2, q, st);   // (opt-in, DGE_AGG_BULK=1)
+  if (rc == -1) { k_agg_fwd_train<<<node_grid(N), 256, 0, st>>>(N, C, t2, rowptr_d, perm_d, src, norm, selfnorm, b2, drop_p, drop_seed, Wh, bh, d2, q); CKL(); }
+  else if (rc) return rc;
   // ---- cost
   k_dqn_cost<<<1, 1024, 0, st>>>(N, q, act, y, inv_batch, dq, loss); CKL();
   // ---- backward

@@ -21,7 +21,7 @@ def _close(a, b, rtol=RTOL, atol=1e-9, what=""):
     assert np.all(err <= rtol), f"{what}: max rel err {err.max():.3e}"
 
 
-def compare_state(cfg, eng, oracles, step_tag, check_map=True):
+def compare_state(cfg, eng, oracles, step_tag, check_map=True, RTOL=RTOL):
     st = {k: v.cpu().numpy() for k, v in eng.state.items()}
     n_border = 0
     for b, o in enumerate(oracles):
