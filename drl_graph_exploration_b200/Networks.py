@@ -340,6 +340,7 @@ class GraphUNet(torch.nn.Module):
             x = self.up_convs[i](xs[j] + up, gss[j])
             if i < self.depth - 1:
                 x = self.act(x)
+        self.last_perms = perms        # nodes kept by the pooling levels of this pass (kept for inspection / parity tests)
         x = F.dropout(F.relu(x), p=p)
         return self.fully_con1(x)
 

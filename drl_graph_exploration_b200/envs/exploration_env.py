@@ -311,7 +311,10 @@ class ExplorationEnv:
             else:
                 seed = int(self.env_index)
             seeds = torch.tensor([seed], dtype=torch.int64, device=self._vec.device)
-            self._vec.reset(seeds=seeds, reference_worlds=True)
+            if self.test:
+                self._reset_reference_world(seed, seeds)
+            else:
+                self._vec.reset(seeds=seeds, reference_worlds=True)
             if int(self._st("observed").sum()) < 1:    # exploration_env.py:416-419
                 print("regenerate a environment")
                 self.env_index = self.env_index + 50
@@ -319,9 +322,48 @@ class ExplorationEnv:
             self.dist = 0.0
             return self._get_obs()
 
+    # -- test=True: the reference's own world and noise streams (exploration_env.py:389-407 seeds everything with env_index) --
+    def _ref_noise(self, odom3):
+        row = np.zeros((1, self._vec.eng.noise_len))
+        od = (ctypes.c_double * 3)(*[float(v) for v in odom3])
+        _check(self._vec.eng._L.dge_refworld_step(self._ref, od, row.ctypes.data_as(ctypes.c_void_p)), "dge_refworld_step")
+        return torch.as_tensor(row, device=self._vec.device)
+
+    def _reset_reference_world(self, seed, seeds):
+        """SS2D.__init__ + the four forced steps with the landmarks, visiting order and noise of the reference's libstdc++
+        streams (``dge_refworld_*``, csrc/dge_refworld.cu): ``ExplorationEnv(40, 0, True)`` IS the world of test.py's seed-0 run."""
+        eng, L = self._vec.eng, self._vec.eng._L
+        if not hasattr(L, "_refworld_ready"):
+            L.dge_refworld_create.restype = ctypes.c_void_p
+            L.dge_refworld_create.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+            L.dge_refworld_destroy.argtypes = [ctypes.c_void_p]
+            L.dge_refworld_destroy.restype = None
+            L.dge_refworld_world.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+            L.dge_refworld_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+            L._refworld_ready = True
+        if getattr(self, "_ref", None):
+            L.dge_refworld_destroy(self._ref)
+        start = np.array(start_pose_for_seed(seed, self.map_size, self._cfg.ext), dtype=np.float64)
+        cs = self._cfg.to_struct()
+        self._ref = ctypes.c_void_p(L.dge_refworld_create(ctypes.byref(cs), ctypes.c_uint32(seed), start.ctypes.data_as(ctypes.c_void_p)))
+        if not self._ref:
+            raise DgeError("dge_refworld_create failed")
+        lm, scan, n0 = np.zeros((1, eng.Lt, 2)), np.zeros((1, eng.Lt), dtype=np.int32), np.zeros((1, eng.noise_len))
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _check(L.dge_refworld_world(self._ref, vp(lm), vp(scan), vp(n0)), "dge_refworld_world")
+        t = lambda a: torch.as_tensor(a, device=self._vec.device)
+        L.dge_set_counting(eng._h, 0)
+        eng.reset(seeds, start=t(start[None]), landmarks=t(lm), scan=t(scan), noise=t(n0))
+        for _ in range(4):
+            eng.step(self._vec._reset_odom, noise=self._ref_noise(RESET_ODOM))
+        L.dge_set_counting(eng._h, 1)
+
     def step(self, action):
         odom = torch.tensor([[action.x, action.y, action.theta]], dtype=torch.float64, device=self._vec.device)
-        self._vec.step(odom)
+        if self.test:
+            self._vec.eng.step(odom, noise=self._ref_noise((action.x, action.y, action.theta)))
+        else:
+            self._vec.step(odom)
         if int(self._st("status")) == -4:      # DGE_ECAP: the trajectory buffer is full -- not an episode end the reference knows
             raise DgeError(f"ExplorationEnv: pose capacity ({self._vec.eng.Tmax}) exhausted; create the env with a larger max_poses")
         self.dist = self.dist + math.sqrt(action.x ** 2 + action.y ** 2)
@@ -405,4 +447,7 @@ class ExplorationEnv:
         return [int(round((y + half) / self.map_resolution - 0.5)), int(round((x + half) / self.map_resolution - 0.5))]
 
     def close(self):
+        if getattr(self, "_ref", None):
+            self._vec.eng._L.dge_refworld_destroy(self._ref)
+            self._ref = None
         self._vec.close()

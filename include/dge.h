@@ -324,6 +324,18 @@ int dge_rollout_rewards(dge_handle dst, dge_handle src, const dge_graph_out *g, 
 /* ---- GNN building blocks (scripts/Networks.py GCN: GCNConv(improved=True) aggregate,
  * bias, ReLU; Linear head) -- hand-written edge/dst-parallel kernels, see dge_gnn.h  */
 
+/* ---- the reference's random streams for `test=True` worlds (host code, csrc/dge_refworld.cu).
+ * ExplorationEnv(map_size, env_index, True) of the reference draws its landmarks, control noise and sensor noise from three
+ * std::mt19937(env_index) (pyss2d.py:89-119, RNG.h:47-126, Simulator2D.cpp:161-173,436-463,505-527) and visits the landmarks in
+ * the iteration order of an std::unordered_map (Simulation2D.h:269).  dge_refworld_* replays those streams on the host and hands
+ * out what dge_reset / dge_step take as explicit inputs: landmarks [Lt,2], scan order [Lt], noise rows [3 + 4 Lt].
+ * start [3] = the start pose (pyss2d.py:88-95).  One object per episode.                                              */
+typedef struct dge_refworld dge_refworld;
+dge_refworld *dge_refworld_create(const dge_config *cfg, uint32_t seed, const double *start);
+void dge_refworld_destroy(dge_refworld *w);
+int dge_refworld_world(const dge_refworld *w, double *landmarks, int32_t *scan, double *init_noise);
+int dge_refworld_step(dge_refworld *w, const double *odom, double *noise);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,11 +102,17 @@ def filter_adj(edge_index, edge_attr, perm, num_nodes):
     return torch.stack([row[keep], col[keep]]), edge_attr[keep]
 
 
-def topk_pool(x, edge_index, edge_attr, batch, weight, ratio=0.5):
-    """TopKPooling(1000, 0.5).forward: score = tanh(x.w / ||w||)."""
+def topk_pool(x, edge_index, edge_attr, batch, weight, ratio=0.5, forced_perm=None, record=None):
+    """TopKPooling(1000, 0.5).forward: score = tanh(x.w / ||w||).  ``forced_perm`` (parity tests): pool THESE nodes instead of the
+    fp64 top-k -- a near-tie of two scores may legitimately be ordered differently in fp32 -- and ``record`` receives
+    (score, own perm) so the test can check that the forced selection is a top-k selection up to such ties."""
     score = (x * weight).sum(dim=-1)
     score = torch.tanh(score / weight.norm(p=2, dim=-1))
     perm = topk_perm(score, ratio, batch)
+    if record is not None:
+        record.append((score.detach(), perm, batch))
+    if forced_perm is not None:
+        perm = forced_perm
     x = x[perm] * score[perm].view(-1, 1)
     batch = batch[perm]
     ei, ea = filter_adj(edge_index, edge_attr, perm, score.size(0))
@@ -239,7 +245,7 @@ class GraphUNet(torch.nn.Module):      # Networks.py:125-230
         self.up_convs.append(_GCNConvParams(hidden_channels, out_channels))
         self.fully_con1 = torch.nn.Linear(out_channels, out)
 
-    def trunk(self, data, p, batch=None, mask=None):
+    def trunk(self, data, p, batch=None, mask=None, forced_perms=None, record=None):
         x, ei, ew = data.x, data.edge_index, data.edge_attr
         if batch is None:
             batch = ei.new_zeros(x.size(0))
@@ -247,7 +253,8 @@ class GraphUNet(torch.nn.Module):      # Networks.py:125-230
         xs, eis, ews, perms = [x], [ei], [ew], []
         for i in range(1, self.depth + 1):
             ei, ew = augment_adj(ei, ew, x.size(0))
-            x, ei, ew, batch, perm = topk_pool(x, ei, ew, batch, self.pools[i - 1].weight, self.ratio)
+            x, ei, ew, batch, perm = topk_pool(x, ei, ew, batch, self.pools[i - 1].weight, self.ratio,
+                                               None if forced_perms is None else forced_perms[i - 1], record)
             x = F.relu(self.down_convs[i](x, ei, ew))
             if i < self.depth:
                 xs.append(x); eis.append(ei); ews.append(ew)
@@ -262,8 +269,8 @@ class GraphUNet(torch.nn.Module):      # Networks.py:125-230
         x = _dropout(F.relu(x), p, mask)
         return self.fully_con1(x)
 
-    def forward(self, data, prob, batch=None, dropout_mask=None):
-        return self.trunk(data, prob, batch, dropout_mask)
+    def forward(self, data, prob, batch=None, dropout_mask=None, forced_perms=None, record=None):
+        return self.trunk(data, prob, batch, dropout_mask, forced_perms, record)
 
 
 class PolicyGraphUNet(GraphUNet):       # Networks.py:233-339

@@ -186,10 +186,20 @@ def test_gcn_backward_and_other_families_match_reference():
         scale = out_ref.abs().max()
         assert out.shape == out_ref.shape and torch.isfinite(out).all()
         if name == "GraphUNet":
-            # top-k pooling selects nodes by score order: an fp32/fp64 near-tie legitimately changes the
-            # pooled node set, so only the bulk agreement is checked for this ("next", section 8 f2) family
-            rel = (out.double() - out_ref).abs() / scale
-            assert rel.median() <= 1e-3
+            # top-k pooling selects nodes by score order: an fp32 / fp64 near-tie of two scores may legitimately be ordered the other
+            # way, so the fp64 reference pools the nodes the CUDA path kept (checked to BE a top-k selection up to such ties), and then
+            # every output has to agree
+            rec = []
+            out_ref = ref(d64, 0.0, batch=batch.batch, forced_perms=model.last_perms, record=rec)
+            for (score, perm64, bt), perm32 in zip(rec, model.last_perms):
+                assert perm32.numel() == perm64.numel()
+                s32, s64 = set(perm32.tolist()), set(perm64.tolist())
+                for node in s32 ^ s64:      # a node only one side kept: its score ties (to 1e-5) with the weakest score the fp64 side kept in its graph
+                    gsel = perm64[bt[perm64] == bt[node]]
+                    assert abs(float(score[node]) - float(score[gsel].min())) < 1e-5, "pooled set differs beyond a score near-tie"
+                assert len(s32 ^ s64) <= max(2, perm32.numel() // 200)
+            scale = out_ref.abs().max()
+            assert (out.double() - out_ref).abs().max() <= 1e-4 * scale, (name, float((out.double() - out_ref).abs().max() / scale))
             continue
         tol = 1e-4 if name == "GCN" else 2e-3   # 3 stacked GRU layers: looser for the "next" family
         assert (out.double() - out_ref).abs().max() <= tol * scale, (name, float((out.double() - out_ref).abs().max() / scale))

@@ -3,8 +3,8 @@
   reached on both sides at the same step;
 * a 100x100 map (50 landmarks: the SLAM kernel's wide-border paths, 100 border columns) followed past 500 poses -- the chunked
   staging of k_slam / k_vmap_env and the workspace indexing at T >= 500 (max_steps of the reference is 5000).
-fp64 state is held to 1e-5 relative per element here (1e-6 in the short-trajectory tests; contract 1e-4): over hundreds of poses the
-small off-diagonal entries of the marginal covariances collect a few 1e-6 of rounding difference between the two elimination orders.
+fp64 state is held to 1e-5 here (1e-6 in the short-trajectory tests; contract 1e-4), covariance blocks relative to their largest
+entry: over hundreds of poses the small off-diagonal entries of the marginals collect rounding differences between the two elimination orders.
 Sorted last (zz): the long run takes the CPU oracle about a minute."""
 import numpy as np
 import pytest
@@ -35,7 +35,7 @@ def _run(cfg, seeds, max_poses, stop, compare_every=1, map_every=1):
         n += 1
         if n % compare_every == 0:
             torch.cuda.synchronize()
-            compare_state(cfg, eng, oracles, f"step {n}", check_map=(n % map_every == 0), RTOL=1e-5)
+            compare_state(cfg, eng, oracles, f"step {n}", check_map=(n % map_every == 0), RTOL=1e-5, cov_matrix_rel=True)
 
     for _ in range(4):
         step([RESET_ODOM] * B)
@@ -46,7 +46,7 @@ def _run(cfg, seeds, max_poses, stop, compare_every=1, map_every=1):
             if stop(oracles, eng):
                 break
     torch.cuda.synchronize()
-    compare_state(cfg, eng, oracles, "final", RTOL=1e-5)
+    compare_state(cfg, eng, oracles, "final", RTOL=1e-5, cov_matrix_rel=True)
     out = (n, [o.sizes()["T"] for o in oracles], eng.state["done"].cpu().numpy().copy(), [o.metrics()["done"] for o in oracles])
     eng.close()
     return out
