@@ -36,6 +36,17 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# ONE JSON line on stdout: native libraries may print to fd 1 (NCCL's version banner does, under torchrun), so fd 1 is pointed at
+# stderr for the life of the process and the line is written to a duplicate of the original stdout
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 MAP_SIZE, N_LANDMARKS, ENVS_PER_GPU, MAX_POSES = 20, 30, 256, 192
 WORKLOAD = f"{ENVS_PER_GPU} envs/GPU, {MAP_SIZE}x{MAP_SIZE} map, {N_LANDMARKS} landmarks, GCN policy inference (BASELINE configs[1])"
 
@@ -141,7 +152,7 @@ def timed_reference(**k):
 
 
 def run_reference(args):
-    """--impl reference: a step = `tps` ticks of all 256 envs, tps chosen from the warm-up so that the K timed steps last >= 2 s."""
+    """--impl reference: a step = `tps` ticks of all 256 envs, tps chosen from the warm-up so that the K timed steps last >= 10 s."""
     threads = os.cpu_count() or 1
     from oracle.cpu_loop import cpu_reference
     run_tick, count = cpu_reference(MAP_SIZE, N_LANDMARKS, ENVS_PER_GPU, threads, MAX_POSES)
@@ -151,7 +162,7 @@ def run_reference(args):
     for _ in range(args.warmup):
         run_tick()
     tick_s = (time.perf_counter() - t0) / args.warmup
-    tps = int(max(1, min(50, math.ceil(2.0 / (args.steps * tick_s)))))
+    tps = int(max(1, min(50, math.ceil(10.0 / (args.steps * tick_s)))))   # >= 10 s timed whatever --steps is (a decision round makes single ticks uneven)
     c0, t0, sT = count(), time.perf_counter(), 0.0
     for _ in range(args.steps * tps):
         run_tick(); sT += run_tick.mean_poses()
@@ -159,12 +170,12 @@ def run_reference(args):
     val = (count() - c0) / dt
     sample = (f"all {ENVS_PER_GPU} envs x {args.steps * tps} ticks ({dt:.1f} s, {tps} ticks per step) after {REF_PREROLL} pre-roll ticks, mean trajectory length "
               f"{sT / (args.steps * tps):.1f}: CPU-oracle envs on a {threads}-thread C++ pool + torch-CPU GCN per decision round (overlapped with the stepping)")
-    print(json.dumps({"impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
+    emit({"impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": WORKLOAD, "sample": sample, "ticks_per_step": tps, "timed_seconds": dt},
                       "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
-                      "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def finish(world, dist):
@@ -197,7 +208,7 @@ def run_train(args):
     rank, world, local, dist = _dist_setup()
     out = measure_train(args, rank, world, local, dist, args.steps, args.warmup)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     finish(world, dist)
 
 
@@ -234,8 +245,10 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
     d0, t0, r0, k0 = tr.decisions, tr.train_steps, tr.rollout_steps, tr.rollout_clones
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
+    t_host = time.perf_counter()
     for _ in range(steps):
         tr.tick(learn=True)
+    t_host = time.perf_counter() - t_host
     b.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -277,7 +290,7 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
                "decisions_per_s": dec / sec, "train_steps_per_s": tsteps / sec / world, "rollout_clone_steps_per_s": None,
                "gnn_samples_per_s": {"forward_acting": dec / sec, "forward_target": tsteps * bsz / sec, "forward_backward": tsteps * bsz / sec},
                "rollout": {"clones_per_s": clones / sec, "clone_engine_ticks_per_s": rsteps / sec}, "loss": tr.last_loss, "epsilon": tr.epsilon, "clocks": clocks,
-               "allreduce_us": ar_us}
+               "allreduce_us": ar_us, "host_issue_ms_per_tick": 1e3 * t_host / steps}
     env.close()
     return out
 
@@ -311,7 +324,7 @@ def run_gnn(args):
     rank, world, local, dist = _dist_setup()
     out = measure_gnn(args, rank, world, local, dist)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     finish(world, dist)
 
 
@@ -694,10 +707,10 @@ def main():
             pass
         tr = measure_train(args, rank, world, local, dist, steps=100, warmup=10)
         if rank == 0:
-            out["train_c3"] = {k: tr[k] for k in ("value", "unit", "ms_per_step", "decisions_per_s", "train_steps_per_s", "allreduce_us", "loss")}
+            out["train_c3"] = {k: tr[k] for k in ("value", "unit", "ms_per_step", "host_issue_ms_per_tick", "decisions_per_s", "train_steps_per_s", "allreduce_us", "loss")}
             out["train_c3"].update(workload=tr["config"]["workload"], schedule=tr["config"]["schedule"], collective=tr["config"]["collective"], ticks=100)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     finish(world, dist)
 
 
