@@ -87,7 +87,7 @@ struct dge_engine {
                                   //     graphs built for a decision, their nodes, their edges, graph batches
   long long *slam_clocks; // [B,12] phase-boundary clocks of the last k_slam launch (+ T in slot 7, sub-phase cycles in 8..11)
   int32_t *forced;       // [B] forced steps left after an in-pipeline reset (| DGE_FRESH_BIT while the initial optimize is pending)
-  uint8_t *step_kind;    // [B] 1 = the env's last step was a policy step
+  uint8_t *step_kind;    // [B] 1 = the env's last step was a policy step, 2 = the last forced step of an in-pipeline reset, 0 = forced / fresh
   uint8_t *pending;      // [B] envs that need a decision (dge_mark_pending)
   int64_t *pack_hdr_host; // [16] pinned: header of the last packed graph batch (dge_graph_host_packed_*)
   double *hp_odom;        // [B,3] pinned staging: actions expanded from host plans (dge_step_host_plans_async)

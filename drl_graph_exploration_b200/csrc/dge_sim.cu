@@ -28,7 +28,7 @@ struct SimArgs {
   int32_t *plan_cursor;
   uint8_t *done, *active;
   int32_t *forced;      // [B] forced steps left after an in-pipeline reset; DGE_FRESH_BIT = reset this tick
-  uint8_t *step_kind;   // [B] 1 = the last step was a policy step (counted), 0 = forced / fresh
+  uint8_t *step_kind;   // [B] 1 = the last step was a policy step (counted), 0 = forced / fresh, 2 = the LAST forced step of an in-pipeline reset
   double forced_odom[3];
 };
 
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(32) k_move_measure(SimArgs a, const double *od
   // (like the reference, a finished episode can still be stepped explicitly; only the queued
   //  mode parks `done` envs until the caller resets them)
   if (act && from_queue == 1 && a.done[b]) act = false;   // from_queue == 2: roll-out clones run their whole plan
-  if (lane == 0) { a.active[b] = act ? 1 : 0; a.step_kind[b] = (act && fl == 0) ? 1 : 0; }
+  if (lane == 0) { a.active[b] = act ? 1 : 0; a.step_kind[b] = (act && fl == 0) ? 1 : ((act && fl == 1) ? 2 : 0); }
   if (!act) return;
   const uint64_t key = a.seed[b];
   const uint64_t step_ctr = (uint64_t)a.sim_step[b] | ((uint64_t)a.update_count[b] << 32);

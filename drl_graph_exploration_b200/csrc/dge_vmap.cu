@@ -219,10 +219,11 @@ __global__ void __launch_bounds__(TILE * TILE, 3) k_vmap_cells(VmapCfg c, int Ts
 __global__ void __launch_bounds__(256) k_vmap_metrics(dge_config cfg, DgeDims d, const double *prob, const double *vinfo,
                                                       const int32_t *sim_step, const int32_t *status, const double *dist,
                                                       double *metrics, uint8_t *done, const uint8_t *mask,
-                                                      const int32_t *n_poses, const int32_t *meas_ptr, unsigned long long *counters, const uint8_t *step_kind) {
+                                                      const int32_t *n_poses, const int32_t *meas_ptr, unsigned long long *counters, const uint8_t *step_kind,
+                                                      const uint8_t *observed) {
   const int b = blockIdx.x;
   if (mask && !mask[b]) return;
-  if (threadIdx.x == 0 && counters && step_kind[b]) {   // integer work counters (order-independent): env-steps, sum T, sum M
+  if (threadIdx.x == 0 && counters && step_kind[b] == 1) {   // integer work counters (order-independent): env-steps, sum T, sum M
     const int T = n_poses[b];
     atomicAdd(&counters[0], 1ull);
     atomicAdd(&counters[1], (unsigned long long)T);
@@ -257,7 +258,11 @@ __global__ void __launch_bounds__(256) k_vmap_metrics(dge_config cfg, DgeDims d,
     metrics[8 * b + 2] = cfg.dist_w0 - (cfg.dist_w0 - cfg.dist_w1) * pk;   // distance weight
     metrics[8 * b + 3] = (double)s_k[0];
     metrics[8 * b + 6] = dist[b];
-    done[b] = (sim_step[b] > cfg.max_steps || explored > 0.85 || status[b] == DGE_ECAP) ? 1 : 0;
+    // exploration_env.py:416-419: a world in which the four forced steps of reset() saw no landmark is regenerated -- here the episode ends
+    // at once (uncounted) and the next reset draws the next world of the env's seed sequence
+    bool blind = false;
+    if (step_kind && step_kind[b] == 2) { int n = 0; for (int j = 0; j < d.Lt; ++j) n += observed[(size_t)b * d.Lt + j]; blind = n == 0; }
+    done[b] = (sim_step[b] > cfg.max_steps || explored > 0.85 || status[b] == DGE_ECAP || blind) ? 1 : 0;
   }
 }
 
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_vmap_env(EnvArgs a) {
   if (a.clocks && tid == 0) a.clocks[4 * b + 3] = clock64();
   if (a.metrics) {
     // ---- metrics (k_vmap_metrics, same summation order: 256 strided partial sums, fixed tree) ---------------------
-    if (tid == 0 && a.counters && a.step_kind[b]) {
+    if (tid == 0 && a.counters && a.step_kind[b] == 1) {
       atomicAdd(&a.counters[0], 1ull);
       atomicAdd(&a.counters[1], (unsigned long long)T);
       atomicAdd(&a.counters[2], (unsigned long long)a.meas_ptr[(size_t)b * (a.d.Tmax + 1) + T]);
@@ -640,7 +645,11 @@ __global__ void __launch_bounds__(NTHR, 2) k_vmap_env(EnvArgs a) {
       a.metrics[8 * b + 2] = a.cfg.dist_w0 - (a.cfg.dist_w0 - a.cfg.dist_w1) * pk;
       a.metrics[8 * b + 3] = (double)s_k[0];
       a.metrics[8 * b + 6] = a.dist[b];
-      a.done[b] = (a.sim_step[b] > a.cfg.max_steps || explored > 0.85 || a.status[b] == DGE_ECAP) ? 1 : 0;
+      // exploration_env.py:416-419: a world in which the four forced steps of reset() saw no landmark is regenerated -- here the episode
+      // ends at once (uncounted) and the next reset draws the next world of the env's seed sequence
+      bool blind = false;
+      if (a.step_kind[b] == 2 && a.lm_obs) { int n = 0; for (int j = 0; j < a.Lfixed; ++j) n += a.lm_obs[(size_t)b * a.Lstride + j]; blind = n == 0; }
+      a.done[b] = (a.sim_step[b] > a.cfg.max_steps || explored > 0.85 || a.status[b] == DGE_ECAP || blind) ? 1 : 0;
     }
   }
   // the shared-memory source of the bulk copies must stay alive until they have been read
@@ -742,7 +751,7 @@ int dge_launch_vmap(dge_engine *e, const uint8_t *mask, cudaStream_t st) {
   k_vmap_cells<<<dim3(tiles, e->d.B), TILE * TILE, 0, st>>>(c, e->d.Tmax, e->n_poses, 0, e->vm_prep, e->vm_cbox, nchm, e->est_l, e->observed,
                                                              e->d.Lt, e->d.Lt, e->prob, e->vinfo, e->seen, mask);
   k_vmap_metrics<<<e->d.B, 256, 0, st>>>(e->cfg, e->d, e->prob, e->vinfo, e->sim_step, e->status, e->dist, e->metrics, e->done, mask,
-                                         e->n_poses, e->meas_ptr, e->count_steps ? e->counters : nullptr, e->step_kind);
+                                         e->n_poses, e->meas_ptr, e->count_steps ? e->counters : nullptr, e->step_kind, e->observed);
   return cudaGetLastError() == cudaSuccess ? DGE_OK : DGE_ECUDA;
 }
 

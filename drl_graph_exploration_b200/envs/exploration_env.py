@@ -119,7 +119,7 @@ class VecExplorationEnv:
         self.episodes_done = 0
 
     # ---------------------------------------------------------------- reset ---
-    def reset(self, mask: Optional[torch.Tensor] = None, seeds: Optional[torch.Tensor] = None, reference_worlds: bool = False):
+    def reset(self, mask: Optional[torch.Tensor] = None, seeds: Optional[torch.Tensor] = None, reference_worlds: bool = False, regenerate: bool = True):
         """exploration_env.py:389-422.  ``reference_worlds`` reproduces the reference's start poses
         (legacy NumPy RNG, pyss2d.py:88-95) on the host; landmarks/noise stay Philox (device)."""
         eng = self.eng
@@ -134,6 +134,22 @@ class VecExplorationEnv:
         for _ in range(4):
             eng.step(self._reset_odom, mask=mask)
         eng._L.dge_set_counting(eng._h, 1)
+        if regenerate and not reference_worlds:
+            # exploration_env.py:416-419: a world whose forced steps saw no landmark is regenerated (the in-pipeline resets apply the same
+            # rule on the device: csrc/dge_vmap.cu ends such an episode at once and the next reset draws the env's next world)
+            for _ in range(64):
+                blind = eng.state["observed"].sum(dim=1) == 0
+                if mask is not None:
+                    blind &= mask.bool()
+                if not bool(blind.any()):            # (one host sync per eager reset)
+                    break
+                self._seeds = torch.where(blind, self._seeds + self.B, self._seeds)
+                bm = blind.to(torch.uint8)
+                eng._L.dge_set_counting(eng._h, 0)
+                eng.reset(self._seeds, mask=bm)
+                for _ in range(4):
+                    eng.step(self._reset_odom, mask=bm)
+                eng._L.dge_set_counting(eng._h, 1)
         return eng.state["prob"]
 
     def reset_done(self, in_pipeline: bool = False):

@@ -143,3 +143,28 @@ def test_gnn_kernels_on_degenerate_graphs():
         out = model(Data(xg, e_index, e_w), 0.0)
         out.sum().backward()
         assert torch.isfinite(xg.grad).all()
+
+
+def test_world_without_an_observed_landmark_is_regenerated():
+    """exploration_env.py:416-419 for B envs: with the 8 landmarks of a 40x40 map a good part of the worlds show no landmark during the four forced steps.
+    The eager reset replaces them (next seed of the env's sequence); the in-pipeline reset ends such an episode at once, uncounted."""
+    import torch
+    from drl_graph_exploration_b200.config import EnvConfig
+    from drl_graph_exploration_b200.envs.exploration_env import RESET_ODOM, VecExplorationEnv
+    cfg = EnvConfig(map_size=40)
+    a = VecExplorationEnv(64, cfg=cfg, max_poses=32, seed0=0)
+    a.reset(regenerate=False)
+    blind0 = a.eng.state["observed"].sum(dim=1) == 0
+    assert int(blind0.sum()) >= 2, int(blind0.sum())               # the situation exists
+    seeds0 = a._seeds.clone()
+    a.reset()                                                      # regenerate=True: every env ends up with a landmark in view
+    assert int((a.eng.state["observed"].sum(dim=1) == 0).sum()) == 0
+    assert bool((a._seeds[blind0] != seeds0[blind0]).all()) and torch.equal(a._seeds[~blind0], seeds0[~blind0])
+    b = VecExplorationEnv(64, cfg=cfg, max_poses=32, seed0=0)
+    b.eng.reset_queued(b._seeds, None, RESET_ODOM, 4)
+    c0 = b.eng.state["counters"].clone()
+    for _ in range(5):
+        b.step_queued()
+    torch.cuda.synchronize()
+    assert torch.equal(b.eng.state["done"].bool(), blind0) and torch.equal(b.eng.state["counters"][:3], c0[:3])
+    a.close(); b.close()

@@ -21,7 +21,7 @@ def _mk(n=24):
 def test_queued_reset_equals_eager_reset():
     from drl_graph_exploration_b200.envs.exploration_env import RESET_ODOM
     a, b = _mk(), _mk()
-    a.reset()
+    a.reset(regenerate=False)          # same worlds on both sides (the eager reset would replace a world that saw no landmark)
     b.eng.reset_queued(b._seeds, None, RESET_ODOM, 4)
     assert int(b.needs_decision().sum()) == 0            # forced steps pending: no decision asked
     c0 = b.eng.state["counters"].clone()
@@ -30,10 +30,16 @@ def test_queued_reset_equals_eager_reset():
     torch.cuda.synchronize()
     assert torch.equal(b.eng.state["counters"], c0)      # forced steps are not policy steps
     assert int(b.eng.state["forced"].abs().sum()) == 0
-    assert int(b.needs_decision().sum()) == int(a.needs_decision().sum()) == a.B
     sa, sb = a.eng.state, b.eng.state
+    seeing = sa["observed"].sum(dim=1) > 0               # (a world that saw no landmark is ended at once by the in-pipeline path, below)
+    assert int(a.needs_decision().sum()) == a.B and torch.equal(b.needs_decision().bool(), seeing)
+    # exploration_env.py:416-419: a world whose forced steps saw no landmark ends its episode at once on the in-pipeline path (the next
+    # reset regenerates it); everywhere else the `done` flags agree
+    blind = sa["observed"].sum(dim=1) == 0
+    assert torch.equal(sb["done"][blind], torch.ones_like(sb["done"][blind])) and torch.equal(sa["done"][~blind], sb["done"][~blind])
     for f in FIELDS:
-        assert torch.equal(sa[f], sb[f]), f
+        if f != "done":
+            assert torch.equal(sa[f], sb[f]), f
     T = int(sa["n_poses"].max())
     assert T == 5
     for f in FIELDS_FP:
@@ -72,7 +78,7 @@ def test_queued_reset_inside_running_loop():
             if pending[i][1] == 0:
                 seed, _ = pending.pop(i)
                 ref = _mk(16)
-                ref.reset(seeds=torch.full((16,), seed, dtype=torch.int64))
+                ref.reset(seeds=torch.full((16,), seed, dtype=torch.int64), regenerate=False)
                 torch.cuda.synchronize()
                 assert int(st["n_poses"][i]) == 5 and int(st["forced"][i]) == 0
                 for f in ("true_pose", "prob", "vinfo", "seen", "observed"):
