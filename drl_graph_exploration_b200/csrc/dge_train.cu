@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(1024) k_dqn_cost(int N, const float *__restric
 // ---- column reductions over the nodes -------------------------------------------------------------------------------------
 // MODE 0 (head):     gWh[c] = sum_n dq[n] d2[n,c];  gbh = sum_n dq[n];  gb2[c] = Wh[c] s sum_n dq[n] [d2[n,c] != 0]
 // MODE 1 (layer 1):  gb1[c] = sum_n dz1[n,c];  gW1[k,c] = sum_n ax[n,k] dz1[n,c]   with dz1 = dh1 * [h1 > 0]
-// Row slabs (n = slab, slab + NSLAB, ...) -> partials; the last CTA to finish adds the partials in slab order.
+// Row slabs (n = slab, slab + NSLAB, ...) -> partials; k_colreduce_final adds the partials in slab order.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_colreduce(int N, int C, int Cin, const float *__restrict__ dq, const float *__restrict__ A /*d2 | dh1*/,
                                                    const float *__restrict__ Bm /*- | h1_hi*/, const float *__restrict__ ax, const float *__restrict__ Wh, float scale,
@@ -243,36 +243,29 @@ __global__ void __launch_bounds__(256) k_colreduce(int N, int C, int Cin, const 
 #pragma unroll
     for (int v = 0; v < NV; ++v) *reinterpret_cast<float4 *>(mine + (size_t)v * C + c0) = make_float4(acc[v][0], acc[v][1], acc[v][2], acc[v][3]);
   if (MODE == 0 && threadIdx.x == 0) part[(size_t)gridDim.x * NV * C + blockIdx.x] = sdq;
-  __threadfence();
-  __shared__ unsigned last;
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1u : 0u;
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  if (act) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (unsigned b = 0; b < gridDim.x; ++b) {
-        const float4 x = *reinterpret_cast<const float4 *>(part + ((size_t)b * NV + v) * C + c0);
-        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
-      }
-      if (MODE == 0) {
-        if (v == 0) *reinterpret_cast<float4 *>(o0 + c0) = s;
-        else { const float4 w = *reinterpret_cast<const float4 *>(Wh + c0); *reinterpret_cast<float4 *>(o1 + c0) = make_float4(s.x * w.x * scale, s.y * w.y * scale, s.z * w.z * scale, s.w * w.w * scale); }
-      } else {
-        if (v == 0) *reinterpret_cast<float4 *>(o0 + c0) = s;
-        else if (v - 1 < Cin) *reinterpret_cast<float4 *>(o1 + (size_t)(v - 1) * C + c0) = s;
-      }
+}
+
+// second stage: one thread per (vector, column) adds the slabs' partials in slab order (deterministic; coalesced across columns)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_colreduce_final(int C, int Cin, int nslab, const float *__restrict__ part, const float *__restrict__ Wh, float scale,
+                                                         float *__restrict__ o0, float *__restrict__ o1, float *__restrict__ o2) {
+  constexpr int NV = MODE == 0 ? 2 : 9;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < NV * C) {
+    const int v = idx / C, c = idx - v * C;
+    float s = 0.f;
+    for (int b = 0; b < nslab; ++b) s += part[((size_t)b * NV + v) * C + c];
+    if (MODE == 0) {
+      if (v == 0) o0[c] = s; else o1[c] = s * Wh[c] * scale;
+    } else {
+      if (v == 0) o0[c] = s; else if (v - 1 < Cin) o1[(size_t)(v - 1) * C + c] = s;
     }
   }
-  if (MODE == 0 && threadIdx.x == 0) {
+  if (MODE == 0 && idx == 0) {
     float s = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += part[(size_t)gridDim.x * NV * C + b];
+    for (int b = 0; b < nslab; ++b) s += part[(size_t)nslab * NV * C + b];
     o2[0] = s;
   }
-  if (threadIdx.x == 0) *counter = 0u;     // ready for the next launch
 }
 
 // ---- g2 = A^T dz2, dz2[n,c] = dq[n] s Wh[c] [d2[n,c] != 0] formed on the fly; gather over the source-sorted CSR --------------------
@@ -349,7 +342,7 @@ extern "C" int dge_gcn_train_step(int N, int Cin, int C, const float *x, const i
   unsigned *counter = reinterpret_cast<unsigned *>(part + (int64_t)NSLAB * 9 * C + NSLAB);
   float *dh1 = t2;
   const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-  if (cudaMemsetAsync(counter, 0, 64 * sizeof(unsigned), st) != cudaSuccess) return -2;
+  (void)counter;
   // ---- forward
   k_conv1_train<<<node_grid(N), 256, 0, st>>>(N, Cin, C, x, rowptr_d, perm_d, src, norm, selfnorm, W1, b1, ax, h1); CKL();
   const dim3 tg((C + 31) / 32, (unsigned)((Np + 31) / 32));
@@ -363,6 +356,7 @@ extern "C" int dge_gcn_train_step(int N, int Cin, int C, const float *x, const i
   k_dqn_cost<<<1, 1024, 0, st>>>(N, q, act, y, inv_batch, dq, loss); CKL();
   // ---- backward
   k_colreduce<0><<<NSLAB, 256, 0, st>>>(N, C, Cin, dq, d2, nullptr, nullptr, Wh, scale, part, counter, gWh, gb2, gbh); CKL();
+  k_colreduce_final<0><<<(2 * C + 255) / 256, 256, 0, st>>>(C, Cin, NSLAB, part, Wh, scale, gWh, gb2, gbh); CKL();
   k_agg_bwd_train<<<node_grid(N), 256, 0, st>>>(N, C, d2, dq, Wh, scale, rowptr_s, perm_s, dst, norm, selfnorm, g2); CKL();
   k_split_transpose<<<tg, 256, 0, st>>>(N, C, (int)Np, g2, g2_hi, g2_lo, g2t_hi, g2t_lo); CKL();
   rc = dge_gemm_tf32x3_ex(N, nullptr, C, C, g2_hi, g2_lo, 0, W2_hi, W2_lo, 0, dh1, C, 1, st);            // dh1 = g2 W2^T
@@ -371,6 +365,7 @@ extern "C" int dge_gcn_train_step(int N, int Cin, int C, const float *x, const i
   rc = dge_gemm_tf32x3_ex(C, nullptr, C, N, h1t_hi, h1t_lo, (int)Np, g2t_hi, g2t_lo, (int)Np, gW2, C, 0, st);   // dW2 = h1^T g2, K = nodes
   if (rc) return rc;
   k_colreduce<1><<<NSLAB, 256, 0, st>>>(N, C, Cin, nullptr, dh1, h1_hi, ax, nullptr, 1.f, part, counter + 1, gb1, gW1, nullptr); CKL();
+  k_colreduce_final<1><<<(9 * C + 255) / 256, 256, 0, st>>>(C, Cin, NSLAB, part, nullptr, 1.f, gb1, gW1, nullptr); CKL();
   return 0;
 }
 

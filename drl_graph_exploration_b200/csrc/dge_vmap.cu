@@ -321,10 +321,13 @@ struct EnvArgs {
   const int32_t *order;                                // nullable [n]: block -> env (cost-ordered placement of the step kernels, dge_slam.cu)
 };
 
-template <int WT, int NTHR>   // WT = block width W when known at compile time (7 for the reference's sensor / resolution), 0 = generic
+// SPEC (512 threads): warp-specialised -- warps [0, 8) PREDICT chunk i + 1 into the second record buffer while warps [8, 16) FOLD chunk i
+// (the fold is a handful of long dependent chains, the prediction is throughput work: run beside each other, not behind);
+// the two groups meet at named barriers (records of a buffer full / free), never at a CTA-wide barrier inside the loop.
+template <int WT, int NTHR, bool SPEC>   // WT = block width W when known at compile time (7 for the reference's sensor / resolution), 0 = generic
 __global__ void __launch_bounds__(NTHR, 2) k_vmap_env(EnvArgs a) {
-  constexpr int NWARP = NTHR / 32;
-  constexpr int GR = NTHR >= 512 ? 2 : 4;                // pairs a lane gates side by side
+  constexpr int NWARP = SPEC ? 8 : NTHR / 32;            // warps that predict
+  constexpr int GR = 4;                                  // pairs a lane gates side by side
   const int b = a.order ? a.order[blockIdx.x] : blockIdx.x;
   if (a.mask && !a.mask[b]) return;
   const VmapCfg &c = a.c;
@@ -336,8 +339,9 @@ __global__ void __launch_bounds__(NTHR, 2) k_vmap_env(EnvArgs a) {
   unsigned *sst = reinterpret_cast<unsigned *>(sinf + 3 * (size_t)V);   // count | ST_UPD | ST_LM
   double *dig = reinterpret_cast<double *>(sst + ((V + 1) & ~1));        // [2][KC][DIG_W]
   const int RS = KC * WW;                                       // records per chunk
-  double *rxx = dig + 2 * KC * DIG_W, *rxy = rxx + RS, *ryy = rxy + RS;  // records (one buffer: predict and fold are separated by barriers)
-  double *s_red = ryy + RS;                                     // [256] + 2 x int[256]
+  double *rec0 = dig + 2 * KC * DIG_W;                          // records [NB][3][RS]: one buffer (predict and fold separated by barriers) or two (SPEC)
+  constexpr int NB = SPEC ? 2 : 1;
+  double *s_red = rec0 + NB * 3 * RS;                           // [256] + 2 x int[256]
   int *s_fr = reinterpret_cast<int *>(s_red + 256 + 256);       // [2][16] first row of every pose's block
   int *s_fc = s_fr + 32;                                        // [2][16] first column
   int4 *s_box = reinterpret_cast<int4 *>((reinterpret_cast<uintptr_t>(s_fc + 32) + 15) & ~uintptr_t(15));   // [2] cell box [r0, r1) x [c0, c1) of the chunk
@@ -413,15 +417,15 @@ __global__ void __launch_bounds__(NTHR, 2) k_vmap_env(EnvArgs a) {
   const int nb1 = __syncthreads_count(1);
   if (a.clocks && tid == 0 && nb1) a.clocks[4 * b + 1] = clock64();
 
-  unsigned short *mylist = s_list + warp * PPW;
+  unsigned short *mylist = s_list + (warp < NWARP ? warp : 0) * PPW;
   long long ph[5] = {0, 0, 0, 0, 0};
-  for (int ch = 0; ch < nch; ++ch) {
-    long long t0 = a.phase ? clock64() : 0, t1;
+  long long t0 = 0;
+  // ---- chunk ch, PREDICT into record buffer rb (the calling warps: [0, NWARP)) -----------------------------------------
+  auto predict = [&](const int ch, const int rb) {
     const int k0 = ch * KC, kc = min(KC, T - k0), bf = ch & 1;
     const double *dg = dig + (size_t)bf * KC * DIG_W;
     const int *fr_ = s_fr + bf * 16, *fc_ = s_fc + bf * 16;
-    if (ch + 1 < nch) load_rows(ch + 1);
-    if (warp == NWARP - 1) chunk_box(ch);
+    double *rxx = rec0 + (size_t)rb * 3 * RS, *rxy = rxx + RS, *ryy = rxy + RS;
     // ---- PREDICT, gate pass: this warp's slice of the chunk's pairs, GR pairs per lane evaluated side by side
     // (independent straight-line instances: instruction-level parallelism for the latency of the fp64 predicates) -----
     const int np = kc * WW, p_lo = min(np, warp * PPW), p_hi = min(np, p_lo + PPW);
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_vmap_env(EnvArgs a) {
       }
     }
     __syncwarp();
-    if (a.phase) { t1 = clock64(); ph[0] += t1 - t0; t0 = t1; }
+    if (a.phase) { const long long t1 = clock64(); ph[0] += t1 - t0; t0 = t1; }
     // ---- PREDICT, SPD pass on the compacted list, two entries per lane side by side ---------------------------------
     for (int i0 = 0; i0 < n_act; i0 += 64) {
 #pragma unroll
@@ -515,16 +519,19 @@ __global__ void __launch_bounds__(NTHR, 2) k_vmap_env(EnvArgs a) {
         }
       }
     }
-    if (a.phase) { t1 = clock64(); ph[1] += t1 - t0; t0 = t1; }
-    {
-      const int nbw = __syncthreads_count(1);
-      if (a.phase && nbw) { t1 = clock64(); ph[2] += t1 - t0; t0 = t1; }
-    }
+    if (a.phase) { const long long t1 = clock64(); ph[1] += t1 - t0; t0 = t1; }
+  };
+  // ---- chunk ch, FOLD from record buffer rb: thread ftid of fthr folding threads ---------------------------------------
+  auto fold = [&](const int ch, const int rb, const int ftid, const int fthr) {
+    const int k0 = ch * KC, kc = min(KC, T - k0), bf = ch & 1;
+    (void)k0;
+    const int *fr_ = s_fr + bf * 16, *fc_ = s_fc + bf * 16;
+    const double *rxx = rec0 + (size_t)rb * 3 * RS, *rxy = rxx + RS, *ryy = rxy + RS;
     // ---- FOLD: the cells of the chunk's box, one thread per cell, the chunk's poses in trajectory order ---------
     {
       const int4 bx = s_box[bf];
       const int r0 = bx.x, c0 = bx.z, bw = bx.w - bx.z, nbc = (bx.y > r0 && bw > 0) ? (bx.y - r0) * bw : 0;
-      for (int ci = tid; ci < nbc; ci += nthr) {
+      for (int ci = ftid; ci < nbc; ci += fthr) {
         const int rr_ = ci / bw, row = r0 + rr_, col = c0 + ci - rr_ * bw;
         const int idx = row * c.cols + col;
         unsigned m = 0;
@@ -570,17 +577,80 @@ __global__ void __launch_bounds__(NTHR, 2) k_vmap_env(EnvArgs a) {
           nxx = fxx; nxy = fxy; nyy = fyy;
         }
         st[0] = ixx; st[1] = ixy; st[2] = iyy;
-        sst[idx] |= ST_UPD;                                 // (the cell's only writer between the two barriers)
+        atomicOr(&sst[idx], ST_UPD);                        // (atomic: the next chunk's gate pass may be counting visibility on this word)
       }
     }
-    if (a.phase) { t1 = clock64(); ph[3] += t1 - t0; t0 = t1; }
-    if (ch + 1 < nch) store_rows(ch + 1);
-    {
-      const int nbw = __syncthreads_count(1);
-      if (a.phase && nbw) { t1 = clock64(); ph[4] += t1 - t0; }
+  };
+  if (!SPEC) {
+    for (int ch = 0; ch < nch; ++ch) {
+      t0 = a.phase ? clock64() : 0;
+      if (ch + 1 < nch) load_rows(ch + 1);
+      if (warp == NWARP - 1) chunk_box(ch);
+      predict(ch, 0);
+      {
+        const int nbw = __syncthreads_count(1);
+        if (a.phase && nbw) { const long long t1 = clock64(); ph[2] += t1 - t0; t0 = t1; }
+      }
+      fold(ch, 0, tid, nthr);
+      if (a.phase) { const long long t1 = clock64(); ph[3] += t1 - t0; t0 = t1; }
+      if (ch + 1 < nch) store_rows(ch + 1);
+      {
+        const int nbw = __syncthreads_count(1);
+        if (a.phase && nbw) { const long long t1 = clock64(); ph[4] += t1 - t0; }
+      }
+    }
+  } else {
+    // named barriers: FULL[b] = 1 + b (records of buffer b written: predict arrives, fold waits), FREE[b] = 3 + b (fold done with buffer b and
+    // with the chunk's block origins / box: fold arrives, predict waits), 5 = the predict group, 6 = the fold group
+    // (immediate barrier ids: with ids in registers the compiler reserves all 16 named barriers of the CTA)
+    auto bar_sync = [](int id, int n) {
+      switch (id) {
+        case 1: asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); break;
+        case 2: asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); break;
+        case 3: asm volatile("bar.sync 3, %0;" ::"r"(n) : "memory"); break;
+        case 4: asm volatile("bar.sync 4, %0;" ::"r"(n) : "memory"); break;
+        case 5: asm volatile("bar.sync 5, %0;" ::"r"(n) : "memory"); break;
+        default: asm volatile("bar.sync 6, %0;" ::"r"(n) : "memory"); break;
+      }
+    };
+    auto bar_arrive = [](int id, int n) {
+      switch (id) {
+        case 1: asm volatile("bar.arrive 1, %0;" ::"r"(n) : "memory"); break;
+        case 2: asm volatile("bar.arrive 2, %0;" ::"r"(n) : "memory"); break;
+        case 3: asm volatile("bar.arrive 3, %0;" ::"r"(n) : "memory"); break;
+        default: asm volatile("bar.arrive 4, %0;" ::"r"(n) : "memory"); break;
+      }
+    };
+    constexpr int GRP = 256;
+    if (warp < NWARP) {
+      for (int ch = 0; ch < nch; ++ch) {
+        t0 = a.phase ? clock64() : 0;
+        if (ch >= 2) bar_sync(3 + (ch & 1), 2 * GRP);                   // fold(ch - 2) has left buffer ch & 1
+        if (ch >= 1) {                                                  // rows of this chunk: registers -> shared memory, then the chunk's box
+          store_rows(ch);
+          bar_sync(5, GRP);
+        }
+        if (warp == NWARP - 1) chunk_box(ch);
+        if (a.phase) { const long long t1 = clock64(); ph[2] += t1 - t0; t0 = t1; }
+        if (ch + 1 < nch) load_rows(ch + 1);
+        predict(ch, ch & 1);
+        bar_arrive(1 + (ch & 1), 2 * GRP);                              // (release: the records, origins and box of chunk ch)
+      }
+    } else {
+      const int ftid = tid - GRP;
+      for (int ch = 0; ch < nch; ++ch) {
+        t0 = a.phase ? clock64() : 0;
+        bar_sync(1 + (ch & 1), 2 * GRP);
+        if (a.phase) { const long long t1 = clock64(); ph[4] += t1 - t0; t0 = t1; }
+        fold(ch, ch & 1, ftid, GRP);
+        bar_sync(6, GRP);                                               // a cell may change hands between chunks: every fold of chunk ch first
+        if (a.phase) { const long long t1 = clock64(); ph[3] += t1 - t0; }
+        if (ch + 2 < nch) bar_arrive(3 + (ch & 1), 2 * GRP);
+      }
     }
   }
-  if (a.phase && tid == 0) for (int i = 0; i < 5; ++i) a.phase[8 * b + i] = ph[i];
+  if (a.phase && tid == 0) for (int i = 0; i < (SPEC ? 3 : 5); ++i) a.phase[8 * b + i] = ph[i];
+  if (SPEC && a.phase && tid == 256) { a.phase[8 * b + 3] = ph[3]; a.phase[8 * b + 4] = ph[4]; }
   // ---- write the map: every output byte once ---------------------------------------------------------------------
   const size_t cell0 = (size_t)b * V;
   const bool bulk = (V & 1) == 0;                        // 24 V bytes and the env's offset are multiples of 16
@@ -689,35 +759,37 @@ int dge_vmap_prep_width() { return PREP_W; }
 
 namespace {
 // geometry of the fused kernel for a map: chunk length and shared memory; false if the map does not fit
-int env_threads() {   // CTA size of the fused kernel: DGE_VMAP_THREADS=256|512 (A/B switch; 256 measured faster at C4: profiles/r02_c4_vmap_sweep_v2.md)
-  static const int n = [] { const char *v = getenv("DGE_VMAP_THREADS"); return (v && atoi(v) == 512) ? 512 : 256; }();
+int env_threads() {   // DGE_VMAP_THREADS=256: the single-group kernel (A/B); default 512 = warp-specialised predict || fold
+  static const int n = [] { const char *v = getenv("DGE_VMAP_THREADS"); return (v && atoi(v) == 256) ? 256 : 512; }();
   return n;
 }
-size_t env_smem(size_t V, int kc, int W, int nthr) {
-  const size_t rs = (size_t)kc * W * W, nw = nthr / 32, ppw = (rs + nw - 1) / nw;
-  return V * 3 * sizeof(double) + ((V + 1) & ~(size_t)1) * sizeof(unsigned) + 2 * (size_t)kc * DIG_W * sizeof(double) + 3 * rs * sizeof(double) +
+size_t env_smem(size_t V, int kc, int W, int nbuf) {
+  const size_t rs = (size_t)kc * W * W, nw = 8, ppw = (rs + nw - 1) / nw;
+  return V * 3 * sizeof(double) + ((V + 1) & ~(size_t)1) * sizeof(unsigned) + 2 * (size_t)kc * DIG_W * sizeof(double) + nbuf * 3 * rs * sizeof(double) +
          256 * (sizeof(double) + 2 * sizeof(int)) + 64 * sizeof(int) + 16 + 2 * sizeof(int4) + nw * ((ppw + 7) & ~(size_t)7) * sizeof(unsigned short) + 32;
 }
-bool env_plan(const dge_config &g, int rows, int cols, int nthr, int *hw, int *W, int *kc, int *ppw, size_t *smem) {
+bool env_plan(const dge_config &g, int rows, int cols, int nbuf, int *hw, int *W, int *kc, int *ppw, size_t *smem) {
   *hw = (int)ceil(g.max_range / g.resolution);
   *W = 2 * *hw + 1;
   if (*W > 15) return false;
-  const size_t V = (size_t)rows * cols, nw = nthr / 32;
-  // chunk length: 16 poses (the fold's hit mask; its digest rows are moved by 16 x 12 threads), shorter only if the record buffer
+  const size_t V = (size_t)rows * cols, nw = 8;
+  // chunk length: up to 16 poses (the fold's hit mask; its digest rows are moved by 16 x 12 threads), shorter only if the record buffer(s)
   // would not leave room for two CTAs per SM
-  for (int k = 16; k >= 1; k >>= 1) {
-    *kc = k; *smem = env_smem(V, k, *W, nthr);
+  for (int k = 16; k >= 1; k = k > 8 ? k - 2 : k >> 1) {
+    *kc = k; *smem = env_smem(V, k, *W, nbuf);
     *ppw = (int)((((size_t)k * *W * *W + nw - 1) / nw + 7) & ~(size_t)7);
-    if (*smem <= 113 * 1024 || (k == 1 && *smem <= 226 * 1024)) return true;
+    if (*smem <= 112 * 1024 || (k == 1 && *smem <= 226 * 1024)) return true;
   }
   return false;
 }
 int env_launch(EnvArgs &a, const dge_config &g, int n, int rows, int cols, cudaStream_t st) {
   size_t smem;
-  const int nthr = env_threads();
-  if (!env_plan(g, rows, cols, nthr, &a.hw, &a.W, &a.kc, &a.ppw, &smem)) return 1;   // caller falls back to the cell-centric kernels
+  int nthr = env_threads();
+  if (nthr == 512 && !env_plan(g, rows, cols, 2, &a.hw, &a.W, &a.kc, &a.ppw, &smem)) nthr = 256;   // (two record buffers do not fit: single-group kernel)
+  if (nthr == 512 && a.kc < 8) nthr = 256;                                                           // (too short chunks for the pipelined schedule)
+  if (nthr == 256 && !env_plan(g, rows, cols, 1, &a.hw, &a.W, &a.kc, &a.ppw, &smem)) return 1;       // caller falls back to the cell-centric kernels
   const int vi = (a.W == 7 ? 1 : 0) + (nthr == 512 ? 2 : 0);
-  void (*kern)(EnvArgs) = vi == 3 ? k_vmap_env<7, 512> : vi == 2 ? k_vmap_env<0, 512> : vi == 1 ? k_vmap_env<7, 256> : k_vmap_env<0, 256>;
+  void (*kern)(EnvArgs) = vi == 3 ? k_vmap_env<7, 512, true> : vi == 2 ? k_vmap_env<0, 512, true> : vi == 1 ? k_vmap_env<7, 256, false> : k_vmap_env<0, 256, false>;
   static size_t configured[4] = {0, 0, 0, 0};
   size_t &cf = configured[vi];
   if (smem > 48 * 1024 && smem > cf) {

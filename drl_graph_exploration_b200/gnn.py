@@ -348,7 +348,7 @@ def gcn_train_eligible(model) -> bool:
 def gcn_train_step(model, x: torch.Tensor, gs: GraphStructure, action, y, inv_batch: float, drop_p: float, seed: Optional[int] = None,
                    return_debug: bool = False):
     """Forward (functional dropout p), DeepQ.cost and the whole backward pass of ``Networks.GCN`` in ONE native call
-    (``dge_gcn_train_step``, csrc/dge_train.cu: 13 launches, the three [nodes,1000]x[1000,1000]-shaped products on the tcgen05
+    (``dge_gcn_train_step``, csrc/dge_train.cu: 15 launches, the three [nodes,1000]x[1000,1000]-shaped products on the tcgen05
     3xTF32 kernel, no autograd graph).  The gradients are WRITTEN into the parameters' ``.grad`` buffers (which must exist and be
     contiguous: ``dist.FlatGradBucket``); returns (loss, q) as device tensors -- nothing is read back.  ``action`` / ``y``: [N] float
     tensors (None: a = 1 / y = 0, i.e. loss = sum(q^2) * inv_batch)."""
@@ -386,7 +386,7 @@ def gcn_train_step(model, x: torch.Tensor, gs: GraphStructure, action, y, inv_ba
                                   _p(loss), _p(q), _p(ws), _st(dev))
     if rc:
         raise DgeError(f"dge_gcn_train_step failed ({rc})")
-    launch_count += 13
+    launch_count += 15
     if return_debug:   # tests: the activations the backward pass used (h1, dropout(h2)) -- views of the workspace, valid until the next call
         NC = N * C
         return loss[0], q, dict(h1=ws[8 * N:8 * N + NC].view(N, C), d2=ws[8 * N + 4 * NC:8 * N + 5 * NC].view(N, C))
