@@ -72,7 +72,7 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.ws_Bt = al.get<double>(B * T * 3 * 2 * L); e.ws_FB = al.get<double>(B * T * 3 * 2 * L);
   e.ws_midx = al.get<int32_t>(B * T * L);
   e.lm_slot = al.get<int32_t>(B * L); e.fc_valid = al.get<int32_t>(B); e.step_order = al.get<int32_t>(B); e.fc_state = al.get<double>(B * (size_t)DGE_FC_WIDTH(L));
-  e.ck_state = al.get<double>(B * (size_t)DGE_FC_WIDTH(L)); e.ck_pos = al.get<int32_t>(B); e.lm_first = al.get<int32_t>(B * L);
+  e.ck_state = al.get<double>(B * (size_t)DGE_CK_DEPTH * DGE_FC_WIDTH(L)); e.ck_pos = al.get<int32_t>(B * (size_t)DGE_CK_STRIDE); e.lm_first = al.get<int32_t>(B * L);
   e.vm_prep = al.get<double>(B * T * dge_vmap_prep_width()); e.vm_cbox = al.get<double>(B * (size_t)dge_vmap_nchunk(d.Tmax) * 4);
   e.seen = al.get<int32_t>(B * V); e.active = al.get<uint8_t>(B);
   e.prob = al.get<double>(B * V); e.vinfo = al.get<double>(B * V * 3); e.metrics = al.get<double>(B * 8); e.dist = al.get<double>(B);

@@ -10,6 +10,8 @@
 #define DGE_PI 3.14159265358979323846
 #define DGE_WS_POSE 40
 #define DGE_FC_WIDTH(Lt) (16 + 4 * (2 * (Lt)) + (2 * (Lt)) * (2 * (Lt)))
+#define DGE_CK_DEPTH 4                       /* checkpoints of the elimination state kept per env (a stack, oldest dropped) */
+#define DGE_CK_STRIDE (2 * DGE_CK_DEPTH + 1)  /* ints per env in ck_pos: positions [DEPTH] (stack order), physical slots [DEPTH] (a permutation), count */
 
 struct DgeDims {
   int B, Tmax, Lt, rows, cols, V, Mmax;
@@ -48,8 +50,9 @@ struct dge_engine {
   int32_t *step_order;   // [B] block -> env of the last SLAM launch (cost-ordered placement); step_order_live: valid for the virtual-map launch that follows
   int step_order_live;
   double *fc_state;      // [B,DGE_FC_WIDTH(Lt)] cached forward-elimination state behind the closed poses (dge_slam.cu)
-  double *ck_state;      // [B,DGE_FC_WIDTH(Lt)] checkpoint of that state a rebuild leaves three poses before its end (the next rebuild resumes there)
-  int32_t *ck_pos;       // [B]             closed poses behind the checkpoint (0 = none)
+  double *ck_state;      // [B,DGE_CK_DEPTH,DGE_FC_WIDTH(Lt)] checkpoints of that state: every rebuild leaves one three poses before its end, the next rebuild
+                         //                 resumes from the newest one nothing in front of which has moved
+  int32_t *ck_pos;       // [B,DGE_CK_STRIDE] the stack: closed poses behind each checkpoint, its physical slot, the count
   int32_t *lm_first;     // [B,Lt]          pose index of a landmark's first observation
   double *vm_prep;       // [B,Tmax,12]     digested poses for the virtual-map kernel
   double *vm_cbox;       // [B,nchunk,4]    per-32-pose bounding boxes

@@ -138,7 +138,9 @@ __global__ void __launch_bounds__(256) k_rollout_clone(dge_config cfg, EngPtrs D
   if (tid == 0) {
     D.seed[c] = S.seed[b];                // Simulator2D copy incl. RNG state (:1420): every roll-out of an env sees the same noise stream
     D.n_poses[c] = T; D.sim_step[c] = S.sim_step[b]; D.update_count[c] = 1; D.status[c] = 0;
-    D.fc_valid[c] = 0; D.ck_pos[c] = 0;   // the clone's SLAM solve starts from a full elimination (no cached state or checkpoint travels with a clone)
+    D.fc_valid[c] = 0;                    // the clone's SLAM solve starts from a full elimination (no cached state or checkpoint travels with a clone)
+    for (int i = 0; i < DGE_CK_DEPTH; ++i) { D.ck_pos[c * DGE_CK_STRIDE + i] = 0; D.ck_pos[c * DGE_CK_STRIDE + DGE_CK_DEPTH + i] = i; }
+    D.ck_pos[c * DGE_CK_STRIDE + 2 * DGE_CK_DEPTH] = 0;
     D.dist[c] = 0; D.rdist[c] = 0; D.done[c] = 0; D.active[c] = 0;
     const double *p = S.est_pose + ((size_t)b * Tm + T - 1) * 3;
     const int gi = 0; (void)gi;

@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(32) k_reset(SimArgs a, const uint8_t *mask, co
   // the mask may be the env's own `done` flag (dge_reset_done_queued): it is cleared below, after this read
   const uint64_t key = seeds ? seeds[b] : a.seed[b] + seed_stride;
   __syncwarp();
-  if (lane == 0) { a.seed[b] = key; a.ck_pos[b] = 0; if (episodes) atomicAdd(episodes, 1ull); }
+  if (lane == 0) { a.seed[b] = key; if (episodes) atomicAdd(episodes, 1ull); }
+  if (lane < DGE_CK_DEPTH) { a.ck_pos[(size_t)b * DGE_CK_STRIDE + lane] = 0; a.ck_pos[(size_t)b * DGE_CK_STRIDE + DGE_CK_DEPTH + lane] = lane; }   // no checkpoints; slots = identity
+  if (lane == 0) a.ck_pos[(size_t)b * DGE_CK_STRIDE + 2 * DGE_CK_DEPTH] = 0;
   // ---- start pose (pyss2d.py:88-95: integer x/y on the *map* half-width, whole-degree heading; q2)
   double sx, sy, sth;
   if (start) { sx = start[3 * b]; sy = start[3 * b + 1]; sth = start[3 * b + 2]; }

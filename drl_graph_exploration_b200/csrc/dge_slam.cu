@@ -57,8 +57,8 @@ struct SlamArgs {
   int32_t *ws_midx;
   int32_t *lm_slot, *fc_valid;   // [B,Lt] landmark id -> border slot ; [B] number of poses the cached elimination state was saved at
   const int32_t *lm_first;       // [B,Lt] pose at which a landmark was first observed (k_move_measure)
-  int32_t *ck_pos;               // [B] number of closed poses behind the CHECKPOINT of the elimination state (0 = none)
-  double *ck_state;              // [B, DGE_FC_WIDTH(Lt)] checkpoint, same layout as fc_state
+  int32_t *ck_pos;               // [B, DGE_CK_STRIDE] stack of checkpoints: closed poses behind each, physical slot of each, count
+  double *ck_state;              // [B, DGE_CK_DEPTH, DGE_FC_WIDTH(Lt)] checkpoints of the elimination state, each laid out like fc_state
   double *fc_state;              // [B, DGE_FC_WIDTH(Lt)] cached state: cD(6) cg(3) pad | cB [N2C][3] | gl [N2C] | S_partial [N2C][N2C]
   int incremental;               // 0: every step eliminates from pose 0 (A/B switch, DGE_SLAM_INCREMENTAL=0)
   const int32_t *order;          // nullable [B]: block -> env (cost-ordered placement, k_step_order)
@@ -165,8 +165,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   int32_t *slot_g = a.lm_slot + (size_t)b * Lt;
   double *fc = a.fc_state + (size_t)b * DGE_FC_WIDTH(Lt);     // cD(6) cg(3) | cB | gl | S_partial
   double *fc_cB = fc + 16, *fc_gl = fc_cB + 3 * N2C, *fc_S = fc_gl + N2C;
-  double *ck = a.ck_state + (size_t)b * DGE_FC_WIDTH(Lt);     // checkpoint: same layout
-  double *ck_cB = ck + 16, *ck_gl = ck_cB + 3 * N2C, *ck_S = ck_gl + N2C;
+  int32_t *ckp = a.ck_pos + (size_t)b * DGE_CK_STRIDE;        // positions [DEPTH] | physical slots [DEPTH] | count
 
   // ---------------------------------------------------------------- step 0 ---
   // ISAM2 relinearisation schedule (gtsam ISAM2::update: ++update_count; every
@@ -201,22 +200,32 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   // the cached elimination state is usable iff nothing was relinearised and it was saved one pose ago
   const int any_moved = __syncthreads_or(moved);
   const bool valid = !any_moved && a.incremental && T >= 2 && a.fc_valid[b] == T - 1;
-  // a rebuild resumes from the checkpoint if nothing in front of it moved (block-wide minimum of rmin), else from pose 0;
-  // it leaves a new checkpoint three poses before its end
-  int c_use = 0;
-  if (!valid && a.incremental && a.ck_pos[b] > 0 && a.ck_pos[b] <= T - 2) {
-    c_use = a.ck_pos[b];
+  // a rebuild resumes from the NEWEST checkpoint nothing in front of which has moved (block-wide minimum of rmin), else from pose 0; the
+  // checkpoints behind that point describe a prefix that no longer exists and are dropped; the rebuild leaves a new one three poses before its end
+  int c_use = 0, ck_cnt = 0, ck_src_slot = 0;
+  if (!valid && a.incremental) {
+    ck_cnt = ckp[2 * DGE_CK_DEPTH];
+    int limit = T - 2;
     if (any_moved) {
       rmin = __reduce_min_sync(0xffffffffu, rmin);
       if (lane == 0) red_i[warp] = rmin;
       __syncthreads();
       int r = red_i[0];
       for (int w = 1; w < NT / 32; ++w) r = min(r, red_i[w]);
-      if (r < c_use) c_use = 0;
+      limit = min(limit, r);
       __syncthreads();
     }
+    while (ck_cnt > 0 && ckp[ck_cnt - 1] > limit) --ck_cnt;
+    if (ck_cnt > 0 && ckp[ck_cnt - 1] > 0) { c_use = ckp[ck_cnt - 1]; ck_src_slot = ckp[DGE_CK_DEPTH + ck_cnt - 1]; }
+    else ck_cnt = 0;
   }
   const int c_new = (!valid && a.incremental && T - 3 > c_use) ? T - 3 : -1;   // position of the checkpoint this step leaves (-1: none)
+  // its storage: the first free physical slot, or (stack full) the oldest checkpoint's, which is dropped
+  const int ck_dst_slot = ckp[DGE_CK_DEPTH + (ck_cnt < DGE_CK_DEPTH ? ck_cnt : 0)];
+  const double *ck = a.ck_state + ((size_t)b * DGE_CK_DEPTH + ck_src_slot) * DGE_FC_WIDTH(Lt);      // resumed from (c_use > 0)
+  const double *ck_S = ck + 16 + 4 * N2C;
+  double *ckn = a.ck_state + ((size_t)b * DGE_CK_DEPTH + ck_dst_slot) * DGE_FC_WIDTH(Lt);           // saved to (c_new >= 0)
+  double *ckn_cB = ckn + 16, *ckn_gl = ckn_cB + 3 * N2C, *ckn_S = ckn_gl + N2C;
   const int k_lo = valid ? T - 2 : c_use;      // poses [k_lo, T-1) are closed in this step; pose T-1 stays open
   const int kz = valid ? T - 1 : c_use;        // poses whose factors are linearised in this step
   const bool append = valid || c_use > 0;      // border slots are kept and new landmarks appended (a rebuild from pose 0 renumbers them)
@@ -368,7 +377,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
       }
     }
     if (c_new >= 0 && ccol < N2C && !colv) {   // columns without a landmark yet: zero in the checkpoint (a later slot resumes from zeros)
-      ck_cB[3 * ccol] = 0.0; ck_cB[3 * ccol + 1] = 0.0; ck_cB[3 * ccol + 2] = 0.0; ck_gl[ccol] = 0.0;
+      ckn_cB[3 * ccol] = 0.0; ckn_cB[3 * ccol + 1] = 0.0; ckn_cB[3 * ccol + 2] = 0.0; ckn_gl[ccol] = 0.0;
     }
     for (int k0 = k_lo; k0 < T; k0 += CH) {
       const int kc = min(CH, T - k0);
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
         for (int kk = 0; kk < kc; ++kk) {
           double *w = stage + kk * SW;
           if ((k0 + kk == T - 1 || k0 + kk == c_new) && lane == 0) {   // the closed poses end here: the state the next step resumes from (/ the checkpoint)
-            double *sv = (k0 + kk == c_new) ? ck : fc;
+            double *sv = (k0 + kk == c_new) ? ckn : fc;
 #pragma unroll
             for (int i = 0; i < 6; ++i) sv[i] = cD[i];
 #pragma unroll
@@ -462,8 +471,8 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
                   fc_gl[c] = glc;
                 }
                 if (k == c_new) {   // checkpoint: carries into pose c_new; rhs without the factors at c_new and behind
-                  ck_cB[3 * c] = cB[0]; ck_cB[3 * c + 1] = cB[1]; ck_cB[3 * c + 2] = cB[2];
-                  ck_gl[c] = glc - glB;
+                  ckn_cB[3 * c] = cB[0]; ckn_cB[3 * c + 1] = cB[1]; ckn_cB[3 * c + 2] = cB[2];
+                  ckn_gl[c] = glc - glB;
                 }
                 const double b0 = nb[u][0] + cB[0], b1 = nb[u][1] + cB[1], b2 = nb[u][2] + cB[2];
                 if (kk + 4 < kc) {
@@ -687,7 +696,7 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
   } else if (c_new >= 0) {   // rebuild that leaves a checkpoint: the sum in front of c_new first, snapshot, then the rest
     schur(k_lo, c_new);
     __syncthreads();
-    for (int i = tid; i < N2C * ldS; i += NT) ck_S[i] = S[i];     // (every row: later slots must find zeros)
+    for (int i = tid; i < N2C * ldS; i += NT) ckn_S[i] = S[i];    // (every row: later slots must find zeros)
     __syncthreads();
     if (colv) { S[(2 * (ccol >> 1)) * ldS + ccol] += sdB0; S[(2 * (ccol >> 1) + 1) * ldS + ccol] += sdB1; }
     __syncthreads();
@@ -1002,8 +1011,21 @@ __global__ void __launch_bounds__(NT, 2) k_slam(SlamArgs a, const uint8_t *mask)
     a.metrics[8 * b + 5] = m;         // max_uncertainty_of_trajectory        exploration_env.py:190-194
     a.update_count[b] = uc;
     a.fc_valid[b] = s_bad ? 0 : T;
-    if (!valid) a.ck_pos[b] = s_bad ? 0 : (c_new >= 0 ? c_new : c_use);
-    else if (s_bad) a.ck_pos[b] = 0;
+    if (s_bad) ckp[2 * DGE_CK_DEPTH] = 0;
+    else if (!valid && a.incremental) {       // the stack after this rebuild: invalidated checkpoints popped, the new one pushed (oldest dropped when full)
+      int cnt = ck_cnt;
+      if (c_new >= 0) {
+        if (cnt == DGE_CK_DEPTH) {
+          const int freed = ckp[DGE_CK_DEPTH];
+          for (int i = 0; i + 1 < DGE_CK_DEPTH; ++i) { ckp[i] = ckp[i + 1]; ckp[DGE_CK_DEPTH + i] = ckp[DGE_CK_DEPTH + i + 1]; }
+          ckp[2 * DGE_CK_DEPTH - 1] = freed;
+          cnt = DGE_CK_DEPTH - 1;
+        }
+        ckp[cnt] = c_new;
+        ++cnt;
+      }
+      ckp[2 * DGE_CK_DEPTH] = cnt;
+    }
     if (a.clocks) { a.clocks[12 * b +6] = clock64(); a.clocks[12 * b +7] = T; a.clocks[12 * b + 10] = valid ? 1 : (c_use > 0 ? 2 : 0); a.clocks[12 * b + 11] = n2; }
     if (s_bad) a.status[b] = 1;
   }
