@@ -244,12 +244,16 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
     c0 = [int(v) for v in env.eng.state["counters"].tolist()[:3]]
     d0, t0, r0, k0 = tr.decisions, tr.train_steps, tr.rollout_steps, tr.rollout_clones
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect(); gc.freeze()          # the objects of the earlier legs of this process leave the collector's generations (the tick is host-bound)
+    ms0 = torch.cuda.memory_stats(env.device)
     a.record()
     t_host = time.perf_counter()
     for _ in range(steps):
         tr.tick(learn=True)
     t_host = time.perf_counter() - t_host
     b.record()
+    ms1 = torch.cuda.memory_stats(env.device)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -290,7 +294,8 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
                "decisions_per_s": dec / sec, "train_steps_per_s": tsteps / sec / world, "rollout_clone_steps_per_s": None,
                "gnn_samples_per_s": {"forward_acting": dec / sec, "forward_target": tsteps * bsz / sec, "forward_backward": tsteps * bsz / sec},
                "rollout": {"clones_per_s": clones / sec, "clone_engine_ticks_per_s": rsteps / sec}, "loss": tr.last_loss, "epsilon": tr.epsilon, "clocks": clocks,
-               "allreduce_us": ar_us, "host_issue_ms_per_tick": 1e3 * t_host / steps}
+               "allreduce_us": ar_us, "host_issue_ms_per_tick": 1e3 * t_host / steps,
+               "allocator": {k: ms1.get(k, 0) - ms0.get(k, 0) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries", "allocation.all.allocated")}}
     env.close()
     return out
 
@@ -707,7 +712,7 @@ def main():
             pass
         tr = measure_train(args, rank, world, local, dist, steps=100, warmup=10)
         if rank == 0:
-            out["train_c3"] = {k: tr[k] for k in ("value", "unit", "ms_per_step", "host_issue_ms_per_tick", "decisions_per_s", "train_steps_per_s", "allreduce_us", "loss")}
+            out["train_c3"] = {k: tr[k] for k in ("value", "unit", "ms_per_step", "host_issue_ms_per_tick", "decisions_per_s", "train_steps_per_s", "allreduce_us", "loss", "allocator")}
             out["train_c3"].update(workload=tr["config"]["workload"], schedule=tr["config"]["schedule"], collective=tr["config"]["collective"], ticks=100)
     if rank == 0:
         emit(out)

@@ -5,6 +5,6 @@ for v in "--no-e2e --no-gnn --no-c4 --no-cpu-baseline" "--no-e2e --no-c4 --no-cp
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('[$v] train_c3 ms/tick', round(d['train_c3']['ms_per_step'], 2), 'host issue', round(d['train_c3']['host_issue_ms_per_tick'], 2))
+        d = json.loads(l); print('[$v] train_c3 ms/tick', round(d['train_c3']['ms_per_step'], 2), 'host issue', round(d['train_c3']['host_issue_ms_per_tick'], 2), d['train_c3']['allocator'])
 "
 done
