@@ -223,7 +223,7 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
     cfg = EnvConfig(map_size=ms)
     if args.train_gemm in ("fp32", "tc3"):
         Networks.set_matmul_precision("tc3", train=args.train_gemm)
-    env = VecExplorationEnv(B, cfg=cfg, max_poses=384, device=local, seed0=rank * 100000)
+    env = VecExplorationEnv(B, cfg=cfg, max_poses=384, device=local, seed0=rank * B, seed_stride=world * B)
     env.reset()
     torch.manual_seed(0)                      # identical replicas on every rank
     pol, tgt = Networks.GCN().to(env.device), Networks.GCN().to(env.device)
@@ -477,14 +477,14 @@ def measure_c4_sweep(dev, n=1024, Ts=(32, 64, 128, 256, 512, 1024), reps=10):
 
 # ------------------------------------------------------------------------- GPU arm ---
 class GpuLoop:
-    def __init__(self, device, seed0, overlap=True, device_tick=True):
+    def __init__(self, device, seed0, overlap=True, device_tick=True, seed_stride=None):
         from drl_graph_exploration_b200 import Networks, gnn
         from drl_graph_exploration_b200.config import EnvConfig
         from drl_graph_exploration_b200.envs.exploration_env import VecExplorationEnv
 
         self.gnn = gnn
         cfg = EnvConfig(map_size=MAP_SIZE, num_landmarks=N_LANDMARKS)
-        self.env = VecExplorationEnv(ENVS_PER_GPU, cfg=cfg, max_poses=MAX_POSES, device=device, seed0=seed0)
+        self.env = VecExplorationEnv(ENVS_PER_GPU, cfg=cfg, max_poses=MAX_POSES, device=device, seed0=seed0, seed_stride=seed_stride)
         torch.manual_seed(0)
         self.model = Networks.GCN().to(self.env.device).eval()
         self.env.reset()
@@ -552,7 +552,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = local
     torch.cuda.set_device(device)
-    loop = GpuLoop(device, seed0=rank * 100000, overlap=not args.no_overlap, device_tick=not args.per_launch)
+    # env-sharded worlds: rank r owns seeds r B .. r B + B - 1 and walks them with stride W B (disjoint from every other rank's for ever)
+    loop = GpuLoop(device, seed0=rank * ENVS_PER_GPU, overlap=not args.no_overlap, device_tick=not args.per_launch, seed_stride=world * ENVS_PER_GPU)
     flush = None if args.no_flush_l2 else L2Flush(loop.dev)
 
     # untimed pre-roll, independent of --warmup: all envs were reset together, so the first ticks see T = 5..30 only.  Run until

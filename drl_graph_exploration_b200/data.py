@@ -15,7 +15,16 @@ class Data:
         return self.x.size(0)
 
     def to(self, device):
-        out = Data(*(None if t is None else t.to(device) for t in (self.x, self.edge_index, self.edge_attr, self.batch)))
+        """Like PyG's ``Data.to``; data that already lives on ``device`` is returned as it is (with the CSR / normalisation a
+        forward pass cached on it, ``_dge_structure``), so the target-net forward, the policy forward and its backward of one
+        gradient step share one preprocessing."""
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        ts = (self.x, self.edge_index, self.edge_attr, self.batch)
+        if all(t is None or (t.device.type == dev.type and (dev.index is None or t.device.index == dev.index)) for t in ts):
+            return self
+        out = type(self)(*(None if t is None else t.to(device) for t in ts))
+        if hasattr(self, "num_graphs"):
+            out.num_graphs = self.num_graphs
         return out
 
     def __repr__(self):

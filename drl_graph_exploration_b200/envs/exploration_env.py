@@ -104,7 +104,7 @@ class VecExplorationEnv:
     """B exploration environments resident on one B200."""
 
     def __init__(self, n_envs: int, map_size: int = 40, cfg: Optional[EnvConfig] = None, max_poses: int = 512, device=0,
-                 seed0: int = 0, test: bool = True):
+                 seed0: int = 0, test: bool = True, seed_stride: Optional[int] = None):
         self.cfg = cfg or EnvConfig(map_size=map_size)
         self.map_size = self.cfg.map_size
         self.eng = Engine(self.cfg, n_envs, max_poses=max_poses, device=device)
@@ -112,6 +112,9 @@ class VecExplorationEnv:
         self.test = test
         self.graph = GraphBatch(self.eng, n_envs)
         self._seeds = torch.arange(seed0, seed0 + n_envs, dtype=torch.int64, device=self.device)
+        # an env's next world = its seed + seed_stride.  One process: B.  Env-sharded over W ranks: seed0 = rank * B and seed_stride = W * B keep the
+        # ranks' world sequences disjoint for ever
+        self.seed_stride = int(seed_stride or n_envs)
         self._next_seed = seed0 + n_envs
         self._reset_odom = torch.tensor([RESET_ODOM] * n_envs, dtype=torch.float64, device=self.device)
         self._choice = torch.zeros(n_envs, dtype=torch.int32, device=self.device)
@@ -143,7 +146,7 @@ class VecExplorationEnv:
                     blind &= mask.bool()
                 if not bool(blind.any()):            # (one host sync per eager reset)
                     break
-                self._seeds = torch.where(blind, self._seeds + self.B, self._seeds)
+                self._seeds = torch.where(blind, self._seeds + self.seed_stride, self._seeds)
                 bm = blind.to(torch.uint8)
                 eng._L.dge_set_counting(eng._h, 0)
                 eng.reset(self._seeds, mask=bm)
@@ -158,7 +161,7 @@ class VecExplorationEnv:
         steps are executed by the next 5 ``step_queued`` ticks together with the other envs' steps (same
         per-env operation sequence and Philox draws as the eager reset, one launch instead of 21)."""
         done = self.eng.state["done"].clone()
-        self._seeds = torch.where(done.bool(), self._seeds + self.B, self._seeds)
+        self._seeds = torch.where(done.bool(), self._seeds + self.seed_stride, self._seeds)
         if in_pipeline:
             self.eng.reset_queued(self._seeds, done, RESET_ODOM, 4)
         else:

@@ -83,7 +83,7 @@ class PolicyLoop:
         from . import Networks, gnn
         self.env, self.model, self.overlap = env, model, overlap
         self.dev = env.device
-        self.seed_stride = int(seed_stride or env.B)
+        self.seed_stride = int(seed_stride or getattr(env, "seed_stride", env.B))
         self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
         self.s_step = torch.cuda.Stream(self.dev) if overlap else None
         self.ev_need = torch.cuda.Event()
@@ -320,7 +320,7 @@ class HostPolicyLoop:
         self.phase = np.zeros(B, dtype=np.int64)       # ticks of reset work (initial optimize + forced steps) still to run
         self.s_step = torch.cuda.Stream(self.dev) if overlap else None
         self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
-        self.seed_stride = B
+        self.seed_stride = int(getattr(env, "seed_stride", B))
         self.steps = 0                                  # policy env-steps executed
         self.h2d = self.d2h = 0                         # bytes moved
         self.launches = 0

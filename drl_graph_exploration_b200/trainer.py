@@ -51,6 +51,7 @@ class VecDQNTrainer:
         from .dist import NativeAdam
         native = gnn.QForwardPlan.eligible(policy_net)
         self.optimizer = NativeAdam(policy_net.parameters(), lr=lr) if native else torch.optim.Adam(policy_net.parameters(), lr=lr)
+        self._sync_replicas()                # rank 0's weights everywhere: the replicas must not depend on every caller seeding alike
         self.target_net.load_state_dict(policy_net.state_dict())
         self.target_net.eval()
         self.train_steps_per_tick = int(train_steps_per_tick)
@@ -90,7 +91,7 @@ class VecDQNTrainer:
         self.ecap_episodes = self.ecap_episodes + ecap_prev.sum()
         need = env.mark_pending().bool().clone()       # empty queue, not done, not in the reset phase
         # ---- step pipeline: restart finished episodes, one simulator step for every env with a queued action ----
-        _check(eng._L.dge_reset_done_queued(eng._h, env.B, self._fo, 4, _stream_ptr(dev)), "dge_reset_done_queued")
+        _check(eng._L.dge_reset_done_queued(eng._h, env.seed_stride, self._fo, 4, _stream_ptr(dev)), "dge_reset_done_queued")
         eng.step_queued()
         # ---- transitions that ended with the episode: terminal, s_t1 is not used by the target (policy.py:166-167) ----
         ended = done_prev & (self.pend_slot >= 0) & ~ecap_prev      # a capacity stop drops its in-flight transition instead of storing y = r
@@ -210,6 +211,15 @@ class VecDQNTrainer:
                 self.learn()
         return ng
 
+    def _sync_replicas(self):
+        """Broadcast the policy net's parameters and buffers from rank 0 (no-op on one rank).  Gradients are all-reduced every step, so
+        replicas that start equal stay equal; this makes them start equal whatever the ranks' seeds or checkpoint files are."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            with torch.no_grad():
+                for t in list(self.policy_net.parameters()) + list(self.policy_net.buffers()):
+                    dist.broadcast(t.data, src=0)
+
     def _learning_started(self) -> bool:
         """policy.py:136: learning starts once OBSERVE decisions have passed (and, here, one minibatch of transitions exists).
         Both counts are rank-local, and a rank that started alone would sit in the gradient all-reduce of ``DeepQ.train``
@@ -292,12 +302,14 @@ class VecDQNTrainer:
             self.replay.load_state_dict(ck["replay"])
         self.pend_slot.fill_(-1)              # in-flight transitions belonged to the episodes of the old process
         self._learning = False                # re-agreed on by the ranks of the new process group
+        self._sync_replicas()
 
     def load(self, path: str):
         """Resume from a ``MyModel.pt`` / ``Model_Policy.pt`` state dict (the reference's or ours)."""
         sd = torch.load(path, map_location=self.dev)
         self.policy_net.load_state_dict(sd)
-        self.target_net.load_state_dict(sd)
+        self._sync_replicas()
+        self.target_net.load_state_dict(self.policy_net.state_dict())
 
 
 def dqn_targets(q1, batch1, a, r, term, off_s, n_s1, off_s1, fro1, n_nodes_s: int, gamma: float):
@@ -365,7 +377,7 @@ class VecA2CTrainer:
         done_prev = st["done"].bool().clone()
         need = env.mark_pending().bool().clone()
         need_u8 = need.to(torch.uint8)
-        _check(eng._L.dge_reset_done_queued(eng._h, B, self._fo, 4, _stream_ptr(dev)), "dge_reset_done_queued")
+        _check(eng._L.dge_reset_done_queued(eng._h, env.seed_stride, self._fo, 4, _stream_ptr(dev)), "dge_reset_done_queued")
         eng.step_queued()
         ended = done_prev & (self.pend_slot >= 0)
         g = env.build_graph(need_u8)
