@@ -219,9 +219,14 @@ class GCN(torch.nn.Module):
 
     def _trunk(self, data, p):
         x = data.x
+        native_q = (self._out == 1 and not torch.is_grad_enabled() and (p == 0 or p == 0.0) and _PRECISION == "tc3" and x.is_cuda and x.size(1) <= 8
+                    and self.conv2.out_channels % 4 == 0 and self.conv2.out_channels <= 1024)
+        if native_q and getattr(data, "_dge_structure", None) is None:
+            # inference on a batch that arrives as a raw edge list (DeepQ.test): CSRs + normalisation + forward in ONE native call
+            return gnn.gcn_q_forward_coo(x, data.edge_index, data.edge_attr, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                                         self.fully_con1.weight[0], self.fully_con1.bias).view(-1, 1)
         gs = _structure(data, x.size(0))
-        if (self._out == 1 and not torch.is_grad_enabled() and (p == 0 or p == 0.0) and _PRECISION == "tc3" and x.is_cuda and x.size(1) <= 8
-                and self.conv2.out_channels % 4 == 0 and self.conv2.out_channels <= 1024):
+        if native_q:
             # inference: the whole Q-network in one native call (three launches)
             return gnn.gcn_q_forward(x, gs, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
                                      self.fully_con1.weight[0], self.fully_con1.bias).view(-1, 1)

@@ -507,6 +507,30 @@ extern "C" int dge_gcn_q_forward(int N, int Cin, int C, const float *x, const in
                                static_cast<cudaStream_t>(stream));
 }
 
+// The same forward from a raw PyG edge list, in ONE call: destination- and source-sorted CSR (dge_gnn_csr_build x 2), the improved-GCN
+// normalisation (dge_gcn_norm) and dge_gcn_q_forward -- what Networks.GCN.forward(data, 0) does for a batch that arrives as
+// (x, edge_index, edge_attr) (DeepQ.test, policy.py:255-259), without four round trips through the caller's language.
+// iws: 4 * (N + 1) + 2 * E + 2 * (2 * N + E) int32 scratch; fws: 3 * N + E + 3 * N * C floats (16-byte aligned).
+extern "C" int64_t dge_gcn_q_forward_coo_iws(int N, int E) { return 4 * ((int64_t)N + 1) + 2 * (int64_t)E + 2 * (2 * (int64_t)N + E) + 8; }
+extern "C" int64_t dge_gcn_q_forward_coo_fws(int N, int E, int C) { return 4 * (((int64_t)N + 3) & ~3) + (((int64_t)E + 3) & ~3) + 3 * (int64_t)N * C + 8; }
+extern "C" int dge_gcn_q_forward_coo(int N, int E, int Cin, int C, const float *x, const int64_t *src, const int64_t *dst, const float *w,
+                                     const float *W1, const float *b1, const float *W2t_hi, const float *W2t_lo, const float *b2, const float *head_w,
+                                     const float *head_b_dev, int32_t *iws, float *fws, float *q, void *stream) {
+  if (N <= 0 || E < 0 || !x || (E > 0 && (!src || !dst || !w)) || !iws || !fws || !q || ((uintptr_t)fws & 15)) return -1;
+  int32_t *rowptr_d = iws, *rowptr_s = rowptr_d + (N + 1), *perm_d = rowptr_s + (N + 1), *perm_s = perm_d + (E > 0 ? E : 1), *ws_d = perm_s + (E > 0 ? E : 1),
+          *ws_s = ws_d + (2 * (size_t)N + E);
+  const size_t Np = ((size_t)N + 3) & ~(size_t)3, Ep = ((size_t)E + 3) & ~(size_t)3;
+  float *dis = fws, *selfw = dis + Np, *selfnorm = selfw + Np, *norm = selfnorm + Np, *ws = norm + Ep + Np;   // (one spare Np block keeps ws 16-byte aligned)
+  int rc = dge_gnn_csr_build(N, E, dst, rowptr_d, perm_d, ws_d, stream);
+  if (rc) return rc;
+  rc = dge_gnn_csr_build(N, E, src, rowptr_s, perm_s, ws_s, stream);
+  if (rc) return rc;
+  rc = dge_gcn_norm(N, E, src, dst, w, rowptr_s, perm_s, 2.0f, dis, selfw, norm, selfnorm, stream);
+  if (rc) return rc;
+  return dge_gcn_q_forward_dev(N, nullptr, Cin, C, x, rowptr_d, perm_d, src, norm, selfnorm, W1, b1, W2t_hi, W2t_lo, b2, head_w, head_b_dev, ws, q,
+                               static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------ GRU cell gates (GG-NN) ---------------------
 // torch.nn.GRUCell after its two dense transforms (GatedGraphConv.forward -> self.rnn(m, h), Networks.py:73-86 via PyG):
 //   r = sigmoid(gi_r + b_ir + gh_r + b_hr),  z = sigmoid(gi_z + b_iz + gh_z + b_hz),

@@ -440,6 +440,47 @@ def gcn_q_forward(x: torch.Tensor, gs: GraphStructure, w1: torch.Tensor, b1, w2:
     return q
 
 
+_coo_ws: dict = {}
+
+
+def gcn_q_forward_coo(x: torch.Tensor, edge_index: torch.Tensor, edge_attr: torch.Tensor, w1: torch.Tensor, b1, w2: torch.Tensor, b2, head_w: torch.Tensor,
+                      head_b: torch.Tensor):
+    """``Networks.GCN.forward(data, 0)`` for a batch that arrives as a raw edge list: CSR builds, normalisation and the three forward
+    launches in ONE native call (``dge_gcn_q_forward_coo``) on grow-only scratch -- one ctypes round trip and one ``torch.empty`` (q) per pass
+    instead of four calls and a dozen allocations.  Returns q [N]."""
+    global launch_count
+    _need_cuda(x, "gcn_q_forward_coo")
+    L = _gemm_lib()
+    if not hasattr(L, "_coo_ready"):
+        L.dge_gcn_q_forward_coo_iws.restype = ctypes.c_int64
+        L.dge_gcn_q_forward_coo_iws.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.dge_gcn_q_forward_coo_fws.restype = ctypes.c_int64
+        L.dge_gcn_q_forward_coo_fws.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.dge_gcn_q_forward_coo.argtypes = [ctypes.c_int] * 4 + [_vp] * 15
+        L._coo_ready = True
+    x = x.contiguous().float()
+    N, cin = x.shape
+    C = w1.shape[1]
+    ei = edge_index if edge_index.dtype == torch.int64 else edge_index.long()
+    E = int(ei.shape[1])
+    src, dst = ei[0].contiguous(), ei[1].contiguous()
+    ew = (torch.ones(E, device=x.device) if edge_attr is None else edge_attr.contiguous().float())
+    margs, keep = _q_forward_model_args(w1, b1, w2, b2, head_w, head_b)
+    dev = x.device
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ni, nf = int(L.dge_gcn_q_forward_coo_iws(N, E)), int(L.dge_gcn_q_forward_coo_fws(N, E, C))
+    ws = _coo_ws.get(key)
+    if ws is None or ws[0].numel() < ni or ws[1].numel() < nf:
+        ws = _coo_ws[key] = (torch.empty(max(ni, 1 << 20), dtype=torch.int32, device=dev), torch.empty(max(nf, 1 << 22), dtype=torch.float32, device=dev))
+    q = torch.empty(N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.dge_gcn_q_forward_coo(N, E, cin, C, _p(x), _p(src), _p(dst), _p(ew), *margs, _p(ws[0]), _p(ws[1]), _p(q), _st(dev))
+    if rc:
+        raise DgeError(f"dge_gcn_q_forward_coo failed ({rc})")
+    launch_count += 16
+    return q
+
+
 class QForwardPlan:
     """``gcn_q_forward`` for the acting loop with its argument list prepared once.  Between two ticks of ``runner.PolicyLoop``
     every pointer of the call is the same -- the weights (inference) and the engine-owned graph batch buffers (x, destination

@@ -59,6 +59,16 @@ int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi
 int dge_gemm_tf32x3_ex(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, int lda, const float *Bt_hi,
                        const float *Bt_lo, int ldb, float *C, int ldc, int splits, void *stream);
 
+/* ---- Q-values of the GCN Q-network (Networks.GCN.forward(data, 0): scripts/Networks.py:18-28, called by DeepQ.test, policy.py:255-259) from a raw
+ * PyG edge list in one call: both CSRs, the improved-GCN normalisation, fused first layer, tcgen05 GEMM, aggregation + ReLU + head.  src / dst =
+ * edge_index rows [E] int64, w = edge_attr [E]; W2t_(hi,lo) = dge_gemm_prep_weight(W2); head_b_dev [1] on the device.  iws / fws: scratch of
+ * dge_gcn_q_forward_coo_iws(N, E) int32 / dge_gcn_q_forward_coo_fws(N, E, C) floats (fws 16-byte aligned).  q [N].                          */
+int64_t dge_gcn_q_forward_coo_iws(int N, int E);
+int64_t dge_gcn_q_forward_coo_fws(int N, int E, int C);
+int dge_gcn_q_forward_coo(int N, int E, int Cin, int C, const float *x, const int64_t *src, const int64_t *dst, const float *w,
+                          const float *W1, const float *b1, const float *W2t_hi, const float *W2t_lo, const float *b2, const float *head_w,
+                          const float *head_b_dev, int32_t *iws, float *fws, float *q, void *stream);
+
 /* ---- one DQN training step of the GCN Q-network without autograd (csrc/dge_train.cu).  Replaces DeepQ.train + DeepQ.cost
  * (scripts/policy.py:234-253: model(data, 0.5) -> sum((Q a - y)^2) / BATCH -> backward) for scripts/Networks.py:12-28:
  * forward with functional dropout drop_p (Philox stream keyed by drop_seed), cost, and the gradients of all six parameters.

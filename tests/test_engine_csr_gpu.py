@@ -38,12 +38,17 @@ def _run(env, model, Data):
             env.reset_done()
         if ng:
             d_fast = g.data()
+            from drl_graph_exploration_b200 import Networks
             d_ref = Data(d_fast.x.clone(), d_fast.edge_index.clone(), d_fast.edge_attr.clone())
+            Networks._structure(d_ref, d_ref.x.size(0))        # the generic preprocessing (CSR builds + normalisation kernels), cached on the data
+            d_coo = Data(d_fast.x.clone(), d_fast.edge_index.clone(), d_fast.edge_attr.clone())   # a raw edge list: the single-call route
             with torch.no_grad():
                 q_fast = model(d_fast, 0.0)
                 q_ref = model(d_ref, 0.0)
+                q_coo = model(d_coo, 0.0)
                 with torch.enable_grad():
                     q_unfused = model(Data(d_fast.x.clone(), d_fast.edge_index.clone(), d_fast.edge_attr.clone()), 0.0).detach()
+            assert getattr(d_coo, "_dge_structure", None) is None and torch.equal(q_coo, q_ref)      # same kernels, same order: identical
             gs_f, gs_r = d_fast._dge_structure, d_ref._dge_structure
             assert torch.equal(gs_f.rowptr_dst, gs_r.rowptr_dst) and torch.equal(gs_f.perm_dst[:e], gs_r.perm_dst[:e])
             nf, sf = gs_f.gcn_norm(True); nr, sr = gs_r.gcn_norm(True)
