@@ -19,6 +19,7 @@
 // Operands are K-major ([rows, K] with K contiguous): A = activations, B^T = the weight stored [out, in].
 // The row count can be read from device memory (M_dev) so that a graph batch whose size is only known on the
 // device needs no host synchronisation: the tile loop is bounded by the live rows, surplus CTAs exit immediately.
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
@@ -28,17 +29,24 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;       // BK fp32 = 128 bytes = one SWIZZLE_128B row
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 4;          // 16 KB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // Ah, Al, Bh, Bl
+constexpr int BM = 128, BK = 32;                 // BK fp32 = 128 bytes = one SWIZZLE_128B row
+// Output tile BM x BN_.  BN_ = 128: 64 KB per stage (Ah, Al, Bh, Bl tiles of 16 KB), 3 stages, two 128-column accumulators in tensor memory.
+// BN_ = 256 (wide): the A tiles are reused over twice the columns -- 96 KB per stage for twice the MMAs, i.e. 0.75x the shared-memory fill
+// traffic per flop (the 3xTF32 product is fed from L2 at ~24 MAC per byte: the fill rate, not the tensor pipe, is what bounds it) -- 2 stages,
+// two 256-column accumulators = all 512 columns of tensor memory.
+constexpr int A_TILE_BYTES = BM * BK * 4;        // 16 KB
+template <int BN_> struct Shape {
+  static constexpr int STAGES = BN_ == 256 ? 2 : 3;
+  static constexpr int B_TILE_BYTES = BN_ * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN_;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+  // instruction descriptor (cute::UMMA::InstrDescriptor layout): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 constexpr int GEMM_THREADS = 192;
-constexpr int TMEM_COLS = 256;                   // 128 lanes x 2 x 128 fp32 columns = two 128x128 accumulators (double buffer)
 constexpr int UMMA_K = 8;                        // tf32: 32 bytes of K per instruction
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
 
-// instruction descriptor (cute::UMMA::InstrDescriptor layout): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -70,7 +78,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t IDESC) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
@@ -100,12 +108,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // (column tile fastest, so neighbouring CTAs share an A row block through L2).  The accumulator is double-buffered in tensor
 // memory (2 x 128 columns): the epilogue of tile i drains buffer i & 1 while the MMAs of tile i + 1 fill the other one, and the
 // TMA ring runs ahead across tile boundaries.  The live row count is read from device memory when M_dev is given.
+template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
               const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
               float *__restrict__ C, int M, const int32_t *__restrict__ M_dev, int N, int K, int ldc, int splits) {
   // splits > 1 (weight-gradient shape: few output tiles, a long K): work item = (tile, K slice); the slices of a tile add their
   // partial products into C with vector atomics (C zeroed by the caller; with two slices the sum is order-independent)
+  constexpr int STAGES = Shape<BN>::STAGES, STAGE_BYTES = Shape<BN>::STAGE_BYTES, TMEM_COLS = Shape<BN>::TMEM_COLS;
+  constexpr int TILE_BYTES = A_TILE_BYTES, B_TILE = Shape<BN>::B_TILE_BYTES;
+  constexpr uint32_t IDESC = Shape<BN>::IDESC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = M_dev ? min(M, *M_dev) : M;
   const int n_tiles = (N + BN - 1) / BN;
@@ -148,7 +160,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
           tma_load_2d(st, &mAh, fb, kb * BK, m0);
           tma_load_2d(st + TILE_BYTES, &mAl, fb, kb * BK, m0);
           tma_load_2d(st + 2 * TILE_BYTES, &mBh, fb, kb * BK, n0);
-          tma_load_2d(st + 3 * TILE_BYTES, &mBl, fb, kb * BK, n0);
+          tma_load_2d(st + 2 * TILE_BYTES + B_TILE, &mBl, fb, kb * BK, n0);
         }
       }
     }
@@ -170,10 +182,10 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint32_t off = k * UMMA_K * 4;           // 32 bytes along K inside the swizzled 128-byte row
             const uint64_t ah = smem_desc(st + off), al = smem_desc(st + TILE_BYTES + off);
-            const uint64_t bh = smem_desc(st + 2 * TILE_BYTES + off), bl = smem_desc(st + 3 * TILE_BYTES + off);
-            umma_tf32(td, al, bh, (kb != kb0 || k) ? 1u : 0u);     // small terms first
-            umma_tf32(td, ah, bl, 1u);
-            umma_tf32(td, ah, bh, 1u);
+            const uint64_t bh = smem_desc(st + 2 * TILE_BYTES + off), bl = smem_desc(st + 2 * TILE_BYTES + B_TILE + off);
+            umma_tf32(td, al, bh, (kb != kb0 || k) ? 1u : 0u, IDESC);     // small terms first
+            umma_tf32(td, ah, bl, 1u, IDESC);
+            umma_tf32(td, ah, bh, 1u, IDESC);
           }
           umma_commit(empty0 + 8 * s);                     // stage free once these MMAs have read it
         }
@@ -276,12 +288,12 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 // [rows, K] fp32 row-major, box = 128 rows x 32 columns (128 bytes), 128-byte swizzle, out-of-bounds reads give 0
-bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t K, uint64_t pitch = 0) {
+bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t K, uint64_t pitch = 0, uint32_t box_rows = BM) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
   if (!enc) return false;
   const cuuint64_t dims[2] = {K, rows};
   const cuuint64_t strides[1] = {(pitch ? pitch : K) * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -315,19 +327,26 @@ extern "C" int dge_gemm_tf32x3_ex(int M, const int32_t *M_dev, int N, int K, con
   if ((lda & 3) || (ldb & 3) || lda < K || ldb < K) return -1;
   if (((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)Bt_hi | (uintptr_t)Bt_lo | (uintptr_t)C) & 15) return -1;
   if (M == 0) return 0;
-  CUtensorMap mAh, mAl, mBh, mBl;
-  if (!make_map(&mAh, A_hi, M, K, lda) || !make_map(&mAl, A_lo, M, K, lda) || !make_map(&mBh, Bt_hi, N, K, ldb) || !make_map(&mBl, Bt_lo, N, K, ldb)) return -2;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM) != cudaSuccess) return -2;
-    configured = true;
-  }
+  // tile width: 128 columns; the 256-column shape (DGE_GEMM_BN=256, A/B) measured the same (158 us vs 160 us at M = 16384, N = K = 1000):
+  // the kernel already runs each of its three products at the rate of the library's single-pass TF32 GEMM (55 us for one product)
+  static const int forced_bn = [] { const char *v = getenv("DGE_GEMM_BN"); return v ? atoi(v) : 0; }();
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
   }
-  const long long tiles_cap = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const long long m_tiles = (M + BM - 1) / BM;
+  const int bn = (forced_bn == 256 && !M_dev) ? 256 : 128;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if (!make_map(&mAh, A_hi, M, K, lda) || !make_map(&mAl, A_lo, M, K, lda) || !make_map(&mBh, Bt_hi, N, K, ldb, bn) || !make_map(&mBl, Bt_lo, N, K, ldb, bn)) return -2;
+  static bool configured[2] = {false, false};
+  if (!configured[bn == 256]) {
+    const cudaError_t ce = bn == 256 ? cudaFuncSetAttribute(k_gemm_tf32x3<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<256>::SMEM)
+                                     : cudaFuncSetAttribute(k_gemm_tf32x3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<128>::SMEM);
+    if (ce != cudaSuccess) return -2;
+    configured[bn == 256] = true;
+  }
+  const long long tiles_cap = (long long)((N + bn - 1) / bn) * m_tiles;
   const int num_kb = (K + BK - 1) / BK;
   if (splits <= 0) {
     splits = 1;
@@ -336,7 +355,10 @@ extern "C" int dge_gemm_tf32x3_ex(int M, const int32_t *M_dev, int N, int K, con
   if (splits > num_kb) splits = num_kb;
   const long long work = tiles_cap * splits;
   const unsigned grid = (unsigned)(work < n_sm ? work : n_sm);
-  k_gemm_tf32x3<<<grid, GEMM_THREADS, GEMM_SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc, splits);
+  if (bn == 256)
+    k_gemm_tf32x3<256><<<grid, GEMM_THREADS, Shape<256>::SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc, splits);
+  else
+    k_gemm_tf32x3<128><<<grid, GEMM_THREADS, Shape<128>::SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc, splits);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
