@@ -50,6 +50,7 @@ class _Env:
 
     def __init__(self, B, seed=0):
         self.B, self.device = B, torch.device("cpu")
+        self.seed_stride = B                  # (VecExplorationEnv: an env's next world = its seed + seed_stride)
         self.rng = np.random.default_rng(seed)
         self.queue = np.zeros(B, dtype=np.int64)
         self.done = torch.zeros(B, dtype=torch.uint8)
