@@ -402,6 +402,60 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res[name] = (float(t.item()) / 1e3, gnn.launch_count - l0)
+    # ---- the other two families of Networks.py on the same batches ("GCN (primary), GG-NN, g-U-Net; forward and
+    # forward+backward"): module forward at inference, and forward (dropout 0.5) + backward + gradient all-reduce + clamp + Adam under
+    # autograd with the dense products, the GRU cell and the aggregations on this package's kernels (Networks.set_matmul_precision 'tc3')
+    fam = {}
+    if not getattr(args, "no_families", False):
+        from drl_graph_exploration_b200.dist import FlatGradBucket as _Bucket
+        if args.train_gemm in ("fp32", "tc3"):
+            Networks.set_matmul_precision("tc3", train=args.train_gemm)
+        for fname, make in (("GGNN", lambda: Networks.GGNN()), ("GraphUNet", lambda: Networks.GraphUNet(5, 1000, 1000, depth=3))):
+            torch.manual_seed(0)
+            net = make().to(dev)
+            f_opt = torch.optim.Adam(net.parameters(), lr=1e-5)
+            f_bucket = _Bucket(net.parameters())
+
+            def f_fwd(i, net=net):
+                x, ei, w, bt = batches[i % nb]
+                with torch.no_grad():
+                    return net(Data(x, ei, w, bt), 0.0, batch=bt)
+
+            def f_fwd_bwd(i, net=net, f_opt=f_opt, f_bucket=f_bucket):
+                x, ei, w, bt = batches[i % nb]
+                f_bucket.zero_()
+                q = net(Data(x, ei, w, bt), 0.5, batch=bt)
+                ((q.view(-1) ** 2).sum() / G).backward()
+                f_bucket.all_reduce_mean(); f_bucket.clamp_(0.5)
+                f_opt.step()
+
+            k = max(3, min(n_steps, 10))
+            row = {}
+            for name, fn in (("forward", f_fwd), ("forward_backward", f_fwd_bwd)):
+                net.eval() if name == "forward" else net.train()
+                for i in range(3):
+                    fn(i)
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                evs, l0 = [], gnn.launch_count
+                for i in range(k):
+                    if flush is not None:
+                        flush()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); fn(i); b.record(); evs.append((a, b))
+                torch.cuda.synchronize()
+                t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sec = float(t.item()) / 1e3
+                row[name + "_graphs_per_s"] = world * G * k / sec
+                row[name + "_ms_per_batch"] = 1e3 * sec / k
+                row[name + "_launches_per_batch"] = (gnn.launch_count - l0) / k
+            row["steps"] = k
+            fam[fname] = row
+            del net, f_opt, f_bucket
+        torch.cuda.empty_cache()
     if rank == 0:
         pk, pk_kind = peaks()
         sec_f, sec_b = res["forward"][0], res["forward_backward"][0]
@@ -421,6 +475,7 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
                             "frac": gemm_flops * n_steps / sec_f / 1e12 / pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1.0)),
                             "note": "whole forward pass time in the denominator (GEMM + 2 aggregations + head), fp32-equivalent flops; the kernel alone: profiles/r01_k_gemm_tf32x3_ncu.md",
                             "traffic": None}}
+        out["families"] = fam
         # the same two legs on the host cores (the PyG restatement of the oracle, bounded sample): the "vs CPU ref" half of the metric
         out["cpu_baseline"] = None
         if world == 1 and not args.no_cpu_baseline:
@@ -521,6 +576,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gnn", action="store_true", help="skip the C5 GNN samples/sec measurement appended to the default line")
+    ap.add_argument("--no-families", action="store_true", help="GNN leg: skip the GG-NN / g-U-Net rows (C5's other two families)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 covariance-propagation roofline sweep appended to the default line (N = 1)")
     ap.add_argument("--no-train", action="store_true", help="skip the C3 DQN-training measurement appended to the default line")
     ap.add_argument("--no-overlap", action="store_true", help="run the step and policy pipelines on one stream (A/B of the overlap)")
@@ -698,7 +754,7 @@ def main():
                              "forward_graphs_per_s": g["forward"]["graphs_per_s"], "forward_ms_per_batch": g["forward"]["ms_per_batch"],
                              "forward_backward_graphs_per_s": g["forward_backward"]["graphs_per_s"],
                              "forward_backward_ms_per_batch": g["forward_backward"]["ms_per_batch"], "train_gemm": args.train_gemm,
-                             "tensor_roofline": g["roofline"], "cpu_baseline": g.get("cpu_baseline")}
+                             "tensor_roofline": g["roofline"], "cpu_baseline": g.get("cpu_baseline"), "families": g.get("families")}
     if not args.no_c4 and world == 1:
         try:
             loop.env.close()

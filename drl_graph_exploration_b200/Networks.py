@@ -21,16 +21,18 @@ import torch.nn.functional as F
 from . import gnn
 
 _PRECISION = "tc3"        # inference (autograd off)
-_PRECISION_TRAIN = "fp32"  # under autograd
+_PRECISION_TRAIN = "tc3"   # under autograd
 
 
 def set_matmul_precision(mode: str, train: str | None = None):
     """Dense node-MLP GEMMs.  ``mode`` (inference, autograd off): 'tc3' (default) = hand-written tcgen05 kernel, 3xTF32
     split, fp32 accumulation in tensor memory -- ~1e-6 of sum|a||w| per product, Q-values within ~1e-5 of fp64 (contract
     1e-4); 'fp32' = library SGEMM (A/B reference); 'tf32' / 'bf16' = library single-pass tensor-core modes (do not meet
-    the contract).  ``train`` (under autograd; default 'fp32'): 'tc3' runs forward and grad-input on the tcgen05 kernel
-    too (3.5x faster); it is opt-in because the ~1e-6 product error shows up as ~1e-3 of the largest gradient entry
-    after the cancellation in the weight-gradient sums, above the 2e-4 gradient parity the tests hold for fp32."""
+    the contract).  ``train`` (under autograd; default 'tc3' too): forward, grad-input and grad-weight (x^T dy, contracted
+    over the nodes with split-K) of every family's dense layers run on the tcgen05 kernel, the GG-NN's GRU cell on
+    ``gnn.gru_cell_train``; 'fp32' = library SGEMM + torch GRUCell (A/B reference).  The products agree with fp64 to ~1e-6
+    of sum|a||b|; what differs between ANY two fp32-grade implementations is on which side of a ReLU kink a pre-activation
+    within that error of zero falls (tests/test_native_train_gpu.py compares kink by kink)."""
     global _PRECISION, _PRECISION_TRAIN
     assert mode in ("tc3", "fp32", "tf32", "bf16") and train in (None, "tc3", "fp32", "tf32", "bf16")
     _PRECISION = mode
@@ -103,11 +105,14 @@ class GatedGraphConv(torch.nn.Module):
 
     def forward(self, x, gs: gnn.GraphStructure):
         h = x if x.size(1) == self.out_channels else torch.cat([x, x.new_zeros(x.size(0), self.out_channels - x.size(1))], dim=1)
-        native = (not torch.is_grad_enabled() and _PRECISION == "tc3" and h.is_cuda and self.out_channels % 4 == 0 and self.rnn.bias)
+        ok = h.is_cuda and self.out_channels % 4 == 0 and self.rnn.bias
+        native = ok and not torch.is_grad_enabled() and _PRECISION == "tc3"
+        native_train = ok and torch.is_grad_enabled() and _PRECISION_TRAIN == "tc3"
         for i in range(self.num_layers):
             m = gnn.weighted_aggregate(_mm(h, self.weight[i]), gs)
-            # inference: the GRU's two transforms on the tcgen05 GEMM + one gate kernel; under autograd: torch's GRUCell
-            h = gnn.gru_cell_inference(m, h, self.rnn) if native else self.rnn(m, h)
+            # the GRU's two transforms on the tcgen05 GEMM + one gate kernel; under autograd the same with their backward
+            # (gnn.gru_cell_train); torch's GRUCell only in the 'fp32' A/B mode
+            h = gnn.gru_cell_inference(m, h, self.rnn) if native else (gnn.gru_cell_train(m, h, self.rnn) if native_train else self.rnn(m, h))
         return h
 
 

@@ -580,6 +580,92 @@ extern "C" int dge_gru_gates(int N, int C, const float *gi, const float *gh, con
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+// ---- backward of the cell: gates recomputed from the saved forward inputs (gi, gh, biases, h), one pass, 8C floats in / 7C out per node
+namespace {
+__global__ void __launch_bounds__(256) k_gru_gates_bwd(int64_t n4, int C4, const float4 *__restrict__ gi, const float4 *__restrict__ gh,
+                                                       const float4 *__restrict__ b_ih, const float4 *__restrict__ b_hh, const float4 *__restrict__ h,
+                                                       const float4 *__restrict__ gout, float4 *__restrict__ dgi, float4 *__restrict__ dgh,
+                                                       float4 *__restrict__ dh) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int64_t row = i / C4;
+  const int c = (int)(i - row * C4);
+  const int64_t g0 = row * 3 * C4 + c;
+  const float4 ir = gi[g0], iz = gi[g0 + C4], in_ = gi[g0 + 2 * C4];
+  const float4 hr = gh[g0], hz = gh[g0 + C4], hn = gh[g0 + 2 * C4];
+  const float4 bir = b_ih[c], biz = b_ih[C4 + c], bin = b_ih[2 * C4 + c];
+  const float4 bhr = b_hh[c], bhz = b_hh[C4 + c], bhn = b_hh[2 * C4 + c];
+  const float4 hv = h[i], g = gout[i];
+  float ar, az, an, anr, dhd;
+  auto cell = [&](float ir_, float iz_, float in2, float hr_, float hz_, float hn_, float b0, float b1, float b2, float c0, float c1, float c2, float hp,
+                  float go) {
+    const float r = sigmoidf_((ir_ + b0) + (hr_ + c0));
+    const float z = sigmoidf_((iz_ + b1) + (hz_ + c1));
+    const float q = hn_ + c2;
+    const float n = tanhf((in2 + b2) + r * q);
+    an = go * (1.0f - z) * (1.0f - n * n);
+    ar = an * q * r * (1.0f - r);
+    az = go * (hp - n) * z * (1.0f - z);
+    anr = an * r;
+    dhd = go * z;
+  };
+  float4 o_r, o_z, o_n, o_nr, o_h;
+#define DGE_GRU_LANE(L)                                                                                                  \
+  cell(ir.L, iz.L, in_.L, hr.L, hz.L, hn.L, bir.L, biz.L, bin.L, bhr.L, bhz.L, bhn.L, hv.L, g.L);                          \
+  o_r.L = ar; o_z.L = az; o_n.L = an; o_nr.L = anr; o_h.L = dhd;
+  DGE_GRU_LANE(x) DGE_GRU_LANE(y) DGE_GRU_LANE(z) DGE_GRU_LANE(w)
+#undef DGE_GRU_LANE
+  dgi[g0] = o_r; dgi[g0 + C4] = o_z; dgi[g0 + 2 * C4] = o_n;
+  dgh[g0] = o_r; dgh[g0 + C4] = o_z; dgh[g0 + 2 * C4] = o_nr;
+  dh[i] = o_h;
+}
+
+// ---- deterministic column sums: slab s adds rows [s * rows, (s + 1) * rows) of its columns, a second launch adds the slabs in order
+constexpr int CS_SLABS = 296;
+__global__ void __launch_bounds__(256) k_colsum_part(int N, int C, int ldx, const float *__restrict__ X, float *__restrict__ part) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  const int rows = (N + CS_SLABS - 1) / CS_SLABS, r0 = blockIdx.y * rows, r1 = min(N, r0 + rows);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += X[(size_t)r * ldx + c]; s1 += X[(size_t)(r + 1) * ldx + c]; s2 += X[(size_t)(r + 2) * ldx + c]; s3 += X[(size_t)(r + 3) * ldx + c];
+  }
+  for (; r < r1; ++r) s0 += X[(size_t)r * ldx + c];
+  part[(size_t)blockIdx.y * C + c] = (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(256) k_colsum_final(int C, const float *__restrict__ part, float *__restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = 0; k < CS_SLABS; ++k) s += part[(size_t)k * C + c];
+  out[c] = s;
+}
+}  // namespace
+
+extern "C" int dge_gru_gates_bwd(int N, int C, const float *gi, const float *gh, const float *b_ih, const float *b_hh, const float *h, const float *gout,
+                                 float *dgi, float *dgh, float *dh, void *stream) {
+  if (N <= 0 || C <= 0 || (C & 3) || !gi || !gh || !b_ih || !b_hh || !h || !gout || !dgi || !dgh || !dh) return -1;
+  if (((uintptr_t)gi | (uintptr_t)gh | (uintptr_t)b_ih | (uintptr_t)b_hh | (uintptr_t)h | (uintptr_t)gout | (uintptr_t)dgi | (uintptr_t)dgh | (uintptr_t)dh) & 15) return -1;
+  const int64_t n4 = (int64_t)N * (C / 4);
+  k_gru_gates_bwd<<<(unsigned)((n4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n4, C / 4, reinterpret_cast<const float4 *>(gi), reinterpret_cast<const float4 *>(gh), reinterpret_cast<const float4 *>(b_ih),
+      reinterpret_cast<const float4 *>(b_hh), reinterpret_cast<const float4 *>(h), reinterpret_cast<const float4 *>(gout),
+      reinterpret_cast<float4 *>(dgi), reinterpret_cast<float4 *>(dgh), reinterpret_cast<float4 *>(dh));
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int64_t dge_colsum_ws_floats(int C) { return (int64_t)CS_SLABS * (C > 0 ? C : 0); }
+extern "C" int dge_colsum(int N, int C, const float *X, int ldx, float *out, float *ws, void *stream) {
+  if (N <= 0 || C <= 0 || !X || !out || !ws) return -1;
+  if (!ldx) ldx = C;
+  if (ldx < C) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_colsum_part<<<dim3((C + 255) / 256, CS_SLABS), 256, 0, st>>>(N, C, ldx, X, ws);
+  k_colsum_final<<<(C + 255) / 256, 256, 0, st>>>(C, ws, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 // ------------------------------------------------------------------ g-U-Net: augmented adjacency ---------------
 // GraphUNet.augment_adj (Networks.py:216-225 via PyG): A <- remove_self_loops((A + I)(A + I)), coalesced (sorted by row, col).
 // The reference goes through torch_sparse.spspmm (cuSPARSE SpGEMM + sort + coalesce); the batched exploration graphs are

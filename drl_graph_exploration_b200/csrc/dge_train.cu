@@ -369,6 +369,16 @@ extern "C" int dge_gcn_train_step(int N, int Cin, int C, const float *x, const i
   return 0;
 }
 
+// X [N,C] -> (hi, lo) [N,C] (nullable pair) and (thi, tlo) [C,Np]: the operand forms of the tcgen05 GEMM for autograd's mm backward
+// (gnn._TcMatmulFn / _TcLinearFn: every family's dense layers under training, not only the fused GCN step above)
+extern "C" int dge_gemm_split_transpose(int N, int C, const float *X, float *hi, float *lo, float *thi, float *tlo, void *stream) {
+  if (N <= 0 || C <= 0 || !X || !thi || !tlo || (!hi != !lo)) return -1;
+  const int64_t Np = ((int64_t)N + 3) & ~3;
+  const dim3 tg((C + 31) / 32, (unsigned)((Np + 31) / 32));
+  k_split_transpose<<<tg, 256, 0, static_cast<cudaStream_t>(stream)>>>(N, C, (int)Np, X, hi, lo, thi, tlo);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 // p -= Adam(clamp(g * gscale)) on flat buffers of n floats; step [1] int64 on the device is incremented first (t = 1 on the first call)
 extern "C" int dge_clamp_adam_step(int64_t n, float *p, float *g, float *m, float *v, int64_t *step, float lr, float beta1, float beta2, float eps,
                                    float clamp, float gscale, void *stream) {

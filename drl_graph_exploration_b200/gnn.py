@@ -167,7 +167,7 @@ class _AggregateFn(torch.autograd.Function):
         gx, _ = _aggregate(ctx.gs, gout, True, ctx.coef, ctx.selfcoef, None, out if ctx.relu else None, False)
         gbias = None
         if ctx.has_bias:
-            gbias = (torch.where(out > 0, gout, torch.zeros_like(gout)) if ctx.relu else gout).sum(dim=0)
+            gbias = colsum(torch.where(out > 0, gout, torch.zeros_like(gout)) if ctx.relu else gout)
         return gx, gbias, None, None, None, None
 
 
@@ -224,6 +224,13 @@ def _gemm_lib():
         L.dge_gemm_split_tf32.argtypes = [ctypes.c_int64, _vp, _vp, _vp, _vp]
         L.dge_gemm_prep_weight.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]
         L.dge_gemm_tf32x3.argtypes = [ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]
+        L.dge_gemm_tf32x3_ex.argtypes = [ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp]
+        L.dge_gemm_split_transpose.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.dge_gru_gates.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp]
+        L.dge_gru_gates_bwd.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.dge_colsum_ws_floats.restype = ctypes.c_int64
+        L.dge_colsum_ws_floats.argtypes = [ctypes.c_int]
+        L.dge_colsum.argtypes = [ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp]
         _gemm_ready = True
     return L
 
@@ -296,31 +303,198 @@ def _tc_gemm(a: torch.Tensor, bt_hi: torch.Tensor, bt_lo: torch.Tensor, m_dev: O
     return c
 
 
+def split_transpose(x: torch.Tensor, plain: bool = True):
+    """x [M,C] -> ((hi, lo) [M,C] or (None, None), (thi, tlo) [C,Mp]) with Mp = M rounded up to 4 (dge_gemm_split_transpose): the
+    row-major split feeds products that contract over C, the transposed one the products that contract over the rows (nodes)."""
+    global launch_count
+    _need_cuda(x, "split_transpose")
+    L = _gemm_lib()
+    x = x.contiguous().float()
+    M, C = x.shape
+    Mp = (M + 3) & ~3
+    hi, lo = (torch.empty_like(x), torch.empty_like(x)) if plain else (None, None)
+    thi, tlo = torch.empty(C, Mp, dtype=torch.float32, device=x.device), torch.empty(C, Mp, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.dge_gemm_split_transpose(M, C, _p(x), _p(hi), _p(lo), _p(thi), _p(tlo), _st(x.device))
+    if rc:
+        raise DgeError(f"dge_gemm_split_transpose failed ({rc})")
+    launch_count += 1
+    return (hi, lo), (thi, tlo)
+
+
+def _tc_gemm_parts(a_hi: torch.Tensor, a_lo: torch.Tensor, bt_hi: torch.Tensor, bt_lo: torch.Tensor):
+    """C [M,N] = A [M,K] @ Bt[N,K]^T from operands that are already split (contraction over the operands' contiguous axis)."""
+    global launch_count
+    L = _gemm_lib()
+    M, K = a_hi.shape
+    N = bt_hi.shape[0]
+    c = torch.empty(M, N, dtype=torch.float32, device=a_hi.device)
+    with torch.cuda.device(a_hi.device):
+        rc = L.dge_gemm_tf32x3_ex(M, None, N, K, _p(a_hi), _p(a_lo), 0, _p(bt_hi), _p(bt_lo), 0, _p(c), N, 1, _st(a_hi.device))
+    if rc:
+        raise DgeError(f"dge_gemm_tf32x3_ex failed ({rc})")
+    launch_count += 1
+    return c
+
+
+def _tc_gemm_over_rows(at: tuple, bt: tuple, rows: int):
+    """C [Ca,Cb] = A^T B for A [rows,Ca], B [rows,Cb] given as their transposed splits ([Ca,Mp], [Cb,Mp] from ``split_transpose``):
+    the weight-gradient shape of autograd's mm backward (few output tiles, K = nodes) -- the library splits K across the SMs and the
+    slices add into the zeroed output."""
+    global launch_count
+    L = _gemm_lib()
+    (a_hi, a_lo), (b_hi, b_lo) = at, bt
+    Ca, Mp = a_hi.shape
+    Cb = b_hi.shape[0]
+    c = torch.zeros(Ca, Cb, dtype=torch.float32, device=a_hi.device)
+    with torch.cuda.device(a_hi.device):
+        rc = L.dge_gemm_tf32x3_ex(Ca, None, Cb, rows, _p(a_hi), _p(a_lo), Mp, _p(b_hi), _p(b_lo), Mp, _p(c), Cb, 0, _st(a_hi.device))
+    if rc:
+        raise DgeError(f"dge_gemm_tf32x3_ex (K = rows) failed ({rc})")
+    launch_count += 2
+    return c
+
+
+_colsum_ws: dict = {}
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of x [M,C] (dge_colsum: deterministic two-stage reduction) -- the bias gradients of the dense layers."""
+    global launch_count
+    _need_cuda(x, "colsum")
+    L = _gemm_lib()
+    x = x.contiguous().float()
+    M, C = x.shape
+    key = (x.device, torch.cuda.current_stream(x.device).cuda_stream)
+    need = int(L.dge_colsum_ws_floats(C))
+    ws = _colsum_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _colsum_ws[key] = torch.empty(max(need, 296 * 3072), dtype=torch.float32, device=x.device)
+    out = torch.empty(C, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.dge_colsum(M, C, _p(x), C, _p(out), _p(ws), _st(x.device))
+    if rc:
+        raise DgeError(f"dge_colsum failed ({rc})")
+    launch_count += 2
+    return out
+
+
 class _TcMatmulFn(torch.autograd.Function):
-    """x @ w with forward and grad-input on the tcgen05 3xTF32 kernel; grad-weight (x^T @ dy, both operands
-    MN-major) stays a library GEMM for now."""
+    """x [M,K] @ w [K,N] with forward, grad-input AND grad-weight on the tcgen05 3xTF32 kernel (the weight gradient x^T dy contracts
+    over the nodes: both operands go through ``split_transpose``)."""
 
     @staticmethod
     def forward(ctx, x, w):
-        ctx.save_for_backward(x, w)
         hi, lo = _weight_operand(w, True)
-        return _tc_gemm(x.float(), hi, lo)
+        x = x.float()
+        if ctx.needs_input_grad[1]:
+            (xh, xl), xt = split_transpose(x)
+            ctx.xt, ctx.rows = xt, x.shape[0]
+        else:
+            xh, xl = split_tf32(x)
+        ctx.save_for_backward(w)
+        return _tc_gemm_parts(xh, xl, hi, lo)
 
     @staticmethod
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
+        (w,) = ctx.saved_tensors
         gx = gw = None
+        gy = gy.contiguous().float()
+        if ctx.needs_input_grad[1]:
+            (gh, gl), gt = split_transpose(gy, plain=ctx.needs_input_grad[0])
+            gw = _tc_gemm_over_rows(ctx.xt, gt, ctx.rows)
+            ctx.xt = None
+        else:
+            gh, gl = split_tf32(gy)
         if ctx.needs_input_grad[0]:
             hi, lo = _weight_operand(w, False)            # dY [M,N] @ W^T: Bt = W [K,N] as stored
-            gx = _tc_gemm(gy.contiguous().float(), hi, lo)
-        if ctx.needs_input_grad[1]:
-            gw = x.t() @ gy
+            gx = _tc_gemm_parts(gh, gl, hi, lo)
         return gx, gw
 
 
 def tc_matmul(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """x [M,K] @ w [K,N], fp32-quality on the 5th-gen tensor cores (csrc/dge_gemm.cu)."""
     return _TcMatmulFn.apply(x, w)
+
+
+class _TcLinearFn(torch.autograd.Function):
+    """x [M,I] @ w[O,I]^T (``F.linear`` without bias: the GRUCell transforms, whose weights already are the K-major B operand),
+    all three products on the tcgen05 3xTF32 kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        hi, lo = _weight_operand(w, False)
+        x = x.float()
+        if ctx.needs_input_grad[1]:
+            (xh, xl), xt = split_transpose(x)
+            ctx.xt, ctx.rows = xt, x.shape[0]
+        else:
+            xh, xl = split_tf32(x)
+        ctx.save_for_backward(w)
+        return _tc_gemm_parts(xh, xl, hi, lo)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (w,) = ctx.saved_tensors
+        gx = gw = None
+        gy = gy.contiguous().float()
+        if ctx.needs_input_grad[1]:
+            (gh, gl), gt = split_transpose(gy, plain=ctx.needs_input_grad[0])
+            gw = _tc_gemm_over_rows(gt, ctx.xt, ctx.rows)          # dW [O,I] = dY^T X
+            ctx.xt = None
+        else:
+            gh, gl = split_tf32(gy)
+        if ctx.needs_input_grad[0]:
+            hi, lo = _weight_operand(w, True)             # dY [M,O] @ W [O,I]: Bt = W^T [I,O]
+            gx = _tc_gemm_parts(gh, gl, hi, lo)
+        return gx, gw
+
+
+def tc_linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    return _TcLinearFn.apply(x, w)
+
+
+class _GruGatesFn(torch.autograd.Function):
+    """h' = GRU gates(gi, gh, b_ih, b_hh, h) (dge_gru_gates); backward = dge_gru_gates_bwd + two dge_colsum for the biases."""
+
+    @staticmethod
+    def forward(ctx, gi, gh, b_ih, b_hh, h):
+        global launch_count
+        L = _gemm_lib()
+        gi, gh, h = gi.contiguous(), gh.contiguous(), h.contiguous().float()
+        b_ih, b_hh = b_ih.detach().contiguous(), b_hh.detach().contiguous()
+        N, C = h.shape
+        out = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            rc = L.dge_gru_gates(N, C, _p(gi), _p(gh), _p(b_ih), _p(b_hh), _p(h), 0, _p(out), _st(h.device))
+        if rc:
+            raise DgeError(f"dge_gru_gates failed ({rc})")
+        launch_count += 1
+        ctx.save_for_backward(gi, gh, b_ih, b_hh, h)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        global launch_count
+        L = _gemm_lib()
+        gi, gh, b_ih, b_hh, h = ctx.saved_tensors
+        gout = gout.contiguous().float()
+        N, C = h.shape
+        dgi, dgh, dh = torch.empty_like(gi), torch.empty_like(gh), torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            rc = L.dge_gru_gates_bwd(N, C, _p(gi), _p(gh), _p(b_ih), _p(b_hh), _p(h), _p(gout), _p(dgi), _p(dgh), _p(dh), _st(h.device))
+        if rc:
+            raise DgeError(f"dge_gru_gates_bwd failed ({rc})")
+        launch_count += 1
+        return dgi, dgh, (colsum(dgi) if ctx.needs_input_grad[2] else None), (colsum(dgh) if ctx.needs_input_grad[3] else None), dh
+
+
+def gru_cell_train(m: torch.Tensor, h: torch.Tensor, rnn: torch.nn.GRUCell) -> torch.Tensor:
+    """``rnn(m, h)`` of GatedGraphConv UNDER AUTOGRAD (Networks.py:76-82 inside DeepQ.train / A2C.train): both transforms, their
+    grad-input and grad-weight products on the tcgen05 3xTF32 GEMM, gate arithmetic and its backward in ``dge_gru_gates(_bwd)``."""
+    _need_cuda(m, "gru_cell_train")
+    gi, gh = tc_linear(m, rnn.weight_ih), tc_linear(h, rnn.weight_hh)
+    return _GruGatesFn.apply(gi, gh, rnn.bias_ih, rnn.bias_hh, h)
 
 
 # ------------------------------------------------------------- DQN training step of the GCN, one native call ---

@@ -96,6 +96,21 @@ int dge_clamp_adam_step(int64_t n, float *p, float *g, float *m, float *v, int64
  * h [N,C] -> h' [N,C] (optionally ReLU'd).  C % 4 == 0, 16-byte aligned pointers.                                    */
 int dge_gru_gates(int N, int C, const float *gi, const float *gh, const float *b_ih, const float *b_hh, const float *h, int relu,
                   float *out, void *stream);
+/* Backward of the same cell (what autograd does inside torch.nn.GRUCell under A2C.train / DeepQ.train of the GG-NN nets,
+ * policy.py:241-253,474-497): from the saved forward inputs and gout = dL/dh' [N,C] (no ReLU on this path) the gates are
+ * recomputed and
+ *   dgi [N,3C] = (da_r | da_z | da_n),   dgh [N,3C] = (da_r | da_z | da_n * r),   dh [N,C] = gout * z   (the direct path)
+ * with da_n = gout (1 - z)(1 - n^2), da_r = da_n (gh_n + b_hn) r (1 - r), da_z = gout (h - n) z (1 - z).  The dense products
+ * (dm = dgi W_ih, dh += dgh W_hh, dW_ih = dgi^T m, dW_hh = dgh^T h) are dge_gemm_tf32x3_ex calls, the bias gradients dge_colsum. */
+int dge_gru_gates_bwd(int N, int C, const float *gi, const float *gh, const float *b_ih, const float *b_hh, const float *h, const float *gout,
+                      float *dgi, float *dgh, float *dh, void *stream);
+/* out [C] = column sums of X [N,C] (row pitch ldx floats), deterministic: row slabs -> partials -> slab-order sum.
+ * ws: dge_colsum_ws_floats(C) floats.  The bias gradients of the dense layers (sum over nodes of dL/dy). */
+int64_t dge_colsum_ws_floats(int C);
+int dge_colsum(int N, int C, const float *X, int ldx, float *out, float *ws, void *stream);
+/* X [N,C] -> its TF32 (hi, lo) split [N,C] (nullable pair) and the split of X^T as (thi, tlo) [C,Np], Np = (N + 3) & ~3, pad
+ * columns zero: both K-major operand forms of dge_gemm_tf32x3_ex -- the transposed one feeds the weight gradient x^T dy (K = nodes). */
+int dge_gemm_split_transpose(int N, int C, const float *X, float *hi, float *lo, float *thi, float *tlo, void *stream);
 
 /* ---- g-U-Net: GraphUNet.augment_adj (Networks.py:216-225: add_self_loops -> spspmm(A, A) -> remove_self_loops, coalesced)
  * for a block-diagonal batch.  rowptr_src / perm_src = source-sorted CSR of the edge list (dge_gnn_csr_build on edge_index[0]),

@@ -20,12 +20,11 @@ def test_engine_csr_equals_generic_preprocessing():
     torch.manual_seed(0)
     model = Networks.GCN().to(env.device).eval()
     # fused vs unfused is a statement about the fusion: both sides use the same GEMM (the unfused path runs under autograd,
-    # whose default GEMM is the library fp32 one -- a 3xTF32-vs-fp32 difference of ~1e-6 of sum|a||w| is not what is tested)
+    # whose GEMM is the tcgen05 one too -- the default training mode)
     Networks.set_matmul_precision("tc3", train="tc3")
     try:
         _run(env, model, Data)
     finally:
-        Networks.set_matmul_precision("tc3", train="fp32")
         env.close()
 
 

@@ -1,0 +1,166 @@
+"""Training path of the GG-NN / g-U-Net families on this package's kernels: the dense products of autograd's
+mm backward (grad-input AND the weight gradient x^T dy contracted over the nodes) on the tcgen05 3xTF32 GEMM, the GRU cell of
+PyG's GatedGraphConv (torch.nn.GRUCell, Networks.py:76-82) with its backward in dge_gru_gates(_bwd), bias gradients through
+dge_colsum -- each against the same operation in fp64 torch.  The operations are smooth (no ReLU kink inside them), so plain
+max-norm bounds apply; the whole GG-NN is then held against the fp64 restatement of oracle/gnn_ref.py."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.double() - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+# 3xTF32 with fp32 accumulation: ~1e-6 of sum|a||b| per product.  For the random operands below sum|a||b| is ~sqrt(K)/2 times the
+# largest output entry's own scale, i.e. a few 1e-6 .. 1e-5 of max|y| at K = 1000..4000 (the library's fp32 SGEMM sits at the same level)
+TOL = 3e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(777, 1000, 1000), (130, 1000, 3000), (4099, 64, 100)])
+def test_tc_matmul_and_linear_forward_and_both_gradients(M, K, N):
+    from drl_graph_exploration_b200 import gnn
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(M)
+    x = torch.randn(M, K, generator=g).to(dev).requires_grad_(True)
+    w = (torch.randn(K, N, generator=g) / K ** 0.5).to(dev).requires_grad_(True)
+    gy = torch.randn(M, N, generator=g).to(dev)
+    x64, w64 = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    l0 = gnn.launch_count
+    y = gnn.tc_matmul(x, w)
+    y.backward(gy)
+    assert gnn.launch_count - l0 >= 7          # split+transpose x2, weight split x2, three products (the K = rows one with its memset)
+    (x64 @ w64).backward(gy.double())
+    assert _rel(y.detach(), (x64 @ w64).detach()) <= TOL
+    assert _rel(x.grad, x64.grad) <= TOL and _rel(w.grad, w64.grad) <= TOL
+    # F.linear form (weights stored [out, in] like GRUCell's)
+    wl = w.detach().t().contiguous().requires_grad_(True)
+    x2 = x.detach().clone().requires_grad_(True)
+    y2 = gnn.tc_linear(x2, wl)
+    y2.backward(gy)
+    assert _rel(y2.detach(), (x64 @ w64).detach()) <= TOL
+    assert _rel(x2.grad, x64.grad) <= TOL and _rel(wl.grad, w64.grad.t()) <= TOL
+    # only one of the two gradients requested
+    x3 = x.detach().clone().requires_grad_(True)
+    gnn.tc_matmul(x3, w.detach()).backward(gy)
+    assert _rel(x3.grad, x64.grad) <= TOL
+    w3 = w.detach().clone().requires_grad_(True)
+    gnn.tc_matmul(x.detach(), w3).backward(gy)
+    assert _rel(w3.grad, w64.grad) <= TOL
+
+
+def test_colsum_is_the_column_sum():
+    from drl_graph_exploration_b200 import gnn
+    dev = torch.device("cuda")
+    for M, C in ((1, 8), (295, 1000), (5001, 3000), (40000, 100)):
+        x = torch.randn(M, C, device=dev)
+        assert _rel(gnn.colsum(x), x.double().sum(0)) <= 1e-5
+    assert torch.equal(gnn.colsum(x), gnn.colsum(x))      # deterministic
+
+
+@pytest.mark.parametrize("N,C", [(513, 1000), (64, 32)])
+def test_gru_cell_train_matches_torch_grucell_in_fp64(N, C):
+    from drl_graph_exploration_b200 import gnn
+    dev = torch.device("cuda")
+    torch.manual_seed(N)
+    rnn = torch.nn.GRUCell(C, C).to(dev)
+    ref = torch.nn.GRUCell(C, C).double().to(dev)
+    ref.load_state_dict({k: v.double() for k, v in rnn.state_dict().items()})
+    m = torch.randn(N, C, device=dev).requires_grad_(True)
+    h = torch.randn(N, C, device=dev).requires_grad_(True)
+    m64, h64 = m.detach().double().requires_grad_(True), h.detach().double().requires_grad_(True)
+    gout = torch.randn(N, C, device=dev)
+    out = gnn.gru_cell_train(m, h, rnn)
+    out.backward(gout)
+    out64 = ref(m64, h64)
+    out64.backward(gout.double())
+    assert _rel(out.detach(), out64.detach()) <= 2 * TOL
+    with torch.no_grad():     # and the inference cell is the same arithmetic
+        assert _rel(gnn.gru_cell_inference(m.detach(), h.detach(), rnn), out64.detach()) <= 2 * TOL
+    assert _rel(m.grad, m64.grad) <= 2 * TOL and _rel(h.grad, h64.grad) <= 2 * TOL
+    for (name, p), (_, q) in zip(rnn.named_parameters(), ref.named_parameters()):
+        assert _rel(p.grad, q.grad) <= 2 * TOL, name
+
+
+def test_ggnn_training_step_on_native_kernels_matches_fp64_reference():
+    """Networks.GGNN under autograd (the default 'tc3' training mode): Q and every parameter gradient of DeepQ.cost against
+    oracle/gnn_ref.GGNN in fp64, and against the library route ('fp32': cuBLAS SGEMM + torch GRUCell)."""
+    from drl_graph_exploration_b200 import Networks, gnn
+    from drl_graph_exploration_b200.data import Data
+    from oracle import gnn_ref
+    from test_graph_gnn_parity_gpu import _random_graph_batch
+
+    dev = torch.device("cuda")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    batch = _random_graph_batch(np.random.default_rng(21), 10, dev)
+    torch.manual_seed(5)
+    model = Networks.GGNN().to(dev).train()
+    ref = gnn_ref.GGNN().double().to(dev)
+    ref.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    N = batch.x.size(0)
+    a = torch.zeros(N, device=dev); a[::5] = 1.0
+    y = torch.randn(N, device=dev)
+
+    def grads(mode):
+        Networks.set_matmul_precision("tc3", train=mode)
+        model.zero_grad(set_to_none=True)
+        l0 = gnn.launch_count
+        out = model(Data(batch.x, batch.edge_index, batch.edge_attr), 0.0, batch=batch.batch)
+        (((out.view(-1) * a - y) ** 2).sum() / 64).backward()
+        return out.detach(), {n: p.grad.clone() for n, p in model.named_parameters()}, gnn.launch_count - l0
+
+    try:
+        out_tc, g_tc, launches_tc = grads("tc3")
+        out_lib, g_lib, launches_lib = grads("fp32")
+    finally:
+        Networks.set_matmul_precision("tc3", train="tc3")
+    assert launches_tc > launches_lib + 50           # per layer: 3 dense layers x (splits + 3 products) + gate kernels + column sums
+    out_ref = ref(gnn_ref.Graph(batch.x.double(), batch.edge_index, batch.edge_attr.double()), 0.0, batch=batch.batch)
+    (((out_ref.view(-1) * a.double() - y.double()) ** 2).sum() / 64).backward()
+    # Three stacked GRU layers behind a sum aggregation with weights up to 6 amplify rounding: the FORWARD of any fp32 implementation
+    # agrees with fp64 to ~2e-3 of max|Q| only (test_gcn_backward_and_other_families_match_reference holds that bound), dq = 2 (Q a - y) a / 64
+    # inherits it, and the ReLU behind the last layer may flip a unit within the forward error of zero.  So the whole-net comparison is
+    # a wiring check at 2e-2 of each gradient's largest entry (a transposed operand or a missing term is O(1)); the precision of every
+    # product and of the cell is held op by op above (3e-5 .. 6e-5).  The library route must sit at the same level.
+    assert _rel(out_tc, out_ref.detach()) <= 2e-3
+    worst_tc = max(_rel(g_tc[name], p.grad) for name, p in ref.named_parameters())
+    worst_lib = max(_rel(g_lib[name], p.grad) for name, p in ref.named_parameters())
+    assert worst_tc <= 2e-2 and worst_lib <= 2e-2, (worst_tc, worst_lib)
+    assert worst_tc <= 10 * worst_lib + 1e-3, (worst_tc, worst_lib)
+
+
+def test_graph_unet_trains_on_the_tensor_core_products():
+    """g-U-Net under autograd: the GCNConv products of all seven levels (forward, grad-input, grad-weight) go through the tcgen05
+    GEMM; gradients agree with the library route on the same pooled sets."""
+    from drl_graph_exploration_b200 import Networks, gnn
+    from drl_graph_exploration_b200.data import Data
+    from test_graph_gnn_parity_gpu import _random_graph_batch
+
+    dev = torch.device("cuda")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    batch = _random_graph_batch(np.random.default_rng(22), 8, dev)
+    torch.manual_seed(6)
+    model = Networks.GraphUNet(5, 1000, 1000, depth=3).to(dev).train()
+
+    def grads(mode):
+        Networks.set_matmul_precision("tc3", train=mode)
+        model.zero_grad(set_to_none=True)
+        l0 = gnn.launch_count
+        out = model(Data(batch.x, batch.edge_index, batch.edge_attr), 0.0, batch=batch.batch)
+        ((out.view(-1) ** 2).sum() / 64).backward()
+        return out.detach(), {n: p.grad.clone() for n, p in model.named_parameters()}, [p.clone() for p in model.last_perms], gnn.launch_count - l0
+
+    try:
+        out_tc, g_tc, perms_tc, l_tc = grads("tc3")
+        out_lib, g_lib, perms_lib, l_lib = grads("fp32")
+    finally:
+        Networks.set_matmul_precision("tc3", train="tc3")
+    assert l_tc > l_lib + 6 * 5
+    same_sets = all(torch.equal(a, b) for a, b in zip(perms_tc, perms_lib))
+    if same_sets:            # (a score near-tie may pool another node: then the two passes are different functions)
+        assert _rel(out_tc, out_lib.double()) <= 1e-4
+        for name in g_tc:
+            assert _rel(g_tc[name], g_lib[name].double()) <= 5e-3, (name, _rel(g_tc[name], g_lib[name].double()))
+    assert all(torch.isfinite(v).all() for v in g_tc.values())

@@ -175,6 +175,17 @@ def test_gcn_backward_and_other_families_match_reference():
     rng = np.random.default_rng(0)
     batch = _random_graph_batch(rng, 12, dev)
     torch.manual_seed(1)
+    # The GCN's gradients are compared entry by entry with fp64 below, without matching ReLU patterns: that holds for the autograd glue +
+    # aggregation kernels on the library fp32 GEMM (the A/B route, 'fp32').  The default training products (tcgen05 3xTF32) are held
+    # kink by kink in test_native_train_gpu.py and op by op in test_family_train_gpu.py.
+    Networks.set_matmul_precision("tc3", train="fp32")
+    try:
+        _families(Networks, Data, gnn_ref, batch, dev)
+    finally:
+        Networks.set_matmul_precision("tc3", train="tc3")
+
+
+def _families(Networks, Data, gnn_ref, batch, dev):
     for name, kwargs in (("GCN", {}), ("GGNN", {}), ("GraphUNet", dict(in_channels=5, hidden_channels=1000, out_channels=1000, depth=3))):
         model = getattr(Networks, name)(**kwargs).to(dev)
         ref = getattr(gnn_ref, name)(**kwargs).double().to(dev)
