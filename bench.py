@@ -575,6 +575,7 @@ def main():
     ap.add_argument("--no-flush-l2", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-python", action="store_true", help="e2e leg: issue the host tick's C-ABI calls from Python instead of dge_host_policy_tick (A/B)")
     ap.add_argument("--no-gnn", action="store_true", help="skip the C5 GNN samples/sec measurement appended to the default line")
     ap.add_argument("--no-families", action="store_true", help="GNN leg: skip the GG-NN / g-U-Net rows (C5's other two families)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 covariance-propagation roofline sweep appended to the default line (N = 1)")
@@ -715,6 +716,8 @@ def main():
     if not args.no_e2e:
         loop.env.reset()                      # fresh episodes: the host loop owns the action lists from here on
         hl = e2e_loop(loop, overlap=not args.no_overlap)
+        if args.e2e_python:
+            hl.native = False
         n_e2e = max(20, n_ticks)
         for _ in range(max(args.warmup, 12)):   # past the first decision and a few restarts
             hl.tick()
@@ -734,7 +737,8 @@ def main():
             dt = float(et.item())
             out["e2e"] = {"value": float(es[0].item()) / dt, "unit": "env-steps/s", "h2d_bytes_per_step": float(es[1].item()) / n_e2e,
                           "d2h_bytes_per_step": float(es[2].item()) / n_e2e, "ticks": n_e2e, "ms_per_tick": 1e3 * dt / n_e2e,
-                          "api": "HostPolicyLoop: dge_step_host_plans_async + dge_graph_host_packed_begin/end + dge_select_plan_host (pinned host buffers), wall clock, max over ranks"}
+                          "api": ("HostPolicyLoop.tick = dge_host_policy_tick (one native call per tick: " if hl.native is not False else "HostPolicyLoop.tick issued from Python (A/B: ") +
+                                 "dge_step_host_plans_async + dge_graph_host_packed_begin/end + H2D + dge_gcn_q_forward + Q D2H + dge_select_plan_host; pinned host buffers), wall clock, max over ranks"}
     elif rank == 0:
         out["e2e"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "dge_internal.cuh"
+#include "../../include/dge_gnn.h"
 
 int dge_gcn_q_forward_dev(int N, const int32_t *N_dev, int Cin, int C, const float *x, const int32_t *rowptr, const int32_t *perm, const int64_t *src,
                           const float *norm, const float *selfnorm, const float *W1, const float *b1, const float *W2t_hi,
@@ -111,4 +112,86 @@ extern "C" int dge_policy_tick(dge_handle h, const dge_graph_out *g, const dge_g
     memcpy(h->tick_key, &key, sizeof(key));
   }
   return cudaGraphLaunch(h->tick_exec, st) == cudaSuccess ? DGE_OK : DGE_ECUDA;
+}
+
+// ---- the host-driven tick (runner.HostPolicyLoop.tick) as one native call: same sequence of C-ABI calls the Python loop makes, the
+// NumPy bookkeeping between them done here.  An env is in exactly one of three states: in its reset phase (phase > 0: the initial
+// optimize + forced steps queued by dge_reset_done_queued run, one per tick), holding a queued action (cursor < plan length), or in
+// need of a decision.
+extern "C" int dge_host_policy_tick(dge_handle h, const dge_graph_out *g, const dge_gcn_policy *pol, dge_host_loop *hl, uint64_t seed_stride,
+                                    const double *forced_odom_host, int n_forced, void *stream, void *stream_step) {
+  if (!h || !g || !pol || !hl || !forced_odom_host || seed_stride == 0) return DGE_EINVAL;
+  if (!hl->plans || !hl->cursor || !hl->phase || !hl->mask || !hl->done || !hl->need || !hl->metrics || !hl->arena_host || !hl->q_host ||
+      !hl->plan_host || !hl->choice_host || !hl->arena_pack || !hl->arena_dev || !pol->ws || !pol->q)
+    return DGE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream), s1 = stream_step ? static_cast<cudaStream_t>(stream_step) : st;
+  if (ensure_streams(h)) return DGE_ECUDA;
+  const int B = h->d.B;
+  hl->n_stepped = hl->n_graphs = hl->n_nodes = hl->h2d_bytes = hl->d2h_bytes = hl->launches = 0;
+  int n_need = 0, n_step = 0;
+  for (int b = 0; b < B; ++b) {
+    const bool in_reset = hl->phase[b] > 0;
+    const bool has_act = !in_reset && hl->cursor[b] < (int64_t)hl->plans[6 * b + 5];
+    const bool need = !in_reset && !has_act;
+    hl->need[b] = need ? 1 : 0;
+    hl->mask[b] = (has_act || in_reset) ? 1 : 0;
+    n_need += need; n_step += has_act;
+  }
+  int rc;
+  if (s1 != st) {   // the step pipeline starts after everything the previous tick left on `stream` (its select / plan)
+    if (cudaEventRecord(h->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(s1, h->ev_fork, 0) != cudaSuccess) return DGE_ECUDA;
+  }
+  // ---- policy pipeline, part 1 (async): graph kernels + pack run while the host launches the step
+  if (n_need) {
+    if ((rc = dge_graph_host_packed_begin(h, hl->need, g, hl->arena_pack, hl->arena_cap, stream))) return rc;
+    hl->launches += 5; hl->h2d_bytes += B;
+  }
+  // ---- step pipeline (async on s1): restart finished episodes, one simulator step from the host's action lists
+  if ((rc = dge_reset_done_queued(h, seed_stride, forced_odom_host, n_forced, s1))) return rc;
+  if ((rc = dge_step_host_plans_async(h, hl->plans, hl->cursor, hl->mask, hl->done, hl->obs, hl->metrics, DGE_STEP_NO_SYNC | DGE_STEP_HONOR_FORCED, s1))) return rc;
+  hl->launches += 6;
+  hl->h2d_bytes += (int64_t)B * 3 * sizeof(double) + B;
+  hl->d2h_bytes += B + (int64_t)B * 8 * sizeof(double) + (hl->obs ? hl->obs_bytes : 0);
+  for (int b = 0; b < B; ++b) {
+    if (hl->phase[b] > 0) hl->phase[b] -= 1;
+    else if (!hl->need[b]) hl->cursor[b] += 1;
+  }
+  hl->n_stepped = n_step;
+  // ---- policy pipeline, part 2: the batch crosses to the host and back, Q-values come to the host, the host picks the frontiers
+  if (n_need) {
+    dge_graph_packed pk;
+    if ((rc = dge_graph_host_packed_end(h, hl->arena_pack, hl->arena_host, hl->arena_cap, &pk, stream))) return rc;
+    hl->d2h_bytes += pk.total_bytes;
+    const int n = pk.n_nodes;
+    if (pk.n_graphs > 0) {
+      if (n > pol->node_cap) return DGE_ECAP;
+      if (cudaMemcpyAsync(hl->arena_dev, hl->arena_host, (size_t)pk.total_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return DGE_ECUDA;
+      hl->h2d_bytes += pk.total_bytes;
+      const unsigned char *ad = static_cast<const unsigned char *>(hl->arena_dev);
+      const int grc = dge_gcn_q_forward(n, pol->Cin, pol->C, reinterpret_cast<const float *>(ad + pk.x), reinterpret_cast<const int32_t *>(ad + pk.csr_rowptr),
+                                        reinterpret_cast<const int32_t *>(ad + pk.csr_perm), reinterpret_cast<const int64_t *>(ad + pk.edge_index),
+                                        reinterpret_cast<const float *>(ad + pk.gcn_norm), reinterpret_cast<const float *>(ad + pk.gcn_selfnorm), pol->W1, pol->b1,
+                                        pol->W2t_hi, pol->W2t_lo, pol->b2, pol->head_w, pol->head_b_dev, pol->ws, pol->q, stream);
+      if (grc) return grc == -1 ? DGE_EINVAL : DGE_ECUDA;
+      if (cudaMemcpyAsync(hl->q_host, pol->q, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) return DGE_ECUDA;
+      if (cudaStreamSynchronize(st) != cudaSuccess) return DGE_ECUDA;
+      hl->launches += 3; hl->d2h_bytes += (int64_t)n * sizeof(float);
+      if ((rc = dge_select_plan_host(h, hl->arena_host, &pk, hl->q_host, hl->need, hl->plan_host, hl->choice_host, stream))) return rc;
+      hl->launches += 1;
+      hl->h2d_bytes += (int64_t)B * 2 * sizeof(double) + B; hl->d2h_bytes += (int64_t)B * 6 * sizeof(double);
+      for (int b = 0; b < B; ++b) {
+        if (!hl->need[b]) continue;
+        if (hl->choice_host[b] < 0) hl->phase[b] = n_forced + 1;        // no frontier left (q15): the episode is over, its reset takes n_forced + 1 ticks
+        for (int i = 0; i < 6; ++i) hl->plans[6 * b + i] = hl->plan_host[6 * b + i];
+        hl->cursor[b] = 0;
+      }
+      hl->n_graphs = pk.n_graphs; hl->n_nodes = n;
+    }
+  }
+  // ---- join: the step's host buffers are valid after this
+  if (cudaStreamSynchronize(s1) != cudaSuccess) return DGE_ECUDA;
+  for (int b = 0; b < B; ++b) {
+    if (hl->done[b]) { hl->phase[b] = n_forced + 1; hl->plans[6 * b + 5] = 0.0; hl->cursor[b] = 0; }
+  }
+  return DGE_OK;
 }

@@ -204,6 +204,13 @@ class GraphHostOut(ctypes.Structure):
                                                "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm")]
 
 
+class HostLoop(ctypes.Structure):
+    """``struct dge_host_loop`` (include/dge.h): host state, pinned buffers and device arenas of ``dge_host_policy_tick``."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("plans", "cursor", "phase", "mask", "done", "need", "obs")] + [("obs_bytes", ctypes.c_int64)] + \
+               [(n, ctypes.c_void_p) for n in ("metrics", "arena_host", "q_host", "plan_host", "choice_host", "arena_pack", "arena_dev")] + \
+               [(n, ctypes.c_int64) for n in ("arena_cap", "n_stepped", "n_graphs", "n_nodes", "h2d_bytes", "d2h_bytes", "launches")]
+
+
 def _make_plan(model, batch):
     """``gnn.QForwardPlan`` for a ``Networks.GCN`` Q-network on the GPU, ``None`` for every other model."""
     from . import gnn
@@ -268,7 +275,10 @@ class HostPolicyLoop:
     flight; NumPy work is vectorised over envs (no per-env Python).
     """
 
-    def __init__(self, env: VecExplorationEnv, model: torch.nn.Module, overlap: bool = True, read_obs: bool = True):
+    def __init__(self, env: VecExplorationEnv, model: torch.nn.Module, overlap: bool = True, read_obs: bool = True, native: bool | None = None):
+        """``native``: None = the whole tick in one native call (``dge_host_policy_tick``) whenever the model is the DQN Q-network on
+        the tcgen05 GEMM and the transfer is packed; False = the same sequence of C-ABI calls issued from Python (A/B, per-section
+        host timing, and the only route for other model families)."""
         import numpy as np
         from .engine import load_library
         self.np = np
@@ -328,6 +338,34 @@ class HostPolicyLoop:
         self._frange = np.arange(eng.Lt + 1)
         self.timing = None                              # optional dict: host seconds per section (dev profiling)
         self._plan = _make_plan(model, g)
+        self.native = native
+        self._native = None                             # (DeviceTick for the policy struct, HostLoop struct), built on first use
+        L.dge_host_policy_tick.argtypes = [vp, vp, vp, vp, ctypes.c_uint64, vp, ctypes.c_int, vp, vp]
+
+    def _native_tick(self):
+        """One tick through ``dge_host_policy_tick``: the sequence of calls below, issued natively (include/dge.h)."""
+        env, L = self.env, self._L
+        if self._native is None:
+            dt = DeviceTick(env, self.model, self.seed_stride, graph=False, overlap=self.overlap)
+            self.plans = self.np.ascontiguousarray(self.plans, dtype=self.np.float64)
+            hl = HostLoop(plans=self.plans.ctypes.data, cursor=self.cursor.ctypes.data, phase=self.phase.ctypes.data, mask=self.t_mask.data_ptr(),
+                          done=self.t_done.data_ptr(), need=self.t_need.data_ptr(), obs=None if self.t_obs is None else self.t_obs.data_ptr(),
+                          obs_bytes=0 if self.t_obs is None else self.t_obs.nbytes, metrics=self.t_metrics.data_ptr(), arena_host=self.a_host.data_ptr(),
+                          q_host=self.t_q.data_ptr(), plan_host=self.t_plan.data_ptr(), choice_host=self.t_choice.data_ptr(),
+                          arena_pack=self.a_pack.data_ptr(), arena_dev=self.a_dev.data_ptr(), arena_cap=self.arena_cap)
+            self._native = (dt, hl, (self.plans, self.cursor, self.phase))      # (the arrays whose addresses the struct holds)
+        dt, hl, held = self._native
+        if held[0] is not self.plans or held[1] is not self.cursor or held[2] is not self.phase:
+            hl.plans, hl.cursor, hl.phase = self.plans.ctypes.data, self.cursor.ctypes.data, self.phase.ctypes.data
+            self._native = (dt, hl, (self.plans, self.cursor, self.phase))
+        pol = dt._policy()
+        main = torch.cuda.current_stream(self.dev)
+        sp = ctypes.c_void_p(self.s_step.cuda_stream) if self.overlap else None
+        _check(L.dge_host_policy_tick(env.eng._h, ctypes.byref(env.graph.c), ctypes.byref(pol), ctypes.byref(hl), self.seed_stride, self._fo, 4,
+                                      ctypes.c_void_p(main.cuda_stream), sp), "dge_host_policy_tick")
+        self.steps += hl.n_stepped; self.graphs += hl.n_graphs
+        self.h2d += hl.h2d_bytes; self.d2h += hl.d2h_bytes; self.launches += hl.launches
+        return int(hl.n_stepped)
 
     def _next_actions(self):
         """Vectorised expansion of action `cursor` of every env's line plan (Planner2D.cpp:982-1038) into odom[B,3]."""
@@ -343,6 +381,14 @@ class HostPolicyLoop:
     @torch.no_grad()
     def tick(self):
         np = self.np
+        if self.native is not False and self.packed and self.timing is None and self._plan is not None:
+            from . import Networks
+            if Networks._PRECISION == "tc3":
+                return self._native_tick()
+            if self.native:
+                raise ValueError("HostPolicyLoop(native=True) needs matmul precision 'tc3'")
+        elif self.native:
+            raise ValueError("HostPolicyLoop(native=True) needs a Networks.GCN Q-network on the GPU and the packed transfer")
         env, eng, L = self.env, self.env.eng, self._L
         B = env.B
         tm = self.timing

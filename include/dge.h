@@ -306,6 +306,29 @@ typedef struct dge_gcn_policy {
 int dge_policy_tick(dge_handle h, const dge_graph_out *g, const dge_gcn_policy *pol, uint64_t seed_stride,
                     const double *forced_odom_host, int n_forced, int flags, void *stream);
 
+/* ---- the same tick driven from the HOST with host buffers: the batched form of test.py:100-143 as the reference runs it -- every
+ * observation crosses to the host, every action comes from it -- in ONE native call (the host-side loop body of
+ * runner.HostPolicyLoop.tick: what the reference's Python does between `env.step` and `model(data)`, for B envs).  Per call:
+ *   host     need / has_action / in_reset from (plans, cursor, phase);
+ *   `stream`       envs that need a decision: dge_graph_host_packed_begin (graph kernels + pack) ... dge_graph_host_packed_end
+ *                  (the batch in arena_host) -> arena_host H2D into arena_dev (DeepQ.test's data.to(device)) -> dge_gcn_q_forward
+ *                  -> Q-values D2H into q_host -> dge_select_plan_host (host arg-max, line plans back in plan_host) -> plans / cursor;
+ *   `stream_step`  dge_reset_done_queued + dge_step_host_plans_async for the envs with a queued action or in their reset phase
+ *                  (done flags, metrics, occupancy maps D2H), joined at the end of the call.
+ * The host state (plans [B,6] in dge_line_plan's compact form, cursor [B], phase [B] = ticks of reset work left) is the caller's
+ * and is updated in place; all other host pointers are pinned buffers.  The out fields count this tick's work and traffic. */
+typedef struct dge_host_loop {
+  double *plans; int64_t *cursor; int64_t *phase;            /* host state, updated in place                                  */
+  uint8_t *mask, *done, *need;                               /* [B] pinned: step mask / done flags out / decision mask         */
+  double *obs; int64_t obs_bytes;                            /* [B,rows,cols] pinned, nullable: occupancy maps after the step  */
+  double *metrics;                                           /* [B,8] pinned                                                   */
+  void *arena_host; float *q_host; double *plan_host; int32_t *choice_host;   /* pinned: packed batch, Q [node_cap], plans, choices */
+  void *arena_pack, *arena_dev; int64_t arena_cap;           /* device arenas: pack target, the policy's copy                  */
+  int64_t n_stepped, n_graphs, n_nodes, h2d_bytes, d2h_bytes, launches;        /* out: this tick                                */
+} dge_host_loop;
+int dge_host_policy_tick(dge_handle h, const dge_graph_out *g, const dge_gcn_policy *pol, dge_host_loop *hl, uint64_t seed_stride,
+                         const double *forced_odom_host, int n_forced, void *stream, void *stream_step);
+
 /* ---- look-ahead roll-out rewards: replaces EMPlanner2D.simulations_reward
  * (Planner2D.cpp:1416-1468, `planner2d` binding Planner2D.cpp:90) and
  * ExplorationEnv.rewards_all_goals (exploration_env.py:145-162).  `dst` is a second engine with the same

@@ -150,10 +150,11 @@ def test_ctypes_structures_mirror_the_header_structs():
     library, against the struct of the same role in include/dge.h."""
     from drl_graph_exploration_b200.config import DgeConfigStruct
     from drl_graph_exploration_b200.engine import GraphOut, _StateView
-    from drl_graph_exploration_b200.runner import GraphHostOut, GraphPacked
+    from drl_graph_exploration_b200.runner import GcnPolicy, GraphHostOut, GraphPacked, HostLoop
     hs = _header_structs()
     for cname, py in (("dge_config", DgeConfigStruct), ("dge_state_view", _StateView), ("dge_graph_out", GraphOut),
-                      ("dge_graph_host_out", GraphHostOut), ("dge_graph_packed", GraphPacked)):
+                      ("dge_graph_host_out", GraphHostOut), ("dge_graph_packed", GraphPacked), ("dge_gcn_policy", GcnPolicy),
+                      ("dge_host_loop", HostLoop)):
         want = hs[cname]
         got = [(n, _ctypes_kind(t)) for n, t in py._fields_]
         assert got == want, (cname, [(a, b) for a, b in zip(got, want) if a != b], len(got), len(want))

@@ -19,15 +19,15 @@ def _mk(n, seed0=300):
     return env
 
 
-@pytest.mark.parametrize("overlap,packed", [(False, True), (True, True), (True, False)])
-def test_host_loop_matches_device_loop(overlap, packed):
+@pytest.mark.parametrize("overlap,packed,native", [(False, True, None), (True, True, None), (True, True, False), (True, False, False)])
+def test_host_loop_matches_device_loop(overlap, packed, native):
     from drl_graph_exploration_b200 import Networks
     from drl_graph_exploration_b200.runner import HostPolicyLoop, PolicyLoop
     a, b = _mk(24), _mk(24)
     torch.manual_seed(0)
     model = Networks.GCN().to(a.device).eval()
     dev_loop = PolicyLoop(a, model, overlap=overlap)
-    host_loop = HostPolicyLoop(b, model, overlap=overlap)
+    host_loop = HostPolicyLoop(b, model, overlap=overlap, native=native)   # None: the tick is ONE native call (dge_host_policy_tick); False: issued from Python
     host_loop.packed = packed                      # one packed transfer per direction (default) / one copy per array
     K = 120                                        # long enough for several episodes to end and restart in-pipeline
     for _ in range(K):
@@ -49,6 +49,7 @@ def test_host_loop_matches_device_loop(overlap, packed):
     np.testing.assert_array_equal(host_loop.t_obs.numpy(), sb["prob"].cpu().numpy())
     np.testing.assert_array_equal(host_loop.metrics[:, 0], sb["metrics"][:, 0].cpu().numpy())
     assert host_loop.h2d > 0 and host_loop.d2h > 0 and host_loop.graphs == dev_loop.graphs
+    assert (host_loop._native is not None) == (native is None and packed)      # the route that was meant to run did run
     a.close(); b.close()
 
 
@@ -106,3 +107,25 @@ def test_packed_graph_transfer_equals_device_graph():
     hdr = loop.a_host[:48].view(i64)
     assert hdr[:3].tolist() == [ng, n, e] and int(hdr[5]) == pk.total_bytes
     env.close()
+
+
+def test_native_host_tick_equals_the_python_issued_tick():
+    """dge_host_policy_tick against the same sequence of C-ABI calls issued from Python: identical host state (plans, cursors, reset
+    phases), identical traffic and launch counts, identical engine state, tick by tick."""
+    from drl_graph_exploration_b200 import Networks
+    from drl_graph_exploration_b200.runner import HostPolicyLoop
+    a, b = _mk(16, seed0=40), _mk(16, seed0=40)
+    torch.manual_seed(0)
+    model = Networks.GCN().to(a.device).eval()
+    nat, py = HostPolicyLoop(a, model, overlap=True), HostPolicyLoop(b, model, overlap=True, native=False)
+    for t in range(90):
+        na, nb = nat.tick(), py.tick()
+        assert na == nb, t
+        np.testing.assert_array_equal(nat.plans, py.plans); np.testing.assert_array_equal(nat.cursor, py.cursor)
+        np.testing.assert_array_equal(nat.phase, py.phase)
+    assert (nat.steps, nat.graphs, nat.h2d, nat.d2h, nat.launches) == (py.steps, py.graphs, py.h2d, py.d2h, py.launches)
+    torch.cuda.synchronize()
+    sa, sb = a.eng.state, b.eng.state
+    for f in ("n_poses", "sim_step", "meas_ptr", "observed", "seed", "seen", "est_pose", "prob"):
+        assert torch.equal(sa[f], sb[f]), f
+    a.close(); b.close()
