@@ -312,6 +312,33 @@ extern "C" int dge_select_plan_host(dge_handle h, const void *arena_host, const 
   const int32_t *nptr = reinterpret_cast<const int32_t *>(ar + lay->node_ptr), *ks = reinterpret_cast<const int32_t *>(ar + lay->key_size);
   const int32_t *fs = reinterpret_cast<const int32_t *>(ar + lay->fro_size);
   const double *fxy = reinterpret_cast<const double *>(ar + lay->frontier_xy);
+  if (lay->frontier_plan > 0) {
+    // the batch carries the line plan of every frontier (actions_all_goals): the host picks actions[key_size + action_index] (test.py:113)
+    // itself -- no device round trip.  An env without a frontier (q15) needs its done flag set on the device: the general path below.
+    bool simple = true;
+    int g0 = 0;
+    for (int b = 0; b < B && simple; ++b) {
+      if (!mask_host[b]) continue;
+      if (g0 >= lay->n_graphs) return fail(DGE_EINVAL, "dge_select_plan_host: mask selects more envs than the batch holds");
+      if (fs[g0] <= 0) simple = false;
+      ++g0;
+    }
+    if (simple) {
+      const double *fpl = reinterpret_cast<const double *>(ar + lay->frontier_plan);
+      int g = 0;
+      for (int b = 0; b < B; ++b) {
+        if (choice_host) choice_host[b] = -1;
+        if (!mask_host[b]) continue;
+        const int F = fs[g], n0 = nptr[g] + ks[g];
+        int best = 0;
+        for (int f = 1; f < F; ++f) if (q_host[n0 + f] > q_host[n0 + best]) best = f;   // first maximum, like np.argmax
+        for (int i = 0; i < 6; ++i) plan_host[6 * b + i] = fpl[((size_t)g * Fmax + best) * 6 + i];
+        if (choice_host) choice_host[b] = best;
+        ++g;
+      }
+      return DGE_OK;
+    }
+  }
   int g = 0;
   for (int b = 0; b < B; ++b) {
     h->hp_mask[b] = 0;
@@ -336,16 +363,20 @@ extern "C" int dge_select_plan_host(dge_handle h, const void *arena_host, const 
 // offsets into the same bytes.  Section order and alignment (16 B) are ABI: see dge_graph_packed in dge.h.
 namespace {
 __host__ __device__ inline int64_t pk_align(int64_t v) { return (v + 15) & ~int64_t(15); }
-struct PackLayout { int64_t off[12]; int64_t total; };
+constexpr int PK_SECTIONS = 13;
+struct PackLayout { int64_t off[PK_SECTIONS]; int64_t total; };
 __host__ __device__ inline PackLayout pack_layout(int64_t G, int64_t N, int64_t E, int64_t Fmax) {
   PackLayout L;
   int64_t o = 128;
-  const int64_t sz[12] = {N * 20, E * 16, E * 4, (G + 1) * 4, (G + 1) * 4, G * 4, G * 4, G * Fmax * 16, (N + 1) * 4, E * 4, E * 4, N * 4};
-  for (int i = 0; i < 12; ++i) { L.off[i] = o; o = pk_align(o + sz[i]); }
+  // (the small per-graph sections the host reads for its decision come last but one; the last one holds the line plan of EVERY frontier:
+  //  ExplorationEnv.actions_all_goals, exploration_env.py:131-143 -- the host then picks actions[key_size + action_index] like test.py:113)
+  const int64_t sz[PK_SECTIONS] = {N * 20, E * 16, E * 4, (G + 1) * 4, (G + 1) * 4, G * 4, G * 4, G * Fmax * 16, (N + 1) * 4, E * 4, E * 4, N * 4, G * Fmax * 48};
+  for (int i = 0; i < PK_SECTIONS; ++i) { L.off[i] = o; o = pk_align(o + sz[i]); }
   L.total = o;
   return L;
 }
-__global__ void __launch_bounds__(256) k_graph_pack(dge_graph_out g, const int32_t *g_sel, int B, int Fmax, unsigned char *arena, int64_t cap) {
+__global__ void __launch_bounds__(256) k_graph_pack(dge_graph_out g, const int32_t *g_sel, int B, int Fmax, unsigned char *arena, int64_t cap, dge_config cfg,
+                                                    const int32_t *n_poses, const double *est_pose, int Tmax) {
   const int64_t G = g.totals[0], N = g.totals[1], E = g.totals[2];
   const PackLayout L = pack_layout(G, N, E, Fmax);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
@@ -375,6 +406,20 @@ __global__ void __launch_bounds__(256) k_graph_pack(dge_graph_out g, const int32
       if (gi >= 0) d[(int64_t)gi * per + (i - (int64_t)b * per)] = reinterpret_cast<const uint32_t *>(g.frontier_xy)[i];
     }
   }
+  {   // line plan of every frontier of every selected env, by graph ordinal (same closed form and the same estimate as k_line_plan / k_select_plan)
+    double *d = reinterpret_cast<double *>(arena + L.off[12]);
+    for (int64_t i = tid; i < (int64_t)B * Fmax; i += nth) {
+      const int b = (int)(i / Fmax), f = (int)(i - (int64_t)b * Fmax), gi = g_sel[b];
+      if (gi < 0) continue;
+      double *pl = d + ((int64_t)gi * Fmax + f) * 6;
+      if (f < g.fro_size[gi]) {
+        const double *p = est_pose + ((size_t)b * Tmax + n_poses[b] - 1) * 3;
+        line_plan(cfg, p[0], p[1], p[2], g.frontier_xy[((size_t)b * Fmax + f) * 2], g.frontier_xy[((size_t)b * Fmax + f) * 2 + 1], pl);
+      } else {
+        for (int k = 0; k < 6; ++k) pl[k] = 0.0;
+      }
+    }
+  }
   if (g.csr_rowptr) {
     cp32(L.off[8], g.csr_rowptr, N + 1);
     cp32(L.off[9], g.csr_perm, E);
@@ -399,13 +444,30 @@ extern "C" int dge_graph_host_packed_begin(dge_handle h, const uint8_t *mask_hos
   }
   const int rc = dge_graph(h, mask, dev, stream);
   if (rc) return rc;
-  k_graph_pack<<<148, 256, 0, st>>>(*dev, h->g_sel, h->d.B, h->d.Fmax, static_cast<unsigned char *>(arena_dev), arena_cap);
+  k_graph_pack<<<148, 256, 0, st>>>(*dev, h->g_sel, h->d.B, h->d.Fmax, static_cast<unsigned char *>(arena_dev), arena_cap, h->cfg, h->n_poses, h->est_pose, h->d.Tmax);
   if (cudaGetLastError() != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host_packed_begin: k_graph_pack");
   if (cudaMemcpyAsync(h->pack_hdr_host, arena_dev, 128, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host_packed_begin: D2H header");
   return DGE_OK;
 }
 
+// `prefetched` bytes of the arena were already queued for the host behind ..._begin on the same stream (dge_graph_host_packed_prefetch): when the
+// batch fits in them the second copy and its synchronisation are not needed
+static int packed_end(dge_handle h, const void *arena_dev, void *arena_host, int64_t arena_cap, int64_t prefetched, dge_graph_packed *out, void *stream);
 extern "C" int dge_graph_host_packed_end(dge_handle h, const void *arena_dev, void *arena_host, int64_t arena_cap, dge_graph_packed *out, void *stream) {
+  return packed_end(h, arena_dev, arena_host, arena_cap, 0, out, stream);
+}
+extern "C" int dge_graph_host_packed_prefetch(dge_handle h, const void *arena_dev, void *arena_host, int64_t bytes, void *stream) {
+  if (!h || !arena_dev || !arena_host || bytes <= 128) return fail(DGE_EINVAL, "dge_graph_host_packed_prefetch: bad arguments");
+  if (cudaMemcpyAsync(static_cast<unsigned char *>(arena_host) + 128, static_cast<const unsigned char *>(arena_dev) + 128, (size_t)(bytes - 128), cudaMemcpyDeviceToHost,
+                      static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return fail(DGE_ECUDA, "dge_graph_host_packed_prefetch: D2H");
+  return DGE_OK;
+}
+extern "C" int dge_graph_host_packed_end_prefetched(dge_handle h, const void *arena_dev, void *arena_host, int64_t arena_cap, int64_t prefetched,
+                                                    dge_graph_packed *out, void *stream) {
+  return packed_end(h, arena_dev, arena_host, arena_cap, prefetched < 128 ? 0 : prefetched, out, stream);
+}
+static int packed_end(dge_handle h, const void *arena_dev, void *arena_host, int64_t arena_cap, int64_t prefetched, dge_graph_packed *out, void *stream) {
   if (!h || !arena_dev || !arena_host || !out) return fail(DGE_EINVAL, "dge_graph_host_packed_end: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host_packed_end: sync");
@@ -416,11 +478,13 @@ extern "C" int dge_graph_host_packed_end(dge_handle h, const void *arena_dev, vo
   out->n_graphs = (int32_t)G; out->n_nodes = (int32_t)N; out->n_edges = (int32_t)E; out->n_done = (int32_t)hdr[4];
   out->total_bytes = G > 0 ? L.total : 128;
   int64_t *o = &out->x;
-  for (int i = 0; i < 12; ++i) o[i] = L.off[i];
+  for (int i = 0; i < PK_SECTIONS; ++i) o[i] = L.off[i];
   memcpy(arena_host, hdr, 128);
   if (G == 0) return DGE_OK;
   if (L.total > arena_cap) return fail(DGE_ECAP, "dge_graph_host_packed_end: arena too small");
-  if (cudaMemcpyAsync(static_cast<unsigned char *>(arena_host) + 128, static_cast<const unsigned char *>(arena_dev) + 128, L.total - 128, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+  const int64_t have = prefetched > 128 ? prefetched : 128;
+  if (L.total <= have) return DGE_OK;            // the whole batch came with the prefetch
+  if (cudaMemcpyAsync(static_cast<unsigned char *>(arena_host) + have, static_cast<const unsigned char *>(arena_dev) + have, L.total - have, cudaMemcpyDeviceToHost, st) != cudaSuccess)
     return fail(DGE_ECUDA, "dge_graph_host_packed_end: D2H arena");
   if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DGE_ECUDA, "dge_graph_host_packed_end: sync");
   return DGE_OK;

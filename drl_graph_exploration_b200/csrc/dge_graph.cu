@@ -337,27 +337,7 @@ __global__ void __launch_bounds__(GT) k_graph_fill(GraphArgs a, dge_graph_out o)
 }
 
 // ------------------------------------------------------------- line planner ---
-// closed form of EMPlanner2D::line_planner (Planner2D.cpp:972-1038); the wasted
-// initialize() (batch ISAM2 rebuild, :938) is dropped.
-__device__ void line_plan(const dge_config &cfg, double rx, double ry, double rth, double gx, double gy, double *pl) {
-  double root = rth, goal = atan2(gy - ry, gx - rx);
-  if (root < 0) root = DGE_PI * 2 + root;
-  if (goal < 0) goal = DGE_PI * 2 + goal;
-  const double dr = 180 * DGE_PI / 180;
-  double diff = goal - root, sign;
-  if (diff > DGE_PI) { diff = 2 * DGE_PI - diff; sign = -1; }
-  else if (diff > -DGE_PI && diff < 0) { diff = fabs(diff); sign = -1; }
-  else if (diff <= -DGE_PI) { diff = 2 * DGE_PI - fabs(diff); sign = 1; }
-  else sign = 1;
-  const int quo = (int)(diff / dr);
-  const double rem = diff - dr * quo;
-  const double dx = rx - gx, dy = ry - gy;
-  const double path = sqrt(dx * dx + dy * dy);
-  const int dq = (int)(path / cfg.max_edge_length);
-  const double drem = path - dq * cfg.max_edge_length;
-  pl[0] = quo; pl[1] = sign; pl[2] = rem; pl[3] = dq; pl[4] = drem; pl[5] = quo + 1 + dq + 1;
-}
-
+// (line_plan: dge_internal.cuh -- the packed host transfer evaluates it for every frontier too)
 __global__ void k_line_plan(dge_config cfg, DgeDims d, const int32_t *n_poses, const double *est_pose, const double *goal,
                             const uint8_t *mask, double *plan_out, uint8_t *done) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -145,6 +145,9 @@ extern "C" int dge_host_policy_tick(dge_handle h, const dge_graph_out *g, const 
   if (n_need) {
     if ((rc = dge_graph_host_packed_begin(h, hl->need, g, hl->arena_pack, hl->arena_cap, stream))) return rc;
     hl->launches += 5; hl->h2d_bytes += B;
+    // the batch follows its header to the host at once, sized by the previous batch (+ margin): one synchronisation instead of two
+    if (hl->prefetch_guess > hl->arena_cap) hl->prefetch_guess = hl->arena_cap;
+    if (hl->prefetch_guess > 128 && (rc = dge_graph_host_packed_prefetch(h, hl->arena_pack, hl->arena_host, hl->prefetch_guess, stream))) return rc;
   }
   // ---- step pipeline (async on s1): restart finished episodes, one simulator step from the host's action lists
   if ((rc = dge_reset_done_queued(h, seed_stride, forced_odom_host, n_forced, s1))) return rc;
@@ -160,8 +163,9 @@ extern "C" int dge_host_policy_tick(dge_handle h, const dge_graph_out *g, const 
   // ---- policy pipeline, part 2: the batch crosses to the host and back, Q-values come to the host, the host picks the frontiers
   if (n_need) {
     dge_graph_packed pk;
-    if ((rc = dge_graph_host_packed_end(h, hl->arena_pack, hl->arena_host, hl->arena_cap, &pk, stream))) return rc;
-    hl->d2h_bytes += pk.total_bytes;
+    if ((rc = dge_graph_host_packed_end_prefetched(h, hl->arena_pack, hl->arena_host, hl->arena_cap, hl->prefetch_guess, &pk, stream))) return rc;
+    hl->d2h_bytes += pk.total_bytes > hl->prefetch_guess ? pk.total_bytes : (hl->prefetch_guess > 128 ? hl->prefetch_guess : pk.total_bytes);   // bytes that crossed the bus
+    if (hl->prefetch_guess > 0) hl->prefetch_guess = pk.total_bytes + pk.total_bytes / 4 + 16384;   // (0 = the caller switched the prefetch off)
     const int n = pk.n_nodes;
     if (pk.n_graphs > 0) {
       if (n > pol->node_cap) return DGE_ECAP;
@@ -176,9 +180,8 @@ extern "C" int dge_host_policy_tick(dge_handle h, const dge_graph_out *g, const 
       if (cudaMemcpyAsync(hl->q_host, pol->q, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) return DGE_ECUDA;
       if (cudaStreamSynchronize(st) != cudaSuccess) return DGE_ECUDA;
       hl->launches += 3; hl->d2h_bytes += (int64_t)n * sizeof(float);
+      // host arg-max; the chosen frontier's plan is in the batch (frontier_plan): no device round trip (the rare no-frontier case excepted)
       if ((rc = dge_select_plan_host(h, hl->arena_host, &pk, hl->q_host, hl->need, hl->plan_host, hl->choice_host, stream))) return rc;
-      hl->launches += 1;
-      hl->h2d_bytes += (int64_t)B * 2 * sizeof(double) + B; hl->d2h_bytes += (int64_t)B * 6 * sizeof(double);
       for (int b = 0; b < B; ++b) {
         if (!hl->need[b]) continue;
         if (hl->choice_host[b] < 0) hl->phase[b] = n_forced + 1;        // no frontier left (q15): the episode is over, its reset takes n_forced + 1 ticks

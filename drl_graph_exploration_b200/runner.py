@@ -194,7 +194,7 @@ class PolicyLoop:
 class GraphPacked(ctypes.Structure):
     """``struct dge_graph_packed`` (include/dge.h): byte offsets of the sections of a packed graph batch + its totals."""
     _fields_ = [(n, ctypes.c_int64) for n in ("total_bytes", "x", "edge_index", "edge_attr", "node_ptr", "edge_ptr", "key_size", "fro_size",
-                                              "frontier_xy", "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm")] + \
+                                              "frontier_xy", "csr_rowptr", "csr_perm", "gcn_norm", "gcn_selfnorm", "frontier_plan")] + \
                [(n, ctypes.c_int32) for n in ("n_graphs", "n_nodes", "n_edges", "n_done")]
 
 
@@ -208,7 +208,7 @@ class HostLoop(ctypes.Structure):
     """``struct dge_host_loop`` (include/dge.h): host state, pinned buffers and device arenas of ``dge_host_policy_tick``."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("plans", "cursor", "phase", "mask", "done", "need", "obs")] + [("obs_bytes", ctypes.c_int64)] + \
                [(n, ctypes.c_void_p) for n in ("metrics", "arena_host", "q_host", "plan_host", "choice_host", "arena_pack", "arena_dev")] + \
-               [(n, ctypes.c_int64) for n in ("arena_cap", "n_stepped", "n_graphs", "n_nodes", "h2d_bytes", "d2h_bytes", "launches")]
+               [(n, ctypes.c_int64) for n in ("arena_cap", "prefetch_guess", "n_stepped", "n_graphs", "n_nodes", "h2d_bytes", "d2h_bytes", "launches")]
 
 
 def _make_plan(model, batch):
@@ -294,6 +294,8 @@ class HostPolicyLoop:
         L.dge_graph_packed_capacity.argtypes = [vp, vp]
         L.dge_graph_host_packed_begin.argtypes = [vp, vp, vp, vp, ctypes.c_int64, vp]
         L.dge_graph_host_packed_end.argtypes = [vp, vp, vp, ctypes.c_int64, vp, vp]
+        L.dge_graph_host_packed_prefetch.argtypes = [vp, vp, vp, ctypes.c_int64, vp]
+        L.dge_graph_host_packed_end_prefetched.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, vp, vp]
         L.dge_step_host_plans_async.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.dge_select_plan_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
@@ -339,6 +341,7 @@ class HostPolicyLoop:
         self.timing = None                              # optional dict: host seconds per section (dev profiling)
         self._plan = _make_plan(model, g)
         self.native = native
+        self.prefetch = True                            # native tick: the batch follows its header to the host at once (sized by the previous batch)
         self._native = None                             # (DeviceTick for the policy struct, HostLoop struct), built on first use
         L.dge_host_policy_tick.argtypes = [vp, vp, vp, vp, ctypes.c_uint64, vp, ctypes.c_int, vp, vp]
 
@@ -352,7 +355,8 @@ class HostPolicyLoop:
                           done=self.t_done.data_ptr(), need=self.t_need.data_ptr(), obs=None if self.t_obs is None else self.t_obs.data_ptr(),
                           obs_bytes=0 if self.t_obs is None else self.t_obs.nbytes, metrics=self.t_metrics.data_ptr(), arena_host=self.a_host.data_ptr(),
                           q_host=self.t_q.data_ptr(), plan_host=self.t_plan.data_ptr(), choice_host=self.t_choice.data_ptr(),
-                          arena_pack=self.a_pack.data_ptr(), arena_dev=self.a_dev.data_ptr(), arena_cap=self.arena_cap)
+                          arena_pack=self.a_pack.data_ptr(), arena_dev=self.a_dev.data_ptr(), arena_cap=self.arena_cap,
+                          prefetch_guess=65536 if self.prefetch else 0)
             self._native = (dt, hl, (self.plans, self.cursor, self.phase))      # (the arrays whose addresses the struct holds)
         dt, hl, held = self._native
         if held[0] is not self.plans or held[1] is not self.cursor or held[2] is not self.phase:
@@ -494,9 +498,7 @@ class HostPolicyLoop:
                     lap("policy: dge_select_plan_host (sync)")
                     choice = self.choice[envs].astype(np.int64)
                     self.phase[envs[choice < 0]] = 5          # no frontier left (q15): episode over
-                    self.launches += 1
-                    self.h2d += self.t_goal.nbytes + B
-                    self.d2h += self.t_plan.nbytes
+                    # (the plans came with the batch -- its frontier_plan section: no launch, no transfer here)
                     self.plans[envs] = self.plan[envs]
                     self.cursor[envs] = 0
                     self.last_choice = (envs, choice)

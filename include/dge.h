@@ -245,15 +245,25 @@ int dge_graph_host(dge_handle h, const uint8_t *mask_host, const dge_graph_out *
 typedef struct dge_graph_packed {
   int64_t total_bytes;
   int64_t x, edge_index, edge_attr, node_ptr, edge_ptr, key_size, fro_size, frontier_xy, csr_rowptr, csr_perm, gcn_norm, gcn_selfnorm;
+  int64_t frontier_plan;   /* [G,Fmax,6] f64: the line plan (dge_line_plan's compact form) of EVERY frontier of every graph -- what
+                              ExplorationEnv.actions_all_goals returns for the frontier nodes (exploration_env.py:131-143) */
   int32_t n_graphs, n_nodes, n_edges, n_done;
 } dge_graph_packed;
 int64_t dge_graph_packed_capacity(dge_handle h, const dge_graph_out *dev);
 int dge_graph_host_packed_begin(dge_handle h, const uint8_t *mask_host, const dge_graph_out *dev, void *arena_dev, int64_t arena_cap, void *stream);
 int dge_graph_host_packed_end(dge_handle h, const void *arena_dev, void *arena_host, int64_t arena_cap, dge_graph_packed *out, void *stream);
+/* optional, between ..._begin and ..._end: queue the first `bytes` of the arena for the host right behind the pack kernel (a guess
+ * of the batch size, e.g. the previous batch's total_bytes plus a margin); ..._end_prefetched(prefetched = bytes) then skips the
+ * second copy and its synchronisation whenever the batch fits in the guess, and copies only the remainder otherwise.       */
+int dge_graph_host_packed_prefetch(dge_handle h, const void *arena_dev, void *arena_host, int64_t bytes, void *stream);
+int dge_graph_host_packed_end_prefetched(dge_handle h, const void *arena_dev, void *arena_host, int64_t arena_cap, int64_t prefetched,
+                                         dge_graph_packed *out, void *stream);
 /* host-side policy read-out on such a batch: per selected env (mask_host as given to ..._begin) the first arg-max of q_host over
  * the graph's last fro_size nodes (np.argmax(readout_t[-fro_size:]), test.py:112 / policy.py:109), the chosen frontier as goal and
  * its line plan (actions_all_goals()[key_size + action_index]) into plan_host [B,6]; choice_host [B] nullable (-1: not selected
- * or no frontier left -- that env's episode is declared over, quirk q15).  Synchronises `stream`.                         */
+ * or no frontier left -- that env's episode is declared over, quirk q15).  The plans are taken from the batch's frontier_plan
+ * section (no device work, no synchronisation); only when an env has no frontier left the goals go to the device
+ * (dge_line_plan_host: that env's done flag is set there) and `stream` is synchronised.                                   */
 int dge_select_plan_host(dge_handle h, const void *arena_host, const dge_graph_packed *layout, const float *q_host, const uint8_t *mask_host,
                          double *plan_host, int32_t *choice_host, void *stream);
 
@@ -324,6 +334,7 @@ typedef struct dge_host_loop {
   double *metrics;                                           /* [B,8] pinned                                                   */
   void *arena_host; float *q_host; double *plan_host; int32_t *choice_host;   /* pinned: packed batch, Q [node_cap], plans, choices */
   void *arena_pack, *arena_dev; int64_t arena_cap;           /* device arenas: pack target, the policy's copy                  */
+  int64_t prefetch_guess;                                    /* in/out: bytes of the batch sent to the host with its header (0: none) */
   int64_t n_stepped, n_graphs, n_nodes, h2d_bytes, d2h_bytes, launches;        /* out: this tick                                */
 } dge_host_loop;
 int dge_host_policy_tick(dge_handle h, const dge_graph_out *g, const dge_gcn_policy *pol, dge_host_loop *hl, uint64_t seed_stride,

@@ -158,7 +158,7 @@ def test_ctypes_structures_mirror_the_header_structs():
         want = hs[cname]
         got = [(n, _ctypes_kind(t)) for n, t in py._fields_]
         assert got == want, (cname, [(a, b) for a, b in zip(got, want) if a != b], len(got), len(want))
-    assert ctypes.sizeof(GraphPacked) == 13 * 8 + 4 * 4 and ctypes.sizeof(GraphHostOut) == 13 * 8
+    assert ctypes.sizeof(GraphPacked) == 14 * 8 + 4 * 4 and ctypes.sizeof(GraphHostOut) == 13 * 8
 
 
 def test_call_sites_pass_as_many_arguments_as_the_prototypes_take():

@@ -104,26 +104,39 @@ def test_packed_graph_transfer_equals_device_graph():
     assert torch.equal(hv(pk.frontier_xy, ng * (env.eng.Lt + 1) * 2, f64, 8).view(ng, env.eng.Lt + 1, 2), g.frontier_xy[envs].cpu())
     assert torch.equal(hv(pk.csr_rowptr, n + 1, i32, 4), g.csr_rowptr[:n + 1].cpu()) and torch.equal(hv(pk.csr_perm, e, i32, 4), g.csr_perm[:e].cpu())
     assert torch.equal(hv(pk.gcn_norm, e, f32, 4), g.gcn_norm[:e].cpu()) and torch.equal(hv(pk.gcn_selfnorm, n, f32, 4), g.gcn_selfnorm[:n].cpu())
+    # the plan of every frontier travels with the batch: frontier f = 0 of every graph against dge_line_plan on the same goal
+    F = env.eng.Lt + 1
+    plans = hv(pk.frontier_plan, ng * F * 6, f64, 8).view(ng, F, 6)
+    ref_plan = env.line_plan(g.frontier_xy[:, 0].contiguous()).cpu()
+    fro = hv(pk.fro_size, ng, i32, 4)
+    for gi, bi in enumerate(envs):
+        if int(fro[gi]) > 0:
+            assert torch.equal(plans[gi, 0], ref_plan[bi]), gi
+        assert bool((plans[gi, int(fro[gi]):] == 0).all())
     hdr = loop.a_host[:48].view(i64)
     assert hdr[:3].tolist() == [ng, n, e] and int(hdr[5]) == pk.total_bytes
     env.close()
 
 
-def test_native_host_tick_equals_the_python_issued_tick():
+@pytest.mark.parametrize("prefetch", [False, True])
+def test_native_host_tick_equals_the_python_issued_tick(prefetch):
     """dge_host_policy_tick against the same sequence of C-ABI calls issued from Python: identical host state (plans, cursors, reset
-    phases), identical traffic and launch counts, identical engine state, tick by tick."""
+    phases), identical traffic and launch counts, identical engine state, tick by tick.  With the prefetch (the batch follows its
+    header to the host at once, sized by the previous batch) the D2H count may only be larger."""
     from drl_graph_exploration_b200 import Networks
     from drl_graph_exploration_b200.runner import HostPolicyLoop
     a, b = _mk(16, seed0=40), _mk(16, seed0=40)
     torch.manual_seed(0)
     model = Networks.GCN().to(a.device).eval()
     nat, py = HostPolicyLoop(a, model, overlap=True), HostPolicyLoop(b, model, overlap=True, native=False)
+    nat.prefetch = prefetch
     for t in range(90):
         na, nb = nat.tick(), py.tick()
         assert na == nb, t
         np.testing.assert_array_equal(nat.plans, py.plans); np.testing.assert_array_equal(nat.cursor, py.cursor)
         np.testing.assert_array_equal(nat.phase, py.phase)
-    assert (nat.steps, nat.graphs, nat.h2d, nat.d2h, nat.launches) == (py.steps, py.graphs, py.h2d, py.d2h, py.launches)
+    assert (nat.steps, nat.graphs, nat.h2d, nat.launches) == (py.steps, py.graphs, py.h2d, py.launches)
+    assert nat.d2h == py.d2h if not prefetch else py.d2h <= nat.d2h <= 3 * py.d2h
     torch.cuda.synchronize()
     sa, sb = a.eng.state, b.eng.state
     for f in ("n_poses", "sim_step", "meas_ptr", "observed", "seed", "seen", "est_pose", "prob"):
