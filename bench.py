@@ -212,6 +212,9 @@ def run_train(args):
     finish(world, dist)
 
 
+TRAIN_PREROLL = 200
+
+
 def measure_train(args, rank, world, local, dist, steps, warmup):
     """BASELINE configs[2] (C3): 256 envs per GPU, 40x40 map, DQN training with batched roll-out rewards, device replay and
     one NCCL all-reduce of the flat gradient bucket per gradient step.  A step = one tick of trainer.VecDQNTrainer."""
@@ -230,7 +233,10 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
     tr = VecDQNTrainer(env, pol, tgt, observe=0, train_steps_per_tick=args.train_steps_per_tick, seed=rank, overlap=not args.no_overlap)
     if args.train_gemm != "native":            # A/B: the autograd path with torch's Adam
         tr.optimizer = torch.optim.Adam(pol.parameters(), lr=1e-5)
-    for _ in range(40):                       # prefill the replay (untimed): every rank needs one minibatch of transitions
+    # untimed pre-roll: fills the replay (every rank needs one minibatch of transitions) and, like the policy loop's pre-roll,
+    # de-synchronises the episodes -- right after the common reset all 256 envs decide in the same ticks (bursts of 256 graphs and
+    # ~1000 roll-out clones, then ticks without a decision); ~200 ticks later a tick sees its stationary ~40 decisions
+    for _ in range(TRAIN_PREROLL):
         tr.tick(learn=False)
     assert tr.replay.size >= tr.dqn.BATCH, "prefill too short"
     for _ in range(warmup):
@@ -288,7 +294,7 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
                "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 simulator / f32 GNN",
                "data": "synthetic",
                "config": {"workload": f"{B} envs/GPU, {ms}x{ms} map, {cfg.n_landmarks} landmarks, DQN+GCN training (BASELINE configs[2])", "batch_graphs_per_rank": bsz,
-                          "train_steps_per_tick": args.train_steps_per_tick, "train_gemm": args.train_gemm,
+                          "train_steps_per_tick": args.train_steps_per_tick, "train_gemm": args.train_gemm, "preroll_ticks": TRAIN_PREROLL,
                           "schedule": "gradient step on a second stream beside the roll-out kernels" if not args.no_overlap else "sequential", "replay": f"device ring, {tr.replay.capacity} transitions, {tr.replay.nbytes() / 2**30:.2f} GiB",
                           "collective": "one all-reduce of the 4.0 MB flat gradient bucket per gradient step" if world > 1 else "none (1 rank)"},
                "decisions_per_s": dec / sec, "train_steps_per_s": tsteps / sec / world, "rollout_clone_steps_per_s": None,

@@ -18,6 +18,10 @@ allocated between a transition's ``s_t`` and its completion.  Every transition c
 graphs AS OF THE TIME THEY WERE STORED (the caller keeps the serial of ``s_t`` next to its slot while the transition is in
 flight); ``sample`` compares them with the ring on every call and accumulates the verdict in a device flag
 (``wrapped``, no host sync) that ``assert_intact`` reads.
+The ring's cursors (``size``, ``head``) live on the DEVICE: ``append_masked`` takes one row per env plus a mask and places the
+selected rows behind the head with a prefix sum, ``sample`` draws distinct positions below the live size with a masked top-k --
+neither needs the host to know how many transitions a tick closed, so a training tick appends and samples without a host
+synchronisation.  ``size`` / ``head`` read as plain ints on demand (a sync; logging, checkpoints, tests).
 Everything is plain tensor plumbing, so the CPU tests exercise the same code.
 """
 from __future__ import annotations
@@ -37,13 +41,33 @@ class GraphReplay:
         self.gn, self.ge, self.gk, self.gf = (z((G,), torch.int64) for _ in range(4))
         self.gserial = torch.full((G,), -1, dtype=torch.int64, device=dev)
         C = self.capacity
-        self.t_s, self.t_s1, self.t_a = z((C,), torch.int64), z((C,), torch.int64), z((C,), torch.int64)
-        self.t_r, self.t_term = z((C,), torch.float32), z((C,), torch.bool)
-        self.t_serial = z((C, 2), torch.int64)      # allocation serials of (s, s1) at append time: detects slot re-use
+        # (position C of every transition array is a trash slot: append_masked sends the rows it does not select there)
+        self.t_s, self.t_s1, self.t_a = z((C + 1,), torch.int64), z((C + 1,), torch.int64), z((C + 1,), torch.int64)
+        self.t_r, self.t_term = z((C + 1,), torch.float32), z((C + 1,), torch.bool)
+        self.t_serial = z((C + 1, 2), torch.int64)  # allocation serials of (s, s1) at append time: detects slot re-use
         self.wrapped = torch.zeros((), dtype=torch.bool, device=dev)   # a sampled transition referred to an overwritten graph
-        self.size = 0          # live transitions (host)
-        self.head = 0          # next transition position (host)
+        self._size = torch.zeros((), dtype=torch.int64, device=dev)    # live transitions
+        self._head = torch.zeros((), dtype=torch.int64, device=dev)    # next transition position
+        self._size_lb = 0      # host-side lower bound of size (size never shrinks): lets sample() skip the read once it is >= k
         self.allocated = 0     # graphs allocated so far (host); slot of allocation i is i % G
+
+    @property
+    def size(self) -> int:
+        """live transitions (reads the device cursor: a host sync)"""
+        self._size_lb = int(self._size)
+        return self._size_lb
+
+    @size.setter
+    def size(self, v: int):
+        self._size.fill_(int(v)); self._size_lb = int(v)
+
+    @property
+    def head(self) -> int:
+        return int(self._head)
+
+    @head.setter
+    def head(self, v: int):
+        self._head.fill_(int(v))
 
     # ------------------------------------------------------------------ graphs ---
     def store_graphs(self, x, edge_index, edge_attr, batch, node_ptr, edge_ptr, key_size, fro_size, n_graphs: int) -> torch.Tensor:
@@ -100,18 +124,41 @@ class GraphReplay:
         if m == 0:
             return
         C, dev = self.capacity, self.device
-        pos = (self.head + torch.arange(m, device=dev)) % C
+        pos = (self._head + torch.arange(m, device=dev)) % C
+        self._write(pos, slot_s, action_node, reward, slot_s1, terminal, serial_s, serial_s1)
+        self._head = (self._head + m) % C
+        self._size = torch.clamp(self._size + m, max=C)
+        self._size_lb = min(C, self._size_lb + m)
+
+    def append_masked(self, mask, slot_s, action_node, reward, slot_s1, terminal, serial_s=None, serial_s1=None):
+        """``append`` of the rows selected by ``mask`` (all arguments [B] device tensors, one row per env), in row order, WITHOUT the
+        host learning how many there are: row b goes to ``head + (number of selected rows before b)``, unselected rows to the trash
+        slot.  B must not exceed the capacity.  Returns the number of appended rows as a device scalar."""
+        C = self.capacity
+        mask = mask.bool()
+        assert mask.numel() <= C, "append_masked: more rows than the ring holds"
+        rank = torch.cumsum(mask.long(), 0) - 1
+        pos = torch.where(mask, (self._head + rank) % C, torch.full_like(rank, C))
+        self._write(pos, slot_s.clamp(min=0), action_node, reward, slot_s1.clamp(min=0), terminal, serial_s, serial_s1)
+        cnt = mask.long().sum()
+        self._head = (self._head + cnt) % C
+        self._size = torch.clamp(self._size + cnt, max=C)
+        return cnt
+
+    def _write(self, pos, slot_s, action_node, reward, slot_s1, terminal, serial_s, serial_s1):
         self.t_s[pos], self.t_s1[pos], self.t_a[pos] = slot_s.long(), slot_s1.long(), action_node.long()
         self.t_r[pos], self.t_term[pos] = reward.float(), terminal.bool()
         self.t_serial[pos, 0] = self.gserial[slot_s.long()] if serial_s is None else serial_s.long()
         self.t_serial[pos, 1] = self.gserial[slot_s1.long()] if serial_s1 is None else serial_s1.long()
-        self.head = (self.head + m) % C
-        self.size = min(C, self.size + m)
 
     def sample(self, k: int, generator=None, check: bool = False):
         """k distinct transitions (random.sample, policy.py:141) -> (slot_s, action_node, reward, slot_s1, terminal)."""
-        assert self.size >= k, "replay holds fewer transitions than the minibatch"
-        idx = torch.randperm(self.size, device=self.device, generator=generator)[:k]
+        if self._size_lb < k:                    # (until the host has once seen size >= k; size never shrinks)
+            assert self.size >= k, "replay holds fewer transitions than the minibatch"
+        # k distinct positions below the live size, which stays on the device: random keys, dead positions pushed out, k smallest
+        key = torch.rand(self.capacity, device=self.device, generator=generator)
+        key = torch.where(torch.arange(self.capacity, device=self.device) < self._size, key, torch.full_like(key, 2.0))
+        idx = torch.topk(key, k, largest=False).indices
         s, s1 = self.t_s[idx], self.t_s1[idx]
         # a stored graph was overwritten while a live transition still refers to it (slack too small): always tested, on the device
         ok = (self.gserial[s] == self.t_serial[idx, 0]) & (self.gserial[s1] == self.t_serial[idx, 1])
@@ -140,7 +187,7 @@ class GraphReplay:
             raise ValueError("replay checkpoint was written with other capacities")
         for k in self._TENSORS:
             getattr(self, k).copy_(d[k])
-        self.size, self.head, self.allocated = int(d["size"]), int(d["head"]), int(d["allocated"])
+        self.size, self.head, self.allocated = int(d["size"]), int(d["head"]), int(d["allocated"])      # (the setters fill the device cursors)
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.x, self.ei, self.ea))

@@ -70,11 +70,30 @@ class VecDQNTrainer:
         self.pend_clo = torch.zeros(B, dtype=torch.bool, device=self.dev)
         self._fo = (ctypes.c_double * 3)(*RESET_ODOM)
         self.gen = torch.Generator(device=self.dev); self.gen.manual_seed(seed)
-        self.decisions = self.train_steps = self.ticks = self.transitions = 0
+        self.decisions = self.train_steps = self.ticks = 0
         self.rollout_steps = self.rollout_clones = 0    # clone-engine ticks launched / clones evaluated
         self._loss = float("nan")
-        self.reward_sum = 0.0
+        # transitions closed / their reward sum: accumulated on the device (a tick closes transitions without the host counting them)
+        self._transitions = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self._reward_sum = torch.zeros((), dtype=torch.float64, device=self.dev)
         self._learning = False                          # see _learning_started
+
+    @property
+    def transitions(self) -> int:
+        """transitions stored so far (reads the device counter: a host sync -- logging, tests, checkpoints)"""
+        return int(self._transitions)
+
+    @transitions.setter
+    def transitions(self, v):
+        self._transitions.fill_(int(v))
+
+    @property
+    def reward_sum(self) -> float:
+        return float(self._reward_sum)
+
+    @reward_sum.setter
+    def reward_sum(self, v):
+        self._reward_sum.fill_(float(v))
 
     # ---------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -131,14 +150,13 @@ class VecDQNTrainer:
         # ---- close the transitions of the envs that decided now (s_t1 = the graph just stored) and of the ended episodes ----
         closing = need & (self.pend_slot >= 0)
         fin = closing | ended
-        idx = fin.nonzero().view(-1)                   # host sync (number of transitions)
-        if idx.numel():
-            s1 = torch.where(closing, slot_new, self.pend_slot)[idx]
-            term = (ended | self.pend_clo | (closing & (fro <= 0)))[idx]
-            ser1 = torch.where(closing, rp.gserial[slot_new.clamp(min=0)], self.pend_serial)[idx]     # s_t1 was stored in this tick (or is s_t itself)
-            rp.append(self.pend_slot[idx], self.pend_a[idx], self.pend_r[idx], s1, term, serial_s=self.pend_serial[idx], serial_s1=ser1)
-            self.transitions += int(idx.numel())
-            self.reward_sum += float(self.pend_r[idx].sum())
+        # one row per env + the mask: the ring places the closing rows behind its head on the device (no host count, no sync)
+        s1 = torch.where(closing, slot_new, self.pend_slot)
+        term = ended | self.pend_clo | (closing & (fro <= 0))
+        ser1 = torch.where(closing, rp.gserial[slot_new.clamp(min=0)], self.pend_serial)     # s_t1 was stored in this tick (or is s_t itself)
+        cnt = rp.append_masked(fin, self.pend_slot, self.pend_a, self.pend_r, s1, term, serial_s=self.pend_serial, serial_s1=ser1)
+        self._transitions += cnt
+        self._reward_sum += torch.where(fin, self.pend_r, torch.zeros_like(self.pend_r)).double().sum()
         self.pend_slot = torch.where(ended, torch.full_like(self.pend_slot, -1), self.pend_slot)
         # ---- open the transitions of the envs that decided now ----
         if ng > 0:

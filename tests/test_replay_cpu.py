@@ -58,7 +58,7 @@ def test_transition_ring_is_fifo_like_the_deque():
         ids = torch.arange(lo, lo + m)
         rp.append(z[:m], ids, ids.float(), z[:m], torch.zeros(m, dtype=torch.bool))
     assert rp.size == 5
-    assert sorted(rp.t_a.tolist()) == [3, 4, 5, 6, 7]              # the three oldest were dropped
+    assert sorted(rp.t_a[:rp.capacity].tolist()) == [3, 4, 5, 6, 7]   # the three oldest were dropped (position `capacity` is append_masked's trash slot)
     s, a, r, s1, term = rp.sample(5, check=True)
     assert sorted(a.tolist()) == [3, 4, 5, 6, 7] and torch.equal(a.float(), r)
     rp.gserial[0] = 99                                             # the slot was re-allocated under a live transition
@@ -136,3 +136,33 @@ def test_vectorised_nstep_returns_equal_the_reference_loop():
         _, a, mask, returns, adv = ac.nstep_batch(last[s])
         assert np.allclose(out[s], returns, rtol=1e-12, atol=1e-12)
         assert np.allclose(adv.reshape(n, 2)[:, 1], returns - vals[s])
+
+
+def test_append_masked_places_the_selected_rows_like_append():
+    """append_masked (one row per env + mask, cursors on the device, no host count) against append of the compacted rows, over
+    several wraps of the ring; sampling stays below the live size while the ring fills."""
+    g = torch.Generator().manual_seed(0)
+    a, b = (GraphReplay(capacity=11, node_cap=4, edge_cap=4, device="cpu", slack=40) for _ in range(2))
+    for rp in (a, b):
+        rp.gserial[:] = torch.arange(rp.G)
+    B = 7
+    for it in range(12):
+        mask = torch.rand(B, generator=g) < 0.45
+        s, s1 = torch.randint(0, a.G, (B,), generator=g), torch.randint(0, a.G, (B,), generator=g)
+        s = torch.where(mask, s, torch.full_like(s, -1))                       # rows that are not selected may hold -1 slots
+        act, r, term = torch.randint(0, 9, (B,), generator=g), torch.rand(B, generator=g), torch.rand(B, generator=g) < 0.3
+        ser, ser1 = a.gserial[s.clamp(min=0)], a.gserial[s1]
+        cnt = a.append_masked(mask, s, act, r, s1, term, serial_s=ser, serial_s1=ser1)
+        idx = mask.nonzero().view(-1)
+        b.append(s[idx], act[idx], r[idx], s1[idx], term[idx], serial_s=ser[idx], serial_s1=ser1[idx])
+        assert int(cnt) == idx.numel() and (a.size, a.head) == (b.size, b.head)
+        C = a.capacity
+        for name in ("t_s", "t_s1", "t_a", "t_r", "t_term", "t_serial"):
+            assert torch.equal(getattr(a, name)[:C], getattr(b, name)[:C]), (it, name)
+        if a.size >= 3:
+            gen = torch.Generator().manual_seed(it)
+            _, aa, rr, _, _ = a.sample(3, generator=gen)
+            live = set(zip(a.t_a[:C].tolist()[:a.size] if a.size < C else a.t_a[:C].tolist(), [round(float(v), 6) for v in (a.t_r[:C][:a.size] if a.size < C else a.t_r[:C])]))
+            assert len(set(zip(aa.tolist(), [round(float(v), 6) for v in rr]))) == 3          # distinct positions
+            assert all((x, round(float(y), 6)) in live for x, y in zip(aa.tolist(), rr))     # ... among the live ones
+    a.assert_intact()

@@ -185,9 +185,10 @@ def test_dqn_bookkeeping_transitions_targets_and_learning(monkeypatch):
         tr.tick()
     rp = tr.replay
     assert rp.size == 64 and tr.transitions > 64 and tr.train_steps > 50 and np.isfinite(tr.last_loss)
-    s, a, r, s1, term = rp.t_s, rp.t_a, rp.t_r, rp.t_s1, rp.t_term
+    C = rp.capacity                                                  # (position C of the transition arrays is append_masked's trash slot)
+    s, a, r, s1, term = rp.t_s[:C], rp.t_a[:C], rp.t_r[:C], rp.t_s1[:C], rp.t_term[:C]
     assert bool(((a >= rp.gk[s]) & (a < rp.gk[s] + rp.gf[s])).all()) and bool((r.abs() <= 1).all())
-    assert bool((rp.gserial[s] == rp.t_serial[:, 0]).all()) and bool((rp.gserial[s1] == rp.t_serial[:, 1]).all())
+    assert bool((rp.gserial[s] == rp.t_serial[:C, 0]).all()) and bool((rp.gserial[s1] == rp.t_serial[:C, 1]).all())
     assert bool(term.any()) and bool((~term).any())
     assert bool((s1[~term] != s[~term]).all())                       # a non-terminal transition ends in a NEW graph
     rp.sample(8, generator=tr.gen, check=True)
