@@ -73,9 +73,10 @@ class ClockSampler(threading.Thread):
     """SM clock / power / throttle reasons DURING the timed region: NVML every 10 ms (nvidia-smi every 200 ms if NVML
     is unavailable).  Reported: median SM clock under load, max SM clock, active slowdown reasons."""
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period=0.01):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.period = float(os.environ.get("DGE_BENCH_SAMPLER_PERIOD", period))   # seconds between NVML samples
         self.nvml = None
         try:
             import pynvml
@@ -107,7 +108,7 @@ class ClockSampler(threading.Thread):
                         self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.01 if self.nvml is not None else 0.2)
+            self._stop_evt.wait(self.period if self.nvml is not None else max(self.period, 0.2))
 
     def stop(self):
         self._stop_evt.set()
@@ -244,7 +245,9 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    # (a training tick is ~150 launches issued from the host: NVML queries take driver locks the launches need, so this leg samples
+    #  the clocks at 5 Hz instead of the policy loop's 100 Hz -- still several samples inside the ~1 s timed region)
+    sampler = ClockSampler(local, period=0.2) if rank == 0 else None
     if sampler:
         sampler.start()
     c0 = [int(v) for v in env.eng.state["counters"].tolist()[:3]]

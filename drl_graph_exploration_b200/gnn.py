@@ -414,6 +414,10 @@ class _TcMatmulFn(torch.autograd.Function):
 
 def tc_matmul(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """x [M,K] @ w [K,N], fp32-quality on the 5th-gen tensor cores (csrc/dge_gemm.cu)."""
+    if not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)):
+        # no backward will follow (inference, or the acting forward of a trainer under no_grad): no transposed operand is prepared
+        hi, lo = _weight_operand(w, True)
+        return _tc_gemm_parts(*split_tf32(x.float()), hi, lo)
     return _TcMatmulFn.apply(x, w)
 
 
@@ -451,6 +455,9 @@ class _TcLinearFn(torch.autograd.Function):
 
 
 def tc_linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    if not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)):
+        hi, lo = _weight_operand(w, False)
+        return _tc_gemm_parts(*split_tf32(x.float()), hi, lo)
     return _TcLinearFn.apply(x, w)
 
 
