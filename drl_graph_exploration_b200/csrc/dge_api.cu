@@ -85,6 +85,7 @@ extern "C" int dge_create(const dge_config *cfg, int n_envs, int max_poses, int 
   e.g_tmp = al.get<int32_t>(B * (size_t)d.Ecap);
   e.slam_clocks = al.get<long long>(B * 12);
   e.forced = al.get<int32_t>(B); e.step_kind = al.get<uint8_t>(B); e.pending = al.get<uint8_t>(B);
+  e.group_heavy = al.get<uint8_t>(B); e.group_light = al.get<uint8_t>(B);
   e.counters = al.get<unsigned long long>(8); e.count_steps = 1; e.park_done = 1;
   e.rdist = al.get<double>(B); e.r_cmap = al.get<int32_t>(B * 2); e.r_cbase = al.get<int32_t>(B); e.r_u0 = al.get<double>(B);
   if (al.ok && cudaMallocHost(reinterpret_cast<void **>(&e.pack_hdr_host), 16 * sizeof(int64_t)) != cudaSuccess) al.ok = false;

@@ -102,6 +102,9 @@ struct dge_engine {
   // ---- dge_policy_tick (csrc/dge_tick.cu): second stream + fork/join events, capture stream, the captured tick and what it was captured for
   cudaStream_t tick_stream, tick_cap_stream;
   cudaEvent_t ev_fork, ev_move, ev_join;
+  cudaStream_t tick_stream2;          // the light group's SLAM -> virtual map chain of a split tick (dge_tick.cu)
+  cudaEvent_t ev_split, ev_light;
+  uint8_t *group_heavy, *group_light;  // [B] masks of the two groups of a split tick (k_split_groups)
   cudaGraphExec_t tick_exec;
   void *tick_key;
 };

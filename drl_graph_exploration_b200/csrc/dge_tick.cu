@@ -13,6 +13,7 @@
 // would have to know to size a launch (how many envs decide, how many nodes their graphs have) stays on the device, so the
 // whole tick is a fixed launch sequence: it is captured ONCE into a CUDA graph (fork / join included) and replayed with
 // one cudaGraphLaunch per tick.
+#include <cstdlib>
 #include <cstring>
 
 #include "dge_internal.cuh"
@@ -36,10 +37,39 @@ struct TickKey {          // everything that is baked into a captured tick
 int ensure_streams(dge_engine *e) {
   if (e->tick_stream) return DGE_OK;
   if (cudaStreamCreateWithFlags(&e->tick_stream, cudaStreamNonBlocking) != cudaSuccess) return DGE_ECUDA;
+  if (cudaStreamCreateWithFlags(&e->tick_stream2, cudaStreamNonBlocking) != cudaSuccess) return DGE_ECUDA;
   if (cudaStreamCreateWithFlags(&e->tick_cap_stream, cudaStreamNonBlocking) != cudaSuccess) return DGE_ECUDA;
-  for (cudaEvent_t *ev : {&e->ev_fork, &e->ev_move, &e->ev_join})
+  for (cudaEvent_t *ev : {&e->ev_fork, &e->ev_move, &e->ev_join, &e->ev_split, &e->ev_light})
     if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return DGE_ECUDA;
   return DGE_OK;
+}
+
+// ---- split of the stepping envs into a HEAVY and a LIGHT group (one CTA) --------------------------------------------------
+// A SLAM launch lasts as long as its slowest env (a rebuild that reaches far back, or a long trajectory: up to ~2.5x the mean), and the
+// virtual-map launch behind it waits for that one CTA although the other envs' estimates have been final for tens of microseconds.  The
+// tick therefore runs two SLAM -> virtual-map chains side by side: the n_heavy envs with the largest expected cost (trajectory length,
+// doubled when the update is on the relinearisation schedule -- the measure of k_step_order) on the step stream, all others on a second
+// stream.  The light group's map rebuild then overlaps the heavy group's SLAM tail; per env nothing changes (both kernels are per-env).
+__global__ void __launch_bounds__(1024) k_split_groups(int B, int n_heavy, int relin_skip, const uint8_t *active, const int32_t *n_poses,
+                                                       const int32_t *update_count, uint8_t *heavy, uint8_t *light) {
+  extern __shared__ int s_cost[];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int cst = -1;
+    if (active[b]) {
+      cst = n_poses[b];
+      if (relin_skip > 0 && (update_count[b] + 1) % relin_skip == 0) cst *= 2;
+    }
+    s_cost[b] = cst;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int cst = s_cost[b];
+    int rank = 0;
+    for (int o = 0; o < B; ++o) { const int co = s_cost[o]; rank += (co > cst || (co == cst && o < b)) ? 1 : 0; }
+    const bool act = cst >= 0, hv = act && rank < n_heavy;
+    heavy[b] = hv ? 1 : 0;
+    light[b] = (act && !hv) ? 1 : 0;
+  }
 }
 
 // the fixed launch sequence of a tick on `st` (+ the engine's second stream unless DGE_TICK_ONE_STREAM)
@@ -55,8 +85,24 @@ int issue_tick(dge_engine *e, const dge_graph_out *g, const dge_gcn_policy *pol,
   if ((rc = dge_launch_reset(e, e->done, nullptr, nullptr, nullptr, nullptr, nullptr, n_forced, seed_stride, s1))) return rc;
   if ((rc = dge_launch_move_measure(e, nullptr, nullptr, nullptr, 1, s1))) return rc;
   if (fork && cudaEventRecord(e->ev_move, s1) != cudaSuccess) return DGE_ECUDA;
-  if ((rc = dge_launch_slam(e, e->active, s1))) return rc;
-  if ((rc = dge_launch_vmap(e, e->active, s1))) return rc;
+  // opt-in (DGE_TICK_HEAVY=n): measured on B200 at 256 envs, n = 16 / 32 / 64: tick 0.187 ms against 0.182 ms with one SLAM / map launch for all
+  // envs (profiles/r02_tick_split_ab.md) -- the light group still contains rebuilds the cost measure does not predict, and the two extra
+  // launches + fork / join cost what the overlap wins; off by default
+  static const int n_heavy = [] { const char *v = getenv("DGE_TICK_HEAVY"); return v ? atoi(v) : 0; }();
+  if (fork && n_heavy > 0 && e->d.B > 2 * n_heavy && e->d.B <= 4096) {
+    cudaStream_t s2 = e->tick_stream2;
+    k_split_groups<<<1, 1024, e->d.B * sizeof(int), s1>>>(e->d.B, n_heavy, e->cfg.relin_skip, e->active, e->n_poses, e->update_count, e->group_heavy, e->group_light);
+    if (cudaGetLastError() != cudaSuccess) return DGE_ECUDA;
+    if (cudaEventRecord(e->ev_split, s1) != cudaSuccess || cudaStreamWaitEvent(s2, e->ev_split, 0) != cudaSuccess) return DGE_ECUDA;
+    if ((rc = dge_launch_slam(e, e->group_heavy, s1))) return rc;      // (issued first: its CTAs take their SMs before the light ones fill the rest)
+    if ((rc = dge_launch_slam(e, e->group_light, s2))) return rc;
+    if ((rc = dge_launch_vmap(e, e->group_light, s2))) return rc;
+    if ((rc = dge_launch_vmap(e, e->group_heavy, s1))) return rc;
+    if (cudaEventRecord(e->ev_light, s2) != cudaSuccess || cudaStreamWaitEvent(s1, e->ev_light, 0) != cudaSuccess) return DGE_ECUDA;
+  } else {
+    if ((rc = dge_launch_slam(e, e->active, s1))) return rc;
+    if ((rc = dge_launch_vmap(e, e->active, s1))) return rc;
+  }
   if (fork && cudaEventRecord(e->ev_join, s1) != cudaSuccess) return DGE_ECUDA;
   // ---- policy pipeline
   if ((rc = dge_launch_graph(e, e->pending, g, st))) return rc;
@@ -76,8 +122,9 @@ void dge_tick_release(dge_engine *e) {
   if (e->tick_exec) { cudaGraphExecDestroy(e->tick_exec); e->tick_exec = nullptr; }
   if (e->tick_key) { free(e->tick_key); e->tick_key = nullptr; }
   if (e->tick_stream) { cudaStreamDestroy(e->tick_stream); e->tick_stream = nullptr; }
+  if (e->tick_stream2) { cudaStreamDestroy(e->tick_stream2); e->tick_stream2 = nullptr; }
   if (e->tick_cap_stream) { cudaStreamDestroy(e->tick_cap_stream); e->tick_cap_stream = nullptr; }
-  for (cudaEvent_t *ev : {&e->ev_fork, &e->ev_move, &e->ev_join})
+  for (cudaEvent_t *ev : {&e->ev_fork, &e->ev_move, &e->ev_join, &e->ev_split, &e->ev_light})
     if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
 }
 

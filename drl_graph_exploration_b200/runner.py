@@ -103,7 +103,9 @@ class PolicyLoop:
         self._plan = _make_plan(model, env.graph)
 
     # kernels per device tick: mark_pending, reset, move_measure, slam, vmap, graph count/scan/fill, conv_small, gemm, aggregate, select_plan
-    DEVICE_TICK_LAUNCHES = 12
+    # (+ split_groups and a second slam / vmap pair when the tick runs its heavy and light envs as two chains: csrc/dge_tick.cu, DGE_TICK_HEAVY)
+    import os as _os
+    DEVICE_TICK_LAUNCHES = 12 if _os.environ.get("DGE_TICK_HEAVY", "0") == "0" else 15
 
     @property
     def launches(self):
