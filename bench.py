@@ -393,7 +393,7 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
     res = {}
     for name, fn in (("forward", fwd), ("forward_backward", fwd_bwd)):
         model.eval() if name == "forward" else model.train()
-        for i in range(max(args.warmup, 3)):
+        for i in range(max(args.warmup, nb)):      # every batch at least once: the caching allocator has seen all sizes before the timed steps
             fn(i)
         torch.cuda.synchronize()
         if world > 1:
@@ -442,7 +442,7 @@ def measure_gnn(args, rank, world, local, dist, steps=None):
             row = {}
             for name, fn in (("forward", f_fwd), ("forward_backward", f_fwd_bwd)):
                 net.eval() if name == "forward" else net.train()
-                for i in range(3):
+                for i in range(nb):           # every batch once: the allocator has seen all sizes, the weight operands are split
                     fn(i)
                 torch.cuda.synchronize()
                 if world > 1:
