@@ -37,7 +37,7 @@ from .replay import GraphReplay
 class VecDQNTrainer:
     def __init__(self, env: VecExplorationEnv, policy_net: torch.nn.Module, target_net: torch.nn.Module, dqn: DeepQ | None = None,
                  replay_capacity: int | None = None, train_steps_per_tick: int = 1, observe: int | None = None, lr: float = 1e-5,
-                 clone_slots: int | None = None, seed: int = 0, overlap: bool = False):
+                 clone_slots: int | None = None, seed: int = 0, overlap: bool | str = False):
         self.env, self.policy_net, self.target_net = env, policy_net, target_net
         self.dqn = dqn or DeepQ()
         self.dev = env.device
@@ -59,6 +59,14 @@ class VecDQNTrainer:
         self.clone_slots = clone_slots
         # overlap: the gradient step of a tick runs on a second stream beside the roll-out kernels of the same tick (it trains
         # on the replay as of the previous tick and finishes before this tick's Q forward reads the weights)
+        # overlap="tail": the gradient step is issued at the END of its tick (exactly the sequential order of operations: it trains on
+        # the replay including this tick's transitions) but on the second stream -- it runs beside the NEXT tick's step pipeline and
+        # roll-out kernels, and the next tick's Q forward waits for it.  The host issues the step -- and, with several ranks, its
+        # gradient all-reduce -- half a tick earlier than in the "beside" schedule, which is slack for ranks whose ticks differ in length.
+        # Measured (bench.py --workload train --train-schedule tail, N = 1): 8.8-10.3 ms per tick against 7.4 ms for "beside" -- the minibatch
+        # gather still reads two totals back (replay.gather), and at the end of a tick that read waits for the tick's whole backlog on the
+        # device.  Bit-identical to the sequential schedule (tests/test_trainer_gpu.py); not the default until the gather is sync-free.
+        self.tail = overlap == "tail"
         self.overlap = bool(overlap)
         self.s_learn = torch.cuda.Stream(self.dev) if self.overlap else None
         self.ev_tick, self.ev_learn = (torch.cuda.Event(), torch.cuda.Event()) if self.overlap else (None, None)
@@ -77,6 +85,7 @@ class VecDQNTrainer:
         self._transitions = torch.zeros((), dtype=torch.int64, device=self.dev)
         self._reward_sum = torch.zeros((), dtype=torch.float64, device=self.dev)
         self._learning = False                          # see _learning_started
+        self._learn_pending = False                     # overlap="tail": a gradient step is in flight on the second stream
 
     @property
     def transitions(self) -> int:
@@ -135,6 +144,9 @@ class VecDQNTrainer:
         if side_work is not None:
             side_work()
             main.wait_event(self.ev_learn)             # the weights and the replay are the gradient step's until it is done
+        elif self.tail and self._learn_pending:
+            torch.cuda.current_stream(dev).wait_event(self.ev_learn)   # the previous tick's gradient step (issued at its end) owns weights and replay until done
+            self._learn_pending = False
         if ng > 0:
             d = g.data()
             q = self.policy_net(d, float(self.epsilon))                     # functional dropout: "bayesian" exploration
@@ -200,9 +212,15 @@ class VecDQNTrainer:
         self.train_steps += 1
         return self.last_loss if check else self._loss
 
+    def _join_learn(self):
+        """overlap="tail": orders the current stream behind the gradient step in flight (weights, loss, optimizer state)."""
+        if self._learn_pending:
+            torch.cuda.current_stream(self.dev).wait_event(self.ev_learn)
+
     @property
     def last_loss(self) -> float:
         """Loss of the last gradient step (reading it synchronises with the step's stream on the native path)."""
+        self._join_learn()
         return float(self._loss)
 
     def _learn_beside(self):
@@ -218,6 +236,14 @@ class VecDQNTrainer:
         sequential mode shifted by one tick (a sequential run of k learning ticks == one acting tick + k overlapped ticks)."""
         if learn is None:
             learn = self._learning_started()
+        if self.tail:
+            ng = self._act()
+            self.ticks += 1
+            if learn:
+                self.ev_tick.record(torch.cuda.current_stream(self.dev))     # this tick's replay writes and weight reads are before this
+                self._learn_beside()
+                self._learn_pending = True
+            return ng
         if self.overlap:
             ng = self._act(self._learn_beside if learn else None)
             self.ticks += 1
@@ -256,6 +282,7 @@ class VecDQNTrainer:
 
     def save(self, path: str):
         """``torch.save(policy_net.state_dict(), .../MyModel.pt)`` like policy.py:192 -- loadable by the reference."""
+        self._join_learn()
         torch.save({k: v.detach().cpu() for k, v in self.policy_net.state_dict().items()}, path)
 
     def run(self, n_ticks: int, out_dir: str | None = None, log_every: int = 100, save_every: int = 50000):
@@ -301,6 +328,7 @@ class VecDQNTrainer:
         epsilon, the replay deque: train.py:33-35, run_training.py:13-16,63-64) next to the two state dicts.  Same content
         here, as one torch file: nets, optimizer, counters, epsilon, sampling generator and (optionally) the device replay.
         Like in the reference the environments are NOT part of it: a resumed run starts fresh episodes."""
+        self._join_learn()
         ck = {"policy": self.policy_net.state_dict(), "target": self.target_net.state_dict(), "optimizer": self.optimizer.state_dict(),
               "dqn": {"step_t": self.dqn.step_t, "epsilon": self.dqn.epsilon, "native_steps": self.dqn.native_steps},
               "counters": {k: getattr(self, k) for k in ("decisions", "train_steps", "ticks", "transitions", "rollout_steps", "rollout_clones", "reward_sum")},

@@ -123,6 +123,30 @@ def test_overlapped_learning_equals_sequential_learning():
     assert torch.equal(w_seq, w_ovl) and l_seq == l_ovl
 
 
+def test_tail_schedule_equals_sequential_learning():
+    """overlap="tail": the gradient step is issued at the end of its tick on the second stream and runs beside the next tick's step /
+    roll-out kernels; the order of operations is the sequential one, so the weights after k ticks are bit-identical -- and the loss read
+    right after a tick is that tick's (the read joins the step in flight)."""
+    def run(overlap):
+        torch.manual_seed(7); torch.cuda.manual_seed(7)
+        env, tr = _make(B=16, seed=500, overlap=overlap)
+        tr.dqn.BATCH = 16
+        for _ in range(25):
+            tr.tick(learn=False)
+        losses = []
+        for _ in range(6):
+            tr.tick(learn=True)
+            losses.append(tr.last_loss)
+        torch.cuda.synchronize()
+        w = torch.cat([p.detach().flatten().clone() for p in tr.policy_net.parameters()])
+        env.close()
+        return w, tr.train_steps, losses
+    w_seq, n_seq, l_seq = run(False)
+    w_tail, n_tail, l_tail = run("tail")
+    assert n_seq == n_tail == 6 and l_seq == l_tail
+    assert torch.equal(w_seq, w_tail)
+
+
 def test_vectorised_a2c_trainer_runs_segments_and_learns():
     """VecA2CTrainer (A2C.running for B envs): segments of nstep decisions close, one gradient step per tick with closed
     segments, actor and critic move, sampled actions are frontier nodes, values / rewards stored per transition are finite."""
