@@ -232,7 +232,7 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
     torch.manual_seed(0)                      # identical replicas on every rank
     pol, tgt = Networks.GCN().to(env.device), Networks.GCN().to(env.device)
     tr = VecDQNTrainer(env, pol, tgt, observe=0, train_steps_per_tick=args.train_steps_per_tick, seed=rank,
-                       overlap=False if args.no_overlap else ("tail" if args.train_schedule == "tail" else True))
+                       overlap=False if args.no_overlap else (args.train_schedule if args.train_schedule in ("tail", "lag") else True))
     if args.train_gemm != "native":            # A/B: the autograd path with torch's Adam
         tr.optimizer = torch.optim.Adam(pol.parameters(), lr=1e-5)
     # untimed pre-roll: fills the replay (every rank needs one minibatch of transitions) and, like the policy loop's pre-roll,
@@ -300,7 +300,8 @@ def measure_train(args, rank, world, local, dist, steps, warmup):
                "config": {"workload": f"{B} envs/GPU, {ms}x{ms} map, {cfg.n_landmarks} landmarks, DQN+GCN training (BASELINE configs[2])", "batch_graphs_per_rank": bsz,
                           "train_steps_per_tick": args.train_steps_per_tick, "train_gemm": args.train_gemm, "preroll_ticks": TRAIN_PREROLL,
                           "schedule": ("sequential" if args.no_overlap else "gradient step issued at the end of its tick on a second stream: runs beside the next tick's step / roll-out kernels (sequential order of operations)"
-                                       if args.train_schedule == "tail" else "gradient step on a second stream beside the roll-out kernels of the same tick"), "replay": f"device ring, {tr.replay.capacity} transitions, {tr.replay.nbytes() / 2**30:.2f} GiB",
+                                       if args.train_schedule == "tail" else "gradient step on a second stream beside the roll-out kernels; its update is applied behind the tick's acting forward (the acting policy is one update staler; the all-reduce has a whole tick before anything waits for it)"
+                                       if args.train_schedule == "lag" else "gradient step on a second stream beside the roll-out kernels of the same tick"), "replay": f"device ring, {tr.replay.capacity} transitions, {tr.replay.nbytes() / 2**30:.2f} GiB",
                           "collective": "one all-reduce of the 4.0 MB flat gradient bucket per gradient step" if world > 1 else "none (1 rank)"},
                "decisions_per_s": dec / sec, "train_steps_per_s": tsteps / sec / world, "rollout_clone_steps_per_s": None,
                "gnn_samples_per_s": {"forward_acting": dec / sec, "forward_target": tsteps * bsz / sec, "forward_backward": tsteps * bsz / sec},
@@ -598,7 +599,7 @@ def main():
     ap.add_argument("--workload", default="policy", choices=["policy", "train", "gnn"],
                     help="policy = BASELINE configs[1] (the headline line); train = configs[2] DQN training; gnn = configs[4] GNN fwd / fwd+bwd")
     ap.add_argument("--train-steps-per-tick", type=int, default=1)
-    ap.add_argument("--train-schedule", default="beside", choices=["tail", "beside"],
+    ap.add_argument("--train-schedule", default="beside", choices=["tail", "beside", "lag"],
                     help="C3: where the gradient step of a tick is issued (trainer.VecDQNTrainer overlap=True / 'tail').  'tail' measured slower (8.8-10.3 vs 7.4 ms per tick at N = 1): "
                          "the two size syncs of the minibatch gather then wait for the whole tick's backlog on the device")
     ap.add_argument("--train-gemm", default="native", choices=["native", "fp32", "tc3"],

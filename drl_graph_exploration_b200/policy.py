@@ -49,6 +49,7 @@ class DeepQ(object):
         self.total_reward = np.empty([0, 0])
         self._bucket = None
         self.native_steps = 0      # gradient steps taken on the native path (keys the dropout stream together with torch.initial_seed())
+        self._pending_apply = None  # (optimizer, clamp, gscale) of a train(..., apply=False) step whose update has not been issued yet
 
     # ------------------------------------------------------------------ data ---
     def data_process(self, data):
@@ -76,7 +77,14 @@ class DeepQ(object):
         readout_action = torch.mul(pred.view(-1), action)
         return torch.pow(readout_action - target.view(-1), 2).sum() / self.BATCH
 
-    def train(self, data, action, y, device, model, optimizer):
+    def apply_pending(self):
+        """The clamp + Adam update of a ``train(..., apply=False)`` step (the trainer issues it behind the acting forward of the tick)."""
+        if self._pending_apply is not None:
+            optimizer, clamp, gscale = self._pending_apply
+            self._pending_apply = None
+            optimizer.step(clamp=clamp, gscale=gscale)
+
+    def train(self, data, action, y, device, model, optimizer, apply: bool = True):
         """policy.py:241-253 (model.train(), dropout p=0.5, clamp +-0.5, Adam step).  With ``dist.NativeAdam`` as the optimizer and
         the DQN Q-network itself (``Networks.GCN`` on CUDA) the whole step runs on the hand-written kernels: forward + cost +
         backward in one native call (``gnn.gcn_train_step``), the gradient all-reduce, then clamp + Adam in one kernel; the loss
@@ -97,7 +105,10 @@ class DeepQ(object):
             world = tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
             if world > 1:
                 tdist.all_reduce(optimizer.bucket.flat, op=tdist.ReduceOp.SUM)     # the one collective of the path
-            optimizer.step(clamp=self.max_grad_norm, gscale=1.0 / world)          # mean over ranks, clamp, Adam: one kernel
+            if apply:
+                optimizer.step(clamp=self.max_grad_norm, gscale=1.0 / world)      # mean over ranks, clamp, Adam: one kernel
+            else:                                                                 # (native path only: the caller applies the update later)
+                self._pending_apply = (optimizer, self.max_grad_norm, 1.0 / world)
             self.temp_loss = loss
             return loss
         if self._bucket is None or self._bucket.params[0] is not next(p for p in model.parameters() if p.requires_grad):

@@ -66,10 +66,18 @@ class VecDQNTrainer:
         # Measured (bench.py --workload train --train-schedule tail, N = 1): 8.8-10.3 ms per tick against 7.4 ms for "beside" -- the minibatch
         # gather still reads two totals back (replay.gather), and at the end of a tick that read waits for the tick's whole backlog on the
         # device.  Bit-identical to the sequential schedule (tests/test_trainer_gpu.py); not the default until the gather is sync-free.
+        # overlap="lag": like True, but the acting forward of a tick does not wait for the tick's gradient step: it reads the weights as
+        # of the PREVIOUS update, and the update of this tick (clamp + Adam) is issued behind it.  The gradient steps themselves are the
+        # same sequence (each is taken at the weights the previous one left); the acting policy is one update staler, which gives the
+        # gradient all-reduce a whole tick before anything waits for it -- ranks whose ticks differ in length stop waiting for each other.
+        self.lag = overlap == "lag"
         self.tail = overlap == "tail"
         self.overlap = bool(overlap)
         self.s_learn = torch.cuda.Stream(self.dev) if self.overlap else None
         self.ev_tick, self.ev_learn = (torch.cuda.Event(), torch.cuda.Event()) if self.overlap else (None, None)
+        self.ev_gathered, self.ev_q = (torch.cuda.Event(), torch.cuda.Event()) if self.overlap else (None, None)
+        if self.lag and (int(train_steps_per_tick) != 1 or not native):
+            raise ValueError("VecDQNTrainer(overlap='lag') takes one gradient step per tick on the native training path (Networks.GCN + dist.NativeAdam)")
         i64 = lambda v: torch.full((B,), v, dtype=torch.int64, device=self.dev)
         self.pend_slot, self.pend_a = i64(-1), i64(0)                  # in-flight transition of every env
         self.pend_serial = i64(-1)                                     # allocation serial of its s_t, read when the graph was stored
@@ -141,7 +149,14 @@ class VecDQNTrainer:
                     self.rollout_steps += env.rollout_steps; self.rollout_clones += acc
                     lo, acc = i, 0
                 acc += f
-        if side_work is not None:
+        if self.lag:
+            cur = torch.cuda.current_stream(dev)
+            if side_work is not None:
+                side_work()                            # forward / backward / all-reduce of this tick's gradient step; its update waits (tick())
+                cur.wait_event(self.ev_gathered)       # the replay is the step's until its minibatch is gathered
+            if self._learn_pending:
+                cur.wait_event(self.ev_learn)          # the weights are the PREVIOUS update's until it is done
+        elif side_work is not None:
             side_work()
             main.wait_event(self.ev_learn)             # the weights and the replay are the gradient step's until it is done
         elif self.tail and self._learn_pending:
@@ -199,16 +214,19 @@ class VecDQNTrainer:
         b_s1, n_s1, off_s1 = rp.gather(s1)
         return b_s, b_s1, (a, r, term, off_s, n_s1, off_s1, rp.gf[s1])
 
-    def learn(self, check: bool = False):
-        """One gradient step (policy.py:136-182); collective inside ``DeepQ.train``."""
+    def learn(self, check: bool = False, apply: bool = True):
+        """One gradient step (policy.py:136-182); collective inside ``DeepQ.train``.  ``apply=False`` (the "lag" schedule): forward,
+        backward and all-reduce only -- ``DeepQ.apply_pending`` issues the update."""
         dqn = self.dqn
         if dqn.TARGET_UPDATE and self.train_steps % int(dqn.TARGET_UPDATE) == 0:
             self.target_net.load_state_dict(self.policy_net.state_dict())
         b_s, b_s1, (a, r, term, off_s, n_s1, off_s1, fro1) = self.minibatch(check=check)
+        if not apply:
+            self.ev_gathered.record(torch.cuda.current_stream(self.dev))
         with torch.no_grad():
             q1 = dqn.test(b_s1, 0.0, self.dev, self.target_net).view(-1)
         act, y = dqn_targets(q1, b_s1.batch, a, r, term, off_s, n_s1, off_s1, fro1, b_s.x.size(0), dqn.GAMMA)
-        self._loss = dqn.train(b_s, act, y, self.dev, self.policy_net, self.optimizer)    # (a device scalar on the native path: no sync here)
+        self._loss = dqn.train(b_s, act, y, self.dev, self.policy_net, self.optimizer, apply=apply)    # (a device scalar on the native path: no sync here)
         self.train_steps += 1
         return self.last_loss if check else self._loss
 
@@ -227,8 +245,9 @@ class VecDQNTrainer:
         with torch.enable_grad(), torch.cuda.stream(self.s_learn):
             self.s_learn.wait_event(self.ev_tick)
             for _ in range(self.train_steps_per_tick):
-                self.learn()
-            self.ev_learn.record(self.s_learn)
+                self.learn(apply=not self.lag)
+            if not self.lag:
+                self.ev_learn.record(self.s_learn)
 
     def tick(self, learn: bool | None = None):
         """One tick.  Sequential mode: act, then ``train_steps_per_tick`` gradient steps.  Overlap mode: the gradient steps run
@@ -242,6 +261,17 @@ class VecDQNTrainer:
             if learn:
                 self.ev_tick.record(torch.cuda.current_stream(self.dev))     # this tick's replay writes and weight reads are before this
                 self._learn_beside()
+                self._learn_pending = True
+            return ng
+        if self.lag:
+            ng = self._act(self._learn_beside if learn else None)
+            self.ticks += 1
+            if learn:     # the update of this tick's step, behind the acting forward that read the old weights
+                self.ev_q.record(torch.cuda.current_stream(self.dev))
+                with torch.cuda.stream(self.s_learn):
+                    self.s_learn.wait_event(self.ev_q)
+                    self.dqn.apply_pending()
+                    self.ev_learn.record(self.s_learn)
                 self._learn_pending = True
             return ng
         if self.overlap:

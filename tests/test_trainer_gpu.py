@@ -200,3 +200,27 @@ def test_training_run_leaves_the_reference_artefacts_and_resumes(tmp_path):
     tr.load(str(tmp_path / "Model_Policy.pt"))
     assert all(torch.equal(a, b) for a, b in zip(tr.policy_net.state_dict().values(), tr.target_net.state_dict().values()))
     env.close()
+
+
+def test_lag_schedule_takes_the_same_number_of_steps_and_learns():
+    """overlap="lag": the acting forward reads the weights as of the previous update, the tick's update is issued behind it (a whole
+    tick of slack for the gradient all-reduce).  The acting policy is one update staler, so trajectories differ from the other
+    schedules; what must hold: one gradient step per learning tick, finite losses, weights that moved, a replay that stays intact,
+    and an update that is never skipped (the step counter of the optimizer equals the number of learning ticks)."""
+    torch.manual_seed(7); torch.cuda.manual_seed(7)
+    env, tr = _make(B=16, seed=500, overlap="lag")
+    tr.dqn.BATCH = 16
+    for _ in range(25):
+        tr.tick(learn=False)
+    w0 = torch.cat([p.detach().flatten().clone() for p in tr.policy_net.parameters()])
+    losses = []
+    for _ in range(8):
+        tr.tick(learn=True)
+        losses.append(tr.last_loss)
+    tr.tick(learn=False)                       # a tick without a step still orders its acting forward behind the last update
+    torch.cuda.synchronize()
+    w1 = torch.cat([p.detach().flatten() for p in tr.policy_net.parameters()])
+    assert tr.train_steps == 8 and int(tr.optimizer.step_t) == 8 and tr.dqn._pending_apply is None
+    assert np.isfinite(losses).all() and not torch.equal(w0, w1) and torch.isfinite(w1).all()
+    tr.replay.assert_intact()
+    env.close()
