@@ -188,29 +188,33 @@ extern "C" int dge_host_policy_tick(dge_handle h, const dge_graph_out *g, const 
   if (s1 != st) {   // the step pipeline starts after everything the previous tick left on `stream` (its select / plan)
     if (cudaEventRecord(h->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(s1, h->ev_fork, 0) != cudaSuccess) return DGE_ECUDA;
   }
-  // Which of the two asynchronous pipelines is issued first: the step's chain (H2D actions, four kernels, 2 MB of maps D2H: ~0.25 ms) is as
-  // long as the policy's, and it is the one the tick ends on (profiles/r02_hostloop_host_profile_v1.txt: 38 us of join wait), so it goes first:
-  // 0.277 vs 0.284 ms per tick (DGE_HOST_TICK_STEP_FIRST=0 for the A/B).  Both orders give the same results, the env sets are disjoint.
-  static const int step_first = [] { const char *v = getenv("DGE_HOST_TICK_STEP_FIRST"); return (v && v[0] == '0') ? 0 : 1; }();
-  for (int pass = 0; pass < 2; ++pass) {
-  if ((pass == 0) != (step_first != 0)) {
-  // ---- policy pipeline, part 1 (async): graph kernels + pack run while the host launches the step
-  if (n_need) {
-    if ((rc = dge_graph_host_packed_begin(h, hl->need, g, hl->arena_pack, hl->arena_cap, stream))) return rc;
+  // ---- policy pipeline, part 1 (async): graph kernels + pack; the batch follows its header to the host at once, sized by the previous
+  // batch (+ margin): one synchronisation instead of two
+  auto issue_graph = [&]() -> int {
+    if (!n_need) return DGE_OK;
+    int r = dge_graph_host_packed_begin(h, hl->need, g, hl->arena_pack, hl->arena_cap, stream);
+    if (r) return r;
     hl->launches += 5; hl->h2d_bytes += B;
-    // the batch follows its header to the host at once, sized by the previous batch (+ margin): one synchronisation instead of two
     if (hl->prefetch_guess > hl->arena_cap) hl->prefetch_guess = hl->arena_cap;
-    if (hl->prefetch_guess > 128 && (rc = dge_graph_host_packed_prefetch(h, hl->arena_pack, hl->arena_host, hl->prefetch_guess, stream))) return rc;
-  }
-  } else {
+    if (hl->prefetch_guess > 128) r = dge_graph_host_packed_prefetch(h, hl->arena_pack, hl->arena_host, hl->prefetch_guess, stream);
+    return r;
+  };
   // ---- step pipeline (async on s1): restart finished episodes, one simulator step from the host's action lists
-  if ((rc = dge_reset_done_queued(h, seed_stride, forced_odom_host, n_forced, s1))) return rc;
-  if ((rc = dge_step_host_plans_async(h, hl->plans, hl->cursor, hl->mask, hl->done, hl->obs, hl->metrics, DGE_STEP_NO_SYNC | DGE_STEP_HONOR_FORCED, s1))) return rc;
-  hl->launches += 6;
-  hl->h2d_bytes += (int64_t)B * 3 * sizeof(double) + B;
-  hl->d2h_bytes += B + (int64_t)B * 8 * sizeof(double) + (hl->obs ? hl->obs_bytes : 0);
-  }
-  }
+  auto issue_step = [&]() -> int {
+    int r = dge_reset_done_queued(h, seed_stride, forced_odom_host, n_forced, s1);
+    if (r) return r;
+    if ((r = dge_step_host_plans_async(h, hl->plans, hl->cursor, hl->mask, hl->done, hl->obs, hl->metrics, DGE_STEP_NO_SYNC | DGE_STEP_HONOR_FORCED, s1))) return r;
+    hl->launches += 6;
+    hl->h2d_bytes += (int64_t)B * 3 * sizeof(double) + B;
+    hl->d2h_bytes += B + (int64_t)B * 8 * sizeof(double) + (hl->obs ? hl->obs_bytes : 0);
+    return DGE_OK;
+  };
+  // Which of the two is issued first: the step's chain (H2D actions, four kernels, 2 MB of maps D2H: ~0.25 ms) is as long as the policy's, and it
+  // is the one the tick ends on (profiles/r02_hostloop_host_profile_v1.txt: 38 us of join wait), so it goes first: 0.277 vs 0.284 ms per tick
+  // (DGE_HOST_TICK_STEP_FIRST=0 for the A/B).  Both orders give the same results, the env sets are disjoint.
+  static const int step_first = [] { const char *v = getenv("DGE_HOST_TICK_STEP_FIRST"); return (v && v[0] == '0') ? 0 : 1; }();
+  if ((rc = step_first ? issue_step() : issue_graph())) return rc;
+  if ((rc = step_first ? issue_graph() : issue_step())) return rc;
   for (int b = 0; b < B; ++b) {
     if (hl->phase[b] > 0) hl->phase[b] -= 1;
     else if (!hl->need[b]) hl->cursor[b] += 1;
