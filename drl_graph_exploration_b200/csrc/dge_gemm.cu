@@ -78,6 +78,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major operand.  For 32-bit elements the tensor core takes ONE shared-memory layout in this mode (cute::UMMA::Layout_MN_SW128_32B_Atom,
+// LayoutType::SWIZZLE_128B_BASE32B = 1; canonical form ((T,8,m),(4,k)):((1,T,LBO),(8T,SBO)), T = 4 floats per 16 bytes): a 128-byte row holds
+// 32 consecutive M (or N) elements of ONE k, its 32-byte chunks XOR-swizzled with (row & 3) -- the TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+// four k rows form the 512-byte atom, the next four start SBO = 512 bytes on, the next 32 M elements LBO = 4096 bytes on (each 32-column
+// chunk of the tile is its own TMA box of BK = 32 rows).
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096u >> 4) << 16) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t IDESC) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
@@ -108,7 +116,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // (column tile fastest, so neighbouring CTAs share an A row block through L2).  The accumulator is double-buffered in tensor
 // memory (2 x 128 columns): the epilogue of tile i drains buffer i & 1 while the MMAs of tile i + 1 fill the other one, and the
 // TMA ring runs ahead across tile boundaries.  The live row count is read from device memory when M_dev is given.
-template <int BN>
+// TN = true: C = A^T B for A [K, M] and B [K, N] as stored (row-major, the contraction runs over the ROWS: the weight gradient x^T dy of a
+// dense layer, K = nodes) -- both operands are read MN-major: every 32-column chunk of a tile is one TMA box of BK rows, the instruction
+// descriptor's major bits are set, and an MMA step advances by eight rows (one swizzle atom) instead of 32 bytes.  No transposed copy of
+// x or dy is ever made.
+template <int BN, bool TN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
               const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
@@ -117,7 +129,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
   // partial products into C with vector atomics (C zeroed by the caller; with two slices the sum is order-independent)
   constexpr int STAGES = Shape<BN>::STAGES, STAGE_BYTES = Shape<BN>::STAGE_BYTES, TMEM_COLS = Shape<BN>::TMEM_COLS;
   constexpr int TILE_BYTES = A_TILE_BYTES, B_TILE = Shape<BN>::B_TILE_BYTES;
-  constexpr uint32_t IDESC = Shape<BN>::IDESC;
+  constexpr uint32_t IDESC = Shape<BN>::IDESC | (TN ? ((1u << 15) | (1u << 16)) : 0u);   // bits 15 / 16: A / B are MN-major
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = M_dev ? min(M, *M_dev) : M;
   const int n_tiles = (N + BN - 1) / BN;
@@ -157,10 +169,23 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
           mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
           const uint32_t st = tiles + s * STAGE_BYTES, fb = full0 + 8 * s;
           mbar_expect_tx(fb, STAGE_BYTES);
-          tma_load_2d(st, &mAh, fb, kb * BK, m0);
-          tma_load_2d(st + TILE_BYTES, &mAl, fb, kb * BK, m0);
-          tma_load_2d(st + 2 * TILE_BYTES, &mBh, fb, kb * BK, n0);
-          tma_load_2d(st + 2 * TILE_BYTES + B_TILE, &mBl, fb, kb * BK, n0);
+          if constexpr (TN) {   // boxes of 32 columns (inner coordinate) x BK rows: 4 KB each, chunk c of a tile at c * 4096
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) {
+              tma_load_2d(st + c * 4096, &mAh, fb, m0 + 32 * c, kb * BK);
+              tma_load_2d(st + TILE_BYTES + c * 4096, &mAl, fb, m0 + 32 * c, kb * BK);
+            }
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+              tma_load_2d(st + 2 * TILE_BYTES + c * 4096, &mBh, fb, n0 + 32 * c, kb * BK);
+              tma_load_2d(st + 2 * TILE_BYTES + B_TILE + c * 4096, &mBl, fb, n0 + 32 * c, kb * BK);
+            }
+          } else {
+            tma_load_2d(st, &mAh, fb, kb * BK, m0);
+            tma_load_2d(st + TILE_BYTES, &mAl, fb, kb * BK, m0);
+            tma_load_2d(st + 2 * TILE_BYTES, &mBh, fb, kb * BK, n0);
+            tma_load_2d(st + 2 * TILE_BYTES + B_TILE, &mBl, fb, kb * BK, n0);
+          }
         }
       }
     }
@@ -180,9 +205,11 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
           const uint32_t st = tiles + s * STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t off = k * UMMA_K * 4;           // 32 bytes along K inside the swizzled 128-byte row
-            const uint64_t ah = smem_desc(st + off), al = smem_desc(st + TILE_BYTES + off);
-            const uint64_t bh = smem_desc(st + 2 * TILE_BYTES + off), bl = smem_desc(st + 2 * TILE_BYTES + B_TILE + off);
+            // K-major: 32 bytes along K inside the swizzled 128-byte row; MN-major: eight k rows = two 512-byte atoms = 1024 bytes
+            const uint32_t off = TN ? k * 1024 : k * UMMA_K * 4;
+            const uint64_t ah = TN ? smem_desc_mn(st + off) : smem_desc(st + off), al = TN ? smem_desc_mn(st + TILE_BYTES + off) : smem_desc(st + TILE_BYTES + off);
+            const uint64_t bh = TN ? smem_desc_mn(st + 2 * TILE_BYTES + off) : smem_desc(st + 2 * TILE_BYTES + off);
+            const uint64_t bl = TN ? smem_desc_mn(st + 2 * TILE_BYTES + B_TILE + off) : smem_desc(st + 2 * TILE_BYTES + B_TILE + off);
             umma_tf32(td, al, bh, (kb != kb0 || k) ? 1u : 0u, IDESC);     // small terms first
             umma_tf32(td, ah, bl, 1u, IDESC);
             umma_tf32(td, ah, bh, 1u, IDESC);
@@ -288,7 +315,8 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 // [rows, K] fp32 row-major, box = 128 rows x 32 columns (128 bytes), 128-byte swizzle, out-of-bounds reads give 0
-bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t K, uint64_t pitch = 0, uint32_t box_rows = BM) {
+bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t K, uint64_t pitch = 0, uint32_t box_rows = BM,
+              CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
   if (!enc) return false;
   const cuuint64_t dims[2] = {K, rows};
@@ -296,7 +324,20 @@ bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t K, uint
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// K slices per output tile when the caller leaves the choice to the library (splits = 0; the caller zeroes C, the slices add into it):
+// (a) as many as fill the SMs when the output has fewer tiles than the machine has SMs and K is long (the weight-gradient shape);
+// (b) at least one per 64 K blocks (2048 elements of K): the tensor core's fp32 accumulator truncates, so the error of a product grows
+//     with the number of MMAs accumulated in tensor memory (measured: 6e-5 of the largest entry at K = 16896 in one or two slices); partial
+//     sums of <= 2048 go through the fp32 atomics' round-to-nearest adds instead.  Two slices add in either order to the same bits; more
+//     than two make the last bits depend on the order of arrival.
+int auto_splits(long long tiles_cap, int num_kb, int n_sm) {
+  int splits = 1;
+  if (tiles_cap < n_sm && num_kb >= 64) { splits = (int)(n_sm / tiles_cap); if (splits > num_kb / 16) splits = num_kb / 16; if (splits < 1) splits = 1; }
+  const int by_len = (num_kb + 63) / 64;
+  return splits > by_len ? splits : by_len;
 }
 
 }  // namespace
@@ -341,24 +382,58 @@ extern "C" int dge_gemm_tf32x3_ex(int M, const int32_t *M_dev, int N, int K, con
   if (!make_map(&mAh, A_hi, M, K, lda) || !make_map(&mAl, A_lo, M, K, lda) || !make_map(&mBh, Bt_hi, N, K, ldb, bn) || !make_map(&mBl, Bt_lo, N, K, ldb, bn)) return -2;
   static bool configured[2] = {false, false};
   if (!configured[bn == 256]) {
-    const cudaError_t ce = bn == 256 ? cudaFuncSetAttribute(k_gemm_tf32x3<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<256>::SMEM)
-                                     : cudaFuncSetAttribute(k_gemm_tf32x3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<128>::SMEM);
+    const cudaError_t ce = bn == 256 ? cudaFuncSetAttribute(k_gemm_tf32x3<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<256>::SMEM)
+                                     : cudaFuncSetAttribute(k_gemm_tf32x3<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<128>::SMEM);
     if (ce != cudaSuccess) return -2;
     configured[bn == 256] = true;
   }
   const long long tiles_cap = (long long)((N + bn - 1) / bn) * m_tiles;
   const int num_kb = (K + BK - 1) / BK;
-  if (splits <= 0) {
-    splits = 1;
-    if (!M_dev && tiles_cap < n_sm && num_kb >= 64) { splits = (int)(n_sm / tiles_cap); if (splits > num_kb / 16) splits = num_kb / 16; if (splits < 1) splits = 1; }
-  }
+  if (splits <= 0) splits = M_dev ? 1 : auto_splits(tiles_cap, num_kb, n_sm);
   if (splits > num_kb) splits = num_kb;
   const long long work = tiles_cap * splits;
   const unsigned grid = (unsigned)(work < n_sm ? work : n_sm);
   if (bn == 256)
-    k_gemm_tf32x3<256><<<grid, GEMM_THREADS, Shape<256>::SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc, splits);
+    k_gemm_tf32x3<256, false><<<grid, GEMM_THREADS, Shape<256>::SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc, splits);
   else
-    k_gemm_tf32x3<128><<<grid, GEMM_THREADS, Shape<128>::SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc, splits);
+    k_gemm_tf32x3<128, false><<<grid, GEMM_THREADS, Shape<128>::SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, M_dev, N, K, ldc, splits);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// C [M,N] = A^T B with A [K,M] (row pitch lda >= M) and B [K,N] (row pitch ldb >= N) as stored, contraction over the rows: the weight
+// gradient of a dense layer (A = x, B = dy, K = nodes) from the SAME (hi, lo) splits the forward / grad-input products use.  splits as in
+// dge_gemm_tf32x3_ex (0: chosen here; > 1: C zeroed by the caller).
+extern "C" int dge_gemm_tf32x3_tn(int M, int N, int K, const float *A_hi, const float *A_lo, int lda, const float *B_hi, const float *B_lo, int ldb,
+                                  float *C, int ldc, int splits, void *stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (ldc & 3) || ldc < N || !A_hi || !A_lo || !B_hi || !B_lo || !C) return -1;
+  if (!lda) lda = M;
+  if (!ldb) ldb = N;
+  if ((lda & 3) || (ldb & 3) || lda < M || ldb < N) return -1;
+  if (((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) & 15) return -1;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  constexpr int bn = 128;
+  // the operands as [K rows, M (or N) columns]: inner dimension = the tile's M / N extent, boxes of 32 columns x BK rows
+  CUtensorMap mAh, mAl, mBh, mBl;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;     // (the one layout the tensor core reads MN-major 32-bit operands in)
+  if (!make_map(&mAh, A_hi, K, M, lda, BK, sw) || !make_map(&mAl, A_lo, K, M, lda, BK, sw) || !make_map(&mBh, B_hi, K, N, ldb, BK, sw) ||
+      !make_map(&mBl, B_lo, K, N, ldb, BK, sw))
+    return -2;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(k_gemm_tf32x3<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<128>::SMEM) != cudaSuccess) return -2;
+    configured = true;
+  }
+  const long long tiles_cap = (long long)((N + bn - 1) / bn) * ((M + BM - 1) / BM);
+  const int num_kb = (K + BK - 1) / BK;
+  if (splits <= 0) splits = auto_splits(tiles_cap, num_kb, n_sm);
+  if (splits > num_kb) splits = num_kb;
+  const long long work = tiles_cap * splits;
+  const unsigned grid = (unsigned)(work < n_sm ? work : n_sm);
+  k_gemm_tf32x3<128, true><<<grid, GEMM_THREADS, Shape<128>::SMEM, static_cast<cudaStream_t>(stream)>>>(mAh, mAl, mBh, mBl, C, M, nullptr, N, K, ldc, splits);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -11,7 +11,7 @@
 //     dz2 = (dq Wh) * [d2 != 0] / (1 - p)   never materialised: rows are formed on the fly where dq != 0
 //     db2 = sum_n dz2                                                                                   (k_colreduce<0>)
 //     g2  = A^T dz2                      gather over the source-sorted CSR, neighbours with dq = 0 skipped   (k_agg_bwd)
-//     dW2 = h1^T g2                      tcgen05 3xTF32 GEMM over K = nodes on transposed (hi, lo) operands, K split across CTAs
+//     dW2 = h1^T g2                      tcgen05 3xTF32 GEMM over K = nodes, both operands read as stored (MN-major: dge_gemm_tf32x3_tn), K split across CTAs
 //     dh1 = g2 W2^T                      tcgen05 3xTF32 GEMM
 //     dz1 = dh1 * [h1 > 0],  db1 = sum_n dz1,  dW1 = (A x)^T dz1                                         (k_colreduce<1>)
 // The column reductions are deterministic (row slabs -> partials -> the last CTA adds them in slab order).
@@ -345,9 +345,9 @@ extern "C" int dge_gcn_train_step(int N, int Cin, int C, const float *x, const i
   (void)counter;
   // ---- forward
   k_conv1_train<<<node_grid(N), 256, 0, st>>>(N, Cin, C, x, rowptr_d, perm_d, src, norm, selfnorm, W1, b1, ax, h1); CKL();
-  const dim3 tg((C + 31) / 32, (unsigned)((Np + 31) / 32));
-  k_split_transpose<<<tg, 256, 0, st>>>(N, C, (int)Np, h1, h1_hi, h1_lo, h1t_hi, h1t_lo); CKL();
-  int rc = dge_gemm_tf32x3_ex(N, nullptr, C, C, h1_hi, h1_lo, 0, W2t_hi, W2t_lo, 0, t2, C, 1, st);
+  int rc = dge_gemm_split_tf32(NC, h1, h1_hi, h1_lo, st);                                             // (one split serves h1 W2 and, as stored, h1^T g2)
+  if (rc) return rc;
+  rc = dge_gemm_tf32x3_ex(N, nullptr, C, C, h1_hi, h1_lo, 0, W2t_hi, W2t_lo, 0, t2, C, 1, st);
   if (rc) return rc;
   rc = dge_agg_fwd_train_bulk(N, C, t2, rowptr_d, perm_d, src, norm, selfnorm, b2, drop_p, drop_seed, Wh, bh, d2, q, st);   // (opt-in, DGE_AGG_BULK=1)
   if (rc == -1) { k_agg_fwd_train<<<node_grid(N), 256, 0, st>>>(N, C, t2, rowptr_d, perm_d, src, norm, selfnorm, b2, drop_p, drop_seed, Wh, bh, d2, q); CKL(); }
@@ -358,11 +358,12 @@ extern "C" int dge_gcn_train_step(int N, int Cin, int C, const float *x, const i
   k_colreduce<0><<<NSLAB, 256, 0, st>>>(N, C, Cin, dq, d2, nullptr, nullptr, Wh, scale, part, counter, gWh, gb2, gbh); CKL();
   k_colreduce_final<0><<<(2 * C + 255) / 256, 256, 0, st>>>(C, Cin, NSLAB, part, Wh, scale, gWh, gb2, gbh); CKL();
   k_agg_bwd_train<<<node_grid(N), 256, 0, st>>>(N, C, d2, dq, Wh, scale, rowptr_s, perm_s, dst, norm, selfnorm, g2); CKL();
-  k_split_transpose<<<tg, 256, 0, st>>>(N, C, (int)Np, g2, g2_hi, g2_lo, g2t_hi, g2t_lo); CKL();
+  rc = dge_gemm_split_tf32(NC, g2, g2_hi, g2_lo, st);
+  if (rc) return rc;
   rc = dge_gemm_tf32x3_ex(N, nullptr, C, C, g2_hi, g2_lo, 0, W2_hi, W2_lo, 0, dh1, C, 1, st);            // dh1 = g2 W2^T
   if (rc) return rc;
   if (cudaMemsetAsync(gW2, 0, sizeof(float) * (size_t)C * C, st) != cudaSuccess) return -2;
-  rc = dge_gemm_tf32x3_ex(C, nullptr, C, N, h1t_hi, h1t_lo, (int)Np, g2t_hi, g2t_lo, (int)Np, gW2, C, 0, st);   // dW2 = h1^T g2, K = nodes
+  rc = dge_gemm_tf32x3_tn(C, C, N, h1_hi, h1_lo, C, g2_hi, g2_lo, C, gW2, C, 0, st);                     // dW2 = h1^T g2, K = nodes, operands as stored (MN-major)
   if (rc) return rc;
   k_colreduce<1><<<NSLAB, 256, 0, st>>>(N, C, Cin, nullptr, dh1, h1_hi, ax, nullptr, 1.f, part, counter + 1, gb1, gW1, nullptr); CKL();
   k_colreduce_final<1><<<(9 * C + 255) / 256, 256, 0, st>>>(C, Cin, NSLAB, part, nullptr, 1.f, gb1, gW1, nullptr); CKL();

@@ -226,6 +226,7 @@ def _gemm_lib():
         L.dge_gemm_tf32x3.argtypes = [ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]
         L.dge_gemm_tf32x3_ex.argtypes = [ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp]
         L.dge_gemm_split_transpose.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.dge_gemm_tf32x3_tn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp]
         L.dge_gru_gates.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp]
         L.dge_gru_gates_bwd.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         L.dge_colsum_ws_floats.restype = ctypes.c_int64
@@ -355,6 +356,24 @@ def _tc_gemm_over_rows(at: tuple, bt: tuple, rows: int):
     return c
 
 
+def tc_gemm_tn(a: tuple, b: tuple):
+    """C [Ca,Cb] = A^T B for A [rows,Ca], B [rows,Cb] given as their plain (hi, lo) splits -- the SAME splits the forward and grad-input
+    products use: the tensor core reads both operands MN-major (dge_gemm_tf32x3_tn), no transposed copy is made.  K = rows is split
+    across the SMs when the output has few tiles; the slices add into the zeroed output."""
+    global launch_count
+    L = _gemm_lib()
+    (a_hi, a_lo), (b_hi, b_lo) = a, b
+    rows, Ca = a_hi.shape
+    Cb = b_hi.shape[1]
+    c = torch.zeros(Ca, Cb, dtype=torch.float32, device=a_hi.device)
+    with torch.cuda.device(a_hi.device):
+        rc = L.dge_gemm_tf32x3_tn(Ca, Cb, rows, _p(a_hi), _p(a_lo), Ca, _p(b_hi), _p(b_lo), Cb, _p(c), Cb, 0, _st(a_hi.device))
+    if rc:
+        raise DgeError(f"dge_gemm_tf32x3_tn failed ({rc})")
+    launch_count += 2
+    return c
+
+
 _colsum_ws: dict = {}
 
 
@@ -380,18 +399,16 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
 
 
 class _TcMatmulFn(torch.autograd.Function):
-    """x [M,K] @ w [K,N] with forward, grad-input AND grad-weight on the tcgen05 3xTF32 kernel (the weight gradient x^T dy contracts
-    over the nodes: both operands go through ``split_transpose``)."""
+    """x [M,K] @ w [K,N] with forward, grad-input AND grad-weight on the tcgen05 3xTF32 kernel.  The weight gradient x^T dy contracts
+    over the nodes; the tensor core reads the (hi, lo) splits of x and dy MN-major (``tc_gemm_tn``), i.e. the splits the forward and the
+    grad-input product make anyway -- nothing is transposed."""
 
     @staticmethod
     def forward(ctx, x, w):
         hi, lo = _weight_operand(w, True)
-        x = x.float()
+        xh, xl = split_tf32(x.float())
         if ctx.needs_input_grad[1]:
-            (xh, xl), xt = split_transpose(x)
-            ctx.xt, ctx.rows = xt, x.shape[0]
-        else:
-            xh, xl = split_tf32(x)
+            ctx.xs = (xh, xl)
         ctx.save_for_backward(w)
         return _tc_gemm_parts(xh, xl, hi, lo)
 
@@ -399,13 +416,10 @@ class _TcMatmulFn(torch.autograd.Function):
     def backward(ctx, gy):
         (w,) = ctx.saved_tensors
         gx = gw = None
-        gy = gy.contiguous().float()
+        gh, gl = split_tf32(gy.contiguous().float())
         if ctx.needs_input_grad[1]:
-            (gh, gl), gt = split_transpose(gy, plain=ctx.needs_input_grad[0])
-            gw = _tc_gemm_over_rows(ctx.xt, gt, ctx.rows)
-            ctx.xt = None
-        else:
-            gh, gl = split_tf32(gy)
+            gw = tc_gemm_tn(ctx.xs, (gh, gl))
+            ctx.xs = None
         if ctx.needs_input_grad[0]:
             hi, lo = _weight_operand(w, False)            # dY [M,N] @ W^T: Bt = W [K,N] as stored
             gx = _tc_gemm_parts(gh, gl, hi, lo)
@@ -428,12 +442,9 @@ class _TcLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
         hi, lo = _weight_operand(w, False)
-        x = x.float()
+        xh, xl = split_tf32(x.float())
         if ctx.needs_input_grad[1]:
-            (xh, xl), xt = split_transpose(x)
-            ctx.xt, ctx.rows = xt, x.shape[0]
-        else:
-            xh, xl = split_tf32(x)
+            ctx.xs = (xh, xl)
         ctx.save_for_backward(w)
         return _tc_gemm_parts(xh, xl, hi, lo)
 
@@ -441,13 +452,10 @@ class _TcLinearFn(torch.autograd.Function):
     def backward(ctx, gy):
         (w,) = ctx.saved_tensors
         gx = gw = None
-        gy = gy.contiguous().float()
+        gh, gl = split_tf32(gy.contiguous().float())
         if ctx.needs_input_grad[1]:
-            (gh, gl), gt = split_transpose(gy, plain=ctx.needs_input_grad[0])
-            gw = _tc_gemm_over_rows(gt, ctx.xt, ctx.rows)          # dW [O,I] = dY^T X
-            ctx.xt = None
-        else:
-            gh, gl = split_tf32(gy)
+            gw = tc_gemm_tn((gh, gl), ctx.xs)                      # dW [O,I] = dY^T X, both operands as stored
+            ctx.xs = None
         if ctx.needs_input_grad[0]:
             hi, lo = _weight_operand(w, True)             # dY [M,O] @ W [O,I]: Bt = W^T [I,O]
             gx = _tc_gemm_parts(gh, gl, hi, lo)

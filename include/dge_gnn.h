@@ -59,6 +59,13 @@ int dge_gemm_tf32x3(int M, const int32_t *M_dev, int N, int K, const float *A_hi
 int dge_gemm_tf32x3_ex(int M, const int32_t *M_dev, int N, int K, const float *A_hi, const float *A_lo, int lda, const float *Bt_hi,
                        const float *Bt_lo, int ldb, float *C, int ldc, int splits, void *stream);
 
+/* transposed-A form for the weight gradient x^T dy of autograd's mm backward (torch: `x.t() @ dy`, cuBLAS SGEMM 'TN'): C[M,N] = A^T B with
+ * A [K,M] and B [K,N] row-major as stored (row pitches lda >= M, ldb >= N, multiples of 4; 0 = M / N), contraction over the K rows (nodes).
+ * Both operands are read MN-major by the tensor core (TMA boxes of 32 columns x 32 rows, major bits of the instruction descriptor), so the
+ * (hi, lo) splits of x and dy that the forward and grad-input products already use serve here too -- no transposed copies.            */
+int dge_gemm_tf32x3_tn(int M, int N, int K, const float *A_hi, const float *A_lo, int lda, const float *B_hi, const float *B_lo, int ldb,
+                       float *C, int ldc, int splits, void *stream);
+
 /* ---- Q-values of the GCN Q-network (Networks.GCN.forward(data, 0): scripts/Networks.py:18-28, called by DeepQ.test, policy.py:255-259) from a raw
  * PyG edge list in one call: both CSRs, the improved-GCN normalisation, fused first layer, tcgen05 GEMM, aggregation + ReLU + head.  src / dst =
  * edge_index rows [E] int64, w = edge_attr [E]; W2t_(hi,lo) = dge_gemm_prep_weight(W2); head_b_dev [1] on the device.  iws / fws: scratch of

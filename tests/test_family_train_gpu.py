@@ -31,7 +31,7 @@ def test_tc_matmul_and_linear_forward_and_both_gradients(M, K, N):
     l0 = gnn.launch_count
     y = gnn.tc_matmul(x, w)
     y.backward(gy)
-    assert gnn.launch_count - l0 >= 7          # split+transpose x2, weight split x2, three products (the K = rows one with its memset)
+    assert gnn.launch_count - l0 >= 7          # split x2, weight split x2, three products (the K = rows one with its memset)
     (x64 @ w64).backward(gy.double())
     assert _rel(y.detach(), (x64 @ w64).detach()) <= TOL
     assert _rel(x.grad, x64.grad) <= TOL and _rel(w.grad, w64.grad) <= TOL
@@ -166,3 +166,22 @@ def test_graph_unet_trains_on_the_tensor_core_products():
         for name in g_tc:
             assert _rel(g_tc[name], g_lib[name].double()) <= 5e-3, (name, _rel(g_tc[name], g_lib[name].double()))
     assert all(torch.isfinite(v).all() for v in g_tc.values())
+
+
+@pytest.mark.parametrize("rows,Ca,Cb", [(777, 1000, 1000), (2600, 3000, 1000), (4099, 64, 100), (31, 128, 36), (16896, 1000, 1000)])
+def test_tn_gemm_reads_both_operands_as_stored(rows, Ca, Cb):
+    """dge_gemm_tf32x3_tn: x^T dy from the plain (hi, lo) splits of x and dy (MN-major operands in the tensor core's descriptors) against
+    fp64, and against the route over transposed copies (same products, same split of K where the shapes agree)."""
+    from drl_graph_exploration_b200 import gnn
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(rows)
+    x = torch.randn(rows, Ca, generator=g).to(dev)
+    dy = torch.randn(rows, Cb, generator=g).to(dev)
+    ref = x.double().t() @ dy.double()
+    c = gnn.tc_gemm_tn(gnn.split_tf32(x), gnn.split_tf32(dy))
+    assert c.shape == (Ca, Cb)
+    assert _rel(c, ref) <= TOL, _rel(c, ref)       # (K is cut into slices of <= 2048: the bound does not grow with the number of rows)
+    (_, _), xt = gnn.split_transpose(x, plain=False)
+    (_, _), dt = gnn.split_transpose(dy, plain=False)
+    c2 = gnn._tc_gemm_over_rows(xt, dt, rows)
+    assert _rel(c, c2.double()) <= TOL
