@@ -213,8 +213,11 @@ extern "C" int dge_host_policy_tick(dge_handle h, const dge_graph_out *g, const 
   // is the one the tick ends on (profiles/r02_hostloop_host_profile_v1.txt: 38 us of join wait), so it goes first: 0.277 vs 0.284 ms per tick
   // (DGE_HOST_TICK_STEP_FIRST=0 for the A/B).  Both orders give the same results, the env sets are disjoint.
   static const int step_first = [] { const char *v = getenv("DGE_HOST_TICK_STEP_FIRST"); return (v && v[0] == '0') ? 0 : 1; }();
-  if ((rc = step_first ? issue_step() : issue_graph())) return rc;
-  if ((rc = step_first ? issue_graph() : issue_step())) return rc;
+  // (an error after the first asynchronous launch: both streams are drained before the call returns, so that no copy into the caller's
+  //  pinned buffers is still in flight when the caller unwinds)
+  auto bail = [&](int code) -> int { cudaStreamSynchronize(st); if (s1 != st) cudaStreamSynchronize(s1); return code; };
+  if ((rc = step_first ? issue_step() : issue_graph())) return bail(rc);
+  if ((rc = step_first ? issue_graph() : issue_step())) return bail(rc);
   for (int b = 0; b < B; ++b) {
     if (hl->phase[b] > 0) hl->phase[b] -= 1;
     else if (!hl->need[b]) hl->cursor[b] += 1;
@@ -223,25 +226,25 @@ extern "C" int dge_host_policy_tick(dge_handle h, const dge_graph_out *g, const 
   // ---- policy pipeline, part 2: the batch crosses to the host and back, Q-values come to the host, the host picks the frontiers
   if (n_need) {
     dge_graph_packed pk;
-    if ((rc = dge_graph_host_packed_end_prefetched(h, hl->arena_pack, hl->arena_host, hl->arena_cap, hl->prefetch_guess, &pk, stream))) return rc;
+    if ((rc = dge_graph_host_packed_end_prefetched(h, hl->arena_pack, hl->arena_host, hl->arena_cap, hl->prefetch_guess, &pk, stream))) return bail(rc);
     hl->d2h_bytes += pk.total_bytes > hl->prefetch_guess ? pk.total_bytes : (hl->prefetch_guess > 128 ? hl->prefetch_guess : pk.total_bytes);   // bytes that crossed the bus
     if (hl->prefetch_guess > 0) hl->prefetch_guess = pk.total_bytes + pk.total_bytes / 4 + 16384;   // (0 = the caller switched the prefetch off)
     const int n = pk.n_nodes;
     if (pk.n_graphs > 0) {
-      if (n > pol->node_cap) return DGE_ECAP;
-      if (cudaMemcpyAsync(hl->arena_dev, hl->arena_host, (size_t)pk.total_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return DGE_ECUDA;
+      if (n > pol->node_cap) return bail(DGE_ECAP);
+      if (cudaMemcpyAsync(hl->arena_dev, hl->arena_host, (size_t)pk.total_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return bail(DGE_ECUDA);
       hl->h2d_bytes += pk.total_bytes;
       const unsigned char *ad = static_cast<const unsigned char *>(hl->arena_dev);
       const int grc = dge_gcn_q_forward(n, pol->Cin, pol->C, reinterpret_cast<const float *>(ad + pk.x), reinterpret_cast<const int32_t *>(ad + pk.csr_rowptr),
                                         reinterpret_cast<const int32_t *>(ad + pk.csr_perm), reinterpret_cast<const int64_t *>(ad + pk.edge_index),
                                         reinterpret_cast<const float *>(ad + pk.gcn_norm), reinterpret_cast<const float *>(ad + pk.gcn_selfnorm), pol->W1, pol->b1,
                                         pol->W2t_hi, pol->W2t_lo, pol->b2, pol->head_w, pol->head_b_dev, pol->ws, pol->q, stream);
-      if (grc) return grc == -1 ? DGE_EINVAL : DGE_ECUDA;
-      if (cudaMemcpyAsync(hl->q_host, pol->q, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) return DGE_ECUDA;
-      if (cudaStreamSynchronize(st) != cudaSuccess) return DGE_ECUDA;
+      if (grc) return bail(grc == -1 ? DGE_EINVAL : DGE_ECUDA);
+      if (cudaMemcpyAsync(hl->q_host, pol->q, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) return bail(DGE_ECUDA);
+      if (cudaStreamSynchronize(st) != cudaSuccess) return bail(DGE_ECUDA);
       hl->launches += 3; hl->d2h_bytes += (int64_t)n * sizeof(float);
       // host arg-max; the chosen frontier's plan is in the batch (frontier_plan): no device round trip (the rare no-frontier case excepted)
-      if ((rc = dge_select_plan_host(h, hl->arena_host, &pk, hl->q_host, hl->need, hl->plan_host, hl->choice_host, stream))) return rc;
+      if ((rc = dge_select_plan_host(h, hl->arena_host, &pk, hl->q_host, hl->need, hl->plan_host, hl->choice_host, stream))) return bail(rc);
       for (int b = 0; b < B; ++b) {
         if (!hl->need[b]) continue;
         if (hl->choice_host[b] < 0) hl->phase[b] = n_forced + 1;        // no frontier left (q15): the episode is over, its reset takes n_forced + 1 ticks

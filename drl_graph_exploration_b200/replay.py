@@ -186,7 +186,11 @@ class GraphReplay:
         if (d["capacity"], d["G"], d["node_cap"], d["edge_cap"]) != (self.capacity, self.G, self.node_cap, self.edge_cap):
             raise ValueError("replay checkpoint was written with other capacities")
         for k in self._TENSORS:
-            getattr(self, k).copy_(d[k])
+            t, src = getattr(self, k), d[k]
+            if k.startswith("t_") and src.shape[0] == self.capacity:      # a checkpoint written before the trash slot existed
+                t[:self.capacity].copy_(src)
+            else:
+                t.copy_(src)
         self.size, self.head, self.allocated = int(d["size"]), int(d["head"]), int(d["allocated"])      # (the setters fill the device cursors)
 
     def nbytes(self) -> int:

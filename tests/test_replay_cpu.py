@@ -166,3 +166,21 @@ def test_append_masked_places_the_selected_rows_like_append():
             assert len(set(zip(aa.tolist(), [round(float(v), 6) for v in rr]))) == 3          # distinct positions
             assert all((x, round(float(y), 6)) in live for x, y in zip(aa.tolist(), rr))     # ... among the live ones
     a.assert_intact()
+
+
+def test_state_dict_round_trip_and_the_older_layout_without_the_trash_slot():
+    """state_dict / load_state_dict carry the rings and the device cursors; a checkpoint whose transition arrays have `capacity` rows
+    (written before append_masked's trash slot existed) still loads."""
+    a = GraphReplay(capacity=6, node_cap=4, edge_cap=4, device="cpu", slack=4)
+    a.gserial[:] = torch.arange(a.G)
+    z = torch.zeros(4, dtype=torch.int64)
+    a.append(z, torch.arange(4), torch.arange(4).float(), z + 1, torch.tensor([False, True, False, True]))
+    sd = a.state_dict()
+    b = GraphReplay(capacity=6, node_cap=4, edge_cap=4, device="cpu", slack=4)
+    b.load_state_dict(sd)
+    assert (b.size, b.head) == (4, 4) and torch.equal(b.t_a, a.t_a) and torch.equal(b.t_term, a.t_term)
+    old = {k: (v[:6] if k.startswith("t_") else v) for k, v in sd.items()}
+    c = GraphReplay(capacity=6, node_cap=4, edge_cap=4, device="cpu", slack=4)
+    c.load_state_dict(old)
+    assert (c.size, c.head) == (4, 4) and torch.equal(c.t_a[:6], a.t_a[:6]) and torch.equal(c.t_serial[:6], a.t_serial[:6])
+    c.sample(3, check=True)
