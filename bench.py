@@ -157,13 +157,14 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     from oracle.cpu_loop import cpu_reference
     run_tick, count = cpu_reference(MAP_SIZE, N_LANDMARKS, ENVS_PER_GPU, threads, MAX_POSES)
-    for _ in range(REF_PREROLL):
+    for _ in range(int(os.environ.get("DGE_BENCH_REF_PREROLL", REF_PREROLL))):
         run_tick()
     t0 = time.perf_counter()
     for _ in range(args.warmup):
         run_tick()
     tick_s = (time.perf_counter() - t0) / args.warmup
-    tps = int(max(1, min(50, math.ceil(10.0 / (args.steps * tick_s)))))   # >= 10 s timed whatever --steps is (a decision round makes single ticks uneven)
+    min_s = float(os.environ.get("DGE_BENCH_REF_SECONDS", "10"))          # (tests shorten the run; the contract's run keeps the default)
+    tps = int(max(1, min(50, math.ceil(min_s / (args.steps * tick_s)))))   # >= 10 s timed whatever --steps is (a decision round makes single ticks uneven)
     c0, t0, sT = count(), time.perf_counter(), 0.0
     for _ in range(args.steps * tps):
         run_tick(); sT += run_tick.mean_poses()
